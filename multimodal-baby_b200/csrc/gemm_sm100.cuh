@@ -1,0 +1,520 @@
+// tcgen05 / TMEM / TMA GEMM engine for the CVCL contrastive path (sm_100a only).
+//
+//   D[m, n] = sum_k A[m, k] * B[n, k]        A: [M, K] bf16 row-major (K-major operand)
+//                                            B: [N, K] bf16 row-major (K-major operand)
+//
+// One CTA = one 128 x BN output tile, fp32 accumulator in TMEM (BN columns), operands staged by
+// TMA into 128B-swizzled shared memory through a STAGES-deep mbarrier ring.
+// Warp roles (192 threads):  warp 0 = TMA producer (one elected lane)
+//                            warp 1 = TMEM allocator + tcgen05.mma issuer (one elected lane)
+//                            warps 2..5 = epilogue; warp w owns TMEM lanes 32*(w%4) .. +31,
+//                                         i.e. thread <-> one accumulator row.
+// The epilogue is a policy class (Epi) with two phases; between them an optional cluster barrier
+// lets the CTAs that share a row block (cluster along N) exchange per-row partial reductions
+// through distributed shared memory (used by the L2-normalise epilogues).
+// blockIdx.z selects one of two independent problems ("directions": image->text and text->image)
+// so that the symmetric InfoNCE needs a single launch.
+#pragma once
+#include "ptx.cuh"
+#include <cuda_bf16.h>
+
+namespace cvcl {
+
+constexpr int kBM = 128;          // UMMA M
+constexpr int kBK = 64;           // one 128-byte swizzle atom of bf16 along K
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 192;
+constexpr int kEpiThreads = 128;
+
+struct GemmShape {
+    int M[2];            // rows of A per direction
+    int N[2];            // rows of B per direction
+    int K;               // contraction length (same for both directions)
+    int m_stride;        // tile origin step along M (kBM unless tiles overlap/segment)
+    int n_stride;        // tile origin step along N
+};
+
+struct EpiCtx {
+    uint32_t tmem_row;   // TMEM address of this thread's row, column 0 of the accumulator
+    int row;             // 0..127 within the tile
+    int m0, n0, z;       // tile origin and direction
+    int tile_m, tile_n;  // tile indices
+    int epi_tid;         // 0..127
+    unsigned char* scratch;
+};
+
+template <int BN, int STAGES>
+struct GemmSmem {
+    static constexpr int kABytes = kBM * kBK * 2;
+    static constexpr int kBBytes = BN * kBK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kBarOff = STAGES * kStageBytes;
+    static constexpr int kScratchOff = kBarOff + 256;
+    template <class Epi>
+    static constexpr int total() { return kScratchOff + Epi::kScratchBytes + 1024 /*align slack*/; }
+};
+
+template <int BN, int STAGES, class Epi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tn_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+                    const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                    const GemmShape gs, const typename Epi::Params ep) {
+    static_assert(BN == 64 || BN == 128 || BN == 256, "BN");
+    using L = GemmSmem<BN, STAGES>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    unsigned char* scratch = smem + L::kScratchOff;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int z = blockIdx.z;
+    const CUtensorMap* tmA = z ? &tmA1 : &tmA0;
+    const CUtensorMap* tmB = z ? &tmB1 : &tmB0;
+    const int m0 = blockIdx.x * gs.m_stride;
+    const int n0 = blockIdx.y * gs.n_stride;
+    const int num_k = (gs.K + kBK - 1) / kBK;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(tmA);
+        ptx::prefetch_tmap(tmB);
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        ptx::mbar_init(tmem_full_bar, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc<(BN < 32 ? 32 : BN)>(tmem_ptr_smem);
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kc = 0; kc < num_k; ++kc) {
+                ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                unsigned char* sa = smem + stage * L::kStageBytes;
+                unsigned char* sb = sa + L::kABytes;
+                ptx::mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+                ptx::tma_load_2d(sa, tmA, &full_bar[stage], kc * kBK, m0);
+                ptx::tma_load_2d(sb, tmB, &full_bar[stage], kc * kBK, n0);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(kBM, BN);
+            int stage = 0; uint32_t phase = 0;
+            for (int kc = 0; kc < num_k; ++kc) {
+                ptx::mbar_wait(&full_bar[stage], phase);
+                ptx::tc_fence_after();
+                const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
+                const uint32_t sb = sa + L::kABytes;
+                const uint64_t adesc = ptx::make_kmajor_sw128_desc(sa);
+                const uint64_t bdesc = ptx::make_kmajor_sw128_desc(sb);
+#pragma unroll
+                for (int k = 0; k < kBK / kUmmaK; ++k) {
+                    // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in 16-byte units
+                    ptx::umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc,
+                                   (kc > 0 || k > 0) ? 1u : 0u);
+                }
+                ptx::umma_commit(&empty_bar[stage]);      // frees the smem slot when MMAs retire
+                if (kc == num_k - 1) ptx::umma_commit(tmem_full_bar);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    }
+
+    EpiCtx cx;
+    cx.epi_tid = threadIdx.x - 64;
+    const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
+    cx.row = quad * 32 + lane;
+    cx.tmem_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    cx.m0 = m0; cx.n0 = n0; cx.z = z; cx.tile_m = blockIdx.x; cx.tile_n = blockIdx.y;
+    cx.scratch = scratch;
+
+    if (warp >= 2) {
+        ptx::mbar_wait(tmem_full_bar, 0);
+        ptx::tc_fence_after();
+        Epi::template phase1<BN>(cx, gs, ep);
+    }
+    if constexpr (Epi::kClusterReduce) {
+        ptx::tc_fence_before();
+        ptx::cluster_sync_all();
+        ptx::tc_fence_after();
+        if (warp >= 2) Epi::template phase2<BN>(cx, gs, ep);
+        ptx::tc_fence_before();
+        ptx::cluster_sync_all();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_base);
+}
+
+// =====================================================================================
+// Epilogue policies
+// =====================================================================================
+
+// ---- plain store: C = alpha * acc, fp32, row-major (dW, materialised logits) ----------
+struct EpiStoreF32 {
+    static constexpr bool kClusterReduce = false;
+    static constexpr int kScratchBytes = 16;
+    struct Params { float* C[2]; int ldc[2]; float alpha; };
+    template <int BN>
+    static __device__ __forceinline__ void phase1(const EpiCtx& cx, const GemmShape& gs, const Params& p) {
+        const int m = cx.m0 + cx.row;
+        const int M = gs.M[cx.z], N = gs.N[cx.z];
+        float* crow = p.C[cx.z] + static_cast<size_t>(m) * p.ldc[cx.z];
+        const bool vec_ok = (p.ldc[cx.z] & 3) == 0;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            float v[32];
+            ptx::tmem_ld_32x32(cx.tmem_row + c, v);     // warp-collective: no early exit above
+            if (m >= M) continue;
+            const int n = cx.n0 + c;
+            if (vec_ok && n + 32 <= N) {
+                float4* dst = reinterpret_cast<float4*>(crow + n);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    dst[j] = make_float4(v[4 * j] * p.alpha, v[4 * j + 1] * p.alpha,
+                                         v[4 * j + 2] * p.alpha, v[4 * j + 3] * p.alpha);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (n + j < N) crow[n + j] = v[j] * p.alpha;
+            }
+        }
+    }
+    template <int BN>
+    static __device__ __forceinline__ void phase2(const EpiCtx&, const GemmShape&, const Params&) {}
+};
+
+// ---- projection head: + bias, L2-normalise the full row (cluster along N), store ------
+// reference: multimodal.py:186-192 (fc) / 181-185 (1x1 conv) + F.normalize at :736
+struct EpiHeadNorm {
+    static constexpr bool kClusterReduce = true;
+    static constexpr int kScratchBytes = kBM * 4;
+    struct Params {
+        const float* bias;          // [N] or null
+        int normalize;
+        float* out_f32;  int ld_f32;        // [M, ld] normalised features (nullable)
+        __nv_bfloat16* out_bf16; int ld_bf16;   // [M, ld] (nullable)
+        __nv_bfloat16* out_bf16_t; int ld_t;    // [N, ld_t] transposed copy (nullable)
+        float* inv_norm;            // [M]  1 / max(||u||, 1e-12)
+    };
+    template <int BN>
+    static __device__ __forceinline__ void phase1(const EpiCtx& cx, const GemmShape& gs, const Params& p) {
+        const int N = gs.N[cx.z];
+        float ssq = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            float v[32];
+            ptx::tmem_ld_32x32(cx.tmem_row + c, v);
+            const int n = cx.n0 + c;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (n + j < N) {
+                    const float u = v[j] + (p.bias ? __ldg(p.bias + n + j) : 0.f);
+                    ssq = fmaf(u, u, ssq);
+                }
+            }
+        }
+        reinterpret_cast<float*>(cx.scratch)[cx.row] = ssq;
+    }
+    template <int BN>
+    static __device__ __forceinline__ void phase2(const EpiCtx& cx, const GemmShape& gs, const Params& p) {
+        const int M = gs.M[cx.z], N = gs.N[cx.z];
+        const int m = cx.m0 + cx.row;
+        const float* my = reinterpret_cast<const float*>(cx.scratch) + cx.row;
+        float tot = 0.f;
+        const uint32_t nc = ptx::cluster_nctarank();
+        for (uint32_t r = 0; r < nc; ++r) tot += ptx::ld_dsmem_f32(my, r);
+        const float denom = p.normalize ? fmaxf(sqrtf(tot), 1e-12f) : 1.f;
+        const float inv = 1.f / denom;
+        if (m < M && cx.tile_n == 0 && p.inv_norm) p.inv_norm[m] = inv;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            float v[32];
+            ptx::tmem_ld_32x32(cx.tmem_row + c, v);
+            if (m >= M) continue;
+            const int n = cx.n0 + c;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                v[j] = (n + j < N) ? (v[j] + (p.bias ? __ldg(p.bias + n + j) : 0.f)) / denom : 0.f;
+            if (p.out_f32) {
+                float* dst = p.out_f32 + static_cast<size_t>(m) * p.ld_f32 + n;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (n + j < N) dst[j] = v[j];
+            }
+            if (p.out_bf16) {
+                __nv_bfloat16* dst = p.out_bf16 + static_cast<size_t>(m) * p.ld_bf16 + n;
+                if (n + 32 <= N && (p.ld_bf16 & 7) == 0) {
+                    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        __nv_bfloat162 a = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
+                        __nv_bfloat162 b = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+                        __nv_bfloat162 c2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+                        __nv_bfloat162 d = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+                        uint4 q;
+                        q.x = *reinterpret_cast<uint32_t*>(&a); q.y = *reinterpret_cast<uint32_t*>(&b);
+                        q.z = *reinterpret_cast<uint32_t*>(&c2); q.w = *reinterpret_cast<uint32_t*>(&d);
+                        d4[j] = q;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (n + j < N) dst[j] = __float2bfloat16_rn(v[j]);
+                }
+            }
+            if (p.out_bf16_t) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (n + j < N)
+                        p.out_bf16_t[static_cast<size_t>(n + j) * p.ld_t + m] = __float2bfloat16_rn(v[j]);
+            }
+        }
+    }
+};
+
+// ---- similarity tile -> online-softmax row statistics (never stores the logits) -------
+// reference: multimodal.py:755,783-787 (match, logit_scale) and 808-818 (CE, argmax, entropy)
+struct RowStat { float m, l, a; int arg; };          // max, sum exp(x-m), sum exp(x-m)*x, argmax
+struct EpiSimStats {
+    static constexpr bool kClusterReduce = false;
+    static constexpr int kScratchBytes = 16;
+    struct Params {
+        float scale;                // exp(s)
+        int diag_off[2];            // positive of row r is column r + diag_off[z]
+        RowStat* part[2];           // [n_tiles][m_pad]
+        int m_pad[2];
+        float* diag[2];             // [M]  logit at the positive
+    };
+    template <int BN>
+    static __device__ __forceinline__ void phase1(const EpiCtx& cx, const GemmShape& gs, const Params& p) {
+        const int M = gs.M[cx.z], N = gs.N[cx.z];
+        const int m = cx.m0 + cx.row;
+        const int dcol = m + p.diag_off[cx.z];
+        constexpr float kLog2e = 1.4426950408889634f;
+        float mx = -INFINITY, l = 0.f, a = 0.f;
+        int arg = cx.n0;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            float v[32];
+            ptx::tmem_ld_32x32(cx.tmem_row + c, v);     // warp-collective
+            const int n = cx.n0 + c;
+            if (n >= N) continue;                       // warp-uniform
+            float nm = mx;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const bool ok = (n + j < N);
+                v[j] *= p.scale;
+                if (ok && v[j] > nm) { nm = v[j]; arg = n + j; }   // strict > keeps the first max
+                if (n + j == dcol && ok && m < M) p.diag[cx.z][m] = v[j];
+            }
+            const float corr = exp2f((mx - nm) * kLog2e);          // mx = -inf -> 0
+            l *= corr; a *= corr;
+            const float nm2 = nm * kLog2e;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (n + j < N) {
+                    const float e = exp2f(fmaf(v[j], kLog2e, -nm2));
+                    l += e;
+                    a = fmaf(e, v[j], a);
+                }
+            }
+            mx = nm;
+        }
+        if (m < M) {
+            RowStat rs; rs.m = mx; rs.l = l; rs.a = a; rs.arg = arg;
+            p.part[cx.z][static_cast<size_t>(cx.tile_n) * p.m_pad[cx.z] + m] = rs;
+        }
+    }
+    template <int BN>
+    static __device__ __forceinline__ void phase2(const EpiCtx&, const GemmShape&, const Params&) {}
+};
+
+
+// ---- backward, step 1: recompute the logits tile and emit dL/dlogits (bf16) --------------
+// G = (softmax_row + softmax_col - 2*I) / (2B)  (the autograd of
+// multimodal.py:808-810).  Stored pre-multiplied by exp(s)*coef so that dI = Gs*T, dT = Gs^T*I.
+// Direction z=1 runs with the operands swapped and therefore emits Gs^T directly.
+struct EpiGradG {
+    static constexpr bool kClusterReduce = false;
+    static constexpr int kScratchBytes = 256 * 4;
+    struct Params {
+        float scale;                 // exp(s)
+        float coef;                  // upstream / (2 * B_global)
+        int diag_off[2];
+        const float* lse_q[2];       // [M]  log-sum-exp of this direction's rows
+        const float* lse_k[2];       // [N]  log-sum-exp of the other direction (columns here)
+        __nv_bfloat16* G[2]; int ldg[2];
+        float* dscale_accum;         // d loss / d s  (atomicAdd, direction 0 only; nullable)
+    };
+    template <int BN>
+    static __device__ __forceinline__ void phase1(const EpiCtx& cx, const GemmShape& gs, const Params& p) {
+        const int M = gs.M[cx.z], N = gs.N[cx.z];
+        const int m = cx.m0 + cx.row;
+        constexpr float kLog2e = 1.4426950408889634f;
+        float* lk = reinterpret_cast<float*>(cx.scratch);
+        for (int j = cx.epi_tid; j < BN; j += kEpiThreads)
+            lk[j] = (cx.n0 + j < N) ? __ldg(p.lse_k[cx.z] + cx.n0 + j) * kLog2e : 0.f;
+        ptx::named_bar_sync(1, kEpiThreads);
+        const float lq = (m < M) ? __ldg(p.lse_q[cx.z] + m) * kLog2e : 0.f;
+        const int dcol = m + p.diag_off[cx.z];
+        const float sc2 = p.scale * kLog2e;
+        const float w = p.scale * p.coef;
+        float ds = 0.f;
+        __nv_bfloat16* grow = p.G[cx.z] + static_cast<size_t>(m) * p.ldg[cx.z];
+        const bool vec_ok = (p.ldg[cx.z] & 7) == 0;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            float v[32];
+            ptx::tmem_ld_32x32(cx.tmem_row + c, v);
+            const int n = cx.n0 + c;
+            if (m >= M || n >= N) continue;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float x2 = v[j] * sc2;                       // logit * log2(e)
+                float g = exp2f(x2 - lq) + exp2f(x2 - lk[c + j]);
+                if (n + j == dcol) g -= 2.f;
+                g *= w;                                            // exp(s) * G * upstream
+                if (n + j < N) ds = fmaf(g, v[j], ds);             // G * logit = Gs * raw dot
+                v[j] = g;
+            }
+            if (vec_ok && n + 32 <= N) {
+                uint4* d4 = reinterpret_cast<uint4*>(grow + n);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    __nv_bfloat162 a = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
+                    __nv_bfloat162 b = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+                    __nv_bfloat162 c2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+                    __nv_bfloat162 d = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+                    uint4 q;
+                    q.x = *reinterpret_cast<uint32_t*>(&a); q.y = *reinterpret_cast<uint32_t*>(&b);
+                    q.z = *reinterpret_cast<uint32_t*>(&c2); q.w = *reinterpret_cast<uint32_t*>(&d);
+                    d4[j] = q;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (n + j < N) grow[n + j] = __float2bfloat16_rn(v[j]);
+            }
+        }
+        if (cx.z == 0 && p.dscale_accum) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ds += __shfl_xor_sync(0xffffffffu, ds, o);
+            if ((cx.row & 31) == 0) atomicAdd(p.dscale_accum, ds);
+        }
+    }
+    template <int BN>
+    static __device__ __forceinline__ void phase2(const EpiCtx&, const GemmShape&, const Params&) {}
+};
+
+// ---- backward, step 2: dFeat = Gs * Other, then the F.normalize backward on the full row ---
+//   du = (dFeat - feat * <feat, dFeat>) * inv_norm       (cluster along N supplies the dot)
+// Outputs (all optional): fp32 [M, N] scaled per row by 1/len (text side: d mean-embedding),
+// bf16 transposed [N, ld_t] (image side: operand of the dW GEMM), d bias (column sums).
+struct EpiNormBwd {
+    static constexpr bool kClusterReduce = true;
+    static constexpr int kScratchBytes = kBM * 4;
+    struct Params {
+        const __nv_bfloat16* feat; int ld_feat;     // normalised features used in the forward
+        const float* inv_norm;                      // [M]
+        int normalize;
+        const long long* row_len;                   // [M] int64 lengths (nullable): out *= 1/len
+        float* out_f32; int ld_f32;
+        __nv_bfloat16* out_bf16_t; int ld_t;
+        float* dbias;                               // [N] atomicAdd (nullable)
+    };
+    template <int BN>
+    static __device__ __forceinline__ void phase1(const EpiCtx& cx, const GemmShape& gs, const Params& p) {
+        const int M = gs.M[cx.z], N = gs.N[cx.z];
+        const int m = cx.m0 + cx.row;
+        float dot = 0.f;
+        if (p.normalize) {
+            const __nv_bfloat16* frow = p.feat + static_cast<size_t>(m < M ? m : 0) * p.ld_feat;
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                float v[32];
+                ptx::tmem_ld_32x32(cx.tmem_row + c, v);
+                const int n = cx.n0 + c;
+                if (m >= M) continue;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (n + j < N) dot = fmaf(__bfloat162float(frow[n + j]), v[j], dot);
+            }
+        }
+        reinterpret_cast<float*>(cx.scratch)[cx.row] = dot;
+    }
+    template <int BN>
+    static __device__ __forceinline__ void phase2(const EpiCtx& cx, const GemmShape& gs, const Params& p) {
+        const int M = gs.M[cx.z], N = gs.N[cx.z];
+        const int m = cx.m0 + cx.row;
+        const bool rv = m < M;
+        const float* my = reinterpret_cast<const float*>(cx.scratch) + cx.row;
+        float dot = 0.f;
+        const uint32_t nc = ptx::cluster_nctarank();
+        for (uint32_t r = 0; r < nc; ++r) dot += ptx::ld_dsmem_f32(my, r);
+        const float inv = (p.normalize && rv) ? __ldg(p.inv_norm + m) : 1.f;
+        const float rs = (p.row_len && rv) ? 1.f / static_cast<float>(p.row_len[m]) : 1.f;
+        const __nv_bfloat16* frow = p.feat + static_cast<size_t>(rv ? m : 0) * p.ld_feat;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            float v[32];
+            ptx::tmem_ld_32x32(cx.tmem_row + c, v);
+            const int n = cx.n0 + c;
+            if (n >= N) continue;                                    // warp-uniform
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float du = 0.f;
+                if (rv && n + j < N) {
+                    du = v[j];
+                    if (p.normalize) du = (du - __bfloat162float(frow[n + j]) * dot) * inv;
+                }
+                v[j] = du;
+            }
+            if (p.out_f32 && rv) {
+                float* dst = p.out_f32 + static_cast<size_t>(m) * p.ld_f32 + n;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (n + j < N) dst[j] = v[j] * rs;
+            }
+            if (p.out_bf16_t && rv) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (n + j < N)
+                        p.out_bf16_t[static_cast<size_t>(n + j) * p.ld_t + m] = __float2bfloat16_rn(v[j]);
+            }
+            if (p.dbias) {
+                // column sums over the 32 rows of this warp: butterfly transpose-reduce,
+                // 31 shuffles for 32 columns; lane j ends up owning column j.
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const bool upper = (cx.row & o) != 0;
+#pragma unroll
+                    for (int j = 0; j < o; ++j) {
+                        const float send = upper ? v[j] : v[j + o];
+                        const float keep = upper ? v[j + o] : v[j];
+                        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                    }
+                }
+                // after the butterfly lane L holds the sum of column bitrev-free index L (see note)
+                const int col = n + (cx.row & 31);
+                if (col < N) atomicAdd(p.dbias + col, v[0]);
+            }
+        }
+    }
+};
+
+}  // namespace cvcl

@@ -1,0 +1,90 @@
+// Host-side helpers shared by the C-ABI entry points: error reporting, TMA tensor-map
+// construction (driver entry point fetched at run time, so the library links only cudart),
+// launch helpers.
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace cvcl {
+
+// thread-local message returned by cvcl_last_error()
+inline char* last_error_buf() {
+    static thread_local char buf[512] = {0};
+    return buf;
+}
+inline int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(last_error_buf(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+enum : int {
+    CVCL_OK = 0,
+    CVCL_ERR_INVALID = -1,      // bad shape / null pointer / misalignment
+    CVCL_ERR_UNSUPPORTED = -2,  // valid request the kernels do not cover (never a fallback)
+    CVCL_ERR_CUDA = -3,         // CUDA runtime / driver error
+};
+
+#define CVCL_CHECK_CUDA(expr)                                                              \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess)                                                             \
+            return ::cvcl::fail(::cvcl::CVCL_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,     \
+                                cudaGetErrorString(_e), __FILE__, __LINE__);               \
+    } while (0)
+
+#define CVCL_REQUIRE(cond, ...)                                                            \
+    do {                                                                                   \
+        if (!(cond)) return ::cvcl::fail(::cvcl::CVCL_ERR_INVALID, __VA_ARGS__);           \
+    } while (0)
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+                cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+// bf16 row-major matrix [rows, cols] with leading dimension ld (elements); box = box_rows x 64
+// columns (one 128-byte swizzle atom).  Out-of-bounds box elements read as zero.
+inline int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols,
+                          uint64_t ld, uint32_t box_rows) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return fail(CVCL_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15))
+        return fail(CVCL_ERR_INVALID, "TMA operand must be 16-byte aligned with 16-byte row pitch "
+                                      "(ptr=%p ld=%llu)", ptr, (unsigned long long)ld);
+    if (rows == 0 || cols == 0) return fail(CVCL_ERR_INVALID, "empty TMA operand");
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {ld * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(CVCL_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d) rows=%llu cols=%llu "
+                                   "ld=%llu box_rows=%u", (int)r, (unsigned long long)rows,
+                    (unsigned long long)cols, (unsigned long long)ld, box_rows);
+    return CVCL_OK;
+}
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace cvcl

@@ -1,0 +1,411 @@
+// HBM-/L2-bound SIMT kernels of the CVCL contrastive path (sm_100a):
+//   K1  length-masked embedding-bag mean + L2-norm (flat), per-token gather + norm (spatial)
+//   K4b merge of the per-tile online-softmax partials -> loss / accuracy / entropy / LSE
+//   K5e embedding-table gradient scatter
+//   K7  n-way cosine evaluation (fp32 end to end, first-index argmax)
+//   casts / transposes feeding the tensor-core GEMMs
+// Coalescing rule used throughout: one warp owns one row of E contiguous floats and moves it as
+// 16-byte vectors (lane-contiguous float4), so every request is a full 512-byte line group.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "gemm_sm100.cuh"   // RowStat
+
+namespace cvcl {
+
+constexpr int kMaxVec = 8;            // E <= 32 lanes * 4 floats * kMaxVec = 1024
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void store_bf16x4(__nv_bfloat16* dst, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 q; q.x = *reinterpret_cast<uint32_t*>(&a); q.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(dst) = q;
+}
+
+// --------------------------------------------------------------------------------------
+// K1: text encoder, embedding branch.  reference: multimodal.py:496-503 (+ :743 normalise)
+//   flat      : feat[b] = normalise( sum_l table[ids[b,l]] / len[b] )
+//   per_token : tok[b,l] = normalise(table[ids[b,l]])           (spatial text features, :498)
+//               pooled[b] = sum_l tok[b,l] * pool_scale / len[b] (spatial "mean" similarity, :765-770)
+// All L positions are visited in order; id 0 (<pad>) is skipped because nn.Embedding(padding_idx=0)
+// keeps that row at exactly zero, so the sum is unchanged.  ids outside [0,V) set *status.
+// --------------------------------------------------------------------------------------
+struct TextFwdParams {
+    const long long* ids;      // [B, L] int64
+    const long long* lens;     // [B]    int64
+    const float* table;        // [V, E] fp32
+    int B, L, E, V;
+    int normalize;
+    int per_token;             // 0: flat, 1: spatial
+    float pool_scale;          // per_token: 1/(H*W)
+    float* feat_f32;           // [B, E]          (nullable)
+    __nv_bfloat16* feat_bf16;  int ld_bf16;     // [B, ld]  (nullable)
+    __nv_bfloat16* feat_bf16_t; int ld_t;       // [E, ld_t] transposed (nullable)
+    float* inv_norm;           // flat: [B]; per_token: [B*L]   (nullable)
+    float* tok_f32;            // per_token: [B*L, E]  (nullable)
+    __nv_bfloat16* tok_bf16;   // per_token: [B*L, E]  (nullable)
+    int* status;               // set to 1 on an out-of-range id (nullable)
+};
+
+__global__ void __launch_bounds__(256) text_encoder_fwd_kernel(const TextFwdParams p) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= p.B) return;
+    const int b = warp;
+    const int nvec = p.E >> 7;                 // float4 chunks per lane (E % 128 == 0 fast path)
+    const int rem = p.E & 127;                 // tail handled by chunk nvec with a lane mask
+    const int nch = nvec + (rem ? 1 : 0);
+    float4 acc[kMaxVec];
+#pragma unroll
+    for (int c = 0; c < kMaxVec; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const long long* idrow = p.ids + static_cast<size_t>(b) * p.L;
+    for (int l = 0; l < p.L; ++l) {
+        const long long id = __ldg(idrow + l);
+        const size_t tok = static_cast<size_t>(b) * p.L + l;
+        if (id < 0 || id >= p.V) { if (lane == 0 && p.status) atomicExch(p.status, 1); continue; }
+        float4 r[kMaxVec];
+        if (id != 0) {
+            const float4* src = reinterpret_cast<const float4*>(p.table + static_cast<size_t>(id) * p.E);
+#pragma unroll
+            for (int c = 0; c < kMaxVec; ++c) {
+                r[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c < nch && (c * 32 + lane) * 4 < p.E) r[c] = __ldg(src + c * 32 + lane);
+            }
+        } else {
+            if (!p.per_token) continue;
+#pragma unroll
+            for (int c = 0; c < kMaxVec; ++c) r[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (!p.per_token) {
+#pragma unroll
+            for (int c = 0; c < kMaxVec; ++c) {
+                acc[c].x += r[c].x; acc[c].y += r[c].y; acc[c].z += r[c].z; acc[c].w += r[c].w;
+            }
+        } else {
+            float ssq = 0.f;
+#pragma unroll
+            for (int c = 0; c < kMaxVec; ++c)
+                ssq += r[c].x * r[c].x + r[c].y * r[c].y + r[c].z * r[c].z + r[c].w * r[c].w;
+            ssq = warp_sum(ssq);
+            const float denom = p.normalize ? fmaxf(sqrtf(ssq), 1e-12f) : 1.f;
+            if (lane == 0 && p.inv_norm) p.inv_norm[tok] = 1.f / denom;
+#pragma unroll
+            for (int c = 0; c < kMaxVec; ++c) {
+                if (c < nch && (c * 32 + lane) * 4 < p.E) {
+                    float4 t = make_float4(r[c].x / denom, r[c].y / denom, r[c].z / denom, r[c].w / denom);
+                    const size_t off = tok * p.E + (c * 32 + lane) * 4;
+                    if (p.tok_f32) *reinterpret_cast<float4*>(p.tok_f32 + off) = t;
+                    if (p.tok_bf16) store_bf16x4(p.tok_bf16 + off, t);
+                    acc[c].x += t.x; acc[c].y += t.y; acc[c].z += t.z; acc[c].w += t.w;
+                }
+            }
+        }
+    }
+    const float flen = static_cast<float>(__ldg(p.lens + b));
+    float ssq = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxVec; ++c) {
+        if (!p.per_token) {
+            acc[c].x /= flen; acc[c].y /= flen; acc[c].z /= flen; acc[c].w /= flen;
+        } else {
+            const float sc = p.pool_scale;
+            acc[c].x = acc[c].x * sc / flen; acc[c].y = acc[c].y * sc / flen;
+            acc[c].z = acc[c].z * sc / flen; acc[c].w = acc[c].w * sc / flen;
+        }
+        ssq += acc[c].x * acc[c].x + acc[c].y * acc[c].y + acc[c].z * acc[c].z + acc[c].w * acc[c].w;
+    }
+    float denom = 1.f;
+    if (!p.per_token) {
+        ssq = warp_sum(ssq);
+        denom = p.normalize ? fmaxf(sqrtf(ssq), 1e-12f) : 1.f;
+        if (lane == 0 && p.inv_norm) p.inv_norm[b] = 1.f / denom;
+    }
+#pragma unroll
+    for (int c = 0; c < kMaxVec; ++c) {
+        const int e = (c * 32 + lane) * 4;
+        if (c < nch && e < p.E) {
+            float4 t = make_float4(acc[c].x / denom, acc[c].y / denom, acc[c].z / denom, acc[c].w / denom);
+            if (p.feat_f32) *reinterpret_cast<float4*>(p.feat_f32 + static_cast<size_t>(b) * p.E + e) = t;
+            if (p.feat_bf16) store_bf16x4(p.feat_bf16 + static_cast<size_t>(b) * p.ld_bf16 + e, t);
+            if (p.feat_bf16_t) {
+                p.feat_bf16_t[static_cast<size_t>(e) * p.ld_t + b] = __float2bfloat16_rn(t.x);
+                p.feat_bf16_t[static_cast<size_t>(e + 1) * p.ld_t + b] = __float2bfloat16_rn(t.y);
+                p.feat_bf16_t[static_cast<size_t>(e + 2) * p.ld_t + b] = __float2bfloat16_rn(t.z);
+                p.feat_bf16_t[static_cast<size_t>(e + 3) * p.ld_t + b] = __float2bfloat16_rn(t.w);
+            }
+        }
+    }
+}
+
+// plain row gather table[ids] -> [B*L, E] fp32: the `text_outputs` tensor the reference API
+// returns (multimodal.py:496,575,584).  One warp per token row.
+__global__ void __launch_bounds__(256) embedding_gather_kernel(const long long* ids, const float* table,
+                                                               float* out, int n_tok, int E, int V) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n_tok) return;
+    long long id = __ldg(ids + warp);
+    if (id < 0 || id >= V) id = 0;
+    const float4* src = reinterpret_cast<const float4*>(table + static_cast<size_t>(id) * E);
+    float4* dst = reinterpret_cast<float4*>(out + static_cast<size_t>(warp) * E);
+    for (int c = lane; c < (E >> 2); c += 32) dst[c] = __ldg(src + c);
+}
+
+// --------------------------------------------------------------------------------------
+// K5e: d table[v] += g[b] for every position l with ids[b,l] = v != 0   (flat)
+//      per_token: g is [B*L, E] (one gradient row per token)
+// g already contains the normalise-backward and the 1/len factor.  Row 0 never receives a
+// gradient (nn.Embedding padding_idx=0, multimodal.py:311-312).  fp32 vector atomics.
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) embedding_scatter_add_kernel(const long long* ids, const float* g,
+                                                                    float* dtable, int B, int L, int E,
+                                                                    int V, int per_token) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_rows = per_token ? B * L : B;
+    if (warp >= n_rows) return;
+    const int nch = (E + 127) >> 7;
+    float4 r[kMaxVec];
+    const float4* src = reinterpret_cast<const float4*>(g + static_cast<size_t>(warp) * E);
+#pragma unroll
+    for (int c = 0; c < kMaxVec; ++c) {
+        r[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < nch && (c * 32 + lane) * 4 < E) r[c] = __ldg(src + c * 32 + lane);
+    }
+    const int l0 = per_token ? 0 : 0, l1 = per_token ? 1 : L;
+    for (int l = l0; l < l1; ++l) {
+        const long long id = per_token ? __ldg(ids + warp) : __ldg(ids + static_cast<size_t>(warp) * L + l);
+        if (id <= 0 || id >= V) continue;
+        float4* dst = reinterpret_cast<float4*>(dtable + static_cast<size_t>(id) * E);
+#pragma unroll
+        for (int c = 0; c < kMaxVec; ++c)
+            if (c < nch && (c * 32 + lane) * 4 < E) atomicAdd(dst + c * 32 + lane, r[c]);
+    }
+}
+
+// spatial text backward: per token recompute tok = normalise(table[id]) and apply
+//   g_tok = dtok[b,l] (+ dpool[b] * pool_scale / len[b])      (either input nullable)
+//   d e   = (g_tok - tok <tok, g_tok>) * inv_norm             (F.normalize backward)
+// then scatter-add into d table.  One warp per token.
+__global__ void __launch_bounds__(256) text_token_bwd_kernel(const long long* ids, const long long* lens,
+                                                             const float* table, const float* dtok,
+                                                             const float* dpool, float pool_scale,
+                                                             float* dtable, int B, int L, int E, int V,
+                                                             int normalize) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= B * L) return;
+    const long long id = __ldg(ids + warp);
+    if (id <= 0 || id >= V) return;
+    const int b = warp / L;
+    const int nch = (E + 127) >> 7;
+    const float4* src = reinterpret_cast<const float4*>(table + static_cast<size_t>(id) * E);
+    const float ps = dpool ? pool_scale / static_cast<float>(__ldg(lens + b)) : 0.f;
+    float4 e[kMaxVec], g[kMaxVec];
+    float ssq = 0.f, dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxVec; ++c) {
+        e[c] = make_float4(0.f, 0.f, 0.f, 0.f); g[c] = e[c];
+        if (c < nch && (c * 32 + lane) * 4 < E) {
+            e[c] = __ldg(src + c * 32 + lane);
+            if (dtok) g[c] = __ldg(reinterpret_cast<const float4*>(dtok + static_cast<size_t>(warp) * E) + c * 32 + lane);
+            if (dpool) {
+                float4 q = __ldg(reinterpret_cast<const float4*>(dpool + static_cast<size_t>(b) * E) + c * 32 + lane);
+                g[c].x = fmaf(q.x, ps, g[c].x); g[c].y = fmaf(q.y, ps, g[c].y);
+                g[c].z = fmaf(q.z, ps, g[c].z); g[c].w = fmaf(q.w, ps, g[c].w);
+            }
+        }
+        ssq += e[c].x * e[c].x + e[c].y * e[c].y + e[c].z * e[c].z + e[c].w * e[c].w;
+        dot += e[c].x * g[c].x + e[c].y * g[c].y + e[c].z * g[c].z + e[c].w * g[c].w;
+    }
+    ssq = warp_sum(ssq); dot = warp_sum(dot);
+    float inv = 1.f, k = 0.f;
+    if (normalize) {
+        const float denom = fmaxf(sqrtf(ssq), 1e-12f);
+        inv = 1.f / denom;
+        k = dot * inv * inv * inv;         // <tok,g> * tok * inv = e * dot / denom^3
+        if (sqrtf(ssq) < 1e-12f) k = 0.f;  // clamp active: y = x / eps, dy/dx = 1/eps
+    }
+    float4* dst = reinterpret_cast<float4*>(dtable + static_cast<size_t>(id) * E);
+#pragma unroll
+    for (int c = 0; c < kMaxVec; ++c) {
+        if (c < nch && (c * 32 + lane) * 4 < E) {
+            float4 o = make_float4(g[c].x * inv - e[c].x * k, g[c].y * inv - e[c].y * k,
+                                   g[c].z * inv - e[c].z * k, g[c].w * inv - e[c].w * k);
+            atomicAdd(dst + c * 32 + lane, o);
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------
+// K4b: merge per-tile online-softmax partials; emits per-row LSE and the five scalars of
+// multimodal.py:808-818.  Deterministic: each block writes its partial sums, the last block to
+// finish (atomic ticket) adds them in block order.
+// out[0..4] = loss, image_accuracy, text_accuracy, image_entropy, text_entropy
+// (scaled by inv_rows = 1/B_global so that shards can be summed across ranks).
+// --------------------------------------------------------------------------------------
+struct FinalizeParams {
+    const RowStat* part[2]; int m_pad[2]; int n_tiles[2]; int M[2];
+    const float* diag[2];
+    int diag_off[2];
+    float* lse[2];               // [M]
+    int* argmax[2];              // [M] (nullable)
+    float inv_rows;              // 1 / B_global
+    float* block_part;           // [gridDim.x * 6]
+    unsigned int* ticket;        // zero-initialised, reset by the kernel
+    float* out;                  // [8]
+};
+
+__global__ void __launch_bounds__(256) infonce_finalize_kernel(const FinalizeParams p) {
+    __shared__ float red[6][8];
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    float ce[2] = {0.f, 0.f}, ent[2] = {0.f, 0.f}, acc[2] = {0.f, 0.f};
+    const int total = p.M[0] + p.M[1];
+    if (tid < total) {
+        const int z = tid < p.M[0] ? 0 : 1;
+        const int m = z ? tid - p.M[0] : tid;
+        float mx = -INFINITY; int arg = 0x7fffffff;
+        for (int t = 0; t < p.n_tiles[z]; ++t) {
+            const RowStat rs = p.part[z][static_cast<size_t>(t) * p.m_pad[z] + m];
+            if (rs.m > mx) { mx = rs.m; arg = rs.arg; }        // strict >: first tile wins ties
+        }
+        float l = 0.f, a = 0.f;
+        for (int t = 0; t < p.n_tiles[z]; ++t) {
+            const RowStat rs = p.part[z][static_cast<size_t>(t) * p.m_pad[z] + m];
+            const float w = __expf(rs.m - mx);
+            l = fmaf(rs.l, w, l); a = fmaf(rs.a, w, a);
+        }
+        const float lse = mx + logf(l);
+        p.lse[z][m] = lse;
+        if (p.argmax[z]) p.argmax[z][m] = arg;
+        ce[z] = lse - p.diag[z][m];
+        ent[z] = lse - a / l;
+        acc[z] = (arg == m + p.diag_off[z]) ? 1.f : 0.f;
+    }
+    float v[6] = {ce[0], ce[1], ent[0], ent[1], acc[0], acc[1]};
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { v[i] = warp_sum(v[i]); if (lane == 0) red[i][w] = v[i]; }
+    __syncthreads();
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 6; ++i) {
+            float s = 0.f;
+            for (int k = 0; k < (blockDim.x >> 5); ++k) s += red[i][k];
+            p.block_part[blockIdx.x * 6 + i] = s;
+        }
+        __threadfence();
+        const unsigned int t = atomicAdd(p.ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        __threadfence();
+        float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (unsigned int b = 0; b < gridDim.x; ++b)
+            for (int i = 0; i < 6; ++i) s[i] += p.block_part[b * 6 + i];
+        p.out[0] = (s[0] + s[1]) * 0.5f * p.inv_rows;
+        p.out[1] = s[4] * p.inv_rows;
+        p.out[2] = s[5] * p.inv_rows;
+        p.out[3] = s[2] * p.inv_rows;
+        p.out[4] = s[3] * p.inv_rows;
+        *p.ticket = 0u;
+    }
+}
+
+// --------------------------------------------------------------------------------------
+// K7: Labeled-S style n-way evaluation, fp32 end to end.
+// reference: multimodal_lit.py:466-511 / eval.py:196-214: per trial the 4 frame embeddings and the
+// label embedding are L2-normalised, dotted, scaled; pred = argmax (first maximal index).
+// One warp per trial; E <= 1024.
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) eval_nway_kernel(const float* img, const float* txt,
+                                                        const int* txt_index, int n_trials, int n_way,
+                                                        int E, int normalize, float scale, int* pred,
+                                                        float* logits) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n_trials) return;
+    const int nch = (E + 127) >> 7;
+    const int ti = txt_index ? __ldg(txt_index + warp) : warp;
+    const float4* tsrc = reinterpret_cast<const float4*>(txt + static_cast<size_t>(ti) * E);
+    float4 t[kMaxVec];
+    float tss = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxVec; ++c) {
+        t[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < nch && (c * 32 + lane) * 4 < E) t[c] = __ldg(tsrc + c * 32 + lane);
+        tss += t[c].x * t[c].x + t[c].y * t[c].y + t[c].z * t[c].z + t[c].w * t[c].w;
+    }
+    if (normalize) {
+        const float d = fmaxf(sqrtf(warp_sum(tss)), 1e-12f);
+#pragma unroll
+        for (int c = 0; c < kMaxVec; ++c) { t[c].x /= d; t[c].y /= d; t[c].z /= d; t[c].w /= d; }
+    }
+    float best = -INFINITY; int arg = 0;
+    for (int w = 0; w < n_way; ++w) {
+        const float4* isrc = reinterpret_cast<const float4*>(img + (static_cast<size_t>(warp) * n_way + w) * E);
+        float4 x[kMaxVec];
+        float ss = 0.f;
+#pragma unroll
+        for (int c = 0; c < kMaxVec; ++c) {
+            x[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < nch && (c * 32 + lane) * 4 < E) x[c] = __ldg(isrc + c * 32 + lane);
+            ss += x[c].x * x[c].x + x[c].y * x[c].y + x[c].z * x[c].z + x[c].w * x[c].w;
+        }
+        float d = 1.f;
+        if (normalize) d = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < kMaxVec; ++c) {
+            dot = fmaf(x[c].x / d, t[c].x, dot); dot = fmaf(x[c].y / d, t[c].y, dot);
+            dot = fmaf(x[c].z / d, t[c].z, dot); dot = fmaf(x[c].w / d, t[c].w, dot);
+        }
+        dot = warp_sum(dot) * scale;
+        if (logits && lane == 0) logits[static_cast<size_t>(warp) * n_way + w] = dot;
+        if (dot > best) { best = dot; arg = w; }
+    }
+    if (lane == 0) pred[warp] = arg;
+}
+
+// --------------------------------------------------------------------------------------
+// casts / transposes:  src [batch][R][C] (fp32 or bf16)  ->  dst [batch][R][C] bf16 (nullable)
+//                                                         and dst_t [batch][C][R] bf16 (nullable)
+// 32x32 tiles through shared memory so both outputs are written coalesced.  With batch = B,
+// R = 2048, C = 49 this is the NCHW -> NHWC conversion of the layer4 map for the spatial head.
+// --------------------------------------------------------------------------------------
+template <typename TIn>
+__global__ void __launch_bounds__(256) cast_transpose_kernel(const TIn* src, __nv_bfloat16* dst,
+                                                             __nv_bfloat16* dst_t, int R, int C,
+                                                             long long ld_src, long long ld_dst,
+                                                             long long ld_t, long long bs_src,
+                                                             long long bs_dst, long long bs_t) {
+    __shared__ float tile[32][33];
+    const int bz = blockIdx.z;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+    for (int i = ty; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + tx;
+        float v = 0.f;
+        if (r < R && c < C) {
+            if constexpr (sizeof(TIn) == 4) v = src[bz * bs_src + r * ld_src + c];
+            else v = __bfloat162float(src[bz * bs_src + r * ld_src + c]);
+            if (dst) dst[bz * bs_dst + r * ld_dst + c] = __float2bfloat16_rn(v);
+        }
+        tile[i][tx] = v;
+    }
+    if (!dst_t) return;
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + tx;
+        if (r < R && c < C) dst_t[bz * bs_t + c * ld_t + r] = __float2bfloat16_rn(tile[tx][i]);
+    }
+}
+
+}  // namespace cvcl

@@ -1,0 +1,162 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on
+seeded synthetic inputs.  TEST INFRASTRUCTURE; runs only in the build container.
+
+    python oracle/make_golden.py            # rewrites tests/golden/
+
+Inputs and weights are drawn from numpy RandomState(seed) (bit-stable across versions) by
+oracle.cvcl_oracle.synth_*, copied into the reference modules' own parameters, and the
+reference's MultiModalModel.forward / calculate_contrastive_loss (+ loss.backward()) are
+run as they are.  Only seeds, shapes and OUTPUTS are stored; tests regenerate the inputs.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import cvcl_oracle as O          # noqa: E402
+from oracle import ref_import as R           # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def case_inputs(seed, B, E, embedding_type, L=25, K=2048, V=2350, Bt=None):
+    """The single source of truth for golden-case inputs (tests call this too)."""
+    rng = np.random.RandomState(seed)
+    W, b, table = O.synth_weights(rng, E, K, V)
+    shape = (B, K) if embedding_type == "flat" else (B, K, 7, 7)
+    f = O.synth_trunk_features(rng, shape)
+    ids, lens = O.synth_tokens(rng, B if Bt is None else Bt, L, V)
+    return dict(W=W, b=b, table=table, f=f, ids=ids, lens=lens)
+
+
+def load_into_reference(model, inp, embedding_type):
+    with torch.no_grad():
+        if embedding_type == "flat":
+            model.image_embed.model.fc.weight.copy_(torch.from_numpy(inp["W"]))
+            model.image_embed.model.fc.bias.copy_(torch.from_numpy(inp["b"]))
+        else:
+            conv = model.image_embed.model[-1]
+            conv.weight.copy_(torch.from_numpy(inp["W"])[:, :, None, None])
+            conv.bias.copy_(torch.from_numpy(inp["b"]))
+        model.text_embed.embedding.weight.copy_(torch.from_numpy(inp["table"]))
+
+
+def run_train_case(name, seed, B, E, embedding_type, sim="mean", store_full_grads=True):
+    inp = case_inputs(seed, B, E, embedding_type)
+    m = R.build_reference_model(embedding_type, sim=sim, embedding_dim=E,
+                                fix_temperature=False)
+    load_into_reference(m, inp, embedding_type)
+    m.train()
+    f = torch.from_numpy(inp["f"]); ids = torch.from_numpy(inp["ids"])
+    lens = torch.from_numpy(inp["lens"])
+    out = m.calculate_contrastive_loss(f, ids, lens)
+    loss = out[0]
+    loss.backward()
+    head = m.image_embed.model.fc if embedding_type == "flat" else m.image_embed.model[-1]
+    dW = head.weight.grad.reshape(E, -1).numpy()
+    dtab = m.text_embed.embedding.weight.grad.numpy()
+    rec = dict(
+        seed=seed, B=B, E=E, embedding_type=embedding_type, sim=sim,
+        loss=loss.item(), image_accuracy=out[1].item(), text_accuracy=out[2].item(),
+        image_entropy=out[3].item(), text_entropy=out[4].item(),
+        logits_per_image=out[5].detach().numpy(), logits_per_text=out[6].detach().numpy(),
+        image_pred=torch.argmax(out[5], -1).numpy(), text_pred=torch.argmax(out[6], -1).numpy(),
+        db=head.bias.grad.numpy(), ds=m.logit_neg_log_temperature.grad.item(),
+        dW_norm=np.linalg.norm(dW.astype(np.float64)),
+        dtable_norm=np.linalg.norm(dtab.astype(np.float64)),
+        dW_slice=dW[:8, :64].copy(), dtable_rows=dtab[:8].copy(),
+    )
+    if embedding_type == "flat":
+        rec["image_features"] = out[7].detach().numpy()
+        tf, _ = m.encode_text(ids, lens)
+        rec["text_features"] = tf.detach().numpy()
+    else:
+        rec["image_features_head"] = out[7].detach().numpy()[:2]       # [2,E,7,7]
+    if store_full_grads:
+        rec["dW"] = dW
+        nz = np.unique(inp["ids"])
+        rec["dtable_nz_ids"] = nz
+        rec["dtable_nz"] = dtab[nz]
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **rec)
+    print(name, "loss", rec["loss"], "ds", rec["ds"])
+
+
+def run_forward_case(name, seed, Ni, Nt, E):
+    """README usage (4 images x 3 texts): Ni != Nt through MultiModalModel.forward."""
+    inp = case_inputs(seed, Ni, E, "flat", Bt=Nt)
+    m = R.build_reference_model("flat", embedding_dim=E, fix_temperature=True)
+    load_into_reference(m, inp, "flat")
+    m.eval()
+    with torch.no_grad():
+        lpi, lpt = m(torch.from_numpy(inp["f"]), torch.from_numpy(inp["ids"]),
+                     torch.from_numpy(inp["lens"]))
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), seed=seed, Ni=Ni, Nt=Nt, E=E,
+                        logits_per_image=lpi.numpy(), logits_per_text=lpt.numpy())
+    print(name, lpi.shape, lpt.shape)
+
+
+def run_eval_case(name, seed, n_trials, E, n_way=4):
+    """Labeled-S trials through the reference's literal loop (eval.py:196-214):
+    per trial model(img[4], label[1,L], len[1]) -> argmax(logits_per_text[0])."""
+    rng = np.random.RandomState(seed)
+    W, b, table = O.synth_weights(rng, E)
+    f = O.synth_trunk_features(rng, (n_trials, n_way, 2048))
+    vocab = R.reference_vocab()
+    cats = ["ball", "car", "kitty", "chair", "door", "hand", "sand", "window"]
+    word_ids = np.array([vocab[c] for c in cats], np.int64)
+    which = rng.randint(0, len(cats), size=n_trials)
+    ids = np.zeros((n_trials, 3), np.int64)
+    ids[:, 0] = O.SOS_TOKEN_ID; ids[:, 1] = word_ids[which]; ids[:, 2] = O.EOS_TOKEN_ID
+    lens = np.full(n_trials, 3, np.int64)
+    m = R.build_reference_model("flat", embedding_dim=E, fix_temperature=True)
+    load_into_reference(m, dict(W=W, b=b, table=table), "flat")
+    m.eval()
+    preds, logits = [], []
+    with torch.no_grad():
+        for t in range(n_trials):
+            _, lpt = m(torch.from_numpy(f[t]), torch.from_numpy(ids[t:t + 1]),
+                       torch.from_numpy(lens[t:t + 1]))
+            preds.append(int(torch.argmax(lpt[0])))
+            logits.append(lpt[0].numpy())
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), seed=seed, n_trials=n_trials, E=E,
+                        n_way=n_way, ids=ids, lens=lens, pred=np.array(preds, np.int32),
+                        logits=np.stack(logits))
+    print(name, "acc", np.mean(np.array(preds) == 0))
+
+
+def run_tokenize_case(name):
+    """MultiModalLitModel.tokenize (multimodal_lit.py:161-190) on pre-tokenised text
+    (whitespace split; spaCy itself is not available offline)."""
+    m = R.build_reference_model("flat", embedding_dim=64, fix_temperature=True, lit=True)
+    texts = ["ball", "look at the kitty", "where is the zzzunknownzzz ball ?",
+             " ".join(["car"] * 40), "a"]
+    ids, lens = m.tokenize(texts)
+    with open(os.path.join(GOLD, name + ".json"), "w") as fh:
+        json.dump(dict(texts=texts, ids=ids.tolist(), lens=lens.tolist()), fh)
+    print(name, lens.tolist())
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    torch.manual_seed(0)
+    run_train_case("flat_e64_b8", 101, 8, 64, "flat")
+    run_train_case("flat_e512_b32", 102, 32, 512, "flat", store_full_grads=False)
+    run_train_case("flat_e512_b160", 103, 160, 512, "flat", store_full_grads=False)
+    run_train_case("spatial_mean_e64_b6", 104, 6, 64, "spatial", "mean")
+    run_train_case("spatial_max_e64_b6", 105, 6, 64, "spatial", "max")
+    run_train_case("spatial_max_e512_b12", 106, 12, 512, "spatial", "max",
+                   store_full_grads=False)
+    run_train_case("spatial_mean_e512_b12", 107, 12, 512, "spatial", "mean",
+                   store_full_grads=False)
+    run_forward_case("forward_4x3_e512", 108, 4, 3, 512)
+    run_forward_case("forward_4x1_e512", 109, 4, 1, 512)
+    run_eval_case("eval_4way_e512", 110, 64, 512)
+    run_tokenize_case("tokenize")
+
+
+if __name__ == "__main__":
+    main()
