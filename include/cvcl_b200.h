@@ -1,0 +1,170 @@
+/* cvcl_b200.h -- C ABI of libcvcl_b200.so: the B200 (sm_100a) implementation of the CVCL
+ * contrastive image-utterance hot path of wkvong/multimodal-baby.
+ *
+ * The reference has no FFI for this path: its boundary is the Python class API of
+ * multimodal/multimodal.py (MultiModalModel) whose arithmetic is dispatched to ATen.  Each
+ * entry point below replaces the ATen op sequence of the cited reference lines; the Python
+ * host (multimodal-baby_b200/) binds them with ctypes and registers them as torch.library ops.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated; the caller (torch) owns all memory,
+ *     the library never allocates, frees or synchronises; work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*), and is CUDA-graph capturable;
+ *   - matrices are row-major; `ld*` are leading dimensions in ELEMENTS; bf16 operands that feed
+ *     the tensor-core GEMMs must be 16-byte aligned with ld % 8 == 0 (TMA requirement);
+ *   - token ids / lengths are int64 exactly as the reference's collate produces them
+ *     (multimodal_data_module.py:98-109);
+ *   - return 0 on success, <0 on error (CVCL_ERR_*); cvcl_last_error() gives the thread-local
+ *     message.  Unsupported requests are errors, never fallbacks.  There is no CPU path.
+ */
+#ifndef CVCL_B200_H
+#define CVCL_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CVCL_ABI_VERSION 1
+#define CVCL_OK 0
+#define CVCL_ERR_INVALID (-1)
+#define CVCL_ERR_UNSUPPORTED (-2)
+#define CVCL_ERR_CUDA (-3)
+
+int cvcl_abi_version(void);
+const char* cvcl_last_error(void);
+
+/* ---- K1 text encoder, embedding branch ------------------------------------------------
+ * replaces TextEncoder.forward (multimodal.py:496-503,575-584) + F.normalize (:743).
+ * per_token = 0 (flat): feat[b] = normalise(sum_l table[ids[b,l]] / len[b]).
+ * per_token = 1 (spatial): tok[b,l] = normalise(table[ids[b,l]]) (:498) and
+ *   feat[b] = sum_l tok[b,l] * pool_scale / len[b] (the text factor of the "mean"
+ *   similarity, :765-770).  Any output pointer may be NULL.  *status is set to 1 if an id is
+ *   outside [0,V) (the reference raises IndexError). */
+int cvcl_text_encoder_fwd(const int64_t* ids, const int64_t* lens, const float* table,
+                          int B, int L, int E, int V, int normalize, int per_token, float pool_scale,
+                          float* feat_f32, void* feat_bf16, int ld_bf16, void* feat_bf16_t, int ld_t,
+                          float* inv_norm, float* tok_f32, void* tok_bf16, int* status, void* stream);
+
+/* text_outputs = embedding(ids) (multimodal.py:496,575-584): [n_tok, E] fp32 row gather. */
+int cvcl_embedding_gather(const int64_t* ids, const float* table, float* out, int n_tok, int E, int V,
+                          void* stream);
+
+/* autograd of nn.Embedding(padding_idx=0): dtable[ids[b,l]] += g[b] (flat, g [B,E]) or
+ * += g[b*L+l] (per_token, g [B*L,E]); row 0 untouched.  dtable must be pre-zeroed. */
+int cvcl_embedding_scatter_add(const int64_t* ids, const float* g, float* dtable, int B, int L, int E,
+                               int V, int per_token, void* stream);
+
+/* spatial text backward: F.normalize backward per token + scatter-add (dtok [B*L,E] and/or
+ * dpool [B,E], either may be NULL). */
+int cvcl_text_token_bwd(const int64_t* ids, const int64_t* lens, const float* table, const float* dtok,
+                        const float* dpool, float pool_scale, float* dtable, int B, int L, int E, int V,
+                        int normalize, void* stream);
+
+/* ---- casts / transposes feeding the GEMMs ------------------------------------------------
+ * src [batch][R][C] (fp32, or bf16 if src_is_bf16) -> dst [batch][R][C] bf16 and/or
+ * dst_t [batch][C][R] bf16.  bs_* are batch strides in elements. */
+int cvcl_cast_transpose(const void* src, int src_is_bf16, void* dst, void* dst_t, int batch, int R, int C,
+                        int64_t ld_src, int64_t ld_dst, int64_t ld_t, int64_t bs_src, int64_t bs_dst,
+                        int64_t bs_t, void* stream);
+
+/* stand-alone backward of the flat text encoder (encode_text differentiated on its own):
+ * dm = F.normalize-backward(g [B,E]; feat, inv_norm) / len, then the embedding scatter-add. */
+int cvcl_embedding_bag_bwd(const int64_t* ids, const int64_t* lens, const float* g, const float* feat,
+                           const float* inv_norm, int normalize, float* dtable, int B, int L, int E, int V,
+                           void* stream);
+
+/* stand-alone F.normalize backward on rows (autograd of multimodal.py:736,743):
+ * du = (g - feat <feat,g>) * inv_norm -> fp32 [M,E] / bf16 [M,ld] / bf16^T [E,ld_t] / dbias += sum. */
+int cvcl_rownorm_bwd(const float* g, const float* feat, const float* inv_norm, int M, int E, int normalize,
+                     float* du_f32, void* du_bf16, int ld, void* du_bf16_t, int ld_t, float* dbias,
+                     void* stream);
+
+/* sum over the H*W locations of a [B,HW,E] fp32 map: image factor of the spatial "mean"
+ * similarity (multimodal.py:765-770). */
+int cvcl_spatial_pool(const float* src, int B, int HW, int E, float* out_f32, void* out_bf16, int ld,
+                      void* out_bf16_t, int ld_t, void* stream);
+
+/* generic C [M,N] fp32 = alpha * A [M,K] . B [N,K]^T on the tcgen05 engine (bf16 operands). */
+int cvcl_gemm_nt_f32out(const void* A, int lda, const void* B, int ldb, int M, int N, int K, float alpha,
+                        float* C, int ldc, void* stream);
+
+/* ---- K2 projection head + L2 normalise -----------------------------------------------------
+ * replaces model.fc / the 1x1 conv (multimodal.py:181-192, applied at :101) + F.normalize (:736).
+ * x [M,K] bf16 (M = B, or B*49 NHWC rows), w [E,K] bf16, bias [E] fp32.  tcgen05 GEMM, bias +
+ * full-row norm in the epilogue (cluster of ceil(E/128) CTAs shares the row sum of squares). */
+int cvcl_head_proj_norm_fwd(const void* x, int ldx, const void* w, int ldw, const float* bias,
+                            int M, int E, int K, int normalize,
+                            float* out_f32, int ld_f32, void* out_bf16, int ld_bf16,
+                            void* out_bf16_t, int ld_t, float* inv_norm, void* stream);
+
+/* ---- K3+K4 similarity GEMM fused with the symmetric InfoNCE statistics ----------------------
+ * replaces multimodal.py:755 (match), :783-787 (logit_scale) and :801-818 (cross-entropy both
+ * ways, argmax accuracy, entropy) without materialising the logits.
+ * Direction 0 (image->text): rows img_q [M0,E] against txt_k [N0,E]; direction 1 (text->image):
+ * rows txt_q [M1,E] against img_k [N1,E].  On one GPU img_q == img_k and txt_q == txt_k; on a
+ * shard the *_q are the local pairs and the *_k the all-gathered features, and diag_off is the
+ * column offset of the local block.  log_scale = s = -log(temperature).
+ * out5 = {loss, image_accuracy, text_accuracy, image_entropy, text_entropy}, each a partial
+ * sum scaled by inv_rows = 1/B_global (sum over ranks gives the global value). */
+size_t cvcl_sim_workspace_bytes(int M0, int N0, int M1, int N1);
+int cvcl_sim_infonce_fwd(const void* img_q, const void* txt_k, const void* txt_q, const void* img_k,
+                         int ld, int M0, int N0, int M1, int N1, int E, float log_scale,
+                         int diag_off, float inv_rows, void* workspace,
+                         float* lse0, float* lse1, int* argmax0, int* argmax1, float* out5,
+                         void* stream);
+
+/* materialised logits for the forward() API (multimodal.py:783-794):
+ * lpi [Ni,Nt] = exp(s) * img . txt^T ; lpt [Nt,Ni] (either may be NULL). */
+int cvcl_sim_logits_fwd(const void* img, const void* txt, int ld, int Ni, int Nt, int E, float log_scale,
+                        float* lpi, float* lpt, void* stream);
+
+/* ---- K5 backward --------------------------------------------------------------------------
+ * (a) dL/dlogits tiles from recomputed logits: Gs0 [M0, N0] (rows = local images) and
+ *     Gs1 [M1, N1] (rows = local texts), bf16, pre-multiplied by exp(s) * coef where
+ *     coef = upstream / (2 B_global); G = (softmax_row + softmax_col - 2 I)/(2B).
+ *     lse_k0 [N0] = column LSEs seen by direction 0 (= all-gathered lse1), lse_k1 [N1] likewise.
+ *     *dscale += sum G * logits (the logit_scale gradient, multimodal.py:711-715,783-787). */
+int cvcl_sim_infonce_bwd_g(const void* img_q, const void* txt_k, const void* txt_q, const void* img_k,
+                           int ld, int M0, int N0, int M1, int N1, int E, float log_scale, int diag_off,
+                           float coef, const float* lse_q0, const float* lse_k0, const float* lse_q1,
+                           const float* lse_k1, void* Gs0, int ldg0, void* Gs1, int ldg1, float* dscale,
+                           void* stream);
+/* (b) dFeat = Gs [M,Kc] . other_t[E,Kc]^T followed by the F.normalize backward in the epilogue.
+ *     Outputs: out_f32 [M,E] (scaled by 1/row_len if given: d mean-embedding), out_bf16_t [E,M]
+ *     (operand of the weight-gradient GEMM), dbias [E] += column sums. */
+int cvcl_feat_grad_norm_bwd(const void* Gs, int ldg, const void* other_t, int ld_other, int M, int E,
+                            int Kc, const void* feat_bf16, int ld_feat, const float* inv_norm,
+                            int normalize, const int64_t* row_len, float* out_f32, int ld_f32,
+                            void* out_bf16_t, int ld_t, float* dbias, void* stream);
+/* (c) dW [E,K] = du_t [E,M] . x_t [K,M]^T  (autograd of nn.Linear / 1x1 conv weight). */
+int cvcl_head_weight_grad(const void* du_t, int ld_du, const void* x_t, int ld_x, int E, int K, int M,
+                          float* dW, int ld_dw, void* stream);
+
+/* ---- fused flat train step: K1 .. K5 sequenced in one call ----------------------------------
+ * replaces MultiModalModel.calculate_contrastive_loss (multimodal.py:796-822) + loss.backward()
+ * for embedding_type = "flat".  x [B,K] trunk-boundary features (fp32 or bf16), w/bias/table the
+ * fp32 master parameters.  Outputs: out5 (see above), dW [E,K], dbias [E], dtable [V,E], dscale [1]
+ * (all fp32, overwritten), optional img/txt features fp32 [B,E].  Gradients are d(loss)/d(param)
+ * for upstream = 1.  Workspace from cvcl_flat_step_workspace_bytes. */
+size_t cvcl_flat_step_workspace_bytes(int B, int L, int E, int K, int V);
+int cvcl_flat_contrastive_step(const void* x, int x_is_bf16, const int64_t* ids, const int64_t* lens,
+                               const float* w, const float* bias, const float* table,
+                               int B, int L, int E, int K, int V, int normalize, float log_scale,
+                               int need_grads, void* workspace,
+                               float* out5, float* img_feat_f32, float* txt_feat_f32,
+                               float* dW, float* dbias, float* dtable, float* dscale,
+                               int* status, void* stream);
+
+/* ---- K7 n-way evaluation (fp32, bit-exact argmax contract) -----------------------------------
+ * replaces the per-trial loop of eval.py:196-214 / multimodal_lit.py:466-511.
+ * img [n_trials*n_way, E] fp32 embeddings (target first), txt [C,E] fp32 label embeddings,
+ * txt_index [n_trials] (NULL = identity).  pred [n_trials] int32; logits [n_trials,n_way] optional. */
+int cvcl_eval_nway_fwd(const float* img, const float* txt, const int* txt_index, int n_trials, int n_way,
+                       int E, int normalize, float log_scale, int* pred, float* logits, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVCL_B200_H */

@@ -1,0 +1,406 @@
+// libcvcl_b200.so -- C-ABI entry points (see include/cvcl_b200.h for the contract and the
+// reference file:line each one replaces).  Links only cudart; no libtorch, no CPU path.
+#include "../../include/cvcl_b200.h"
+#include "gemm_launch.cuh"
+#include "kernels_simt.cuh"
+#include <cmath>
+
+using namespace cvcl;
+
+namespace {
+
+constexpr int kBN = 128;
+constexpr int kStages = 4;
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline int warps_grid(long long n_warps, int block = 256) {
+    return static_cast<int>((n_warps * 32 + block - 1) / block);
+}
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline int pad8(int x) { return (x + 7) / 8 * 8; }
+
+struct SimWs {               // carve-up of the sim workspace
+    RowStat* part[2]; int m_pad[2]; int n_tiles[2];
+    float* diag[2]; float* block_part; unsigned int* ticket; size_t bytes;
+};
+SimWs carve_sim_ws(void* ws, int M0, int N0, int M1, int N1) {
+    SimWs w{};
+    const int M[2] = {M0, M1}, N[2] = {N0, N1};
+    size_t off = 0;
+    unsigned char* base = static_cast<unsigned char*>(ws);
+    w.ticket = reinterpret_cast<unsigned int*>(base + off); off += 256;
+    for (int z = 0; z < 2; ++z) {
+        w.m_pad[z] = ceil_div(M[z], kBM) * kBM;
+        w.n_tiles[z] = ceil_div(N[z], kBN);
+        w.part[z] = reinterpret_cast<RowStat*>(base + off);
+        off += align_up(sizeof(RowStat) * static_cast<size_t>(w.m_pad[z]) * w.n_tiles[z], 256);
+        w.diag[z] = reinterpret_cast<float*>(base + off);
+        off += align_up(sizeof(float) * static_cast<size_t>(w.m_pad[z]), 256);
+    }
+    const int fin_blocks = ceil_div(M0 + M1, 256);
+    w.block_part = reinterpret_cast<float*>(base + off);
+    off += align_up(sizeof(float) * 6 * static_cast<size_t>(fin_blocks), 256);
+    w.bytes = off;
+    return w;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cvcl_abi_version(void) { return CVCL_ABI_VERSION; }
+const char* cvcl_last_error(void) { return last_error_buf(); }
+
+// ------------------------------------------------------------------------------------ K1
+int cvcl_text_encoder_fwd(const int64_t* ids, const int64_t* lens, const float* table,
+                          int B, int L, int E, int V, int normalize, int per_token, float pool_scale,
+                          float* feat_f32, void* feat_bf16, int ld_bf16, void* feat_bf16_t, int ld_t,
+                          float* inv_norm, float* tok_f32, void* tok_bf16, int* status, void* stream) {
+    CVCL_REQUIRE(ids && lens && table, "text_encoder_fwd: null input");
+    CVCL_REQUIRE(B >= 0 && L > 0 && V > 0, "text_encoder_fwd: bad shape B=%d L=%d V=%d", B, L, V);
+    CVCL_REQUIRE(E > 0 && E % 4 == 0 && E <= 128 * kMaxVec, "text_encoder_fwd: E=%d must be a multiple of 4, <= %d", E, 128 * kMaxVec);
+    CVCL_REQUIRE((reinterpret_cast<uintptr_t>(table) & 15) == 0, "text_encoder_fwd: table not 16-byte aligned");
+    if (B == 0) return CVCL_OK;
+    TextFwdParams p{};
+    p.ids = reinterpret_cast<const long long*>(ids); p.lens = reinterpret_cast<const long long*>(lens);
+    p.table = table; p.B = B; p.L = L; p.E = E; p.V = V; p.normalize = normalize; p.per_token = per_token;
+    p.pool_scale = pool_scale; p.feat_f32 = feat_f32;
+    p.feat_bf16 = static_cast<__nv_bfloat16*>(feat_bf16); p.ld_bf16 = ld_bf16;
+    p.feat_bf16_t = static_cast<__nv_bfloat16*>(feat_bf16_t); p.ld_t = ld_t;
+    p.inv_norm = inv_norm; p.tok_f32 = tok_f32; p.tok_bf16 = static_cast<__nv_bfloat16*>(tok_bf16);
+    p.status = status;
+    text_encoder_fwd_kernel<<<warps_grid(B), 256, 0, as_stream(stream)>>>(p);
+    CVCL_CHECK_CUDA(cudaGetLastError());
+    return CVCL_OK;
+}
+
+int cvcl_embedding_gather(const int64_t* ids, const float* table, float* out, int n_tok, int E, int V,
+                          void* stream) {
+    CVCL_REQUIRE(ids && table && out, "embedding_gather: null pointer");
+    CVCL_REQUIRE(E > 0 && E % 4 == 0, "embedding_gather: E=%d must be a multiple of 4", E);
+    if (n_tok == 0) return CVCL_OK;
+    embedding_gather_kernel<<<warps_grid(n_tok), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const long long*>(ids), table, out, n_tok, E, V);
+    CVCL_CHECK_CUDA(cudaGetLastError());
+    return CVCL_OK;
+}
+
+int cvcl_embedding_scatter_add(const int64_t* ids, const float* g, float* dtable, int B, int L, int E,
+                               int V, int per_token, void* stream) {
+    CVCL_REQUIRE(ids && g && dtable, "embedding_scatter_add: null pointer");
+    CVCL_REQUIRE(E > 0 && E % 4 == 0 && E <= 128 * kMaxVec, "embedding_scatter_add: bad E=%d", E);
+    if (B == 0) return CVCL_OK;
+    const long long rows = per_token ? static_cast<long long>(B) * L : B;
+    embedding_scatter_add_kernel<<<warps_grid(rows), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const long long*>(ids), g, dtable, B, L, E, V, per_token);
+    CVCL_CHECK_CUDA(cudaGetLastError());
+    return CVCL_OK;
+}
+
+int cvcl_text_token_bwd(const int64_t* ids, const int64_t* lens, const float* table, const float* dtok,
+                        const float* dpool, float pool_scale, float* dtable, int B, int L, int E, int V,
+                        int normalize, void* stream) {
+    CVCL_REQUIRE(ids && lens && table && dtable && (dtok || dpool), "text_token_bwd: null pointer");
+    CVCL_REQUIRE(E > 0 && E % 4 == 0 && E <= 128 * kMaxVec, "text_token_bwd: bad E=%d", E);
+    if (B == 0) return CVCL_OK;
+    text_token_bwd_kernel<<<warps_grid(static_cast<long long>(B) * L), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const long long*>(ids), reinterpret_cast<const long long*>(lens), table, dtok,
+        dpool, pool_scale, dtable, B, L, E, V, normalize);
+    CVCL_CHECK_CUDA(cudaGetLastError());
+    return CVCL_OK;
+}
+
+int cvcl_cast_transpose(const void* src, int src_is_bf16, void* dst, void* dst_t, int batch, int R, int C,
+                        int64_t ld_src, int64_t ld_dst, int64_t ld_t, int64_t bs_src, int64_t bs_dst,
+                        int64_t bs_t, void* stream) {
+    CVCL_REQUIRE(src && (dst || dst_t), "cast_transpose: null pointer");
+    if (batch == 0 || R == 0 || C == 0) return CVCL_OK;
+    CVCL_REQUIRE(batch <= 65535 && ceil_div(R, 32) <= 65535, "cast_transpose: grid too large");
+    dim3 grid(ceil_div(C, 32), ceil_div(R, 32), batch);
+    if (src_is_bf16)
+        cast_transpose_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(
+            static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst),
+            static_cast<__nv_bfloat16*>(dst_t), R, C, ld_src, ld_dst, ld_t, bs_src, bs_dst, bs_t);
+    else
+        cast_transpose_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(
+            static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst),
+            static_cast<__nv_bfloat16*>(dst_t), R, C, ld_src, ld_dst, ld_t, bs_src, bs_dst, bs_t);
+    CVCL_CHECK_CUDA(cudaGetLastError());
+    return CVCL_OK;
+}
+
+int cvcl_embedding_bag_bwd(const int64_t* ids, const int64_t* lens, const float* g, const float* feat,
+                           const float* inv_norm, int normalize, float* dtable, int B, int L, int E, int V,
+                           void* stream) {
+    CVCL_REQUIRE(ids && lens && g && dtable, "embedding_bag_bwd: null pointer");
+    CVCL_REQUIRE(!normalize || (feat && inv_norm), "embedding_bag_bwd: normalize needs feat and inv_norm");
+    CVCL_REQUIRE(E > 0 && E % 4 == 0 && E <= 128 * kMaxVec, "embedding_bag_bwd: bad E=%d", E);
+    if (B == 0) return CVCL_OK;
+    embedding_bag_bwd_kernel<<<warps_grid(B), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const long long*>(ids), reinterpret_cast<const long long*>(lens), g, feat, inv_norm,
+        normalize, dtable, B, L, E, V);
+    CVCL_CHECK_CUDA(cudaGetLastError());
+    return CVCL_OK;
+}
+
+int cvcl_rownorm_bwd(const float* g, const float* feat, const float* inv_norm, int M, int E, int normalize,
+                     float* du_f32, void* du_bf16, int ld, void* du_bf16_t, int ld_t, float* dbias,
+                     void* stream) {
+    CVCL_REQUIRE(g, "rownorm_bwd: null pointer");
+    CVCL_REQUIRE(!normalize || (feat && inv_norm), "rownorm_bwd: normalize needs feat and inv_norm");
+    CVCL_REQUIRE(E > 0 && E % 4 == 0 && E <= 128 * kMaxVec, "rownorm_bwd: bad E=%d", E);
+    if (M == 0) return CVCL_OK;
+    rownorm_bwd_kernel<<<warps_grid(M), 256, 0, as_stream(stream)>>>(
+        g, feat, inv_norm, M, E, normalize, du_f32, static_cast<__nv_bfloat16*>(du_bf16), ld,
+        static_cast<__nv_bfloat16*>(du_bf16_t), ld_t, dbias);
+    CVCL_CHECK_CUDA(cudaGetLastError());
+    return CVCL_OK;
+}
+
+int cvcl_spatial_pool(const float* src, int B, int HW, int E, float* out_f32, void* out_bf16, int ld,
+                      void* out_bf16_t, int ld_t, void* stream) {
+    CVCL_REQUIRE(src && (out_f32 || out_bf16 || out_bf16_t), "spatial_pool: null pointer");
+    CVCL_REQUIRE(E > 0 && E % 4 == 0 && HW > 0, "spatial_pool: bad shape");
+    if (B == 0) return CVCL_OK;
+    dim3 grid(ceil_div(E / 4, 128), B);
+    spatial_pool_kernel<<<grid, 128, 0, as_stream(stream)>>>(src, B, HW, E, out_f32,
+        static_cast<__nv_bfloat16*>(out_bf16), ld, static_cast<__nv_bfloat16*>(out_bf16_t), ld_t);
+    CVCL_CHECK_CUDA(cudaGetLastError());
+    return CVCL_OK;
+}
+
+int cvcl_gemm_nt_f32out(const void* A, int lda, const void* Bm, int ldb, int M, int N, int K, float alpha,
+                        float* C, int ldc, void* stream) {
+    CVCL_REQUIRE(A && Bm && C, "gemm_nt_f32out: null pointer");
+    CVCL_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_nt_f32out: bad shape");
+    GemmOperands op{}; op.A[0] = A; op.ld_a[0] = lda; op.B[0] = Bm; op.ld_b[0] = ldb; op.ndir = 1;
+    GemmShape gs{}; gs.M[0] = gs.M[1] = M; gs.N[0] = gs.N[1] = N; gs.K = K; gs.m_stride = kBM; gs.n_stride = kBN;
+    EpiStoreF32::Params ep{}; ep.C[0] = ep.C[1] = C; ep.ldc[0] = ep.ldc[1] = ldc; ep.alpha = alpha;
+    return launch_gemm<kBN, kStages, EpiStoreF32>(op, gs, ep, 1, as_stream(stream));
+}
+
+// ------------------------------------------------------------------------------------ K2
+int cvcl_head_proj_norm_fwd(const void* x, int ldx, const void* w, int ldw, const float* bias,
+                            int M, int E, int K, int normalize,
+                            float* out_f32, int ld_f32, void* out_bf16, int ld_bf16,
+                            void* out_bf16_t, int ld_t, float* inv_norm, void* stream) {
+    CVCL_REQUIRE(x && w, "head_proj_norm_fwd: null operand");
+    CVCL_REQUIRE(M > 0 && E > 0 && K > 0, "head_proj_norm_fwd: bad shape M=%d E=%d K=%d", M, E, K);
+    const int cluster = ceil_div(E, kBN);
+    if (cluster > 8)
+        return fail(CVCL_ERR_UNSUPPORTED, "head_proj_norm_fwd: E=%d needs a cluster of %d > 8 CTAs", E, cluster);
+    GemmOperands op{}; op.A[0] = x; op.ld_a[0] = ldx; op.B[0] = w; op.ld_b[0] = ldw; op.ndir = 1;
+    GemmShape gs{}; gs.M[0] = gs.M[1] = M; gs.N[0] = gs.N[1] = E; gs.K = K; gs.m_stride = kBM; gs.n_stride = kBN;
+    EpiHeadNorm::Params ep{};
+    ep.bias = bias; ep.normalize = normalize; ep.out_f32 = out_f32; ep.ld_f32 = ld_f32;
+    ep.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); ep.ld_bf16 = ld_bf16;
+    ep.out_bf16_t = static_cast<__nv_bfloat16*>(out_bf16_t); ep.ld_t = ld_t; ep.inv_norm = inv_norm;
+    return launch_gemm<kBN, kStages, EpiHeadNorm>(op, gs, ep, cluster, as_stream(stream));
+}
+
+// ------------------------------------------------------------------------------------ K3+K4
+size_t cvcl_sim_workspace_bytes(int M0, int N0, int M1, int N1) {
+    return carve_sim_ws(nullptr, M0, N0, M1, N1).bytes;
+}
+
+int cvcl_sim_infonce_fwd(const void* img_q, const void* txt_k, const void* txt_q, const void* img_k,
+                         int ld, int M0, int N0, int M1, int N1, int E, float log_scale,
+                         int diag_off, float inv_rows, void* workspace,
+                         float* lse0, float* lse1, int* argmax0, int* argmax1, float* out5,
+                         void* stream) {
+    CVCL_REQUIRE(img_q && txt_k && txt_q && img_k && workspace && lse0 && lse1 && out5,
+                 "sim_infonce_fwd: null pointer");
+    CVCL_REQUIRE(M0 > 0 && N0 > 0 && M1 > 0 && N1 > 0 && E > 0, "sim_infonce_fwd: bad shape");
+    CVCL_REQUIRE(diag_off >= 0 && M0 + diag_off <= N0 && M1 + diag_off <= N1,
+                 "sim_infonce_fwd: positives out of range (M0=%d N0=%d M1=%d N1=%d diag_off=%d)", M0, N0, M1, N1, diag_off);
+    SimWs w = carve_sim_ws(workspace, M0, N0, M1, N1);
+    CVCL_CHECK_CUDA(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned int), as_stream(stream)));
+    GemmOperands op{}; op.ndir = 2;
+    op.A[0] = img_q; op.B[0] = txt_k; op.A[1] = txt_q; op.B[1] = img_k;
+    op.ld_a[0] = op.ld_a[1] = op.ld_b[0] = op.ld_b[1] = ld;
+    GemmShape gs{}; gs.M[0] = M0; gs.N[0] = N0; gs.M[1] = M1; gs.N[1] = N1; gs.K = E;
+    gs.m_stride = kBM; gs.n_stride = kBN;
+    EpiSimStats::Params ep{};
+    ep.scale = expf(log_scale);
+    for (int z = 0; z < 2; ++z) {
+        ep.diag_off[z] = diag_off; ep.part[z] = w.part[z]; ep.m_pad[z] = w.m_pad[z]; ep.diag[z] = w.diag[z];
+    }
+    int rc = launch_gemm<kBN, kStages, EpiSimStats>(op, gs, ep, 1, as_stream(stream));
+    if (rc) return rc;
+    FinalizeParams fp{};
+    for (int z = 0; z < 2; ++z) {
+        fp.part[z] = w.part[z]; fp.m_pad[z] = w.m_pad[z]; fp.n_tiles[z] = w.n_tiles[z];
+        fp.diag[z] = w.diag[z]; fp.diag_off[z] = diag_off;
+    }
+    fp.M[0] = M0; fp.M[1] = M1; fp.lse[0] = lse0; fp.lse[1] = lse1;
+    fp.argmax[0] = argmax0; fp.argmax[1] = argmax1; fp.inv_rows = inv_rows;
+    fp.block_part = w.block_part; fp.ticket = w.ticket; fp.out = out5;
+    infonce_finalize_kernel<<<ceil_div(M0 + M1, 256), 256, 0, as_stream(stream)>>>(fp);
+    CVCL_CHECK_CUDA(cudaGetLastError());
+    return CVCL_OK;
+}
+
+int cvcl_sim_logits_fwd(const void* img, const void* txt, int ld, int Ni, int Nt, int E, float log_scale,
+                        float* lpi, float* lpt, void* stream) {
+    CVCL_REQUIRE(img && txt && (lpi || lpt), "sim_logits_fwd: null pointer");
+    CVCL_REQUIRE(Ni > 0 && Nt > 0 && E > 0, "sim_logits_fwd: bad shape Ni=%d Nt=%d E=%d", Ni, Nt, E);
+    EpiStoreF32::Params ep{}; ep.alpha = expf(log_scale);
+    GemmShape gs{}; gs.K = E; gs.m_stride = kBM; gs.n_stride = kBN;
+    GemmOperands op{};
+    int z = 0;
+    if (lpi) { op.A[z] = img; op.B[z] = txt; gs.M[z] = Ni; gs.N[z] = Nt; ep.C[z] = lpi; ep.ldc[z] = Nt; ++z; }
+    if (lpt) { op.A[z] = txt; op.B[z] = img; gs.M[z] = Nt; gs.N[z] = Ni; ep.C[z] = lpt; ep.ldc[z] = Ni; ++z; }
+    op.ndir = z;
+    for (int i = 0; i < 2; ++i) { op.ld_a[i] = ld; op.ld_b[i] = ld; }
+    if (z == 1) { gs.M[1] = gs.M[0]; gs.N[1] = gs.N[0]; ep.C[1] = ep.C[0]; ep.ldc[1] = ep.ldc[0]; }
+    return launch_gemm<kBN, kStages, EpiStoreF32>(op, gs, ep, 1, as_stream(stream));
+}
+
+// ------------------------------------------------------------------------------------ K5
+int cvcl_sim_infonce_bwd_g(const void* img_q, const void* txt_k, const void* txt_q, const void* img_k,
+                           int ld, int M0, int N0, int M1, int N1, int E, float log_scale, int diag_off,
+                           float coef, const float* lse_q0, const float* lse_k0, const float* lse_q1,
+                           const float* lse_k1, void* Gs0, int ldg0, void* Gs1, int ldg1, float* dscale,
+                           void* stream) {
+    CVCL_REQUIRE(img_q && txt_k && txt_q && img_k && lse_q0 && lse_k0 && lse_q1 && lse_k1 && Gs0 && Gs1,
+                 "sim_infonce_bwd_g: null pointer");
+    CVCL_REQUIRE(M0 > 0 && N0 > 0 && M1 > 0 && N1 > 0 && E > 0, "sim_infonce_bwd_g: bad shape");
+    GemmOperands op{}; op.ndir = 2;
+    op.A[0] = img_q; op.B[0] = txt_k; op.A[1] = txt_q; op.B[1] = img_k;
+    op.ld_a[0] = op.ld_a[1] = op.ld_b[0] = op.ld_b[1] = ld;
+    GemmShape gs{}; gs.M[0] = M0; gs.N[0] = N0; gs.M[1] = M1; gs.N[1] = N1; gs.K = E;
+    gs.m_stride = kBM; gs.n_stride = kBN;
+    EpiGradG::Params ep{};
+    ep.scale = expf(log_scale); ep.coef = coef; ep.diag_off[0] = ep.diag_off[1] = diag_off;
+    ep.lse_q[0] = lse_q0; ep.lse_k[0] = lse_k0; ep.lse_q[1] = lse_q1; ep.lse_k[1] = lse_k1;
+    ep.G[0] = static_cast<__nv_bfloat16*>(Gs0); ep.ldg[0] = ldg0;
+    ep.G[1] = static_cast<__nv_bfloat16*>(Gs1); ep.ldg[1] = ldg1;
+    ep.dscale_accum = dscale;
+    return launch_gemm<kBN, kStages, EpiGradG>(op, gs, ep, 1, as_stream(stream));
+}
+
+int cvcl_feat_grad_norm_bwd(const void* Gs, int ldg, const void* other_t, int ld_other, int M, int E,
+                            int Kc, const void* feat_bf16, int ld_feat, const float* inv_norm,
+                            int normalize, const int64_t* row_len, float* out_f32, int ld_f32,
+                            void* out_bf16_t, int ld_t, float* dbias, void* stream) {
+    CVCL_REQUIRE(Gs && other_t, "feat_grad_norm_bwd: null operand");
+    CVCL_REQUIRE(!normalize || (feat_bf16 && inv_norm), "feat_grad_norm_bwd: normalize needs feat and inv_norm");
+    CVCL_REQUIRE(M > 0 && E > 0 && Kc > 0, "feat_grad_norm_bwd: bad shape");
+    const int cluster = ceil_div(E, kBN);
+    if (cluster > 8)
+        return fail(CVCL_ERR_UNSUPPORTED, "feat_grad_norm_bwd: E=%d needs a cluster of %d > 8 CTAs", E, cluster);
+    GemmOperands op{}; op.A[0] = Gs; op.ld_a[0] = ldg; op.B[0] = other_t; op.ld_b[0] = ld_other; op.ndir = 1;
+    GemmShape gs{}; gs.M[0] = gs.M[1] = M; gs.N[0] = gs.N[1] = E; gs.K = Kc; gs.m_stride = kBM; gs.n_stride = kBN;
+    EpiNormBwd::Params ep{};
+    ep.feat = static_cast<const __nv_bfloat16*>(feat_bf16); ep.ld_feat = ld_feat; ep.inv_norm = inv_norm;
+    ep.normalize = normalize; ep.row_len = reinterpret_cast<const long long*>(row_len);
+    ep.out_f32 = out_f32; ep.ld_f32 = ld_f32;
+    ep.out_bf16_t = static_cast<__nv_bfloat16*>(out_bf16_t); ep.ld_t = ld_t; ep.dbias = dbias;
+    return launch_gemm<kBN, kStages, EpiNormBwd>(op, gs, ep, cluster, as_stream(stream));
+}
+
+int cvcl_head_weight_grad(const void* du_t, int ld_du, const void* x_t, int ld_x, int E, int K, int M,
+                          float* dW, int ld_dw, void* stream) {
+    CVCL_REQUIRE(du_t && x_t && dW, "head_weight_grad: null pointer");
+    CVCL_REQUIRE(E > 0 && K > 0 && M > 0, "head_weight_grad: bad shape");
+    GemmOperands op{}; op.A[0] = du_t; op.ld_a[0] = ld_du; op.B[0] = x_t; op.ld_b[0] = ld_x; op.ndir = 1;
+    GemmShape gs{}; gs.M[0] = gs.M[1] = E; gs.N[0] = gs.N[1] = K; gs.K = M; gs.m_stride = kBM; gs.n_stride = kBN;
+    EpiStoreF32::Params ep{}; ep.C[0] = ep.C[1] = dW; ep.ldc[0] = ep.ldc[1] = ld_dw; ep.alpha = 1.f;
+    return launch_gemm<kBN, kStages, EpiStoreF32>(op, gs, ep, 1, as_stream(stream));
+}
+
+// ------------------------------------------------------------------------------------ fused flat step
+namespace {
+struct FlatWs {
+    __nv_bfloat16 *w16, *x16, *x16t, *img16, *img16t, *txt16, *txt16t, *G0, *G1, *du16t;
+    float *invn_i, *invn_t, *lse0, *lse1, *dm;
+    void* sim; int ldB; size_t bytes;
+};
+FlatWs carve_flat_ws(void* ws, int B, int L, int E, int K, int V) {
+    (void)L; (void)V;
+    FlatWs f{};
+    unsigned char* base = static_cast<unsigned char*>(ws);
+    size_t off = 0;
+    f.ldB = pad8(B);
+    auto take = [&](size_t bytes) { void* p = base + off; off += align_up(bytes, 256); return p; };
+    f.w16 = static_cast<__nv_bfloat16*>(take(2ull * E * K));
+    f.x16 = static_cast<__nv_bfloat16*>(take(2ull * B * K));
+    f.x16t = static_cast<__nv_bfloat16*>(take(2ull * K * f.ldB));
+    f.img16 = static_cast<__nv_bfloat16*>(take(2ull * B * E));
+    f.img16t = static_cast<__nv_bfloat16*>(take(2ull * E * f.ldB));
+    f.txt16 = static_cast<__nv_bfloat16*>(take(2ull * B * E));
+    f.txt16t = static_cast<__nv_bfloat16*>(take(2ull * E * f.ldB));
+    f.G0 = static_cast<__nv_bfloat16*>(take(2ull * B * f.ldB));
+    f.G1 = static_cast<__nv_bfloat16*>(take(2ull * B * f.ldB));
+    f.du16t = static_cast<__nv_bfloat16*>(take(2ull * E * f.ldB));
+    f.invn_i = static_cast<float*>(take(4ull * B));
+    f.invn_t = static_cast<float*>(take(4ull * B));
+    f.lse0 = static_cast<float*>(take(4ull * B));
+    f.lse1 = static_cast<float*>(take(4ull * B));
+    f.dm = static_cast<float*>(take(4ull * B * E));
+    f.sim = base + off;
+    off += align_up(cvcl_sim_workspace_bytes(B, B, B, B), 256);
+    f.bytes = off;
+    return f;
+}
+}  // namespace
+
+size_t cvcl_flat_step_workspace_bytes(int B, int L, int E, int K, int V) {
+    return carve_flat_ws(nullptr, B, L, E, K, V).bytes;
+}
+
+int cvcl_flat_contrastive_step(const void* x, int x_is_bf16, const int64_t* ids, const int64_t* lens,
+                               const float* w, const float* bias, const float* table,
+                               int B, int L, int E, int K, int V, int normalize, float log_scale,
+                               int need_grads, void* workspace,
+                               float* out5, float* img_feat_f32, float* txt_feat_f32,
+                               float* dW, float* dbias, float* dtable, float* dscale,
+                               int* status, void* stream) {
+    CVCL_REQUIRE(x && ids && lens && w && table && workspace && out5, "flat_contrastive_step: null pointer");
+    CVCL_REQUIRE(!need_grads || (dW && dbias && dtable && dscale), "flat_contrastive_step: null gradient output");
+    CVCL_REQUIRE(B > 0 && E % 8 == 0 && K % 8 == 0, "flat_contrastive_step: need B>0, E%%8==0, K%%8==0 (B=%d E=%d K=%d)", B, E, K);
+    cudaStream_t st = as_stream(stream);
+    FlatWs f = carve_flat_ws(workspace, B, L, E, K, V);
+    int rc;
+    // operand staging: bf16 copies of the master weight and the trunk features (+ transpose for dW)
+    if ((rc = cvcl_cast_transpose(w, 0, f.w16, nullptr, 1, E, K, K, K, 0, 0, 0, 0, stream))) return rc;
+    if ((rc = cvcl_cast_transpose(x, x_is_bf16, f.x16, need_grads ? f.x16t : nullptr, 1, B, K, K, K, f.ldB, 0, 0, 0, stream))) return rc;
+    // K1, K2
+    if ((rc = cvcl_text_encoder_fwd(ids, lens, table, B, L, E, V, normalize, 0, 1.f, txt_feat_f32, f.txt16, E,
+                                    need_grads ? f.txt16t : nullptr, f.ldB, f.invn_t, nullptr, nullptr, status, stream))) return rc;
+    if ((rc = cvcl_head_proj_norm_fwd(f.x16, K, f.w16, K, bias, B, E, K, normalize, img_feat_f32, E, f.img16, E,
+                                      need_grads ? f.img16t : nullptr, f.ldB, f.invn_i, stream))) return rc;
+    // K3 + K4
+    if ((rc = cvcl_sim_infonce_fwd(f.img16, f.txt16, f.txt16, f.img16, E, B, B, B, B, E, log_scale, 0,
+                                   1.f / static_cast<float>(B), f.sim, f.lse0, f.lse1, nullptr, nullptr, out5, stream))) return rc;
+    if (!need_grads) return CVCL_OK;
+    // K5
+    CVCL_CHECK_CUDA(cudaMemsetAsync(dscale, 0, sizeof(float), st));
+    CVCL_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * E, st));
+    CVCL_CHECK_CUDA(cudaMemsetAsync(dtable, 0, sizeof(float) * static_cast<size_t>(V) * E, st));
+    if ((rc = cvcl_sim_infonce_bwd_g(f.img16, f.txt16, f.txt16, f.img16, E, B, B, B, B, E, log_scale, 0,
+                                     0.5f / static_cast<float>(B), f.lse0, f.lse1, f.lse1, f.lse0,
+                                     f.G0, f.ldB, f.G1, f.ldB, dscale, stream))) return rc;
+    if ((rc = cvcl_feat_grad_norm_bwd(f.G0, f.ldB, f.txt16t, f.ldB, B, E, B, f.img16, E, f.invn_i, normalize,
+                                      nullptr, nullptr, 0, f.du16t, f.ldB, dbias, stream))) return rc;
+    if ((rc = cvcl_feat_grad_norm_bwd(f.G1, f.ldB, f.img16t, f.ldB, B, E, B, f.txt16, E, f.invn_t, normalize,
+                                      lens, f.dm, E, nullptr, 0, nullptr, stream))) return rc;
+    if ((rc = cvcl_head_weight_grad(f.du16t, f.ldB, f.x16t, f.ldB, E, K, B, dW, K, stream))) return rc;
+    if ((rc = cvcl_embedding_scatter_add(ids, f.dm, dtable, B, L, E, V, 0, stream))) return rc;
+    return CVCL_OK;
+}
+
+// ------------------------------------------------------------------------------------ K7
+int cvcl_eval_nway_fwd(const float* img, const float* txt, const int* txt_index, int n_trials, int n_way,
+                       int E, int normalize, float log_scale, int* pred, float* logits, void* stream) {
+    CVCL_REQUIRE(img && txt && pred, "eval_nway_fwd: null pointer");
+    CVCL_REQUIRE(n_trials >= 0 && n_way > 0, "eval_nway_fwd: bad shape");
+    CVCL_REQUIRE(E > 0 && E % 4 == 0 && E <= 128 * kMaxVec, "eval_nway_fwd: bad E=%d", E);
+    if (n_trials == 0) return CVCL_OK;
+    eval_nway_kernel<<<warps_grid(n_trials), 256, 0, as_stream(stream)>>>(
+        img, txt, txt_index, n_trials, n_way, E, normalize, expf(log_scale), pred, logits);
+    CVCL_CHECK_CUDA(cudaGetLastError());
+    return CVCL_OK;
+}
+
+}  // extern "C"

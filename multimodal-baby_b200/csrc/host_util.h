@@ -24,24 +24,25 @@ inline int fail(int code, const char* fmt, ...) {
     return code;
 }
 
-enum : int {
-    CVCL_OK = 0,
-    CVCL_ERR_INVALID = -1,      // bad shape / null pointer / misalignment
-    CVCL_ERR_UNSUPPORTED = -2,  // valid request the kernels do not cover (never a fallback)
-    CVCL_ERR_CUDA = -3,         // CUDA runtime / driver error
-};
+// error codes: the macros of include/cvcl_b200.h (repeated here for stand-alone tools)
+#ifndef CVCL_OK
+#define CVCL_OK 0
+#define CVCL_ERR_INVALID (-1)      // bad shape / null pointer / misalignment
+#define CVCL_ERR_UNSUPPORTED (-2)  // valid request the kernels do not cover (never a fallback)
+#define CVCL_ERR_CUDA (-3)         // CUDA runtime / driver error
+#endif
 
 #define CVCL_CHECK_CUDA(expr)                                                              \
     do {                                                                                   \
         cudaError_t _e = (expr);                                                           \
         if (_e != cudaSuccess)                                                             \
-            return ::cvcl::fail(::cvcl::CVCL_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,     \
+            return ::cvcl::fail(CVCL_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,     \
                                 cudaGetErrorString(_e), __FILE__, __LINE__);               \
     } while (0)
 
 #define CVCL_REQUIRE(cond, ...)                                                            \
     do {                                                                                   \
-        if (!(cond)) return ::cvcl::fail(::cvcl::CVCL_ERR_INVALID, __VA_ARGS__);           \
+        if (!(cond)) return ::cvcl::fail(CVCL_ERR_INVALID, __VA_ARGS__);           \
     } while (0)
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,

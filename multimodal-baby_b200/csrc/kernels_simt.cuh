@@ -408,4 +408,115 @@ __global__ void __launch_bounds__(256) cast_transpose_kernel(const TIn* src, __n
     }
 }
 
+
+// --------------------------------------------------------------------------------------
+// stand-alone backward of the flat text encoder (used when encode_text is differentiated on
+// its own): dm = F.normalize-backward(g) / len, then the embedding scatter.  One warp per row.
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) embedding_bag_bwd_kernel(const long long* ids, const long long* lens,
+                                                                const float* g, const float* feat,
+                                                                const float* inv_norm, int normalize,
+                                                                float* dtable, int B, int L, int E, int V) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    const int nch = (E + 127) >> 7;
+    float4 r[kMaxVec], f[kMaxVec];
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxVec; ++c) {
+        r[c] = make_float4(0.f, 0.f, 0.f, 0.f); f[c] = r[c];
+        if (c < nch && (c * 32 + lane) * 4 < E) {
+            r[c] = __ldg(reinterpret_cast<const float4*>(g + static_cast<size_t>(warp) * E) + c * 32 + lane);
+            if (normalize) f[c] = __ldg(reinterpret_cast<const float4*>(feat + static_cast<size_t>(warp) * E) + c * 32 + lane);
+        }
+        dot += r[c].x * f[c].x + r[c].y * f[c].y + r[c].z * f[c].z + r[c].w * f[c].w;
+    }
+    dot = warp_sum(dot);
+    const float inv = normalize ? __ldg(inv_norm + warp) : 1.f;
+    const float sc = inv / static_cast<float>(__ldg(lens + warp));
+#pragma unroll
+    for (int c = 0; c < kMaxVec; ++c) {
+        r[c].x = (r[c].x - f[c].x * dot) * sc; r[c].y = (r[c].y - f[c].y * dot) * sc;
+        r[c].z = (r[c].z - f[c].z * dot) * sc; r[c].w = (r[c].w - f[c].w * dot) * sc;
+    }
+    for (int l = 0; l < L; ++l) {
+        const long long id = __ldg(ids + static_cast<size_t>(warp) * L + l);
+        if (id <= 0 || id >= V) continue;
+        float4* dst = reinterpret_cast<float4*>(dtable + static_cast<size_t>(id) * E);
+#pragma unroll
+        for (int c = 0; c < kMaxVec; ++c)
+            if (c < nch && (c * 32 + lane) * 4 < E) atomicAdd(dst + c * 32 + lane, r[c]);
+    }
+}
+
+// stand-alone F.normalize backward on rows: du = (g - feat <feat,g>) * inv_norm.
+// Outputs (nullable): fp32 [M,E], bf16 [M,ld], bf16 transposed [E,ld_t], dbias[E] += sum_m du.
+__global__ void __launch_bounds__(256) rownorm_bwd_kernel(const float* g, const float* feat,
+                                                          const float* inv_norm, int M, int E, int normalize,
+                                                          float* du_f32, __nv_bfloat16* du_bf16, int ld,
+                                                          __nv_bfloat16* du_bf16_t, int ld_t, float* dbias) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= M) return;
+    const int nch = (E + 127) >> 7;
+    float4 r[kMaxVec], f[kMaxVec];
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxVec; ++c) {
+        r[c] = make_float4(0.f, 0.f, 0.f, 0.f); f[c] = r[c];
+        if (c < nch && (c * 32 + lane) * 4 < E) {
+            r[c] = __ldg(reinterpret_cast<const float4*>(g + static_cast<size_t>(warp) * E) + c * 32 + lane);
+            if (normalize) f[c] = __ldg(reinterpret_cast<const float4*>(feat + static_cast<size_t>(warp) * E) + c * 32 + lane);
+        }
+        dot += r[c].x * f[c].x + r[c].y * f[c].y + r[c].z * f[c].z + r[c].w * f[c].w;
+    }
+    dot = warp_sum(dot);
+    const float inv = normalize ? __ldg(inv_norm + warp) : 1.f;
+#pragma unroll
+    for (int c = 0; c < kMaxVec; ++c) {
+        const int e = (c * 32 + lane) * 4;
+        if (c < nch && e < E) {
+            float4 o = make_float4((r[c].x - f[c].x * dot) * inv, (r[c].y - f[c].y * dot) * inv,
+                                   (r[c].z - f[c].z * dot) * inv, (r[c].w - f[c].w * dot) * inv);
+            if (du_f32) *reinterpret_cast<float4*>(du_f32 + static_cast<size_t>(warp) * E + e) = o;
+            if (du_bf16) store_bf16x4(du_bf16 + static_cast<size_t>(warp) * ld + e, o);
+            if (du_bf16_t) {
+                du_bf16_t[static_cast<size_t>(e) * ld_t + warp] = __float2bfloat16_rn(o.x);
+                du_bf16_t[static_cast<size_t>(e + 1) * ld_t + warp] = __float2bfloat16_rn(o.y);
+                du_bf16_t[static_cast<size_t>(e + 2) * ld_t + warp] = __float2bfloat16_rn(o.z);
+                du_bf16_t[static_cast<size_t>(e + 3) * ld_t + warp] = __float2bfloat16_rn(o.w);
+            }
+            if (dbias) {
+                atomicAdd(dbias + e, o.x); atomicAdd(dbias + e + 1, o.y);
+                atomicAdd(dbias + e + 2, o.z); atomicAdd(dbias + e + 3, o.w);
+            }
+        }
+    }
+}
+
+// sum over the HW locations of a [B, HW, E] fp32 map (image factor of the spatial "mean"
+// similarity, multimodal.py:765-770).  Thread = 4 consecutive channels, coalesced over E.
+__global__ void __launch_bounds__(128) spatial_pool_kernel(const float* src, int B, int HW, int E,
+                                                           float* out_f32, __nv_bfloat16* out_bf16, int ld,
+                                                           __nv_bfloat16* out_bf16_t, int ld_t) {
+    const int b = blockIdx.y;
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (e >= E) return;
+    const float4* p = reinterpret_cast<const float4*>(src + (static_cast<size_t>(b) * HW) * E + e);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int h = 0; h < HW; ++h) {
+        const float4 v = __ldg(p + static_cast<size_t>(h) * (E >> 2));
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + static_cast<size_t>(b) * E + e) = a;
+    if (out_bf16) store_bf16x4(out_bf16 + static_cast<size_t>(b) * ld + e, a);
+    if (out_bf16_t) {
+        out_bf16_t[static_cast<size_t>(e) * ld_t + b] = __float2bfloat16_rn(a.x);
+        out_bf16_t[static_cast<size_t>(e + 1) * ld_t + b] = __float2bfloat16_rn(a.y);
+        out_bf16_t[static_cast<size_t>(e + 2) * ld_t + b] = __float2bfloat16_rn(a.z);
+        out_bf16_t[static_cast<size_t>(e + 3) * ld_t + b] = __float2bfloat16_rn(a.w);
+    }
+}
+
 }  // namespace cvcl

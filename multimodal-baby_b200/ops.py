@@ -1,0 +1,679 @@
+"""torch.library custom ops over the C ABI of libcvcl_b200.so + their autograd wiring.
+
+Every op in the `cvcl_b200::` namespace is a thin marshalling layer: it allocates the outputs
+with torch (torch owns all device memory), passes raw device pointers, sizes and the current
+CUDA stream to one `extern "C"` entry point, and returns.  There is NO CPU implementation:
+CPU tensors raise, and a missing shared library raises `CvclLibraryMissing` at first use.
+
+Reference call sites replaced (paths relative to the reference repo):
+  text_features     multimodal/multimodal.py:496-503, 575-584, 743
+  head_features     multimodal/multimodal.py:181-192 (applied at :101), 736
+  sim_logits        multimodal/multimodal.py:755, 783-794
+  sim_infonce       multimodal/multimodal.py:755, 783-787, 801-818 (+ autograd)
+  flat_contrastive_step   multimodal/multimodal.py:796-822 + loss.backward()
+  eval_nway         multimodal/multimodal_lit.py:466-511, eval.py:196-214
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _cabi
+
+_NS = "cvcl_b200"
+
+
+# ----------------------------------------------------------------------------------------
+# marshalling helpers
+# ----------------------------------------------------------------------------------------
+def _p(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("cvcl_b200 ops run only on CUDA (sm_100a) tensors; there is no CPU "
+                               "fallback (got a %s tensor)" % t.device)
+
+
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def _i64(t: Tensor) -> Tensor:
+    if t.dtype != torch.int64:
+        raise TypeError("token ids / lengths must be int64 (got %s)" % t.dtype)
+    return t.contiguous()
+
+
+def _f32(t: Tensor) -> Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+def to_bf16_pair(x: Tensor, want_t: bool) -> Tuple[Tensor, Optional[Tensor]]:
+    """[R,C] fp32/bf16 -> (bf16 [R,C] contiguous, bf16 transposed [C, pad8(R)] or None)."""
+    x = x.detach()
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    x = x.contiguous()
+    R, C = x.shape
+    if x.dtype == torch.bfloat16 and not want_t:
+        return x, None
+    dst = x if x.dtype == torch.bfloat16 else torch.empty((R, C), dtype=torch.bfloat16, device=x.device)
+    ldt = _pad8(R)
+    dst_t = torch.empty((C, ldt), dtype=torch.bfloat16, device=x.device) if want_t else None
+    _cabi.call("cvcl_cast_transpose", _p(x), int(x.dtype == torch.bfloat16),
+               None if dst is x else _p(dst), _p(dst_t), 1, R, C, C, C, ldt, 0, 0, 0, _stream())
+    return dst, dst_t
+
+
+# ----------------------------------------------------------------------------------------
+# K1 text encoder
+# ----------------------------------------------------------------------------------------
+@torch.library.custom_op(_NS + "::text_encoder_fwd", mutates_args=())
+def text_encoder_fwd(ids: Tensor, lens: Tensor, table: Tensor, normalize: bool, per_token: bool,
+                     pool_scale: float) -> Tuple[Tensor, Tensor, Tensor]:
+    """-> (feat [B,E] fp32, inv_norm [B] or [B*L] fp32, tok [B,L,E] fp32 (per_token) or empty)."""
+    _need_cuda(ids, lens, table)
+    ids = _i64(ids); lens = _i64(lens); table = _f32(table)
+    B, L = ids.shape
+    V, E = table.shape
+    dev = ids.device
+    feat = torch.empty((B, E), dtype=torch.float32, device=dev)
+    inv = torch.empty((B * L if per_token else B,), dtype=torch.float32, device=dev)
+    tok = torch.empty((B, L, E) if per_token else (0,), dtype=torch.float32, device=dev)
+    _cabi.call("cvcl_text_encoder_fwd", _p(ids), _p(lens), _p(table), B, L, E, V, int(normalize),
+               int(per_token), float(pool_scale), _p(feat), None, 0, None, 0, _p(inv),
+               _p(tok) if per_token else None, None, None, _stream())
+    return feat, inv, tok
+
+
+@text_encoder_fwd.register_fake
+def _(ids, lens, table, normalize, per_token, pool_scale):
+    B, L = ids.shape
+    E = table.shape[1]
+    return (table.new_empty((B, E)), table.new_empty((B * L if per_token else B,)),
+            table.new_empty((B, L, E) if per_token else (0,)))
+
+
+@torch.library.custom_op(_NS + "::embedding_bag_bwd", mutates_args=())
+def embedding_bag_bwd(ids: Tensor, lens: Tensor, g: Tensor, feat: Tensor, inv_norm: Tensor,
+                      normalize: bool, V: int) -> Tensor:
+    _need_cuda(ids, g)
+    ids = _i64(ids); lens = _i64(lens); g = _f32(g)
+    B, L = ids.shape
+    E = g.shape[1]
+    dtable = torch.zeros((V, E), dtype=torch.float32, device=g.device)
+    _cabi.call("cvcl_embedding_bag_bwd", _p(ids), _p(lens), _p(g), _p(feat.contiguous()),
+               _p(inv_norm), int(normalize), _p(dtable), B, L, E, V, _stream())
+    return dtable
+
+
+@embedding_bag_bwd.register_fake
+def _(ids, lens, g, feat, inv_norm, normalize, V):
+    return g.new_empty((V, g.shape[1]))
+
+
+@torch.library.custom_op(_NS + "::text_token_bwd", mutates_args=())
+def text_token_bwd(ids: Tensor, lens: Tensor, table: Tensor, dtok: Optional[Tensor],
+                   dpool: Optional[Tensor], pool_scale: float, normalize: bool) -> Tensor:
+    _need_cuda(ids, table)
+    ids = _i64(ids); lens = _i64(lens); table = _f32(table)
+    B, L = ids.shape
+    V, E = table.shape
+    dtok = None if dtok is None else _f32(dtok)
+    dpool = None if dpool is None else _f32(dpool)
+    dtable = torch.zeros((V, E), dtype=torch.float32, device=table.device)
+    _cabi.call("cvcl_text_token_bwd", _p(ids), _p(lens), _p(table), _p(dtok), _p(dpool),
+               float(pool_scale), _p(dtable), B, L, E, V, int(normalize), _stream())
+    return dtable
+
+
+@text_token_bwd.register_fake
+def _(ids, lens, table, dtok, dpool, pool_scale, normalize):
+    return table.new_empty(table.shape)
+
+
+@torch.library.custom_op(_NS + "::embedding_gather", mutates_args=())
+def embedding_gather(ids: Tensor, table: Tensor) -> Tensor:
+    _need_cuda(ids, table)
+    ids = _i64(ids); table = _f32(table)
+    V, E = table.shape
+    out = torch.empty(tuple(ids.shape) + (E,), dtype=torch.float32, device=table.device)
+    _cabi.call("cvcl_embedding_gather", _p(ids), _p(table), _p(out), ids.numel(), E, V, _stream())
+    return out
+
+
+@embedding_gather.register_fake
+def _(ids, table):
+    return table.new_empty(tuple(ids.shape) + (table.shape[1],))
+
+
+@torch.library.custom_op(_NS + "::embedding_scatter_add", mutates_args=())
+def embedding_scatter_add(ids: Tensor, g: Tensor, V: int) -> Tensor:
+    """autograd of embedding_gather: one gradient row per token."""
+    _need_cuda(ids, g)
+    ids = _i64(ids); g = _f32(g)
+    E = g.shape[-1]
+    n = ids.numel()
+    dtable = torch.zeros((V, E), dtype=torch.float32, device=g.device)
+    _cabi.call("cvcl_embedding_scatter_add", _p(ids), _p(g), _p(dtable), n, 1, E, V, 1, _stream())
+    return dtable
+
+
+@embedding_scatter_add.register_fake
+def _(ids, g, V):
+    return g.new_empty((V, g.shape[-1]))
+
+
+class _TextFeaturesFlat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ids, lens, table, normalize):
+        feat, inv, _ = text_encoder_fwd(ids, lens, table, normalize, False, 1.0)
+        ctx.save_for_backward(ids, lens, feat, inv)
+        ctx.normalize = normalize
+        ctx.V = table.shape[0]
+        return feat
+
+    @staticmethod
+    def backward(ctx, g):
+        ids, lens, feat, inv = ctx.saved_tensors
+        return None, None, embedding_bag_bwd(ids, lens, g, feat, inv, ctx.normalize, ctx.V), None
+
+
+class _TextFeaturesSpatial(torch.autograd.Function):
+    """-> (tok [B,L,E] normalised per token, pooled [B,E] = sum_l tok * pool_scale / len)."""
+
+    @staticmethod
+    def forward(ctx, ids, lens, table, normalize, pool_scale):
+        pooled, inv, tok = text_encoder_fwd(ids, lens, table, normalize, True, pool_scale)
+        ctx.save_for_backward(ids, lens, table)
+        ctx.normalize = normalize
+        ctx.pool_scale = pool_scale
+        return tok, pooled
+
+    @staticmethod
+    def backward(ctx, dtok, dpool):
+        ids, lens, table = ctx.saved_tensors
+        return None, None, text_token_bwd(ids, lens, table, dtok, dpool, ctx.pool_scale,
+                                          ctx.normalize), None, None
+
+
+class _EmbeddingGather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ids, table):
+        ctx.save_for_backward(ids)
+        ctx.V = table.shape[0]
+        return embedding_gather(ids, table)
+
+    @staticmethod
+    def backward(ctx, g):
+        (ids,) = ctx.saved_tensors
+        return None, embedding_scatter_add(ids, g, ctx.V)
+
+
+def text_features_flat(ids, lens, table, normalize=True):
+    return _TextFeaturesFlat.apply(ids, lens, table, bool(normalize))
+
+
+def text_features_spatial(ids, lens, table, normalize=True, pool_scale=1.0 / 49):
+    return _TextFeaturesSpatial.apply(ids, lens, table, bool(normalize), float(pool_scale))
+
+
+def text_outputs(ids, table):
+    return _EmbeddingGather.apply(ids, table)
+
+
+# ----------------------------------------------------------------------------------------
+# K2 projection head
+# ----------------------------------------------------------------------------------------
+@torch.library.custom_op(_NS + "::head_proj_norm_fwd", mutates_args=())
+def head_proj_norm_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor], normalize: bool) -> Tuple[Tensor, Tensor]:
+    """x [M,K] (fp32/bf16), w [E,K] -> (feat [M,E] fp32, inv_norm [M])."""
+    _need_cuda(x, w)
+    x16, _ = to_bf16_pair(x, False)
+    w16, _ = to_bf16_pair(w, False)
+    M, K = x16.shape
+    E = w16.shape[0]
+    b = None if bias is None else _f32(bias)
+    feat = torch.empty((M, E), dtype=torch.float32, device=x.device)
+    inv = torch.empty((M,), dtype=torch.float32, device=x.device)
+    _cabi.call("cvcl_head_proj_norm_fwd", _p(x16), K, _p(w16), K, _p(b), M, E, K, int(normalize),
+               _p(feat), E, None, 0, None, 0, _p(inv), _stream())
+    return feat, inv
+
+
+@head_proj_norm_fwd.register_fake
+def _(x, w, bias, normalize):
+    return (x.new_empty((x.shape[0], w.shape[0]), dtype=torch.float32),
+            x.new_empty((x.shape[0],), dtype=torch.float32))
+
+
+@torch.library.custom_op(_NS + "::head_proj_norm_bwd", mutates_args=())
+def head_proj_norm_bwd(g: Tensor, feat: Tensor, inv_norm: Tensor, x: Tensor, w: Tensor,
+                       normalize: bool, need_dx: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """-> (dW [E,K], db [E], dx [M,K] or empty), all fp32."""
+    _need_cuda(g, x, w)
+    g = _f32(g)
+    M, E = g.shape
+    K = x.shape[1]
+    dev = g.device
+    ldt = _pad8(M)
+    du_t = torch.empty((E, ldt), dtype=torch.bfloat16, device=dev)
+    du16 = torch.empty((M, E), dtype=torch.bfloat16, device=dev) if need_dx else None
+    db = torch.zeros((E,), dtype=torch.float32, device=dev)
+    _cabi.call("cvcl_rownorm_bwd", _p(g), _p(feat.contiguous()), _p(inv_norm), M, E, int(normalize),
+               None, _p(du16), E, _p(du_t), ldt, _p(db), _stream())
+    _, x_t = to_bf16_pair(x, True)
+    dW = torch.empty((E, K), dtype=torch.float32, device=dev)
+    _cabi.call("cvcl_head_weight_grad", _p(du_t), ldt, _p(x_t), ldt, E, K, M, _p(dW), K, _stream())
+    if need_dx:
+        _, w_t = to_bf16_pair(w, True)                      # [K, pad8(E)]
+        dx = torch.empty((M, K), dtype=torch.float32, device=dev)
+        _cabi.call("cvcl_gemm_nt_f32out", _p(du16), E, _p(w_t), _pad8(E), M, K, E, 1.0, _p(dx), K,
+                   _stream())
+    else:
+        dx = torch.empty((0,), dtype=torch.float32, device=dev)
+    return dW, db, dx
+
+
+@head_proj_norm_bwd.register_fake
+def _(g, feat, inv_norm, x, w, normalize, need_dx):
+    return (g.new_empty(w.shape, dtype=torch.float32), g.new_empty((w.shape[0],), dtype=torch.float32),
+            g.new_empty(x.shape if need_dx else (0,), dtype=torch.float32))
+
+
+class _HeadFeatures(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, normalize):
+        feat, inv = head_proj_norm_fwd(x, w, bias, normalize)
+        ctx.save_for_backward(x, w, feat, inv)
+        ctx.normalize = normalize
+        ctx.has_bias = bias is not None
+        return feat
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, feat, inv = ctx.saved_tensors
+        need_dx = ctx.needs_input_grad[0]
+        dW, db, dx = head_proj_norm_bwd(g, feat, inv, x, w, ctx.normalize, need_dx)
+        return (dx.to(x.dtype) if need_dx else None, dW.to(w.dtype),
+                db if ctx.has_bias else None, None)
+
+
+def head_features(x, w, bias, normalize=True):
+    """normalise(x @ w.T + bias) on the tcgen05 engine; x [M,K] -> [M,E] fp32."""
+    return _HeadFeatures.apply(x, w, bias, bool(normalize))
+
+
+# ----------------------------------------------------------------------------------------
+# spatial pooling (image factor of the "mean" similarity)
+# ----------------------------------------------------------------------------------------
+@torch.library.custom_op(_NS + "::spatial_pool", mutates_args=())
+def spatial_pool_fwd(x: Tensor) -> Tensor:
+    _need_cuda(x)
+    x = _f32(x)
+    B, HW, E = x.shape
+    out = torch.empty((B, E), dtype=torch.float32, device=x.device)
+    _cabi.call("cvcl_spatial_pool", _p(x), B, HW, E, _p(out), None, 0, None, 0, _stream())
+    return out
+
+
+@spatial_pool_fwd.register_fake
+def _(x):
+    return x.new_empty((x.shape[0], x.shape[2]))
+
+
+class _SpatialPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.hw = x.shape[1]
+        return spatial_pool_fwd(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.unsqueeze(1).expand(-1, ctx.hw, -1)
+
+
+def spatial_pool(x):
+    return _SpatialPool.apply(x)
+
+
+# ----------------------------------------------------------------------------------------
+# K3 logits (materialised, for the forward() API)
+# ----------------------------------------------------------------------------------------
+@torch.library.custom_op(_NS + "::sim_logits_fwd", mutates_args=())
+def sim_logits_fwd(img: Tensor, txt: Tensor, log_scale: float) -> Tuple[Tensor, Tensor]:
+    _need_cuda(img, txt)
+    i16, _ = to_bf16_pair(img, False)
+    t16, _ = to_bf16_pair(txt, False)
+    Ni, E = i16.shape
+    Nt = t16.shape[0]
+    lpi = torch.empty((Ni, Nt), dtype=torch.float32, device=img.device)
+    lpt = torch.empty((Nt, Ni), dtype=torch.float32, device=img.device)
+    _cabi.call("cvcl_sim_logits_fwd", _p(i16), _p(t16), E, Ni, Nt, E, float(log_scale), _p(lpi), _p(lpt),
+               _stream())
+    return lpi, lpt
+
+
+@sim_logits_fwd.register_fake
+def _(img, txt, log_scale):
+    return (img.new_empty((img.shape[0], txt.shape[0]), dtype=torch.float32),
+            img.new_empty((txt.shape[0], img.shape[0]), dtype=torch.float32))
+
+
+@torch.library.custom_op(_NS + "::sim_logits_bwd", mutates_args=())
+def sim_logits_bwd(g: Tensor, img: Tensor, txt: Tensor, log_scale: float) -> Tuple[Tensor, Tensor]:
+    """g = d/d(lpi) + d/d(lpt)^T  [Ni,Nt] fp32 -> (dimg [Ni,E], dtxt [Nt,E]) fp32."""
+    _need_cuda(g, img, txt)
+    g16, g16t = to_bf16_pair(g, True)               # [Ni,Nt], [Nt,pad8(Ni)]
+    _, i_t = to_bf16_pair(img, True)                # [E, pad8(Ni)]
+    _, t_t = to_bf16_pair(txt, True)                # [E, pad8(Nt)]
+    Ni, Nt = g.shape
+    E = img.shape[1]
+    scale = math.exp(log_scale)
+    dimg = torch.empty((Ni, E), dtype=torch.float32, device=g.device)
+    dtxt = torch.empty((Nt, E), dtype=torch.float32, device=g.device)
+    if Nt % 8 == 0:
+        _cabi.call("cvcl_gemm_nt_f32out", _p(g16), Nt, _p(t_t), _pad8(Nt), Ni, E, Nt, scale, _p(dimg), E,
+                   _stream())
+    else:                                           # TMA needs a 16-byte row pitch: re-pitch G
+        gp = torch.zeros((Ni, _pad8(Nt)), dtype=torch.bfloat16, device=g.device)
+        gp[:, :Nt] = g16
+        _cabi.call("cvcl_gemm_nt_f32out", _p(gp), _pad8(Nt), _p(t_t), _pad8(Nt), Ni, E, Nt, scale,
+                   _p(dimg), E, _stream())
+    _cabi.call("cvcl_gemm_nt_f32out", _p(g16t), _pad8(Ni), _p(i_t), _pad8(Ni), Nt, E, Ni, scale, _p(dtxt), E,
+               _stream())
+    return dimg, dtxt
+
+
+@sim_logits_bwd.register_fake
+def _(g, img, txt, log_scale):
+    return (img.new_empty(img.shape, dtype=torch.float32), txt.new_empty(txt.shape, dtype=torch.float32))
+
+
+class _SimLogits(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, txt, s):
+        ls = float(s)
+        lpi, lpt = sim_logits_fwd(img, txt, ls)
+        ctx.save_for_backward(img, txt, lpi)
+        ctx.ls = ls
+        ctx.s_is_tensor = torch.is_tensor(s)
+        return lpi, lpt
+
+    @staticmethod
+    def backward(ctx, glpi, glpt):
+        img, txt, lpi = ctx.saved_tensors
+        g = glpi + glpt.t()
+        dimg, dtxt = sim_logits_bwd(g, img, txt, ctx.ls)
+        ds = (g * lpi).sum() if ctx.s_is_tensor and ctx.needs_input_grad[2] else None
+        return dimg.to(img.dtype), dtxt.to(txt.dtype), ds
+
+
+def sim_logits(img, txt, s):
+    """(logits_per_image [Ni,Nt], logits_per_text [Nt,Ni]) = exp(s) * img @ txt.T (+ transpose)."""
+    return _SimLogits.apply(img, txt, s)
+
+
+# ----------------------------------------------------------------------------------------
+# K3+K4+K5: fused similarity + symmetric InfoNCE at feature level (single GPU or one shard)
+# ----------------------------------------------------------------------------------------
+@torch.library.custom_op(_NS + "::sim_infonce_fwd", mutates_args=())
+def sim_infonce_fwd(img_q: Tensor, txt_k: Tensor, txt_q: Tensor, img_k: Tensor, log_scale: float,
+                    diag_off: int, inv_rows: float) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """bf16 operands [.,E] -> (out5 [8] fp32, lse0 [M0], lse1 [M1], argmax0 [M0], argmax1 [M1])."""
+    _need_cuda(img_q, txt_k, txt_q, img_k)
+    M0, E = img_q.shape
+    N0 = txt_k.shape[0]
+    M1 = txt_q.shape[0]
+    N1 = img_k.shape[0]
+    dev = img_q.device
+    lib = _cabi.load()
+    ws = torch.empty((lib.cvcl_sim_workspace_bytes(M0, N0, M1, N1),), dtype=torch.uint8, device=dev)
+    out5 = torch.zeros((8,), dtype=torch.float32, device=dev)
+    lse0 = torch.empty((M0,), dtype=torch.float32, device=dev)
+    lse1 = torch.empty((M1,), dtype=torch.float32, device=dev)
+    a0 = torch.empty((M0,), dtype=torch.int32, device=dev)
+    a1 = torch.empty((M1,), dtype=torch.int32, device=dev)
+    _cabi.call("cvcl_sim_infonce_fwd", _p(img_q), _p(txt_k), _p(txt_q), _p(img_k), E, M0, N0, M1, N1, E,
+               float(log_scale), int(diag_off), float(inv_rows), _p(ws), _p(lse0), _p(lse1), _p(a0), _p(a1),
+               _p(out5), _stream())
+    return out5, lse0, lse1, a0, a1
+
+
+@sim_infonce_fwd.register_fake
+def _(img_q, txt_k, txt_q, img_k, log_scale, diag_off, inv_rows):
+    f = dict(dtype=torch.float32)
+    return (img_q.new_empty((8,), **f), img_q.new_empty((img_q.shape[0],), **f),
+            img_q.new_empty((txt_q.shape[0],), **f),
+            img_q.new_empty((img_q.shape[0],), dtype=torch.int32),
+            img_q.new_empty((txt_q.shape[0],), dtype=torch.int32))
+
+
+@torch.library.custom_op(_NS + "::sim_infonce_bwd", mutates_args=())
+def sim_infonce_bwd(img_q: Tensor, txt_k: Tensor, txt_q: Tensor, img_k: Tensor, log_scale: float,
+                    diag_off: int, coef: float, lse_q0: Tensor, lse_k0: Tensor, lse_q1: Tensor,
+                    lse_k1: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """-> (dimg_q [M0,E] fp32, dtxt_q [M1,E] fp32, dscale [1] fp32 (local rows only))."""
+    _need_cuda(img_q, txt_k, txt_q, img_k)
+    M0, E = img_q.shape
+    N0 = txt_k.shape[0]
+    M1 = txt_q.shape[0]
+    N1 = img_k.shape[0]
+    dev = img_q.device
+    ld0, ld1 = _pad8(N0), _pad8(N1)
+    G0 = torch.empty((M0, ld0), dtype=torch.bfloat16, device=dev)
+    G1 = torch.empty((M1, ld1), dtype=torch.bfloat16, device=dev)
+    ds = torch.zeros((1,), dtype=torch.float32, device=dev)
+    _cabi.call("cvcl_sim_infonce_bwd_g", _p(img_q), _p(txt_k), _p(txt_q), _p(img_k), E, M0, N0, M1, N1, E,
+               float(log_scale), int(diag_off), float(coef), _p(lse_q0), _p(lse_k0), _p(lse_q1), _p(lse_k1),
+               _p(G0), ld0, _p(G1), ld1, _p(ds), _stream())
+    _, txt_k_t = to_bf16_pair(txt_k, True)           # [E, pad8(N0)]
+    _, img_k_t = to_bf16_pair(img_k, True)           # [E, pad8(N1)]
+    dimg = torch.empty((M0, E), dtype=torch.float32, device=dev)
+    dtxt = torch.empty((M1, E), dtype=torch.float32, device=dev)
+    _cabi.call("cvcl_feat_grad_norm_bwd", _p(G0), ld0, _p(txt_k_t), ld0, M0, E, N0, None, 0, None, 0, None,
+               _p(dimg), E, None, 0, None, _stream())
+    _cabi.call("cvcl_feat_grad_norm_bwd", _p(G1), ld1, _p(img_k_t), ld1, M1, E, N1, None, 0, None, 0, None,
+               _p(dtxt), E, None, 0, None, _stream())
+    return dimg, dtxt, ds
+
+
+@sim_infonce_bwd.register_fake
+def _(img_q, txt_k, txt_q, img_k, log_scale, diag_off, coef, lse_q0, lse_k0, lse_q1, lse_k1):
+    f = dict(dtype=torch.float32)
+    return (img_q.new_empty(img_q.shape, **f), txt_q.new_empty(txt_q.shape, **f), img_q.new_empty((1,), **f))
+
+
+class _SimInfoNCE(torch.autograd.Function):
+    """Symmetric InfoNCE on (local) features; with a process group the features are all-gathered
+    and each rank evaluates its row block and column block.  Returns the five
+    GLOBAL scalars (identical on all ranks).  Gradients: d img / d txt for the local pairs are
+    complete; d s is summed over ranks (all-reduce) so every rank holds the full value."""
+
+    @staticmethod
+    def forward(ctx, img, txt, s, group):
+        import torch.distributed as dist
+        world = dist.get_world_size(group) if group is not None else 1
+        rank = dist.get_rank(group) if group is not None else 0
+        ls = float(s)
+        i16, _ = to_bf16_pair(img, False)
+        t16, _ = to_bf16_pair(txt, False)
+        b = i16.shape[0]
+        if world > 1:
+            i_all = torch.empty((world * b, i16.shape[1]), dtype=torch.bfloat16, device=i16.device)
+            t_all = torch.empty_like(i_all)
+            dist.all_gather_into_tensor(i_all, i16, group=group)
+            dist.all_gather_into_tensor(t_all, t16, group=group)
+        else:
+            i_all, t_all = i16, t16
+        Bg = world * b
+        out5, lse0, lse1, a0, a1 = sim_infonce_fwd(i16, t_all, t16, i_all, ls, rank * b, 1.0 / Bg)
+        out5 = out5.clone()
+        if world > 1:
+            dist.all_reduce(out5, group=group)
+        ctx.save_for_backward(i16, t16, i_all, t_all, lse0, lse1)
+        ctx.meta = (ls, rank, b, world, group, img.dtype, txt.dtype, torch.is_tensor(s))
+        ctx.mark_non_differentiable(a0, a1)
+        return out5[0], out5[1], out5[2], out5[3], out5[4], a0, a1
+
+    @staticmethod
+    def backward(ctx, gloss, *unused):
+        import torch.distributed as dist
+        i16, t16, i_all, t_all, lse0, lse1 = ctx.saved_tensors
+        ls, rank, b, world, group, idt, tdt, s_is_tensor = ctx.meta
+        if world > 1:
+            lse0_all = torch.empty((world * b,), dtype=torch.float32, device=lse0.device)
+            lse1_all = torch.empty_like(lse0_all)
+            dist.all_gather_into_tensor(lse0_all, lse0, group=group)
+            dist.all_gather_into_tensor(lse1_all, lse1, group=group)
+        else:
+            lse0_all, lse1_all = lse0, lse1
+        Bg = world * b
+        dimg, dtxt, ds = sim_infonce_bwd(i16, t_all, t16, i_all, ls, rank * b, 0.5 / Bg,
+                                         lse0, lse1_all, lse1, lse0_all)
+        if world > 1:
+            dist.all_reduce(ds, group=group)
+        dimg = (dimg * gloss).to(idt)
+        dtxt = (dtxt * gloss).to(tdt)
+        ds_out = (ds[0] * gloss) if (s_is_tensor and ctx.needs_input_grad[2]) else None
+        return dimg, dtxt, ds_out, None
+
+
+def sim_infonce(img, txt, s, group=None):
+    """-> (loss, image_accuracy, text_accuracy, image_entropy, text_entropy, image_pred, text_pred)."""
+    return _SimInfoNCE.apply(img, txt, s, group)
+
+
+# ----------------------------------------------------------------------------------------
+# fused flat train step (K1..K5 sequenced inside one C call)
+# ----------------------------------------------------------------------------------------
+@torch.library.custom_op(_NS + "::flat_contrastive_step", mutates_args=())
+def flat_contrastive_step(x: Tensor, ids: Tensor, lens: Tensor, w: Tensor, bias: Tensor, table: Tensor,
+                          log_scale: float, normalize: bool, need_grads: bool, want_features: bool
+                          ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """-> (out5 [8], img_feat [B,E] | empty, txt_feat [B,E] | empty, dW, db, dtable, dscale)."""
+    _need_cuda(x, ids, lens, w, bias, table)
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    x = x.detach().contiguous()
+    ids = _i64(ids); lens = _i64(lens)
+    w = _f32(w); bias = _f32(bias); table = _f32(table)
+    B, K = x.shape
+    L = ids.shape[1]
+    V, E = table.shape
+    dev = x.device
+    lib = _cabi.load()
+    ws = torch.empty((lib.cvcl_flat_step_workspace_bytes(B, L, E, K, V),), dtype=torch.uint8, device=dev)
+    out5 = torch.zeros((8,), dtype=torch.float32, device=dev)
+    f32 = dict(dtype=torch.float32, device=dev)
+    img_f = torch.empty((B, E), **f32) if want_features else torch.empty((0,), **f32)
+    txt_f = torch.empty((B, E), **f32) if want_features else torch.empty((0,), **f32)
+    if need_grads:
+        dW = torch.empty((E, K), **f32); db = torch.empty((E,), **f32)
+        dtable = torch.empty((V, E), **f32); ds = torch.empty((1,), **f32)
+    else:
+        dW, db, dtable, ds = (torch.empty((0,), **f32) for _ in range(4))
+    _cabi.call("cvcl_flat_contrastive_step", _p(x), int(x.dtype == torch.bfloat16), _p(ids), _p(lens),
+               _p(w), _p(bias), _p(table), B, L, E, K, V, int(normalize), float(log_scale),
+               int(need_grads), _p(ws), _p(out5), _p(img_f) if want_features else None,
+               _p(txt_f) if want_features else None,
+               _p(dW) if need_grads else None, _p(db) if need_grads else None,
+               _p(dtable) if need_grads else None, _p(ds) if need_grads else None, None, _stream())
+    return out5, img_f, txt_f, dW, db, dtable, ds
+
+
+@flat_contrastive_step.register_fake
+def _(x, ids, lens, w, bias, table, log_scale, normalize, need_grads, want_features):
+    f = dict(dtype=torch.float32)
+    B = x.shape[0]
+    V, E = table.shape
+    def e():
+        return x.new_empty((0,), **f)
+
+    def feat():
+        return x.new_empty((B, E), **f) if want_features else e()
+    if need_grads:
+        return (x.new_empty((8,), **f), feat(), feat(), x.new_empty(w.shape, **f), x.new_empty((E,), **f),
+                x.new_empty((V, E), **f), x.new_empty((1,), **f))
+    return (x.new_empty((8,), **f), feat(), feat(), e(), e(), e(), e())
+
+
+class _FlatContrastiveStep(torch.autograd.Function):
+    """loss and all parameter gradients in one pass; backward only scales the saved gradients by
+    the upstream scalar (the loss is a scalar, so d(c*loss)/dtheta = c * dloss/dtheta)."""
+
+    @staticmethod
+    def forward(ctx, x, ids, lens, w, bias, table, s, normalize, want_features):
+        need = any(t is not None and torch.is_tensor(t) and t.requires_grad for t in (w, bias, table, s))
+        if torch.is_tensor(x) and x.requires_grad:
+            raise RuntimeError("flat_contrastive_step does not produce d/dx; use the op-by-op path "
+                               "(finetune_cnn=True) instead")
+        out5, img_f, txt_f, dW, db, dtable, ds = flat_contrastive_step(
+            x, ids, lens, w, bias, table, float(s), normalize, need, want_features)
+        ctx.need = need
+        ctx.s_is_tensor = torch.is_tensor(s)
+        if need:
+            ctx.save_for_backward(dW, db, dtable, ds)
+        ctx.mark_non_differentiable(img_f, txt_f)
+        return out5[0], out5[1], out5[2], out5[3], out5[4], img_f, txt_f
+
+    @staticmethod
+    def backward(ctx, gloss, *unused):
+        if not ctx.need:
+            return (None,) * 9
+        dW, db, dtable, ds = ctx.saved_tensors
+        return (None, None, None, dW * gloss, db * gloss, dtable * gloss,
+                (ds[0] * gloss) if ctx.s_is_tensor else None, None, None)
+
+
+def flat_contrastive_loss(x, ids, lens, w, bias, table, s, normalize=True, want_features=False):
+    """-> (loss, img_acc, txt_acc, img_ent, txt_ent, img_feat|empty, txt_feat|empty)."""
+    return _FlatContrastiveStep.apply(x, ids, lens, w, bias, table, s, bool(normalize),
+                                      bool(want_features))
+
+
+# ----------------------------------------------------------------------------------------
+# K7 evaluation
+# ----------------------------------------------------------------------------------------
+@torch.library.custom_op(_NS + "::eval_nway", mutates_args=())
+def eval_nway(img: Tensor, txt: Tensor, txt_index: Optional[Tensor], n_way: int, normalize: bool,
+              log_scale: float) -> Tuple[Tensor, Tensor]:
+    """img [N*n_way, E] fp32, txt [C,E] fp32, txt_index [N] int32 | None -> (pred [N] i32, logits [N,n_way])."""
+    _need_cuda(img, txt)
+    img = _f32(img); txt = _f32(txt)
+    E = img.shape[-1]
+    N = img.numel() // (E * n_way)
+    if txt_index is not None:
+        txt_index = txt_index.to(torch.int32).contiguous()
+    pred = torch.empty((N,), dtype=torch.int32, device=img.device)
+    logits = torch.empty((N, n_way), dtype=torch.float32, device=img.device)
+    _cabi.call("cvcl_eval_nway_fwd", _p(img), _p(txt), _p(txt_index), N, n_way, E, int(normalize),
+               float(log_scale), _p(pred), _p(logits), _stream())
+    return pred, logits
+
+
+@eval_nway.register_fake
+def _(img, txt, txt_index, n_way, normalize, log_scale):
+    N = img.numel() // (img.shape[-1] * n_way)
+    return img.new_empty((N,), dtype=torch.int32), img.new_empty((N, n_way), dtype=torch.float32)
+
+
+# ----------------------------------------------------------------------------------------
+# K6 spatial "max" similarity (multimodal.py:771-780) -- see spatial ops below
+# ----------------------------------------------------------------------------------------
+def spatial_max_similarity(img_nhwc, tok, lens):
+    raise NotImplementedError("spatial max similarity kernel not built yet")
+
+
+def infonce_from_match(match, s):
+    raise NotImplementedError("spatial max similarity kernel not built yet")

@@ -175,7 +175,7 @@ def contrastive_step(f, ids, lens, W, b, table, s, embedding_type="flat", sim="m
     W = W.detach().to(dtype).clone().requires_grad_(True)
     b = b.detach().to(dtype).clone().requires_grad_(True)
     table = table.detach().to(dtype).clone().requires_grad_(True)
-    s = torch.as_tensor(s).detach().to(dtype).clone().requires_grad_(True)
+    s = torch.as_tensor(s, dtype=torch.float64).detach().to(dtype).clone().requires_grad_(True)
     f = f.detach().to(dtype).clone().requires_grad_(need_df)
     lpi, lpt, img, txt = forward(f, ids, lens, W, b, table, s, embedding_type, sim, normalize)
     res = infonce(lpi, lpt)
