@@ -1,0 +1,457 @@
+#!/usr/bin/env python
+"""bench.py -- contrastive fwd+bwd pairs/s of the CVCL hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload ...]
+
+Workload (default `flat512`, BASELINE.json configs[1]): CVCL flat-embedding contrastive train
+step, 512 synthetic pairs per GPU (max utterance length 25, E=512, K=2048, V=2350), bf16 operands
+with fp32 accumulation.  A "step" = text encoder + projection head + similarity/InfoNCE forward
+and the full backward (dW, db, d table, d s) for one batch.  With N > 1 GPUs every rank holds
+512 pairs and the InfoNCE runs over the global batch of 512*N pairs (NCCL all-gather of the
+features): weak scaling.
+
+One JSON line on stdout (rank 0):
+  value        pairs/s, inputs resident in HBM, CUDA-event timed per step, L2 flushed between steps
+  e2e          pairs/s through MultiModalModel.calculate_contrastive_loss(...) + backward() with
+               pinned HOST inputs (H2D inside the timed region) and a D2H read of the loss
+  roofline     dominant kernel of the step, event-timed in isolation: algorithmic bytes or flops
+               / duration vs MEASURED_PEAKS.json
+  cpu_baseline the oracle port (same ATen fp32 op sequence as the reference) on the host cores
+
+`--impl reference` times that CPU path alone (rank 0 only) and prints the same line shape.
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "contrastive fwd+bwd pairs/sec"
+E, K, V, L = 512, 2048, 2350, 25
+S_FIXED = float(-np.log(0.07))
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"],
+                    bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+# ----------------------------------------------------------------------------------------------
+def synth_batch(seed, B):
+    from oracle import cvcl_oracle as O
+    rng = np.random.RandomState(seed)
+    f = O.synth_trunk_features(rng, (B, K))
+    ids, lens = O.synth_tokens(rng, B, L, V)
+    return f, ids, lens
+
+
+def synth_weights():
+    from oracle import cvcl_oracle as O
+    return O.synth_weights(np.random.RandomState(0), E, K, V)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            c = [x.strip() for x in r.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+def build_model(dev, group=None):
+    import multimodal_baby_b200 as m
+    args = argparse.Namespace(embedding_type="flat", embedding_dim=E, normalize_features=True,
+                              fix_temperature=True, temperature=0.07, text_encoder="embedding")
+    vocab = {str(i): i for i in range(V)}
+    model = m.MultiModalModel(m.VisionEncoder(args, trunk="pooled"), m.TextEncoder(vocab, K, args), args)
+    W, b, table = synth_weights()
+    with torch.no_grad():
+        model.image_embed.model.fc.weight.copy_(torch.from_numpy(W))
+        model.image_embed.model.fc.bias.copy_(torch.from_numpy(b))
+        model.text_embed.embedding.weight.copy_(torch.from_numpy(table))
+    model.to(dev).train()
+    model.materialize_logits = False          # the trainer ignores them (multimodal_lit.py:241-266)
+    model.materialize_text_outputs = False
+    model.process_group = group
+    return m, model
+
+
+def step_api(model, x, ids, lens, world):
+    """the call a user makes: loss + backward (+ DDP-style gradient sum across ranks)."""
+    for p in model.parameters():
+        p.grad = None
+    out = model.calculate_contrastive_loss(x, ids, lens)
+    out[0].backward()
+    if world > 1:
+        import torch.distributed as dist
+        grads = [p.grad for p in model.parameters() if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat)
+    return out[0]
+
+
+def kernel_breakdown(m, dev, B, reps, flush, peaks):
+    """event-time each C-ABI kernel of the flat step in isolation (same shapes / buffers)."""
+    from multimodal_baby_b200 import _cabi
+    ops = m.ops
+    lib = _cabi.load()
+    f, ids, lens = synth_batch(1234, B)
+    W, b, table = synth_weights()
+    x16 = torch.from_numpy(f).to(dev).to(torch.bfloat16)
+    ids_d = torch.from_numpy(ids).to(dev); lens_d = torch.from_numpy(lens).to(dev)
+    W_d = torch.from_numpy(W).to(dev); b_d = torch.from_numpy(b).to(dev); tab_d = torch.from_numpy(table).to(dev)
+    bf = dict(dtype=torch.bfloat16, device=dev); f32 = dict(dtype=torch.float32, device=dev)
+    ldB = (B + 7) // 8 * 8
+    w16 = torch.empty((E, K), **bf); xc = torch.empty((B, K), **bf); x16t = torch.empty((K, ldB), **bf)
+    img16 = torch.empty((B, E), **bf); img16t = torch.empty((E, ldB), **bf)
+    txt16 = torch.empty((B, E), **bf); txt16t = torch.empty((E, ldB), **bf)
+    G0 = torch.empty((B, ldB), **bf); G1 = torch.empty((B, ldB), **bf); du16t = torch.empty((E, ldB), **bf)
+    invn_i = torch.empty((B,), **f32); invn_t = torch.empty((B,), **f32)
+    lse0 = torch.empty((B,), **f32); lse1 = torch.empty((B,), **f32); dm = torch.empty((B, E), **f32)
+    dW = torch.empty((E, K), **f32); db = torch.zeros((E,), **f32); dtab = torch.zeros((V, E), **f32)
+    ds = torch.zeros((1,), **f32); out5 = torch.zeros((8,), **f32)
+    ws = torch.empty((lib.cvcl_sim_workspace_bytes(B, B, B, B),), dtype=torch.uint8, device=dev)
+    p = ops._p
+    st = lambda: torch.cuda.current_stream().cuda_stream
+    sum_len = int(lens.sum())
+    dcoef = -2.0 * math.exp(S_FIXED) * 0.5 / B
+    C = _cabi.call
+    kernels = [
+        ("cast_w_f32_to_bf16", lambda: C("cvcl_cast_transpose", p(W_d), 0, p(w16), None, 1, E, K, K, K, 0, 0, 0, 0, st()),
+         dict(bytes=E * K * 6)),
+        ("cast_transpose_x", lambda: C("cvcl_cast_transpose", p(x16), 1, p(xc), p(x16t), 1, B, K, K, K, ldB, 0, 0, 0, st()),
+         dict(bytes=B * K * 6)),
+        ("K1_text_encoder_fwd", lambda: C("cvcl_text_encoder_fwd", p(ids_d), p(lens_d), p(tab_d), B, L, E, V, 1, 0, 1.0,
+                                          None, p(txt16), E, p(txt16t), ldB, p(invn_t), None, None, None, st()),
+         dict(bytes=8 * B * L + sum_len * E * 4 + B * E * 4)),
+        ("K2_head_proj_norm_fwd", lambda: C("cvcl_head_proj_norm_fwd", p(xc), K, p(w16), K, p(b_d), B, E, K, 1, None, 0,
+                                            p(img16), E, p(img16t), ldB, p(invn_i), st()),
+         dict(bytes=2 * B * K + 2 * E * K + 4 * B * E, flops=2 * B * K * E)),
+        ("K3K4_sim_infonce_fwd", lambda: C("cvcl_sim_infonce_fwd", p(img16), p(txt16), p(txt16), p(img16), E, B, B, B, B, E,
+                                           S_FIXED, 0, 1.0 / B, p(ws), p(lse0), p(lse1), None, None, p(out5), st()),
+         dict(bytes=4 * B * E * 2, flops=4 * B * B * E)),
+        ("K5a_sim_infonce_bwd_g", lambda: C("cvcl_sim_infonce_bwd_g", p(img16), p(txt16), p(txt16), p(img16), E, B, B, B, B, E,
+                                            S_FIXED, 0, 0.5 / B, p(lse0), p(lse1), p(lse1), p(lse0), p(G0), ldB, p(G1), ldB,
+                                            p(ds), st()),
+         dict(bytes=4 * B * E * 2 + 2 * B * B * 2, flops=4 * B * B * E)),
+        ("K5b_dimg_norm_bwd", lambda: C("cvcl_feat_grad_norm_bwd", p(G0), ldB, p(txt16t), ldB, B, E, B, p(img16), E, p(invn_i),
+                                        1, None, p(txt16), E, 0, dcoef, None, 0, p(du16t), ldB, p(db), st()),
+         dict(bytes=2 * B * B + 2 * B * E * 3 + 2 * B * E, flops=2 * B * B * E)),
+        ("K5b_dtxt_norm_bwd", lambda: C("cvcl_feat_grad_norm_bwd", p(G1), ldB, p(img16t), ldB, B, E, B, p(txt16), E, p(invn_t),
+                                        1, p(lens_d), p(img16), E, 0, dcoef, p(dm), E, None, 0, None, st()),
+         dict(bytes=2 * B * B + 2 * B * E * 3 + 4 * B * E, flops=2 * B * B * E)),
+        ("K5c_head_weight_grad", lambda: C("cvcl_head_weight_grad", p(du16t), ldB, p(x16t), ldB, E, K, B, p(dW), K, st()),
+         dict(bytes=2 * E * B + 2 * K * B + 4 * E * K, flops=2 * E * K * B)),
+        ("K5e_embedding_scatter_add", lambda: C("cvcl_embedding_scatter_add", p(ids_d), p(dm), p(dtab), B, L, E, V, 0, st()),
+         dict(bytes=8 * B * L + 4 * B * E + 2 * sum_len * E * 4)),
+    ]
+    rows = []
+    for name, fn, work in kernels:
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = statistics.mean(ts)
+        gbs = work["bytes"] / (ms * 1e-3) / 1e9
+        row = dict(kernel=name, ms=ms, ms_min=min(ts), bytes=work["bytes"], gb_s=gbs,
+                   hbm_frac=gbs / peaks["hbm_gbs"])
+        t_h = work["bytes"] / (peaks["hbm_gbs"] * 1e9)
+        bound = "hbm"
+        if "flops" in work:
+            tf = work["flops"] / (ms * 1e-3) / 1e12
+            row.update(flops=work["flops"], tflop_s=tf, tensor_frac=tf / peaks["bf16_tflops"])
+            if work["flops"] / (peaks["bf16_tflops"] * 1e12) > t_h:
+                bound = "tensor"
+        row["bound"] = bound
+        rows.append(row)
+    return rows
+
+
+def roofline_from(rows, peaks):
+    top = max(rows, key=lambda r: r["ms"])
+    if top["bound"] == "tensor":
+        return dict(kernel=top["kernel"], bound="tensor", achieved=top["tflop_s"], peak=peaks["bf16_tflops"],
+                    unit="TFLOP/s", frac=top["tensor_frac"], traffic=None, peak_source=peaks["source"],
+                    ms=top["ms"])
+    return dict(kernel=top["kernel"], bound="hbm", achieved=top["gb_s"], peak=peaks["hbm_gbs"], unit="GB/s",
+                frac=top["hbm_frac"], traffic=None, peak_source=peaks["source"], ms=top["ms"])
+
+
+def cpu_reference_step_fn(B):
+    """the oracle port: same ATen fp32 op sequence as the reference's calculate_contrastive_loss +
+    backward, on trunk-boundary features, all host threads."""
+    from oracle import cvcl_oracle as O
+    f, ids, lens = synth_batch(1234, B)
+    W, b, table = synth_weights()
+    tf, tids, tl = torch.from_numpy(f), torch.from_numpy(ids), torch.from_numpy(lens)
+    tW, tb, tt = torch.from_numpy(W), torch.from_numpy(b), torch.from_numpy(table)
+
+    def fn():
+        return O.contrastive_step(tf, tids, tl, tW, tb, tt, S_FIXED)["loss"]
+    return fn
+
+
+def time_cpu(B, steps, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    fn = cpu_reference_step_fn(B)
+    for _ in range(warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    dt = (time.perf_counter() - t0) / steps
+    return dt
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs-per-gpu", type=int, default=512)
+    ap.add_argument("--no-breakdown", action="store_true")
+    ap.add_argument("--breakdown-out", default="")
+    a = ap.parse_args()
+    if a.warmup < 3:
+        a.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    B = a.pairs_per_gpu
+    config = {"workload": "CVCL flat-embedding contrastive train step (fwd+bwd), %d synthetic pairs per GPU, "
+                          "global InfoNCE batch %d, L<=25, E=512, K=2048, V=2350" % (B, B * max(world, 1)),
+              "pairs_per_gpu": B, "global_batch": B * max(world, 1), "max_len": L,
+              "parallelism": "pairs sharded over %d rank(s), NCCL feature all-gather" % world if world > 1 else "single GPU",
+              "l2": "256 MiB write between timed steps (inputs are smaller than L2)"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        steps = a.steps
+        dt = time_cpu(B, steps, a.warmup)
+        val = B / dt
+        cores = os.cpu_count() or 1
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": a.gpus,
+            "steps": steps, "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port",
+                             "sample": "%d steps of the B=%d flat train step (oracle port of the reference's "
+                                       "ATen fp32 op sequence, torch %d threads)" % (steps, B, cores)},
+            "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return
+
+    assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device (no CPU fallback)"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    group = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    peaks = load_peaks()
+    m, model = build_model(dev, group)
+    from multimodal_baby_b200 import _cabi
+    lib = _cabi.load()
+
+    f, ids, lens = synth_batch(1234 + rank, B)
+    x_host = torch.from_numpy(f).to(torch.bfloat16).pin_memory()
+    ids_host = torch.from_numpy(ids).pin_memory(); lens_host = torch.from_numpy(lens).pin_memory()
+    x = x_host.to(dev); ids_d = ids_host.to(dev); lens_d = lens_host.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ device-timed value
+    fcw, fcb = model.image_embed.model.fc.weight, model.image_embed.model.fc.bias
+    table = model.text_embed.embedding.weight
+    graph = None
+    if world == 1:
+        def raw_step():
+            return m.ops.flat_contrastive_step(x, ids_d, lens_d, fcw, fcb, table, S_FIXED, True, True, False)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                raw_step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            g_out = raw_step()
+        run_step = graph.replay
+    else:
+        run_step = lambda: step_api(model, x, ids_d, lens_d, world)
+
+    sampler = ClockSampler(local_rank)
+    for _ in range(a.warmup):
+        flush.zero_(); run_step()
+    barrier()
+    if rank == 0:
+        sampler.start()
+    n0 = lib.cvcl_launch_count()
+    evs = []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for _ in range(a.steps):
+        flush.zero_()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); run_step(); e1.record()
+        evs.append((e0, e1))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    ms = statistics.mean(step_ms)
+    n_launch = lib.cvcl_launch_count() - n0
+    if graph is not None:       # replays launch the captured kernels without passing through the C ABI
+        n1 = lib.cvcl_launch_count(); raw_step(); per = lib.cvcl_launch_count() - n1
+        n_launch = per * a.steps
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = B * world / (ms * 1e-3)
+
+    # ------------------------------------------------------------------ e2e through the public API
+    e2e_steps = max(50, min(a.steps, 500))
+    for _ in range(3):
+        x.copy_(x_host, non_blocking=True); step_api(model, x, ids_d, lens_d, world).item()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        x.copy_(x_host, non_blocking=True)
+        ids_d.copy_(ids_host, non_blocking=True)
+        lens_d.copy_(lens_host, non_blocking=True)
+        loss_host = step_api(model, x, ids_d, lens_d, world).item()      # D2H read of the loss
+    barrier()
+    e2e_dt = (time.perf_counter() - t0) / e2e_steps
+    t = torch.tensor([e2e_dt], device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_dt = float(t.item())
+    h2d = x_host.numel() * 2 + ids_host.numel() * 8 + lens_host.numel() * 8
+
+    # ------------------------------------------------------------------ per-kernel roofline
+    rows, roof = [], None
+    if not a.no_breakdown and rank == 0:
+        rows = kernel_breakdown(m, dev, B, 50, flush, peaks)
+        roof = roofline_from(rows, peaks)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier(); dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1:
+        n_cpu = 40
+        cdt = time_cpu(B, n_cpu, 3)
+        cores = os.cpu_count() or 1
+        cpu = {"value": B / cdt, "unit": "pairs/s", "cores": cores, "kind": "port", "ms_per_step": cdt * 1e3,
+               "sample": "%d steps of the same B=%d flat train step (oracle port: the reference's ATen fp32 op "
+                         "sequence + autograd on CPU, %d torch threads)" % (n_cpu, B, cores)}
+    line = {
+        "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
+        "e2e": {"value": B * world / e2e_dt, "unit": "pairs/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "ms_per_step": e2e_dt * 1e3, "steps": e2e_steps,
+                "api": "MultiModalModel.calculate_contrastive_loss + backward"},
+        "gpu_launches": int(n_launch), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "timing": {"ms_min": min(step_ms), "ms_median": statistics.median(step_ms),
+                   "wall_s_incl_flush": t_wall, "cuda_graph": graph is not None},
+    }
+    if rows:
+        out = a.breakdown_out or os.path.join(ROOT, "gpurun_out", "bench_breakdown_n%d.json" % world)
+        try:
+            os.makedirs(os.path.dirname(out), exist_ok=True)
+            with open(out, "w") as fh:
+                json.dump({"peaks": peaks, "kernels": rows, "step_ms": ms}, fh, indent=1)
+        except OSError:
+            pass
+    print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier(); dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -34,6 +34,8 @@ extern "C" {
 
 int cvcl_abi_version(void);
 const char* cvcl_last_error(void);
+/* number of CUDA kernels this library has launched so far in the process (host-side counter). */
+unsigned long long cvcl_launch_count(void);
 
 /* ---- K1 text encoder, embedding branch ------------------------------------------------
  * replaces TextEncoder.forward (multimodal.py:496-503,575-584) + F.normalize (:743).
@@ -122,8 +124,9 @@ int cvcl_sim_logits_fwd(const void* img, const void* txt, int ld, int Ni, int Nt
 
 /* ---- K5 backward --------------------------------------------------------------------------
  * (a) dL/dlogits tiles from recomputed logits: Gs0 [M0, N0] (rows = local images) and
- *     Gs1 [M1, N1] (rows = local texts), bf16, pre-multiplied by exp(s) * coef where
- *     coef = upstream / (2 B_global); G = (softmax_row + softmax_col - 2 I)/(2B).
+ *     Gs1 [M1, N1] (rows = local texts), bf16, = exp(s) * coef * (softmax_row + softmax_col) with
+ *     coef = upstream / (2 B_global).  The -2*I term of G = (softmax_row + softmax_col - 2 I)/(2B)
+ *     is NOT in the bf16 matrix (it would dominate the rounding error); (b) adds it in fp32.
  *     lse_k0 [N0] = column LSEs seen by direction 0 (= all-gathered lse1), lse_k1 [N1] likewise.
  *     *dscale += sum G * logits (the logit_scale gradient, multimodal.py:711-715,783-787). */
 int cvcl_sim_infonce_bwd_g(const void* img_q, const void* txt_k, const void* txt_q, const void* img_k,
@@ -131,12 +134,14 @@ int cvcl_sim_infonce_bwd_g(const void* img_q, const void* txt_k, const void* txt
                            float coef, const float* lse_q0, const float* lse_k0, const float* lse_q1,
                            const float* lse_k1, void* Gs0, int ldg0, void* Gs1, int ldg1, float* dscale,
                            void* stream);
-/* (b) dFeat = Gs [M,Kc] . other_t[E,Kc]^T followed by the F.normalize backward in the epilogue.
- *     Outputs: out_f32 [M,E] (scaled by 1/row_len if given: d mean-embedding), out_bf16_t [E,M]
- *     (operand of the weight-gradient GEMM), dbias [E] += column sums. */
+/* (b) dFeat = Gs [M,Kc] . other_t[E,Kc]^T + diag_coef * diag_feat[m + diag_off] (the -2*I term of
+ *     G, applied in fp32; diag_feat may be NULL), followed by the F.normalize backward in the
+ *     epilogue.  Outputs: out_f32 [M,E] (scaled by 1/row_len if given: d mean-embedding),
+ *     out_bf16_t [E,M] (operand of the weight-gradient GEMM), dbias [E] += column sums. */
 int cvcl_feat_grad_norm_bwd(const void* Gs, int ldg, const void* other_t, int ld_other, int M, int E,
                             int Kc, const void* feat_bf16, int ld_feat, const float* inv_norm,
-                            int normalize, const int64_t* row_len, float* out_f32, int ld_f32,
+                            int normalize, const int64_t* row_len, const void* diag_feat, int ld_diag,
+                            int diag_off, float diag_coef, float* out_f32, int ld_f32,
                             void* out_bf16_t, int ld_t, float* dbias, void* stream);
 /* (c) dW [E,K] = du_t [E,M] . x_t [K,M]^T  (autograd of nn.Linear / 1x1 conv weight). */
 int cvcl_head_weight_grad(const void* du_t, int ld_du, const void* x_t, int ld_x, int E, int K, int M,

@@ -29,6 +29,7 @@ _L = c_int64
 PROTOTYPES = {
     "cvcl_abi_version": (c_int, []),
     "cvcl_last_error": (c_char_p, []),
+    "cvcl_launch_count": (ctypes.c_ulonglong, []),
     "cvcl_text_encoder_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _I, _P, _I, _P,
                                       _P, _P, _P, _P]),
     "cvcl_embedding_gather": (c_int, [_P, _P, _P, _I, _I, _I, _P]),
@@ -45,8 +46,8 @@ PROTOTYPES = {
     "cvcl_sim_logits_fwd": (c_int, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P]),
     "cvcl_sim_infonce_bwd_g": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _F, _P, _P, _P, _P,
                                        _P, _I, _P, _I, _P, _P]),
-    "cvcl_feat_grad_norm_bwd": (c_int, [_P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _I, _P, _I,
-                                        _P, _P]),
+    "cvcl_feat_grad_norm_bwd": (c_int, [_P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _I, _I, _F,
+                                        _P, _I, _P, _I, _P, _P]),
     "cvcl_head_weight_grad": (c_int, [_P, _I, _P, _I, _I, _I, _I, _P, _I, _P]),
     "cvcl_gemm_nt_f32out": (c_int, [_P, _I, _P, _I, _I, _I, _I, _F, _P, _I, _P]),
     "cvcl_flat_step_workspace_bytes": (c_size_t, [_I, _I, _I, _I, _I]),

@@ -50,12 +50,14 @@ extern "C" {
 
 int cvcl_abi_version(void) { return CVCL_ABI_VERSION; }
 const char* cvcl_last_error(void) { return last_error_buf(); }
+unsigned long long cvcl_launch_count(void) { return __atomic_load_n(&launch_counter(), __ATOMIC_RELAXED); }
 
 // ------------------------------------------------------------------------------------ K1
 int cvcl_text_encoder_fwd(const int64_t* ids, const int64_t* lens, const float* table,
                           int B, int L, int E, int V, int normalize, int per_token, float pool_scale,
                           float* feat_f32, void* feat_bf16, int ld_bf16, void* feat_bf16_t, int ld_t,
                           float* inv_norm, float* tok_f32, void* tok_bf16, int* status, void* stream) {
+    if (B == 0) return CVCL_OK;
     CVCL_REQUIRE(ids && lens && table, "text_encoder_fwd: null input");
     CVCL_REQUIRE(B >= 0 && L > 0 && V > 0, "text_encoder_fwd: bad shape B=%d L=%d V=%d", B, L, V);
     CVCL_REQUIRE(E > 0 && E % 4 == 0 && E <= 128 * kMaxVec, "text_encoder_fwd: E=%d must be a multiple of 4, <= %d", E, 128 * kMaxVec);
@@ -71,6 +73,7 @@ int cvcl_text_encoder_fwd(const int64_t* ids, const int64_t* lens, const float* 
     p.status = status;
     text_encoder_fwd_kernel<<<warps_grid(B), 256, 0, as_stream(stream)>>>(p);
     CVCL_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return CVCL_OK;
 }
 
@@ -82,6 +85,7 @@ int cvcl_embedding_gather(const int64_t* ids, const float* table, float* out, in
     embedding_gather_kernel<<<warps_grid(n_tok), 256, 0, as_stream(stream)>>>(
         reinterpret_cast<const long long*>(ids), table, out, n_tok, E, V);
     CVCL_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return CVCL_OK;
 }
 
@@ -94,6 +98,7 @@ int cvcl_embedding_scatter_add(const int64_t* ids, const float* g, float* dtable
     embedding_scatter_add_kernel<<<warps_grid(rows), 256, 0, as_stream(stream)>>>(
         reinterpret_cast<const long long*>(ids), g, dtable, B, L, E, V, per_token);
     CVCL_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return CVCL_OK;
 }
 
@@ -107,6 +112,7 @@ int cvcl_text_token_bwd(const int64_t* ids, const int64_t* lens, const float* ta
         reinterpret_cast<const long long*>(ids), reinterpret_cast<const long long*>(lens), table, dtok,
         dpool, pool_scale, dtable, B, L, E, V, normalize);
     CVCL_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return CVCL_OK;
 }
 
@@ -126,6 +132,7 @@ int cvcl_cast_transpose(const void* src, int src_is_bf16, void* dst, void* dst_t
             static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst),
             static_cast<__nv_bfloat16*>(dst_t), R, C, ld_src, ld_dst, ld_t, bs_src, bs_dst, bs_t);
     CVCL_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return CVCL_OK;
 }
 
@@ -140,6 +147,7 @@ int cvcl_embedding_bag_bwd(const int64_t* ids, const int64_t* lens, const float*
         reinterpret_cast<const long long*>(ids), reinterpret_cast<const long long*>(lens), g, feat, inv_norm,
         normalize, dtable, B, L, E, V);
     CVCL_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return CVCL_OK;
 }
 
@@ -154,6 +162,7 @@ int cvcl_rownorm_bwd(const float* g, const float* feat, const float* inv_norm, i
         g, feat, inv_norm, M, E, normalize, du_f32, static_cast<__nv_bfloat16*>(du_bf16), ld,
         static_cast<__nv_bfloat16*>(du_bf16_t), ld_t, dbias);
     CVCL_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return CVCL_OK;
 }
 
@@ -166,6 +175,7 @@ int cvcl_spatial_pool(const float* src, int B, int HW, int E, float* out_f32, vo
     spatial_pool_kernel<<<grid, 128, 0, as_stream(stream)>>>(src, B, HW, E, out_f32,
         static_cast<__nv_bfloat16*>(out_bf16), ld, static_cast<__nv_bfloat16*>(out_bf16_t), ld_t);
     CVCL_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return CVCL_OK;
 }
 
@@ -237,6 +247,7 @@ int cvcl_sim_infonce_fwd(const void* img_q, const void* txt_k, const void* txt_q
     fp.block_part = w.block_part; fp.ticket = w.ticket; fp.out = out5;
     infonce_finalize_kernel<<<ceil_div(M0 + M1, 256), 256, 0, as_stream(stream)>>>(fp);
     CVCL_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return CVCL_OK;
 }
 
@@ -281,7 +292,8 @@ int cvcl_sim_infonce_bwd_g(const void* img_q, const void* txt_k, const void* txt
 
 int cvcl_feat_grad_norm_bwd(const void* Gs, int ldg, const void* other_t, int ld_other, int M, int E,
                             int Kc, const void* feat_bf16, int ld_feat, const float* inv_norm,
-                            int normalize, const int64_t* row_len, float* out_f32, int ld_f32,
+                            int normalize, const int64_t* row_len, const void* diag_feat, int ld_diag,
+                            int diag_off, float diag_coef, float* out_f32, int ld_f32,
                             void* out_bf16_t, int ld_t, float* dbias, void* stream) {
     CVCL_REQUIRE(Gs && other_t, "feat_grad_norm_bwd: null operand");
     CVCL_REQUIRE(!normalize || (feat_bf16 && inv_norm), "feat_grad_norm_bwd: normalize needs feat and inv_norm");
@@ -294,6 +306,8 @@ int cvcl_feat_grad_norm_bwd(const void* Gs, int ldg, const void* other_t, int ld
     EpiNormBwd::Params ep{};
     ep.feat = static_cast<const __nv_bfloat16*>(feat_bf16); ep.ld_feat = ld_feat; ep.inv_norm = inv_norm;
     ep.normalize = normalize; ep.row_len = reinterpret_cast<const long long*>(row_len);
+    ep.diag_feat = static_cast<const __nv_bfloat16*>(diag_feat); ep.ld_diag = ld_diag;
+    ep.diag_off = diag_off; ep.diag_coef = diag_coef;
     ep.out_f32 = out_f32; ep.ld_f32 = ld_f32;
     ep.out_bf16_t = static_cast<__nv_bfloat16*>(out_bf16_t); ep.ld_t = ld_t; ep.dbias = dbias;
     return launch_gemm<kBN, kStages, EpiNormBwd>(op, gs, ep, cluster, as_stream(stream));
@@ -381,10 +395,11 @@ int cvcl_flat_contrastive_step(const void* x, int x_is_bf16, const int64_t* ids,
     if ((rc = cvcl_sim_infonce_bwd_g(f.img16, f.txt16, f.txt16, f.img16, E, B, B, B, B, E, log_scale, 0,
                                      0.5f / static_cast<float>(B), f.lse0, f.lse1, f.lse1, f.lse0,
                                      f.G0, f.ldB, f.G1, f.ldB, dscale, stream))) return rc;
+    const float dcoef = -2.f * expf(log_scale) * 0.5f / static_cast<float>(B);
     if ((rc = cvcl_feat_grad_norm_bwd(f.G0, f.ldB, f.txt16t, f.ldB, B, E, B, f.img16, E, f.invn_i, normalize,
-                                      nullptr, nullptr, 0, f.du16t, f.ldB, dbias, stream))) return rc;
+                                      nullptr, f.txt16, E, 0, dcoef, nullptr, 0, f.du16t, f.ldB, dbias, stream))) return rc;
     if ((rc = cvcl_feat_grad_norm_bwd(f.G1, f.ldB, f.img16t, f.ldB, B, E, B, f.txt16, E, f.invn_t, normalize,
-                                      lens, f.dm, E, nullptr, 0, nullptr, stream))) return rc;
+                                      lens, f.img16, E, 0, dcoef, f.dm, E, nullptr, 0, nullptr, stream))) return rc;
     if ((rc = cvcl_head_weight_grad(f.du16t, f.ldB, f.x16t, f.ldB, E, K, B, dW, K, stream))) return rc;
     if ((rc = cvcl_embedding_scatter_add(ids, f.dm, dtable, B, L, E, V, 0, stream))) return rc;
     return CVCL_OK;
@@ -400,6 +415,7 @@ int cvcl_eval_nway_fwd(const float* img, const float* txt, const int* txt_index,
     eval_nway_kernel<<<warps_grid(n_trials), 256, 0, as_stream(stream)>>>(
         img, txt, txt_index, n_trials, n_way, E, normalize, expf(log_scale), pred, logits);
     CVCL_CHECK_CUDA(cudaGetLastError());
+    count_launch();
     return CVCL_OK;
 }
 

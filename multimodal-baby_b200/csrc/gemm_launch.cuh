@@ -48,6 +48,7 @@ int launch_gemm(const GemmOperands& op, const GemmShape& gs, const typename Epi:
     cfg.attrs = at;
     cfg.numAttrs = 1;
     CVCL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], gs, ep));
+    count_launch();
     return CVCL_OK;
 }
 

@@ -349,7 +349,10 @@ struct EpiSimStats {
 
 // ---- backward, step 1: recompute the logits tile and emit dL/dlogits (bf16) --------------
 // G = (softmax_row + softmax_col - 2*I) / (2B)  (the autograd of
-// multimodal.py:808-810).  Stored pre-multiplied by exp(s)*coef so that dI = Gs*T, dT = Gs^T*I.
+// multimodal.py:808-810).  The bf16 matrix written here is Gs = exp(s)*coef*(softmax_row +
+// softmax_col) only: the -2*I term is ~B times larger than any other entry, and rounding it to
+// bf16 would dominate the error of every column sum of G (they cancel to ~0), so the consumer
+// (EpiNormBwd) adds it back in fp32.  dI = Gs*T - 2*exp(s)*coef*T_pos, dT likewise.
 // Direction z=1 runs with the operands swapped and therefore emits Gs^T directly.
 struct EpiGradG {
     static constexpr bool kClusterReduce = false;
@@ -389,9 +392,9 @@ struct EpiGradG {
             for (int j = 0; j < 32; ++j) {
                 const float x2 = v[j] * sc2;                       // logit * log2(e)
                 float g = exp2f(x2 - lq) + exp2f(x2 - lk[c + j]);
-                if (n + j == dcol) g -= 2.f;
-                g *= w;                                            // exp(s) * G * upstream
+                g *= w;                                            // exp(s) * coef * (P_row + P_col)
                 if (n + j < N) ds = fmaf(g, v[j], ds);             // G * logit = Gs * raw dot
+                if (n + j == dcol) ds = fmaf(-2.f * w, v[j], ds);  // the -2*I term, kept in fp32
                 v[j] = g;
             }
             if (vec_ok && n + 32 <= N) {
@@ -434,6 +437,8 @@ struct EpiNormBwd {
         const float* inv_norm;                      // [M]
         int normalize;
         const long long* row_len;                   // [M] int64 lengths (nullable): out *= 1/len
+        const __nv_bfloat16* diag_feat; int ld_diag; // positives of the other modality (nullable)
+        int diag_off; float diag_coef;              // acc[m,:] += diag_coef * diag_feat[m+diag_off,:]
         float* out_f32; int ld_f32;
         __nv_bfloat16* out_bf16_t; int ld_t;
         float* dbias;                               // [N] atomicAdd (nullable)
@@ -445,6 +450,8 @@ struct EpiNormBwd {
         float dot = 0.f;
         if (p.normalize) {
             const __nv_bfloat16* frow = p.feat + static_cast<size_t>(m < M ? m : 0) * p.ld_feat;
+            const __nv_bfloat16* drow = p.diag_feat
+                ? p.diag_feat + static_cast<size_t>((m < M ? m : 0) + p.diag_off) * p.ld_diag : nullptr;
 #pragma unroll 1
             for (int c = 0; c < BN; c += 32) {
                 float v[32];
@@ -452,8 +459,13 @@ struct EpiNormBwd {
                 const int n = cx.n0 + c;
                 if (m >= M) continue;
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (n + j < N) dot = fmaf(__bfloat162float(frow[n + j]), v[j], dot);
+                for (int j = 0; j < 32; ++j) {
+                    if (n + j < N) {
+                        float a = v[j];
+                        if (drow) a = fmaf(p.diag_coef, __bfloat162float(drow[n + j]), a);
+                        dot = fmaf(__bfloat162float(frow[n + j]), a, dot);
+                    }
+                }
             }
         }
         reinterpret_cast<float*>(cx.scratch)[cx.row] = dot;
@@ -470,6 +482,8 @@ struct EpiNormBwd {
         const float inv = (p.normalize && rv) ? __ldg(p.inv_norm + m) : 1.f;
         const float rs = (p.row_len && rv) ? 1.f / static_cast<float>(p.row_len[m]) : 1.f;
         const __nv_bfloat16* frow = p.feat + static_cast<size_t>(rv ? m : 0) * p.ld_feat;
+        const __nv_bfloat16* drow = p.diag_feat
+            ? p.diag_feat + static_cast<size_t>((rv ? m : 0) + p.diag_off) * p.ld_diag : nullptr;
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
             float v[32];
@@ -481,6 +495,7 @@ struct EpiNormBwd {
                 float du = 0.f;
                 if (rv && n + j < N) {
                     du = v[j];
+                    if (drow) du = fmaf(p.diag_coef, __bfloat162float(drow[n + j]), du);
                     if (p.normalize) du = (du - __bfloat162float(frow[n + j]) * dot) * inv;
                 }
                 v[j] = du;

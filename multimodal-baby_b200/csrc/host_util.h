@@ -88,4 +88,11 @@ inline int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// number of kernels this library has launched (all threads); read through cvcl_launch_count()
+inline unsigned long long& launch_counter() {
+    static unsigned long long n = 0;
+    return n;
+}
+inline void count_launch() { __atomic_fetch_add(&launch_counter(), 1ull, __ATOMIC_RELAXED); }
+
 }  // namespace cvcl

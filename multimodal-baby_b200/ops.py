@@ -481,10 +481,11 @@ def sim_infonce_bwd(img_q: Tensor, txt_k: Tensor, txt_q: Tensor, img_k: Tensor, 
     _, img_k_t = to_bf16_pair(img_k, True)           # [E, pad8(N1)]
     dimg = torch.empty((M0, E), dtype=torch.float32, device=dev)
     dtxt = torch.empty((M1, E), dtype=torch.float32, device=dev)
+    dcoef = -2.0 * math.exp(log_scale) * coef            # the -2*I term of G, applied in fp32
     _cabi.call("cvcl_feat_grad_norm_bwd", _p(G0), ld0, _p(txt_k_t), ld0, M0, E, N0, None, 0, None, 0, None,
-               _p(dimg), E, None, 0, None, _stream())
+               _p(txt_k), E, int(diag_off), dcoef, _p(dimg), E, None, 0, None, _stream())
     _cabi.call("cvcl_feat_grad_norm_bwd", _p(G1), ld1, _p(img_k_t), ld1, M1, E, N1, None, 0, None, 0, None,
-               _p(dtxt), E, None, 0, None, _stream())
+               _p(img_k), E, int(diag_off), dcoef, _p(dtxt), E, None, 0, None, _stream())
     return dimg, dtxt, ds
 
 
