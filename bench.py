@@ -144,10 +144,8 @@ def step_api(model, x, ids, lens, world):
     out = model.calculate_contrastive_loss(x, ids, lens)
     out[0].backward()
     if world > 1:
-        import torch.distributed as dist
-        grads = [p.grad for p in model.parameters() if p.grad is not None]
-        flat = torch.cat([g.reshape(-1) for g in grads])
-        dist.all_reduce(flat)
+        from multimodal_baby_b200 import sharding
+        sharding.allreduce_gradients(model.parameters(), model.process_group)
     return out[0]
 
 

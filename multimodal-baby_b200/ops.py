@@ -497,53 +497,27 @@ def _(img_q, txt_k, txt_q, img_k, log_scale, diag_off, coef, lse_q0, lse_k0, lse
 
 class _SimInfoNCE(torch.autograd.Function):
     """Symmetric InfoNCE on (local) features; with a process group the features are all-gathered
-    and each rank evaluates its row block and column block.  Returns the five
-    GLOBAL scalars (identical on all ranks).  Gradients: d img / d txt for the local pairs are
-    complete; d s is summed over ranks (all-reduce) so every rank holds the full value."""
+    and each rank evaluates its row block and column block (sharding.py).
+    Returns the five GLOBAL scalars (identical on all ranks).  Gradients: d img / d txt for the
+    local pairs are complete; d s is summed over ranks so every rank holds the full value."""
 
     @staticmethod
     def forward(ctx, img, txt, s, group):
-        import torch.distributed as dist
-        world = dist.get_world_size(group) if group is not None else 1
-        rank = dist.get_rank(group) if group is not None else 0
-        ls = float(s)
+        from . import sharding
         i16, _ = to_bf16_pair(img, False)
         t16, _ = to_bf16_pair(txt, False)
-        b = i16.shape[0]
-        if world > 1:
-            i_all = torch.empty((world * b, i16.shape[1]), dtype=torch.bfloat16, device=i16.device)
-            t_all = torch.empty_like(i_all)
-            dist.all_gather_into_tensor(i_all, i16, group=group)
-            dist.all_gather_into_tensor(t_all, t16, group=group)
-        else:
-            i_all, t_all = i16, t16
-        Bg = world * b
-        out5, lse0, lse1, a0, a1 = sim_infonce_fwd(i16, t_all, t16, i_all, ls, rank * b, 1.0 / Bg)
-        out5 = out5.clone()
-        if world > 1:
-            dist.all_reduce(out5, group=group)
-        ctx.save_for_backward(i16, t16, i_all, t_all, lse0, lse1)
-        ctx.meta = (ls, rank, b, world, group, img.dtype, txt.dtype, torch.is_tensor(s))
+        out5, saved, (a0, a1) = sharding.infonce_forward(i16, t16, float(s), group, sim_infonce_fwd)
+        ctx.saved = saved
+        ctx.group = group
+        ctx.meta = (img.dtype, txt.dtype, torch.is_tensor(s))
         ctx.mark_non_differentiable(a0, a1)
         return out5[0], out5[1], out5[2], out5[3], out5[4], a0, a1
 
     @staticmethod
     def backward(ctx, gloss, *unused):
-        import torch.distributed as dist
-        i16, t16, i_all, t_all, lse0, lse1 = ctx.saved_tensors
-        ls, rank, b, world, group, idt, tdt, s_is_tensor = ctx.meta
-        if world > 1:
-            lse0_all = torch.empty((world * b,), dtype=torch.float32, device=lse0.device)
-            lse1_all = torch.empty_like(lse0_all)
-            dist.all_gather_into_tensor(lse0_all, lse0, group=group)
-            dist.all_gather_into_tensor(lse1_all, lse1, group=group)
-        else:
-            lse0_all, lse1_all = lse0, lse1
-        Bg = world * b
-        dimg, dtxt, ds = sim_infonce_bwd(i16, t_all, t16, i_all, ls, rank * b, 0.5 / Bg,
-                                         lse0, lse1_all, lse1, lse0_all)
-        if world > 1:
-            dist.all_reduce(ds, group=group)
+        from . import sharding
+        idt, tdt, s_is_tensor = ctx.meta
+        dimg, dtxt, ds = sharding.infonce_backward(ctx.saved, ctx.group, sim_infonce_bwd)
         dimg = (dimg * gloss).to(idt)
         dtxt = (dtxt * gloss).to(tdt)
         ds_out = (ds[0] * gloss) if (s_is_tensor and ctx.needs_input_grad[2]) else None

@@ -1,0 +1,58 @@
+"""torchrun target: sharded global-batch InfoNCE (NCCL all-gather over NVLink) == the single-GPU
+global-batch result, and the full sharded model step == single-GPU step on the concatenated batch.
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/sharded_check.py [B_global]
+Prints `SHARDED_OK ...` on rank 0 on success, raises otherwise."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, torch.distributed as dist
+
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
+dev = torch.device("cuda", lr); torch.cuda.set_device(dev)
+dist.init_process_group("nccl", device_id=dev)
+import multimodal_baby_b200 as m
+from bench import build_model, synth_batch, step_api, S_FIXED, E
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+b = B // world
+g = torch.Generator().manual_seed(11)
+img = torch.nn.functional.normalize(torch.randn(B, E, generator=g), dim=1).to(dev)
+txt = torch.nn.functional.normalize(torch.randn(B, E, generator=g), dim=1).to(dev)
+sl = slice(rank * b, (rank + 1) * b)
+
+# (1) feature-level op: sharded vs single-device
+def run(i, t, group):
+    i = i.clone().requires_grad_(True); t = t.clone().requires_grad_(True)
+    s = torch.tensor(S_FIXED, device=dev, requires_grad=True)
+    out = m.ops.sim_infonce(i, t, s, group)
+    out[0].backward()
+    return [o.detach() for o in out[:5]], i.grad, t.grad, s.grad, out[5]
+ref5, rdi, rdt, rds, rarg = run(img, txt, None)
+got5, gdi, gdt, gds, garg = run(img[sl], txt[sl], dist.group.WORLD)
+for a, c in zip(ref5, got5):
+    assert abs(a.item() - c.item()) <= 2e-6 * max(1.0, abs(a.item())), (a.item(), c.item())
+def rel(a, c): return float((a - c).norm() / c.norm())
+assert rel(gdi, rdi[sl]) <= 1e-5, rel(gdi, rdi[sl])
+assert rel(gdt, rdt[sl]) <= 1e-5, rel(gdt, rdt[sl])
+assert abs(gds.item() - rds.item()) <= 1e-4 * abs(rds.item()) + 1e-6, (gds.item(), rds.item())
+assert torch.equal(garg, rarg[sl])
+
+# (2) whole model step through the public API: sharded (512*world pairs) vs single GPU
+_, model_s = build_model(dev, dist.group.WORLD)
+_, model_1 = build_model(dev, None)
+model_1.train_path = "ops"
+fs, ids, lens = zip(*[synth_batch(1234 + r, 512) for r in range(world)])
+x_all = torch.from_numpy(np.concatenate(fs)).to(dev).to(torch.bfloat16)
+ids_all = torch.from_numpy(np.concatenate(ids)).to(dev); lens_all = torch.from_numpy(np.concatenate(lens)).to(dev)
+l1 = step_api(model_1, x_all, ids_all, lens_all, 1)
+ls = step_api(model_s, x_all[rank * 512:(rank + 1) * 512], ids_all[rank * 512:(rank + 1) * 512],
+              lens_all[rank * 512:(rank + 1) * 512], world)
+assert abs(l1.item() - ls.item()) <= 2e-6 * abs(l1.item()), (l1.item(), ls.item())
+for (n, p1), (_, ps) in zip(model_1.named_parameters(), model_s.named_parameters()):
+    if p1.grad is None:
+        continue
+    r = rel(ps.grad, p1.grad)
+    assert r <= 2e-3, (n, r)
+torch.cuda.synchronize(); dist.barrier()
+if rank == 0:
+    print("SHARDED_OK world=%d B=%d loss=%.6f model_loss=%.6f" % (world, B, got5[0].item(), ls.item()))
+dist.destroy_process_group()
