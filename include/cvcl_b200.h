@@ -162,6 +162,26 @@ int cvcl_flat_contrastive_step(const void* x, int x_is_bf16, const int64_t* ids,
                                float* dW, float* dbias, float* dtable, float* dscale,
                                int* status, void* stream);
 
+/* ---- K6 spatial "max" similarity --------------------------------------------------------------
+ * replaces multimodal.py:771-780 (einsum 'iehw,tle->itlhw' + amax over (h,w) + sum over l / len)
+ * without materialising the [B,B,L,H,W] tensor.  tok [Bt*L, E] bf16 (per-token normalised text
+ * features), img [Bi*HW, E] bf16 (NHWC location features).  match [Bi,Bt] fp32; the argmax
+ * location per (i,t,l) is saved as uint8 in both [Bi, Bt*L] and [Bt*L, Bi] layouts. */
+int cvcl_spatial_max_fwd(const void* tok, const void* img, const int64_t* lens, int Bt, int L, int Bi, int HW,
+                         int E, float* match, unsigned char* amax_it, unsigned char* amax_ti, void* stream);
+/* autograd of the above: dtok [Bt*L,E] and dimg [Bi*HW,E] fp32 (either may be NULL) from
+ * gmatch = dL/dmatch [Bi,Bt].  ids [Bt*L] (nullable) lets pad tokens be skipped. */
+int cvcl_spatial_max_bwd(const float* gmatch, const int64_t* lens, const int64_t* ids,
+                         const unsigned char* amax_it, const unsigned char* amax_ti, const void* tok,
+                         const void* img, int Bt, int L, int Bi, int HW, int E, float* dtok, float* dimg,
+                         void* stream);
+/* symmetric InfoNCE statistics (multimodal.py:801-818) from a materialised match [B,B] fp32 and
+ * their backward: dmatch = exp(s) * G, *dscale += sum G * logits.  workspace as for K3+K4. */
+int cvcl_match_infonce_fwd(const float* match, int B, float log_scale, float inv_rows, void* workspace,
+                           float* lse0, float* lse1, int* argmax0, int* argmax1, float* out5, void* stream);
+int cvcl_match_infonce_bwd(const float* match, int B, float log_scale, float coef, const float* lse0,
+                           const float* lse1, float* dmatch, float* dscale, void* stream);
+
 /* ---- K7 n-way evaluation (fp32, bit-exact argmax contract) -----------------------------------
  * replaces the per-trial loop of eval.py:196-214 / multimodal_lit.py:466-511.
  * img [n_trials*n_way, E] fp32 embeddings (target first), txt [C,E] fp32 label embeddings,

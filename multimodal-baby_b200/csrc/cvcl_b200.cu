@@ -405,6 +405,80 @@ int cvcl_flat_contrastive_step(const void* x, int x_is_bf16, const int64_t* ids,
     return CVCL_OK;
 }
 
+// ------------------------------------------------------------------------------------ K6 spatial max
+int cvcl_spatial_max_fwd(const void* tok, const void* img, const int64_t* lens, int Bt, int L, int Bi, int HW,
+                         int E, float* match, unsigned char* amax_it, unsigned char* amax_ti, void* stream) {
+    CVCL_REQUIRE(tok && img && lens && match && amax_it && amax_ti, "spatial_max_fwd: null pointer");
+    CVCL_REQUIRE(Bt > 0 && Bi > 0 && E > 0, "spatial_max_fwd: bad shape");
+    CVCL_REQUIRE(L >= 1 && L <= kBM && HW >= 1 && HW <= 256, "spatial_max_fwd: need L<=128, HW<=256 (L=%d HW=%d)", L, HW);
+    constexpr int BN = 256;
+    EpiSpatialMax::Params ep{};
+    ep.L = L; ep.HW = HW; ep.TPM = kBM / L; ep.IPN = BN / HW; ep.Bt = Bt; ep.Bi = Bi;
+    if (ep.IPN > EpiSpatialMax::kMaxIPN) ep.IPN = EpiSpatialMax::kMaxIPN;
+    ep.lens = reinterpret_cast<const long long*>(lens); ep.match = match;
+    ep.amax_it = amax_it; ep.amax_ti = amax_ti;
+    GemmOperands op{}; op.A[0] = tok; op.ld_a[0] = E; op.B[0] = img; op.ld_b[0] = E; op.ndir = 1;
+    GemmShape gs{}; gs.M[0] = gs.M[1] = Bt * L; gs.N[0] = gs.N[1] = Bi * HW; gs.K = E;
+    gs.m_stride = ep.TPM * L; gs.n_stride = ep.IPN * HW;
+    return launch_gemm<BN, 4, EpiSpatialMax>(op, gs, ep, 1, as_stream(stream));
+}
+
+int cvcl_spatial_max_bwd(const float* gmatch, const int64_t* lens, const int64_t* ids,
+                         const unsigned char* amax_it, const unsigned char* amax_ti, const void* tok,
+                         const void* img, int Bt, int L, int Bi, int HW, int E, float* dtok, float* dimg,
+                         void* stream) {
+    CVCL_REQUIRE(gmatch && lens && amax_it && amax_ti && tok && img, "spatial_max_bwd: null pointer");
+    CVCL_REQUIRE(E % 8 == 0 && E <= 1024, "spatial_max_bwd: E=%d must be a multiple of 8, <= 1024", E);
+    if (dtok) {
+        spatial_max_dtok_kernel<<<warps_grid(static_cast<long long>(Bt) * L), 256, 0, as_stream(stream)>>>(
+            gmatch, reinterpret_cast<const long long*>(lens), reinterpret_cast<const long long*>(ids), amax_ti,
+            static_cast<const __nv_bfloat16*>(img), dtok, Bi, Bt, L, HW, E);
+        CVCL_CHECK_CUDA(cudaGetLastError());
+        count_launch();
+    }
+    if (dimg) {
+        spatial_max_dimg_kernel<<<warps_grid(static_cast<long long>(Bi) * HW), 256, 0, as_stream(stream)>>>(
+            gmatch, reinterpret_cast<const long long*>(lens), amax_it, static_cast<const __nv_bfloat16*>(tok),
+            dimg, Bi, Bt, L, HW, E);
+        CVCL_CHECK_CUDA(cudaGetLastError());
+        count_launch();
+    }
+    return CVCL_OK;
+}
+
+int cvcl_match_infonce_fwd(const float* match, int B, float log_scale, float inv_rows, void* workspace,
+                           float* lse0, float* lse1, int* argmax0, int* argmax1, float* out5, void* stream) {
+    CVCL_REQUIRE(match && workspace && lse0 && lse1 && out5, "match_infonce_fwd: null pointer");
+    CVCL_REQUIRE(B > 0, "match_infonce_fwd: bad shape");
+    SimWs w = carve_sim_ws(workspace, B, B, B, B);
+    CVCL_CHECK_CUDA(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned int), as_stream(stream)));
+    match_stats_kernel<<<warps_grid(2ll * B), 256, 0, as_stream(stream)>>>(
+        match, B, B, expf(log_scale), w.part[0], w.part[1], w.diag[0], w.diag[1]);
+    CVCL_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    FinalizeParams fp{};
+    for (int z = 0; z < 2; ++z) {
+        fp.part[z] = w.part[z]; fp.m_pad[z] = w.m_pad[z]; fp.n_tiles[z] = 1; fp.diag[z] = w.diag[z];
+        fp.diag_off[z] = 0; fp.M[z] = B;
+    }
+    fp.lse[0] = lse0; fp.lse[1] = lse1; fp.argmax[0] = argmax0; fp.argmax[1] = argmax1;
+    fp.inv_rows = inv_rows; fp.block_part = w.block_part; fp.ticket = w.ticket; fp.out = out5;
+    infonce_finalize_kernel<<<ceil_div(2 * B, 256), 256, 0, as_stream(stream)>>>(fp);
+    CVCL_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return CVCL_OK;
+}
+
+int cvcl_match_infonce_bwd(const float* match, int B, float log_scale, float coef, const float* lse0,
+                           const float* lse1, float* dmatch, float* dscale, void* stream) {
+    CVCL_REQUIRE(match && lse0 && lse1 && dmatch, "match_infonce_bwd: null pointer");
+    match_grad_kernel<<<ceil_div(B * B, 256), 256, 0, as_stream(stream)>>>(
+        match, B, B, expf(log_scale), coef, lse0, lse1, dmatch, dscale);
+    CVCL_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return CVCL_OK;
+}
+
 // ------------------------------------------------------------------------------------ K7
 int cvcl_eval_nway_fwd(const float* img, const float* txt, const int* txt_index, int n_trials, int n_way,
                        int E, int normalize, float log_scale, int* pred, float* logits, void* stream) {

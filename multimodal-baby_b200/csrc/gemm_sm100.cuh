@@ -532,4 +532,72 @@ struct EpiNormBwd {
     }
 };
 
+
+// ---- spatial "max" similarity (multimodal.py:771-780) -----------------------------------------
+// GEMM rows = text tokens (t,l), columns = image locations (i,hw).  A 128 x 256 tile holds
+// TPM = 128/L whole texts and IPN = 256/HW whole images (tile origins step by TPM*L / IPN*HW).
+// Thread = one token row: running max + argmax over each image's HW columns (in-thread), then the
+// L token maxima of a text are summed through shared memory and divided by len[t]:
+//   match[i,t] = sum_l max_hw <img[i,hw,:], tok[t,l,:]> / len[t]       (never stores [B,B,L,HW])
+// The argmax location is kept (uint8, both [i][t,l] and [t,l][i] layouts) for the backward.
+struct EpiSpatialMax {
+    static constexpr bool kClusterReduce = false;
+    static constexpr int kMaxIPN = 16;
+    static constexpr int kScratchBytes = kBM * kMaxIPN * 4;
+    struct Params {
+        int L, HW, TPM, IPN;          // tokens per text, locations per image, texts / images per tile
+        int Bt, Bi;
+        const long long* lens;        // [Bt]
+        float* match;                 // [Bi, Bt]
+        unsigned char* amax_it;       // [Bi, Bt*L]
+        unsigned char* amax_ti;       // [Bt*L, Bi]
+    };
+    template <int BN>
+    static __device__ __forceinline__ void phase1(const EpiCtx& cx, const GemmShape& gs, const Params& p) {
+        float* vals = reinterpret_cast<float*>(cx.scratch);          // [128][IPN]
+        const int r = cx.row;
+        const int grow = cx.m0 + r;                                  // global token row
+        const bool row_ok = r < p.TPM * p.L && grow < p.Bt * p.L;
+        const int img0 = cx.tile_n * p.IPN;                          // first image of this tile
+        int q = 0, nextb = p.HW, hw = 0;
+        float best = -INFINITY; int barg = 0;
+        const int ncols = p.IPN * p.HW;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            float v[32];
+            ptx::tmem_ld_32x32(cx.tmem_row + c, v);
+            if (c >= ncols) continue;                                // warp-uniform
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int col = c + j;
+                if (col < ncols) {
+                    if (v[j] > best) { best = v[j]; barg = hw; }     // strict >: first maximum
+                    ++hw;
+                    if (col + 1 == nextb) {                          // end of image q's segment
+                        vals[r * p.IPN + q] = best;
+                        const int i = img0 + q;
+                        if (row_ok && i < p.Bi) {
+                            p.amax_it[static_cast<size_t>(i) * (p.Bt * p.L) + grow] = static_cast<unsigned char>(barg);
+                            p.amax_ti[static_cast<size_t>(grow) * p.Bi + i] = static_cast<unsigned char>(barg);
+                        }
+                        ++q; nextb += p.HW; hw = 0; best = -INFINITY; barg = 0;
+                    }
+                }
+            }
+        }
+        ptx::named_bar_sync(1, kEpiThreads);
+        if (cx.epi_tid < p.TPM * p.IPN) {
+            const int tt = cx.epi_tid / p.IPN, qq = cx.epi_tid % p.IPN;
+            const int t = cx.tile_m * p.TPM + tt, i = img0 + qq;
+            if (t < p.Bt && i < p.Bi) {
+                float s = 0.f;
+                for (int l = 0; l < p.L; ++l) s += vals[(tt * p.L + l) * p.IPN + qq];
+                p.match[static_cast<size_t>(i) * p.Bt + t] = s / static_cast<float>(p.lens[t]);
+            }
+        }
+    }
+    template <int BN>
+    static __device__ __forceinline__ void phase2(const EpiCtx&, const GemmShape&, const Params&) {}
+};
+
 }  // namespace cvcl

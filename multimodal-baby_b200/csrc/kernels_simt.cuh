@@ -519,4 +519,170 @@ __global__ void __launch_bounds__(128) spatial_pool_kernel(const float* src, int
     }
 }
 
+
+// --------------------------------------------------------------------------------------
+// spatial "max" similarity backward (SIMT gather form, v1).  g = dL/dmatch [Bi,Bt];
+// coef[i,t] = g[i,t] / len[t].  With hw* = argmax location saved by the forward:
+//   dtok[t,l,:]  = sum_i    coef[i,t] * img[i, hw*(i,t,l), :]
+//   dimg[i,hw,:] = sum_{t,l : hw*(i,t,l) = hw} coef[i,t] * tok[t,l,:]
+// (autograd of einsum + amax + sum + div, multimodal.py:775-780; ties only occur for all-zero pad
+// tokens, whose contributions vanish).  One warp per output row, bf16 row gathers from L2.
+// --------------------------------------------------------------------------------------
+__device__ __forceinline__ void fma_bf16x8(float* acc, uint4 q, float c) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float2 f = __bfloat1622float2(h[k]);
+        acc[2 * k] = fmaf(c, f.x, acc[2 * k]);
+        acc[2 * k + 1] = fmaf(c, f.y, acc[2 * k + 1]);
+    }
+}
+
+__global__ void __launch_bounds__(256) spatial_max_dtok_kernel(const float* g, const long long* lens,
+                                                               const long long* ids,
+                                                               const unsigned char* amax_ti,
+                                                               const __nv_bfloat16* img, float* dtok,
+                                                               int Bi, int Bt, int L, int HW, int E) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= Bt * L) return;
+    const int t = warp / L;
+    const int nv = E >> 3;                        // uint4 (8 bf16) chunks per row; lane handles nv/32 (E%256==0 fast)
+    float acc[4][8];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[c][k] = 0.f;
+    if (ids == nullptr || __ldg(ids + warp) != 0) {
+        const float invlen = 1.f / static_cast<float>(__ldg(lens + t));
+        for (int i0 = 0; i0 < Bi; i0 += 32) {
+            const int ii = i0 + lane;
+            const int a_l = ii < Bi ? amax_ti[static_cast<size_t>(warp) * Bi + ii] : 0;
+            const float c_l = ii < Bi ? __ldg(g + static_cast<size_t>(ii) * Bt + t) * invlen : 0.f;
+            const int n = min(32, Bi - i0);
+            for (int k = 0; k < n; ++k) {
+                const int a = __shfl_sync(0xffffffffu, a_l, k);
+                const float c = __shfl_sync(0xffffffffu, c_l, k);
+                const uint4* src = reinterpret_cast<const uint4*>(img + (static_cast<size_t>(i0 + k) * HW + a) * E);
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc)
+                    if (cc * 32 + lane < nv) fma_bf16x8(acc[cc], __ldg(src + cc * 32 + lane), c);
+            }
+        }
+    }
+    float* dst = dtok + static_cast<size_t>(warp) * E;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        if (cc * 32 + lane < nv) {
+            float4* d4 = reinterpret_cast<float4*>(dst + (cc * 32 + lane) * 8);
+            d4[0] = make_float4(acc[cc][0], acc[cc][1], acc[cc][2], acc[cc][3]);
+            d4[1] = make_float4(acc[cc][4], acc[cc][5], acc[cc][6], acc[cc][7]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) spatial_max_dimg_kernel(const float* g, const long long* lens,
+                                                               const unsigned char* amax_it,
+                                                               const __nv_bfloat16* tok, float* dimg,
+                                                               int Bi, int Bt, int L, int HW, int E) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= Bi * HW) return;
+    const int i = warp / HW, hw = warp % HW;
+    const int nv = E >> 3;
+    float acc[4][8];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[c][k] = 0.f;
+    const int ntl = Bt * L;
+    const unsigned char* arow = amax_it + static_cast<size_t>(i) * ntl;
+    for (int tl0 = 0; tl0 < ntl; tl0 += 32) {
+        const int tl = tl0 + lane;
+        const bool hit = tl < ntl && arow[tl] == hw;
+        unsigned mask = __ballot_sync(0xffffffffu, hit);
+        while (mask) {
+            const int k = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int x = tl0 + k, t = x / L;
+            const float c = __ldg(g + static_cast<size_t>(i) * Bt + t) / static_cast<float>(__ldg(lens + t));
+            const uint4* src = reinterpret_cast<const uint4*>(tok + static_cast<size_t>(x) * E);
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+                if (cc * 32 + lane < nv) fma_bf16x8(acc[cc], __ldg(src + cc * 32 + lane), c);
+        }
+    }
+    float* dst = dimg + static_cast<size_t>(warp) * E;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        if (cc * 32 + lane < nv) {
+            float4* d4 = reinterpret_cast<float4*>(dst + (cc * 32 + lane) * 8);
+            d4[0] = make_float4(acc[cc][0], acc[cc][1], acc[cc][2], acc[cc][3]);
+            d4[1] = make_float4(acc[cc][4], acc[cc][5], acc[cc][6], acc[cc][7]);
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------
+// InfoNCE statistics from a MATERIALISED similarity matrix match [Bi,Bt] (spatial "max" path:
+// the [B,B] matrix is small next to the B*B*L*HW contraction that produced it).
+// One warp per row (z=0: image rows) or per column (z=1: text rows of match^T); writes the same
+// RowStat partials (n_tiles = 1) that infonce_finalize_kernel merges.
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) match_stats_kernel(const float* match, int Bi, int Bt, float scale,
+                                                          RowStat* part0, RowStat* part1, float* diag0,
+                                                          float* diag1) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= Bi + Bt) return;
+    const int z = warp < Bi ? 0 : 1;
+    const int m = z ? warp - Bi : warp;
+    const int n = z ? Bi : Bt;
+    const size_t stride = z ? Bt : 1;
+    const float* base = z ? match + m : match + static_cast<size_t>(m) * Bt;
+    float mx = -INFINITY; int arg = 0x7fffffff;
+    for (int j = lane; j < n; j += 32) {
+        const float x = base[j * stride] * scale;
+        if (x > mx) { mx = x; arg = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+    }
+    float l = 0.f, a = 0.f;
+    for (int j = lane; j < n; j += 32) {
+        const float x = base[j * stride] * scale;
+        const float e = __expf(x - mx);
+        l += e; a = fmaf(e, x, a);
+    }
+    l = warp_sum(l); a = warp_sum(a);
+    if (lane == 0) {
+        RowStat rs; rs.m = mx; rs.l = l; rs.a = a; rs.arg = arg;
+        (z ? part1 : part0)[m] = rs;
+        if (m < n) (z ? diag1 : diag0)[m] = base[m * stride] * scale;
+    }
+}
+
+// d loss / d match = scale * G,  G = coef * (exp(x - lse0[i]) + exp(x - lse1[t]) - 2 delta_it),
+// x = scale * match;  *dscale += sum G * x.
+__global__ void __launch_bounds__(256) match_grad_kernel(const float* match, int Bi, int Bt, float scale,
+                                                         float coef, const float* lse0, const float* lse1,
+                                                         float* dmatch, float* dscale) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    float ds = 0.f;
+    if (idx < Bi * Bt) {
+        const int i = idx / Bt, t = idx % Bt;
+        const float x = match[idx] * scale;
+        float gg = __expf(x - lse0[i]) + __expf(x - lse1[t]);
+        if (i == t) gg -= 2.f;
+        gg *= coef;
+        dmatch[idx] = gg * scale;
+        ds = gg * x;
+    }
+    ds = warp_sum(ds);
+    if ((threadIdx.x & 31) == 0 && dscale) atomicAdd(dscale, ds);
+}
+
 }  // namespace cvcl

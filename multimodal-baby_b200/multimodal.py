@@ -306,7 +306,7 @@ class MultiModalModel(nn.Module):
                                                  1.0 / (H * W))
             return ops.sim_logits(ops.spatial_pool(nhwc), tpool, s)
         tok, _ = ops.text_features_spatial(text, text_length, table, self.normalize_features)
-        match = ops.spatial_max_similarity(nhwc, tok, text_length)
+        match = ops.spatial_max_similarity(nhwc, tok, text_length, text)
         scale = s.exp() if torch.is_tensor(s) else math.exp(s)
         scale = scale.to(match.device) if torch.is_tensor(scale) else scale
         return match * scale, match.t() * scale
@@ -357,7 +357,7 @@ class MultiModalModel(nn.Module):
                 loss, iacc, tacc, ient, tent, _, _ = ops.sim_infonce(img_f, txt_f, s, self.process_group)
             else:
                 tok, _ = ops.text_features_spatial(y, y_len, table, self.normalize_features)
-                match = ops.spatial_max_similarity(nhwc, tok, y_len)
+                match = ops.spatial_max_similarity(nhwc, tok, y_len, y)
                 loss, iacc, tacc, ient, tent, lpi, lpt = ops.infonce_from_match(match, s)
         logits_per_image = logits_per_text = None
         if self.materialize_logits:

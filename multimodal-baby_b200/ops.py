@@ -644,11 +644,145 @@ def _(img, txt, txt_index, n_way, normalize, log_scale):
 
 
 # ----------------------------------------------------------------------------------------
-# K6 spatial "max" similarity (multimodal.py:771-780) -- see spatial ops below
+# K6 spatial "max" similarity (multimodal.py:771-780) + InfoNCE on the materialised match
 # ----------------------------------------------------------------------------------------
-def spatial_max_similarity(img_nhwc, tok, lens):
-    raise NotImplementedError("spatial max similarity kernel not built yet")
+@torch.library.custom_op(_NS + "::spatial_max_fwd", mutates_args=())
+def spatial_max_fwd(img16: Tensor, tok16: Tensor, lens: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """img16 [Bi,HW,E] bf16, tok16 [Bt,L,E] bf16 -> (match [Bi,Bt] fp32, amax_it u8, amax_ti u8)."""
+    _need_cuda(img16, tok16, lens)
+    Bi, HW, E = img16.shape
+    Bt, L, _ = tok16.shape
+    dev = img16.device
+    match = torch.empty((Bi, Bt), dtype=torch.float32, device=dev)
+    a_it = torch.empty((Bi, Bt * L), dtype=torch.uint8, device=dev)
+    a_ti = torch.empty((Bt * L, Bi), dtype=torch.uint8, device=dev)
+    _cabi.call("cvcl_spatial_max_fwd", _p(tok16), _p(img16), _p(_i64(lens)), Bt, L, Bi, HW, E, _p(match),
+               _p(a_it), _p(a_ti), _stream())
+    return match, a_it, a_ti
+
+
+@spatial_max_fwd.register_fake
+def _(img16, tok16, lens):
+    Bi, Bt, L = img16.shape[0], tok16.shape[0], tok16.shape[1]
+    return (img16.new_empty((Bi, Bt), dtype=torch.float32), img16.new_empty((Bi, Bt * L), dtype=torch.uint8),
+            img16.new_empty((Bt * L, Bi), dtype=torch.uint8))
+
+
+@torch.library.custom_op(_NS + "::spatial_max_bwd", mutates_args=())
+def spatial_max_bwd(g: Tensor, lens: Tensor, ids: Optional[Tensor], a_it: Tensor, a_ti: Tensor,
+                    img16: Tensor, tok16: Tensor, need_dimg: bool, need_dtok: bool) -> Tuple[Tensor, Tensor]:
+    _need_cuda(g, img16, tok16)
+    Bi, HW, E = img16.shape
+    Bt, L, _ = tok16.shape
+    dev = g.device
+    g = _f32(g)
+    dimg = torch.empty((Bi, HW, E) if need_dimg else (0,), dtype=torch.float32, device=dev)
+    dtok = torch.empty((Bt, L, E) if need_dtok else (0,), dtype=torch.float32, device=dev)
+    _cabi.call("cvcl_spatial_max_bwd", _p(g), _p(_i64(lens)), None if ids is None else _p(_i64(ids)),
+               _p(a_it), _p(a_ti), _p(tok16), _p(img16), Bt, L, Bi, HW, E,
+               _p(dtok) if need_dtok else None, _p(dimg) if need_dimg else None, _stream())
+    return dimg, dtok
+
+
+@spatial_max_bwd.register_fake
+def _(g, lens, ids, a_it, a_ti, img16, tok16, need_dimg, need_dtok):
+    return (g.new_empty(img16.shape if need_dimg else (0,), dtype=torch.float32),
+            g.new_empty(tok16.shape if need_dtok else (0,), dtype=torch.float32))
+
+
+class _SpatialMax(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, tok, lens, ids):
+        Bi, HW, E = img.shape
+        Bt, L, _ = tok.shape
+        i16, _ = to_bf16_pair(img.reshape(Bi * HW, E), False)
+        t16, _ = to_bf16_pair(tok.reshape(Bt * L, E), False)
+        i16 = i16.view(Bi, HW, E); t16 = t16.view(Bt, L, E)
+        match, a_it, a_ti = spatial_max_fwd(i16, t16, lens)
+        ctx.save_for_backward(lens, ids, a_it, a_ti, i16, t16)
+        ctx.dt = (img.dtype, tok.dtype)
+        return match
+
+    @staticmethod
+    def backward(ctx, g):
+        lens, ids, a_it, a_ti, i16, t16 = ctx.saved_tensors
+        dimg, dtok = spatial_max_bwd(g, lens, ids, a_it, a_ti, i16, t16, ctx.needs_input_grad[0],
+                                     ctx.needs_input_grad[1])
+        return (dimg.to(ctx.dt[0]) if ctx.needs_input_grad[0] else None,
+                dtok.to(ctx.dt[1]) if ctx.needs_input_grad[1] else None, None, None)
+
+
+def spatial_max_similarity(img_nhwc, tok, lens, ids=None):
+    """match[i,t] = sum_l max_hw <img[i,hw,:], tok[t,l,:]> / len[t]   (multimodal.py:771-780).
+    img_nhwc [Bi,HW,E], tok [Bt,L,E] (fp32 or bf16) -> [Bi,Bt] fp32."""
+    return _SpatialMax.apply(img_nhwc, tok, lens, ids)
+
+
+@torch.library.custom_op(_NS + "::match_infonce_fwd", mutates_args=())
+def match_infonce_fwd(match: Tensor, log_scale: float) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    _need_cuda(match)
+    match = _f32(match)
+    B = match.shape[0]
+    if match.shape[1] != B:
+        raise ValueError("InfoNCE needs a square similarity matrix, got %s" % (tuple(match.shape),))
+    dev = match.device
+    lib = _cabi.load()
+    ws = torch.empty((lib.cvcl_sim_workspace_bytes(B, B, B, B),), dtype=torch.uint8, device=dev)
+    out5 = torch.zeros((8,), dtype=torch.float32, device=dev)
+    lse0 = torch.empty((B,), dtype=torch.float32, device=dev); lse1 = torch.empty_like(lse0)
+    a0 = torch.empty((B,), dtype=torch.int32, device=dev); a1 = torch.empty_like(a0)
+    _cabi.call("cvcl_match_infonce_fwd", _p(match), B, float(log_scale), 1.0 / B, _p(ws), _p(lse0), _p(lse1),
+               _p(a0), _p(a1), _p(out5), _stream())
+    return out5, lse0, lse1, a0, a1
+
+
+@match_infonce_fwd.register_fake
+def _(match, log_scale):
+    B = match.shape[0]
+    f = dict(dtype=torch.float32)
+    return (match.new_empty((8,), **f), match.new_empty((B,), **f), match.new_empty((B,), **f),
+            match.new_empty((B,), dtype=torch.int32), match.new_empty((B,), dtype=torch.int32))
+
+
+@torch.library.custom_op(_NS + "::match_infonce_bwd", mutates_args=())
+def match_infonce_bwd(match: Tensor, log_scale: float, lse0: Tensor, lse1: Tensor) -> Tuple[Tensor, Tensor]:
+    _need_cuda(match)
+    match = _f32(match)
+    B = match.shape[0]
+    dmatch = torch.empty_like(match)
+    ds = torch.zeros((1,), dtype=torch.float32, device=match.device)
+    _cabi.call("cvcl_match_infonce_bwd", _p(match), B, float(log_scale), 0.5 / B, _p(lse0), _p(lse1),
+               _p(dmatch), _p(ds), _stream())
+    return dmatch, ds
+
+
+@match_infonce_bwd.register_fake
+def _(match, log_scale, lse0, lse1):
+    return match.new_empty(match.shape, dtype=torch.float32), match.new_empty((1,), dtype=torch.float32)
+
+
+class _MatchInfoNCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, match, s):
+        ls = float(s)
+        out5, lse0, lse1, a0, a1 = match_infonce_fwd(match, ls)
+        ctx.save_for_backward(match, lse0, lse1)
+        ctx.ls = ls
+        ctx.s_is_tensor = torch.is_tensor(s)
+        ctx.mark_non_differentiable(a0, a1)
+        return out5[0], out5[1], out5[2], out5[3], out5[4], a0, a1
+
+    @staticmethod
+    def backward(ctx, gloss, *unused):
+        match, lse0, lse1 = ctx.saved_tensors
+        dmatch, ds = match_infonce_bwd(match, ctx.ls, lse0, lse1)
+        return dmatch * gloss, (ds[0] * gloss) if ctx.s_is_tensor and ctx.needs_input_grad[1] else None
 
 
 def infonce_from_match(match, s):
-    raise NotImplementedError("spatial max similarity kernel not built yet")
+    """symmetric InfoNCE (multimodal.py:801-818) of logits = exp(s) * match, match [B,B] fp32.
+    -> (loss, img_acc, txt_acc, img_ent, txt_ent, logits_per_image, logits_per_text)."""
+    loss, iacc, tacc, ient, tent, _, _ = _MatchInfoNCE.apply(match, s)
+    with torch.no_grad():
+        lpi = match * math.exp(float(s))
+    return loss, iacc, tacc, ient, tent, lpi, lpi.t()

@@ -1,0 +1,103 @@
+"""-m gpu: spatial-embedding path (7x7 layer4 map, per-token text features) with "mean" and "max"
+text-to-location similarity (multimodal.py:757-780), forward + backward, against the reference
+golden vectors and the CPU oracle.  The model is driven through the drop-in MultiModalModel API."""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+
+from _util import O, S_DEFAULT, assert_grad_close, assert_logits_close, case_inputs, golden, t, rel_fro
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def build(cv, E, sim, inp, fix_temperature=False):
+    args = argparse.Namespace(embedding_type="spatial", embedding_dim=E, normalize_features=True,
+                              fix_temperature=fix_temperature, temperature=0.07, text_encoder="embedding",
+                              sim=sim)
+    vocab = {str(i): i for i in range(2350)}
+    m = cv.MultiModalModel(cv.VisionEncoder(args, trunk="pooled"), cv.TextEncoder(vocab, 2048, args), args)
+    with torch.no_grad():
+        conv = m.image_embed.model[-1]
+        conv.weight.copy_(t(inp["W"])[:, :, None, None]); conv.bias.copy_(t(inp["b"]))
+        m.text_embed.embedding.weight.copy_(t(inp["table"]))
+    return m.to(DEV).train()
+
+
+@pytest.fixture(scope="module")
+def cv():
+    import multimodal_baby_b200 as m
+    m._cabi.load()
+    return m
+
+
+def run_model(cv, E, sim, inp):
+    m = build(cv, E, sim, inp)
+    out = m.calculate_contrastive_loss(t(inp["f"], DEV), t(inp["ids"], DEV), t(inp["lens"], DEV))
+    out[0].backward()
+    conv = m.image_embed.model[-1]
+    return out, dict(dW=conv.weight.grad.reshape(E, -1).cpu().numpy(), db=conv.bias.grad.cpu().numpy(),
+                     dtable=m.text_embed.embedding.weight.grad.cpu().numpy(),
+                     ds=m.logit_neg_log_temperature.grad.item())
+
+
+@pytest.mark.parametrize("name,sim", [("spatial_mean_e64_b6", "mean"), ("spatial_mean_e512_b12", "mean"),
+                                      ("spatial_max_e64_b6", "max"), ("spatial_max_e512_b12", "max")])
+def test_spatial_vs_reference_golden(cv, name, sim):
+    g = golden(name)
+    E, B = int(g["E"]), int(g["B"])
+    inp = case_inputs(int(g["seed"]), B, E, "spatial")
+    out, gr = run_model(cv, E, sim, inp)
+    assert abs(out[0].item() - float(g["loss"])) <= 1e-3 * abs(float(g["loss"]))
+    assert_logits_close(out[5].cpu().numpy(), g["logits_per_image"])
+    assert_logits_close(out[6].cpu().numpy(), g["logits_per_text"])
+    assert out[7].shape == (B, E, 7, 7) and out[8].shape == (B, 2048, 7, 7)
+    assert float((out[7][:2].detach().cpu() - t(g["image_features_head"])).abs().max()) <= 6e-3
+    assert_grad_close(gr["db"], g["db"], "db", cos_min=0.998, rel_max=5e-2)
+    assert abs(gr["ds"] - float(g["ds"])) <= 3e-2 * abs(float(g["ds"])) + 2e-3
+    assert rel_fro(gr["dW"][:8, :64], g["dW_slice"]) <= 5e-2
+    assert abs(np.linalg.norm(gr["dW"]) - float(g["dW_norm"])) <= 3e-2 * float(g["dW_norm"])
+    assert rel_fro(gr["dtable"][:8], g["dtable_rows"]) <= 5e-2
+    assert abs(np.linalg.norm(gr["dtable"]) - float(g["dtable_norm"])) <= 3e-2 * float(g["dtable_norm"])
+    assert not gr["dtable"][0].any()
+    if "dW" in g:
+        assert_grad_close(gr["dW"], g["dW"], "dW", cos_min=0.998, rel_max=5e-2)
+
+
+@pytest.mark.parametrize("sim,B", [("mean", 40), ("max", 40), ("max", 37)])
+def test_spatial_vs_oracle(cv, sim, B):
+    E = 512
+    inp = case_inputs(900 + B, B, E, "spatial")
+    ref = O.contrastive_step(t(inp["f"]), t(inp["ids"]), t(inp["lens"]), t(inp["W"]), t(inp["b"]),
+                             t(inp["table"]), S_DEFAULT, "spatial", sim)
+    out, gr = run_model(cv, E, sim, inp)
+    assert abs(out[0].item() - ref["loss"].item()) <= 1e-3 * abs(ref["loss"].item())
+    assert_logits_close(out[5].cpu().numpy(), ref["logits_per_image"].numpy())
+    assert_grad_close(gr["dW"], ref["dW"].reshape(E, -1).numpy(), "dW", cos_min=0.998, rel_max=5e-2)
+    assert_grad_close(gr["dtable"], ref["dtable"].numpy(), "dtable", cos_min=0.998, rel_max=5e-2)
+    assert abs(gr["ds"] - ref["ds"].item()) <= 3e-2 * abs(ref["ds"].item()) + 2e-3
+
+
+def test_spatial_max_kernel_exact_on_bf16_inputs(cv):
+    """kernel-level: with bf16-representable inputs the only difference to the fp64 oracle is the
+    fp32 accumulation order, so match agrees to ~1e-6 and the saved argmax is exact (no near-ties)."""
+    rng = np.random.RandomState(3)
+    Bi, Bt, L, HW, E = 23, 17, 25, 49, 512
+    img = torch.nn.functional.normalize(t(rng.standard_normal((Bi, HW, E)).astype(np.float32)), dim=-1)
+    tok = torch.nn.functional.normalize(t(rng.standard_normal((Bt, L, E)).astype(np.float32)), dim=-1)
+    img = img.to(torch.bfloat16).float(); tok = tok.to(torch.bfloat16).float()
+    lens = t(rng.randint(3, L + 1, size=Bt).astype(np.int64))
+    for b in range(Bt):
+        tok[b, lens[b]:] = 0
+    ref = O.similarity_spatial_max(img.double().permute(0, 2, 1).reshape(Bi, E, 7, 7), tok.double(), lens)
+    match, a_it, a_ti = cv.ops.spatial_max_fwd(img.to(DEV).to(torch.bfloat16), tok.to(DEV).to(torch.bfloat16),
+                                               lens.to(DEV))
+    assert float((match.cpu().double() - ref).abs().max()) <= 2e-6
+    mm = torch.einsum('ihe,tle->itlh', img.double(), tok.double())
+    ref_arg = mm.argmax(-1)                                     # [Bi,Bt,L]
+    got = a_it.cpu().view(Bi, Bt, L).long()
+    valid = (torch.arange(L)[None, :] < lens[:, None])[None].expand(Bi, -1, -1)
+    assert torch.equal(got[valid], ref_arg[valid])
+    assert torch.equal(a_ti.cpu().view(Bt, L, Bi).permute(2, 0, 1), a_it.cpu().view(Bi, Bt, L))
