@@ -154,10 +154,21 @@ def encode_text(ids, lens, table, embedding_type="flat", normalize=True):
     return (l2_normalize(ret, -1) if normalize else ret), out
 
 
-def forward(f, ids, lens, W, b, table, s, embedding_type="flat", sim="mean", normalize=True):
-    """multimodal.py:746-794 -> (logits_per_image, logits_per_text, img_feat, txt_feat)."""
+def _round_bf16_ste(x):
+    """round to bf16 with a straight-through gradient: emulates the kernels' operand precision
+    (bf16 features, fp32 accumulation) inside the otherwise unchanged reference algorithm."""
+    return x + (x.detach().to(torch.bfloat16).to(x.dtype) - x.detach())
+
+
+def forward(f, ids, lens, W, b, table, s, embedding_type="flat", sim="mean", normalize=True,
+            feature_round=None):
+    """multimodal.py:746-794 -> (logits_per_image, logits_per_text, img_feat, txt_feat).
+    feature_round="bf16" (not in the reference) rounds the encoded features to bf16 before the
+    similarity, which is the operand precision BASELINE.json north_star prescribes."""
     img = encode_image(f, W, b, embedding_type, normalize)
     txt, _ = encode_text(ids, lens, table, embedding_type, normalize)
+    if feature_round == "bf16":
+        img, txt = _round_bf16_ste(img), _round_bf16_ste(txt)
     if embedding_type == "flat":
         match = similarity_flat(img, txt)
     elif sim == "mean":
@@ -169,7 +180,7 @@ def forward(f, ids, lens, W, b, table, s, embedding_type="flat", sim="mean", nor
 
 
 def contrastive_step(f, ids, lens, W, b, table, s, embedding_type="flat", sim="mean",
-                     normalize=True, dtype=torch.float32, need_df=False):
+                     normalize=True, dtype=torch.float32, need_df=False, feature_round=None):
     """multimodal.py:796-822 + loss.backward(): returns a dict with the forward outputs
     and the gradients of the four trainable tensors (+ df if need_df)."""
     W = W.detach().to(dtype).clone().requires_grad_(True)
@@ -177,7 +188,8 @@ def contrastive_step(f, ids, lens, W, b, table, s, embedding_type="flat", sim="m
     table = table.detach().to(dtype).clone().requires_grad_(True)
     s = torch.as_tensor(s, dtype=torch.float64).detach().to(dtype).clone().requires_grad_(True)
     f = f.detach().to(dtype).clone().requires_grad_(need_df)
-    lpi, lpt, img, txt = forward(f, ids, lens, W, b, table, s, embedding_type, sim, normalize)
+    lpi, lpt, img, txt = forward(f, ids, lens, W, b, table, s, embedding_type, sim, normalize,
+                                 feature_round)
     res = infonce(lpi, lpt)
     res.loss.backward()
     dtab = table.grad.clone()

@@ -55,29 +55,38 @@ def test_spatial_vs_reference_golden(cv, name, sim):
     assert_logits_close(out[6].cpu().numpy(), g["logits_per_text"])
     assert out[7].shape == (B, E, 7, 7) and out[8].shape == (B, 2048, 7, 7)
     assert float((out[7][:2].detach().cpu() - t(g["image_features_head"])).abs().max()) <= 6e-3
-    assert_grad_close(gr["db"], g["db"], "db", cos_min=0.998, rel_max=5e-2)
-    assert abs(gr["ds"] - float(g["ds"])) <= 3e-2 * abs(float(g["ds"])) + 2e-3
-    assert rel_fro(gr["dW"][:8, :64], g["dW_slice"]) <= 5e-2
-    assert abs(np.linalg.norm(gr["dW"]) - float(g["dW_norm"])) <= 3e-2 * float(g["dW_norm"])
-    assert rel_fro(gr["dtable"][:8], g["dtable_rows"]) <= 5e-2
-    assert abs(np.linalg.norm(gr["dtable"]) - float(g["dtable_norm"])) <= 3e-2 * float(g["dtable_norm"])
+    # "max": the arg-max location of near-tied (random-init) locations is not stable under bf16
+    # operands, and every flip moves a gradient row to another location, so
+    # the gate against the fp32 reference is looser; test_spatial_max_backward_exact_given_argmax
+    # pins the backward itself tightly on bf16-representable inputs.
+    cm, rm = (0.998, 5e-2) if sim == "mean" else (0.93, 0.5)   # tiny batches: a few flips dominate
+    assert_grad_close(gr["db"], g["db"], "db", cos_min=cm, rel_max=rm)
+    assert abs(gr["ds"] - float(g["ds"])) <= rm * abs(float(g["ds"])) + 2e-3
+    assert rel_fro(gr["dW"][:8, :64], g["dW_slice"]) <= rm
+    assert abs(np.linalg.norm(gr["dW"]) - float(g["dW_norm"])) <= rm * float(g["dW_norm"])
+    assert rel_fro(gr["dtable"][:8], g["dtable_rows"]) <= rm
+    assert abs(np.linalg.norm(gr["dtable"]) - float(g["dtable_norm"])) <= rm * float(g["dtable_norm"])
     assert not gr["dtable"][0].any()
     if "dW" in g:
-        assert_grad_close(gr["dW"], g["dW"], "dW", cos_min=0.998, rel_max=5e-2)
+        assert_grad_close(gr["dW"], g["dW"], "dW", cos_min=cm, rel_max=rm)
 
 
-@pytest.mark.parametrize("sim,B", [("mean", 40), ("max", 40), ("max", 37)])
-def test_spatial_vs_oracle(cv, sim, B):
+@pytest.mark.parametrize("sim,B,fr", [("mean", 40, None), ("max", 40, None), ("max", 37, None),
+                                      ("max", 24, "bf16"), ("max", 6, "bf16")])
+def test_spatial_vs_oracle(cv, sim, B, fr):
+    """fr="bf16": the oracle rounds the encoded features to bf16 (the kernels' operand precision),
+    which removes most arg-max flips, so the tight gradient gate applies to the max path too."""
     E = 512
     inp = case_inputs(900 + B, B, E, "spatial")
     ref = O.contrastive_step(t(inp["f"]), t(inp["ids"]), t(inp["lens"]), t(inp["W"]), t(inp["b"]),
-                             t(inp["table"]), S_DEFAULT, "spatial", sim)
+                             t(inp["table"]), S_DEFAULT, "spatial", sim, feature_round=fr)
     out, gr = run_model(cv, E, sim, inp)
     assert abs(out[0].item() - ref["loss"].item()) <= 1e-3 * abs(ref["loss"].item())
     assert_logits_close(out[5].cpu().numpy(), ref["logits_per_image"].numpy())
-    assert_grad_close(gr["dW"], ref["dW"].reshape(E, -1).numpy(), "dW", cos_min=0.998, rel_max=5e-2)
-    assert_grad_close(gr["dtable"], ref["dtable"].numpy(), "dtable", cos_min=0.998, rel_max=5e-2)
-    assert abs(gr["ds"] - ref["ds"].item()) <= 3e-2 * abs(ref["ds"].item()) + 2e-3
+    cm, rm = (0.998, 5e-2) if sim == "mean" else ((0.997, 8e-2) if fr else (0.98, 0.2))
+    assert_grad_close(gr["dW"], ref["dW"].reshape(E, -1).numpy(), "dW", cos_min=cm, rel_max=rm)
+    assert_grad_close(gr["dtable"], ref["dtable"].numpy(), "dtable", cos_min=cm, rel_max=rm)
+    assert abs(gr["ds"] - ref["ds"].item()) <= rm * abs(ref["ds"].item()) + 2e-3
 
 
 def test_spatial_max_kernel_exact_on_bf16_inputs(cv):
@@ -101,3 +110,27 @@ def test_spatial_max_kernel_exact_on_bf16_inputs(cv):
     valid = (torch.arange(L)[None, :] < lens[:, None])[None].expand(Bi, -1, -1)
     assert torch.equal(got[valid], ref_arg[valid])
     assert torch.equal(a_ti.cpu().view(Bt, L, Bi).permute(2, 0, 1), a_it.cpu().view(Bi, Bt, L))
+
+
+def test_spatial_max_backward_exact_given_argmax(cv):
+    """backward of the max similarity on bf16-representable inputs (kernel argmax == fp64 argmax):
+    must equal torch autograd of einsum+amax+sum+div (multimodal.py:775-780) to fp32 accuracy."""
+    rng = np.random.RandomState(4)
+    Bi, Bt, L, HW, E = 19, 21, 25, 49, 256
+    img = torch.nn.functional.normalize(t(rng.standard_normal((Bi, HW, E)).astype(np.float32)), dim=-1)
+    tok = torch.nn.functional.normalize(t(rng.standard_normal((Bt, L, E)).astype(np.float32)), dim=-1)
+    img = img.to(torch.bfloat16).float(); tok = tok.to(torch.bfloat16).float()
+    ids, lens = O.synth_tokens(rng, Bt, L, 2350)
+    for b in range(Bt):
+        tok[b, lens[b]:] = 0
+    g = t(rng.standard_normal((Bi, Bt)).astype(np.float32))
+    ir = img.double().clone().requires_grad_(True); tr = tok.double().clone().requires_grad_(True)
+    ref = O.similarity_spatial_max(ir.permute(0, 2, 1).reshape(Bi, E, 7, 7), tr, t(lens))
+    (ref * g.double()).sum().backward()
+    idv = img.to(DEV).requires_grad_(True); tdv = tok.to(DEV).requires_grad_(True)
+    got = cv.ops.spatial_max_similarity(idv, tdv, t(lens, DEV), t(ids, DEV))
+    (got * g.to(DEV)).sum().backward()
+    assert float((got.detach().cpu().double() - ref.detach()).abs().max()) <= 2e-6
+    assert rel_fro(idv.grad.cpu().numpy(), ir.grad.numpy()) <= 1e-5
+    valid = (torch.arange(L)[None, :] < t(lens)[:, None])
+    assert rel_fro(tdv.grad.cpu()[valid].numpy(), tr.grad[valid].numpy()) <= 1e-5
