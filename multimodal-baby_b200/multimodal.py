@@ -365,7 +365,7 @@ class MultiModalModel(nn.Module):
                 logits_per_image, logits_per_text = lpi, lpt
             else:
                 with torch.no_grad():
-                    logits_per_image, logits_per_text = ops.sim_logits(img_f, txt_f, float(s))
+                    logits_per_image, logits_per_text = ops.sim_logits(img_f, txt_f, ops._scalar(s))
         text_outputs = ops.text_outputs(y, table) if self.materialize_text_outputs else None
         return (loss, iacc, tacc, ient, tent, logits_per_image, logits_per_text,
                 image_features, fmap, text_outputs)

@@ -206,7 +206,7 @@ class MultiModalLitModel(_Base):
         (None: C == N).  Returns (pred int32 [N], logits fp32 [N, n_way]); fp32 end to end."""
         m = self.model
         table = m.text_embed.embedding.weight
-        s = float(m.logit_neg_log_temperature)
+        s = ops._scalar(m.logit_neg_log_temperature)
         txt = ops.text_features_flat(label_ids, label_lens, table, normalize=False)
         N = trial_features.shape[0]
         feats = trial_features.reshape(N * n_way, -1).float()

@@ -44,6 +44,13 @@ def _need_cuda(*ts):
                                "fallback (got a %s tensor)" % t.device)
 
 
+def _scalar(s) -> float:
+    """host value of the log-scale `s` (a python float, a CPU 0-dim tensor when the temperature is
+    fixed -- multimodal.py:712 -- or a CUDA Parameter, in which case this is the one D2H sync the
+    reference's own logging already performs every step, multimodal_lit.py:252)."""
+    return float(s.detach()) if torch.is_tensor(s) else float(s)
+
+
 def _pad8(n: int) -> int:
     return (n + 7) // 8 * 8
 
@@ -403,7 +410,7 @@ def _(g, img, txt, log_scale):
 class _SimLogits(torch.autograd.Function):
     @staticmethod
     def forward(ctx, img, txt, s):
-        ls = float(s)
+        ls = _scalar(s)
         lpi, lpt = sim_logits_fwd(img, txt, ls)
         ctx.save_for_backward(img, txt, lpi)
         ctx.ls = ls
@@ -506,7 +513,7 @@ class _SimInfoNCE(torch.autograd.Function):
         from . import sharding
         i16, _ = to_bf16_pair(img, False)
         t16, _ = to_bf16_pair(txt, False)
-        out5, saved, (a0, a1) = sharding.infonce_forward(i16, t16, float(s), group, sim_infonce_fwd)
+        out5, saved, (a0, a1) = sharding.infonce_forward(i16, t16, _scalar(s), group, sim_infonce_fwd)
         ctx.saved = saved
         ctx.group = group
         ctx.meta = (img.dtype, txt.dtype, torch.is_tensor(s))
@@ -594,7 +601,7 @@ class _FlatContrastiveStep(torch.autograd.Function):
             raise RuntimeError("flat_contrastive_step does not produce d/dx; use the op-by-op path "
                                "(finetune_cnn=True) instead")
         out5, img_f, txt_f, dW, db, dtable, ds = flat_contrastive_step(
-            x, ids, lens, w, bias, table, float(s), normalize, need, want_features)
+            x, ids, lens, w, bias, table, _scalar(s), normalize, need, want_features)
         ctx.need = need
         ctx.s_is_tensor = torch.is_tensor(s)
         if need:
@@ -764,7 +771,7 @@ def _(match, log_scale, lse0, lse1):
 class _MatchInfoNCE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, match, s):
-        ls = float(s)
+        ls = _scalar(s)
         out5, lse0, lse1, a0, a1 = match_infonce_fwd(match, ls)
         ctx.save_for_backward(match, lse0, lse1)
         ctx.ls = ls
@@ -784,5 +791,5 @@ def infonce_from_match(match, s):
     -> (loss, img_acc, txt_acc, img_ent, txt_ent, logits_per_image, logits_per_text)."""
     loss, iacc, tacc, ient, tent, _, _ = _MatchInfoNCE.apply(match, s)
     with torch.no_grad():
-        lpi = match * math.exp(float(s))
+        lpi = match * math.exp(_scalar(s))
     return loss, iacc, tacc, ient, tent, lpi, lpi.t()

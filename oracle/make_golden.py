@@ -140,6 +140,23 @@ def run_tokenize_case(name):
     print(name, lens.tolist())
 
 
+def run_state_dict_case(name):
+    """parameter attribute paths the drop-in must keep (load_from_checkpoint compatibility)."""
+    rec = {}
+    for et in ("flat", "spatial"):
+        for fix in (False, True):
+            m = R.build_reference_model(et, embedding_dim=64, fix_temperature=fix, lit=True)
+            rec["%s_fix%d" % (et, int(fix))] = {
+                "state_dict": sorted(m.state_dict().keys()),
+                "trainable": sorted(n for n, p in m.named_parameters() if p.requires_grad),
+                "temperature_is_parameter": isinstance(m.model.logit_neg_log_temperature, torch.nn.Parameter),
+                "temperature_value": float(m.model.logit_neg_log_temperature),
+            }
+    with open(os.path.join(GOLD, name + ".json"), "w") as fh:
+        json.dump(rec, fh, indent=1)
+    print(name, list(rec))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
@@ -156,6 +173,7 @@ def main():
     run_forward_case("forward_4x1_e512", 109, 4, 1, 512)
     run_eval_case("eval_4way_e512", 110, 64, 512)
     run_tokenize_case("tokenize")
+    run_state_dict_case("state_dict_keys")
 
 
 if __name__ == "__main__":

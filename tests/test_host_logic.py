@@ -1,0 +1,170 @@
+"""CPU suite (-m "not gpu"): host-side mirror of the reference interface and the C-ABI surface.
+No compute call is made (there is no CPU path); what is checked is everything around it:
+symbol export, prototypes, state_dict key parity with the reference, tokenisation, argument
+semantics and loud failure modes."""
+import argparse
+import ctypes
+import json
+import os
+import re
+
+import pytest
+import torch
+
+from _util import GOLD, ROOT
+
+import multimodal_baby_b200 as cv
+
+
+def _vocab():
+    try:
+        return cv.load_vocab()
+    except FileNotFoundError:
+        return None
+
+
+def _args(**kw):
+    d = dict(embedding_type="flat", embedding_dim=64, normalize_features=True, fix_temperature=False,
+             temperature=0.07, text_encoder="embedding", sim="mean", dropout_o=0.0)
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+def _lit(**kw):
+    a = _args(**kw)
+    vocab = {"<pad>": 0, "<unk>": 1, "<sos>": 2, "<eos>": 3, **{"w%d" % i: i for i in range(4, 2350)}}
+    return cv.MultiModalLitModel(cv.VisionEncoder(a, trunk="pooled"), cv.TextEncoder(vocab, 2048, a), a,
+                                 vocab=vocab)
+
+
+# ------------------------------------------------------------------------------ C ABI surface
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "cvcl_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(cvcl_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 25
+    lib = ctypes.CDLL(cv._cabi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), "libcvcl_b200.so does not export %s" % name
+    # the ctypes prototype table covers exactly the header
+    assert sorted(cv._cabi.PROTOTYPES) == declared
+    assert cv._cabi.load().cvcl_abi_version() == 1
+
+
+def test_library_links_no_torch_and_is_sm100a():
+    import subprocess
+    out = subprocess.run(["ldd", cv._cabi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "libtorch" not in out and "libc10" not in out
+    cu = subprocess.run(["cuobjdump", "-lelf", cv._cabi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in cu
+
+
+def test_missing_library_is_loud(monkeypatch):
+    monkeypatch.setattr(cv._cabi, "_lib", None)
+    with pytest.raises(cv.CvclLibraryMissing):
+        cv._cabi.load("/nonexistent/libcvcl_b200.so")
+    monkeypatch.undo()
+    cv._cabi.load()
+
+
+def test_cpu_tensors_raise_no_fallback():
+    lit = _lit()
+    ids, lens = lit.tokenize(["w5 w6"])
+    with pytest.raises(RuntimeError, match="no CPU"):
+        lit(torch.randn(2, 2048), ids, lens)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        lit.model.calculate_contrastive_loss(torch.randn(1, 2048), ids, lens)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        cv.ops.eval_nway(torch.randn(8, 64), torch.randn(2, 64), None, 4, True, 0.0)
+
+
+def test_package_never_imports_oracle():
+    pkg = os.path.join(ROOT, "multimodal-baby_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), fn
+
+
+# ------------------------------------------------------------------------------ reference interface
+@pytest.mark.parametrize("et", ["flat", "spatial"])
+@pytest.mark.parametrize("fix", [False, True])
+def test_state_dict_keys_match_reference(et, fix):
+    with open(os.path.join(GOLD, "state_dict_keys.json")) as fh:
+        g = json.load(fh)["%s_fix%d" % (et, int(fix))]
+    lit = _lit(embedding_type=et, fix_temperature=fix)
+    assert sorted(lit.state_dict().keys()) == g["state_dict"]
+    assert sorted(n for n, p in lit.named_parameters() if p.requires_grad) == g["trainable"]
+    s = lit.model.logit_neg_log_temperature
+    assert isinstance(s, torch.nn.Parameter) == g["temperature_is_parameter"]
+    assert abs(float(s) - g["temperature_value"]) < 1e-7
+    assert s.dim() == 0 and s.dtype == torch.float32
+    # tied LM head and shared encoders, as in the reference
+    assert lit.language_model.output_layer.weight is lit.text_encoder.embedding.weight
+    assert lit.model.image_embed is lit.vision_encoder and lit.model.text_embed is lit.text_encoder
+
+
+def test_tokenize_matches_reference_golden():
+    vocab = _vocab()
+    if vocab is None:
+        pytest.skip("vocab.json not available")
+    with open(os.path.join(GOLD, "tokenize.json")) as fh:
+        g = json.load(fh)
+    a = _args()
+    lit = cv.MultiModalLitModel(cv.VisionEncoder(a, trunk="pooled"), cv.TextEncoder(vocab, 2048, a), a,
+                                vocab=vocab)
+    ids, lens = lit.tokenize(g["texts"])
+    assert ids.dtype == torch.int64 and lens.dtype == torch.int64
+    assert ids.tolist() == g["ids"] and lens.tolist() == g["lens"]
+    one, n = lit.tokenize(g["texts"][0])            # a bare string is one utterance
+    assert one.tolist() == [g["ids"][0]] and n.tolist() == [g["lens"][0]]
+
+
+def test_unsupported_configurations_raise():
+    with pytest.raises(NotImplementedError):
+        cv.TextEncoder({"<pad>": 0}, 2048, _args(text_encoder="lstm"))
+    with pytest.raises(NotImplementedError):
+        _lit(lambda_lm=0.5)
+    lit = _lit(dropout_o=0.3)
+    lit.train()
+    ids, lens = lit.tokenize(["w5"])
+    with pytest.raises(NotImplementedError, match="dropout_o"):
+        lit.model.encode_text(ids, lens)
+    with pytest.raises(NotImplementedError):
+        cv.VisionEncoder(_args(vit_dino=True), trunk="pooled")
+
+
+def test_defaults_follow_reference_argparse():
+    p = argparse.ArgumentParser()
+    cv.MultiModalModel.add_to_argparse(p)
+    a = p.parse_args([])
+    assert (a.embedding_type, a.embedding_dim, a.normalize_features, a.sim, a.temperature,
+            a.fix_temperature) == ("flat", 128, False, "max", 0.07, False)   # multimodal.py:17-29
+
+
+def test_trunk_split_keeps_reference_semantics():
+    """split_trunk_forward(run_head=True) == the stock module forward, and run_head=False hands the
+    kernels the input of the head (flat: pooled activations; spatial: the layer4 map)."""
+    a = _args()
+    ve = cv.VisionEncoder(a, trunk="pooled")
+    x = torch.randn(3, 2048)
+    feats, fmap = cv.split_trunk_forward(ve, x, run_head=True)
+    assert torch.allclose(feats, ve.model.fc(x)) and torch.equal(fmap, x)
+    pooled, fmap2 = cv.split_trunk_forward(ve, x, run_head=False)
+    assert torch.equal(pooled, x) and isinstance(ve.model.fc, torch.nn.Linear)
+    vs = cv.VisionEncoder(_args(embedding_type="spatial"), trunk="pooled")
+    xs = torch.randn(2, 2048, 7, 7)
+    b, f = cv.split_trunk_forward(vs, xs, run_head=False)
+    assert torch.equal(b, xs) and torch.equal(f, xs)
+
+
+def test_full_resnext_trunk_split_matches_torchvision():
+    a = _args()
+    ve = cv.VisionEncoder(a, trunk="resnext").eval()
+    x = torch.randn(1, 3, 64, 64)
+    with torch.no_grad():
+        pooled, fmap = cv.split_trunk_forward(ve, x, run_head=False)
+        ref = ve.model(x)
+        assert pooled.shape == (1, 2048) and fmap.shape[1] == 2048
+        assert torch.allclose(ve.model.fc(pooled), ref, atol=1e-5)
+    assert not any(p.requires_grad for n, p in ve.model.named_parameters() if not n.startswith("fc."))
+    assert all(p.requires_grad for p in ve.model.fc.parameters())
