@@ -161,10 +161,9 @@ def kernel_breakdown(m, dev, B, reps, flush, peaks):
     W_d = torch.from_numpy(W).to(dev); b_d = torch.from_numpy(b).to(dev); tab_d = torch.from_numpy(table).to(dev)
     bf = dict(dtype=torch.bfloat16, device=dev); f32 = dict(dtype=torch.float32, device=dev)
     ldB = (B + 7) // 8 * 8
-    w16 = torch.empty((E, K), **bf); xc = torch.empty((B, K), **bf); x16t = torch.empty((K, ldB), **bf)
-    img16 = torch.empty((B, E), **bf); img16t = torch.empty((E, ldB), **bf)
-    txt16 = torch.empty((B, E), **bf); txt16t = torch.empty((E, ldB), **bf)
-    G0 = torch.empty((B, ldB), **bf); G1 = torch.empty((B, ldB), **bf); du16t = torch.empty((E, ldB), **bf)
+    w16 = torch.empty((E, K), **bf)
+    img16 = torch.empty((B, E), **bf); txt16 = torch.empty((B, E), **bf)
+    G0 = torch.empty((B, ldB), **bf); du16 = torch.empty((B, E), **bf)
     invn_i = torch.empty((B,), **f32); invn_t = torch.empty((B,), **f32)
     lse0 = torch.empty((B,), **f32); lse1 = torch.empty((B,), **f32); dm = torch.empty((B, E), **f32)
     dW = torch.empty((E, K), **f32); db = torch.zeros((E,), **f32); dtab = torch.zeros((V, E), **f32)
@@ -173,33 +172,32 @@ def kernel_breakdown(m, dev, B, reps, flush, peaks):
     p = ops._p
     st = lambda: torch.cuda.current_stream().cuda_stream
     sum_len = int(lens.sum())
-    dcoef = -2.0 * math.exp(S_FIXED) * 0.5 / B
+    coef = 0.5 / B
+    dcoef = -2.0 * math.exp(S_FIXED) * coef
     C = _cabi.call
     kernels = [
         ("cast_w_f32_to_bf16", lambda: C("cvcl_cast_transpose", p(W_d), 0, p(w16), None, 1, E, K, K, K, 0, 0, 0, 0, st()),
          dict(bytes=E * K * 6)),
-        ("cast_transpose_x", lambda: C("cvcl_cast_transpose", p(x16), 1, p(xc), p(x16t), 1, B, K, K, K, ldB, 0, 0, 0, st()),
-         dict(bytes=B * K * 6)),
         ("K1_text_encoder_fwd", lambda: C("cvcl_text_encoder_fwd", p(ids_d), p(lens_d), p(tab_d), B, L, E, V, 1, 0, 1.0,
-                                          None, p(txt16), E, p(txt16t), ldB, p(invn_t), None, None, None, st()),
-         dict(bytes=8 * B * L + sum_len * E * 4 + B * E * 4)),
-        ("K2_head_proj_norm_fwd", lambda: C("cvcl_head_proj_norm_fwd", p(xc), K, p(w16), K, p(b_d), B, E, K, 1, None, 0,
-                                            p(img16), E, p(img16t), ldB, p(invn_i), st()),
-         dict(bytes=2 * B * K + 2 * E * K + 4 * B * E, flops=2 * B * K * E)),
+                                          None, p(txt16), E, p(invn_t), None, None, None, st()),
+         dict(bytes=8 * B * L + sum_len * E * 4 + B * E * 2)),
+        ("K2_head_proj_norm_fwd", lambda: C("cvcl_head_proj_norm_fwd", p(x16), K, p(w16), K, p(b_d), B, E, K, 1, None, 0,
+                                            p(img16), E, p(invn_i), st()),
+         dict(bytes=2 * B * K + 2 * E * K + 2 * B * E, flops=2 * B * K * E)),
         ("K3K4_sim_infonce_fwd", lambda: C("cvcl_sim_infonce_fwd", p(img16), p(txt16), p(txt16), p(img16), E, B, B, B, B, E,
                                            S_FIXED, 0, 1.0 / B, p(ws), p(lse0), p(lse1), None, None, p(out5), st()),
          dict(bytes=4 * B * E * 2, flops=4 * B * B * E)),
-        ("K5a_sim_infonce_bwd_g", lambda: C("cvcl_sim_infonce_bwd_g", p(img16), p(txt16), p(txt16), p(img16), E, B, B, B, B, E,
-                                            S_FIXED, 0, 0.5 / B, p(lse0), p(lse1), p(lse1), p(lse0), p(G0), ldB, p(G1), ldB,
+        ("K5a_sim_infonce_bwd_g", lambda: C("cvcl_sim_infonce_bwd_g", p(img16), p(txt16), None, None, E, B, B, 0, 0, E,
+                                            S_FIXED, 0, coef, p(lse0), p(lse1), None, None, p(G0), ldB, None, 0,
                                             p(ds), st()),
-         dict(bytes=4 * B * E * 2 + 2 * B * B * 2, flops=4 * B * B * E)),
-        ("K5b_dimg_norm_bwd", lambda: C("cvcl_feat_grad_norm_bwd", p(G0), ldB, p(txt16t), ldB, B, E, B, p(img16), E, p(invn_i),
-                                        1, None, p(txt16), E, 0, dcoef, None, 0, p(du16t), ldB, p(db), st()),
+         dict(bytes=2 * B * E * 2 + B * B * 2, flops=2 * B * B * E)),
+        ("K5b_dimg_norm_bwd", lambda: C("cvcl_feat_grad_norm_bwd", p(G0), ldB, 0, p(txt16), E, B, E, B, p(img16), E, p(invn_i),
+                                        1, None, p(txt16), E, B, 0, dcoef, None, 0, p(du16), E, p(db), st()),
          dict(bytes=2 * B * B + 2 * B * E * 3 + 2 * B * E, flops=2 * B * B * E)),
-        ("K5b_dtxt_norm_bwd", lambda: C("cvcl_feat_grad_norm_bwd", p(G1), ldB, p(img16t), ldB, B, E, B, p(txt16), E, p(invn_t),
-                                        1, p(lens_d), p(img16), E, 0, dcoef, p(dm), E, None, 0, None, st()),
+        ("K5b_dtxt_norm_bwd", lambda: C("cvcl_feat_grad_norm_bwd", p(G0), ldB, 1, p(img16), E, B, E, B, p(txt16), E, p(invn_t),
+                                        1, p(lens_d), p(img16), E, B, 0, dcoef, p(dm), E, None, 0, None, st()),
          dict(bytes=2 * B * B + 2 * B * E * 3 + 4 * B * E, flops=2 * B * B * E)),
-        ("K5c_head_weight_grad", lambda: C("cvcl_head_weight_grad", p(du16t), ldB, p(x16t), ldB, E, K, B, p(dW), K, st()),
+        ("K5c_head_weight_grad", lambda: C("cvcl_head_weight_grad", p(du16), E, p(x16), K, E, K, B, p(dW), K, st()),
          dict(bytes=2 * E * B + 2 * K * B + 4 * E * K, flops=2 * E * K * B)),
         ("K5e_embedding_scatter_add", lambda: C("cvcl_embedding_scatter_add", p(ids_d), p(dm), p(dtab), B, L, E, V, 0, st()),
          dict(bytes=8 * B * L + 4 * B * E + 2 * sum_len * E * 4)),

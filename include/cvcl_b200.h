@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CVCL_ABI_VERSION 1
+#define CVCL_ABI_VERSION 2
 #define CVCL_OK 0
 #define CVCL_ERR_INVALID (-1)
 #define CVCL_ERR_UNSUPPORTED (-2)
@@ -46,7 +46,7 @@ unsigned long long cvcl_launch_count(void);
  *   outside [0,V) (the reference raises IndexError). */
 int cvcl_text_encoder_fwd(const int64_t* ids, const int64_t* lens, const float* table,
                           int B, int L, int E, int V, int normalize, int per_token, float pool_scale,
-                          float* feat_f32, void* feat_bf16, int ld_bf16, void* feat_bf16_t, int ld_t,
+                          float* feat_f32, void* feat_bf16, int ld_bf16,
                           float* inv_norm, float* tok_f32, void* tok_bf16, int* status, void* stream);
 
 /* text_outputs = embedding(ids) (multimodal.py:496,575-584): [n_tok, E] fp32 row gather. */
@@ -88,18 +88,21 @@ int cvcl_rownorm_bwd(const float* g, const float* feat, const float* inv_norm, i
 int cvcl_spatial_pool(const float* src, int B, int HW, int E, float* out_f32, void* out_bf16, int ld,
                       void* out_bf16_t, int ld_t, void* stream);
 
-/* generic C [M,N] fp32 = alpha * A [M,K] . B [N,K]^T on the tcgen05 engine (bf16 operands). */
-int cvcl_gemm_nt_f32out(const void* A, int lda, const void* B, int ldb, int M, int N, int K, float alpha,
-                        float* C, int ldc, void* stream);
+/* generic C [M,N] fp32 = alpha * A . B^T on the tcgen05 engine (bf16 operands, fp32 accumulate).
+ * a_mn = 0: A stored [M,K] (K-major);  a_mn = 1: A stored [K,M] (MN-major, i.e. the transposed
+ * matrix is read in place through an MN-major UMMA descriptor).  Same for B ([N,K] / [K,N]). */
+int cvcl_gemm_f32out(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int N, int K,
+                     float alpha, float* C, int ldc, void* stream);
 
 /* ---- K2 projection head + L2 normalise -----------------------------------------------------
  * replaces model.fc / the 1x1 conv (multimodal.py:181-192, applied at :101) + F.normalize (:736).
  * x [M,K] bf16 (M = B, or B*49 NHWC rows), w [E,K] bf16, bias [E] fp32.  tcgen05 GEMM, bias +
- * full-row norm in the epilogue (cluster of ceil(E/128) CTAs shares the row sum of squares). */
+ * full-row norm in the epilogue (cluster of ceil(E/128) CTAs shares the row sum of squares);
+ * the bf16 feature tile leaves through a TMA store. */
 int cvcl_head_proj_norm_fwd(const void* x, int ldx, const void* w, int ldw, const float* bias,
                             int M, int E, int K, int normalize,
                             float* out_f32, int ld_f32, void* out_bf16, int ld_bf16,
-                            void* out_bf16_t, int ld_t, float* inv_norm, void* stream);
+                            float* inv_norm, void* stream);
 
 /* ---- K3+K4 similarity GEMM fused with the symmetric InfoNCE statistics ----------------------
  * replaces multimodal.py:755 (match), :783-787 (logit_scale) and :801-818 (cross-entropy both
@@ -128,23 +131,28 @@ int cvcl_sim_logits_fwd(const void* img, const void* txt, int ld, int Ni, int Nt
  *     coef = upstream / (2 B_global).  The -2*I term of G = (softmax_row + softmax_col - 2 I)/(2B)
  *     is NOT in the bf16 matrix (it would dominate the rounding error); (b) adds it in fp32.
  *     lse_k0 [N0] = column LSEs seen by direction 0 (= all-gathered lse1), lse_k1 [N1] likewise.
+ *     Gs1 may be NULL (single GPU: the dT GEMM reads Gs0 transposed in place).
  *     *dscale += sum G * logits (the logit_scale gradient, multimodal.py:711-715,783-787). */
 int cvcl_sim_infonce_bwd_g(const void* img_q, const void* txt_k, const void* txt_q, const void* img_k,
                            int ld, int M0, int N0, int M1, int N1, int E, float log_scale, int diag_off,
                            float coef, const float* lse_q0, const float* lse_k0, const float* lse_q1,
                            const float* lse_k1, void* Gs0, int ldg0, void* Gs1, int ldg1, float* dscale,
                            void* stream);
-/* (b) dFeat = Gs [M,Kc] . other_t[E,Kc]^T + diag_coef * diag_feat[m + diag_off] (the -2*I term of
- *     G, applied in fp32; diag_feat may be NULL), followed by the F.normalize backward in the
- *     epilogue.  Outputs: out_f32 [M,E] (scaled by 1/row_len if given: d mean-embedding),
- *     out_bf16_t [E,M] (operand of the weight-gradient GEMM), dbias [E] += column sums. */
-int cvcl_feat_grad_norm_bwd(const void* Gs, int ldg, const void* other_t, int ld_other, int M, int E,
-                            int Kc, const void* feat_bf16, int ld_feat, const float* inv_norm,
+/* (b) dFeat = Gs . other + diag_coef * diag_feat[m + diag_off] (the -2*I term of G, applied in
+ *     fp32; diag_feat [diag_rows,E] bf16 may be NULL), followed by the F.normalize backward in the
+ *     epilogue (feat [M,E] bf16 + inv_norm).  Gs is [M,Kc] (gs_transposed = 0) or stored [Kc,M]
+ *     (gs_transposed = 1: the other orientation is read in place, MN-major); other is the [Kc,E] bf16
+ *     feature matrix as stored.  Exactly one output: out_f32 [M,E] (scaled by 1/row_len if given:
+ *     d mean-embedding) or out_bf16 [M,E] (operand of the weight-gradient GEMM); dbias [E] += column
+ *     sums (nullable). */
+int cvcl_feat_grad_norm_bwd(const void* Gs, int ldg, int gs_transposed, const void* other, int ld_other,
+                            int M, int E, int Kc, const void* feat_bf16, int ld_feat, const float* inv_norm,
                             int normalize, const int64_t* row_len, const void* diag_feat, int ld_diag,
-                            int diag_off, float diag_coef, float* out_f32, int ld_f32,
-                            void* out_bf16_t, int ld_t, float* dbias, void* stream);
-/* (c) dW [E,K] = du_t [E,M] . x_t [K,M]^T  (autograd of nn.Linear / 1x1 conv weight). */
-int cvcl_head_weight_grad(const void* du_t, int ld_du, const void* x_t, int ld_x, int E, int K, int M,
+                            int diag_rows, int diag_off, float diag_coef, float* out_f32, int ld_f32,
+                            void* out_bf16, int ld_bf16, float* dbias, void* stream);
+/* (c) dW [E,K] = sum_m du[m,:]^T x[m,:]  (autograd of nn.Linear / 1x1 conv weight); du [M,E] and
+ *     x [M,K] bf16 as stored (both read MN-major). */
+int cvcl_head_weight_grad(const void* du, int ld_du, const void* x, int ld_x, int E, int K, int M,
                           float* dW, int ld_dw, void* stream);
 
 /* ---- fused flat train step: K1 .. K5 sequenced in one call ----------------------------------

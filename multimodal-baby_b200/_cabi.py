@@ -9,7 +9,7 @@ from ctypes import c_float, c_int, c_int64, c_size_t, c_void_p, c_char_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libcvcl_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class CvclLibraryMissing(RuntimeError):
@@ -30,7 +30,7 @@ PROTOTYPES = {
     "cvcl_abi_version": (c_int, []),
     "cvcl_last_error": (c_char_p, []),
     "cvcl_launch_count": (ctypes.c_ulonglong, []),
-    "cvcl_text_encoder_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _I, _P, _I, _P,
+    "cvcl_text_encoder_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _I, _P,
                                       _P, _P, _P, _P]),
     "cvcl_embedding_gather": (c_int, [_P, _P, _P, _I, _I, _I, _P]),
     "cvcl_embedding_scatter_add": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
@@ -39,17 +39,17 @@ PROTOTYPES = {
     "cvcl_cast_transpose": (c_int, [_P, _I, _P, _P, _I, _I, _I, _L, _L, _L, _L, _L, _L, _P]),
     "cvcl_rownorm_bwd": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P]),
     "cvcl_spatial_pool": (c_int, [_P, _I, _I, _I, _P, _P, _I, _P, _I, _P]),
-    "cvcl_head_proj_norm_fwd": (c_int, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _P]),
+    "cvcl_head_proj_norm_fwd": (c_int, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P]),
     "cvcl_sim_workspace_bytes": (c_size_t, [_I, _I, _I, _I]),
     "cvcl_sim_infonce_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _F, _P, _P, _P, _P,
                                      _P, _P, _P]),
     "cvcl_sim_logits_fwd": (c_int, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P]),
     "cvcl_sim_infonce_bwd_g": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _F, _P, _P, _P, _P,
                                        _P, _I, _P, _I, _P, _P]),
-    "cvcl_feat_grad_norm_bwd": (c_int, [_P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _I, _I, _F,
-                                        _P, _I, _P, _I, _P, _P]),
+    "cvcl_feat_grad_norm_bwd": (c_int, [_P, _I, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _I, _I, _I,
+                                        _F, _P, _I, _P, _I, _P, _P]),
     "cvcl_head_weight_grad": (c_int, [_P, _I, _P, _I, _I, _I, _I, _P, _I, _P]),
-    "cvcl_gemm_nt_f32out": (c_int, [_P, _I, _P, _I, _I, _I, _I, _F, _P, _I, _P]),
+    "cvcl_gemm_f32out": (c_int, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _F, _P, _I, _P]),
     "cvcl_flat_step_workspace_bytes": (c_size_t, [_I, _I, _I, _I, _I]),
     "cvcl_flat_contrastive_step": (c_int, [_P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P,
                                            _P, _P, _P, _P, _P, _P, _P, _P, _P]),

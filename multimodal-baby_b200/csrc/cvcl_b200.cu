@@ -55,7 +55,7 @@ unsigned long long cvcl_launch_count(void) { return __atomic_load_n(&launch_coun
 // ------------------------------------------------------------------------------------ K1
 int cvcl_text_encoder_fwd(const int64_t* ids, const int64_t* lens, const float* table,
                           int B, int L, int E, int V, int normalize, int per_token, float pool_scale,
-                          float* feat_f32, void* feat_bf16, int ld_bf16, void* feat_bf16_t, int ld_t,
+                          float* feat_f32, void* feat_bf16, int ld_bf16,
                           float* inv_norm, float* tok_f32, void* tok_bf16, int* status, void* stream) {
     if (B == 0) return CVCL_OK;
     CVCL_REQUIRE(ids && lens && table, "text_encoder_fwd: null input");
@@ -68,7 +68,6 @@ int cvcl_text_encoder_fwd(const int64_t* ids, const int64_t* lens, const float* 
     p.table = table; p.B = B; p.L = L; p.E = E; p.V = V; p.normalize = normalize; p.per_token = per_token;
     p.pool_scale = pool_scale; p.feat_f32 = feat_f32;
     p.feat_bf16 = static_cast<__nv_bfloat16*>(feat_bf16); p.ld_bf16 = ld_bf16;
-    p.feat_bf16_t = static_cast<__nv_bfloat16*>(feat_bf16_t); p.ld_t = ld_t;
     p.inv_norm = inv_norm; p.tok_f32 = tok_f32; p.tok_bf16 = static_cast<__nv_bfloat16*>(tok_bf16);
     p.status = status;
     text_encoder_fwd_kernel<<<warps_grid(B), 256, 0, as_stream(stream)>>>(p);
@@ -179,33 +178,48 @@ int cvcl_spatial_pool(const float* src, int B, int HW, int E, float* out_f32, vo
     return CVCL_OK;
 }
 
-int cvcl_gemm_nt_f32out(const void* A, int lda, const void* Bm, int ldb, int M, int N, int K, float alpha,
-                        float* C, int ldc, void* stream) {
-    CVCL_REQUIRE(A && Bm && C, "gemm_nt_f32out: null pointer");
-    CVCL_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_nt_f32out: bad shape");
-    GemmOperands op{}; op.A[0] = A; op.ld_a[0] = lda; op.B[0] = Bm; op.ld_b[0] = ldb; op.ndir = 1;
+int cvcl_gemm_f32out(const void* A, int lda, int a_mn, const void* Bm, int ldb, int b_mn, int M, int N, int K,
+                     float alpha, float* C, int ldc, void* stream) {
+    CVCL_REQUIRE(A && Bm && C, "gemm_f32out: null pointer");
+    CVCL_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_f32out: bad shape");
+    GemmOperands op{}; op.ndir = 1;
+    op.A[0] = a_mn ? mat(A, K, M, lda) : mat(A, M, K, lda);
+    op.B[0] = b_mn ? mat(Bm, K, N, ldb) : mat(Bm, N, K, ldb);
+    op.out[0] = mat(C, M, N, ldc);
     GemmShape gs{}; gs.M[0] = gs.M[1] = M; gs.N[0] = gs.N[1] = N; gs.K = K; gs.m_stride = kBM; gs.n_stride = kBN;
-    EpiStoreF32::Params ep{}; ep.C[0] = ep.C[1] = C; ep.ldc[0] = ep.ldc[1] = ldc; ep.alpha = alpha;
-    return launch_gemm<kBN, kStages, EpiStoreF32>(op, gs, ep, 1, as_stream(stream));
+    cudaStream_t st = as_stream(stream);
+    if ((ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) {
+        EpiStoreF32::Params ep{}; ep.alpha = alpha;
+        if (!a_mn && !b_mn) return launch_gemm<kBN, kStages, EpiStoreF32, false, false>(op, gs, ep, 1, st);
+        if (!a_mn && b_mn) return launch_gemm<kBN, kStages, EpiStoreF32, false, true>(op, gs, ep, 1, st);
+        if (a_mn && !b_mn) return launch_gemm<kBN, kStages, EpiStoreF32, true, false>(op, gs, ep, 1, st);
+        return launch_gemm<kBN, kStages, EpiStoreF32, true, true>(op, gs, ep, 1, st);
+    }
+    EpiStoreF32Direct::Params ep{}; ep.C[0] = ep.C[1] = C; ep.ldc[0] = ep.ldc[1] = ldc; ep.alpha = alpha;
+    if (!a_mn && !b_mn) return launch_gemm<kBN, kStages, EpiStoreF32Direct, false, false>(op, gs, ep, 1, st);
+    if (!a_mn && b_mn) return launch_gemm<kBN, kStages, EpiStoreF32Direct, false, true>(op, gs, ep, 1, st);
+    if (a_mn && !b_mn) return launch_gemm<kBN, kStages, EpiStoreF32Direct, true, false>(op, gs, ep, 1, st);
+    return launch_gemm<kBN, kStages, EpiStoreF32Direct, true, true>(op, gs, ep, 1, st);
 }
 
 // ------------------------------------------------------------------------------------ K2
 int cvcl_head_proj_norm_fwd(const void* x, int ldx, const void* w, int ldw, const float* bias,
                             int M, int E, int K, int normalize,
                             float* out_f32, int ld_f32, void* out_bf16, int ld_bf16,
-                            void* out_bf16_t, int ld_t, float* inv_norm, void* stream) {
+                            float* inv_norm, void* stream) {
     CVCL_REQUIRE(x && w, "head_proj_norm_fwd: null operand");
     CVCL_REQUIRE(M > 0 && E > 0 && K > 0, "head_proj_norm_fwd: bad shape M=%d E=%d K=%d", M, E, K);
     const int cluster = ceil_div(E, kBN);
     if (cluster > 8)
         return fail(CVCL_ERR_UNSUPPORTED, "head_proj_norm_fwd: E=%d needs a cluster of %d > 8 CTAs", E, cluster);
-    GemmOperands op{}; op.A[0] = x; op.ld_a[0] = ldx; op.B[0] = w; op.ld_b[0] = ldw; op.ndir = 1;
+    GemmOperands op{}; op.ndir = 1;
+    op.A[0] = mat(x, M, K, ldx); op.B[0] = mat(w, E, K, ldw);
+    op.out[0] = out_bf16 ? mat(out_bf16, M, E, ld_bf16) : mat(x, M, K, ldx);
     GemmShape gs{}; gs.M[0] = gs.M[1] = M; gs.N[0] = gs.N[1] = E; gs.K = K; gs.m_stride = kBM; gs.n_stride = kBN;
     EpiHeadNorm::Params ep{};
     ep.bias = bias; ep.normalize = normalize; ep.out_f32 = out_f32; ep.ld_f32 = ld_f32;
-    ep.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); ep.ld_bf16 = ld_bf16;
-    ep.out_bf16_t = static_cast<__nv_bfloat16*>(out_bf16_t); ep.ld_t = ld_t; ep.inv_norm = inv_norm;
-    return launch_gemm<kBN, kStages, EpiHeadNorm>(op, gs, ep, cluster, as_stream(stream));
+    ep.store_bf16 = out_bf16 != nullptr; ep.inv_norm = inv_norm;
+    return launch_gemm<kBN, kStages, EpiHeadNorm, false, false>(op, gs, ep, cluster, as_stream(stream));
 }
 
 // ------------------------------------------------------------------------------------ K3+K4
@@ -226,8 +240,8 @@ int cvcl_sim_infonce_fwd(const void* img_q, const void* txt_k, const void* txt_q
     SimWs w = carve_sim_ws(workspace, M0, N0, M1, N1);
     CVCL_CHECK_CUDA(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned int), as_stream(stream)));
     GemmOperands op{}; op.ndir = 2;
-    op.A[0] = img_q; op.B[0] = txt_k; op.A[1] = txt_q; op.B[1] = img_k;
-    op.ld_a[0] = op.ld_a[1] = op.ld_b[0] = op.ld_b[1] = ld;
+    op.A[0] = mat(img_q, M0, E, ld); op.B[0] = mat(txt_k, N0, E, ld);
+    op.A[1] = mat(txt_q, M1, E, ld); op.B[1] = mat(img_k, N1, E, ld);
     GemmShape gs{}; gs.M[0] = M0; gs.N[0] = N0; gs.M[1] = M1; gs.N[1] = N1; gs.K = E;
     gs.m_stride = kBM; gs.n_stride = kBN;
     EpiSimStats::Params ep{};
@@ -235,7 +249,7 @@ int cvcl_sim_infonce_fwd(const void* img_q, const void* txt_k, const void* txt_q
     for (int z = 0; z < 2; ++z) {
         ep.diag_off[z] = diag_off; ep.part[z] = w.part[z]; ep.m_pad[z] = w.m_pad[z]; ep.diag[z] = w.diag[z];
     }
-    int rc = launch_gemm<kBN, kStages, EpiSimStats>(op, gs, ep, 1, as_stream(stream));
+    int rc = launch_gemm<kBN, kStages, EpiSimStats, false, false>(op, gs, ep, 1, as_stream(stream));
     if (rc) return rc;
     FinalizeParams fp{};
     for (int z = 0; z < 2; ++z) {
@@ -255,16 +269,11 @@ int cvcl_sim_logits_fwd(const void* img, const void* txt, int ld, int Ni, int Nt
                         float* lpi, float* lpt, void* stream) {
     CVCL_REQUIRE(img && txt && (lpi || lpt), "sim_logits_fwd: null pointer");
     CVCL_REQUIRE(Ni > 0 && Nt > 0 && E > 0, "sim_logits_fwd: bad shape Ni=%d Nt=%d E=%d", Ni, Nt, E);
-    EpiStoreF32::Params ep{}; ep.alpha = expf(log_scale);
-    GemmShape gs{}; gs.K = E; gs.m_stride = kBM; gs.n_stride = kBN;
-    GemmOperands op{};
-    int z = 0;
-    if (lpi) { op.A[z] = img; op.B[z] = txt; gs.M[z] = Ni; gs.N[z] = Nt; ep.C[z] = lpi; ep.ldc[z] = Nt; ++z; }
-    if (lpt) { op.A[z] = txt; op.B[z] = img; gs.M[z] = Nt; gs.N[z] = Ni; ep.C[z] = lpt; ep.ldc[z] = Ni; ++z; }
-    op.ndir = z;
-    for (int i = 0; i < 2; ++i) { op.ld_a[i] = ld; op.ld_b[i] = ld; }
-    if (z == 1) { gs.M[1] = gs.M[0]; gs.N[1] = gs.N[0]; ep.C[1] = ep.C[0]; ep.ldc[1] = ep.ldc[0]; }
-    return launch_gemm<kBN, kStages, EpiStoreF32>(op, gs, ep, 1, as_stream(stream));
+    const float alpha = expf(log_scale);
+    int rc = 0;
+    if (lpi) rc = cvcl_gemm_f32out(img, ld, 0, txt, ld, 0, Ni, Nt, E, alpha, lpi, Nt, stream);
+    if (!rc && lpt) rc = cvcl_gemm_f32out(txt, ld, 0, img, ld, 0, Nt, Ni, E, alpha, lpt, Ni, stream);
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------ K5
@@ -273,60 +282,73 @@ int cvcl_sim_infonce_bwd_g(const void* img_q, const void* txt_k, const void* txt
                            float coef, const float* lse_q0, const float* lse_k0, const float* lse_q1,
                            const float* lse_k1, void* Gs0, int ldg0, void* Gs1, int ldg1, float* dscale,
                            void* stream) {
-    CVCL_REQUIRE(img_q && txt_k && txt_q && img_k && lse_q0 && lse_k0 && lse_q1 && lse_k1 && Gs0 && Gs1,
-                 "sim_infonce_bwd_g: null pointer");
-    CVCL_REQUIRE(M0 > 0 && N0 > 0 && M1 > 0 && N1 > 0 && E > 0, "sim_infonce_bwd_g: bad shape");
-    GemmOperands op{}; op.ndir = 2;
-    op.A[0] = img_q; op.B[0] = txt_k; op.A[1] = txt_q; op.B[1] = img_k;
-    op.ld_a[0] = op.ld_a[1] = op.ld_b[0] = op.ld_b[1] = ld;
-    GemmShape gs{}; gs.M[0] = M0; gs.N[0] = N0; gs.M[1] = M1; gs.N[1] = N1; gs.K = E;
-    gs.m_stride = kBM; gs.n_stride = kBN;
+    CVCL_REQUIRE(img_q && txt_k && lse_q0 && lse_k0 && Gs0, "sim_infonce_bwd_g: null pointer");
+    CVCL_REQUIRE(!Gs1 || (txt_q && img_k && lse_q1 && lse_k1), "sim_infonce_bwd_g: direction 1 needs its operands");
+    CVCL_REQUIRE(M0 > 0 && N0 > 0 && E > 0, "sim_infonce_bwd_g: bad shape");
+    GemmOperands op{}; op.ndir = Gs1 ? 2 : 1;
+    op.A[0] = mat(img_q, M0, E, ld); op.B[0] = mat(txt_k, N0, E, ld); op.out[0] = mat(Gs0, M0, N0, ldg0);
+    GemmShape gs{}; gs.M[0] = gs.M[1] = M0; gs.N[0] = gs.N[1] = N0; gs.K = E; gs.m_stride = kBM; gs.n_stride = kBN;
     EpiGradG::Params ep{};
     ep.scale = expf(log_scale); ep.coef = coef; ep.diag_off[0] = ep.diag_off[1] = diag_off;
-    ep.lse_q[0] = lse_q0; ep.lse_k[0] = lse_k0; ep.lse_q[1] = lse_q1; ep.lse_k[1] = lse_k1;
-    ep.G[0] = static_cast<__nv_bfloat16*>(Gs0); ep.ldg[0] = ldg0;
-    ep.G[1] = static_cast<__nv_bfloat16*>(Gs1); ep.ldg[1] = ldg1;
+    ep.lse_q[0] = ep.lse_q[1] = lse_q0; ep.lse_k[0] = ep.lse_k[1] = lse_k0;
+    if (Gs1) {
+        op.A[1] = mat(txt_q, M1, E, ld); op.B[1] = mat(img_k, N1, E, ld); op.out[1] = mat(Gs1, M1, N1, ldg1);
+        gs.M[1] = M1; gs.N[1] = N1; ep.lse_q[1] = lse_q1; ep.lse_k[1] = lse_k1;
+    }
     ep.dscale_accum = dscale;
-    return launch_gemm<kBN, kStages, EpiGradG>(op, gs, ep, 1, as_stream(stream));
+    return launch_gemm<kBN, kStages, EpiGradG, false, false>(op, gs, ep, 1, as_stream(stream));
 }
 
-int cvcl_feat_grad_norm_bwd(const void* Gs, int ldg, const void* other_t, int ld_other, int M, int E,
-                            int Kc, const void* feat_bf16, int ld_feat, const float* inv_norm,
+int cvcl_feat_grad_norm_bwd(const void* Gs, int ldg, int gs_transposed, const void* other, int ld_other,
+                            int M, int E, int Kc, const void* feat_bf16, int ld_feat, const float* inv_norm,
                             int normalize, const int64_t* row_len, const void* diag_feat, int ld_diag,
-                            int diag_off, float diag_coef, float* out_f32, int ld_f32,
-                            void* out_bf16_t, int ld_t, float* dbias, void* stream) {
-    CVCL_REQUIRE(Gs && other_t, "feat_grad_norm_bwd: null operand");
+                            int diag_rows, int diag_off, float diag_coef, float* out_f32, int ld_f32,
+                            void* out_bf16, int ld_bf16, float* dbias, void* stream) {
+    CVCL_REQUIRE(Gs && other, "feat_grad_norm_bwd: null operand");
+    CVCL_REQUIRE((out_f32 != nullptr) != (out_bf16 != nullptr), "feat_grad_norm_bwd: exactly one of out_f32 / out_bf16");
     CVCL_REQUIRE(!normalize || (feat_bf16 && inv_norm), "feat_grad_norm_bwd: normalize needs feat and inv_norm");
+    CVCL_REQUIRE(feat_bf16 || diag_feat, "feat_grad_norm_bwd: needs feat or diag_feat (use cvcl_gemm_f32out otherwise)");
     CVCL_REQUIRE(M > 0 && E > 0 && Kc > 0, "feat_grad_norm_bwd: bad shape");
     const int cluster = ceil_div(E, kBN);
     if (cluster > 8)
         return fail(CVCL_ERR_UNSUPPORTED, "feat_grad_norm_bwd: E=%d needs a cluster of %d > 8 CTAs", E, cluster);
-    GemmOperands op{}; op.A[0] = Gs; op.ld_a[0] = ldg; op.B[0] = other_t; op.ld_b[0] = ld_other; op.ndir = 1;
+    GemmOperands op{}; op.ndir = 1;
+    op.A[0] = gs_transposed ? mat(Gs, Kc, M, ldg) : mat(Gs, M, Kc, ldg);
+    op.B[0] = mat(other, Kc, E, ld_other);                         // MN-major: features as stored
+    const Mat fm = feat_bf16 ? mat(feat_bf16, M, E, ld_feat) : mat(diag_feat, diag_rows, E, ld_diag);
+    const Mat dm = diag_feat ? mat(diag_feat, diag_rows, E, ld_diag) : fm;
+    op.aux[0] = fm; op.aux[1] = dm;
+    op.out[0] = out_f32 ? mat(out_f32, M, E, ld_f32) : mat(out_bf16, M, E, ld_bf16);
     GemmShape gs{}; gs.M[0] = gs.M[1] = M; gs.N[0] = gs.N[1] = E; gs.K = Kc; gs.m_stride = kBM; gs.n_stride = kBN;
-    EpiNormBwd::Params ep{};
-    ep.feat = static_cast<const __nv_bfloat16*>(feat_bf16); ep.ld_feat = ld_feat; ep.inv_norm = inv_norm;
-    ep.normalize = normalize; ep.row_len = reinterpret_cast<const long long*>(row_len);
-    ep.diag_feat = static_cast<const __nv_bfloat16*>(diag_feat); ep.ld_diag = ld_diag;
-    ep.diag_off = diag_off; ep.diag_coef = diag_coef;
-    ep.out_f32 = out_f32; ep.ld_f32 = ld_f32;
-    ep.out_bf16_t = static_cast<__nv_bfloat16*>(out_bf16_t); ep.ld_t = ld_t; ep.dbias = dbias;
-    return launch_gemm<kBN, kStages, EpiNormBwd>(op, gs, ep, cluster, as_stream(stream));
+    gs.aux_row_off[0] = 0; gs.aux_row_off[1] = diag_feat ? diag_off : 0;
+    cudaStream_t st = as_stream(stream);
+    constexpr int kSt = 3;                                         // 2 aux tiles share the smem budget
+    if (out_f32) {
+        EpiNormBwdT<true>::Params ep{};
+        ep.inv_norm = inv_norm; ep.normalize = normalize; ep.row_len = reinterpret_cast<const long long*>(row_len);
+        ep.use_diag = diag_feat != nullptr; ep.diag_coef = diag_coef; ep.dbias = dbias;
+        return gs_transposed ? launch_gemm<kBN, kSt, EpiNormBwdT<true>, true, true>(op, gs, ep, cluster, st)
+                             : launch_gemm<kBN, kSt, EpiNormBwdT<true>, false, true>(op, gs, ep, cluster, st);
+    }
+    EpiNormBwdT<false>::Params ep{};
+    ep.inv_norm = inv_norm; ep.normalize = normalize; ep.row_len = reinterpret_cast<const long long*>(row_len);
+    ep.use_diag = diag_feat != nullptr; ep.diag_coef = diag_coef; ep.dbias = dbias;
+    return gs_transposed ? launch_gemm<kBN, kSt, EpiNormBwdT<false>, true, true>(op, gs, ep, cluster, st)
+                         : launch_gemm<kBN, kSt, EpiNormBwdT<false>, false, true>(op, gs, ep, cluster, st);
 }
 
-int cvcl_head_weight_grad(const void* du_t, int ld_du, const void* x_t, int ld_x, int E, int K, int M,
+int cvcl_head_weight_grad(const void* du, int ld_du, const void* x, int ld_x, int E, int K, int M,
                           float* dW, int ld_dw, void* stream) {
-    CVCL_REQUIRE(du_t && x_t && dW, "head_weight_grad: null pointer");
+    CVCL_REQUIRE(du && x && dW, "head_weight_grad: null pointer");
     CVCL_REQUIRE(E > 0 && K > 0 && M > 0, "head_weight_grad: bad shape");
-    GemmOperands op{}; op.A[0] = du_t; op.ld_a[0] = ld_du; op.B[0] = x_t; op.ld_b[0] = ld_x; op.ndir = 1;
-    GemmShape gs{}; gs.M[0] = gs.M[1] = E; gs.N[0] = gs.N[1] = K; gs.K = M; gs.m_stride = kBM; gs.n_stride = kBN;
-    EpiStoreF32::Params ep{}; ep.C[0] = ep.C[1] = dW; ep.ldc[0] = ep.ldc[1] = ld_dw; ep.alpha = 1.f;
-    return launch_gemm<kBN, kStages, EpiStoreF32>(op, gs, ep, 1, as_stream(stream));
+    // dW[e,k] = sum_m du[m,e] * x[m,k]: both operands MN-major (the contraction index m strides)
+    return cvcl_gemm_f32out(du, ld_du, 1, x, ld_x, 1, E, K, M, 1.f, dW, ld_dw, stream);
 }
 
 // ------------------------------------------------------------------------------------ fused flat step
 namespace {
 struct FlatWs {
-    __nv_bfloat16 *w16, *x16, *x16t, *img16, *img16t, *txt16, *txt16t, *G0, *G1, *du16t;
+    __nv_bfloat16 *w16, *x16, *img16, *txt16, *G0, *du16;
     float *invn_i, *invn_t, *lse0, *lse1, *dm;
     void* sim; int ldB; size_t bytes;
 };
@@ -339,14 +361,10 @@ FlatWs carve_flat_ws(void* ws, int B, int L, int E, int K, int V) {
     auto take = [&](size_t bytes) { void* p = base + off; off += align_up(bytes, 256); return p; };
     f.w16 = static_cast<__nv_bfloat16*>(take(2ull * E * K));
     f.x16 = static_cast<__nv_bfloat16*>(take(2ull * B * K));
-    f.x16t = static_cast<__nv_bfloat16*>(take(2ull * K * f.ldB));
     f.img16 = static_cast<__nv_bfloat16*>(take(2ull * B * E));
-    f.img16t = static_cast<__nv_bfloat16*>(take(2ull * E * f.ldB));
     f.txt16 = static_cast<__nv_bfloat16*>(take(2ull * B * E));
-    f.txt16t = static_cast<__nv_bfloat16*>(take(2ull * E * f.ldB));
     f.G0 = static_cast<__nv_bfloat16*>(take(2ull * B * f.ldB));
-    f.G1 = static_cast<__nv_bfloat16*>(take(2ull * B * f.ldB));
-    f.du16t = static_cast<__nv_bfloat16*>(take(2ull * E * f.ldB));
+    f.du16 = static_cast<__nv_bfloat16*>(take(2ull * B * E));
     f.invn_i = static_cast<float*>(take(4ull * B));
     f.invn_t = static_cast<float*>(take(4ull * B));
     f.lse0 = static_cast<float*>(take(4ull * B));
@@ -376,31 +394,35 @@ int cvcl_flat_contrastive_step(const void* x, int x_is_bf16, const int64_t* ids,
     cudaStream_t st = as_stream(stream);
     FlatWs f = carve_flat_ws(workspace, B, L, E, K, V);
     int rc;
-    // operand staging: bf16 copies of the master weight and the trunk features (+ transpose for dW)
+    // operand staging: bf16 copy of the master weight; trunk features are used in place when bf16
     if ((rc = cvcl_cast_transpose(w, 0, f.w16, nullptr, 1, E, K, K, K, 0, 0, 0, 0, stream))) return rc;
-    if ((rc = cvcl_cast_transpose(x, x_is_bf16, f.x16, need_grads ? f.x16t : nullptr, 1, B, K, K, K, f.ldB, 0, 0, 0, stream))) return rc;
+    const void* x16 = x;
+    if (!x_is_bf16 || (reinterpret_cast<uintptr_t>(x) & 15)) {
+        if ((rc = cvcl_cast_transpose(x, x_is_bf16, f.x16, nullptr, 1, B, K, K, K, 0, 0, 0, 0, stream))) return rc;
+        x16 = f.x16;
+    }
     // K1, K2
     if ((rc = cvcl_text_encoder_fwd(ids, lens, table, B, L, E, V, normalize, 0, 1.f, txt_feat_f32, f.txt16, E,
-                                    need_grads ? f.txt16t : nullptr, f.ldB, f.invn_t, nullptr, nullptr, status, stream))) return rc;
-    if ((rc = cvcl_head_proj_norm_fwd(f.x16, K, f.w16, K, bias, B, E, K, normalize, img_feat_f32, E, f.img16, E,
-                                      need_grads ? f.img16t : nullptr, f.ldB, f.invn_i, stream))) return rc;
+                                    f.invn_t, nullptr, nullptr, status, stream))) return rc;
+    if ((rc = cvcl_head_proj_norm_fwd(x16, K, f.w16, K, bias, B, E, K, normalize, img_feat_f32, E, f.img16, E,
+                                      f.invn_i, stream))) return rc;
     // K3 + K4
     if ((rc = cvcl_sim_infonce_fwd(f.img16, f.txt16, f.txt16, f.img16, E, B, B, B, B, E, log_scale, 0,
                                    1.f / static_cast<float>(B), f.sim, f.lse0, f.lse1, nullptr, nullptr, out5, stream))) return rc;
     if (!need_grads) return CVCL_OK;
-    // K5
+    // K5: Gs (one orientation) -> dI (K-major Gs) and dT (the same Gs read MN-major) -> dW -> scatter
     CVCL_CHECK_CUDA(cudaMemsetAsync(dscale, 0, sizeof(float), st));
     CVCL_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * E, st));
     CVCL_CHECK_CUDA(cudaMemsetAsync(dtable, 0, sizeof(float) * static_cast<size_t>(V) * E, st));
-    if ((rc = cvcl_sim_infonce_bwd_g(f.img16, f.txt16, f.txt16, f.img16, E, B, B, B, B, E, log_scale, 0,
-                                     0.5f / static_cast<float>(B), f.lse0, f.lse1, f.lse1, f.lse0,
-                                     f.G0, f.ldB, f.G1, f.ldB, dscale, stream))) return rc;
-    const float dcoef = -2.f * expf(log_scale) * 0.5f / static_cast<float>(B);
-    if ((rc = cvcl_feat_grad_norm_bwd(f.G0, f.ldB, f.txt16t, f.ldB, B, E, B, f.img16, E, f.invn_i, normalize,
-                                      nullptr, f.txt16, E, 0, dcoef, nullptr, 0, f.du16t, f.ldB, dbias, stream))) return rc;
-    if ((rc = cvcl_feat_grad_norm_bwd(f.G1, f.ldB, f.img16t, f.ldB, B, E, B, f.txt16, E, f.invn_t, normalize,
-                                      lens, f.img16, E, 0, dcoef, f.dm, E, nullptr, 0, nullptr, stream))) return rc;
-    if ((rc = cvcl_head_weight_grad(f.du16t, f.ldB, f.x16t, f.ldB, E, K, B, dW, K, stream))) return rc;
+    const float coef = 0.5f / static_cast<float>(B);
+    if ((rc = cvcl_sim_infonce_bwd_g(f.img16, f.txt16, nullptr, nullptr, E, B, B, 0, 0, E, log_scale, 0, coef,
+                                     f.lse0, f.lse1, nullptr, nullptr, f.G0, f.ldB, nullptr, 0, dscale, stream))) return rc;
+    const float dcoef = -2.f * expf(log_scale) * coef;
+    if ((rc = cvcl_feat_grad_norm_bwd(f.G0, f.ldB, 0, f.txt16, E, B, E, B, f.img16, E, f.invn_i, normalize,
+                                      nullptr, f.txt16, E, B, 0, dcoef, nullptr, 0, f.du16, E, dbias, stream))) return rc;
+    if ((rc = cvcl_feat_grad_norm_bwd(f.G0, f.ldB, 1, f.img16, E, B, E, B, f.txt16, E, f.invn_t, normalize,
+                                      lens, f.img16, E, B, 0, dcoef, f.dm, E, nullptr, 0, nullptr, stream))) return rc;
+    if ((rc = cvcl_head_weight_grad(f.du16, E, x16, K, E, K, B, dW, K, stream))) return rc;
     if ((rc = cvcl_embedding_scatter_add(ids, f.dm, dtable, B, L, E, V, 0, stream))) return rc;
     return CVCL_OK;
 }
@@ -417,10 +439,11 @@ int cvcl_spatial_max_fwd(const void* tok, const void* img, const int64_t* lens, 
     if (ep.IPN > EpiSpatialMax::kMaxIPN) ep.IPN = EpiSpatialMax::kMaxIPN;
     ep.lens = reinterpret_cast<const long long*>(lens); ep.match = match;
     ep.amax_it = amax_it; ep.amax_ti = amax_ti;
-    GemmOperands op{}; op.A[0] = tok; op.ld_a[0] = E; op.B[0] = img; op.ld_b[0] = E; op.ndir = 1;
+    GemmOperands op{}; op.ndir = 1;
+    op.A[0] = mat(tok, Bt * L, E, E); op.B[0] = mat(img, Bi * HW, E, E);
     GemmShape gs{}; gs.M[0] = gs.M[1] = Bt * L; gs.N[0] = gs.N[1] = Bi * HW; gs.K = E;
     gs.m_stride = ep.TPM * L; gs.n_stride = ep.IPN * HW;
-    return launch_gemm<BN, 4, EpiSpatialMax>(op, gs, ep, 1, as_stream(stream));
+    return launch_gemm<BN, 4, EpiSpatialMax, false, false>(op, gs, ep, 1, as_stream(stream));
 }
 
 int cvcl_spatial_max_bwd(const float* gmatch, const int64_t* lens, const int64_t* ids,

@@ -1,35 +1,62 @@
-// Host launcher for gemm_tn_bf16_kernel: tensor maps, cluster attribute, dynamic smem opt-in.
+// Host launcher for gemm_bf16_kernel: tensor maps, cluster attribute, dynamic smem opt-in.
 #pragma once
 #include "gemm_sm100.cuh"
 #include "host_util.h"
 
 namespace cvcl {
 
-struct GemmOperands {           // per direction: A [M,K] ld_a, B [N,K] ld_b (bf16, row-major)
-    const void* A[2]; int ld_a[2];
-    const void* B[2]; int ld_b[2];
+struct Mat {                    // a row-major matrix as it sits in memory
+    const void* ptr; int rows, cols, ld;
+};
+inline Mat mat(const void* p, int rows, int cols, int ld) { Mat m; m.ptr = p; m.rows = rows; m.cols = cols; m.ld = ld; return m; }
+
+struct GemmOperands {
+    Mat A[2], B[2];             // per direction; K-major: [M or N, K]; MN-major: [K, M or N]
+    Mat aux[2];                 // epilogue input tiles, bf16 [M, N]   (Epi::kNumAux of them)
+    Mat out[2];                 // epilogue output per direction, [M, N] bf16 / fp32 (Epi::kOutElemBytes)
     int ndir;                   // 1 or 2
 };
 
-template <int BN, int STAGES, class Epi>
+template <int BN, int STAGES, class Epi, bool A_MN, bool B_MN>
 int launch_gemm(const GemmOperands& op, const GemmShape& gs, const typename Epi::Params& ep,
                 int cluster_n, cudaStream_t stream) {
-    using L = GemmSmem<BN, STAGES>;
+    using L = GemmSmem<BN, STAGES, Epi::kNumAux>;
     constexpr int smem_bytes = L::template total<Epi>();
     static_assert(smem_bytes <= 227 * 1024, "shared memory budget");
-    auto kern = gemm_tn_bf16_kernel<BN, STAGES, Epi>;
+    auto kern = gemm_bf16_kernel<BN, STAGES, Epi, A_MN, B_MN>;
     static thread_local bool attr_done = false;
     if (!attr_done) {
         CVCL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         attr_done = true;
     }
-    CUtensorMap maps[4];
+    GemmMaps maps;
+    int rc;
     for (int z = 0; z < 2; ++z) {
         const int zz = z < op.ndir ? z : 0;
-        int rc = make_tmap_bf16(&maps[2 * z], op.A[zz], gs.M[zz], gs.K, op.ld_a[zz], kBM);
+        const Mat& a = op.A[zz]; const Mat& b = op.B[zz];
+        if (A_MN) rc = make_tmap(&maps.a[z], a.ptr, 2, a.rows, a.cols, a.ld, 64, kBK);
+        else      rc = make_tmap(&maps.a[z], a.ptr, 2, a.rows, a.cols, a.ld, 64, kBM);
         if (rc) return rc;
-        rc = make_tmap_bf16(&maps[2 * z + 1], op.B[zz], gs.N[zz], gs.K, op.ld_b[zz], BN);
+        if (B_MN) rc = make_tmap(&maps.b[z], b.ptr, 2, b.rows, b.cols, b.ld, 64, kBK);
+        else      rc = make_tmap(&maps.b[z], b.ptr, 2, b.rows, b.cols, b.ld, 64, BN);
         if (rc) return rc;
+        if (Epi::kOutElemBytes) {
+            const Mat& o = op.out[zz];
+            rc = make_tmap(&maps.out[z], o.ptr, Epi::kOutElemBytes, o.rows, o.cols, o.ld,
+                           128 / Epi::kOutElemBytes, kBM);
+            if (rc) return rc;
+        } else {
+            maps.out[z] = maps.a[z];
+        }
+    }
+    for (int i = 0; i < 2; ++i) {
+        if (i < Epi::kNumAux) {
+            const Mat& x = op.aux[i];
+            rc = make_tmap(&maps.aux[i], x.ptr, 2, x.rows, x.cols, x.ld, 64, kBM);
+            if (rc) return rc;
+        } else {
+            maps.aux[i] = maps.a[0];
+        }
     }
     int max_m = gs.M[0], max_n = gs.N[0];
     if (op.ndir == 2) { max_m = max_m > gs.M[1] ? max_m : gs.M[1]; max_n = max_n > gs.N[1] ? max_n : gs.N[1]; }
@@ -47,7 +74,7 @@ int launch_gemm(const GemmOperands& op, const GemmShape& gs, const typename Epi:
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    CVCL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], gs, ep));
+    CVCL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, gs, ep));
     count_launch();
     return CVCL_OK;
 }

@@ -27,11 +27,19 @@ constexpr int kGemmThreads = 192;
 constexpr int kEpiThreads = 128;
 
 struct GemmShape {
-    int M[2];            // rows of A per direction
-    int N[2];            // rows of B per direction
+    int M[2];            // rows of the output per direction
+    int N[2];            // columns of the output per direction
     int K;               // contraction length (same for both directions)
     int m_stride;        // tile origin step along M (kBM unless tiles overlap/segment)
     int n_stride;        // tile origin step along N
+    int aux_row_off[2];  // row offset of each epilogue input tile relative to m0
+};
+
+// All tensor maps of one launch (passed as a single __grid_constant__ parameter).
+struct alignas(64) GemmMaps {
+    CUtensorMap a[2], b[2];   // operands per direction
+    CUtensorMap aux[2];       // epilogue INPUT tiles, bf16 [M,N] row-major (e.g. features, positives)
+    CUtensorMap out[2];       // epilogue OUTPUT tile per direction (bf16 or fp32, [M,N] row-major)
 };
 
 struct EpiCtx {
@@ -41,40 +49,91 @@ struct EpiCtx {
     int tile_m, tile_n;  // tile indices
     int epi_tid;         // 0..127
     unsigned char* scratch;
+    unsigned char* aux[2];          // smem: epilogue input tiles (128B-swizzled TMA boxes)
+    unsigned char* out_stage;       // smem: output staging (reuses the operand ring after the mainloop)
+    const CUtensorMap* out_map;
 };
 
-template <int BN, int STAGES>
+// ---- swizzled shared-memory tile access (layout written / read by TMA with SWIZZLE_128B) --------
+// A tile is a sequence of boxes of 128 rows x 128 bytes; box b covers byte columns [128b, 128b+128).
+// Row r of a box sits at r*128; its 16-byte chunk c is stored at chunk position c ^ (r & 7).
+__device__ __forceinline__ unsigned char* swz_ptr(unsigned char* tile, int row, int byte_col) {
+    const int box = byte_col >> 7, chunk = (byte_col & 127) >> 4;
+    return tile + box * (kBM * 128) + row * 128 + ((chunk ^ (row & 7)) << 4);
+}
+__device__ __forceinline__ uint4 swz_ld16(unsigned char* tile, int row, int byte_col) {
+    return *reinterpret_cast<const uint4*>(swz_ptr(tile, row, byte_col));
+}
+__device__ __forceinline__ void swz_st16(unsigned char* tile, int row, int byte_col, uint4 v) {
+    *reinterpret_cast<uint4*>(swz_ptr(tile, row, byte_col)) = v;
+}
+__device__ __forceinline__ uint4 pack_bf16x8(const float* v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    uint4 q;
+    q.x = *reinterpret_cast<uint32_t*>(&a); q.y = *reinterpret_cast<uint32_t*>(&b);
+    q.z = *reinterpret_cast<uint32_t*>(&c); q.w = *reinterpret_cast<uint32_t*>(&d);
+    return q;
+}
+__device__ __forceinline__ void unpack_bf16x8(uint4 q, float* v) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h[k]); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
+}
+// After every epilogue thread has written its row into out_stage: publish to the async proxy,
+// then one thread stores the boxes with TMA (rows / columns beyond the tensor are clipped).
+template <int BN, int ELEM>
+__device__ __forceinline__ void out_tile_commit(const EpiCtx& cx) {
+    ptx::fence_proxy_async_smem();
+    ptx::named_bar_sync(2, kEpiThreads);
+    if (cx.epi_tid == 0) {
+        constexpr int kBoxCols = 128 / ELEM;
+#pragma unroll
+        for (int b = 0; b < BN / kBoxCols; ++b)
+            ptx::tma_store_2d(cx.out_map, cx.out_stage + b * (kBM * 128), cx.n0 + b * kBoxCols, cx.m0);
+        ptx::tma_store_commit_and_wait();
+    }
+}
+
+template <int BN, int STAGES, int NAUX>
 struct GemmSmem {
     static constexpr int kABytes = kBM * kBK * 2;
     static constexpr int kBBytes = BN * kBK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kBarOff = STAGES * kStageBytes;
+    static constexpr int kAuxBytes = kBM * BN * 2;
+    static constexpr int kAuxOff = STAGES * kStageBytes;
+    static constexpr int kBarOff = kAuxOff + NAUX * kAuxBytes;
     static constexpr int kScratchOff = kBarOff + 256;
     template <class Epi>
     static constexpr int total() { return kScratchOff + Epi::kScratchBytes + 1024 /*align slack*/; }
 };
 
-template <int BN, int STAGES, class Epi>
+// D[m, n] = sum_k A[m, k] * B[n, k].  Operand storage per template flag:
+//   K-major  (flag false): memory [rows = M or N, cols = K] row-major  (contraction contiguous)
+//   MN-major (flag true) : memory [rows = K, cols = M or N] row-major  (contraction strided) --
+//                          lets a backward GEMM consume a forward tensor without a transposed copy.
+template <int BN, int STAGES, class Epi, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tn_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
-                    const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
-                    const GemmShape gs, const typename Epi::Params ep) {
+gemm_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmShape gs, const typename Epi::Params ep) {
     static_assert(BN == 64 || BN == 128 || BN == 256, "BN");
-    using L = GemmSmem<BN, STAGES>;
+    using L = GemmSmem<BN, STAGES, Epi::kNumAux>;
+    static_assert(Epi::kOutElemBytes == 0 || STAGES * L::kStageBytes >= kBM * BN * Epi::kOutElemBytes,
+                  "output staging must fit in the operand ring");
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* aux_bar = tmem_full_bar + 1;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aux_bar + 1);
     unsigned char* scratch = smem + L::kScratchOff;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int z = blockIdx.z;
-    const CUtensorMap* tmA = z ? &tmA1 : &tmA0;
-    const CUtensorMap* tmB = z ? &tmB1 : &tmB0;
+    const CUtensorMap* tmA = &maps.a[z];
+    const CUtensorMap* tmB = &maps.b[z];
     const int m0 = blockIdx.x * gs.m_stride;
     const int n0 = blockIdx.y * gs.n_stride;
     const int num_k = (gs.K + kBK - 1) / kBK;
@@ -87,6 +146,7 @@ gemm_tn_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             ptx::mbar_init(&empty_bar[s], 1);
         }
         ptx::mbar_init(tmem_full_bar, 1);
+        ptx::mbar_init(aux_bar, 1);
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
@@ -100,14 +160,35 @@ gemm_tn_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
+            if constexpr (Epi::kNumAux > 0) {
+                ptx::mbar_arrive_expect_tx(aux_bar, Epi::kNumAux * L::kAuxBytes);
+#pragma unroll
+                for (int i = 0; i < Epi::kNumAux; ++i)
+#pragma unroll
+                    for (int j = 0; j < BN / 64; ++j)
+                        ptx::tma_load_2d(smem + L::kAuxOff + i * L::kAuxBytes + j * (kBM * 128), &maps.aux[i],
+                                         aux_bar, n0 + 64 * j, m0 + gs.aux_row_off[i]);
+            }
             int stage = 0; uint32_t phase = 0;
             for (int kc = 0; kc < num_k; ++kc) {
                 ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                 unsigned char* sa = smem + stage * L::kStageBytes;
                 unsigned char* sb = sa + L::kABytes;
                 ptx::mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
-                ptx::tma_load_2d(sa, tmA, &full_bar[stage], kc * kBK, m0);
-                ptx::tma_load_2d(sb, tmB, &full_bar[stage], kc * kBK, n0);
+                if constexpr (A_MN) {
+#pragma unroll
+                    for (int j = 0; j < kBM / 64; ++j)
+                        ptx::tma_load_2d(sa + j * (kBK * 128), tmA, &full_bar[stage], m0 + 64 * j, kc * kBK);
+                } else {
+                    ptx::tma_load_2d(sa, tmA, &full_bar[stage], kc * kBK, m0);
+                }
+                if constexpr (B_MN) {
+#pragma unroll
+                    for (int j = 0; j < BN / 64; ++j)
+                        ptx::tma_load_2d(sb + j * (kBK * 128), tmB, &full_bar[stage], n0 + 64 * j, kc * kBK);
+                } else {
+                    ptx::tma_load_2d(sb, tmB, &full_bar[stage], kc * kBK, n0);
+                }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -115,19 +196,22 @@ gemm_tn_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
         if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16(kBM, BN);
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(kBM, BN, A_MN, B_MN);
+            // per UMMA_K=16 step the start address advances by 32 B (K-major: inside the swizzle atom)
+            // or by 16 rows * 128 B (MN-major), in 16-byte descriptor units
+            constexpr uint32_t a_step = A_MN ? (kUmmaK * 128) >> 4 : (kUmmaK * 2) >> 4;
+            constexpr uint32_t b_step = B_MN ? (kUmmaK * 128) >> 4 : (kUmmaK * 2) >> 4;
             int stage = 0; uint32_t phase = 0;
             for (int kc = 0; kc < num_k; ++kc) {
                 ptx::mbar_wait(&full_bar[stage], phase);
                 ptx::tc_fence_after();
                 const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
                 const uint32_t sb = sa + L::kABytes;
-                const uint64_t adesc = ptx::make_kmajor_sw128_desc(sa);
-                const uint64_t bdesc = ptx::make_kmajor_sw128_desc(sb);
+                const uint64_t adesc = A_MN ? ptx::make_mnmajor_sw128_desc(sa, kBK * 128) : ptx::make_kmajor_sw128_desc(sa);
+                const uint64_t bdesc = B_MN ? ptx::make_mnmajor_sw128_desc(sb, kBK * 128) : ptx::make_kmajor_sw128_desc(sb);
 #pragma unroll
                 for (int k = 0; k < kBK / kUmmaK; ++k) {
-                    // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in 16-byte units
-                    ptx::umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc,
+                    ptx::umma_bf16(tmem_base, adesc + a_step * k, bdesc + b_step * k, idesc,
                                    (kc > 0 || k > 0) ? 1u : 0u);
                 }
                 ptx::umma_commit(&empty_bar[stage]);      // frees the smem slot when MMAs retire
@@ -145,8 +229,13 @@ gemm_tn_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     cx.tmem_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     cx.m0 = m0; cx.n0 = n0; cx.z = z; cx.tile_m = blockIdx.x; cx.tile_n = blockIdx.y;
     cx.scratch = scratch;
+    cx.aux[0] = smem + L::kAuxOff;
+    cx.aux[1] = smem + L::kAuxOff + (Epi::kNumAux > 1 ? L::kAuxBytes : 0);
+    cx.out_stage = smem;                          // operand ring is idle once tmem_full has fired
+    cx.out_map = &maps.out[z];
 
     if (warp >= 2) {
+        if constexpr (Epi::kNumAux > 0) ptx::mbar_wait(aux_bar, 0);
         ptx::mbar_wait(tmem_full_bar, 0);
         ptx::tc_fence_after();
         Epi::template phase1<BN>(cx, gs, ep);
@@ -165,37 +254,60 @@ gemm_tn_bf16_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 }
 
 // =====================================================================================
-// Epilogue policies
+// Epilogue policies.  Interface: kClusterReduce, kScratchBytes, kNumAux (epilogue input tiles
+// fetched by TMA), kOutElemBytes (0: no staged output, 2: bf16 tile, 4: fp32 tile stored by TMA),
+// Params, phase1<BN>() and, for cluster epilogues, phase2<BN>().
 // =====================================================================================
 
-// ---- plain store: C = alpha * acc, fp32, row-major (dW, materialised logits) ----------
+// ---- plain store C = alpha * acc, fp32, staged in smem and written with TMA (dW, big logits) ----
 struct EpiStoreF32 {
     static constexpr bool kClusterReduce = false;
     static constexpr int kScratchBytes = 16;
+    static constexpr int kNumAux = 0;
+    static constexpr int kOutElemBytes = 4;
+    struct Params { float alpha; };
+    template <int BN>
+    static __device__ __forceinline__ void phase1(const EpiCtx& cx, const GemmShape&, const Params& p) {
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            float v[32];
+            ptx::tmem_ld_32x32(cx.tmem_row + c, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                uint4 q;
+                q.x = __float_as_uint(v[4 * j] * p.alpha); q.y = __float_as_uint(v[4 * j + 1] * p.alpha);
+                q.z = __float_as_uint(v[4 * j + 2] * p.alpha); q.w = __float_as_uint(v[4 * j + 3] * p.alpha);
+                swz_st16(cx.out_stage, cx.row, (c + 4 * j) * 4, q);
+            }
+        }
+        out_tile_commit<BN, 4>(cx);
+    }
+    template <int BN>
+    static __device__ __forceinline__ void phase2(const EpiCtx&, const GemmShape&, const Params&) {}
+};
+
+// ---- same, direct global stores: for outputs whose row pitch is not 16-byte aligned (the 4 x 3 /
+// 4 x 1 logits of the inference API) ----
+struct EpiStoreF32Direct {
+    static constexpr bool kClusterReduce = false;
+    static constexpr int kScratchBytes = 16;
+    static constexpr int kNumAux = 0;
+    static constexpr int kOutElemBytes = 0;
     struct Params { float* C[2]; int ldc[2]; float alpha; };
     template <int BN>
     static __device__ __forceinline__ void phase1(const EpiCtx& cx, const GemmShape& gs, const Params& p) {
         const int m = cx.m0 + cx.row;
         const int M = gs.M[cx.z], N = gs.N[cx.z];
         float* crow = p.C[cx.z] + static_cast<size_t>(m) * p.ldc[cx.z];
-        const bool vec_ok = (p.ldc[cx.z] & 3) == 0;
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
             float v[32];
             ptx::tmem_ld_32x32(cx.tmem_row + c, v);     // warp-collective: no early exit above
             if (m >= M) continue;
             const int n = cx.n0 + c;
-            if (vec_ok && n + 32 <= N) {
-                float4* dst = reinterpret_cast<float4*>(crow + n);
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    dst[j] = make_float4(v[4 * j] * p.alpha, v[4 * j + 1] * p.alpha,
-                                         v[4 * j + 2] * p.alpha, v[4 * j + 3] * p.alpha);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (n + j < N) crow[n + j] = v[j] * p.alpha;
-            }
+            for (int j = 0; j < 32; ++j)
+                if (n + j < N) crow[n + j] = v[j] * p.alpha;
         }
     }
     template <int BN>
@@ -207,14 +319,28 @@ struct EpiStoreF32 {
 struct EpiHeadNorm {
     static constexpr bool kClusterReduce = true;
     static constexpr int kScratchBytes = kBM * 4;
+    static constexpr int kNumAux = 0;
+    static constexpr int kOutElemBytes = 2;          // bf16 features by TMA store
     struct Params {
         const float* bias;          // [N] or null
         int normalize;
-        float* out_f32;  int ld_f32;        // [M, ld] normalised features (nullable)
-        __nv_bfloat16* out_bf16; int ld_bf16;   // [M, ld] (nullable)
-        __nv_bfloat16* out_bf16_t; int ld_t;    // [N, ld_t] transposed copy (nullable)
+        float* out_f32;  int ld_f32;        // [M, ld] fp32 copy of the features (nullable)
+        int store_bf16;                     // stage + TMA-store the bf16 tile (maps.out[0])
         float* inv_norm;            // [M]  1 / max(||u||, 1e-12)
     };
+    static __device__ __forceinline__ void add_bias(float* v, const float* bias, int n, int N) {
+        if (!bias) return;
+        if (n + 32 <= N) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n) + j);
+                v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (n + j < N) v[j] += __ldg(bias + n + j);
+        }
+    }
     template <int BN>
     static __device__ __forceinline__ void phase1(const EpiCtx& cx, const GemmShape& gs, const Params& p) {
         const int N = gs.N[cx.z];
@@ -224,13 +350,10 @@ struct EpiHeadNorm {
             float v[32];
             ptx::tmem_ld_32x32(cx.tmem_row + c, v);
             const int n = cx.n0 + c;
+            if (n >= N) continue;
+            add_bias(v, p.bias, n, N);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                if (n + j < N) {
-                    const float u = v[j] + (p.bias ? __ldg(p.bias + n + j) : 0.f);
-                    ssq = fmaf(u, u, ssq);
-                }
-            }
+            for (int j = 0; j < 32; ++j) if (n + j < N) ssq = fmaf(v[j], v[j], ssq);
         }
         reinterpret_cast<float*>(cx.scratch)[cx.row] = ssq;
     }
@@ -243,49 +366,32 @@ struct EpiHeadNorm {
         const uint32_t nc = ptx::cluster_nctarank();
         for (uint32_t r = 0; r < nc; ++r) tot += ptx::ld_dsmem_f32(my, r);
         const float denom = p.normalize ? fmaxf(sqrtf(tot), 1e-12f) : 1.f;
-        const float inv = 1.f / denom;
-        if (m < M && cx.tile_n == 0 && p.inv_norm) p.inv_norm[m] = inv;
+        if (m < M && cx.tile_n == 0 && p.inv_norm) p.inv_norm[m] = 1.f / denom;
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
             float v[32];
             ptx::tmem_ld_32x32(cx.tmem_row + c, v);
-            if (m >= M) continue;
             const int n = cx.n0 + c;
+            if (n < N) add_bias(v, p.bias, n, N);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-                v[j] = (n + j < N) ? (v[j] + (p.bias ? __ldg(p.bias + n + j) : 0.f)) / denom : 0.f;
-            if (p.out_f32) {
+            for (int j = 0; j < 32; ++j) v[j] = (n + j < N) ? v[j] / denom : 0.f;
+            if (p.out_f32 && m < M && n < N) {
                 float* dst = p.out_f32 + static_cast<size_t>(m) * p.ld_f32 + n;
+                if (n + 32 <= N && (p.ld_f32 & 3) == 0) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) if (n + j < N) dst[j] = v[j];
-            }
-            if (p.out_bf16) {
-                __nv_bfloat16* dst = p.out_bf16 + static_cast<size_t>(m) * p.ld_bf16 + n;
-                if (n + 32 <= N && (p.ld_bf16 & 7) == 0) {
-                    uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        __nv_bfloat162 a = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
-                        __nv_bfloat162 b = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-                        __nv_bfloat162 c2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
-                        __nv_bfloat162 d = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
-                        uint4 q;
-                        q.x = *reinterpret_cast<uint32_t*>(&a); q.y = *reinterpret_cast<uint32_t*>(&b);
-                        q.z = *reinterpret_cast<uint32_t*>(&c2); q.w = *reinterpret_cast<uint32_t*>(&d);
-                        d4[j] = q;
-                    }
+                    for (int j = 0; j < 8; ++j)
+                        reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) if (n + j < N) dst[j] = __float2bfloat16_rn(v[j]);
+                    for (int j = 0; j < 32; ++j) if (n + j < N) dst[j] = v[j];
                 }
             }
-            if (p.out_bf16_t) {
+            if (p.store_bf16) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (n + j < N)
-                        p.out_bf16_t[static_cast<size_t>(n + j) * p.ld_t + m] = __float2bfloat16_rn(v[j]);
+                for (int j = 0; j < 4; ++j) swz_st16(cx.out_stage, cx.row, (c + 8 * j) * 2, pack_bf16x8(v + 8 * j));
             }
         }
+        if (p.store_bf16) out_tile_commit<BN, 2>(cx);
     }
 };
 
@@ -295,6 +401,8 @@ struct RowStat { float m, l, a; int arg; };          // max, sum exp(x-m), sum e
 struct EpiSimStats {
     static constexpr bool kClusterReduce = false;
     static constexpr int kScratchBytes = 16;
+    static constexpr int kNumAux = 0;
+    static constexpr int kOutElemBytes = 0;
     struct Params {
         float scale;                // exp(s)
         int diag_off[2];            // positive of row r is column r + diag_off[z]
@@ -353,17 +461,18 @@ struct EpiSimStats {
 // softmax_col) only: the -2*I term is ~B times larger than any other entry, and rounding it to
 // bf16 would dominate the error of every column sum of G (they cancel to ~0), so the consumer
 // (EpiNormBwd) adds it back in fp32.  dI = Gs*T - 2*exp(s)*coef*T_pos, dT likewise.
-// Direction z=1 runs with the operands swapped and therefore emits Gs^T directly.
+// Direction z=1 (sharded runs only) has the operands swapped and emits the column block Gs^T.
 struct EpiGradG {
     static constexpr bool kClusterReduce = false;
     static constexpr int kScratchBytes = 256 * 4;
+    static constexpr int kNumAux = 0;
+    static constexpr int kOutElemBytes = 2;
     struct Params {
         float scale;                 // exp(s)
         float coef;                  // upstream / (2 * B_global)
         int diag_off[2];
         const float* lse_q[2];       // [M]  log-sum-exp of this direction's rows
         const float* lse_k[2];       // [N]  log-sum-exp of the other direction (columns here)
-        __nv_bfloat16* G[2]; int ldg[2];
         float* dscale_accum;         // d loss / d s  (atomicAdd, direction 0 only; nullable)
     };
     template <int BN>
@@ -380,41 +489,27 @@ struct EpiGradG {
         const float sc2 = p.scale * kLog2e;
         const float w = p.scale * p.coef;
         float ds = 0.f;
-        __nv_bfloat16* grow = p.G[cx.z] + static_cast<size_t>(m) * p.ldg[cx.z];
-        const bool vec_ok = (p.ldg[cx.z] & 7) == 0;
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
             float v[32];
             ptx::tmem_ld_32x32(cx.tmem_row + c, v);
             const int n = cx.n0 + c;
-            if (m >= M || n >= N) continue;
+            const bool live = (m < M) && (n < N);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const float x2 = v[j] * sc2;                       // logit * log2(e)
                 float g = exp2f(x2 - lq) + exp2f(x2 - lk[c + j]);
                 g *= w;                                            // exp(s) * coef * (P_row + P_col)
-                if (n + j < N) ds = fmaf(g, v[j], ds);             // G * logit = Gs * raw dot
-                if (n + j == dcol) ds = fmaf(-2.f * w, v[j], ds);  // the -2*I term, kept in fp32
-                v[j] = g;
-            }
-            if (vec_ok && n + 32 <= N) {
-                uint4* d4 = reinterpret_cast<uint4*>(grow + n);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    __nv_bfloat162 a = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
-                    __nv_bfloat162 b = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-                    __nv_bfloat162 c2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
-                    __nv_bfloat162 d = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
-                    uint4 q;
-                    q.x = *reinterpret_cast<uint32_t*>(&a); q.y = *reinterpret_cast<uint32_t*>(&b);
-                    q.z = *reinterpret_cast<uint32_t*>(&c2); q.w = *reinterpret_cast<uint32_t*>(&d);
-                    d4[j] = q;
+                if (live && n + j < N) {
+                    ds = fmaf(g, v[j], ds);                        // G * logit = Gs * raw dot
+                    if (n + j == dcol) ds = fmaf(-2.f * w, v[j], ds);   // the -2*I term, kept in fp32
                 }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) if (n + j < N) grow[n + j] = __float2bfloat16_rn(v[j]);
+                v[j] = live ? g : 0.f;
             }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) swz_st16(cx.out_stage, cx.row, (c + 8 * j) * 2, pack_bf16x8(v + 8 * j));
         }
+        out_tile_commit<BN, 2>(cx);
         if (cx.z == 0 && p.dscale_accum) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) ds += __shfl_xor_sync(0xffffffffu, ds, o);
@@ -425,46 +520,54 @@ struct EpiGradG {
     static __device__ __forceinline__ void phase2(const EpiCtx&, const GemmShape&, const Params&) {}
 };
 
-// ---- backward, step 2: dFeat = Gs * Other, then the F.normalize backward on the full row ---
-//   du = (dFeat - feat * <feat, dFeat>) * inv_norm       (cluster along N supplies the dot)
-// Outputs (all optional): fp32 [M, N] scaled per row by 1/len (text side: d mean-embedding),
-// bf16 transposed [N, ld_t] (image side: operand of the dW GEMM), d bias (column sums).
-struct EpiNormBwd {
+// ---- backward, step 2: dFeat = Gs * Other (+ the -2*I term), then the F.normalize backward ----
+//   acc[m,:] += diag_coef * pos[m,:]                      (pos = positives of the other modality)
+//   du = (acc - feat * <feat, acc>) * inv_norm            (cluster along N supplies the dot)
+// feat and pos tiles arrive by TMA (aux 0 / aux 1).  Output tile by TMA store: bf16 du (image side,
+// operand of the dW GEMM; + dbias column sums) or fp32 scaled by 1/len (text side: d mean-embedding).
+template <bool kOutF32>
+struct EpiNormBwdT {
     static constexpr bool kClusterReduce = true;
     static constexpr int kScratchBytes = kBM * 4;
+    static constexpr int kNumAux = 2;
+    static constexpr int kOutElemBytes = kOutF32 ? 4 : 2;
     struct Params {
-        const __nv_bfloat16* feat; int ld_feat;     // normalised features used in the forward
         const float* inv_norm;                      // [M]
         int normalize;
         const long long* row_len;                   // [M] int64 lengths (nullable): out *= 1/len
-        const __nv_bfloat16* diag_feat; int ld_diag; // positives of the other modality (nullable)
-        int diag_off; float diag_coef;              // acc[m,:] += diag_coef * diag_feat[m+diag_off,:]
-        float* out_f32; int ld_f32;
-        __nv_bfloat16* out_bf16_t; int ld_t;
+        int use_diag; float diag_coef;
         float* dbias;                               // [N] atomicAdd (nullable)
     };
     template <int BN>
+    static __device__ __forceinline__ void load_acc(const EpiCtx& cx, const Params& p, int c, float* v) {
+        ptx::tmem_ld_32x32(cx.tmem_row + c, v);
+        if (p.use_diag) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float d[8];
+                unpack_bf16x8(swz_ld16(cx.aux[1], cx.row, (c + 8 * j) * 2), d);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[8 * j + k] = fmaf(p.diag_coef, d[k], v[8 * j + k]);
+            }
+        }
+    }
+    template <int BN>
     static __device__ __forceinline__ void phase1(const EpiCtx& cx, const GemmShape& gs, const Params& p) {
-        const int M = gs.M[cx.z], N = gs.N[cx.z];
-        const int m = cx.m0 + cx.row;
+        const int N = gs.N[cx.z];
         float dot = 0.f;
         if (p.normalize) {
-            const __nv_bfloat16* frow = p.feat + static_cast<size_t>(m < M ? m : 0) * p.ld_feat;
-            const __nv_bfloat16* drow = p.diag_feat
-                ? p.diag_feat + static_cast<size_t>((m < M ? m : 0) + p.diag_off) * p.ld_diag : nullptr;
 #pragma unroll 1
             for (int c = 0; c < BN; c += 32) {
                 float v[32];
-                ptx::tmem_ld_32x32(cx.tmem_row + c, v);
+                load_acc<BN>(cx, p, c, v);
                 const int n = cx.n0 + c;
-                if (m >= M) continue;
+                if (n >= N) continue;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (n + j < N) {
-                        float a = v[j];
-                        if (drow) a = fmaf(p.diag_coef, __bfloat162float(drow[n + j]), a);
-                        dot = fmaf(__bfloat162float(frow[n + j]), a, dot);
-                    }
+                for (int j = 0; j < 4; ++j) {
+                    float f[8];
+                    unpack_bf16x8(swz_ld16(cx.aux[0], cx.row, (c + 8 * j) * 2), f);   // OOB columns are 0
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) dot = fmaf(f[k], v[8 * j + k], dot);
                 }
             }
         }
@@ -481,39 +584,37 @@ struct EpiNormBwd {
         for (uint32_t r = 0; r < nc; ++r) dot += ptx::ld_dsmem_f32(my, r);
         const float inv = (p.normalize && rv) ? __ldg(p.inv_norm + m) : 1.f;
         const float rs = (p.row_len && rv) ? 1.f / static_cast<float>(p.row_len[m]) : 1.f;
-        const __nv_bfloat16* frow = p.feat + static_cast<size_t>(rv ? m : 0) * p.ld_feat;
-        const __nv_bfloat16* drow = p.diag_feat
-            ? p.diag_feat + static_cast<size_t>((rv ? m : 0) + p.diag_off) * p.ld_diag : nullptr;
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
             float v[32];
-            ptx::tmem_ld_32x32(cx.tmem_row + c, v);
+            load_acc<BN>(cx, p, c, v);
             const int n = cx.n0 + c;
-            if (n >= N) continue;                                    // warp-uniform
+            if (p.normalize) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float du = 0.f;
-                if (rv && n + j < N) {
-                    du = v[j];
-                    if (drow) du = fmaf(p.diag_coef, __bfloat162float(drow[n + j]), du);
-                    if (p.normalize) du = (du - __bfloat162float(frow[n + j]) * dot) * inv;
+                for (int j = 0; j < 4; ++j) {
+                    float f[8];
+                    unpack_bf16x8(swz_ld16(cx.aux[0], cx.row, (c + 8 * j) * 2), f);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[8 * j + k] = (v[8 * j + k] - f[k] * dot) * inv;
                 }
-                v[j] = du;
             }
-            if (p.out_f32 && rv) {
-                float* dst = p.out_f32 + static_cast<size_t>(m) * p.ld_f32 + n;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) if (n + j < N) dst[j] = v[j] * rs;
-            }
-            if (p.out_bf16_t && rv) {
+            for (int j = 0; j < 32; ++j) v[j] = (rv && n + j < N) ? v[j] * rs : 0.f;
+            if constexpr (kOutF32) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (n + j < N)
-                        p.out_bf16_t[static_cast<size_t>(n + j) * p.ld_t + m] = __float2bfloat16_rn(v[j]);
+                for (int j = 0; j < 8; ++j) {
+                    uint4 q;
+                    q.x = __float_as_uint(v[4 * j]); q.y = __float_as_uint(v[4 * j + 1]);
+                    q.z = __float_as_uint(v[4 * j + 2]); q.w = __float_as_uint(v[4 * j + 3]);
+                    swz_st16(cx.out_stage, cx.row, (c + 4 * j) * 4, q);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) swz_st16(cx.out_stage, cx.row, (c + 8 * j) * 2, pack_bf16x8(v + 8 * j));
             }
-            if (p.dbias) {
-                // column sums over the 32 rows of this warp: butterfly transpose-reduce,
-                // 31 shuffles for 32 columns; lane j ends up owning column j.
+            if (p.dbias && n < N) {
+                // column sums over the 32 rows of this warp: butterfly transpose-reduce (31 shuffles
+                // for 32 columns); lane j ends up owning column j.
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     const bool upper = (cx.row & o) != 0;
@@ -524,14 +625,13 @@ struct EpiNormBwd {
                         v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
                     }
                 }
-                // after the butterfly lane L holds the sum of column bitrev-free index L (see note)
                 const int col = n + (cx.row & 31);
                 if (col < N) atomicAdd(p.dbias + col, v[0]);
             }
         }
+        out_tile_commit<BN, kOutElemBytes>(cx);
     }
 };
-
 
 // ---- spatial "max" similarity (multimodal.py:771-780) -----------------------------------------
 // GEMM rows = text tokens (t,l), columns = image locations (i,hw).  A 128 x 256 tile holds
@@ -544,6 +644,8 @@ struct EpiSpatialMax {
     static constexpr bool kClusterReduce = false;
     static constexpr int kMaxIPN = 16;
     static constexpr int kScratchBytes = kBM * kMaxIPN * 4;
+    static constexpr int kNumAux = 0;
+    static constexpr int kOutElemBytes = 0;
     struct Params {
         int L, HW, TPM, IPN;          // tokens per text, locations per image, texts / images per tile
         int Bt, Bi;

@@ -62,27 +62,29 @@ inline PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
-// bf16 row-major matrix [rows, cols] with leading dimension ld (elements); box = box_rows x 64
-// columns (one 128-byte swizzle atom).  Out-of-bounds box elements read as zero.
-inline int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols,
-                          uint64_t ld, uint32_t box_rows) {
+// Row-major matrix [rows, cols] of bf16 (elem = 2) or fp32 (elem = 4) with leading dimension ld
+// (elements); box = box_rows x box_cols, box_cols * elem == 128 bytes (one swizzle atom).
+// Loads: out-of-bounds box elements read as zero; stores: they are clipped.
+inline int make_tmap(CUtensorMap* map, const void* ptr, int elem, uint64_t rows, uint64_t cols,
+                     uint64_t ld, uint32_t box_cols, uint32_t box_rows) {
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) return fail(CVCL_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15))
-        return fail(CVCL_ERR_INVALID, "TMA operand must be 16-byte aligned with 16-byte row pitch "
-                                      "(ptr=%p ld=%llu)", ptr, (unsigned long long)ld);
-    if (rows == 0 || cols == 0) return fail(CVCL_ERR_INVALID, "empty TMA operand");
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * elem) & 15))
+        return fail(CVCL_ERR_INVALID, "TMA tensor must be 16-byte aligned with a 16-byte row pitch "
+                                      "(ptr=%p ld=%llu elem=%d)", ptr, (unsigned long long)ld, elem);
+    if (rows == 0 || cols == 0) return fail(CVCL_ERR_INVALID, "empty TMA tensor");
     cuuint64_t gdim[2] = {cols, rows};
-    cuuint64_t gstr[1] = {ld * 2};
-    cuuint32_t box[2] = {64, box_rows};
+    cuuint64_t gstr[1] = {ld * elem};
+    cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr,
-                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(map, elem == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                     const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return fail(CVCL_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d) rows=%llu cols=%llu "
-                                   "ld=%llu box_rows=%u", (int)r, (unsigned long long)rows,
-                    (unsigned long long)cols, (unsigned long long)ld, box_rows);
+                                   "ld=%llu box=%ux%u", (int)r, (unsigned long long)rows,
+                    (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols);
     return CVCL_OK;
 }
 

@@ -46,7 +46,6 @@ struct TextFwdParams {
     float pool_scale;          // per_token: 1/(H*W)
     float* feat_f32;           // [B, E]          (nullable)
     __nv_bfloat16* feat_bf16;  int ld_bf16;     // [B, ld]  (nullable)
-    __nv_bfloat16* feat_bf16_t; int ld_t;       // [E, ld_t] transposed (nullable)
     float* inv_norm;           // flat: [B]; per_token: [B*L]   (nullable)
     float* tok_f32;            // per_token: [B*L, E]  (nullable)
     __nv_bfloat16* tok_bf16;   // per_token: [B*L, E]  (nullable)
@@ -133,12 +132,6 @@ __global__ void __launch_bounds__(256) text_encoder_fwd_kernel(const TextFwdPara
             float4 t = make_float4(acc[c].x / denom, acc[c].y / denom, acc[c].z / denom, acc[c].w / denom);
             if (p.feat_f32) *reinterpret_cast<float4*>(p.feat_f32 + static_cast<size_t>(b) * p.E + e) = t;
             if (p.feat_bf16) store_bf16x4(p.feat_bf16 + static_cast<size_t>(b) * p.ld_bf16 + e, t);
-            if (p.feat_bf16_t) {
-                p.feat_bf16_t[static_cast<size_t>(e) * p.ld_t + b] = __float2bfloat16_rn(t.x);
-                p.feat_bf16_t[static_cast<size_t>(e + 1) * p.ld_t + b] = __float2bfloat16_rn(t.y);
-                p.feat_bf16_t[static_cast<size_t>(e + 2) * p.ld_t + b] = __float2bfloat16_rn(t.z);
-                p.feat_bf16_t[static_cast<size_t>(e + 3) * p.ld_t + b] = __float2bfloat16_rn(t.w);
-            }
         }
     }
 }

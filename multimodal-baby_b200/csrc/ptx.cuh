@@ -69,6 +69,18 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
           "r"(c0), "r"(c1) : "memory");
 }
 
+// 2-D tiled store shared -> global (bulk async group); out-of-bounds box elements are clipped.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c0,
+                                             int32_t c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_and_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 template <int kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {   // whole warp, .sync.aligned
@@ -130,12 +142,26 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(2) << 61;                             // [61,64) SWIZZLE_128B
     return d;
 }
-// 32-bit instruction descriptor: fp32 accumulate, bf16 A/B, both K-major, M x N tile.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+// Same for an MN-major operand (the M or N index is contiguous in memory, the contraction index
+// strides): canonical layout ((8,n),(8,k)) in 16-byte units with strides ((1,LBO),(8,SBO)) --
+// a 64-element (128 B) run along MN, 8 contraction rows 128 B apart form one swizzle atom;
+// SBO = 1024 B between 8-row groups along K, LBO = byte distance between 64-element MN chunks.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;    // [16,30) LBO
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;                     // [32,46) SBO
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+// 32-bit instruction descriptor: fp32 accumulate, bf16 A/B, M x N tile; a_mn / b_mn select
+// MN-major operands (bit 15 / 16).
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn = false, bool b_mn = false) {
     return (1u << 4)                      // c_format  = F32
          | (1u << 7)                      // a_format  = BF16
          | (1u << 10)                     // b_format  = BF16
-         | (0u << 15) | (0u << 16)        // a_major, b_major = K
+         | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16)
          | (static_cast<uint32_t>(N >> 3) << 17)
          | (static_cast<uint32_t>(M >> 4) << 24);
 }

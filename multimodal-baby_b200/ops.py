@@ -98,7 +98,7 @@ def text_encoder_fwd(ids: Tensor, lens: Tensor, table: Tensor, normalize: bool, 
     inv = torch.empty((B * L if per_token else B,), dtype=torch.float32, device=dev)
     tok = torch.empty((B, L, E) if per_token else (0,), dtype=torch.float32, device=dev)
     _cabi.call("cvcl_text_encoder_fwd", _p(ids), _p(lens), _p(table), B, L, E, V, int(normalize),
-               int(per_token), float(pool_scale), _p(feat), None, 0, None, 0, _p(inv),
+               int(per_token), float(pool_scale), _p(feat), None, 0, _p(inv),
                _p(tok) if per_token else None, None, None, _stream())
     return feat, inv, tok
 
@@ -254,7 +254,7 @@ def head_proj_norm_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor], normalize: 
     feat = torch.empty((M, E), dtype=torch.float32, device=x.device)
     inv = torch.empty((M,), dtype=torch.float32, device=x.device)
     _cabi.call("cvcl_head_proj_norm_fwd", _p(x16), K, _p(w16), K, _p(b), M, E, K, int(normalize),
-               _p(feat), E, None, 0, None, 0, _p(inv), _stream())
+               _p(feat), E, None, 0, _p(inv), _stream())
     return feat, inv
 
 
@@ -273,20 +273,17 @@ def head_proj_norm_bwd(g: Tensor, feat: Tensor, inv_norm: Tensor, x: Tensor, w: 
     M, E = g.shape
     K = x.shape[1]
     dev = g.device
-    ldt = _pad8(M)
-    du_t = torch.empty((E, ldt), dtype=torch.bfloat16, device=dev)
-    du16 = torch.empty((M, E), dtype=torch.bfloat16, device=dev) if need_dx else None
+    du16 = torch.empty((M, E), dtype=torch.bfloat16, device=dev)
     db = torch.zeros((E,), dtype=torch.float32, device=dev)
     _cabi.call("cvcl_rownorm_bwd", _p(g), _p(feat.contiguous()), _p(inv_norm), M, E, int(normalize),
-               None, _p(du16), E, _p(du_t), ldt, _p(db), _stream())
-    _, x_t = to_bf16_pair(x, True)
+               None, _p(du16), E, None, 0, _p(db), _stream())
+    x16, _ = to_bf16_pair(x, False)
     dW = torch.empty((E, K), dtype=torch.float32, device=dev)
-    _cabi.call("cvcl_head_weight_grad", _p(du_t), ldt, _p(x_t), ldt, E, K, M, _p(dW), K, _stream())
+    _cabi.call("cvcl_head_weight_grad", _p(du16), E, _p(x16), K, E, K, M, _p(dW), K, _stream())
     if need_dx:
-        _, w_t = to_bf16_pair(w, True)                      # [K, pad8(E)]
+        w16, _ = to_bf16_pair(w, False)                     # [E,K] read MN-major: dx = du . W
         dx = torch.empty((M, K), dtype=torch.float32, device=dev)
-        _cabi.call("cvcl_gemm_nt_f32out", _p(du16), E, _p(w_t), _pad8(E), M, K, E, 1.0, _p(dx), K,
-                   _stream())
+        _cabi.call("cvcl_gemm_f32out", _p(du16), E, 0, _p(w16), K, 1, M, K, E, 1.0, _p(dx), K, _stream())
     else:
         dx = torch.empty((0,), dtype=torch.float32, device=dev)
     return dW, db, dx
@@ -381,24 +378,20 @@ def _(img, txt, log_scale):
 def sim_logits_bwd(g: Tensor, img: Tensor, txt: Tensor, log_scale: float) -> Tuple[Tensor, Tensor]:
     """g = d/d(lpi) + d/d(lpt)^T  [Ni,Nt] fp32 -> (dimg [Ni,E], dtxt [Nt,E]) fp32."""
     _need_cuda(g, img, txt)
-    g16, g16t = to_bf16_pair(g, True)               # [Ni,Nt], [Nt,pad8(Ni)]
-    _, i_t = to_bf16_pair(img, True)                # [E, pad8(Ni)]
-    _, t_t = to_bf16_pair(txt, True)                # [E, pad8(Nt)]
     Ni, Nt = g.shape
     E = img.shape[1]
+    ldg = _pad8(Nt)
+    g32 = _f32(g)
+    g16 = torch.empty((Ni, ldg), dtype=torch.bfloat16, device=g.device)
+    _cabi.call("cvcl_cast_transpose", _p(g32), 0, _p(g16), None, 1, Ni, Nt, Nt, ldg, 0, 0, 0, 0, _stream())
+    i16, _ = to_bf16_pair(img, False)
+    t16, _ = to_bf16_pair(txt, False)
     scale = math.exp(log_scale)
     dimg = torch.empty((Ni, E), dtype=torch.float32, device=g.device)
     dtxt = torch.empty((Nt, E), dtype=torch.float32, device=g.device)
-    if Nt % 8 == 0:
-        _cabi.call("cvcl_gemm_nt_f32out", _p(g16), Nt, _p(t_t), _pad8(Nt), Ni, E, Nt, scale, _p(dimg), E,
-                   _stream())
-    else:                                           # TMA needs a 16-byte row pitch: re-pitch G
-        gp = torch.zeros((Ni, _pad8(Nt)), dtype=torch.bfloat16, device=g.device)
-        gp[:, :Nt] = g16
-        _cabi.call("cvcl_gemm_nt_f32out", _p(gp), _pad8(Nt), _p(t_t), _pad8(Nt), Ni, E, Nt, scale,
-                   _p(dimg), E, _stream())
-    _cabi.call("cvcl_gemm_nt_f32out", _p(g16t), _pad8(Ni), _p(i_t), _pad8(Ni), Nt, E, Ni, scale, _p(dtxt), E,
-               _stream())
+    # dimg = g . txt (txt read MN-major);  dtxt = g^T . img (g and img both read MN-major)
+    _cabi.call("cvcl_gemm_f32out", _p(g16), ldg, 0, _p(t16), E, 1, Ni, E, Nt, scale, _p(dimg), E, _stream())
+    _cabi.call("cvcl_gemm_f32out", _p(g16), ldg, 1, _p(i16), E, 1, Nt, E, Ni, scale, _p(dtxt), E, _stream())
     return dimg, dtxt
 
 
@@ -477,22 +470,25 @@ def sim_infonce_bwd(img_q: Tensor, txt_k: Tensor, txt_q: Tensor, img_k: Tensor, 
     M1 = txt_q.shape[0]
     N1 = img_k.shape[0]
     dev = img_q.device
+    single = img_q.data_ptr() == img_k.data_ptr() and txt_q.data_ptr() == txt_k.data_ptr()
     ld0, ld1 = _pad8(N0), _pad8(N1)
     G0 = torch.empty((M0, ld0), dtype=torch.bfloat16, device=dev)
-    G1 = torch.empty((M1, ld1), dtype=torch.bfloat16, device=dev)
+    G1 = None if single else torch.empty((M1, ld1), dtype=torch.bfloat16, device=dev)
     ds = torch.zeros((1,), dtype=torch.float32, device=dev)
     _cabi.call("cvcl_sim_infonce_bwd_g", _p(img_q), _p(txt_k), _p(txt_q), _p(img_k), E, M0, N0, M1, N1, E,
                float(log_scale), int(diag_off), float(coef), _p(lse_q0), _p(lse_k0), _p(lse_q1), _p(lse_k1),
                _p(G0), ld0, _p(G1), ld1, _p(ds), _stream())
-    _, txt_k_t = to_bf16_pair(txt_k, True)           # [E, pad8(N0)]
-    _, img_k_t = to_bf16_pair(img_k, True)           # [E, pad8(N1)]
     dimg = torch.empty((M0, E), dtype=torch.float32, device=dev)
     dtxt = torch.empty((M1, E), dtype=torch.float32, device=dev)
     dcoef = -2.0 * math.exp(log_scale) * coef            # the -2*I term of G, applied in fp32
-    _cabi.call("cvcl_feat_grad_norm_bwd", _p(G0), ld0, _p(txt_k_t), ld0, M0, E, N0, None, 0, None, 0, None,
-               _p(txt_k), E, int(diag_off), dcoef, _p(dimg), E, None, 0, None, _stream())
-    _cabi.call("cvcl_feat_grad_norm_bwd", _p(G1), ld1, _p(img_k_t), ld1, M1, E, N1, None, 0, None, 0, None,
-               _p(img_k), E, int(diag_off), dcoef, _p(dtxt), E, None, 0, None, _stream())
+    _cabi.call("cvcl_feat_grad_norm_bwd", _p(G0), ld0, 0, _p(txt_k), E, M0, E, N0, None, 0, None, 0, None,
+               _p(txt_k), E, N0, int(diag_off), dcoef, _p(dimg), E, None, 0, None, _stream())
+    if single:      # dT = Gs^T . I: the same Gs read MN-major, no second orientation needed
+        _cabi.call("cvcl_feat_grad_norm_bwd", _p(G0), ld0, 1, _p(img_k), E, M1, E, N1, None, 0, None, 0, None,
+                   _p(img_k), E, N1, int(diag_off), dcoef, _p(dtxt), E, None, 0, None, _stream())
+    else:
+        _cabi.call("cvcl_feat_grad_norm_bwd", _p(G1), ld1, 0, _p(img_k), E, M1, E, N1, None, 0, None, 0, None,
+                   _p(img_k), E, N1, int(diag_off), dcoef, _p(dtxt), E, None, 0, None, _stream())
     return dimg, dtxt, ds
 
 
