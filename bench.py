@@ -133,6 +133,7 @@ def build_model(dev, group=None):
     model.to(dev).train()
     model.materialize_logits = False          # the trainer ignores them (multimodal_lit.py:241-266)
     model.materialize_text_outputs = False
+    model.materialize_features = False
     model.process_group = group
     return m, model
 
@@ -142,10 +143,7 @@ def step_api(model, x, ids, lens, world):
     for p in model.parameters():
         p.grad = None
     out = model.calculate_contrastive_loss(x, ids, lens)
-    out[0].backward()
-    if world > 1:
-        from multimodal_baby_b200 import sharding
-        sharding.allreduce_gradients(model.parameters(), model.process_group)
+    out[0].backward()          # sharded fused path: gradients are already summed over the ranks
     return out[0]
 
 

@@ -70,7 +70,7 @@ int cvcl_text_encoder_fwd(const int64_t* ids, const int64_t* lens, const float* 
     p.feat_bf16 = static_cast<__nv_bfloat16*>(feat_bf16); p.ld_bf16 = ld_bf16;
     p.inv_norm = inv_norm; p.tok_f32 = tok_f32; p.tok_bf16 = static_cast<__nv_bfloat16*>(tok_bf16);
     p.status = status;
-    text_encoder_fwd_kernel<<<warps_grid(B), 256, 0, as_stream(stream)>>>(p);
+    text_encoder_fwd_kernel<<<warps_grid(B, 128), 128, 0, as_stream(stream)>>>(p);
     CVCL_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return CVCL_OK;
@@ -93,8 +93,8 @@ int cvcl_embedding_scatter_add(const int64_t* ids, const float* g, float* dtable
     CVCL_REQUIRE(ids && g && dtable, "embedding_scatter_add: null pointer");
     CVCL_REQUIRE(E > 0 && E % 4 == 0 && E <= 128 * kMaxVec, "embedding_scatter_add: bad E=%d", E);
     if (B == 0) return CVCL_OK;
-    const long long rows = per_token ? static_cast<long long>(B) * L : B;
-    embedding_scatter_add_kernel<<<warps_grid(rows), 256, 0, as_stream(stream)>>>(
+    if (per_token) { B = B * L; L = 1; }
+    embedding_scatter_add_kernel<<<warps_grid(static_cast<long long>(B) * L), 256, 0, as_stream(stream)>>>(
         reinterpret_cast<const long long*>(ids), g, dtable, B, L, E, V, per_token);
     CVCL_CHECK_CUDA(cudaGetLastError());
     count_launch();
@@ -121,6 +121,17 @@ int cvcl_cast_transpose(const void* src, int src_is_bf16, void* dst, void* dst_t
     CVCL_REQUIRE(src && (dst || dst_t), "cast_transpose: null pointer");
     if (batch == 0 || R == 0 || C == 0) return CVCL_OK;
     CVCL_REQUIRE(batch <= 65535 && ceil_div(R, 32) <= 65535, "cast_transpose: grid too large");
+    if (!src_is_bf16 && dst && !dst_t && batch == 1 && ld_src == C && ld_dst == C &&
+        (static_cast<long long>(R) * C) % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {                 // contiguous: vectorised cast
+        const long long n8 = static_cast<long long>(R) * C / 8;
+        const int blocks = static_cast<int>(n8 / 256 + 1 < 148 * 16 ? n8 / 256 + 1 : 148 * 16);
+        cast_f32_bf16_kernel<<<blocks, 256, 0, as_stream(stream)>>>(static_cast<const float*>(src),
+                                                                    static_cast<__nv_bfloat16*>(dst), n8);
+        CVCL_CHECK_CUDA(cudaGetLastError());
+        count_launch();
+        return CVCL_OK;
+    }
     dim3 grid(ceil_div(C, 32), ceil_div(R, 32), batch);
     if (src_is_bf16)
         cast_transpose_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(
@@ -238,7 +249,8 @@ int cvcl_sim_infonce_fwd(const void* img_q, const void* txt_k, const void* txt_q
     CVCL_REQUIRE(diag_off >= 0 && M0 + diag_off <= N0 && M1 + diag_off <= N1,
                  "sim_infonce_fwd: positives out of range (M0=%d N0=%d M1=%d N1=%d diag_off=%d)", M0, N0, M1, N1, diag_off);
     SimWs w = carve_sim_ws(workspace, M0, N0, M1, N1);
-    CVCL_CHECK_CUDA(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned int), as_stream(stream)));
+    const bool one_block = M0 + M1 <= 1024;
+    if (!one_block) CVCL_CHECK_CUDA(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned int), as_stream(stream)));
     GemmOperands op{}; op.ndir = 2;
     op.A[0] = mat(img_q, M0, E, ld); op.B[0] = mat(txt_k, N0, E, ld);
     op.A[1] = mat(txt_q, M1, E, ld); op.B[1] = mat(img_k, N1, E, ld);
@@ -259,7 +271,8 @@ int cvcl_sim_infonce_fwd(const void* img_q, const void* txt_k, const void* txt_q
     fp.M[0] = M0; fp.M[1] = M1; fp.lse[0] = lse0; fp.lse[1] = lse1;
     fp.argmax[0] = argmax0; fp.argmax[1] = argmax1; fp.inv_rows = inv_rows;
     fp.block_part = w.block_part; fp.ticket = w.ticket; fp.out = out5;
-    infonce_finalize_kernel<<<ceil_div(M0 + M1, 256), 256, 0, as_stream(stream)>>>(fp);
+    if (one_block) infonce_finalize_kernel<<<1, 1024, 0, as_stream(stream)>>>(fp);
+    else infonce_finalize_kernel<<<ceil_div(M0 + M1, 256), 256, 0, as_stream(stream)>>>(fp);
     CVCL_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return CVCL_OK;
@@ -411,9 +424,13 @@ int cvcl_flat_contrastive_step(const void* x, int x_is_bf16, const int64_t* ids,
                                    1.f / static_cast<float>(B), f.sim, f.lse0, f.lse1, nullptr, nullptr, out5, stream))) return rc;
     if (!need_grads) return CVCL_OK;
     // K5: Gs (one orientation) -> dI (K-major Gs) and dT (the same Gs read MN-major) -> dW -> scatter
-    CVCL_CHECK_CUDA(cudaMemsetAsync(dscale, 0, sizeof(float), st));
-    CVCL_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * E, st));
-    CVCL_CHECK_CUDA(cudaMemsetAsync(dtable, 0, sizeof(float) * static_cast<size_t>(V) * E, st));
+    if (dbias == dscale + 4 && dtable == dbias + E) {          // one flat buffer: a single memset node
+        CVCL_CHECK_CUDA(cudaMemsetAsync(dscale, 0, sizeof(float) * (4 + E + static_cast<size_t>(V) * E), st));
+    } else {
+        CVCL_CHECK_CUDA(cudaMemsetAsync(dscale, 0, sizeof(float), st));
+        CVCL_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * E, st));
+        CVCL_CHECK_CUDA(cudaMemsetAsync(dtable, 0, sizeof(float) * static_cast<size_t>(V) * E, st));
+    }
     const float coef = 0.5f / static_cast<float>(B);
     if ((rc = cvcl_sim_infonce_bwd_g(f.img16, f.txt16, nullptr, nullptr, E, B, B, 0, 0, E, log_scale, 0, coef,
                                      f.lse0, f.lse1, nullptr, nullptr, f.G0, f.ldB, nullptr, 0, dscale, stream))) return rc;

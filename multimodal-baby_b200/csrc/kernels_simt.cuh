@@ -52,56 +52,92 @@ struct TextFwdParams {
     int* status;               // set to 1 on an out-of-range id (nullable)
 };
 
-__global__ void __launch_bounds__(256) text_encoder_fwd_kernel(const TextFwdParams p) {
+__global__ void __launch_bounds__(128) text_encoder_fwd_kernel(const TextFwdParams p) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= p.B) return;
     const int b = warp;
-    const int nvec = p.E >> 7;                 // float4 chunks per lane (E % 128 == 0 fast path)
-    const int rem = p.E & 127;                 // tail handled by chunk nvec with a lane mask
-    const int nch = nvec + (rem ? 1 : 0);
+    const int nch = (p.E + 127) >> 7;          // float4 chunks per lane; tail chunk is lane-masked
+    constexpr int kInFlight = 4;               // token rows gathered before they are consumed
     float4 acc[kMaxVec];
 #pragma unroll
     for (int c = 0; c < kMaxVec; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     const long long* idrow = p.ids + static_cast<size_t>(b) * p.L;
-    for (int l = 0; l < p.L; ++l) {
-        const long long id = __ldg(idrow + l);
-        const size_t tok = static_cast<size_t>(b) * p.L + l;
-        if (id < 0 || id >= p.V) { if (lane == 0 && p.status) atomicExch(p.status, 1); continue; }
-        float4 r[kMaxVec];
-        if (id != 0) {
-            const float4* src = reinterpret_cast<const float4*>(p.table + static_cast<size_t>(id) * p.E);
-#pragma unroll
-            for (int c = 0; c < kMaxVec; ++c) {
-                r[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (c < nch && (c * 32 + lane) * 4 < p.E) r[c] = __ldg(src + c * 32 + lane);
-            }
-        } else {
-            if (!p.per_token) continue;
-#pragma unroll
-            for (int c = 0; c < kMaxVec; ++c) r[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+    for (int l0 = 0; l0 < p.L; l0 += 32) {
+        // one coalesced load of up to 32 ids, then broadcast by shuffle
+        long long my_id = (l0 + lane < p.L) ? __ldg(idrow + l0 + lane) : 0;
+        if (my_id < 0 || my_id >= p.V) { if (p.status) atomicExch(p.status, 1); my_id = 0; }
+        const int nl = min(32, p.L - l0);
         if (!p.per_token) {
+            // flat: only non-pad tokens matter; compact them so the gathers stay dense
+            unsigned live = __ballot_sync(0xffffffffu, my_id != 0 && lane < nl);
+            while (live) {
+                int src_lane[kInFlight]; int n = 0;
 #pragma unroll
-            for (int c = 0; c < kMaxVec; ++c) {
-                acc[c].x += r[c].x; acc[c].y += r[c].y; acc[c].z += r[c].z; acc[c].w += r[c].w;
+                for (int k = 0; k < kInFlight; ++k) {
+                    src_lane[k] = -1;
+                    if (live) { src_lane[k] = __ffs(live) - 1; live &= live - 1; ++n; }
+                }
+                float4 r[kInFlight][4];
+#pragma unroll
+                for (int k = 0; k < kInFlight; ++k) {
+                    const long long id = __shfl_sync(0xffffffffu, my_id, src_lane[k] < 0 ? 0 : src_lane[k]);
+                    const float4* src = reinterpret_cast<const float4*>(p.table + static_cast<size_t>(id) * p.E);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        r[k][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (src_lane[k] >= 0 && c < nch && (c * 32 + lane) * 4 < p.E) r[k][c] = __ldg(src + c * 32 + lane);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < kInFlight; ++k)        // position order, as sum(dim=1) does
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        acc[c].x += r[k][c].x; acc[c].y += r[k][c].y; acc[c].z += r[k][c].z; acc[c].w += r[k][c].w;
+                    }
+                if (nch > 4) {                               // E > 512: remaining chunks, same tokens
+#pragma unroll
+                    for (int k = 0; k < kInFlight; ++k) {
+                        if (src_lane[k] < 0) continue;
+                        const long long id = __shfl_sync(0xffffffffu, my_id, src_lane[k]);
+                        const float4* src = reinterpret_cast<const float4*>(p.table + static_cast<size_t>(id) * p.E);
+#pragma unroll
+                        for (int c = 4; c < kMaxVec; ++c)
+                            if (c < nch && (c * 32 + lane) * 4 < p.E) {
+                                const float4 v = __ldg(src + c * 32 + lane);
+                                acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
+                            }
+                    }
+                }
+                (void)n;
             }
         } else {
-            float ssq = 0.f;
+            for (int k = 0; k < nl; ++k) {
+                const long long id = __shfl_sync(0xffffffffu, my_id, k);
+                const size_t tok = static_cast<size_t>(b) * p.L + l0 + k;
+                float4 r[kMaxVec];
+                const float4* src = reinterpret_cast<const float4*>(p.table + static_cast<size_t>(id) * p.E);
 #pragma unroll
-            for (int c = 0; c < kMaxVec; ++c)
-                ssq += r[c].x * r[c].x + r[c].y * r[c].y + r[c].z * r[c].z + r[c].w * r[c].w;
-            ssq = warp_sum(ssq);
-            const float denom = p.normalize ? fmaxf(sqrtf(ssq), 1e-12f) : 1.f;
-            if (lane == 0 && p.inv_norm) p.inv_norm[tok] = 1.f / denom;
+                for (int c = 0; c < kMaxVec; ++c) {
+                    r[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (id != 0 && c < nch && (c * 32 + lane) * 4 < p.E) r[c] = __ldg(src + c * 32 + lane);
+                }
+                float ssq = 0.f;
 #pragma unroll
-            for (int c = 0; c < kMaxVec; ++c) {
-                if (c < nch && (c * 32 + lane) * 4 < p.E) {
-                    float4 t = make_float4(r[c].x / denom, r[c].y / denom, r[c].z / denom, r[c].w / denom);
-                    const size_t off = tok * p.E + (c * 32 + lane) * 4;
-                    if (p.tok_f32) *reinterpret_cast<float4*>(p.tok_f32 + off) = t;
-                    if (p.tok_bf16) store_bf16x4(p.tok_bf16 + off, t);
-                    acc[c].x += t.x; acc[c].y += t.y; acc[c].z += t.z; acc[c].w += t.w;
+                for (int c = 0; c < kMaxVec; ++c)
+                    ssq += r[c].x * r[c].x + r[c].y * r[c].y + r[c].z * r[c].z + r[c].w * r[c].w;
+                ssq = warp_sum(ssq);
+                const float denom = p.normalize ? fmaxf(sqrtf(ssq), 1e-12f) : 1.f;
+                if (lane == 0 && p.inv_norm) p.inv_norm[tok] = 1.f / denom;
+#pragma unroll
+                for (int c = 0; c < kMaxVec; ++c) {
+                    if (c < nch && (c * 32 + lane) * 4 < p.E) {
+                        float4 t = make_float4(r[c].x / denom, r[c].y / denom, r[c].z / denom, r[c].w / denom);
+                        const size_t off = tok * p.E + (c * 32 + lane) * 4;
+                        if (p.tok_f32) *reinterpret_cast<float4*>(p.tok_f32 + off) = t;
+                        if (p.tok_bf16) store_bf16x4(p.tok_bf16 + off, t);
+                        acc[c].x += t.x; acc[c].y += t.y; acc[c].z += t.z; acc[c].w += t.w;
+                    }
                 }
             }
         }
@@ -159,27 +195,15 @@ __global__ void __launch_bounds__(256) embedding_gather_kernel(const long long* 
 __global__ void __launch_bounds__(256) embedding_scatter_add_kernel(const long long* ids, const float* g,
                                                                     float* dtable, int B, int L, int E,
                                                                     int V, int per_token) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // one warp per token position
     const int lane = threadIdx.x & 31;
-    const int n_rows = per_token ? B * L : B;
-    if (warp >= n_rows) return;
-    const int nch = (E + 127) >> 7;
-    float4 r[kMaxVec];
-    const float4* src = reinterpret_cast<const float4*>(g + static_cast<size_t>(warp) * E);
-#pragma unroll
-    for (int c = 0; c < kMaxVec; ++c) {
-        r[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < nch && (c * 32 + lane) * 4 < E) r[c] = __ldg(src + c * 32 + lane);
-    }
-    const int l0 = per_token ? 0 : 0, l1 = per_token ? 1 : L;
-    for (int l = l0; l < l1; ++l) {
-        const long long id = per_token ? __ldg(ids + warp) : __ldg(ids + static_cast<size_t>(warp) * L + l);
-        if (id <= 0 || id >= V) continue;
-        float4* dst = reinterpret_cast<float4*>(dtable + static_cast<size_t>(id) * E);
-#pragma unroll
-        for (int c = 0; c < kMaxVec; ++c)
-            if (c < nch && (c * 32 + lane) * 4 < E) atomicAdd(dst + c * 32 + lane, r[c]);
-    }
+    if (warp >= B * L) return;
+    const long long id = __ldg(ids + warp);
+    if (id <= 0 || id >= V) return;
+    const int row = per_token ? warp : warp / L;
+    const float4* src = reinterpret_cast<const float4*>(g + static_cast<size_t>(row) * E);
+    float4* dst = reinterpret_cast<float4*>(dtable + static_cast<size_t>(id) * E);
+    for (int c = lane; c < (E >> 2); c += 32) atomicAdd(dst + c, __ldg(src + c));
 }
 
 // spatial text backward: per token recompute tok = normalise(table[id]) and apply
@@ -255,8 +279,8 @@ struct FinalizeParams {
     float* out;                  // [8]
 };
 
-__global__ void __launch_bounds__(256) infonce_finalize_kernel(const FinalizeParams p) {
-    __shared__ float red[6][8];
+__global__ void __launch_bounds__(1024) infonce_finalize_kernel(const FinalizeParams p) {
+    __shared__ float red[6][32];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     float ce[2] = {0.f, 0.f}, ent[2] = {0.f, 0.f}, acc[2] = {0.f, 0.f};
     const int total = p.M[0] + p.M[1];
@@ -294,8 +318,12 @@ __global__ void __launch_bounds__(256) infonce_finalize_kernel(const FinalizePar
             p.block_part[blockIdx.x * 6 + i] = s;
         }
         __threadfence();
-        const unsigned int t = atomicAdd(p.ticket, 1u);
-        is_last = (t == gridDim.x - 1);
+        if (gridDim.x == 1) {
+            is_last = true;                      // single block: no ticket (and no memset) needed
+        } else {
+            const unsigned int t = atomicAdd(p.ticket, 1u);
+            is_last = (t == gridDim.x - 1);
+        }
     }
     __syncthreads();
     if (is_last && threadIdx.x == 0) {
@@ -308,7 +336,7 @@ __global__ void __launch_bounds__(256) infonce_finalize_kernel(const FinalizePar
         p.out[2] = s[5] * p.inv_rows;
         p.out[3] = s[2] * p.inv_rows;
         p.out[4] = s[3] * p.inv_rows;
-        *p.ticket = 0u;
+        if (gridDim.x > 1) *p.ticket = 0u;
     }
 }
 
@@ -365,6 +393,21 @@ __global__ void __launch_bounds__(256) eval_nway_kernel(const float* img, const 
         if (dot > best) { best = dot; arg = w; }
     }
     if (lane == 0) pred[warp] = arg;
+}
+
+// contiguous fp32 -> bf16 cast, 8 elements per thread (two 16-byte loads, one 16-byte store)
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* src, __nv_bfloat16* dst, long long n8) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+        uint4 q;
+        q.x = *reinterpret_cast<uint32_t*>(&p0); q.y = *reinterpret_cast<uint32_t*>(&p1);
+        q.z = *reinterpret_cast<uint32_t*>(&p2); q.w = *reinterpret_cast<uint32_t*>(&p3);
+        reinterpret_cast<uint4*>(dst)[i] = q;
+    }
 }
 
 // --------------------------------------------------------------------------------------

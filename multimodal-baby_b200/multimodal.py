@@ -245,6 +245,7 @@ class MultiModalModel(nn.Module):
         # those tuple slots and keep the step fully fused.
         self.materialize_logits = True
         self.materialize_text_outputs = True
+        self.materialize_features = True
         # "fused": one C call computes loss and all head gradients (flat embeddings, frozen trunk);
         # "ops": op-by-op autograd path (always used for spatial embeddings / finetune_cnn).
         self.train_path = "fused"
@@ -332,12 +333,14 @@ class MultiModalModel(nn.Module):
         table = self.text_embed.embedding.weight
         boundary, fmap = self._trunk(x)
         fused_ok = (self.embedding_type == "flat" and self.train_path == "fused"
-                    and self.process_group is None and not boundary.requires_grad)
+                    and not boundary.requires_grad)
         if fused_ok:
+            # one fused pass: loss + all head gradients (already summed over ranks when sharded)
             w, b = self._head()
             loss, iacc, tacc, ient, tent, img_f, txt_f = ops.flat_contrastive_loss(
-                boundary, y, y_len, w, b, table, s, self.normalize_features, want_features=True)
-            image_features = img_f
+                boundary, y, y_len, w, b, table, s, self.normalize_features,
+                want_features=self.materialize_features, group=self.process_group)
+            image_features = img_f if self.materialize_features else None
         else:
             image_features = self._image_features_from_trunk(boundary)
             if self.embedding_type == "flat":
@@ -360,6 +363,8 @@ class MultiModalModel(nn.Module):
                 match = ops.spatial_max_similarity(nhwc, tok, y_len, y)
                 loss, iacc, tacc, ient, tent, lpi, lpt = ops.infonce_from_match(match, s)
         logits_per_image = logits_per_text = None
+        if self.materialize_logits and img_f is not None and img_f.numel() == 0:
+            raise RuntimeError("materialize_logits=True needs materialize_features=True on the fused path")
         if self.materialize_logits:
             if self.embedding_type == "spatial" and self.sim == "max":
                 logits_per_image, logits_per_text = lpi, lpt

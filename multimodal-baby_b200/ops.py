@@ -535,11 +535,19 @@ def sim_infonce(img, txt, s, group=None):
 # ----------------------------------------------------------------------------------------
 # fused flat train step (K1..K5 sequenced inside one C call)
 # ----------------------------------------------------------------------------------------
+def split_flat_grads(flat: Tensor, E: int, K: int, V: int):
+    """views into the flat gradient buffer [ds(4) | db(E) | dtable(V*E) | dW(E*K)]."""
+    return (flat[0:1], flat[4:4 + E], flat[4 + E:4 + E + V * E].view(V, E),
+            flat[4 + E + V * E:4 + E + V * E + E * K].view(E, K))
+
+
 @torch.library.custom_op(_NS + "::flat_contrastive_step", mutates_args=())
 def flat_contrastive_step(x: Tensor, ids: Tensor, lens: Tensor, w: Tensor, bias: Tensor, table: Tensor,
                           log_scale: float, normalize: bool, need_grads: bool, want_features: bool
-                          ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
-    """-> (out5 [8], img_feat [B,E] | empty, txt_feat [B,E] | empty, dW, db, dtable, dscale)."""
+                          ) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """-> (out5 [8], img_feat [B,E] | empty, txt_feat [B,E] | empty, grads_flat | empty); the flat
+    buffer holds [ds(4) | db(E) | dtable(V*E) | dW(E*K)] (see split_flat_grads): one memset node,
+    one all-reduce when sharded."""
     _need_cuda(x, ids, lens, w, bias, table)
     if x.dtype not in (torch.float32, torch.bfloat16):
         x = x.float()
@@ -557,33 +565,28 @@ def flat_contrastive_step(x: Tensor, ids: Tensor, lens: Tensor, w: Tensor, bias:
     img_f = torch.empty((B, E), **f32) if want_features else torch.empty((0,), **f32)
     txt_f = torch.empty((B, E), **f32) if want_features else torch.empty((0,), **f32)
     if need_grads:
-        dW = torch.empty((E, K), **f32); db = torch.empty((E,), **f32)
-        dtable = torch.empty((V, E), **f32); ds = torch.empty((1,), **f32)
+        flat = torch.empty((4 + E + V * E + E * K,), **f32)
+        ds, db, dtable, dW = split_flat_grads(flat, E, K, V)
     else:
-        dW, db, dtable, ds = (torch.empty((0,), **f32) for _ in range(4))
+        flat = torch.empty((0,), **f32)
+        ds = db = dtable = dW = None
     _cabi.call("cvcl_flat_contrastive_step", _p(x), int(x.dtype == torch.bfloat16), _p(ids), _p(lens),
                _p(w), _p(bias), _p(table), B, L, E, K, V, int(normalize), float(log_scale),
                int(need_grads), _p(ws), _p(out5), _p(img_f) if want_features else None,
-               _p(txt_f) if want_features else None,
-               _p(dW) if need_grads else None, _p(db) if need_grads else None,
-               _p(dtable) if need_grads else None, _p(ds) if need_grads else None, None, _stream())
-    return out5, img_f, txt_f, dW, db, dtable, ds
+               _p(txt_f) if want_features else None, _p(dW), _p(db), _p(dtable), _p(ds), None, _stream())
+    return out5, img_f, txt_f, flat
 
 
 @flat_contrastive_step.register_fake
 def _(x, ids, lens, w, bias, table, log_scale, normalize, need_grads, want_features):
     f = dict(dtype=torch.float32)
-    B = x.shape[0]
+    B, K = x.shape
     V, E = table.shape
-    def e():
-        return x.new_empty((0,), **f)
 
     def feat():
-        return x.new_empty((B, E), **f) if want_features else e()
-    if need_grads:
-        return (x.new_empty((8,), **f), feat(), feat(), x.new_empty(w.shape, **f), x.new_empty((E,), **f),
-                x.new_empty((V, E), **f), x.new_empty((1,), **f))
-    return (x.new_empty((8,), **f), feat(), feat(), e(), e(), e(), e())
+        return x.new_empty((B, E) if want_features else (0,), **f)
+    return (x.new_empty((8,), **f), feat(), feat(),
+            x.new_empty((4 + E + V * E + E * K) if need_grads else 0, **f))
 
 
 class _FlatContrastiveStep(torch.autograd.Function):
@@ -596,12 +599,13 @@ class _FlatContrastiveStep(torch.autograd.Function):
         if torch.is_tensor(x) and x.requires_grad:
             raise RuntimeError("flat_contrastive_step does not produce d/dx; use the op-by-op path "
                                "(finetune_cnn=True) instead")
-        out5, img_f, txt_f, dW, db, dtable, ds = flat_contrastive_step(
+        out5, img_f, txt_f, flat = flat_contrastive_step(
             x, ids, lens, w, bias, table, _scalar(s), normalize, need, want_features)
         ctx.need = need
         ctx.s_is_tensor = torch.is_tensor(s)
+        ctx.dims = (table.shape[1], x.shape[1], table.shape[0])
         if need:
-            ctx.save_for_backward(dW, db, dtable, ds)
+            ctx.save_for_backward(flat)
         ctx.mark_non_differentiable(img_f, txt_f)
         return out5[0], out5[1], out5[2], out5[3], out5[4], img_f, txt_f
 
@@ -609,15 +613,119 @@ class _FlatContrastiveStep(torch.autograd.Function):
     def backward(ctx, gloss, *unused):
         if not ctx.need:
             return (None,) * 9
-        dW, db, dtable, ds = ctx.saved_tensors
-        return (None, None, None, dW * gloss, db * gloss, dtable * gloss,
-                (ds[0] * gloss) if ctx.s_is_tensor else None, None, None)
+        (flat,) = ctx.saved_tensors
+        E, K, V = ctx.dims
+        ds, db, dtable, dW = split_flat_grads(flat * gloss, E, K, V)
+        return (None, None, None, dW, db, dtable, ds[0] if ctx.s_is_tensor else None, None, None)
 
 
-def flat_contrastive_loss(x, ids, lens, w, bias, table, s, normalize=True, want_features=False):
-    """-> (loss, img_acc, txt_acc, img_ent, txt_ent, img_feat|empty, txt_feat|empty)."""
+def flat_contrastive_loss(x, ids, lens, w, bias, table, s, normalize=True, want_features=False, group=None):
+    """-> (loss, img_acc, txt_acc, img_ent, txt_ent, img_feat|empty, txt_feat|empty).
+    group: torch.distributed process group -> global-batch InfoNCE over the ranks (the returned
+    scalars are global; parameter gradients are already summed over ranks)."""
+    if group is not None:
+        return _FlatContrastiveStepSharded.apply(x, ids, lens, w, bias, table, s, bool(normalize),
+                                                 bool(want_features), group)
     return _FlatContrastiveStep.apply(x, ids, lens, w, bias, table, s, bool(normalize),
                                       bool(want_features))
+
+
+def flat_step_sharded(x, ids, lens, w, bias, table, log_scale, normalize, need_grads, want_features, group):
+    """The flat train step with the batch sharded by pairs over `group`: local encoders,
+    ONE all-gather of the bf16 [img|txt] features, row-block + column-block InfoNCE, one all-gather of
+    the LSEs, local backward, ONE all-reduce of [out5 | ds | db | dtable | dW].
+    -> (stats_flat, img_feat | None, txt_feat | None); stats_flat = [out5(8) | split_flat_grads layout]."""
+    from . import sharding
+    _need_cuda(x, ids, lens, w, bias, table)
+    world, rank = sharding.group_info(group)
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    x = x.detach().contiguous()
+    ids = _i64(ids); lens = _i64(lens)
+    w = _f32(w); bias = _f32(bias); table = _f32(table)
+    B, K = x.shape
+    L = ids.shape[1]
+    V, E = table.shape
+    Bg = B * world
+    dev = x.device
+    lib = _cabi.load()
+    C = _cabi.call
+    st = _stream()
+    bf = dict(dtype=torch.bfloat16, device=dev); f32 = dict(dtype=torch.float32, device=dev)
+    w16 = torch.empty((E, K), **bf)
+    C("cvcl_cast_transpose", _p(w), 0, _p(w16), None, 1, E, K, K, K, 0, 0, 0, 0, st)
+    x16, _ = to_bf16_pair(x, False)
+    feats = torch.empty((B, 2 * E), **bf)                 # [img | txt] per pair: one gather moves both
+    img_l, txt_l = feats[:, :E], feats[:, E:]
+    invn_i = torch.empty((B,), **f32); invn_t = torch.empty((B,), **f32)
+    img_f = torch.empty((B, E), **f32) if want_features else None
+    txt_f = torch.empty((B, E), **f32) if want_features else None
+    C("cvcl_text_encoder_fwd", _p(ids), _p(lens), _p(table), B, L, E, V, int(normalize), 0, 1.0,
+      _p(txt_f), _p(txt_l), 2 * E, _p(invn_t), None, None, None, st)
+    C("cvcl_head_proj_norm_fwd", _p(x16), K, _p(w16), K, _p(bias), B, E, K, int(normalize), _p(img_f), E,
+      _p(img_l), 2 * E, _p(invn_i), st)
+    feats_all = sharding.all_gather_rows(feats, group, world)          # [Bg, 2E]
+    img_a, txt_a = feats_all[:, :E], feats_all[:, E:]
+    n_g = 4 + E + V * E + E * K
+    stats = torch.zeros((8 + (n_g if need_grads else 0),), **f32)
+    ws = torch.empty((lib.cvcl_sim_workspace_bytes(B, Bg, B, Bg),), dtype=torch.uint8, device=dev)
+    lse = torch.empty((2, B), **f32)
+    C("cvcl_sim_infonce_fwd", _p(img_l), _p(txt_a), _p(txt_l), _p(img_a), 2 * E, B, Bg, B, Bg, E,
+      float(log_scale), rank * B, 1.0 / Bg, _p(ws), _p(lse[0]), _p(lse[1]), None, None, _p(stats), st)
+    if need_grads:
+        if world > 1:
+            lse_all = sharding.all_gather_rows(lse, group, world).view(world, 2, B).permute(1, 0, 2).contiguous()
+        else:
+            lse_all = lse
+        lse0_all, lse1_all = lse_all[0].reshape(-1), lse_all[1].reshape(-1)
+        ds, db, dtable, dW = split_flat_grads(stats[8:], E, K, V)
+        ldg = _pad8(Bg)
+        G0 = torch.empty((B, ldg), **bf); G1 = torch.empty((B, ldg), **bf)
+        coef = 0.5 / Bg
+        C("cvcl_sim_infonce_bwd_g", _p(img_l), _p(txt_a), _p(txt_l), _p(img_a), 2 * E, B, Bg, B, Bg, E,
+          float(log_scale), rank * B, coef, _p(lse[0]), _p(lse1_all), _p(lse[1]), _p(lse0_all),
+          _p(G0), ldg, _p(G1), ldg, _p(ds), st)
+        dcoef = -2.0 * math.exp(log_scale) * coef
+        du16 = torch.empty((B, E), **bf); dm = torch.empty((B, E), **f32)
+        C("cvcl_feat_grad_norm_bwd", _p(G0), ldg, 0, _p(txt_a), 2 * E, B, E, Bg, _p(img_l), 2 * E, _p(invn_i),
+          int(normalize), None, _p(txt_a), 2 * E, Bg, rank * B, dcoef, None, 0, _p(du16), E, _p(db), st)
+        C("cvcl_feat_grad_norm_bwd", _p(G1), ldg, 0, _p(img_a), 2 * E, B, E, Bg, _p(txt_l), 2 * E, _p(invn_t),
+          int(normalize), _p(lens), _p(img_a), 2 * E, Bg, rank * B, dcoef, _p(dm), E, None, 0, None, st)
+        C("cvcl_head_weight_grad", _p(du16), E, _p(x16), K, E, K, B, _p(dW), K, st)
+        C("cvcl_embedding_scatter_add", _p(ids), _p(dm), _p(dtable), B, L, E, V, 0, st)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(stats, group=group)
+    return stats, img_f, txt_f
+
+
+class _FlatContrastiveStepSharded(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ids, lens, w, bias, table, s, normalize, want_features, group):
+        need = any(t is not None and torch.is_tensor(t) and t.requires_grad for t in (w, bias, table, s))
+        if torch.is_tensor(x) and x.requires_grad:
+            raise RuntimeError("the sharded flat step does not produce d/dx; use train_path='ops'")
+        stats, img_f, txt_f = flat_step_sharded(x, ids, lens, w, bias, table, _scalar(s), normalize, need,
+                                                want_features, group)
+        ctx.need = need
+        ctx.s_is_tensor = torch.is_tensor(s)
+        ctx.dims = (table.shape[1], x.shape[1], table.shape[0])
+        if need:
+            ctx.save_for_backward(stats)
+        e = stats.new_empty((0,))
+        img_f = e if img_f is None else img_f
+        txt_f = e.clone() if txt_f is None else txt_f
+        ctx.mark_non_differentiable(img_f, txt_f)
+        return stats[0], stats[1], stats[2], stats[3], stats[4], img_f, txt_f
+
+    @staticmethod
+    def backward(ctx, gloss, *unused):
+        if not ctx.need:
+            return (None,) * 10
+        (stats,) = ctx.saved_tensors
+        E, K, V = ctx.dims
+        ds, db, dtable, dW = split_flat_grads(stats[8:] * gloss, E, K, V)
+        return (None, None, None, dW, db, dtable, ds[0] if ctx.s_is_tensor else None, None, None, None)
 
 
 # ----------------------------------------------------------------------------------------

@@ -39,7 +39,6 @@ assert torch.equal(garg, rarg[sl])
 # (2) whole model step through the public API: sharded (512*world pairs) vs single GPU
 _, model_s = build_model(dev, dist.group.WORLD)
 _, model_1 = build_model(dev, None)
-model_1.train_path = "ops"
 fs, ids, lens = zip(*[synth_batch(1234 + r, 512) for r in range(world)])
 x_all = torch.from_numpy(np.concatenate(fs)).to(dev).to(torch.bfloat16)
 ids_all = torch.from_numpy(np.concatenate(ids)).to(dev); lens_all = torch.from_numpy(np.concatenate(lens)).to(dev)
@@ -51,7 +50,21 @@ for (n, p1), (_, ps) in zip(model_1.named_parameters(), model_s.named_parameters
     if p1.grad is None:
         continue
     r = rel(ps.grad, p1.grad)
-    assert r <= 2e-3, (n, r)
+    assert r <= 5e-3, (n, r)
+# (3) op-by-op sharded path (features -> sim_infonce with the group) + explicit gradient all-reduce
+_, model_o = build_model(dev, dist.group.WORLD)
+model_o.train_path = "ops"
+for p in model_o.parameters():
+    p.grad = None
+lo = model_o.calculate_contrastive_loss(x_all[rank * 512:(rank + 1) * 512], ids_all[rank * 512:(rank + 1) * 512],
+                                        lens_all[rank * 512:(rank + 1) * 512])[0]
+lo.backward()
+m.sharding.allreduce_gradients(model_o.parameters(), dist.group.WORLD)
+assert abs(l1.item() - lo.item()) <= 2e-6 * abs(l1.item()), (l1.item(), lo.item())
+for (n, p1), (_, po) in zip(model_1.named_parameters(), model_o.named_parameters()):
+    if p1.grad is None:
+        continue
+    assert rel(po.grad, p1.grad) <= 5e-3, (n, rel(po.grad, p1.grad))
 torch.cuda.synchronize(); dist.barrier()
 if rank == 0:
     print("SHARDED_OK world=%d B=%d loss=%.6f model_loss=%.6f" % (world, B, got5[0].item(), ls.item()))
