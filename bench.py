@@ -337,19 +337,27 @@ def main():
     if world == 1:
         def raw_step():
             return m.ops.flat_contrastive_step(x, ids_d, lens_d, fcw, fcb, table, S_FIXED, True, True, False)
+    else:
+        def raw_step():
+            return m.ops.flat_step_sharded(x, ids_d, lens_d, fcw, fcb, table, S_FIXED, True, True, False, group)
+    try:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(3):
                 raw_step()
         torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
+        barrier()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             g_out = raw_step()
         run_step = graph.replay
-    else:
-        run_step = lambda: step_api(model, x, ids_d, lens_d, world)
+        run_step(); barrier()
+    except Exception as exc:                 # e.g. NCCL capture unsupported: time the eager step
+        if rank == 0:
+            print("CUDA graph capture failed (%s); timing the eager step" % exc, file=sys.stderr)
+        graph = None
+        run_step = (lambda: raw_step()) if world == 1 else (lambda: step_api(model, x, ids_d, lens_d, world))
 
     sampler = ClockSampler(local_rank)
     for _ in range(a.warmup):
@@ -374,6 +382,7 @@ def main():
     if graph is not None:       # replays launch the captured kernels without passing through the C ABI
         n1 = lib.cvcl_launch_count(); raw_step(); per = lib.cvcl_launch_count() - n1
         n_launch = per * a.steps
+        torch.cuda.synchronize()
     t = torch.tensor([ms], device=dev)
     if world > 1:
         import torch.distributed as dist

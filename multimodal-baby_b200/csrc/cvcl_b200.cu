@@ -360,6 +360,26 @@ int cvcl_head_weight_grad(const void* du, int ld_du, const void* x, int ld_x, in
 
 // ------------------------------------------------------------------------------------ fused flat step
 namespace {
+// Independent kernels of the step run on a second stream (fork/join with events) so that under
+// stream capture they become parallel branches of the CUDA graph: K1 || (cast W -> K2),
+// dI || dT, dW || embedding scatter.  One side stream + 4 events per host thread, created lazily.
+struct SideStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork[3] = {nullptr, nullptr, nullptr}, join[3] = {nullptr, nullptr, nullptr};
+    bool ok = false;
+    int init() {
+        if (ok) return CVCL_OK;
+        CVCL_CHECK_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        for (int i = 0; i < 3; ++i) {
+            CVCL_CHECK_CUDA(cudaEventCreateWithFlags(&fork[i], cudaEventDisableTiming));
+            CVCL_CHECK_CUDA(cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming));
+        }
+        ok = true;
+        return CVCL_OK;
+    }
+};
+SideStream& side_stream() { static thread_local SideStream ss; return ss; }
+
 struct FlatWs {
     __nv_bfloat16 *w16, *x16, *img16, *txt16, *G0, *du16;
     float *invn_i, *invn_t, *lse0, *lse1, *dm;
@@ -406,41 +426,54 @@ int cvcl_flat_contrastive_step(const void* x, int x_is_bf16, const int64_t* ids,
     CVCL_REQUIRE(B > 0 && E % 8 == 0 && K % 8 == 0, "flat_contrastive_step: need B>0, E%%8==0, K%%8==0 (B=%d E=%d K=%d)", B, E, K);
     cudaStream_t st = as_stream(stream);
     FlatWs f = carve_flat_ws(workspace, B, L, E, K, V);
+    SideStream& ss = side_stream();
     int rc;
-    // operand staging: bf16 copy of the master weight; trunk features are used in place when bf16
+    if ((rc = ss.init())) return rc;
+    void* side = ss.s;
+    // ---- forward: text encoder (side) || cast W -> head GEMM (main)
+    CVCL_CHECK_CUDA(cudaEventRecord(ss.fork[0], st));
+    CVCL_CHECK_CUDA(cudaStreamWaitEvent(ss.s, ss.fork[0], 0));
+    if ((rc = cvcl_text_encoder_fwd(ids, lens, table, B, L, E, V, normalize, 0, 1.f, txt_feat_f32, f.txt16, E,
+                                    f.invn_t, nullptr, nullptr, status, side))) return rc;
+    if (need_grads) {   // gradient accumulators are zeroed off the critical path
+        if (dbias == dscale + 4 && dtable == dbias + E) {
+            CVCL_CHECK_CUDA(cudaMemsetAsync(dscale, 0, sizeof(float) * (4 + E + static_cast<size_t>(V) * E), ss.s));
+        } else {
+            CVCL_CHECK_CUDA(cudaMemsetAsync(dscale, 0, sizeof(float), ss.s));
+            CVCL_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * E, ss.s));
+            CVCL_CHECK_CUDA(cudaMemsetAsync(dtable, 0, sizeof(float) * static_cast<size_t>(V) * E, ss.s));
+        }
+    }
+    CVCL_CHECK_CUDA(cudaEventRecord(ss.join[0], ss.s));
     if ((rc = cvcl_cast_transpose(w, 0, f.w16, nullptr, 1, E, K, K, K, 0, 0, 0, 0, stream))) return rc;
     const void* x16 = x;
     if (!x_is_bf16 || (reinterpret_cast<uintptr_t>(x) & 15)) {
         if ((rc = cvcl_cast_transpose(x, x_is_bf16, f.x16, nullptr, 1, B, K, K, K, 0, 0, 0, 0, stream))) return rc;
         x16 = f.x16;
     }
-    // K1, K2
-    if ((rc = cvcl_text_encoder_fwd(ids, lens, table, B, L, E, V, normalize, 0, 1.f, txt_feat_f32, f.txt16, E,
-                                    f.invn_t, nullptr, nullptr, status, stream))) return rc;
     if ((rc = cvcl_head_proj_norm_fwd(x16, K, f.w16, K, bias, B, E, K, normalize, img_feat_f32, E, f.img16, E,
                                       f.invn_i, stream))) return rc;
-    // K3 + K4
+    CVCL_CHECK_CUDA(cudaStreamWaitEvent(st, ss.join[0], 0));
+    // ---- K3 + K4
     if ((rc = cvcl_sim_infonce_fwd(f.img16, f.txt16, f.txt16, f.img16, E, B, B, B, B, E, log_scale, 0,
                                    1.f / static_cast<float>(B), f.sim, f.lse0, f.lse1, nullptr, nullptr, out5, stream))) return rc;
     if (!need_grads) return CVCL_OK;
-    // K5: Gs (one orientation) -> dI (K-major Gs) and dT (the same Gs read MN-major) -> dW -> scatter
-    if (dbias == dscale + 4 && dtable == dbias + E) {          // one flat buffer: a single memset node
-        CVCL_CHECK_CUDA(cudaMemsetAsync(dscale, 0, sizeof(float) * (4 + E + static_cast<size_t>(V) * E), st));
-    } else {
-        CVCL_CHECK_CUDA(cudaMemsetAsync(dscale, 0, sizeof(float), st));
-        CVCL_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * E, st));
-        CVCL_CHECK_CUDA(cudaMemsetAsync(dtable, 0, sizeof(float) * static_cast<size_t>(V) * E, st));
-    }
+    // ---- K5: Gs (one orientation) -> dI (K-major Gs, main) || dT (the same Gs read MN-major, side)
     const float coef = 0.5f / static_cast<float>(B);
     if ((rc = cvcl_sim_infonce_bwd_g(f.img16, f.txt16, nullptr, nullptr, E, B, B, 0, 0, E, log_scale, 0, coef,
                                      f.lse0, f.lse1, nullptr, nullptr, f.G0, f.ldB, nullptr, 0, dscale, stream))) return rc;
     const float dcoef = -2.f * expf(log_scale) * coef;
+    CVCL_CHECK_CUDA(cudaEventRecord(ss.fork[1], st));
+    CVCL_CHECK_CUDA(cudaStreamWaitEvent(ss.s, ss.fork[1], 0));
+    if ((rc = cvcl_feat_grad_norm_bwd(f.G0, f.ldB, 1, f.img16, E, B, E, B, f.txt16, E, f.invn_t, normalize,
+                                      lens, f.img16, E, B, 0, dcoef, f.dm, E, nullptr, 0, nullptr, side))) return rc;
+    // ... then the embedding scatter follows dT on the side stream while dI -> dW run on the main one
+    if ((rc = cvcl_embedding_scatter_add(ids, f.dm, dtable, B, L, E, V, 0, side))) return rc;
+    CVCL_CHECK_CUDA(cudaEventRecord(ss.join[1], ss.s));
     if ((rc = cvcl_feat_grad_norm_bwd(f.G0, f.ldB, 0, f.txt16, E, B, E, B, f.img16, E, f.invn_i, normalize,
                                       nullptr, f.txt16, E, B, 0, dcoef, nullptr, 0, f.du16, E, dbias, stream))) return rc;
-    if ((rc = cvcl_feat_grad_norm_bwd(f.G0, f.ldB, 1, f.img16, E, B, E, B, f.txt16, E, f.invn_t, normalize,
-                                      lens, f.img16, E, B, 0, dcoef, f.dm, E, nullptr, 0, nullptr, stream))) return rc;
     if ((rc = cvcl_head_weight_grad(f.du16, E, x16, K, E, K, B, dW, K, stream))) return rc;
-    if ((rc = cvcl_embedding_scatter_add(ids, f.dm, dtable, B, L, E, V, 0, stream))) return rc;
+    CVCL_CHECK_CUDA(cudaStreamWaitEvent(st, ss.join[1], 0));
     return CVCL_OK;
 }
 
