@@ -196,6 +196,8 @@ def split_trunk_forward(image_embed, x, run_head=True):
     model = image_embed.model
     if getattr(image_embed, "vit_dino", False):
         raise NotImplementedError("vit_dino trunk is outside the cvcl_b200 hot path")
+    if isinstance(model, PooledTrunk):             # trunk-boundary features fed directly
+        return (model.fc(x) if run_head else x), x
     if image_embed.embedding_type == "spatial":
         fmap = x
         for layer in list(model.children())[:-1]:

@@ -342,3 +342,37 @@ def test_errors_are_loud(cv):
         cv.ops.text_features_flat(ids.int().to(DEV), lens.to(DEV), table.to(DEV))
     with pytest.raises(cv.CvclError):           # E not a multiple of 4
         cv.ops.text_features_flat(ids.to(DEV), lens.to(DEV), torch.randn(100, 30, device=DEV))
+
+
+def test_graphed_step_equals_eager(cv):
+    """GraphedContrastiveStep (H2D + fused step + D2H captured in one CUDA graph) == the eager module
+    call, and replays pick up new staged batches."""
+    import argparse
+    E = 512
+    inp = case_inputs(321, 256, E, "flat")
+    args = argparse.Namespace(embedding_type="flat", embedding_dim=E, normalize_features=True,
+                              fix_temperature=True, temperature=0.07, text_encoder="embedding")
+    vocab = {str(i): i for i in range(2350)}
+    m = cv.MultiModalModel(cv.VisionEncoder(args, trunk="pooled"), cv.TextEncoder(vocab, 2048, args), args)
+    with torch.no_grad():
+        m.image_embed.model.fc.weight.copy_(t(inp["W"])); m.image_embed.model.fc.bias.copy_(t(inp["b"]))
+        m.text_embed.embedding.weight.copy_(t(inp["table"]))
+    m.to(DEV).train()
+    m.materialize_logits = m.materialize_text_outputs = m.materialize_features = False
+    out = m.calculate_contrastive_loss(t(inp["f"], DEV), t(inp["ids"], DEV), t(inp["lens"], DEV))
+    out[0].backward()
+    ref = [p.grad.clone() for p in (m.image_embed.model.fc.weight, m.image_embed.model.fc.bias,
+                                    m.text_embed.embedding.weight)]
+    xh = t(inp["f"]).pin_memory(); ih = t(inp["ids"]).pin_memory(); lh = t(inp["lens"]).pin_memory()
+    step = cv.GraphedContrastiveStep(m, xh, ih, lh)
+    loss = step()
+    assert abs(loss - out[0].item()) <= 1e-6 * abs(loss)
+    got = [m.image_embed.model.fc.weight.grad, m.image_embed.model.fc.bias.grad, m.text_embed.embedding.weight.grad]
+    for a, b in zip(got, ref):
+        assert rel_fro(a.cpu().numpy(), b.cpu().numpy()) <= 1e-4       # float-atomic order only
+    # a new batch staged in the pinned buffers is picked up by the next replay
+    inp2 = case_inputs(322, 256, E, "flat")
+    xh.copy_(t(inp2["f"])); ih.copy_(t(inp2["ids"])); lh.copy_(t(inp2["lens"]))
+    loss2 = step()
+    out2 = m.calculate_contrastive_loss(t(inp2["f"], DEV), t(inp2["ids"], DEV), t(inp2["lens"], DEV))
+    assert abs(loss2 - out2[0].item()) <= 1e-6 * abs(loss2) and abs(loss2 - loss) > 1e-6
