@@ -70,8 +70,7 @@ int cvcl_text_encoder_fwd(const int64_t* ids, const int64_t* lens, const float* 
     p.feat_bf16 = static_cast<__nv_bfloat16*>(feat_bf16); p.ld_bf16 = ld_bf16;
     p.inv_norm = inv_norm; p.tok_f32 = tok_f32; p.tok_bf16 = static_cast<__nv_bfloat16*>(tok_bf16);
     p.status = status;
-    text_encoder_fwd_kernel<<<warps_grid(B, 128), 128, 0, as_stream(stream)>>>(p);
-    CVCL_CHECK_CUDA(cudaGetLastError());
+    CVCL_CHECK_CUDA(launch_pdl(text_encoder_fwd_kernel, dim3(warps_grid(B, 128)), dim3(128), 0, as_stream(stream), p));
     count_launch();
     return CVCL_OK;
 }
@@ -81,9 +80,7 @@ int cvcl_embedding_gather(const int64_t* ids, const float* table, float* out, in
     CVCL_REQUIRE(ids && table && out, "embedding_gather: null pointer");
     CVCL_REQUIRE(E > 0 && E % 4 == 0, "embedding_gather: E=%d must be a multiple of 4", E);
     if (n_tok == 0) return CVCL_OK;
-    embedding_gather_kernel<<<warps_grid(n_tok), 256, 0, as_stream(stream)>>>(
-        reinterpret_cast<const long long*>(ids), table, out, n_tok, E, V);
-    CVCL_CHECK_CUDA(cudaGetLastError());
+    CVCL_CHECK_CUDA(launch_pdl(embedding_gather_kernel, dim3(warps_grid(n_tok)), dim3(256), 0, as_stream(stream), reinterpret_cast<const long long*>(ids), table, out, n_tok, E, V));
     count_launch();
     return CVCL_OK;
 }
@@ -94,9 +91,7 @@ int cvcl_embedding_scatter_add(const int64_t* ids, const float* g, float* dtable
     CVCL_REQUIRE(E > 0 && E % 4 == 0 && E <= 128 * kMaxVec, "embedding_scatter_add: bad E=%d", E);
     if (B == 0) return CVCL_OK;
     if (per_token) { B = B * L; L = 1; }
-    embedding_scatter_add_kernel<<<warps_grid(static_cast<long long>(B) * L), 256, 0, as_stream(stream)>>>(
-        reinterpret_cast<const long long*>(ids), g, dtable, B, L, E, V, per_token);
-    CVCL_CHECK_CUDA(cudaGetLastError());
+    CVCL_CHECK_CUDA(launch_pdl(embedding_scatter_add_kernel, dim3(warps_grid(static_cast<long long>(B) * L)), dim3(256), 0, as_stream(stream), reinterpret_cast<const long long*>(ids), g, dtable, B, L, E, V, per_token));
     count_launch();
     return CVCL_OK;
 }
@@ -107,10 +102,7 @@ int cvcl_text_token_bwd(const int64_t* ids, const int64_t* lens, const float* ta
     CVCL_REQUIRE(ids && lens && table && dtable && (dtok || dpool), "text_token_bwd: null pointer");
     CVCL_REQUIRE(E > 0 && E % 4 == 0 && E <= 128 * kMaxVec, "text_token_bwd: bad E=%d", E);
     if (B == 0) return CVCL_OK;
-    text_token_bwd_kernel<<<warps_grid(static_cast<long long>(B) * L), 256, 0, as_stream(stream)>>>(
-        reinterpret_cast<const long long*>(ids), reinterpret_cast<const long long*>(lens), table, dtok,
-        dpool, pool_scale, dtable, B, L, E, V, normalize);
-    CVCL_CHECK_CUDA(cudaGetLastError());
+    CVCL_CHECK_CUDA(launch_pdl(text_token_bwd_kernel, dim3(warps_grid(static_cast<long long>(B) * L)), dim3(256), 0, as_stream(stream), reinterpret_cast<const long long*>(ids), reinterpret_cast<const long long*>(lens), table, dtok, dpool, pool_scale, dtable, B, L, E, V, normalize));
     count_launch();
     return CVCL_OK;
 }
@@ -126,22 +118,15 @@ int cvcl_cast_transpose(const void* src, int src_is_bf16, void* dst, void* dst_t
         (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {                 // contiguous: vectorised cast
         const long long n8 = static_cast<long long>(R) * C / 8;
         const int blocks = static_cast<int>(n8 / 256 + 1 < 148 * 16 ? n8 / 256 + 1 : 148 * 16);
-        cast_f32_bf16_kernel<<<blocks, 256, 0, as_stream(stream)>>>(static_cast<const float*>(src),
-                                                                    static_cast<__nv_bfloat16*>(dst), n8);
-        CVCL_CHECK_CUDA(cudaGetLastError());
+        CVCL_CHECK_CUDA(launch_pdl(cast_f32_bf16_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst), n8));
         count_launch();
         return CVCL_OK;
     }
     dim3 grid(ceil_div(C, 32), ceil_div(R, 32), batch);
     if (src_is_bf16)
-        cast_transpose_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(
-            static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst),
-            static_cast<__nv_bfloat16*>(dst_t), R, C, ld_src, ld_dst, ld_t, bs_src, bs_dst, bs_t);
+        CVCL_CHECK_CUDA(launch_pdl(cast_transpose_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, as_stream(stream), static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), static_cast<__nv_bfloat16*>(dst_t), R, C, ld_src, ld_dst, ld_t, bs_src, bs_dst, bs_t));
     else
-        cast_transpose_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(
-            static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst),
-            static_cast<__nv_bfloat16*>(dst_t), R, C, ld_src, ld_dst, ld_t, bs_src, bs_dst, bs_t);
-    CVCL_CHECK_CUDA(cudaGetLastError());
+        CVCL_CHECK_CUDA(launch_pdl(cast_transpose_kernel<float>, dim3(grid), dim3(256), 0, as_stream(stream), static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst), static_cast<__nv_bfloat16*>(dst_t), R, C, ld_src, ld_dst, ld_t, bs_src, bs_dst, bs_t));
     count_launch();
     return CVCL_OK;
 }
@@ -153,10 +138,7 @@ int cvcl_embedding_bag_bwd(const int64_t* ids, const int64_t* lens, const float*
     CVCL_REQUIRE(!normalize || (feat && inv_norm), "embedding_bag_bwd: normalize needs feat and inv_norm");
     CVCL_REQUIRE(E > 0 && E % 4 == 0 && E <= 128 * kMaxVec, "embedding_bag_bwd: bad E=%d", E);
     if (B == 0) return CVCL_OK;
-    embedding_bag_bwd_kernel<<<warps_grid(B), 256, 0, as_stream(stream)>>>(
-        reinterpret_cast<const long long*>(ids), reinterpret_cast<const long long*>(lens), g, feat, inv_norm,
-        normalize, dtable, B, L, E, V);
-    CVCL_CHECK_CUDA(cudaGetLastError());
+    CVCL_CHECK_CUDA(launch_pdl(embedding_bag_bwd_kernel, dim3(warps_grid(B)), dim3(256), 0, as_stream(stream), reinterpret_cast<const long long*>(ids), reinterpret_cast<const long long*>(lens), g, feat, inv_norm, normalize, dtable, B, L, E, V));
     count_launch();
     return CVCL_OK;
 }
@@ -168,10 +150,7 @@ int cvcl_rownorm_bwd(const float* g, const float* feat, const float* inv_norm, i
     CVCL_REQUIRE(!normalize || (feat && inv_norm), "rownorm_bwd: normalize needs feat and inv_norm");
     CVCL_REQUIRE(E > 0 && E % 4 == 0 && E <= 128 * kMaxVec, "rownorm_bwd: bad E=%d", E);
     if (M == 0) return CVCL_OK;
-    rownorm_bwd_kernel<<<warps_grid(M), 256, 0, as_stream(stream)>>>(
-        g, feat, inv_norm, M, E, normalize, du_f32, static_cast<__nv_bfloat16*>(du_bf16), ld,
-        static_cast<__nv_bfloat16*>(du_bf16_t), ld_t, dbias);
-    CVCL_CHECK_CUDA(cudaGetLastError());
+    CVCL_CHECK_CUDA(launch_pdl(rownorm_bwd_kernel, dim3(warps_grid(M)), dim3(256), 0, as_stream(stream), g, feat, inv_norm, M, E, normalize, du_f32, static_cast<__nv_bfloat16*>(du_bf16), ld, static_cast<__nv_bfloat16*>(du_bf16_t), ld_t, dbias));
     count_launch();
     return CVCL_OK;
 }
@@ -182,9 +161,7 @@ int cvcl_spatial_pool(const float* src, int B, int HW, int E, float* out_f32, vo
     CVCL_REQUIRE(E > 0 && E % 4 == 0 && HW > 0, "spatial_pool: bad shape");
     if (B == 0) return CVCL_OK;
     dim3 grid(ceil_div(E / 4, 128), B);
-    spatial_pool_kernel<<<grid, 128, 0, as_stream(stream)>>>(src, B, HW, E, out_f32,
-        static_cast<__nv_bfloat16*>(out_bf16), ld, static_cast<__nv_bfloat16*>(out_bf16_t), ld_t);
-    CVCL_CHECK_CUDA(cudaGetLastError());
+    CVCL_CHECK_CUDA(launch_pdl(spatial_pool_kernel, dim3(grid), dim3(128), 0, as_stream(stream), src, B, HW, E, out_f32, static_cast<__nv_bfloat16*>(out_bf16), ld, static_cast<__nv_bfloat16*>(out_bf16_t), ld_t));
     count_launch();
     return CVCL_OK;
 }
@@ -230,7 +207,9 @@ int cvcl_head_proj_norm_fwd(const void* x, int ldx, const void* w, int ldw, cons
     EpiHeadNorm::Params ep{};
     ep.bias = bias; ep.normalize = normalize; ep.out_f32 = out_f32; ep.ld_f32 = ld_f32;
     ep.store_bf16 = out_bf16 != nullptr; ep.inv_norm = inv_norm;
-    return launch_gemm<kBN, kStages, EpiHeadNorm, false, false>(op, gs, ep, cluster, as_stream(stream));
+    // K = 2048 streams 32 k-chunks per CTA and few CTAs exist at small M: a 6-deep ring keeps
+    // 192 KB in flight per SM (latency-bound mainloop)
+    return launch_gemm<kBN, 6, EpiHeadNorm, false, false>(op, gs, ep, cluster, as_stream(stream));
 }
 
 // ------------------------------------------------------------------------------------ K3+K4
@@ -249,8 +228,6 @@ int cvcl_sim_infonce_fwd(const void* img_q, const void* txt_k, const void* txt_q
     CVCL_REQUIRE(diag_off >= 0 && M0 + diag_off <= N0 && M1 + diag_off <= N1,
                  "sim_infonce_fwd: positives out of range (M0=%d N0=%d M1=%d N1=%d diag_off=%d)", M0, N0, M1, N1, diag_off);
     SimWs w = carve_sim_ws(workspace, M0, N0, M1, N1);
-    const bool one_block = M0 + M1 <= 1024;
-    if (!one_block) CVCL_CHECK_CUDA(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned int), as_stream(stream)));
     GemmOperands op{}; op.ndir = 2;
     op.A[0] = mat(img_q, M0, E, ld); op.B[0] = mat(txt_k, N0, E, ld);
     op.A[1] = mat(txt_q, M1, E, ld); op.B[1] = mat(img_k, N1, E, ld);
@@ -261,6 +238,7 @@ int cvcl_sim_infonce_fwd(const void* img_q, const void* txt_k, const void* txt_q
     for (int z = 0; z < 2; ++z) {
         ep.diag_off[z] = diag_off; ep.part[z] = w.part[z]; ep.m_pad[z] = w.m_pad[z]; ep.diag[z] = w.diag[z];
     }
+    ep.ticket = w.ticket;
     int rc = launch_gemm<kBN, kStages, EpiSimStats, false, false>(op, gs, ep, 1, as_stream(stream));
     if (rc) return rc;
     FinalizeParams fp{};
@@ -271,9 +249,7 @@ int cvcl_sim_infonce_fwd(const void* img_q, const void* txt_k, const void* txt_q
     fp.M[0] = M0; fp.M[1] = M1; fp.lse[0] = lse0; fp.lse[1] = lse1;
     fp.argmax[0] = argmax0; fp.argmax[1] = argmax1; fp.inv_rows = inv_rows;
     fp.block_part = w.block_part; fp.ticket = w.ticket; fp.out = out5;
-    if (one_block) infonce_finalize_kernel<<<1, 1024, 0, as_stream(stream)>>>(fp);
-    else infonce_finalize_kernel<<<ceil_div(M0 + M1, 256), 256, 0, as_stream(stream)>>>(fp);
-    CVCL_CHECK_CUDA(cudaGetLastError());
+    CVCL_CHECK_CUDA(launch_pdl(infonce_finalize_kernel, dim3(ceil_div(M0 + M1, 256)), dim3(256), 0, as_stream(stream), fp));
     count_launch();
     return CVCL_OK;
 }
@@ -503,17 +479,11 @@ int cvcl_spatial_max_bwd(const float* gmatch, const int64_t* lens, const int64_t
     CVCL_REQUIRE(gmatch && lens && amax_it && amax_ti && tok && img, "spatial_max_bwd: null pointer");
     CVCL_REQUIRE(E % 8 == 0 && E <= 1024, "spatial_max_bwd: E=%d must be a multiple of 8, <= 1024", E);
     if (dtok) {
-        spatial_max_dtok_kernel<<<warps_grid(static_cast<long long>(Bt) * L), 256, 0, as_stream(stream)>>>(
-            gmatch, reinterpret_cast<const long long*>(lens), reinterpret_cast<const long long*>(ids), amax_ti,
-            static_cast<const __nv_bfloat16*>(img), dtok, Bi, Bt, L, HW, E);
-        CVCL_CHECK_CUDA(cudaGetLastError());
+        CVCL_CHECK_CUDA(launch_pdl(spatial_max_dtok_kernel, dim3(warps_grid(static_cast<long long>(Bt) * L)), dim3(256), 0, as_stream(stream), gmatch, reinterpret_cast<const long long*>(lens), reinterpret_cast<const long long*>(ids), amax_ti, static_cast<const __nv_bfloat16*>(img), dtok, Bi, Bt, L, HW, E));
         count_launch();
     }
     if (dimg) {
-        spatial_max_dimg_kernel<<<warps_grid(static_cast<long long>(Bi) * HW), 256, 0, as_stream(stream)>>>(
-            gmatch, reinterpret_cast<const long long*>(lens), amax_it, static_cast<const __nv_bfloat16*>(tok),
-            dimg, Bi, Bt, L, HW, E);
-        CVCL_CHECK_CUDA(cudaGetLastError());
+        CVCL_CHECK_CUDA(launch_pdl(spatial_max_dimg_kernel, dim3(warps_grid(static_cast<long long>(Bi) * HW)), dim3(256), 0, as_stream(stream), gmatch, reinterpret_cast<const long long*>(lens), amax_it, static_cast<const __nv_bfloat16*>(tok), dimg, Bi, Bt, L, HW, E));
         count_launch();
     }
     return CVCL_OK;
@@ -524,10 +494,7 @@ int cvcl_match_infonce_fwd(const float* match, int B, float log_scale, float inv
     CVCL_REQUIRE(match && workspace && lse0 && lse1 && out5, "match_infonce_fwd: null pointer");
     CVCL_REQUIRE(B > 0, "match_infonce_fwd: bad shape");
     SimWs w = carve_sim_ws(workspace, B, B, B, B);
-    CVCL_CHECK_CUDA(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned int), as_stream(stream)));
-    match_stats_kernel<<<warps_grid(2ll * B), 256, 0, as_stream(stream)>>>(
-        match, B, B, expf(log_scale), w.part[0], w.part[1], w.diag[0], w.diag[1]);
-    CVCL_CHECK_CUDA(cudaGetLastError());
+    CVCL_CHECK_CUDA(launch_pdl(match_stats_kernel, dim3(warps_grid(2ll * B)), dim3(256), 0, as_stream(stream), match, B, B, expf(log_scale), w.part[0], w.part[1], w.diag[0], w.diag[1], w.ticket));
     count_launch();
     FinalizeParams fp{};
     for (int z = 0; z < 2; ++z) {
@@ -536,8 +503,7 @@ int cvcl_match_infonce_fwd(const float* match, int B, float log_scale, float inv
     }
     fp.lse[0] = lse0; fp.lse[1] = lse1; fp.argmax[0] = argmax0; fp.argmax[1] = argmax1;
     fp.inv_rows = inv_rows; fp.block_part = w.block_part; fp.ticket = w.ticket; fp.out = out5;
-    infonce_finalize_kernel<<<ceil_div(2 * B, 256), 256, 0, as_stream(stream)>>>(fp);
-    CVCL_CHECK_CUDA(cudaGetLastError());
+    CVCL_CHECK_CUDA(launch_pdl(infonce_finalize_kernel, dim3(ceil_div(2 * B, 256)), dim3(256), 0, as_stream(stream), fp));
     count_launch();
     return CVCL_OK;
 }
@@ -545,9 +511,7 @@ int cvcl_match_infonce_fwd(const float* match, int B, float log_scale, float inv
 int cvcl_match_infonce_bwd(const float* match, int B, float log_scale, float coef, const float* lse0,
                            const float* lse1, float* dmatch, float* dscale, void* stream) {
     CVCL_REQUIRE(match && lse0 && lse1 && dmatch, "match_infonce_bwd: null pointer");
-    match_grad_kernel<<<ceil_div(B * B, 256), 256, 0, as_stream(stream)>>>(
-        match, B, B, expf(log_scale), coef, lse0, lse1, dmatch, dscale);
-    CVCL_CHECK_CUDA(cudaGetLastError());
+    CVCL_CHECK_CUDA(launch_pdl(match_grad_kernel, dim3(ceil_div(B * B, 256)), dim3(256), 0, as_stream(stream), match, B, B, expf(log_scale), coef, lse0, lse1, dmatch, dscale));
     count_launch();
     return CVCL_OK;
 }
@@ -559,9 +523,7 @@ int cvcl_eval_nway_fwd(const float* img, const float* txt, const int* txt_index,
     CVCL_REQUIRE(n_trials >= 0 && n_way > 0, "eval_nway_fwd: bad shape");
     CVCL_REQUIRE(E > 0 && E % 4 == 0 && E <= 128 * kMaxVec, "eval_nway_fwd: bad E=%d", E);
     if (n_trials == 0) return CVCL_OK;
-    eval_nway_kernel<<<warps_grid(n_trials), 256, 0, as_stream(stream)>>>(
-        img, txt, txt_index, n_trials, n_way, E, normalize, expf(log_scale), pred, logits);
-    CVCL_CHECK_CUDA(cudaGetLastError());
+    CVCL_CHECK_CUDA(launch_pdl(eval_nway_kernel, dim3(warps_grid(n_trials)), dim3(256), 0, as_stream(stream), img, txt, txt_index, n_trials, n_way, E, normalize, expf(log_scale), pred, logits));
     count_launch();
     return CVCL_OK;
 }

@@ -67,13 +67,15 @@ int launch_gemm(const GemmOperands& op, const GemmShape& gs, const typename Epi:
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 1;
     at[0].val.clusterDim.y = cluster_n > 1 ? cluster_n : 1;
     at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: see ptx::pdl_wait()
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     CVCL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, gs, ep));
     count_launch();
     return CVCL_OK;

@@ -138,6 +138,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmShape gs, cons
     const int n0 = blockIdx.y * gs.n_stride;
     const int num_k = (gs.K + kBK - 1) / kBK;
 
+    ptx::pdl_launch_dependents();          // the next kernel may begin its prologue on idle SMs
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(tmA);
         ptx::prefetch_tmap(tmB);
@@ -156,6 +157,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmShape gs, cons
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    ptx::pdl_wait();                       // everything above overlapped the previous kernel's tail
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
@@ -409,6 +411,7 @@ struct EpiSimStats {
         RowStat* part[2];           // [n_tiles][m_pad]
         int m_pad[2];
         float* diag[2];             // [M]  logit at the positive
+        unsigned int* ticket;       // zeroed here for the merge kernel that follows
     };
     template <int BN>
     static __device__ __forceinline__ void phase1(const EpiCtx& cx, const GemmShape& gs, const Params& p) {
@@ -416,6 +419,7 @@ struct EpiSimStats {
         const int m = cx.m0 + cx.row;
         const int dcol = m + p.diag_off[cx.z];
         constexpr float kLog2e = 1.4426950408889634f;
+        if (cx.tile_m == 0 && cx.tile_n == 0 && cx.z == 0 && cx.epi_tid == 0) *p.ticket = 0u;
         float mx = -INFINITY, l = 0.f, a = 0.f;
         int arg = cx.n0;
 #pragma unroll 1

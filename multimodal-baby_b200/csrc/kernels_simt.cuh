@@ -11,10 +11,25 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include "gemm_sm100.cuh"   // RowStat
+#include "host_util.h"
 
 namespace cvcl {
 
 constexpr int kMaxVec = 8;            // E <= 32 lanes * 4 floats * kMaxVec = 1024
+
+// launch with programmatic stream serialization: the kernel's blocks may be scheduled while the
+// previous kernel drains; every kernel here starts with griddepcontrol.wait, so this is safe.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -53,6 +68,7 @@ struct TextFwdParams {
 };
 
 __global__ void __launch_bounds__(128) text_encoder_fwd_kernel(const TextFwdParams p) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= p.B) return;
@@ -176,6 +192,7 @@ __global__ void __launch_bounds__(128) text_encoder_fwd_kernel(const TextFwdPara
 // returns (multimodal.py:496,575,584).  One warp per token row.
 __global__ void __launch_bounds__(256) embedding_gather_kernel(const long long* ids, const float* table,
                                                                float* out, int n_tok, int E, int V) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= n_tok) return;
@@ -195,6 +212,7 @@ __global__ void __launch_bounds__(256) embedding_gather_kernel(const long long* 
 __global__ void __launch_bounds__(256) embedding_scatter_add_kernel(const long long* ids, const float* g,
                                                                     float* dtable, int B, int L, int E,
                                                                     int V, int per_token) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // one warp per token position
     const int lane = threadIdx.x & 31;
     if (warp >= B * L) return;
@@ -215,6 +233,7 @@ __global__ void __launch_bounds__(256) text_token_bwd_kernel(const long long* id
                                                              const float* dpool, float pool_scale,
                                                              float* dtable, int B, int L, int E, int V,
                                                              int normalize) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= B * L) return;
@@ -279,24 +298,39 @@ struct FinalizeParams {
     float* out;                  // [8]
 };
 
-__global__ void __launch_bounds__(1024) infonce_finalize_kernel(const FinalizeParams p) {
-    __shared__ float red[6][32];
+__global__ void __launch_bounds__(256) infonce_finalize_kernel(const FinalizeParams p) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
+    __shared__ float red[6][8];
+    __shared__ bool is_last;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     float ce[2] = {0.f, 0.f}, ent[2] = {0.f, 0.f}, acc[2] = {0.f, 0.f};
     const int total = p.M[0] + p.M[1];
     if (tid < total) {
         const int z = tid < p.M[0] ? 0 : 1;
         const int m = z ? tid - p.M[0] : tid;
-        float mx = -INFINITY; int arg = 0x7fffffff;
-        for (int t = 0; t < p.n_tiles[z]; ++t) {
-            const RowStat rs = p.part[z][static_cast<size_t>(t) * p.m_pad[z] + m];
-            if (rs.m > mx) { mx = rs.m; arg = rs.arg; }        // strict >: first tile wins ties
-        }
-        float l = 0.f, a = 0.f;
-        for (int t = 0; t < p.n_tiles[z]; ++t) {
-            const RowStat rs = p.part[z][static_cast<size_t>(t) * p.m_pad[z] + m];
-            const float w = __expf(rs.m - mx);
-            l = fmaf(rs.l, w, l); a = fmaf(rs.a, w, a);
+        const RowStat* base = p.part[z] + m;
+        const size_t stride = p.m_pad[z];
+        const int nt = p.n_tiles[z];
+        float mx = -INFINITY, l = 0.f, a = 0.f; int arg = 0x7fffffff;
+        // one pass, 4 independent loads in flight; online merge (strict >: the first tile wins ties)
+        for (int t0 = 0; t0 < nt; t0 += 4) {
+            RowStat rs[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (t0 + k < nt) rs[k] = base[static_cast<size_t>(t0 + k) * stride];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (t0 + k < nt) {
+                    if (rs[k].m > mx) {
+                        const float w = __expf(mx - rs[k].m);          // mx = -inf -> 0
+                        l *= w; a *= w; mx = rs[k].m; arg = rs[k].arg;
+                        l += rs[k].l; a += rs[k].a;
+                    } else {
+                        const float w = __expf(rs[k].m - mx);
+                        l = fmaf(rs[k].l, w, l); a = fmaf(rs[k].a, w, a);
+                    }
+                }
+            }
         }
         const float lse = mx + logf(l);
         p.lse[z][m] = lse;
@@ -310,7 +344,6 @@ __global__ void __launch_bounds__(1024) infonce_finalize_kernel(const FinalizePa
 #pragma unroll
     for (int i = 0; i < 6; ++i) { v[i] = warp_sum(v[i]); if (lane == 0) red[i][w] = v[i]; }
     __syncthreads();
-    __shared__ bool is_last;
     if (threadIdx.x == 0) {
         for (int i = 0; i < 6; ++i) {
             float s = 0.f;
@@ -318,25 +351,26 @@ __global__ void __launch_bounds__(1024) infonce_finalize_kernel(const FinalizePa
             p.block_part[blockIdx.x * 6 + i] = s;
         }
         __threadfence();
-        if (gridDim.x == 1) {
-            is_last = true;                      // single block: no ticket (and no memset) needed
-        } else {
-            const unsigned int t = atomicAdd(p.ticket, 1u);
-            is_last = (t == gridDim.x - 1);
-        }
+        const unsigned int t = atomicAdd(p.ticket, 1u);
+        is_last = (t == gridDim.x - 1);
     }
     __syncthreads();
-    if (is_last && threadIdx.x == 0) {
+    if (is_last && threadIdx.x < 32) {          // deterministic: fixed lane-strided order + tree
         __threadfence();
         float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (unsigned int b = 0; b < gridDim.x; ++b)
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += 32)
+#pragma unroll
             for (int i = 0; i < 6; ++i) s[i] += p.block_part[b * 6 + i];
-        p.out[0] = (s[0] + s[1]) * 0.5f * p.inv_rows;
-        p.out[1] = s[4] * p.inv_rows;
-        p.out[2] = s[5] * p.inv_rows;
-        p.out[3] = s[2] * p.inv_rows;
-        p.out[4] = s[3] * p.inv_rows;
-        if (gridDim.x > 1) *p.ticket = 0u;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) s[i] = warp_sum(s[i]);
+        if (threadIdx.x == 0) {
+            p.out[0] = (s[0] + s[1]) * 0.5f * p.inv_rows;
+            p.out[1] = s[4] * p.inv_rows;
+            p.out[2] = s[5] * p.inv_rows;
+            p.out[3] = s[2] * p.inv_rows;
+            p.out[4] = s[3] * p.inv_rows;
+            *p.ticket = 0u;
+        }
     }
 }
 
@@ -350,6 +384,7 @@ __global__ void __launch_bounds__(256) eval_nway_kernel(const float* img, const 
                                                         const int* txt_index, int n_trials, int n_way,
                                                         int E, int normalize, float scale, int* pred,
                                                         float* logits) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= n_trials) return;
@@ -397,6 +432,7 @@ __global__ void __launch_bounds__(256) eval_nway_kernel(const float* img, const 
 
 // contiguous fp32 -> bf16 cast, 8 elements per thread (two 16-byte loads, one 16-byte store)
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* src, __nv_bfloat16* dst, long long n8) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i);
@@ -422,6 +458,7 @@ __global__ void __launch_bounds__(256) cast_transpose_kernel(const TIn* src, __n
                                                              long long ld_src, long long ld_dst,
                                                              long long ld_t, long long bs_src,
                                                              long long bs_dst, long long bs_t) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
     __shared__ float tile[32][33];
     const int bz = blockIdx.z;
     const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -453,6 +490,7 @@ __global__ void __launch_bounds__(256) embedding_bag_bwd_kernel(const long long*
                                                                 const float* g, const float* feat,
                                                                 const float* inv_norm, int normalize,
                                                                 float* dtable, int B, int L, int E, int V) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= B) return;
@@ -492,6 +530,7 @@ __global__ void __launch_bounds__(256) rownorm_bwd_kernel(const float* g, const 
                                                           const float* inv_norm, int M, int E, int normalize,
                                                           float* du_f32, __nv_bfloat16* du_bf16, int ld,
                                                           __nv_bfloat16* du_bf16_t, int ld_t, float* dbias) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= M) return;
@@ -536,6 +575,7 @@ __global__ void __launch_bounds__(256) rownorm_bwd_kernel(const float* g, const 
 __global__ void __launch_bounds__(128) spatial_pool_kernel(const float* src, int B, int HW, int E,
                                                            float* out_f32, __nv_bfloat16* out_bf16, int ld,
                                                            __nv_bfloat16* out_bf16_t, int ld_t) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
     const int b = blockIdx.y;
     const int e = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (e >= E) return;
@@ -579,6 +619,7 @@ __global__ void __launch_bounds__(256) spatial_max_dtok_kernel(const float* g, c
                                                                const unsigned char* amax_ti,
                                                                const __nv_bfloat16* img, float* dtok,
                                                                int Bi, int Bt, int L, int HW, int E) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= Bt * L) return;
@@ -621,6 +662,7 @@ __global__ void __launch_bounds__(256) spatial_max_dimg_kernel(const float* g, c
                                                                const unsigned char* amax_it,
                                                                const __nv_bfloat16* tok, float* dimg,
                                                                int Bi, int Bt, int L, int HW, int E) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= Bi * HW) return;
@@ -667,7 +709,9 @@ __global__ void __launch_bounds__(256) spatial_max_dimg_kernel(const float* g, c
 // --------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) match_stats_kernel(const float* match, int Bi, int Bt, float scale,
                                                           RowStat* part0, RowStat* part1, float* diag0,
-                                                          float* diag1) {
+                                                          float* diag1, unsigned int* ticket) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
+    if (blockIdx.x == 0 && threadIdx.x == 0) *ticket = 0u;        // finalize's ticket (runs after us)
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= Bi + Bt) return;
@@ -706,6 +750,7 @@ __global__ void __launch_bounds__(256) match_stats_kernel(const float* match, in
 __global__ void __launch_bounds__(256) match_grad_kernel(const float* match, int Bi, int Bt, float scale,
                                                          float coef, const float* lse0, const float* lse1,
                                                          float* dmatch, float* dscale) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     float ds = 0.f;
     if (idx < Bi * Bt) {

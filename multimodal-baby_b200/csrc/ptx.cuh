@@ -166,6 +166,17 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn =
          | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// launch_dependents: the next kernel in the stream may start its prologue now (on idle SMs);
+// wait: block until the previous kernel has completed and its writes are visible.  Both are no-ops
+// when the kernel was not launched with the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- clusters / DSMEM
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r;

@@ -41,6 +41,7 @@ class GraphedContrastiveStep:
         norm = bool(model.normalize_features)
         E, K, V = table.shape[1], w.shape[1], table.shape[0]
 
+        @torch.no_grad()
         def body():
             self.x.copy_(self.x_host, non_blocking=True)
             self.ids.copy_(self.ids_host, non_blocking=True)
