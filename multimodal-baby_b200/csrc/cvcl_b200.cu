@@ -23,15 +23,17 @@ struct SimWs {               // carve-up of the sim workspace
     RowStat* part[2]; int m_pad[2]; int n_tiles[2];
     float* diag[2]; float* block_part; unsigned int* ticket; size_t bytes;
 };
+inline int sim_bn(int N0, int N1) { return (N0 > N1 ? N0 : N1) >= 4096 ? 256 : 128; }   // tile width of the sim kernels
 SimWs carve_sim_ws(void* ws, int M0, int N0, int M1, int N1) {
     SimWs w{};
+    const int bn = sim_bn(N0, N1);
     const int M[2] = {M0, M1}, N[2] = {N0, N1};
     size_t off = 0;
     unsigned char* base = static_cast<unsigned char*>(ws);
     w.ticket = reinterpret_cast<unsigned int*>(base + off); off += 256;
     for (int z = 0; z < 2; ++z) {
         w.m_pad[z] = ceil_div(M[z], kBM) * kBM;
-        w.n_tiles[z] = ceil_div(N[z], kBN);
+        w.n_tiles[z] = ceil_div(N[z], bn);
         w.part[z] = reinterpret_cast<RowStat*>(base + off);
         off += align_up(sizeof(RowStat) * static_cast<size_t>(w.m_pad[z]) * w.n_tiles[z], 256);
         w.diag[z] = reinterpret_cast<float*>(base + off);
@@ -178,10 +180,12 @@ int cvcl_gemm_f32out(const void* A, int lda, int a_mn, const void* Bm, int ldb, 
     cudaStream_t st = as_stream(stream);
     if ((ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) {
         EpiStoreF32::Params ep{}; ep.alpha = alpha;
-        if (!a_mn && !b_mn) return launch_gemm<kBN, kStages, EpiStoreF32, false, false>(op, gs, ep, 1, st);
-        if (!a_mn && b_mn) return launch_gemm<kBN, kStages, EpiStoreF32, false, true>(op, gs, ep, 1, st);
-        if (a_mn && !b_mn) return launch_gemm<kBN, kStages, EpiStoreF32, true, false>(op, gs, ep, 1, st);
-        return launch_gemm<kBN, kStages, EpiStoreF32, true, true>(op, gs, ep, 1, st);
+        // 2-deep ring = 64 KB (also the fp32 staging tile): three CTAs per SM hide each other's
+        // prologue / epilogue (measured 430 -> 707 TF/s at 16384^2 x 512)
+        if (!a_mn && !b_mn) return launch_gemm<kBN, 2, EpiStoreF32, false, false>(op, gs, ep, 1, st);
+        if (!a_mn && b_mn) return launch_gemm<kBN, 2, EpiStoreF32, false, true>(op, gs, ep, 1, st);
+        if (a_mn && !b_mn) return launch_gemm<kBN, 2, EpiStoreF32, true, false>(op, gs, ep, 1, st);
+        return launch_gemm<kBN, 2, EpiStoreF32, true, true>(op, gs, ep, 1, st);
     }
     EpiStoreF32Direct::Params ep{}; ep.C[0] = ep.C[1] = C; ep.ldc[0] = ep.ldc[1] = ldc; ep.alpha = alpha;
     if (!a_mn && !b_mn) return launch_gemm<kBN, kStages, EpiStoreF32Direct, false, false>(op, gs, ep, 1, st);
@@ -239,7 +243,16 @@ int cvcl_sim_infonce_fwd(const void* img_q, const void* txt_k, const void* txt_q
         ep.diag_off[z] = diag_off; ep.part[z] = w.part[z]; ep.m_pad[z] = w.m_pad[z]; ep.diag[z] = w.diag[z];
     }
     ep.ticket = w.ticket;
-    int rc = launch_gemm<kBN, kStages, EpiSimStats, false, false>(op, gs, ep, 1, as_stream(stream));
+    // two CTAs fit per SM (96 KB ring, <= 256 TMEM columns each) so one tile's softmax epilogue
+    // overlaps another tile's MMAs; wide tiles (fewer per-CTA fixed costs, less smem traffic per
+    // flop) once the problem is large enough to fill the machine anyway
+    int rc;
+    if (sim_bn(N0, N1) == 256) {
+        gs.n_stride = 256;
+        rc = launch_gemm<256, 2, EpiSimStats, false, false>(op, gs, ep, 1, as_stream(stream));
+    } else {
+        rc = launch_gemm<kBN, 3, EpiSimStats, false, false>(op, gs, ep, 1, as_stream(stream));
+    }
     if (rc) return rc;
     FinalizeParams fp{};
     for (int z = 0; z < 2; ++z) {
@@ -285,7 +298,11 @@ int cvcl_sim_infonce_bwd_g(const void* img_q, const void* txt_k, const void* txt
         gs.M[1] = M1; gs.N[1] = N1; ep.lse_q[1] = lse_q1; ep.lse_k[1] = lse_k1;
     }
     ep.dscale_accum = dscale;
-    return launch_gemm<kBN, kStages, EpiGradG, false, false>(op, gs, ep, 1, as_stream(stream));
+    if (sim_bn(N0, Gs1 ? N1 : N0) == 256) {
+        gs.n_stride = 256;
+        return launch_gemm<256, 2, EpiGradG, false, false>(op, gs, ep, 1, as_stream(stream));
+    }
+    return launch_gemm<kBN, 2, EpiGradG, false, false>(op, gs, ep, 1, as_stream(stream));
 }
 
 int cvcl_feat_grad_norm_bwd(const void* Gs, int ldg, int gs_transposed, const void* other, int ld_other,
@@ -523,7 +540,10 @@ int cvcl_eval_nway_fwd(const float* img, const float* txt, const int* txt_index,
     CVCL_REQUIRE(n_trials >= 0 && n_way > 0, "eval_nway_fwd: bad shape");
     CVCL_REQUIRE(E > 0 && E % 4 == 0 && E <= 128 * kMaxVec, "eval_nway_fwd: bad E=%d", E);
     if (n_trials == 0) return CVCL_OK;
-    CVCL_CHECK_CUDA(launch_pdl(eval_nway_kernel, dim3(warps_grid(n_trials)), dim3(256), 0, as_stream(stream), img, txt, txt_index, n_trials, n_way, E, normalize, expf(log_scale), pred, logits));
+    if (n_way == 4 && E <= 512)
+        CVCL_CHECK_CUDA(launch_pdl(eval_nway_kernel<4>, dim3(warps_grid(n_trials)), dim3(256), 0, as_stream(stream), img, txt, txt_index, n_trials, n_way, E, normalize, expf(log_scale), pred, logits));
+    else
+        CVCL_CHECK_CUDA(launch_pdl(eval_nway_kernel<0>, dim3(warps_grid(n_trials)), dim3(256), 0, as_stream(stream), img, txt, txt_index, n_trials, n_way, E, normalize, expf(log_scale), pred, logits));
     count_launch();
     return CVCL_OK;
 }

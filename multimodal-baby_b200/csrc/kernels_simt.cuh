@@ -380,6 +380,7 @@ __global__ void __launch_bounds__(256) infonce_finalize_kernel(const FinalizePar
 // label embedding are L2-normalised, dotted, scaled; pred = argmax (first maximal index).
 // One warp per trial; E <= 1024.
 // --------------------------------------------------------------------------------------
+template <int kWays>      // kWays > 0: all candidate rows are fetched before any reduction (MLP)
 __global__ void __launch_bounds__(256) eval_nway_kernel(const float* img, const float* txt,
                                                         const int* txt_index, int n_trials, int n_way,
                                                         int E, int normalize, float scale, int* pred,
@@ -388,44 +389,89 @@ __global__ void __launch_bounds__(256) eval_nway_kernel(const float* img, const 
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= n_trials) return;
-    const int nch = (E + 127) >> 7;
     const int ti = txt_index ? __ldg(txt_index + warp) : warp;
     const float4* tsrc = reinterpret_cast<const float4*>(txt + static_cast<size_t>(ti) * E);
-    float4 t[kMaxVec];
-    float tss = 0.f;
-#pragma unroll
-    for (int c = 0; c < kMaxVec; ++c) {
-        t[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < nch && (c * 32 + lane) * 4 < E) t[c] = __ldg(tsrc + c * 32 + lane);
-        tss += t[c].x * t[c].x + t[c].y * t[c].y + t[c].z * t[c].z + t[c].w * t[c].w;
-    }
-    if (normalize) {
-        const float d = fmaxf(sqrtf(warp_sum(tss)), 1e-12f);
-#pragma unroll
-        for (int c = 0; c < kMaxVec; ++c) { t[c].x /= d; t[c].y /= d; t[c].z /= d; t[c].w /= d; }
-    }
     float best = -INFINITY; int arg = 0;
-    for (int w = 0; w < n_way; ++w) {
-        const float4* isrc = reinterpret_cast<const float4*>(img + (static_cast<size_t>(warp) * n_way + w) * E);
-        float4 x[kMaxVec];
-        float ss = 0.f;
+    if constexpr (kWays > 0) {
+        // E <= 512: 4 float4 per lane per row; kWays image rows + the text row in flight together
+        float4 t[4], x[kWays][4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            t[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if ((c * 32 + lane) * 4 < E) t[c] = __ldg(tsrc + c * 32 + lane);
+        }
+#pragma unroll
+        for (int w = 0; w < kWays; ++w) {
+            const float4* isrc = reinterpret_cast<const float4*>(img + (static_cast<size_t>(warp) * kWays + w) * E);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                x[w][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if ((c * 32 + lane) * 4 < E) x[w][c] = __ldg(isrc + c * 32 + lane);
+            }
+        }
+        float tss = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tss += t[c].x * t[c].x + t[c].y * t[c].y + t[c].z * t[c].z + t[c].w * t[c].w;
+        if (normalize) {
+            const float d = fmaxf(sqrtf(warp_sum(tss)), 1e-12f);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { t[c].x /= d; t[c].y /= d; t[c].z /= d; t[c].w /= d; }
+        }
+#pragma unroll
+        for (int w = 0; w < kWays; ++w) {
+            float ss = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                ss += x[w][c].x * x[w][c].x + x[w][c].y * x[w][c].y + x[w][c].z * x[w][c].z + x[w][c].w * x[w][c].w;
+            float d = 1.f;
+            if (normalize) d = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+            float dot = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                dot = fmaf(x[w][c].x / d, t[c].x, dot); dot = fmaf(x[w][c].y / d, t[c].y, dot);
+                dot = fmaf(x[w][c].z / d, t[c].z, dot); dot = fmaf(x[w][c].w / d, t[c].w, dot);
+            }
+            dot = warp_sum(dot) * scale;
+            if (logits && lane == 0) logits[static_cast<size_t>(warp) * kWays + w] = dot;
+            if (dot > best) { best = dot; arg = w; }
+        }
+    } else {
+        const int nch = (E + 127) >> 7;
+        float4 t[kMaxVec];
+        float tss = 0.f;
 #pragma unroll
         for (int c = 0; c < kMaxVec; ++c) {
-            x[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c < nch && (c * 32 + lane) * 4 < E) x[c] = __ldg(isrc + c * 32 + lane);
-            ss += x[c].x * x[c].x + x[c].y * x[c].y + x[c].z * x[c].z + x[c].w * x[c].w;
+            t[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < nch && (c * 32 + lane) * 4 < E) t[c] = __ldg(tsrc + c * 32 + lane);
+            tss += t[c].x * t[c].x + t[c].y * t[c].y + t[c].z * t[c].z + t[c].w * t[c].w;
         }
-        float d = 1.f;
-        if (normalize) d = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
-        float dot = 0.f;
+        if (normalize) {
+            const float d = fmaxf(sqrtf(warp_sum(tss)), 1e-12f);
 #pragma unroll
-        for (int c = 0; c < kMaxVec; ++c) {
-            dot = fmaf(x[c].x / d, t[c].x, dot); dot = fmaf(x[c].y / d, t[c].y, dot);
-            dot = fmaf(x[c].z / d, t[c].z, dot); dot = fmaf(x[c].w / d, t[c].w, dot);
+            for (int c = 0; c < kMaxVec; ++c) { t[c].x /= d; t[c].y /= d; t[c].z /= d; t[c].w /= d; }
         }
-        dot = warp_sum(dot) * scale;
-        if (logits && lane == 0) logits[static_cast<size_t>(warp) * n_way + w] = dot;
-        if (dot > best) { best = dot; arg = w; }
+        for (int w = 0; w < n_way; ++w) {
+            const float4* isrc = reinterpret_cast<const float4*>(img + (static_cast<size_t>(warp) * n_way + w) * E);
+            float4 x[kMaxVec];
+            float ss = 0.f;
+#pragma unroll
+            for (int c = 0; c < kMaxVec; ++c) {
+                x[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c < nch && (c * 32 + lane) * 4 < E) x[c] = __ldg(isrc + c * 32 + lane);
+                ss += x[c].x * x[c].x + x[c].y * x[c].y + x[c].z * x[c].z + x[c].w * x[c].w;
+            }
+            float d = 1.f;
+            if (normalize) d = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+            float dot = 0.f;
+#pragma unroll
+            for (int c = 0; c < kMaxVec; ++c) {
+                dot = fmaf(x[c].x / d, t[c].x, dot); dot = fmaf(x[c].y / d, t[c].y, dot);
+                dot = fmaf(x[c].z / d, t[c].z, dot); dot = fmaf(x[c].w / d, t[c].w, dot);
+            }
+            dot = warp_sum(dot) * scale;
+            if (logits && lane == 0) logits[static_cast<size_t>(warp) * n_way + w] = dot;
+            if (dot > best) { best = dot; arg = w; }
+        }
     }
     if (lane == 0) pred[warp] = arg;
 }

@@ -1,0 +1,105 @@
+"""Secondary workloads of BASELINE.json (configs 3, 4, 5) on one GPU: event-timed, L2 flushed
+between iterations, with the algorithmic work of SURVEY 8d and the measured peaks.
+    python tools/bench_configs.py [--out profiles/r01_configs.json] [--cpu]
+Each entry: ms per step, pairs/s (or frames/s), achieved TFLOP/s or GB/s and fraction of peak."""
+import argparse, json, math, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import multimodal_baby_b200 as m
+from bench import load_peaks, S_FIXED
+from oracle import cvcl_oracle as O
+
+ap = argparse.ArgumentParser(); ap.add_argument("--out", default=""); ap.add_argument("--cpu", action="store_true")
+ap.add_argument("--big", type=int, default=32768)
+a = ap.parse_args()
+dev = torch.device("cuda:0"); peaks = load_peaks()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+res = {}
+
+def timeit(fn, reps=10, warm=3):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.mean(ts)), float(np.min(ts))
+
+def rec(name, ms, mn, units, unit_name, flops=None, bytes_=None, note=""):
+    r = dict(ms=ms, ms_min=mn, per_s=units / (ms * 1e-3), unit=unit_name + "/s", note=note)
+    if flops: r.update(flops=flops, tflop_s=flops / (ms * 1e-3) / 1e12, tensor_frac=flops / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"])
+    if bytes_: r.update(bytes=bytes_, gb_s=bytes_ / (ms * 1e-3) / 1e9, hbm_frac=bytes_ / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"])
+    res[name] = r
+    print(name, json.dumps(r))
+
+E = 512
+# ---------------- config 3: global-batch loss, B = 32768 on one GPU (feature level, fwd and fwd+bwd)
+B = a.big
+g = torch.Generator().manual_seed(1)
+img = torch.nn.functional.normalize(torch.randn(B, E, generator=g), dim=1).to(dev).to(torch.bfloat16)
+txt = torch.nn.functional.normalize(torch.randn(B, E, generator=g), dim=1).to(dev).to(torch.bfloat16)
+def fwd():
+    return m.ops.sim_infonce_fwd(img, txt, txt, img, S_FIXED, 0, 1.0 / B)
+ms, mn = timeit(fwd, 5, 2)
+rec("config3_global%d_fwd_1gpu" % B, ms, mn, B, "pairs", flops=4 * B * B * E,
+    note="similarity + symmetric InfoNCE stats, both directions, logits never stored")
+def fwdbwd():
+    i = img.detach().requires_grad_(True); t = txt.detach().requires_grad_(True)
+    out = m.ops.sim_infonce(i, t, S_FIXED)
+    out[0].backward()
+ms, mn = timeit(fwdbwd, 5, 2)
+rec("config3_global%d_fwd_bwd_1gpu" % B, ms, mn, B, "pairs", flops=8 * B * B * E,
+    note="fwd + Gs (bf16, materialised) + dI + dT; algorithmic flops 8*B^2*E")
+del img, txt
+# ---------------- config 4: spatial 7x7, max and mean, B = 1024
+B4, L, HW = 1024, 25, 49
+rng = np.random.RandomState(4)
+ids, lens = O.synth_tokens(rng, B4); _, _, table = O.synth_weights(rng, E, 8)
+ids_d = torch.from_numpy(ids).to(dev); lens_d = torch.from_numpy(lens).to(dev); table_d = torch.from_numpy(table).to(dev)
+imgs = torch.nn.functional.normalize(torch.randn(B4, HW, E, generator=g), dim=-1).to(dev)
+def sp(sim):
+    def fn():
+        i = imgs.detach().requires_grad_(True); tab = table_d.detach().requires_grad_(True)
+        if sim == "max":
+            tok, _ = m.ops.text_features_spatial(ids_d, lens_d, tab, True)
+            match = m.ops.spatial_max_similarity(i, tok, lens_d, ids_d)
+            loss = m.ops.infonce_from_match(match, S_FIXED)[0]
+        else:
+            _, tp = m.ops.text_features_spatial(ids_d, lens_d, tab, True, 1.0 / HW)
+            loss = m.ops.sim_infonce(m.ops.spatial_pool(i), tp, S_FIXED)[0]
+        loss.backward()
+    return fn
+ms, mn = timeit(sp("max"), 5, 2)
+rec("config4_spatial_max_b1024_fwd_bwd", ms, mn, B4, "pairs", flops=2 * B4 * B4 * HW * L * E + 4 * B4 * B4 * L * E,
+    note="projected features in; tcgen05 segmented-max fwd + SIMT gather bwd + text token bwd")
+i16 = imgs.to(torch.bfloat16); tok16 = m.ops.text_features_spatial(ids_d, lens_d, table_d, True)[0].to(torch.bfloat16)
+ms, mn = timeit(lambda: m.ops.spatial_max_fwd(i16, tok16, lens_d), 5, 2)
+rec("config4_spatial_max_b1024_fwd_kernel", ms, mn, B4, "pairs", flops=2 * B4 * B4 * HW * L * E, note="forward kernel only")
+ms, mn = timeit(sp("mean"), 10, 3)
+rec("config4_spatial_mean_b1024_fwd_bwd", ms, mn, B4, "pairs", bytes_=2 * (B4 * HW * E + B4 * L * E) * 4,
+    note="pool-then-GEMM; fp32 feature maps in")
+# ---------------- config 5: 4-way eval on 100k frames, 22 categories
+N, C = 25000, 22
+frames = torch.randn(N * 4, E, generator=g).to(dev); cats = torch.randn(C, E, generator=g).to(dev)
+idx = torch.randint(0, C, (N,), generator=g).to(torch.int32).to(dev)
+ms, mn = timeit(lambda: m.ops.eval_nway(frames, cats, idx, 4, True, S_FIXED), 20, 3)
+rec("config5_eval_4way_100k_frames", ms, mn, N * 4, "frames", bytes_=N * 4 * E * 4, note="fp32 normalise + dot + argmax")
+if a.cpu:
+    torch.set_num_threads(os.cpu_count())
+    fr, ca, ix = frames.cpu(), cats.cpu(), idx.cpu().long()
+    t0 = time.perf_counter(); O.eval_nway(fr.reshape(N, 4, E), ca[ix], S_FIXED); dt = time.perf_counter() - t0
+    res["config5_cpu_oracle_batched"] = dict(ms=dt * 1e3, per_s=N * 4 / dt, unit="frames/s", cores=os.cpu_count())
+    print("config5 cpu", res["config5_cpu_oracle_batched"])
+    Bc = 4096
+    ic = torch.nn.functional.normalize(torch.randn(Bc, E), dim=1); tc = torch.nn.functional.normalize(torch.randn(Bc, E), dim=1)
+    def cpu_step():
+        i = ic.clone().requires_grad_(True); t = tc.clone().requires_grad_(True)
+        lpi, lpt = O.logits_from_match(O.similarity_flat(i, t), S_FIXED); O.infonce(lpi, lpt).loss.backward()
+    cpu_step(); t0 = time.perf_counter(); cpu_step(); dt = time.perf_counter() - t0
+    res["config3_cpu_oracle_b4096_fwd_bwd"] = dict(ms=dt * 1e3, per_s=Bc / dt, unit="pairs/s", cores=os.cpu_count())
+    print("config3 cpu b4096", res["config3_cpu_oracle_b4096_fwd_bwd"])
+if a.out:
+    with open(a.out, "w") as fh:
+        json.dump(dict(peaks=peaks, results=res), fh, indent=1)
