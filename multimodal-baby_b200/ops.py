@@ -652,22 +652,29 @@ def flat_step_sharded(x, ids, lens, w, bias, table, log_scale, normalize, need_g
     C = _cabi.call
     st = _stream()
     bf = dict(dtype=torch.bfloat16, device=dev); f32 = dict(dtype=torch.float32, device=dev)
-    w16 = torch.empty((E, K), **bf)
-    C("cvcl_cast_transpose", _p(w), 0, _p(w16), None, 1, E, K, K, K, 0, 0, 0, 0, st)
-    x16, _ = to_bf16_pair(x, False)
+    main = torch.cuda.current_stream(dev)
+    side = _side_stream(dev)
+    n_g = 4 + E + V * E + E * K
     feats = torch.empty((B, 2 * E), **bf)                 # [img | txt] per pair: one gather moves both
     img_l, txt_l = feats[:, :E], feats[:, E:]
     invn_i = torch.empty((B,), **f32); invn_t = torch.empty((B,), **f32)
     img_f = torch.empty((B, E), **f32) if want_features else None
     txt_f = torch.empty((B, E), **f32) if want_features else None
-    C("cvcl_text_encoder_fwd", _p(ids), _p(lens), _p(table), B, L, E, V, int(normalize), 0, 1.0,
-      _p(txt_f), _p(txt_l), 2 * E, _p(invn_t), None, None, None, st)
+    stats = torch.empty((8 + (n_g if need_grads else 0),), **f32)
+    # ---- forward: text encoder + accumulator zeroing (side) || cast W -> head GEMM (main)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        C("cvcl_text_encoder_fwd", _p(ids), _p(lens), _p(table), B, L, E, V, int(normalize), 0, 1.0,
+          _p(txt_f), _p(txt_l), 2 * E, _p(invn_t), None, None, None, side.cuda_stream)
+        stats.zero_()
+    w16 = torch.empty((E, K), **bf)
+    C("cvcl_cast_transpose", _p(w), 0, _p(w16), None, 1, E, K, K, K, 0, 0, 0, 0, st)
+    x16, _ = to_bf16_pair(x, False)
     C("cvcl_head_proj_norm_fwd", _p(x16), K, _p(w16), K, _p(bias), B, E, K, int(normalize), _p(img_f), E,
       _p(img_l), 2 * E, _p(invn_i), st)
+    main.wait_stream(side)
     feats_all = sharding.all_gather_rows(feats, group, world)          # [Bg, 2E]
     img_a, txt_a = feats_all[:, :E], feats_all[:, E:]
-    n_g = 4 + E + V * E + E * K
-    stats = torch.zeros((8 + (n_g if need_grads else 0),), **f32)
     ws = torch.empty((lib.cvcl_sim_workspace_bytes(B, Bg, B, Bg),), dtype=torch.uint8, device=dev)
     lse = torch.empty((2, B), **f32)
     C("cvcl_sim_infonce_fwd", _p(img_l), _p(txt_a), _p(txt_l), _p(img_a), 2 * E, B, Bg, B, Bg, E,
@@ -687,16 +694,32 @@ def flat_step_sharded(x, ids, lens, w, bias, table, log_scale, normalize, need_g
           _p(G0), ldg, _p(G1), ldg, _p(ds), st)
         dcoef = -2.0 * math.exp(log_scale) * coef
         du16 = torch.empty((B, E), **bf); dm = torch.empty((B, E), **f32)
+        # ---- backward: dT -> embedding scatter (side) || dI -> dW (main)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            ss = side.cuda_stream
+            C("cvcl_feat_grad_norm_bwd", _p(G1), ldg, 0, _p(img_a), 2 * E, B, E, Bg, _p(txt_l), 2 * E, _p(invn_t),
+              int(normalize), _p(lens), _p(img_a), 2 * E, Bg, rank * B, dcoef, _p(dm), E, None, 0, None, ss)
+            C("cvcl_embedding_scatter_add", _p(ids), _p(dm), _p(dtable), B, L, E, V, 0, ss)
         C("cvcl_feat_grad_norm_bwd", _p(G0), ldg, 0, _p(txt_a), 2 * E, B, E, Bg, _p(img_l), 2 * E, _p(invn_i),
           int(normalize), None, _p(txt_a), 2 * E, Bg, rank * B, dcoef, None, 0, _p(du16), E, _p(db), st)
-        C("cvcl_feat_grad_norm_bwd", _p(G1), ldg, 0, _p(img_a), 2 * E, B, E, Bg, _p(txt_l), 2 * E, _p(invn_t),
-          int(normalize), _p(lens), _p(img_a), 2 * E, Bg, rank * B, dcoef, _p(dm), E, None, 0, None, st)
         C("cvcl_head_weight_grad", _p(du16), E, _p(x16), K, E, K, B, _p(dW), K, st)
-        C("cvcl_embedding_scatter_add", _p(ids), _p(dm), _p(dtable), B, L, E, V, 0, st)
+        main.wait_stream(side)        # every side-stream use is ordered before anything that follows
     if world > 1:
         import torch.distributed as dist
         dist.all_reduce(stats, group=group)
     return stats, img_f, txt_f
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    s = _SIDE_STREAMS.get(key)
+    if s is None:
+        s = _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return s
 
 
 class _FlatContrastiveStepSharded(torch.autograd.Function):
