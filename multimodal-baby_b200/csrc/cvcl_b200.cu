@@ -486,15 +486,33 @@ int cvcl_spatial_max_fwd(const void* tok, const void* img, const int64_t* lens, 
     op.A[0] = mat(tok, Bt * L, E, E); op.B[0] = mat(img, Bi * HW, E, E);
     GemmShape gs{}; gs.M[0] = gs.M[1] = Bt * L; gs.N[0] = gs.N[1] = Bi * HW; gs.K = E;
     gs.m_stride = ep.TPM * L; gs.n_stride = ep.IPN * HW;
-    return launch_gemm<BN, 4, EpiSpatialMax, false, false>(op, gs, ep, 1, as_stream(stream));
+    return launch_gemm<BN, 2, EpiSpatialMax, false, false>(op, gs, ep, 1, as_stream(stream));   // 96 KB ring: 2 CTAs/SM
+}
+
+size_t cvcl_spatial_max_bwd_workspace_bytes(int Bt, int L, int Bi, int HW) {
+    return align_up(2ull * static_cast<size_t>(Bt) * L * pad8(Bi * HW), 256);
 }
 
 int cvcl_spatial_max_bwd(const float* gmatch, const int64_t* lens, const int64_t* ids,
                          const unsigned char* amax_it, const unsigned char* amax_ti, const void* tok,
                          const void* img, int Bt, int L, int Bi, int HW, int E, float* dtok, float* dimg,
-                         void* stream) {
+                         void* workspace, void* stream) {
     CVCL_REQUIRE(gmatch && lens && amax_it && amax_ti && tok && img, "spatial_max_bwd: null pointer");
     CVCL_REQUIRE(E % 8 == 0 && E <= 1024, "spatial_max_bwd: E=%d must be a multiple of 8, <= 1024", E);
+    if (workspace) {
+        // tensor-core form: P (bf16, [Bt*L, Bi*HW]) then two GEMMs; P is read K-major for dtok and
+        // MN-major (transposed in place) for dimg, the features are read MN-major as stored.
+        const int ntl = Bt * L, ncol = Bi * HW, ldp = pad8(ncol);
+        __nv_bfloat16* P = static_cast<__nv_bfloat16*>(workspace);
+        CVCL_CHECK_CUDA(launch_pdl(spatial_max_expand_kernel, dim3(ntl), dim3(256), 0, as_stream(stream), gmatch,
+                                   reinterpret_cast<const long long*>(lens), amax_ti, P, static_cast<long long>(ldp),
+                                   Bi, Bt, L, HW));
+        count_launch();
+        int rc;
+        if (dtok && (rc = cvcl_gemm_f32out(P, ldp, 0, img, E, 1, ntl, E, ncol, 1.f, dtok, E, stream))) return rc;
+        if (dimg && (rc = cvcl_gemm_f32out(P, ldp, 1, tok, E, 1, ncol, E, ntl, 1.f, dimg, E, stream))) return rc;
+        return CVCL_OK;
+    }
     if (dtok) {
         CVCL_CHECK_CUDA(launch_pdl(spatial_max_dtok_kernel, dim3(warps_grid(static_cast<long long>(Bt) * L)), dim3(256), 0, as_stream(stream), gmatch, reinterpret_cast<const long long*>(lens), reinterpret_cast<const long long*>(ids), amax_ti, static_cast<const __nv_bfloat16*>(img), dtok, Bi, Bt, L, HW, E));
         count_launch();

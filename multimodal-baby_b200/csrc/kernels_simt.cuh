@@ -812,4 +812,40 @@ __global__ void __launch_bounds__(256) match_grad_kernel(const float* match, int
     if ((threadIdx.x & 31) == 0 && dscale) atomicAdd(dscale, ds);
 }
 
+
+// --------------------------------------------------------------------------------------
+// spatial "max" backward, tensor-core form: expand the saved arg-max into the (mostly zero) bf16
+// matrix  P[(t,l), (i,hw)] = [hw = hw*(i,t,l)] * g[i,t] / len[t]  so that both gradients become
+// plain GEMMs on the tcgen05 engine:  dtok = P . img   and   dimg = P^T . tok  (P read MN-major).
+// One block per token row; threads sweep the Bi*HW columns coalesced.
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) spatial_max_expand_kernel(const float* g, const long long* lens,
+                                                                 const unsigned char* amax_ti,
+                                                                 __nv_bfloat16* P, long long ldp,
+                                                                 int Bi, int Bt, int L, int HW) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
+    const int tl = blockIdx.x;
+    const int t = tl / L;
+    const float invlen = 1.f / static_cast<float>(__ldg(lens + t));
+    const unsigned char* arow = amax_ti + static_cast<size_t>(tl) * Bi;
+    __nv_bfloat16* prow = P + static_cast<size_t>(tl) * ldp;
+    const int ncol = Bi * HW;
+    // two columns per thread (one 4-byte store); ldp is a multiple of 8 so rows stay 4-byte aligned
+    for (int c = threadIdx.x * 2; c < ncol; c += blockDim.x * 2) {
+        float v[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int cc = c + k;
+            v[k] = 0.f;
+            if (cc < ncol) {
+                const int i = cc / HW, hw = cc - i * HW;
+                if (arow[i] == hw) v[k] = __ldg(g + static_cast<size_t>(i) * Bt + t) * invlen;
+            }
+        }
+        __nv_bfloat162 o = __floats2bfloat162_rn(v[0], v[1]);
+        if (c + 1 < ncol) *reinterpret_cast<__nv_bfloat162*>(prow + c) = o;
+        else prow[c] = __float2bfloat16_rn(v[0]);
+    }
+}
+
 }  // namespace cvcl

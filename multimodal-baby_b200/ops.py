@@ -802,6 +802,9 @@ def _(img16, tok16, lens):
             img16.new_empty((Bt * L, Bi), dtype=torch.uint8))
 
 
+SPATIAL_MAX_BWD_MMA = True     # False: always use the SIMT gather backward
+
+
 @torch.library.custom_op(_NS + "::spatial_max_bwd", mutates_args=())
 def spatial_max_bwd(g: Tensor, lens: Tensor, ids: Optional[Tensor], a_it: Tensor, a_ti: Tensor,
                     img16: Tensor, tok16: Tensor, need_dimg: bool, need_dtok: bool) -> Tuple[Tensor, Tensor]:
@@ -812,9 +815,14 @@ def spatial_max_bwd(g: Tensor, lens: Tensor, ids: Optional[Tensor], a_it: Tensor
     g = _f32(g)
     dimg = torch.empty((Bi, HW, E) if need_dimg else (0,), dtype=torch.float32, device=dev)
     dtok = torch.empty((Bt, L, E) if need_dtok else (0,), dtype=torch.float32, device=dev)
+    # tensor-core form (P expansion + two GEMMs) once the problem is big enough to pay for P
+    ws = None
+    if SPATIAL_MAX_BWD_MMA and Bi * Bt >= 64 * 64:
+        nbytes = _cabi.load().cvcl_spatial_max_bwd_workspace_bytes(Bt, L, Bi, HW)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
     _cabi.call("cvcl_spatial_max_bwd", _p(g), _p(_i64(lens)), None if ids is None else _p(_i64(ids)),
                _p(a_it), _p(a_ti), _p(tok16), _p(img16), Bt, L, Bi, HW, E,
-               _p(dtok) if need_dtok else None, _p(dimg) if need_dimg else None, _stream())
+               _p(dtok) if need_dtok else None, _p(dimg) if need_dimg else None, _p(ws), _stream())
     return dimg, dtok
 
 

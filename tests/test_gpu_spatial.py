@@ -134,3 +134,32 @@ def test_spatial_max_backward_exact_given_argmax(cv):
     assert rel_fro(idv.grad.cpu().numpy(), ir.grad.numpy()) <= 1e-5
     valid = (torch.arange(L)[None, :] < t(lens)[:, None])
     assert rel_fro(tdv.grad.cpu()[valid].numpy(), tr.grad[valid].numpy()) <= 1e-5
+
+
+def test_spatial_max_backward_mma_form_equals_gather_form(cv):
+    """tensor-core backward (P expansion + two GEMMs, bf16 P) == SIMT gather backward == autograd."""
+    rng = np.random.RandomState(6)
+    Bi, Bt, L, HW, E = 70, 66, 25, 49, 512
+    img = torch.nn.functional.normalize(t(rng.standard_normal((Bi, HW, E)).astype(np.float32)), dim=-1)
+    tok = torch.nn.functional.normalize(t(rng.standard_normal((Bt, L, E)).astype(np.float32)), dim=-1)
+    img = img.to(torch.bfloat16).float(); tok = tok.to(torch.bfloat16).float()
+    ids, lens = O.synth_tokens(rng, Bt, L, 2350)
+    for b in range(Bt):
+        tok[b, lens[b]:] = 0
+    g = t(rng.standard_normal((Bi, Bt)).astype(np.float32))
+    res = {}
+    for flag in (True, False):
+        cv.ops.SPATIAL_MAX_BWD_MMA = flag
+        idv = img.to(DEV).requires_grad_(True); tdv = tok.to(DEV).requires_grad_(True)
+        got = cv.ops.spatial_max_similarity(idv, tdv, t(lens, DEV), t(ids, DEV))
+        (got * g.to(DEV)).sum().backward()
+        res[flag] = (idv.grad.cpu().numpy(), tdv.grad.cpu().numpy())
+    cv.ops.SPATIAL_MAX_BWD_MMA = True
+    valid = (torch.arange(L)[None, :] < t(lens)[:, None]).numpy()
+    assert rel_fro(res[True][0], res[False][0]) <= 4e-3          # P coefficients are bf16
+    assert rel_fro(res[True][1][valid], res[False][1][valid]) <= 4e-3
+    ir = img.double().clone().requires_grad_(True); tr = tok.double().clone().requires_grad_(True)
+    ref = O.similarity_spatial_max(ir.permute(0, 2, 1).reshape(Bi, E, 7, 7), tr, t(lens))
+    (ref * g.double()).sum().backward()
+    assert rel_fro(res[True][0], ir.grad.numpy()) <= 4e-3
+    assert rel_fro(res[True][1][valid], tr.grad.numpy()[valid]) <= 4e-3
