@@ -247,9 +247,9 @@ int cvcl_sim_infonce_fwd(const void* img_q, const void* txt_k, const void* txt_q
     // overlaps another tile's MMAs; wide tiles (fewer per-CTA fixed costs, less smem traffic per
     // flop) once the problem is large enough to fill the machine anyway
     int rc;
-    if (sim_bn(N0, N1) == 256) {
+    if (sim_bn(N0, N1) == 256) {       // large: persistent CTAs, double-buffered TMEM accumulator
         gs.n_stride = 256;
-        rc = launch_gemm<256, 2, EpiSimStats, false, false>(op, gs, ep, 1, as_stream(stream));
+        rc = launch_gemm_persistent<256, 4, EpiSimStats>(op, gs, ep, as_stream(stream));
     } else {
         rc = launch_gemm<kBN, 3, EpiSimStats, false, false>(op, gs, ep, 1, as_stream(stream));
     }
@@ -300,7 +300,7 @@ int cvcl_sim_infonce_bwd_g(const void* img_q, const void* txt_k, const void* txt
     ep.dscale_accum = dscale;
     if (sim_bn(N0, Gs1 ? N1 : N0) == 256) {
         gs.n_stride = 256;
-        return launch_gemm<256, 2, EpiGradG, false, false>(op, gs, ep, 1, as_stream(stream));
+        return launch_gemm_persistent<256, 3, EpiGradG>(op, gs, ep, as_stream(stream));
     }
     return launch_gemm<kBN, 2, EpiGradG, false, false>(op, gs, ep, 1, as_stream(stream));
 }
@@ -486,6 +486,8 @@ int cvcl_spatial_max_fwd(const void* tok, const void* img, const int64_t* lens, 
     op.A[0] = mat(tok, Bt * L, E, E); op.B[0] = mat(img, Bi * HW, E, E);
     GemmShape gs{}; gs.M[0] = gs.M[1] = Bt * L; gs.N[0] = gs.N[1] = Bi * HW; gs.K = E;
     gs.m_stride = ep.TPM * L; gs.n_stride = ep.IPN * HW;
+    if (ceil_div(Bt * L, gs.m_stride) * ceil_div(Bi * HW, gs.n_stride) > 2 * sm_count())
+        return launch_gemm_persistent<BN, 4, EpiSpatialMax>(op, gs, ep, as_stream(stream));
     return launch_gemm<BN, 2, EpiSpatialMax, false, false>(op, gs, ep, 1, as_stream(stream));   // 96 KB ring: 2 CTAs/SM
 }
 

@@ -81,4 +81,60 @@ int launch_gemm(const GemmOperands& op, const GemmShape& gs, const typename Epi:
     return CVCL_OK;
 }
 
+inline int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+// Persistent launch (K-major operands, streaming epilogue): one CTA per SM over all tiles.
+template <int BN, int STAGES, class Epi>
+int launch_gemm_persistent(const GemmOperands& op, const GemmShape& gs, const typename Epi::Params& ep,
+                           cudaStream_t stream) {
+    using L = PersistSmem<BN, STAGES, Epi::kOutElemBytes>;
+    constexpr int smem_bytes = L::template total<Epi>();
+    static_assert(smem_bytes <= 227 * 1024, "shared memory budget");
+    auto kern = gemm_bf16_persistent_kernel<BN, STAGES, Epi>;
+    static thread_local bool attr_done = false;
+    if (!attr_done) {
+        CVCL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        attr_done = true;
+    }
+    GemmMaps maps;
+    TileGrid tg{};
+    int rc;
+    for (int z = 0; z < 2; ++z) {
+        const int zz = z < op.ndir ? z : 0;
+        if ((rc = make_tmap(&maps.a[z], op.A[zz].ptr, 2, op.A[zz].rows, op.A[zz].cols, op.A[zz].ld, 64, kBM))) return rc;
+        if ((rc = make_tmap(&maps.b[z], op.B[zz].ptr, 2, op.B[zz].rows, op.B[zz].cols, op.B[zz].ld, 64, BN))) return rc;
+        if (Epi::kOutElemBytes) {
+            const Mat& o = op.out[zz];
+            if ((rc = make_tmap(&maps.out[z], o.ptr, Epi::kOutElemBytes, o.rows, o.cols, o.ld, 128 / Epi::kOutElemBytes, kBM))) return rc;
+        } else {
+            maps.out[z] = maps.a[z];
+        }
+        tg.tiles_m[z] = z < op.ndir ? ceil_div(gs.M[z], gs.m_stride) : 0;
+        tg.tiles_n[z] = z < op.ndir ? ceil_div(gs.N[z], gs.n_stride) : 0;
+    }
+    maps.aux[0] = maps.aux[1] = maps.a[0];
+    tg.total = tg.tiles_m[0] * tg.tiles_n[0] + tg.tiles_m[1] * tg.tiles_n[1];
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(tg.total < sm_count() ? tg.total : sm_count());
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CVCL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, gs, tg, ep));
+    count_launch();
+    return CVCL_OK;
+}
+
 }  // namespace cvcl

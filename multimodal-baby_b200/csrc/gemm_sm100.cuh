@@ -255,6 +255,144 @@ gemm_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmShape gs, cons
     if (warp == 1) ptx::tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_base);
 }
 
+// -------------------------------------------------------------------------------------------------
+// Persistent variant for large problems (K-major operands, non-cluster epilogues): one CTA per SM
+// loops over output tiles.  The accumulator is double-buffered in TMEM (2 x BN columns), so the MMAs
+// of tile i+1 run while the epilogue warps drain tile i, and the per-CTA costs (launch, TMEM
+// allocation, barrier init, descriptor fetch, store drain at exit) are paid once per SM instead of
+// once per tile.  Tiles are enumerated direction-major with the M index fastest, so the CTAs that
+// run concurrently share the same B (key) tile in L2.
+// -------------------------------------------------------------------------------------------------
+template <int BN, int STAGES, int OUT_BYTES>
+struct PersistSmem {
+    static constexpr int kABytes = kBM * kBK * 2;
+    static constexpr int kBBytes = BN * kBK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kOutOff = STAGES * kStageBytes;
+    static constexpr int kOutBytes = kBM * BN * OUT_BYTES;
+    static constexpr int kBarOff = kOutOff + kOutBytes;
+    static constexpr int kScratchOff = kBarOff + 256;
+    template <class Epi>
+    static constexpr int total() { return kScratchOff + Epi::kScratchBytes + 1024; }
+};
+
+struct TileGrid { int tiles_m[2], tiles_n[2], total; };
+
+template <int BN, int STAGES, class Epi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_persistent_kernel(const __grid_constant__ GemmMaps maps, const GemmShape gs, const TileGrid tg,
+                            const typename Epi::Params ep) {
+    static_assert(!Epi::kClusterReduce && Epi::kNumAux == 0, "persistent kernel: streaming epilogues only");
+    static_assert(BN == 128 || BN == 256, "BN");
+    using L = PersistSmem<BN, STAGES, Epi::kOutElemBytes>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;          // [2] accumulator ready for the epilogue
+    uint64_t* tempty_bar = tfull_bar + 2;              // [2] accumulator drained (4 warp arrivals)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    unsigned char* scratch = smem + L::kScratchOff;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_k = (gs.K + kBK - 1) / kBK;
+    const int count0 = tg.tiles_m[0] * tg.tiles_n[0];
+
+    ptx::pdl_launch_dependents();
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&maps.a[0]); ptx::prefetch_tmap(&maps.b[0]);
+        ptx::prefetch_tmap(&maps.a[1]); ptx::prefetch_tmap(&maps.b[1]);
+        for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 4); }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) ptx::tmem_alloc<2 * BN>(tmem_ptr_smem);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    ptx::pdl_wait();
+
+    auto decode = [&](int t, int& z, int& tm, int& tn) {
+        z = t >= count0 ? 1 : 0;
+        const int local = z ? t - count0 : t;
+        tm = local % tg.tiles_m[z];
+        tn = local / tg.tiles_m[z];
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < tg.total; t += gridDim.x) {
+                int z, tm, tn; decode(t, z, tm, tn);
+                const int m0 = tm * gs.m_stride, n0 = tn * gs.n_stride;
+                for (int kc = 0; kc < num_k; ++kc) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char* sa = smem + stage * L::kStageBytes;
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+                    ptx::tma_load_2d(sa, &maps.a[z], &full_bar[stage], kc * kBK, m0);
+                    ptx::tma_load_2d(sa + L::kABytes, &maps.b[z], &full_bar[stage], kc * kBK, n0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(kBM, BN, false, false);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < tg.total; t += gridDim.x) {
+                ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);     // epilogue has drained this buffer
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kc = 0; kc < num_k; ++kc) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
+                    const uint64_t adesc = ptx::make_kmajor_sw128_desc(sa);
+                    const uint64_t bdesc = ptx::make_kmajor_sw128_desc(sa + L::kABytes);
+#pragma unroll
+                    for (int k = 0; k < kBK / kUmmaK; ++k)
+                        ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                    ptx::umma_commit(&empty_bar[stage]);
+                    if (kc == num_k - 1) ptx::umma_commit(&tfull_bar[acc]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                acc ^= 1; if (acc == 0) acc_phase ^= 1;
+            }
+        }
+        __syncwarp();
+    } else {
+        EpiCtx cx;
+        cx.epi_tid = threadIdx.x - 64;
+        const int quad = warp & 3;
+        cx.row = quad * 32 + lane;
+        cx.scratch = scratch;
+        cx.aux[0] = cx.aux[1] = nullptr;
+        cx.out_stage = smem + L::kOutOff;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < tg.total; t += gridDim.x) {
+            int z, tm, tn; decode(t, z, tm, tn);
+            cx.z = z; cx.tile_m = tm; cx.tile_n = tn; cx.m0 = tm * gs.m_stride; cx.n0 = tn * gs.n_stride;
+            cx.out_map = &maps.out[z];
+            cx.tmem_row = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
+            ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+            ptx::tc_fence_after();
+            Epi::template phase1<BN>(cx, gs, ep);
+            ptx::tc_fence_before();
+            ptx::named_bar_sync(3, kEpiThreads);           // scratch / staging reuse across tiles
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+            acc ^= 1; if (acc == 0) acc_phase ^= 1;
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc<2 * BN>(tmem_base);
+}
+
 // =====================================================================================
 // Epilogue policies.  Interface: kClusterReduce, kScratchBytes, kNumAux (epilogue input tiles
 // fetched by TMA), kOutElemBytes (0: no staged output, 2: bf16 tile, 4: fp32 tile stored by TMA),
