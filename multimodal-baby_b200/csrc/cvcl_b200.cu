@@ -26,7 +26,7 @@ struct SimWs {               // carve-up of the sim workspace
 inline int sim_bn(int N0, int N1) { return (N0 > N1 ? N0 : N1) >= 4096 ? 256 : 128; }   // tile width of the sim kernels
 SimWs carve_sim_ws(void* ws, int M0, int N0, int M1, int N1) {
     SimWs w{};
-    const int bn = sim_bn(N0, N1);
+    const int bn = 128;                 // epilogue tile width (the MMA tile may be 256 wide)
     const int M[2] = {M0, M1}, N[2] = {N0, N1};
     size_t off = 0;
     unsigned char* base = static_cast<unsigned char*>(ws);
@@ -486,8 +486,6 @@ int cvcl_spatial_max_fwd(const void* tok, const void* img, const int64_t* lens, 
     op.A[0] = mat(tok, Bt * L, E, E); op.B[0] = mat(img, Bi * HW, E, E);
     GemmShape gs{}; gs.M[0] = gs.M[1] = Bt * L; gs.N[0] = gs.N[1] = Bi * HW; gs.K = E;
     gs.m_stride = ep.TPM * L; gs.n_stride = ep.IPN * HW;
-    if (ceil_div(Bt * L, gs.m_stride) * ceil_div(Bi * HW, gs.n_stride) > 2 * sm_count())
-        return launch_gemm_persistent<BN, 4, EpiSpatialMax>(op, gs, ep, as_stream(stream));
     return launch_gemm<BN, 2, EpiSpatialMax, false, false>(op, gs, ep, 1, as_stream(stream));   // 96 KB ring: 2 CTAs/SM
 }
 

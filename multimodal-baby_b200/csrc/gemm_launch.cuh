@@ -95,8 +95,8 @@ inline int sm_count() {
 template <int BN, int STAGES, class Epi>
 int launch_gemm_persistent(const GemmOperands& op, const GemmShape& gs, const typename Epi::Params& ep,
                            cudaStream_t stream) {
-    using L = PersistSmem<BN, STAGES, Epi::kOutElemBytes>;
-    constexpr int smem_bytes = L::template total<Epi>();
+    using L = PersistSmem<BN, STAGES, Epi::kOutElemBytes, Epi::kScratchBytes>;
+    constexpr int smem_bytes = L::total();
     static_assert(smem_bytes <= 227 * 1024, "shared memory budget");
     auto kern = gemm_bf16_persistent_kernel<BN, STAGES, Epi>;
     static thread_local bool attr_done = false;
@@ -124,7 +124,7 @@ int launch_gemm_persistent(const GemmOperands& op, const GemmShape& gs, const ty
     tg.total = tg.tiles_m[0] * tg.tiles_n[0] + tg.tiles_m[1] * tg.tiles_n[1];
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(tg.total < sm_count() ? tg.total : sm_count());
-    cfg.blockDim = dim3(kGemmThreads);
+    cfg.blockDim = dim3(64 + 128 * (BN / 128));
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute at[1];

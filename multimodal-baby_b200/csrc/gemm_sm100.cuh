@@ -52,6 +52,7 @@ struct EpiCtx {
     unsigned char* aux[2];          // smem: epilogue input tiles (128B-swizzled TMA boxes)
     unsigned char* out_stage;       // smem: output staging (reuses the operand ring after the mainloop)
     const CUtensorMap* out_map;
+    int bar_base;                   // named-barrier id offset of this epilogue group (0 unless persistent)
 };
 
 // ---- swizzled shared-memory tile access (layout written / read by TMA with SWIZZLE_128B) --------
@@ -85,7 +86,7 @@ __device__ __forceinline__ void unpack_bf16x8(uint4 q, float* v) {
 template <int BN, int ELEM>
 __device__ __forceinline__ void out_tile_commit(const EpiCtx& cx) {
     ptx::fence_proxy_async_smem();
-    ptx::named_bar_sync(2, kEpiThreads);
+    ptx::named_bar_sync(2 + cx.bar_base, kEpiThreads);
     if (cx.epi_tid == 0) {
         constexpr int kBoxCols = 128 / ELEM;
 #pragma unroll
@@ -235,6 +236,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmShape gs, cons
     cx.aux[1] = smem + L::kAuxOff + (Epi::kNumAux > 1 ? L::kAuxBytes : 0);
     cx.out_stage = smem;                          // operand ring is idle once tmem_full has fired
     cx.out_map = &maps.out[z];
+    cx.bar_base = 0;
 
     if (warp >= 2) {
         if constexpr (Epi::kNumAux > 0) ptx::mbar_wait(aux_bar, 0);
@@ -263,37 +265,40 @@ gemm_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmShape gs, cons
 // once per tile.  Tiles are enumerated direction-major with the M index fastest, so the CTAs that
 // run concurrently share the same B (key) tile in L2.
 // -------------------------------------------------------------------------------------------------
-template <int BN, int STAGES, int OUT_BYTES>
+template <int BN, int STAGES, int OUT_BYTES, int SCRATCH>
 struct PersistSmem {
+    static constexpr int kGroups = BN / 128;                 // epilogue groups: 128 columns each
     static constexpr int kABytes = kBM * kBK * 2;
     static constexpr int kBBytes = BN * kBK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kOutOff = STAGES * kStageBytes;
-    static constexpr int kOutBytes = kBM * BN * OUT_BYTES;
-    static constexpr int kBarOff = kOutOff + kOutBytes;
+    static constexpr int kOutBytes = kBM * 128 * OUT_BYTES;  // per group
+    static constexpr int kBarOff = kOutOff + kGroups * kOutBytes;
     static constexpr int kScratchOff = kBarOff + 256;
-    template <class Epi>
-    static constexpr int total() { return kScratchOff + Epi::kScratchBytes + 1024; }
+    static constexpr int kScratchBytes = (SCRATCH + 15) / 16 * 16;   // per group
+    static constexpr int total() { return kScratchOff + kGroups * kScratchBytes + 1024; }
 };
 
 struct TileGrid { int tiles_m[2], tiles_n[2], total; };
 
+// The MMA tile is 128 x BN; the epilogue sees it as BN/128 independent 128 x 128 tiles, each drained
+// by its own group of four warps (one thread per row), so a BN = 256 CTA runs 8 epilogue warps.
 template <int BN, int STAGES, class Epi>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(64 + 128 * (BN / 128), 1)
 gemm_bf16_persistent_kernel(const __grid_constant__ GemmMaps maps, const GemmShape gs, const TileGrid tg,
                             const typename Epi::Params ep) {
     static_assert(!Epi::kClusterReduce && Epi::kNumAux == 0, "persistent kernel: streaming epilogues only");
     static_assert(BN == 128 || BN == 256, "BN");
-    using L = PersistSmem<BN, STAGES, Epi::kOutElemBytes>;
+    using L = PersistSmem<BN, STAGES, Epi::kOutElemBytes, Epi::kScratchBytes>;
+    constexpr int kGroups = L::kGroups;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;          // [2] accumulator ready for the epilogue
-    uint64_t* tempty_bar = tfull_bar + 2;              // [2] accumulator drained (4 warp arrivals)
+    uint64_t* tempty_bar = tfull_bar + 2;              // [2] accumulator drained (one arrival per epilogue warp)
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    unsigned char* scratch = smem + L::kScratchOff;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -305,7 +310,7 @@ gemm_bf16_persistent_kernel(const __grid_constant__ GemmMaps maps, const GemmSha
         ptx::prefetch_tmap(&maps.a[0]); ptx::prefetch_tmap(&maps.b[0]);
         ptx::prefetch_tmap(&maps.a[1]); ptx::prefetch_tmap(&maps.b[1]);
         for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 4); }
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 4 * kGroups); }
         ptx::fence_mbar_init();
     }
     if (warp == 1) ptx::tmem_alloc<2 * BN>(tmem_ptr_smem);
@@ -367,23 +372,26 @@ gemm_bf16_persistent_kernel(const __grid_constant__ GemmMaps maps, const GemmSha
         __syncwarp();
     } else {
         EpiCtx cx;
-        cx.epi_tid = threadIdx.x - 64;
+        const int grp = (warp - 2) >> 2;               // which 128-column slice of the MMA tile
+        cx.epi_tid = (threadIdx.x - 64) & 127;
         const int quad = warp & 3;
         cx.row = quad * 32 + lane;
-        cx.scratch = scratch;
+        cx.scratch = smem + L::kScratchOff + grp * L::kScratchBytes;
         cx.aux[0] = cx.aux[1] = nullptr;
-        cx.out_stage = smem + L::kOutOff;
+        cx.out_stage = smem + L::kOutOff + grp * L::kOutBytes;
+        cx.bar_base = 4 * grp;                         // named barriers 1..3 (+4 per group)
         int acc = 0; uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < tg.total; t += gridDim.x) {
             int z, tm, tn; decode(t, z, tm, tn);
-            cx.z = z; cx.tile_m = tm; cx.tile_n = tn; cx.m0 = tm * gs.m_stride; cx.n0 = tn * gs.n_stride;
+            cx.z = z; cx.tile_m = tm; cx.tile_n = tn * kGroups + grp;
+            cx.m0 = tm * gs.m_stride; cx.n0 = tn * gs.n_stride + grp * 128;
             cx.out_map = &maps.out[z];
-            cx.tmem_row = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
+            cx.tmem_row = tmem_base + acc * BN + grp * 128 + (static_cast<uint32_t>(quad * 32) << 16);
             ptx::mbar_wait(&tfull_bar[acc], acc_phase);
             ptx::tc_fence_after();
-            Epi::template phase1<BN>(cx, gs, ep);
+            Epi::template phase1<128>(cx, gs, ep);
             ptx::tc_fence_before();
-            ptx::named_bar_sync(3, kEpiThreads);           // scratch / staging reuse across tiles
+            ptx::named_bar_sync(3 + cx.bar_base, kEpiThreads);   // scratch / staging reuse across tiles
             if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
             acc ^= 1; if (acc == 0) acc_phase ^= 1;
         }
@@ -625,7 +633,7 @@ struct EpiGradG {
         float* lk = reinterpret_cast<float*>(cx.scratch);
         for (int j = cx.epi_tid; j < BN; j += kEpiThreads)
             lk[j] = (cx.n0 + j < N) ? __ldg(p.lse_k[cx.z] + cx.n0 + j) * kLog2e : 0.f;
-        ptx::named_bar_sync(1, kEpiThreads);
+        ptx::named_bar_sync(1 + cx.bar_base, kEpiThreads);
         const float lq = (m < M) ? __ldg(p.lse_q[cx.z] + m) * kLog2e : 0.f;
         const int dcol = m + p.diag_off[cx.z];
         const float sc2 = p.scale * kLog2e;
@@ -829,7 +837,7 @@ struct EpiSpatialMax {
                 }
             }
         }
-        ptx::named_bar_sync(1, kEpiThreads);
+        ptx::named_bar_sync(1 + cx.bar_base, kEpiThreads);
         if (cx.epi_tid < p.TPM * p.IPN) {
             const int tt = cx.epi_tid / p.IPN, qq = cx.epi_tid % p.IPN;
             const int t = cx.tile_m * p.TPM + tt, i = img0 + qq;
