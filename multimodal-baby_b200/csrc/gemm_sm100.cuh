@@ -566,37 +566,60 @@ struct EpiSimStats {
         const int dcol = m + p.diag_off[cx.z];
         constexpr float kLog2e = 1.4426950408889634f;
         if (cx.tile_m == 0 && cx.tile_n == 0 && cx.z == 0 && cx.epi_tid == 0) *p.ticket = 0u;
-        float mx = -INFINITY, l = 0.f, a = 0.f;
+        // Work on the raw dot products r (logit = scale * r, scale > 0): the scale is folded into the
+        // exp2 argument, so the hot loop is FMNMX + FFMA + MUFU.EX2 + FADD + FFMA per element.
+        float mx = -INFINITY, l = 0.f, a = 0.f;        // mx, a in the raw domain
         int arg = cx.n0;
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-            float v[32];
-            ptx::tmem_ld_32x32(cx.tmem_row + c, v);     // warp-collective
+        const float sc2 = p.scale * kLog2e;
+        auto chunk = [&](float* v, int c) {
             const int n = cx.n0 + c;
-            if (n >= N) continue;                       // warp-uniform
-            float nm = mx;
+            if (n >= N) return;                         // warp-uniform
+            const bool full = n + 32 <= N;              // warp-uniform
+            if (!full) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const bool ok = (n + j < N);
-                v[j] *= p.scale;
-                if (ok && v[j] > nm) { nm = v[j]; arg = n + j; }   // strict > keeps the first max
-                if (n + j == dcol && ok && m < M) p.diag[cx.z][m] = v[j];
+                for (int j = 0; j < 32; ++j) if (n + j >= N) v[j] = -INFINITY;
             }
-            const float corr = exp2f((mx - nm) * kLog2e);          // mx = -inf -> 0
+            float cm = v[0];
+#pragma unroll
+            for (int j = 1; j < 32; ++j) cm = fmaxf(cm, v[j]);
+            if (cm > mx) {                              // rare after the first chunks: locate the first max
+                int k = 31;
+#pragma unroll
+                for (int j = 31; j >= 0; --j) if (v[j] == cm) k = j;
+                arg = n + k;
+            }
+            if (dcol >= n && dcol < n + 32 && m < M) { // the positive lives in exactly one chunk per row
+                float dv = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (n + j == dcol) dv = v[j];
+                p.diag[cx.z][m] = dv * p.scale;
+            }
+            const float nm = fmaxf(mx, cm);
+            const float corr = exp2f((mx - nm) * sc2);             // mx = -inf -> 0
             l *= corr; a *= corr;
-            const float nm2 = nm * kLog2e;
+            const float nm2 = nm * sc2;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                if (n + j < N) {
-                    const float e = exp2f(fmaf(v[j], kLog2e, -nm2));
-                    l += e;
-                    a = fmaf(e, v[j], a);
-                }
+                const float e = exp2f(fmaf(v[j], sc2, -nm2));      // masked columns: exp2(-inf) = 0
+                l += e;
+                a = fmaf(e, full ? v[j] : (n + j < N ? v[j] : 0.f), a);
             }
             mx = nm;
+        };
+        // two register buffers: the TMEM load of the next 32 columns is in flight during the math
+        float va[32], vb[32];
+        ptx::tmem_ld_32x32_issue(cx.tmem_row, va);
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 64) {
+            ptx::tmem_ld_wait();
+            ptx::tmem_ld_32x32_issue(cx.tmem_row + c + 32, vb);
+            chunk(va, c);
+            ptx::tmem_ld_wait();
+            if (c + 64 < BN) ptx::tmem_ld_32x32_issue(cx.tmem_row + c + 64, va);
+            chunk(vb, c + 32);
         }
         if (m < M) {
-            RowStat rs; rs.m = mx; rs.l = l; rs.a = a; rs.arg = arg;
+            RowStat rs; rs.m = mx * p.scale; rs.l = l; rs.a = a * p.scale; rs.arg = arg;
             p.part[cx.z][static_cast<size_t>(cx.tile_n) * p.m_pad[cx.z] + m] = rs;
         }
     }
@@ -647,8 +670,7 @@ struct EpiGradG {
             const bool live = (m < M) && (n < N);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const float x2 = v[j] * sc2;                       // logit * log2(e)
-                float g = exp2f(x2 - lq) + exp2f(x2 - lk[c + j]);
+                float g = exp2f(fmaf(v[j], sc2, -lq)) + exp2f(fmaf(v[j], sc2, -lk[c + j]));   // P_row + P_col
                 g *= w;                                            // exp(s) * coef * (P_row + P_col)
                 if (live && n + j < N) {
                     ds = fmaf(g, v[j], ds);                        // G * logit = Gs * raw dot
