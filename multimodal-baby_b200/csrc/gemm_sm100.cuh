@@ -653,33 +653,53 @@ struct EpiGradG {
         const int M = gs.M[cx.z], N = gs.N[cx.z];
         const int m = cx.m0 + cx.row;
         constexpr float kLog2e = 1.4426950408889634f;
+        // Gs = w * (2^(r*sc2 - lse_q*log2e) + 2^(r*sc2 - lse_k*log2e)), w = exp(s)*coef: fold log2(w)
+        // into both offsets so each softmax term is one FFMA + one MUFU.EX2.
+        const float w = p.scale * p.coef;
+        const float l2w = log2f(w);
         float* lk = reinterpret_cast<float*>(cx.scratch);
         for (int j = cx.epi_tid; j < BN; j += kEpiThreads)
-            lk[j] = (cx.n0 + j < N) ? __ldg(p.lse_k[cx.z] + cx.n0 + j) * kLog2e : 0.f;
+            lk[j] = (cx.n0 + j < N) ? __ldg(p.lse_k[cx.z] + cx.n0 + j) * kLog2e - l2w : INFINITY;
         ptx::named_bar_sync(1 + cx.bar_base, kEpiThreads);
-        const float lq = (m < M) ? __ldg(p.lse_q[cx.z] + m) * kLog2e : 0.f;
+        const float lq = (m < M) ? __ldg(p.lse_q[cx.z] + m) * kLog2e - l2w : INFINITY;   // dead rows -> 0
         const int dcol = m + p.diag_off[cx.z];
         const float sc2 = p.scale * kLog2e;
-        const float w = p.scale * p.coef;
         float ds = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-            float v[32];
-            ptx::tmem_ld_32x32(cx.tmem_row + c, v);
+        auto chunk = [&](float* v, int c) {
             const int n = cx.n0 + c;
-            const bool live = (m < M) && (n < N);
+            float dv = 0.f;
+            if (dcol >= n && dcol < n + 32) {           // the -2*I term (fp32) touches one chunk per row
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float g = exp2f(fmaf(v[j], sc2, -lq)) + exp2f(fmaf(v[j], sc2, -lk[c + j]));   // P_row + P_col
-                g *= w;                                            // exp(s) * coef * (P_row + P_col)
-                if (live && n + j < N) {
-                    ds = fmaf(g, v[j], ds);                        // G * logit = Gs * raw dot
-                    if (n + j == dcol) ds = fmaf(-2.f * w, v[j], ds);   // the -2*I term, kept in fp32
-                }
-                v[j] = live ? g : 0.f;
+                for (int j = 0; j < 32; ++j) if (n + j == dcol) dv = v[j];
             }
+            float g[32];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) swz_st16(cx.out_stage, cx.row, (c + 8 * j) * 2, pack_bf16x8(v + 8 * j));
+            for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 k4 = *reinterpret_cast<const float4*>(lk + c + 4 * j4);   // masked columns: +inf -> 0
+                const float kk[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int j = 4 * j4 + q;
+                    const float r = v[j];
+                    const float gg = exp2f(fmaf(r, sc2, -lq)) + exp2f(fmaf(r, sc2, -kk[q]));
+                    ds = fmaf(gg, r, ds);                              // G * logit = Gs * raw dot
+                    g[j] = gg;
+                }
+            }
+            ds = fmaf(-2.f * w, dv, ds);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) swz_st16(cx.out_stage, cx.row, (c + 8 * j) * 2, pack_bf16x8(g + 8 * j));
+        };
+        float va[32], vb[32];
+        ptx::tmem_ld_32x32_issue(cx.tmem_row, va);
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 64) {
+            ptx::tmem_ld_wait();
+            ptx::tmem_ld_32x32_issue(cx.tmem_row + c + 32, vb);
+            chunk(va, c);
+            ptx::tmem_ld_wait();
+            if (c + 64 < BN) ptx::tmem_ld_32x32_issue(cx.tmem_row + c + 64, va);
+            chunk(vb, c + 32);
         }
         out_tile_commit<BN, 2>(cx);
         if (cx.z == 0 && p.dscale_accum) {
