@@ -846,8 +846,72 @@ struct EpiSpatialMax {
         unsigned char* amax_it;       // [Bi, Bt*L]
         unsigned char* amax_ti;       // [Bt*L, Bi]
     };
+    // Static-segment fast path (HW known at compile time, e.g. the 7x7 = 49 locations of the ResNeXt
+    // layer4 map): the chunk loop is fully unrolled, so every column's image slot is a compile-time
+    // constant, the running maxima live in registers, and the hot loop is one FMNMX per element; the
+    // arg-max scan only runs when a chunk improves its segment's maximum.
+    template <int BN, int HW>
+    static __device__ __forceinline__ void phase1_static(const EpiCtx& cx, const Params& p) {
+        constexpr int IPN = BN / HW;
+        float* vals = reinterpret_cast<float*>(cx.scratch);          // [128][IPN]
+        const int r = cx.row;
+        const int grow = cx.m0 + r;
+        const bool row_ok = r < p.TPM * p.L && grow < p.Bt * p.L;
+        const int img0 = cx.tile_n * IPN;
+        float best[IPN]; int barg[IPN];
+#pragma unroll
+        for (int q = 0; q < IPN; ++q) { best[q] = -INFINITY; barg[q] = 0; }
+        float va[32], vb[32];
+        ptx::tmem_ld_32x32_issue(cx.tmem_row, va);
+#pragma unroll
+        for (int c = 0; c < BN; c += 32) {
+            float* v = ((c >> 5) & 1) ? vb : va;
+            ptx::tmem_ld_wait();
+            if (c + 32 < BN) ptx::tmem_ld_32x32_issue(cx.tmem_row + c + 32, ((c >> 5) & 1) ? va : vb);
+            // a 32-column chunk touches at most two image segments
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+                const int q = c / HW + part;                          // compile-time after unrolling
+                const int lo = part == 0 ? 0 : (c / HW + 1) * HW - c;
+                const int hi = part == 0 ? ((c / HW + 1) * HW - c < 32 ? (c / HW + 1) * HW - c : 32) : 32;
+                if (q < IPN && lo < hi && lo < 32) {
+                    float cm = v[lo];
+#pragma unroll
+                    for (int j = lo + 1; j < hi; ++j) cm = fmaxf(cm, v[j]);
+                    if (cm > best[q]) {                               // strict >: earlier columns win ties
+                        int k = hi - 1;
+#pragma unroll
+                        for (int j = hi - 1; j >= lo; --j) if (v[j] == cm) k = j;
+                        best[q] = cm; barg[q] = c + k - q * HW;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < IPN; ++q) {
+            vals[r * IPN + q] = best[q];
+            const int i = img0 + q;
+            if (row_ok && i < p.Bi) {
+                p.amax_it[static_cast<size_t>(i) * (p.Bt * p.L) + grow] = static_cast<unsigned char>(barg[q]);
+                p.amax_ti[static_cast<size_t>(grow) * p.Bi + i] = static_cast<unsigned char>(barg[q]);
+            }
+        }
+        ptx::named_bar_sync(1 + cx.bar_base, kEpiThreads);
+        if (cx.epi_tid < p.TPM * IPN) {
+            const int tt = cx.epi_tid / IPN, qq = cx.epi_tid % IPN;
+            const int t = cx.tile_m * p.TPM + tt, i = img0 + qq;
+            if (t < p.Bt && i < p.Bi) {
+                float s = 0.f;
+                for (int l = 0; l < p.L; ++l) s += vals[(tt * p.L + l) * IPN + qq];
+                p.match[static_cast<size_t>(i) * p.Bt + t] = s / static_cast<float>(p.lens[t]);
+            }
+        }
+    }
     template <int BN>
     static __device__ __forceinline__ void phase1(const EpiCtx& cx, const GemmShape& gs, const Params& p) {
+        if constexpr (BN == 256) {
+            if (p.HW == 49 && p.IPN == 5) { phase1_static<256, 49>(cx, p); return; }
+        }
         float* vals = reinterpret_cast<float*>(cx.scratch);          // [128][IPN]
         const int r = cx.row;
         const int grow = cx.m0 + r;                                  // global token row
