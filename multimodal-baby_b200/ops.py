@@ -481,6 +481,17 @@ def sim_infonce_bwd(img_q: Tensor, txt_k: Tensor, txt_q: Tensor, img_k: Tensor, 
     dimg = torch.empty((M0, E), dtype=torch.float32, device=dev)
     dtxt = torch.empty((M1, E), dtype=torch.float32, device=dev)
     dcoef = -2.0 * math.exp(log_scale) * coef            # the -2*I term of G, applied in fp32
+    if min(N0, N1) >= 4096:
+        # long contraction: plain 128 x 256-tile GEMMs (higher tensor throughput), then the fp32
+        # diagonal term as one axpy over [M,E]
+        _cabi.call("cvcl_gemm_f32out", _p(G0), ld0, 0, _p(txt_k), E, 1, M0, E, N0, 1.0, _p(dimg), E, _stream())
+        if single:
+            _cabi.call("cvcl_gemm_f32out", _p(G0), ld0, 1, _p(img_k), E, 1, M1, E, N1, 1.0, _p(dtxt), E, _stream())
+        else:
+            _cabi.call("cvcl_gemm_f32out", _p(G1), ld1, 0, _p(img_k), E, 1, M1, E, N1, 1.0, _p(dtxt), E, _stream())
+        dimg.add_(txt_k[diag_off:diag_off + M0].float(), alpha=dcoef)
+        dtxt.add_(img_k[diag_off:diag_off + M1].float(), alpha=dcoef)
+        return dimg, dtxt, ds
     _cabi.call("cvcl_feat_grad_norm_bwd", _p(G0), ld0, 0, _p(txt_k), E, M0, E, N0, None, 0, None, 0, None,
                _p(txt_k), E, N0, int(diag_off), dcoef, _p(dimg), E, None, 0, None, _stream())
     if single:      # dT = Gs^T . I: the same Gs read MN-major, no second orientation needed
