@@ -408,8 +408,9 @@ def main():
     #     fwd+bwd, D2H of the loss all inside the replay; wall clock per call incl. the stream sync
     e2e_dt, e2e_api = eager_dt, "MultiModalModel.calculate_contrastive_loss + backward (eager)"
     try:
-        gstep = m.GraphedContrastiveStep(model, x_host, ids_host, lens_host)
-        for _ in range(5):
+        gstep = m.GraphedContrastiveStep(model, x_host, ids_host, lens_host, prefetch=True)
+        gstep.prime()
+        for _ in range(6):
             gstep()
         barrier()
         t0 = time.perf_counter()
@@ -418,7 +419,9 @@ def main():
         barrier()
         g_dt = (time.perf_counter() - t0) / e2e_steps
         if g_dt < e2e_dt:
-            e2e_dt, e2e_api = g_dt, "GraphedContrastiveStep(model)() = calculate_contrastive_loss + backward as one CUDA graph"
+            e2e_dt, e2e_api = g_dt, ("GraphedContrastiveStep(model, prefetch=True)() = calculate_contrastive_loss + backward as "
+                                     "one CUDA graph; every call copies one full batch H2D (overlapped with the kernels of "
+                                     "the previously copied batch) and reads the loss back")
     except Exception as exc:
         if rank == 0:
             print("graphed e2e step unavailable: %s" % exc, file=sys.stderr)

@@ -8,6 +8,12 @@ MultiModalModel.calculate_contrastive_loss + backward, multimodal.py:796-822).
     # gradients are in p.grad of the head parameters (static views of one flat buffer)
 
 The loader writes the next batch into `step.x_host / ids_host / lens_host` (pinned) between calls.
+
+`prefetch=True` double-buffers the device inputs: replay k computes on the batch that replay k-1
+copied while it was computing, and copies the batch now staged in the pinned buffers for replay k+1
+(H2D overlaps the kernels on a second graph branch).  Every call still moves one full batch host ->
+device; the returned loss belongs to the batch staged one call earlier (call `prime()` once after
+staging the first batch).
 """
 from __future__ import annotations
 
@@ -17,7 +23,7 @@ from . import ops
 
 
 class GraphedContrastiveStep:
-    def __init__(self, model, x_host, ids_host, lens_host, warmup=3):
+    def __init__(self, model, x_host, ids_host, lens_host, warmup=3, prefetch=False):
         if model.embedding_type != "flat":
             raise NotImplementedError("GraphedContrastiveStep covers the flat-embedding train step")
         for t in (x_host, ids_host, lens_host):
@@ -30,10 +36,14 @@ class GraphedContrastiveStep:
         table = model.text_embed.embedding.weight
         dev = table.device
         self.dev = dev
-        self.x = torch.empty_like(x_host, device=dev)
-        self.ids = torch.empty_like(ids_host, device=dev)
-        self.lens = torch.empty_like(lens_host, device=dev)
+        self.prefetch = bool(prefetch)
+        nbuf = 2 if self.prefetch else 1
+        self.bufs = [(torch.empty_like(x_host, device=dev), torch.empty_like(ids_host, device=dev),
+                      torch.empty_like(lens_host, device=dev)) for _ in range(nbuf)]
+        self.x, self.ids, self.lens = self.bufs[0]
         self.stats_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self.copy_stream = torch.cuda.Stream(device=dev) if self.prefetch else None
+        self.calls = 0
         s = model.logit_neg_log_temperature
         if isinstance(s, torch.nn.Parameter):
             raise NotImplementedError("graphed step needs fix_temperature=True (s is baked into the graph)")
@@ -41,46 +51,81 @@ class GraphedContrastiveStep:
         norm = bool(model.normalize_features)
         E, K, V = table.shape[1], w.shape[1], table.shape[0]
 
+        def h2d(buf):
+            buf[0].copy_(self.x_host, non_blocking=True)
+            buf[1].copy_(self.ids_host, non_blocking=True)
+            buf[2].copy_(self.lens_host, non_blocking=True)
+
         @torch.no_grad()
-        def body():
-            self.x.copy_(self.x_host, non_blocking=True)
-            self.ids.copy_(self.ids_host, non_blocking=True)
-            self.lens.copy_(self.lens_host, non_blocking=True)
-            if self.group is None:
-                out5, _, _, flat = ops.flat_contrastive_step(self.x, self.ids, self.lens, w, b, table, ls,
-                                                             norm, True, False)
+        def body(cur, nxt):
+            main = torch.cuda.current_stream(dev)
+            if nxt is None:
+                h2d(cur)                                   # copy, then compute (serial)
             else:
-                stats, _, _ = ops.flat_step_sharded(self.x, self.ids, self.lens, w, b, table, ls, norm,
-                                                    True, False, self.group)
+                self.copy_stream.wait_stream(main)         # copy the NEXT batch beside the kernels
+                with torch.cuda.stream(self.copy_stream):
+                    h2d(nxt)
+            x_d, ids_d, lens_d = cur
+            if self.group is None:
+                out5, _, _, flat = ops.flat_contrastive_step(x_d, ids_d, lens_d, w, b, table, ls, norm, True, False)
+            else:
+                stats, _, _ = ops.flat_step_sharded(x_d, ids_d, lens_d, w, b, table, ls, norm, True, False,
+                                                    self.group)
                 out5, flat = stats[:8], stats[8:]
             self.stats_host.copy_(out5, non_blocking=True)
+            if nxt is not None:
+                main.wait_stream(self.copy_stream)
             return flat
 
+        pairs = [(self.bufs[0], None)] if not self.prefetch else [(self.bufs[0], self.bufs[1]),
+                                                                  (self.bufs[1], self.bufs[0])]
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                body()
+                for cur, nxt in pairs:
+                    body(cur, nxt)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.flat = body()
-        ds, db, dtable, dW = ops.split_flat_grads(self.flat, E, K, V)
-        # static gradient views: replay overwrites them in place
+        # one flat gradient buffer shared by all graphs: the parameters' .grad are static views of it
+        self.graphs, flats = [], []
+        for cur, nxt in pairs:
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph):
+                flats.append(body(cur, nxt))
+            self.graphs.append(gph)
+        self.graph = self.graphs[0]
+        self.flats = flats
+        self.flat = flats[0]
+        self._bind_grads(0, E, K, V, table)
+        self._dims = (E, K, V, table)
+
+    def _bind_grads(self, which, E, K, V, table):
+        ds, db, dtable, dW = ops.split_flat_grads(self.flats[which], E, K, V)
         w_param, b_param = self._head_params()
         w_param.grad = dW.view_as(w_param)
         if b_param is not None:
             b_param.grad = db
         table.grad = dtable
 
+    def prime(self):
+        """prefetch mode: copy the batch currently staged in the pinned buffers into device buffer 0."""
+        for d, h in zip(self.bufs[0], (self.x_host, self.ids_host, self.lens_host)):
+            d.copy_(h, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        self.calls = 0
+
     def _head_params(self):
         m = self.model.image_embed.model
         return m.fc.weight, m.fc.bias
 
     def __call__(self):
-        self.graph.replay()
+        which = self.calls % len(self.graphs)
+        self.graphs[which].replay()
         torch.cuda.current_stream(self.dev).synchronize()
+        if len(self.graphs) > 1:
+            self._bind_grads(which, *self._dims)           # .grad views of the buffer just written
+        self.calls += 1
         return float(self.stats_host[0])
 
     def stats(self):

@@ -376,3 +376,31 @@ def test_graphed_step_equals_eager(cv):
     loss2 = step()
     out2 = m.calculate_contrastive_loss(t(inp2["f"], DEV), t(inp2["ids"], DEV), t(inp2["lens"], DEV))
     assert abs(loss2 - out2[0].item()) <= 1e-6 * abs(loss2) and abs(loss2 - loss) > 1e-6
+
+
+def test_graphed_step_prefetch_pipeline(cv):
+    """prefetch=True: call k computes on the batch copied during call k-1 and copies the batch staged
+    now; losses therefore trail the staged batches by one call."""
+    import argparse
+    E = 512
+    args = argparse.Namespace(embedding_type="flat", embedding_dim=E, normalize_features=True,
+                              fix_temperature=True, temperature=0.07, text_encoder="embedding")
+    vocab = {str(i): i for i in range(2350)}
+    m = cv.MultiModalModel(cv.VisionEncoder(args, trunk="pooled"), cv.TextEncoder(vocab, 2048, args), args)
+    inps = [case_inputs(400 + k, 128, E, "flat") for k in range(3)]
+    with torch.no_grad():
+        m.image_embed.model.fc.weight.copy_(t(inps[0]["W"])); m.image_embed.model.fc.bias.copy_(t(inps[0]["b"]))
+        m.text_embed.embedding.weight.copy_(t(inps[0]["table"]))
+    m.to(DEV).train()
+    m.materialize_logits = m.materialize_text_outputs = m.materialize_features = False
+    ref = [m.calculate_contrastive_loss(t(i["f"], DEV), t(i["ids"], DEV), t(i["lens"], DEV))[0].item() for i in inps]
+    xh = t(inps[0]["f"]).pin_memory(); ih = t(inps[0]["ids"]).pin_memory(); lh = t(inps[0]["lens"]).pin_memory()
+    step = cv.GraphedContrastiveStep(m, xh, ih, lh, prefetch=True)
+    step.prime()                                        # batch 0 on the device
+    got = []
+    for k in (1, 2, 2):                                 # stage batch k, run: computes batch k-1
+        xh.copy_(t(inps[k]["f"])); ih.copy_(t(inps[k]["ids"])); lh.copy_(t(inps[k]["lens"]))
+        got.append(step())
+    for a, b in zip(got, ref):
+        assert abs(a - b) <= 1e-6 * abs(b), (got, ref)
+    assert m.image_embed.model.fc.weight.grad is not None
