@@ -220,8 +220,11 @@ int cvcl_head_proj_norm_fwd(const void* x, int ldx, const void* w, int ldw, cons
     EpiHeadNorm::Params ep{};
     ep.bias = bias; ep.normalize = normalize; ep.out_f32 = out_f32; ep.ld_f32 = ld_f32;
     ep.store_bf16 = out_bf16 != nullptr; ep.inv_norm = inv_norm;
-    // K = 2048 streams 32 k-chunks per CTA and few CTAs exist at small M: a 6-deep ring keeps
-    // 192 KB in flight per SM (latency-bound mainloop)
+    // small M: few CTAs, a 6-deep ring keeps 192 KB in flight per SM (latency-bound mainloop);
+    // large M (spatial head, M = B*49): 3-deep ring so two CTAs share an SM and one's cluster
+    // epilogue overlaps the other's MMAs
+    if (ceil_div(M, kBM) * cluster > 2 * sm_count())
+        return launch_gemm<kBN, 3, EpiHeadNorm, false, false>(op, gs, ep, cluster, as_stream(stream));
     return launch_gemm<kBN, 6, EpiHeadNorm, false, false>(op, gs, ep, cluster, as_stream(stream));
 }
 
@@ -357,6 +360,25 @@ int cvcl_head_weight_grad(const void* du, int ld_du, const void* x, int ld_x, in
     CVCL_REQUIRE(du && x && dW, "head_weight_grad: null pointer");
     CVCL_REQUIRE(E > 0 && K > 0 && M > 0, "head_weight_grad: bad shape");
     // dW[e,k] = sum_m du[m,e] * x[m,k]: both operands MN-major (the contraction index m strides)
+    const int tiles = ceil_div(E, kBM) * ceil_div(K, kBN);
+    const int chunks = ceil_div(M, kBK);
+    if (tiles < sm_count() && chunks >= 64 && (ld_dw & 3) == 0 && (reinterpret_cast<uintptr_t>(dW) & 15) == 0) {
+        // long contraction, few output tiles (spatial head: M = B*49): split the contraction over
+        // blockIdx.z so every SM has work; partial tiles are added with fp32 vector atomics
+        int splits = ceil_div(2 * sm_count(), tiles);
+        if (splits > chunks / 8) splits = chunks / 8;
+        // every split must own at least one chunk: ceil(chunks / splits) * (splits - 1) < chunks
+        while (splits > 1 && ceil_div(chunks, splits) * (splits - 1) >= chunks) --splits;
+        if (splits > 1) {
+            CVCL_CHECK_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * static_cast<size_t>(E) * ld_dw, as_stream(stream)));
+            GemmOperands op{}; op.ndir = 1;
+            op.A[0] = mat(du, M, E, ld_du); op.B[0] = mat(x, M, K, ld_x);
+            GemmShape gs{}; gs.M[0] = gs.M[1] = E; gs.N[0] = gs.N[1] = K; gs.K = M; gs.m_stride = kBM; gs.n_stride = kBN;
+            gs.k_splits = splits;
+            EpiAtomicAddF32::Params ep{}; ep.C = dW; ep.ldc = ld_dw; ep.alpha = 1.f;
+            return launch_gemm<kBN, 3, EpiAtomicAddF32, true, true>(op, gs, ep, 1, as_stream(stream));
+        }
+    }
     return cvcl_gemm_f32out(du, ld_du, 1, x, ld_x, 1, E, K, M, 1.f, dW, ld_dw, stream);
 }
 

@@ -60,7 +60,7 @@ int launch_gemm(const GemmOperands& op, const GemmShape& gs, const typename Epi:
     }
     int max_m = gs.M[0], max_n = gs.N[0];
     if (op.ndir == 2) { max_m = max_m > gs.M[1] ? max_m : gs.M[1]; max_n = max_n > gs.N[1] ? max_n : gs.N[1]; }
-    dim3 grid(ceil_div(max_m, gs.m_stride), ceil_div(max_n, gs.n_stride), op.ndir);
+    dim3 grid(ceil_div(max_m, gs.m_stride), ceil_div(max_n, gs.n_stride), gs.k_splits > 1 ? gs.k_splits : op.ndir);
     if (cluster_n > 1) grid.y = ceil_div((int)grid.y, cluster_n) * cluster_n;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;

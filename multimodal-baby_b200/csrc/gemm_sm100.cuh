@@ -33,6 +33,7 @@ struct GemmShape {
     int m_stride;        // tile origin step along M (kBM unless tiles overlap/segment)
     int n_stride;        // tile origin step along N
     int aux_row_off[2];  // row offset of each epilogue input tile relative to m0
+    int k_splits;        // > 1: blockIdx.z splits the contraction (single direction, additive epilogue)
 };
 
 // All tensor maps of one launch (passed as a single __grid_constant__ parameter).
@@ -132,12 +133,16 @@ gemm_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmShape gs, cons
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int z = blockIdx.z;
+    const bool split = gs.k_splits > 1;
+    const int z = split ? 0 : blockIdx.z;
     const CUtensorMap* tmA = &maps.a[z];
     const CUtensorMap* tmB = &maps.b[z];
     const int m0 = blockIdx.x * gs.m_stride;
     const int n0 = blockIdx.y * gs.n_stride;
-    const int num_k = (gs.K + kBK - 1) / kBK;
+    const int num_k_all = (gs.K + kBK - 1) / kBK;
+    const int per_split = split ? (num_k_all + gs.k_splits - 1) / gs.k_splits : num_k_all;
+    const int kc_begin = split ? blockIdx.z * per_split : 0;
+    const int kc_end = (kc_begin + per_split < num_k_all) ? kc_begin + per_split : num_k_all;
 
     ptx::pdl_launch_dependents();          // the next kernel may begin its prologue on idle SMs
     if (warp == 0 && lane == 0) {
@@ -173,7 +178,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmShape gs, cons
                                          aux_bar, n0 + 64 * j, m0 + gs.aux_row_off[i]);
             }
             int stage = 0; uint32_t phase = 0;
-            for (int kc = 0; kc < num_k; ++kc) {
+            for (int kc = kc_begin; kc < kc_end; ++kc) {
                 ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                 unsigned char* sa = smem + stage * L::kStageBytes;
                 unsigned char* sb = sa + L::kABytes;
@@ -205,7 +210,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmShape gs, cons
             constexpr uint32_t a_step = A_MN ? (kUmmaK * 128) >> 4 : (kUmmaK * 2) >> 4;
             constexpr uint32_t b_step = B_MN ? (kUmmaK * 128) >> 4 : (kUmmaK * 2) >> 4;
             int stage = 0; uint32_t phase = 0;
-            for (int kc = 0; kc < num_k; ++kc) {
+            for (int kc = kc_begin; kc < kc_end; ++kc) {
                 ptx::mbar_wait(&full_bar[stage], phase);
                 ptx::tc_fence_after();
                 const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
@@ -215,10 +220,10 @@ gemm_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmShape gs, cons
 #pragma unroll
                 for (int k = 0; k < kBK / kUmmaK; ++k) {
                     ptx::umma_bf16(tmem_base, adesc + a_step * k, bdesc + b_step * k, idesc,
-                                   (kc > 0 || k > 0) ? 1u : 0u);
+                                   (kc > kc_begin || k > 0) ? 1u : 0u);
                 }
                 ptx::umma_commit(&empty_bar[stage]);      // frees the smem slot when MMAs retire
-                if (kc == num_k - 1) ptx::umma_commit(tmem_full_bar);
+                if (kc == kc_end - 1) ptx::umma_commit(tmem_full_bar);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -429,6 +434,39 @@ struct EpiStoreF32 {
             }
         }
         out_tile_commit<BN, 4>(cx);
+    }
+    template <int BN>
+    static __device__ __forceinline__ void phase2(const EpiCtx&, const GemmShape&, const Params&) {}
+};
+
+// ---- split-K partial: C += alpha * acc with fp32 vector atomics (C zero-initialised by the caller) ----
+struct EpiAtomicAddF32 {
+    static constexpr bool kClusterReduce = false;
+    static constexpr int kScratchBytes = 16;
+    static constexpr int kNumAux = 0;
+    static constexpr int kOutElemBytes = 0;
+    struct Params { float* C; int ldc; float alpha; };
+    template <int BN>
+    static __device__ __forceinline__ void phase1(const EpiCtx& cx, const GemmShape& gs, const Params& p) {
+        const int m = cx.m0 + cx.row;
+        const int M = gs.M[0], N = gs.N[0];
+        float* crow = p.C + static_cast<size_t>(m) * p.ldc;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            float v[32];
+            ptx::tmem_ld_32x32(cx.tmem_row + c, v);
+            if (m >= M) continue;
+            const int n = cx.n0 + c;
+            if (n + 32 <= N) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    atomicAdd(reinterpret_cast<float4*>(crow + n) + j,
+                              make_float4(v[4 * j] * p.alpha, v[4 * j + 1] * p.alpha, v[4 * j + 2] * p.alpha, v[4 * j + 3] * p.alpha));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (n + j < N) atomicAdd(crow + n + j, v[j] * p.alpha);
+            }
+        }
     }
     template <int BN>
     static __device__ __forceinline__ void phase2(const EpiCtx&, const GemmShape&, const Params&) {}

@@ -404,3 +404,22 @@ def test_graphed_step_prefetch_pipeline(cv):
     for a, b in zip(got, ref):
         assert abs(a - b) <= 1e-6 * abs(b), (got, ref)
     assert m.image_embed.model.fc.weight.grad is not None
+
+
+def test_head_backward_large_m_split_k(cv):
+    """M = 128*49 rows (spatial-head shape): the weight gradient takes the split-K path
+    (contraction split over blockIdx.z, fp32 vector atomics) and the head GEMM the 2-CTA/SM config."""
+    rng = np.random.RandomState(23)
+    M, E = 128 * 49, 512
+    W, b, _ = O.synth_weights(rng, E, 2048, 8)
+    f = O.synth_trunk_features(rng, (M, 2048))
+    g = rng.standard_normal((M, E)).astype(np.float32)
+    Wr, br = t(W).requires_grad_(True), t(b).requires_grad_(True)
+    ref = O.encode_image(t(f), Wr, br, "flat", True)
+    (ref * t(g)).sum().backward()
+    Wd, bd = t(W, DEV).requires_grad_(True), t(b, DEV).requires_grad_(True)
+    got = cv.ops.head_features(t(f, DEV), Wd, bd, True)
+    (got * t(g, DEV)).sum().backward()
+    assert float((got.detach().cpu() - ref.detach()).abs().max()) <= 6e-3
+    assert_grad_close(Wd.grad.cpu().numpy(), Wr.grad.numpy(), "dW")
+    assert_grad_close(bd.grad.cpu().numpy(), br.grad.numpy(), "db")

@@ -86,6 +86,31 @@ frames = torch.randn(N * 4, E, generator=g).to(dev); cats = torch.randn(C, E, ge
 idx = torch.randint(0, C, (N,), generator=g).to(torch.int32).to(dev)
 ms, mn = timeit(lambda: m.ops.eval_nway(frames, cats, idx, 4, True, S_FIXED), 20, 3)
 rec("config5_eval_4way_100k_frames", ms, mn, N * 4, "frames", bytes_=N * 4 * E * 4, note="fp32 normalise + dot + argmax")
+# ---------------- per-kernel at scale: text encoder, embedding scatter, projection head (+ its backward)
+from multimodal_baby_b200 import _cabi
+C = _cabi.call; P = m.ops._p
+st = lambda: torch.cuda.current_stream().cuda_stream
+Bk, V, K = 32768, 2350, 2048
+ids_k, lens_k = O.synth_tokens(np.random.RandomState(7), Bk)
+ids_k = torch.from_numpy(ids_k).to(dev); sum_len = int(lens_k.sum()); lens_k = torch.from_numpy(lens_k).to(dev)
+txt16 = torch.empty((Bk, E), dtype=torch.bfloat16, device=dev); invn = torch.empty((Bk,), dtype=torch.float32, device=dev)
+ms, mn = timeit(lambda: C("cvcl_text_encoder_fwd", P(ids_k), P(lens_k), P(table_d), Bk, 25, E, V, 1, 0, 1.0, None, P(txt16), E,
+                          P(invn), None, None, None, st()), 10, 3)
+rec("K1_text_encoder_fwd_b32768", ms, mn, Bk, "pairs", bytes_=8 * Bk * 25 + sum_len * E * 4 + Bk * E * 2,
+    note="gathers hit the L2-resident 4.8 MB table; bytes = ids + gathered rows + bf16 features")
+dm = torch.randn(Bk, E, device=dev); dtab = torch.zeros(V, E, device=dev)
+ms, mn = timeit(lambda: C("cvcl_embedding_scatter_add", P(ids_k), P(dm), P(dtab), Bk, 25, E, V, 0, st()), 10, 3)
+rec("K5e_embedding_scatter_b32768", ms, mn, Bk, "pairs", bytes_=8 * Bk * 25 + 4 * Bk * E + 2 * sum_len * E * 4,
+    note="fp32 vector atomics into the 4.8 MB table (L2)")
+Mh = 1024 * 49
+xh = torch.randn(Mh, K, device=dev).to(torch.bfloat16); w16 = (torch.randn(E, K, device=dev) / 45).to(torch.bfloat16)
+bias = torch.zeros(E, device=dev); f16 = torch.empty((Mh, E), dtype=torch.bfloat16, device=dev); inv_h = torch.empty((Mh,), device=dev)
+ms, mn = timeit(lambda: C("cvcl_head_proj_norm_fwd", P(xh), K, P(w16), K, P(bias), Mh, E, K, 1, None, 0, P(f16), E, P(inv_h), st()), 10, 3)
+rec("K2_head_proj_norm_fwd_m50176", ms, mn, 1024, "pairs", flops=2 * Mh * K * E, bytes_=2 * Mh * K + 2 * E * K + 2 * Mh * E,
+    note="spatial projection head (1x1 conv as GEMM, M = 1024*49) + bias + per-location L2 norm (cluster epilogue)")
+du16 = torch.randn(Mh, E, device=dev).to(torch.bfloat16); dWh = torch.empty((E, K), device=dev)
+ms, mn = timeit(lambda: C("cvcl_head_weight_grad", P(du16), E, P(xh), K, E, K, Mh, P(dWh), K, st()), 10, 3)
+rec("K5c_head_weight_grad_m50176", ms, mn, 1024, "pairs", flops=2 * Mh * K * E, note="dW = du^T x, both operands MN-major, contraction 50176")
 if a.cpu:
     torch.set_num_threads(os.cpu_count())
     fr, ca, ix = frames.cpu(), cats.cpu(), idx.cpu().long()
