@@ -1,0 +1,91 @@
+"""-m gpu: the reference's own test strategy (tests/test_batching.py:59-106): a batched forward must
+equal the per-example ("unbatched") forward.  The reference file is stale against its current
+signatures, so the property is restated here on the drop-in modules with the same
+shapes (B=4, max_len=16, ids in [1,16), lens in [1,16)) and tolerances (atol 1e-5)."""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def random_padded_tensor(rng, batch_size, max_seq_len, lo, hi):
+    """tests/test_batching.py:45-57: random ids in [lo,hi), random lens in [1,max_seq_len), zero padded."""
+    x = rng.randint(lo, hi, size=(batch_size, max_seq_len)).astype(np.int64)
+    x_len = rng.randint(1, max_seq_len, size=batch_size).astype(np.int64)
+    for i, n in enumerate(x_len):
+        x[i, n:] = 0
+    return torch.from_numpy(x), torch.from_numpy(x_len)
+
+
+def make_text_encoder(cv, embedding_type, E=128, V=16):
+    args = argparse.Namespace(embedding_type=embedding_type, embedding_dim=E, text_encoder="embedding",
+                              dropout_i=0.0, dropout_o=0.0, crange=1)
+    vocab = {str(i): i for i in range(V)}
+    return cv.TextEncoder(vocab, 2048, args).to(DEV)
+
+
+@pytest.fixture(scope="module")
+def cv():
+    import multimodal_baby_b200 as m
+    m._cabi.load()
+    return m
+
+
+def forward_unbatched(model, x, x_len):
+    """multimodal.py:586-600 (_forward_unbatched, embedding branch) through the same module."""
+    outs = []
+    for i in range(x.shape[0]):
+        ret, _, _ = model(x[i:i + 1], x_len[i:i + 1])
+        outs.append(ret[0])
+    return torch.stack(outs)
+
+
+@pytest.mark.parametrize("embedding_type", ["flat", "spatial"])
+def test_text_encoder_batched_equals_unbatched(cv, embedding_type):
+    rng = np.random.RandomState(0)
+    model = make_text_encoder(cv, embedding_type)
+    x, x_len = random_padded_tensor(rng, 4, 16, 1, 16)
+    x, x_len = x.to(DEV), x_len.to(DEV)
+    batched, _, _ = model(x, x_len)
+    unbatched = forward_unbatched(model, x, x_len)
+    assert torch.allclose(batched, unbatched, atol=1e-5)
+    # and both equal the definition: sum_l E[x_l] / len (flat) or E[x] (spatial)
+    emb = model.embedding.weight[x]
+    ref = emb.sum(1) / x_len[:, None] if embedding_type == "flat" else emb
+    assert torch.allclose(batched, ref, atol=1e-5)
+
+
+def test_head_batched_equals_unbatched(cv):
+    """the image side of the same property (tests/test_batching.py:21-42, test_cnn): rows of a batch
+    through the projection head == each row alone (different tile occupancy, same numbers)."""
+    rng = np.random.RandomState(1)
+    W = torch.from_numpy((rng.standard_normal((128, 2048)) / 45).astype(np.float32)).to(DEV)
+    b = torch.from_numpy(rng.standard_normal(128).astype(np.float32) * 0.01).to(DEV)
+    x = torch.from_numpy(np.maximum(rng.standard_normal((4, 2048)), 0).astype(np.float32)).to(DEV)
+    batched = cv.ops.head_features(x, W, b, True)
+    single = torch.cat([cv.ops.head_features(x[i:i + 1], W, b, True) for i in range(4)])
+    assert torch.allclose(batched, single, atol=1e-5)
+
+
+def test_model_forward_batched_equals_per_pair(cv):
+    """logits[i, t] of a batched forward == the 1x1 forward of image i with text t."""
+    rng = np.random.RandomState(2)
+    E = 128
+    args = argparse.Namespace(embedding_type="flat", embedding_dim=E, normalize_features=True,
+                              fix_temperature=True, temperature=0.07, text_encoder="embedding")
+    vocab = {str(i): i for i in range(64)}
+    m = cv.MultiModalModel(cv.VisionEncoder(args, trunk="pooled"), cv.TextEncoder(vocab, 2048, args), args).to(DEV).eval()
+    x = torch.from_numpy(np.maximum(rng.standard_normal((4, 2048)), 0).astype(np.float32)).to(DEV)
+    ids, lens = random_padded_tensor(rng, 3, 16, 1, 64)
+    ids, lens = ids.to(DEV), lens.to(DEV)
+    with torch.no_grad():
+        lpi, lpt = m(x, ids, lens)
+        assert lpi.shape == (4, 3) and lpt.shape == (3, 4)
+        for i in range(4):
+            for j in range(3):
+                one, _ = m(x[i:i + 1], ids[j:j + 1], lens[j:j + 1])
+                assert abs(one.item() - lpi[i, j].item()) <= 1e-4
