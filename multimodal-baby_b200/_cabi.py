@@ -69,7 +69,15 @@ def load(path=None):
     global _lib
     if _lib is not None:
         return _lib
-    path = path or os.environ.get("CVCL_B200_LIB", LIB_PATH)
+    explicit = path or os.environ.get("CVCL_B200_LIB")
+    path = explicit or LIB_PATH
+    if not os.path.exists(path) and not explicit:
+        # in-tree build on first use (nvcc cross-compiles sm_100a anywhere); still no CPU path
+        try:
+            from . import build as _build
+            _build.build_library()
+        except Exception as exc:                                   # noqa: BLE001
+            raise CvclLibraryMissing("libcvcl_b200.so is missing and could not be built: %s" % exc)
     if not os.path.exists(path):
         raise CvclLibraryMissing(
             "libcvcl_b200.so not found at %s -- build it with `python multimodal-baby_b200/build.py` "
