@@ -194,6 +194,15 @@ int cvcl_match_infonce_fwd(const float* match, int B, float log_scale, float inv
 int cvcl_match_infonce_bwd(const float* match, int B, float log_scale, float coef, const float* lse0,
                            const float* lse1, float* dmatch, float* dscale, void* stream);
 
+/* ---- fused AdamW for the head parameters -------------------------------------
+ * replaces torch.optim.AdamW.step (multimodal_lit.py:112-128) for one fp32 tensor of n elements:
+ * p *= 1 - lr*wd; m = lerp(m, g, 1-beta1); v = beta2*v + (1-beta2)*g^2;
+ * p -= lr/(1-beta1^step) * m / (sqrt(v)/sqrt(1-beta2^step) + eps).   g is read as g*grad_scale.
+ * bf16_shadow (nullable): refreshed bf16 copy of p (the operand the head GEMM consumes). */
+int cvcl_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int step, float grad_scale, void* bf16_shadow,
+                    void* stream);
+
 /* ---- K7 n-way evaluation (fp32, bit-exact argmax contract) -----------------------------------
  * replaces the per-trial loop of eval.py:196-214 / multimodal_lit.py:466-511.
  * img [n_trials*n_way, E] fp32 embeddings (target first), txt [C,E] fp32 label embeddings,

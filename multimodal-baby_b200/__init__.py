@@ -15,6 +15,7 @@ from ._cabi import CvclError, CvclLibraryMissing                   # noqa: F401
 from .multimodal import (MultiModalModel, PooledTrunk, TextEncoder, VisionEncoder,  # noqa: F401
                          split_trunk_forward)
 from .graphed import GraphedContrastiveStep                         # noqa: F401
+from .optim import FusedAdamW                                       # noqa: F401
 from .multimodal_lit import MultiModalLitModel, WhitespaceTokenizer, load_vocab      # noqa: F401
 
 __version__ = "0.1.0"

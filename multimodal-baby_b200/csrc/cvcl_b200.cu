@@ -582,6 +582,27 @@ int cvcl_match_infonce_bwd(const float* match, int B, float log_scale, float coe
     return CVCL_OK;
 }
 
+// ------------------------------------------------------------------------------------ fused AdamW
+int cvcl_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int step, float grad_scale, void* bf16_shadow,
+                    void* stream) {
+    CVCL_REQUIRE(p && g && m && v, "adamw_step: null pointer");
+    CVCL_REQUIRE(n >= 0 && step >= 1, "adamw_step: bad n / step");
+    CVCL_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                   reinterpret_cast<uintptr_t>(v)) & 15) == 0, "adamw_step: tensors must be 16-byte aligned");
+    if (n == 0) return CVCL_OK;
+    const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
+    const float bc2_sqrt = sqrtf(1.f - powf(beta2, static_cast<float>(step)));
+    long long blocks = (n / 4 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    CVCL_CHECK_CUDA(launch_pdl(adamw_step_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, as_stream(stream),
+                               p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, grad_scale,
+                               static_cast<__nv_bfloat16*>(bf16_shadow)));
+    count_launch();
+    return CVCL_OK;
+}
+
 // ------------------------------------------------------------------------------------ K7
 int cvcl_eval_nway_fwd(const float* img, const float* txt, const int* txt_index, int n_trials, int n_way,
                        int E, int normalize, float log_scale, int* pred, float* logits, void* stream) {

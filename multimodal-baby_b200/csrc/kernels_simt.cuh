@@ -848,4 +848,53 @@ __global__ void __launch_bounds__(256) spatial_max_expand_kernel(const float* g,
     }
 }
 
+
+// --------------------------------------------------------------------------------------
+// Fused AdamW for the head parameters (the optimiser the reference configures,
+// multimodal_lit.py:112-128: torch.optim.AdamW, decoupled weight decay).  One pass over p, g, m, v
+// (28 B / parameter); optionally refreshes the bf16 shadow copy that the head GEMM consumes, so the
+// per-step fp32->bf16 cast of W disappears from a training loop.  Same update order as
+// torch.optim.AdamW (single-tensor path): decay, moments, bias-corrected step.
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adamw_step_kernel(float* p, const float* g, float* m, float* v,
+                                                         long long n, float lr, float beta1, float beta2,
+                                                         float eps, float wd, float bc1, float bc2_sqrt,
+                                                         float grad_scale, __nv_bfloat16* shadow) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
+    const float step_size = lr / bc1;
+    for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x * 4) {
+        if (i + 4 <= n) {
+            float4 P = *reinterpret_cast<float4*>(p + i);
+            const float4 G = __ldg(reinterpret_cast<const float4*>(g + i));
+            float4 M = *reinterpret_cast<float4*>(m + i), V = *reinterpret_cast<float4*>(v + i);
+            float pp[4] = {P.x, P.y, P.z, P.w}, gg[4] = {G.x, G.y, G.z, G.w};
+            float mm[4] = {M.x, M.y, M.z, M.w}, vv[4] = {V.x, V.y, V.z, V.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float gk = gg[k] * grad_scale;
+                pp[k] *= 1.f - lr * wd;
+                mm[k] = mm[k] + (gk - mm[k]) * (1.f - beta1);            // lerp, as torch does
+                vv[k] = vv[k] * beta2 + gk * gk * (1.f - beta2);
+                const float denom = sqrtf(vv[k]) / bc2_sqrt + eps;
+                pp[k] -= step_size * (mm[k] / denom);
+            }
+            *reinterpret_cast<float4*>(p + i) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+            *reinterpret_cast<float4*>(m + i) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+            *reinterpret_cast<float4*>(v + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+            if (shadow) store_bf16x4(shadow + i, make_float4(pp[0], pp[1], pp[2], pp[3]));
+        } else {
+            for (long long j = i; j < n; ++j) {
+                const float gk = g[j] * grad_scale;
+                float pj = p[j] * (1.f - lr * wd);
+                const float mj = m[j] + (gk - m[j]) * (1.f - beta1);
+                const float vj = v[j] * beta2 + gk * gk * (1.f - beta2);
+                pj -= step_size * (mj / (sqrtf(vj) / bc2_sqrt + eps));
+                p[j] = pj; m[j] = mj; v[j] = vj;
+                if (shadow) shadow[j] = __float2bfloat16_rn(pj);
+            }
+        }
+    }
+}
+
 }  // namespace cvcl

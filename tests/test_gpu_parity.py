@@ -423,3 +423,21 @@ def test_head_backward_large_m_split_k(cv):
     assert float((got.detach().cpu() - ref.detach()).abs().max()) <= 6e-3
     assert_grad_close(Wd.grad.cpu().numpy(), Wr.grad.numpy(), "dW")
     assert_grad_close(bd.grad.cpu().numpy(), br.grad.numpy(), "db")
+
+
+def test_fused_adamw_matches_torch(cv):
+    """FusedAdamW == torch.optim.AdamW (the reference's optimiser, multimodal_lit.py:112-128) over a
+    few steps on head-shaped tensors, including a length that is not a multiple of 4."""
+    gen = torch.Generator().manual_seed(9)
+    shapes = [(512, 2048), (512,), (2350, 512), (7,)]
+    ref_p = [torch.randn(s, generator=gen).to(DEV).requires_grad_(True) for s in shapes]
+    got_p = [p.detach().clone().requires_grad_(True) for p in ref_p]
+    ref_opt = torch.optim.AdamW(ref_p, lr=1e-2, weight_decay=0.1)
+    got_opt = cv.FusedAdamW(got_p, lr=1e-2, weight_decay=0.1)
+    for it in range(4):
+        for a, b in zip(ref_p, got_p):
+            g = torch.randn(a.shape, generator=gen).to(DEV)
+            a.grad = g.clone(); b.grad = g.clone()
+        ref_opt.step(); got_opt.step()
+    for a, b in zip(ref_p, got_p):
+        assert float((a - b).abs().max()) <= 2e-6 * max(1.0, float(a.abs().max()))
