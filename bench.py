@@ -228,14 +228,25 @@ def kernel_breakdown(m, dev, B, reps, flush, peaks):
     return rows
 
 
+def ncu_traffic(label):
+    """DRAM bytes per launch of that kernel from the committed `ncu --set full` capture
+    (profiles/r01_ncu_traffic.json, written by tools/ncu_traffic.py); None if not captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as fh:
+            return json.load(fh).get(label, {}).get("traffic")
+    except (OSError, ValueError):
+        return None
+
+
 def roofline_from(rows, peaks):
     top = max(rows, key=lambda r: r["ms"])
     if top["bound"] == "tensor":
         return dict(kernel=top["kernel"], bound="tensor", achieved=top["tflop_s"], peak=peaks["bf16_tflops"],
-                    unit="TFLOP/s", frac=top["tensor_frac"], traffic=None, peak_source=peaks["source"],
-                    ms=top["ms"])
+                    unit="TFLOP/s", frac=top["tensor_frac"], traffic=ncu_traffic(top["kernel"]),
+                    peak_source=peaks["source"], ms=top["ms"])
     return dict(kernel=top["kernel"], bound="hbm", achieved=top["gb_s"], peak=peaks["hbm_gbs"], unit="GB/s",
-                frac=top["hbm_frac"], traffic=None, peak_source=peaks["source"], ms=top["ms"])
+                frac=top["hbm_frac"], traffic=ncu_traffic(top["kernel"]), algorithmic_bytes=top["bytes"],
+                peak_source=peaks["source"], ms=top["ms"])
 
 
 def cpu_reference_step_fn(B):
