@@ -20,8 +20,9 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline int pad8(int x) { return (x + 7) / 8 * 8; }
 
 struct SimWs {               // carve-up of the sim workspace
-    RowStat* part[2]; int m_pad[2]; int n_tiles[2];
-    float* diag[2]; float* block_part; unsigned int* ticket; size_t bytes;
+    RowStat* part[2]; int m_pad[2]; int n_tiles[2]; int tiles_m[2];
+    float* diag[2]; float* block_part; unsigned int* ticket; unsigned int* rb_ticket; float* rb_part;
+    size_t bytes;
 };
 inline int sim_bn(int N0, int N1) { return (N0 > N1 ? N0 : N1) >= 4096 ? 256 : 128; }   // tile width of the sim kernels
 SimWs carve_sim_ws(void* ws, int M0, int N0, int M1, int N1) {
@@ -31,6 +32,11 @@ SimWs carve_sim_ws(void* ws, int M0, int N0, int M1, int N1) {
     size_t off = 0;
     unsigned char* base = static_cast<unsigned char*>(ws);
     w.ticket = reinterpret_cast<unsigned int*>(base + off); off += 256;
+    w.tiles_m[0] = ceil_div(M0, kBM); w.tiles_m[1] = ceil_div(M1, kBM);
+    w.rb_ticket = reinterpret_cast<unsigned int*>(base + off);
+    off += align_up(sizeof(unsigned int) * (1 + w.tiles_m[0] + w.tiles_m[1]), 256);
+    w.rb_part = reinterpret_cast<float*>(base + off);
+    off += align_up(sizeof(float) * 6 * (w.tiles_m[0] + w.tiles_m[1]), 256);
     for (int z = 0; z < 2; ++z) {
         w.m_pad[z] = ceil_div(M[z], kBM) * kBM;
         w.n_tiles[z] = ceil_div(N[z], bn);
@@ -255,6 +261,15 @@ int cvcl_sim_infonce_fwd(const void* img_q, const void* txt_k, const void* txt_q
         ep.diag_off[z] = diag_off; ep.part[z] = w.part[z]; ep.m_pad[z] = w.m_pad[z]; ep.diag[z] = w.diag[z];
     }
     ep.ticket = w.ticket;
+    // small problems: merge inside the similarity kernel (saves a launch on the critical path)
+    const bool fuse = sim_bn(N0, N1) == 128 && w.tiles_m[0] + w.tiles_m[1] <= 256;
+    ep.fuse_merge = fuse;
+    for (int z = 0; z < 2; ++z) { ep.n_tiles[z] = w.n_tiles[z]; ep.tiles_m[z] = w.tiles_m[z]; }
+    ep.rb_ticket = w.rb_ticket; ep.rb_part = w.rb_part;
+    ep.lse[0] = lse0; ep.lse[1] = lse1; ep.argmax[0] = argmax0; ep.argmax[1] = argmax1;
+    ep.inv_rows = inv_rows; ep.out5 = out5;
+    if (fuse)
+        CVCL_CHECK_CUDA(cudaMemsetAsync(w.rb_ticket, 0, sizeof(unsigned int) * (1 + w.tiles_m[0] + w.tiles_m[1]), as_stream(stream)));
     // two CTAs fit per SM (96 KB ring, <= 256 TMEM columns each) so one tile's softmax epilogue
     // overlaps another tile's MMAs; wide tiles (fewer per-CTA fixed costs, less smem traffic per
     // flop) once the problem is large enough to fill the machine anyway
@@ -265,7 +280,7 @@ int cvcl_sim_infonce_fwd(const void* img_q, const void* txt_k, const void* txt_q
     } else {
         rc = launch_gemm<kBN, 3, EpiSimStats, false, false>(op, gs, ep, 1, as_stream(stream));
     }
-    if (rc) return rc;
+    if (rc || fuse) return rc;
     FinalizeParams fp{};
     for (int z = 0; z < 2; ++z) {
         fp.part[z] = w.part[z]; fp.m_pad[z] = w.m_pad[z]; fp.n_tiles[z] = w.n_tiles[z];

@@ -586,7 +586,7 @@ struct EpiHeadNorm {
 struct RowStat { float m, l, a; int arg; };          // max, sum exp(x-m), sum exp(x-m)*x, argmax
 struct EpiSimStats {
     static constexpr bool kClusterReduce = false;
-    static constexpr int kScratchBytes = 16;
+    static constexpr int kScratchBytes = 256;
     static constexpr int kNumAux = 0;
     static constexpr int kOutElemBytes = 0;
     struct Params {
@@ -595,7 +595,15 @@ struct EpiSimStats {
         RowStat* part[2];           // [n_tiles][m_pad]
         int m_pad[2];
         float* diag[2];             // [M]  logit at the positive
-        unsigned int* ticket;       // zeroed here for the merge kernel that follows
+        unsigned int* ticket;       // zeroed here for the merge kernel that follows (unfused path)
+        // fused merge (small problems): the last CTA of a row block merges that block's partials,
+        // the last row block to finish adds the block sums in a fixed order -> no merge kernel
+        int fuse_merge;
+        int n_tiles[2], tiles_m[2];
+        unsigned int* rb_ticket;    // [1 + tiles_m[0] + tiles_m[1]], zero on entry, left zero on exit
+        float* rb_part;             // [(tiles_m[0] + tiles_m[1]) * 6]
+        float* lse[2]; int* argmax[2];
+        float inv_rows; float* out5;
     };
     template <int BN>
     static __device__ __forceinline__ void phase1(const EpiCtx& cx, const GemmShape& gs, const Params& p) {
@@ -603,7 +611,7 @@ struct EpiSimStats {
         const int m = cx.m0 + cx.row;
         const int dcol = m + p.diag_off[cx.z];
         constexpr float kLog2e = 1.4426950408889634f;
-        if (cx.tile_m == 0 && cx.tile_n == 0 && cx.z == 0 && cx.epi_tid == 0) *p.ticket = 0u;
+        if (!p.fuse_merge && cx.tile_m == 0 && cx.tile_n == 0 && cx.z == 0 && cx.epi_tid == 0) *p.ticket = 0u;
         // Work on the raw dot products r (logit = scale * r, scale > 0): the scale is folded into the
         // exp2 argument, so the hot loop is FMNMX + FFMA + MUFU.EX2 + FADD + FFMA per element.
         float mx = -INFINITY, l = 0.f, a = 0.f;        // mx, a in the raw domain
@@ -659,6 +667,60 @@ struct EpiSimStats {
         if (m < M) {
             RowStat rs; rs.m = mx * p.scale; rs.l = l; rs.a = a * p.scale; rs.arg = arg;
             p.part[cx.z][static_cast<size_t>(cx.tile_n) * p.m_pad[cx.z] + m] = rs;
+        }
+        if (!p.fuse_merge) return;
+        // ---- fused merge: threadFenceReduction pattern per row block, then across row blocks ----
+        float* red = reinterpret_cast<float*>(cx.scratch);               // [4][6] + flag
+        int* flag = reinterpret_cast<int*>(cx.scratch + 128);
+        const int z = cx.z;
+        const int rb = (z ? p.tiles_m[0] : 0) + cx.tile_m;
+        __threadfence();
+        ptx::named_bar_sync(1 + cx.bar_base, kEpiThreads);
+        if (cx.epi_tid == 0) *flag = (atomicAdd(p.rb_ticket + 1 + rb, 1u) == static_cast<unsigned>(p.n_tiles[z] - 1));
+        ptx::named_bar_sync(1 + cx.bar_base, kEpiThreads);
+        if (!*flag) return;
+        __threadfence();
+        float v6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (m < M) {
+            const RowStat* base = p.part[z] + m;
+            const size_t stride = p.m_pad[z];
+            float gm = -INFINITY, gl = 0.f, ga = 0.f; int garg = 0x7fffffff;
+            for (int t = 0; t < p.n_tiles[z]; ++t) {                  // strict >: the first tile wins ties
+                const float4 q = __ldcg(reinterpret_cast<const float4*>(base + static_cast<size_t>(t) * stride));
+                const float rm = q.x, rl = q.y, ra = q.z; const int rarg = __float_as_int(q.w);
+                if (rm > gm) { const float w = __expf(gm - rm); gl = gl * w + rl; ga = ga * w + ra; gm = rm; garg = rarg; }
+                else { const float w = __expf(rm - gm); gl = fmaf(rl, w, gl); ga = fmaf(ra, w, ga); }
+            }
+            const float lse = gm + logf(gl);
+            p.lse[z][m] = lse;
+            if (p.argmax[z]) p.argmax[z][m] = garg;
+            v6[z] = lse - __ldcg(p.diag[z] + m);                       // cross-entropy term
+            v6[2 + z] = lse - ga / gl;                                 // entropy
+            v6[4 + z] = (garg == m + p.diag_off[z]) ? 1.f : 0.f;       // retrieval hit
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v6[i] += __shfl_xor_sync(0xffffffffu, v6[i], o);
+            if ((cx.row & 31) == 0) red[(cx.row >> 5) * 6 + i] = v6[i];
+        }
+        ptx::named_bar_sync(1 + cx.bar_base, kEpiThreads);
+        if (cx.epi_tid == 0) {
+            for (int i = 0; i < 6; ++i) p.rb_part[rb * 6 + i] = red[i] + red[6 + i] + red[12 + i] + red[18 + i];
+            __threadfence();
+            const int nrb = p.tiles_m[0] + p.tiles_m[1];
+            if (atomicAdd(p.rb_ticket, 1u) == static_cast<unsigned>(nrb - 1)) {
+                __threadfence();
+                float s6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                for (int b = 0; b < nrb; ++b)                          // fixed order: deterministic
+                    for (int i = 0; i < 6; ++i) s6[i] += __ldcg(p.rb_part + b * 6 + i);
+                p.out5[0] = (s6[0] + s6[1]) * 0.5f * p.inv_rows;
+                p.out5[1] = s6[4] * p.inv_rows;
+                p.out5[2] = s6[5] * p.inv_rows;
+                p.out5[3] = s6[2] * p.inv_rows;
+                p.out5[4] = s6[3] * p.inv_rows;
+                for (int b = 0; b <= nrb; ++b) p.rb_ticket[b] = 0u;    // leave the tickets zeroed
+            }
         }
     }
     template <int BN>
