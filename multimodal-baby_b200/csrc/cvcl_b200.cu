@@ -239,11 +239,11 @@ size_t cvcl_sim_workspace_bytes(int M0, int N0, int M1, int N1) {
     return carve_sim_ws(nullptr, M0, N0, M1, N1).bytes;
 }
 
-int cvcl_sim_infonce_fwd(const void* img_q, const void* txt_k, const void* txt_q, const void* img_k,
-                         int ld, int M0, int N0, int M1, int N1, int E, float log_scale,
-                         int diag_off, float inv_rows, void* workspace,
-                         float* lse0, float* lse1, int* argmax0, int* argmax1, float* out5,
-                         void* stream) {
+static int sim_infonce_fwd_impl(const void* img_q, const void* txt_k, const void* txt_q, const void* img_k,
+                               int ld, int M0, int N0, int M1, int N1, int E, float log_scale,
+                               int diag_off, float inv_rows, void* workspace,
+                               float* lse0, float* lse1, int* argmax0, int* argmax1, float* out5,
+                               void* stream, bool tickets_zeroed) {
     CVCL_REQUIRE(img_q && txt_k && txt_q && img_k && workspace && lse0 && lse1 && out5,
                  "sim_infonce_fwd: null pointer");
     CVCL_REQUIRE(M0 > 0 && N0 > 0 && M1 > 0 && N1 > 0 && E > 0, "sim_infonce_fwd: bad shape");
@@ -268,7 +268,7 @@ int cvcl_sim_infonce_fwd(const void* img_q, const void* txt_k, const void* txt_q
     ep.rb_ticket = w.rb_ticket; ep.rb_part = w.rb_part;
     ep.lse[0] = lse0; ep.lse[1] = lse1; ep.argmax[0] = argmax0; ep.argmax[1] = argmax1;
     ep.inv_rows = inv_rows; ep.out5 = out5;
-    if (fuse)
+    if (fuse && !tickets_zeroed)
         CVCL_CHECK_CUDA(cudaMemsetAsync(w.rb_ticket, 0, sizeof(unsigned int) * (1 + w.tiles_m[0] + w.tiles_m[1]), as_stream(stream)));
     // two CTAs fit per SM (96 KB ring, <= 256 TMEM columns each) so one tile's softmax epilogue
     // overlaps another tile's MMAs; wide tiles (fewer per-CTA fixed costs, less smem traffic per
@@ -292,6 +292,15 @@ int cvcl_sim_infonce_fwd(const void* img_q, const void* txt_k, const void* txt_q
     CVCL_CHECK_CUDA(launch_pdl(infonce_finalize_kernel, dim3(ceil_div(M0 + M1, 256)), dim3(256), 0, as_stream(stream), fp));
     count_launch();
     return CVCL_OK;
+}
+
+int cvcl_sim_infonce_fwd(const void* img_q, const void* txt_k, const void* txt_q, const void* img_k,
+                         int ld, int M0, int N0, int M1, int N1, int E, float log_scale,
+                         int diag_off, float inv_rows, void* workspace,
+                         float* lse0, float* lse1, int* argmax0, int* argmax1, float* out5,
+                         void* stream) {
+    return sim_infonce_fwd_impl(img_q, txt_k, txt_q, img_k, ld, M0, N0, M1, N1, E, log_scale, diag_off, inv_rows,
+                                workspace, lse0, lse1, argmax0, argmax1, out5, stream, false);
 }
 
 int cvcl_sim_logits_fwd(const void* img, const void* txt, int ld, int Ni, int Nt, int E, float log_scale,
@@ -474,6 +483,10 @@ int cvcl_flat_contrastive_step(const void* x, int x_is_bf16, const int64_t* ids,
     CVCL_CHECK_CUDA(cudaStreamWaitEvent(ss.s, ss.fork[0], 0));
     if ((rc = cvcl_text_encoder_fwd(ids, lens, table, B, L, E, V, normalize, 0, 1.f, txt_feat_f32, f.txt16, E,
                                     f.invn_t, nullptr, nullptr, status, side))) return rc;
+    {   // row-block tickets of the fused merge: zeroed off the critical path
+        SimWs sw = carve_sim_ws(f.sim, B, B, B, B);
+        CVCL_CHECK_CUDA(cudaMemsetAsync(sw.rb_ticket, 0, sizeof(unsigned int) * (1 + sw.tiles_m[0] + sw.tiles_m[1]), ss.s));
+    }
     if (need_grads) {   // gradient accumulators are zeroed off the critical path
         if (dbias == dscale + 4 && dtable == dbias + E) {
             CVCL_CHECK_CUDA(cudaMemsetAsync(dscale, 0, sizeof(float) * (4 + E + static_cast<size_t>(V) * E), ss.s));
@@ -494,8 +507,9 @@ int cvcl_flat_contrastive_step(const void* x, int x_is_bf16, const int64_t* ids,
                                       f.invn_i, stream))) return rc;
     CVCL_CHECK_CUDA(cudaStreamWaitEvent(st, ss.join[0], 0));
     // ---- K3 + K4
-    if ((rc = cvcl_sim_infonce_fwd(f.img16, f.txt16, f.txt16, f.img16, E, B, B, B, B, E, log_scale, 0,
-                                   1.f / static_cast<float>(B), f.sim, f.lse0, f.lse1, nullptr, nullptr, out5, stream))) return rc;
+    if ((rc = sim_infonce_fwd_impl(f.img16, f.txt16, f.txt16, f.img16, E, B, B, B, B, E, log_scale, 0,
+                                   1.f / static_cast<float>(B), f.sim, f.lse0, f.lse1, nullptr, nullptr, out5, stream,
+                                   true))) return rc;
     if (!need_grads) return CVCL_OK;
     // ---- K5: Gs (one orientation) -> dI (K-major Gs, main) || dT (the same Gs read MN-major, side)
     const float coef = 0.5f / static_cast<float>(B);
