@@ -427,20 +427,23 @@ def main():
     #     fwd+bwd, D2H of the loss all inside the replay; wall clock per call incl. the stream sync
     e2e_dt, e2e_api = eager_dt, "MultiModalModel.calculate_contrastive_loss + backward (eager)"
     try:
-        gstep = m.GraphedContrastiveStep(model, x_host, ids_host, lens_host, prefetch=True)
+        gstep = m.GraphedContrastiveStep(model, x_host, ids_host, lens_host, prefetch=True, lagged_loss=True)
         gstep.prime()
         for _ in range(6):
             gstep()
+        gstep.flush()
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            loss_host = gstep()
+            loss_host = gstep()            # loss of the previous replay (read back every step)
+        loss_host = gstep.flush()          # ... and of the last one, inside the timed region
         barrier()
         g_dt = (time.perf_counter() - t0) / e2e_steps
         if g_dt < e2e_dt:
-            e2e_dt, e2e_api = g_dt, ("GraphedContrastiveStep(model, prefetch=True)() = calculate_contrastive_loss + backward as "
-                                     "one CUDA graph; every call copies one full batch H2D (overlapped with the kernels of "
-                                     "the previously copied batch) and reads the loss back")
+            e2e_dt, e2e_api = g_dt, ("GraphedContrastiveStep(model, prefetch=True, lagged_loss=True)() = "
+                                     "calculate_contrastive_loss + backward as one CUDA graph; every call copies one full "
+                                     "batch H2D (overlapped with the kernels of the previously copied batch) and reads back "
+                                     "the loss of the previous replay (one replay in flight, flushed inside the timed region)")
     except Exception as exc:
         if rank == 0:
             print("graphed e2e step unavailable: %s" % exc, file=sys.stderr)

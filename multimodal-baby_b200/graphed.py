@@ -14,6 +14,11 @@ copied while it was computing, and copies the batch now staged in the pinned buf
 (H2D overlaps the kernels on a second graph branch).  Every call still moves one full batch host ->
 device; the returned loss belongs to the batch staged one call earlier (call `prime()` once after
 staging the first batch).
+
+`lagged_loss=True` (needs prefetch) additionally keeps one replay in flight: a call enqueues replay k and
+waits only for replay k-1, whose loss it returns (each graph writes its own pinned stats buffer).  The
+host never idles behind the GPU; every step's loss is still read back, one call later.  `flush()` waits
+for the replay in flight and returns its loss.
 """
 from __future__ import annotations
 
@@ -23,7 +28,7 @@ from . import ops
 
 
 class GraphedContrastiveStep:
-    def __init__(self, model, x_host, ids_host, lens_host, warmup=3, prefetch=False):
+    def __init__(self, model, x_host, ids_host, lens_host, warmup=3, prefetch=False, lagged_loss=False):
         if model.embedding_type != "flat":
             raise NotImplementedError("GraphedContrastiveStep covers the flat-embedding train step")
         for t in (x_host, ids_host, lens_host):
@@ -41,7 +46,13 @@ class GraphedContrastiveStep:
         self.bufs = [(torch.empty_like(x_host, device=dev), torch.empty_like(ids_host, device=dev),
                       torch.empty_like(lens_host, device=dev)) for _ in range(nbuf)]
         self.x, self.ids, self.lens = self.bufs[0]
-        self.stats_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        if lagged_loss and not prefetch:
+            raise ValueError("lagged_loss=True needs prefetch=True (two alternating graphs)")
+        self.lagged = bool(lagged_loss)
+        self.stats_bufs = [torch.zeros(8, dtype=torch.float32).pin_memory() for _ in range(nbuf)]
+        self.stats_host = self.stats_bufs[0]
+        self.events = [torch.cuda.Event() for _ in range(nbuf)]
+        self.pending = None
         self.copy_stream = torch.cuda.Stream(device=dev) if self.prefetch else None
         self.calls = 0
         s = model.logit_neg_log_temperature
@@ -57,7 +68,7 @@ class GraphedContrastiveStep:
             buf[2].copy_(self.lens_host, non_blocking=True)
 
         @torch.no_grad()
-        def body(cur, nxt):
+        def body(cur, nxt, stats_host):
             main = torch.cuda.current_stream(dev)
             if nxt is None:
                 h2d(cur)                                   # copy, then compute (serial)
@@ -72,27 +83,27 @@ class GraphedContrastiveStep:
                 stats, _, _ = ops.flat_step_sharded(x_d, ids_d, lens_d, w, b, table, ls, norm, True, False,
                                                     self.group)
                 out5, flat = stats[:8], stats[8:]
-            self.stats_host.copy_(out5, non_blocking=True)
+            stats_host.copy_(out5, non_blocking=True)
             if nxt is not None:
                 main.wait_stream(self.copy_stream)
             return flat
 
-        pairs = [(self.bufs[0], None)] if not self.prefetch else [(self.bufs[0], self.bufs[1]),
-                                                                  (self.bufs[1], self.bufs[0])]
+        pairs = [(self.bufs[0], None, self.stats_bufs[0])] if not self.prefetch else [
+            (self.bufs[0], self.bufs[1], self.stats_bufs[0]), (self.bufs[1], self.bufs[0], self.stats_bufs[1])]
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                for cur, nxt in pairs:
-                    body(cur, nxt)
+                for cur, nxt, sh in pairs:
+                    body(cur, nxt, sh)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         # one flat gradient buffer shared by all graphs: the parameters' .grad are static views of it
         self.graphs, flats = [], []
-        for cur, nxt in pairs:
+        for cur, nxt, sh in pairs:
             gph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gph):
-                flats.append(body(cur, nxt))
+                flats.append(body(cur, nxt, sh))
             self.graphs.append(gph)
         self.graph = self.graphs[0]
         self.flats = flats
@@ -122,10 +133,31 @@ class GraphedContrastiveStep:
     def __call__(self):
         which = self.calls % len(self.graphs)
         self.graphs[which].replay()
-        torch.cuda.current_stream(self.dev).synchronize()
-        if len(self.graphs) > 1:
-            self._bind_grads(which, *self._dims)           # .grad views of the buffer just written
         self.calls += 1
+        if not self.lagged:
+            torch.cuda.current_stream(self.dev).synchronize()
+            if len(self.graphs) > 1:
+                self._bind_grads(which, *self._dims)       # .grad views of the buffer just written
+            self.stats_host = self.stats_bufs[which]
+            return float(self.stats_host[0])
+        # one replay stays in flight: wait for the previous one only and return ITS loss
+        self.events[which].record(torch.cuda.current_stream(self.dev))
+        prev, self.pending = self.pending, which
+        if prev is None:
+            return float("nan")                            # nothing finished yet (first call)
+        self.events[prev].synchronize()
+        self._bind_grads(prev, *self._dims)
+        self.stats_host = self.stats_bufs[prev]
+        return float(self.stats_host[0])
+
+    def flush(self):
+        """lagged mode: wait for the replay still in flight, bind its gradients, return its loss."""
+        if self.pending is None:
+            return float(self.stats_host[0])
+        prev, self.pending = self.pending, None
+        self.events[prev].synchronize()
+        self._bind_grads(prev, *self._dims)
+        self.stats_host = self.stats_bufs[prev]
         return float(self.stats_host[0])
 
     def stats(self):

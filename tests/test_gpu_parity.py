@@ -441,3 +441,32 @@ def test_fused_adamw_matches_torch(cv):
         ref_opt.step(); got_opt.step()
     for a, b in zip(ref_p, got_p):
         assert float((a - b).abs().max()) <= 2e-6 * max(1.0, float(a.abs().max()))
+
+
+def test_graphed_step_lagged_loss(cv):
+    """lagged_loss=True: call k returns the loss of replay k-1; flush() returns the last one."""
+    import argparse
+    E = 512
+    args = argparse.Namespace(embedding_type="flat", embedding_dim=E, normalize_features=True,
+                              fix_temperature=True, temperature=0.07, text_encoder="embedding")
+    vocab = {str(i): i for i in range(2350)}
+    m = cv.MultiModalModel(cv.VisionEncoder(args, trunk="pooled"), cv.TextEncoder(vocab, 2048, args), args)
+    inps = [case_inputs(500 + k, 128, E, "flat") for k in range(3)]
+    with torch.no_grad():
+        m.image_embed.model.fc.weight.copy_(t(inps[0]["W"])); m.image_embed.model.fc.bias.copy_(t(inps[0]["b"]))
+        m.text_embed.embedding.weight.copy_(t(inps[0]["table"]))
+    m.to(DEV).train()
+    m.materialize_logits = m.materialize_text_outputs = m.materialize_features = False
+    ref = [m.calculate_contrastive_loss(t(i["f"], DEV), t(i["ids"], DEV), t(i["lens"], DEV))[0].item() for i in inps]
+    xh = t(inps[0]["f"]).pin_memory(); ih = t(inps[0]["ids"]).pin_memory(); lh = t(inps[0]["lens"]).pin_memory()
+    step = cv.GraphedContrastiveStep(m, xh, ih, lh, prefetch=True, lagged_loss=True)
+    step.prime()                                        # batch 0 on the device
+    got = []
+    for k in (1, 2, 2):                                 # replay j computes batch j (copied during replay j-1)
+        xh.copy_(t(inps[k]["f"])); ih.copy_(t(inps[k]["ids"])); lh.copy_(t(inps[k]["lens"]))
+        got.append(step())
+        torch.cuda.synchronize()                        # the staged batch must not change while it is copied
+    got.append(step.flush())
+    assert got[0] != got[0]                             # NaN: nothing had finished at the first call
+    for a, b in zip(got[1:], ref):
+        assert abs(a - b) <= 1e-6 * abs(b), (got, ref)
