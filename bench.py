@@ -483,6 +483,11 @@ def main():
         cpu = {"value": B / cdt, "unit": "pairs/s", "cores": cores, "kind": "port", "ms_per_step": cdt * 1e3,
                "sample": "%d steps of the same B=%d flat train step (oracle port: the reference's ATen fp32 op "
                          "sequence + autograd on CPU, %d torch threads)" % (n_cpu, B, cores)}
+    if world > 1:
+        from multimodal_baby_b200 import sharding as _sh
+        used = [v is not None for v in _sh.PeerExchange._cache.values()]
+        config["exchange"] = ("symmetric-memory barrier + P2P gather kernel over NVLink (features, LSEs); "
+                              "NCCL all-reduce (gradients)") if used and all(used) else "NCCL all-gather / all-reduce"
     line = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",

@@ -194,6 +194,14 @@ int cvcl_match_infonce_fwd(const float* match, int B, float log_scale, float inv
 int cvcl_match_infonce_bwd(const float* match, int B, float log_scale, float coef, const float* lse0,
                            const float* lse1, float* dmatch, float* dscale, void* stream);
 
+/* ---- all-gather over NVLink peer memory (the exchange step of the sharded loss) ------
+ * peer_ptrs: HOST array of `world` device pointers, entry r = rank r's block (symmetric memory, peer
+ * mapped).  Copies `bytes_per_rank` bytes from every rank except skip_rank (-1: none) to
+ * dst + r * dst_stride_bytes with 16-byte loads from the peer pointers.  The caller orders it after a
+ * cross-rank barrier (torch symmetric-memory barrier). */
+int cvcl_p2p_gather(const void* const* peer_ptrs, int world, int skip_rank, long long bytes_per_rank, void* dst,
+                    long long dst_stride_bytes, void* stream);
+
 /* ---- fused AdamW for the head parameters -------------------------------------
  * replaces torch.optim.AdamW.step (multimodal_lit.py:112-128) for one fp32 tensor of n elements:
  * p *= 1 - lr*wd; m = lerp(m, g, 1-beta1); v = beta2*v + (1-beta2)*g^2;

@@ -611,6 +611,27 @@ int cvcl_match_infonce_bwd(const float* match, int B, float log_scale, float coe
     return CVCL_OK;
 }
 
+// ------------------------------------------------------------------------------------ peer-memory gather
+int cvcl_p2p_gather(const void* const* peer_ptrs, int world, int skip_rank, long long bytes_per_rank, void* dst,
+                    long long dst_stride_bytes, void* stream) {
+    CVCL_REQUIRE(peer_ptrs && dst, "p2p_gather: null pointer");
+    CVCL_REQUIRE(world >= 1 && world <= 8, "p2p_gather: world size %d not in [1,8]", world);
+    CVCL_REQUIRE(bytes_per_rank % 16 == 0 && dst_stride_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+                 "p2p_gather: 16-byte granularity required");
+    if (bytes_per_rank == 0) return CVCL_OK;
+    PeerPtrs pp{};
+    for (int r = 0; r < world; ++r) {
+        CVCL_REQUIRE(peer_ptrs[r] && (reinterpret_cast<uintptr_t>(peer_ptrs[r]) & 15) == 0, "p2p_gather: bad peer pointer %d", r);
+        pp.p[r] = peer_ptrs[r];
+    }
+    long long blocks = (bytes_per_rank / 16 + 255) / 256;
+    if (blocks > 64) blocks = 64;
+    CVCL_CHECK_CUDA(launch_pdl(p2p_gather_kernel, dim3(static_cast<unsigned>(blocks), world), dim3(256), 0, as_stream(stream),
+                               pp, static_cast<unsigned char*>(dst), bytes_per_rank, dst_stride_bytes, skip_rank));
+    count_launch();
+    return CVCL_OK;
+}
+
 // ------------------------------------------------------------------------------------ fused AdamW
 int cvcl_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
                     float beta2, float eps, float weight_decay, int step, float grad_scale, void* bf16_shadow,

@@ -897,4 +897,32 @@ __global__ void __launch_bounds__(256) adamw_step_kernel(float* p, const float* 
     }
 }
 
+
+// --------------------------------------------------------------------------------------
+// All-gather over NVLink peer memory: every rank exposes its block in symmetric memory; after a
+// cross-rank barrier each rank pulls the other ranks' blocks with 16-byte loads from the PEER
+// pointers (NVSwitch gives every peer full bandwidth) into its local gathered buffer.  Replaces an
+// NCCL all-gather (17 us measured for 1 MB per rank at 2 GPUs) by a 6 us barrier + this copy.
+// blockIdx.y = source rank; grid-stride over the block's 16-byte words.
+// --------------------------------------------------------------------------------------
+struct PeerPtrs { const void* p[8]; };
+
+__global__ void __launch_bounds__(256) p2p_gather_kernel(const PeerPtrs peers, unsigned char* dst,
+                                                         long long bytes_per_rank, long long dst_stride,
+                                                         int skip_rank) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
+    const int r = blockIdx.y;
+    if (r == skip_rank) return;
+    const uint4* src = reinterpret_cast<const uint4*>(peers.p[r]);
+    uint4* out = reinterpret_cast<uint4*>(dst + static_cast<long long>(r) * dst_stride);
+    const long long n16 = bytes_per_rank >> 4;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n16;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        uint4 v;
+        asm volatile("ld.global.relaxed.sys.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + i) : "memory");
+        out[i] = v;
+    }
+}
+
 }  // namespace cvcl

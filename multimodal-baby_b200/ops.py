@@ -673,7 +673,9 @@ def flat_step_sharded(x, ids, lens, w, bias, table, log_scale, normalize, need_g
     main = torch.cuda.current_stream(dev)
     side = _side_stream(dev)
     n_g = 4 + E + V * E + E * K
-    feats = torch.empty((B, 2 * E), **bf)                 # [img | txt] per pair: one gather moves both
+    px = sharding.PeerExchange.get(group, B, E, dev) if (world > 1 and B % 4 == 0) else None
+    # [img | txt] per pair: one exchange moves both; in peer-mapped symmetric memory when available
+    feats = px.feats if px is not None else torch.empty((B, 2 * E), **bf)
     img_l, txt_l = feats[:, :E], feats[:, E:]
     invn_i = torch.empty((B,), **f32); invn_t = torch.empty((B,), **f32)
     img_f = torch.empty((B, E), **f32) if want_features else None
@@ -691,14 +693,21 @@ def flat_step_sharded(x, ids, lens, w, bias, table, log_scale, normalize, need_g
     C("cvcl_head_proj_norm_fwd", _p(x16), K, _p(w16), K, _p(bias), B, E, K, int(normalize), _p(img_f), E,
       _p(img_l), 2 * E, _p(invn_i), st)
     main.wait_stream(side)
-    feats_all = sharding.all_gather_rows(feats, group, world)          # [Bg, 2E]
+    if px is not None:       # barrier + 16-byte loads from the peers' blocks over NVLink
+        feats_all = torch.empty((Bg, 2 * E), **bf)
+        px.gather_feats(feats_all, st)
+    else:
+        feats_all = sharding.all_gather_rows(feats, group, world)      # [Bg, 2E] (NCCL)
     img_a, txt_a = feats_all[:, :E], feats_all[:, E:]
     ws = torch.empty((lib.cvcl_sim_workspace_bytes(B, Bg, B, Bg),), dtype=torch.uint8, device=dev)
-    lse = torch.empty((2, B), **f32)
+    lse = px.lse if px is not None else torch.empty((2, B), **f32)
     C("cvcl_sim_infonce_fwd", _p(img_l), _p(txt_a), _p(txt_l), _p(img_a), 2 * E, B, Bg, B, Bg, E,
       float(log_scale), rank * B, 1.0 / Bg, _p(ws), _p(lse[0]), _p(lse[1]), None, None, _p(stats), st)
     if need_grads:
-        if world > 1:
+        if px is not None:
+            lse_all = torch.empty((2, Bg), **f32)
+            px.gather_lse(lse_all, st)
+        elif world > 1:
             lse_all = sharding.all_gather_rows(lse, group, world).view(world, 2, B).permute(1, 0, 2).contiguous()
         else:
             lse_all = lse
@@ -726,6 +735,8 @@ def flat_step_sharded(x, ids, lens, w, bias, table, log_scale, normalize, need_g
     if world > 1:
         import torch.distributed as dist
         dist.all_reduce(stats, group=group)
+        if px is not None and not need_grads:
+            px.barrier()         # no gradient all-reduce to fence the next step's overwrite of the blocks
     return stats, img_f, txt_f
 
 

@@ -15,6 +15,8 @@ orchestration (offsets, gathers, reductions) is covered without a GPU.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -78,3 +80,68 @@ def allreduce_gradients(params, group=None):
         n = g.numel()
         g.copy_(flat[off:off + n].view_as(g))
         off += n
+
+
+# ----------------------------------------------------------------------------------------------
+# exchange over NVLink peer memory (symmetric memory) instead of NCCL all-gathers
+# ----------------------------------------------------------------------------------------------
+class PeerExchange:
+    """Per-(group, b, E) symmetric-memory buffers for the two exchange steps of the sharded loss:
+    the bf16 [img|txt] feature block and the two fp32 LSE vectors of every rank live in peer-mapped
+    memory; an exchange = symmetric-memory barrier (about 6 us) + `cvcl_p2p_gather` (16-byte loads from
+    the peer pointers over NVLink) instead of an NCCL all-gather (about 17 us each at 2 GPUs).
+    Created once (the rendezvous is itself a collective) and reused every step: a rank can only start
+    overwriting its block for step s+1 after the gradient all-reduce of step s, which no rank leaves
+    before every rank has finished reading step s."""
+
+    _cache = {}
+
+    def __init__(self, group, b, E, dev):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        self.world, self.rank = group_info(group)
+        self.b, self.E = b, E
+        self.feats = symm.empty((b, 2 * E), dtype=torch.bfloat16, device=dev)
+        self.h_feats = symm.rendezvous(self.feats, group)
+        self.lse = symm.empty((2, b), dtype=torch.float32, device=dev)
+        self.h_lse = symm.rendezvous(self.lse, group)
+        arr = ctypes.c_void_p * self.world
+        self.p_feats = arr(*[int(p) for p in self.h_feats.buffer_ptrs])
+        self.p_lse0 = arr(*[int(p) for p in self.h_lse.buffer_ptrs])
+        self.p_lse1 = arr(*[int(p) + 4 * b for p in self.h_lse.buffer_ptrs])
+
+    @classmethod
+    def get(cls, group, b, E, dev):
+        import os
+        # opt-in (CVCL_B200_SYMM=1): measured identical to the NCCL all-gathers at 2 GPUs (174.1 vs
+        # 173.9 us per step) -- the step is bounded by the 9.6 MB gradient all-reduce, not by the
+        # gathers -- so the default stays on the path validated at 2/4/8 GPUs.
+        if os.environ.get("CVCL_B200_SYMM") != "1":
+            return None
+        key = (id(group), b, E, dev.index)
+        if key not in cls._cache:
+            try:
+                cls._cache[key] = cls(group, b, E, dev)
+            except Exception as exc:             # noqa: BLE001  (no symmetric memory: NCCL all-gathers)
+                if os.environ.get("CVCL_B200_DEBUG"):
+                    print("PeerExchange unavailable, using NCCL all-gathers: %r" % (exc,), flush=True)
+                cls._cache[key] = None
+        return cls._cache[key]
+
+    def gather_feats(self, dst, stream):
+        """dst [world*b, 2E] bf16 <- every rank's feature block (after a cross-rank barrier)."""
+        from . import _cabi
+        self.h_feats.barrier()
+        nbytes = self.b * 2 * self.E * 2
+        _cabi.call("cvcl_p2p_gather", self.p_feats, self.world, -1, nbytes, dst.data_ptr(), nbytes, stream)
+
+    def gather_lse(self, dst, stream):
+        """dst [2, world*b] fp32 <- every rank's lse0 / lse1."""
+        from . import _cabi
+        self.h_lse.barrier()
+        nb = self.b * 4
+        _cabi.call("cvcl_p2p_gather", self.p_lse0, self.world, -1, nb, dst[0].data_ptr(), nb, stream)
+        _cabi.call("cvcl_p2p_gather", self.p_lse1, self.world, -1, nb, dst[1].data_ptr(), nb, stream)
+
+    def barrier(self):
+        self.h_feats.barrier()

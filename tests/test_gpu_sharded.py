@@ -27,3 +27,16 @@ def test_sharded_equals_single_gpu(world):
            os.path.join(ROOT, "tools", "sharded_check.py"), "2048"]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert res.returncode == 0 and "SHARDED_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+
+
+def test_sharded_peer_memory_exchange_equals_single_gpu():
+    """same check with the exchange steps over symmetric memory (barrier + P2P gather kernel over
+    NVLink) instead of NCCL all-gathers (CVCL_B200_SYMM=1)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, CVCL_B200_SYMM="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(ROOT, "tools", "sharded_check.py"), "2048"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert res.returncode == 0 and "SHARDED_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
