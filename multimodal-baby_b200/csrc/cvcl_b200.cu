@@ -4,6 +4,7 @@
 #include "gemm_launch.cuh"
 #include "kernels_simt.cuh"
 #include <cmath>
+#include <cstdlib>
 
 using namespace cvcl;
 
@@ -13,6 +14,13 @@ constexpr int kBN = 128;
 constexpr int kStages = 4;
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+// the fused step zeroes the split-K scratch on its side stream; it tells the head entry point so
+inline bool& head_scratch_zeroed() { static thread_local bool v = false; return v; }
+inline bool head_splitk_disabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("CVCL_B200_HEAD_SPLITK"); v = (e && e[0] == '0') ? 1 : 0; }
+    return v == 1;
+}
 inline int warps_grid(long long n_warps, int block = 256) {
     return static_cast<int>((n_warps * 32 + block - 1) / block);
 }
@@ -223,6 +231,32 @@ int cvcl_head_proj_norm_fwd(const void* x, int ldx, const void* w, int ldw, cons
     op.A[0] = mat(x, M, K, ldx); op.B[0] = mat(w, E, K, ldw);
     op.out[0] = out_bf16 ? mat(out_bf16, M, E, ld_bf16) : mat(x, M, K, ldx);
     GemmShape gs{}; gs.M[0] = gs.M[1] = M; gs.N[0] = gs.N[1] = E; gs.K = K; gs.m_stride = kBM; gs.n_stride = kBN;
+    {
+        // small M (e.g. 512 pairs): 16 tiles cannot fill 148 SMs and each would stream all of K
+        // serially.  Split the contraction 8-ways over blockIdx.z (fp32 vector atomics into the fp32
+        // output buffer), then one warp-per-row pass adds the bias and normalises.
+        const int tiles = ceil_div(M, kBM) * ceil_div(E, kBN);
+        const int chunks = ceil_div(K, kBK);
+        if (out_f32 && tiles * 4 <= sm_count() && chunks >= 16 && ld_f32 % 4 == 0 && E % 4 == 0 &&
+            (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0 && !head_splitk_disabled()) {
+            int splits = sm_count() / tiles;
+            if (splits > chunks / 4) splits = chunks / 4;
+            while (splits > 1 && ceil_div(chunks, splits) * (splits - 1) >= chunks) --splits;
+            if (splits > 1) {
+                if (!head_scratch_zeroed())
+                    CVCL_CHECK_CUDA(cudaMemsetAsync(out_f32, 0, sizeof(float) * static_cast<size_t>(M) * ld_f32, as_stream(stream)));
+                gs.k_splits = splits;
+                EpiAtomicAddF32::Params ea{}; ea.C = out_f32; ea.ldc = ld_f32; ea.alpha = 1.f;
+                int rc = launch_gemm<kBN, 4, EpiAtomicAddF32, false, false>(op, gs, ea, 1, as_stream(stream));
+                if (rc) return rc;
+                CVCL_CHECK_CUDA(launch_pdl(bias_norm_rows_kernel, dim3(warps_grid(M, 128)), dim3(128), 0, as_stream(stream),
+                                           out_f32, ld_f32, bias, M, E, normalize, static_cast<__nv_bfloat16*>(out_bf16),
+                                           ld_bf16, inv_norm));
+                count_launch();
+                return CVCL_OK;
+            }
+        }
+    }
     EpiHeadNorm::Params ep{};
     ep.bias = bias; ep.normalize = normalize; ep.out_f32 = out_f32; ep.ld_f32 = ld_f32;
     ep.store_bf16 = out_bf16 != nullptr; ep.inv_norm = inv_norm;
@@ -430,7 +464,7 @@ SideStream& side_stream() { static thread_local SideStream ss; return ss; }
 
 struct FlatWs {
     __nv_bfloat16 *w16, *x16, *img16, *txt16, *G0, *du16;
-    float *invn_i, *invn_t, *lse0, *lse1, *dm;
+    float *invn_i, *invn_t, *lse0, *lse1, *dm, *u32;
     void* sim; int ldB; size_t bytes;
 };
 FlatWs carve_flat_ws(void* ws, int B, int L, int E, int K, int V) {
@@ -451,6 +485,7 @@ FlatWs carve_flat_ws(void* ws, int B, int L, int E, int K, int V) {
     f.lse0 = static_cast<float*>(take(4ull * B));
     f.lse1 = static_cast<float*>(take(4ull * B));
     f.dm = static_cast<float*>(take(4ull * B * E));
+    f.u32 = static_cast<float*>(take(4ull * B * E));
     f.sim = base + off;
     off += align_up(cvcl_sim_workspace_bytes(B, B, B, B), 256);
     f.bytes = off;
@@ -478,16 +513,18 @@ int cvcl_flat_contrastive_step(const void* x, int x_is_bf16, const int64_t* ids,
     int rc;
     if ((rc = ss.init())) return rc;
     void* side = ss.s;
-    // ---- forward: text encoder (side) || cast W -> head GEMM (main)
+    // ---- forward: [memsets -> text encoder] (side) || [cast W -> head GEMM] (main)
     CVCL_CHECK_CUDA(cudaEventRecord(ss.fork[0], st));
     CVCL_CHECK_CUDA(cudaStreamWaitEvent(ss.s, ss.fork[0], 0));
-    if ((rc = cvcl_text_encoder_fwd(ids, lens, table, B, L, E, V, normalize, 0, 1.f, txt_feat_f32, f.txt16, E,
-                                    f.invn_t, nullptr, nullptr, status, side))) return rc;
-    {   // row-block tickets of the fused merge: zeroed off the critical path
+    // all accumulators are zeroed off the critical path, first thing on the side stream
+    float* img_f32 = img_feat_f32 ? img_feat_f32 : f.u32;      // also the split-K accumulator of the head
+    CVCL_CHECK_CUDA(cudaMemsetAsync(img_f32, 0, sizeof(float) * static_cast<size_t>(B) * E, ss.s));
+    {   // row-block tickets of the fused merge
         SimWs sw = carve_sim_ws(f.sim, B, B, B, B);
         CVCL_CHECK_CUDA(cudaMemsetAsync(sw.rb_ticket, 0, sizeof(unsigned int) * (1 + sw.tiles_m[0] + sw.tiles_m[1]), ss.s));
     }
-    if (need_grads) {   // gradient accumulators are zeroed off the critical path
+    CVCL_CHECK_CUDA(cudaEventRecord(ss.fork[2], ss.s));          // head GEMM (split-K atomics) waits for this only
+    if (need_grads) {
         if (dbias == dscale + 4 && dtable == dbias + E) {
             CVCL_CHECK_CUDA(cudaMemsetAsync(dscale, 0, sizeof(float) * (4 + E + static_cast<size_t>(V) * E), ss.s));
         } else {
@@ -496,6 +533,8 @@ int cvcl_flat_contrastive_step(const void* x, int x_is_bf16, const int64_t* ids,
             CVCL_CHECK_CUDA(cudaMemsetAsync(dtable, 0, sizeof(float) * static_cast<size_t>(V) * E, ss.s));
         }
     }
+    if ((rc = cvcl_text_encoder_fwd(ids, lens, table, B, L, E, V, normalize, 0, 1.f, txt_feat_f32, f.txt16, E,
+                                    f.invn_t, nullptr, nullptr, status, side))) return rc;
     CVCL_CHECK_CUDA(cudaEventRecord(ss.join[0], ss.s));
     if ((rc = cvcl_cast_transpose(w, 0, f.w16, nullptr, 1, E, K, K, K, 0, 0, 0, 0, stream))) return rc;
     const void* x16 = x;
@@ -503,8 +542,11 @@ int cvcl_flat_contrastive_step(const void* x, int x_is_bf16, const int64_t* ids,
         if ((rc = cvcl_cast_transpose(x, x_is_bf16, f.x16, nullptr, 1, B, K, K, K, 0, 0, 0, 0, stream))) return rc;
         x16 = f.x16;
     }
-    if ((rc = cvcl_head_proj_norm_fwd(x16, K, f.w16, K, bias, B, E, K, normalize, img_feat_f32, E, f.img16, E,
-                                      f.invn_i, stream))) return rc;
+    CVCL_CHECK_CUDA(cudaStreamWaitEvent(st, ss.fork[2], 0));
+    head_scratch_zeroed() = true;
+    rc = cvcl_head_proj_norm_fwd(x16, K, f.w16, K, bias, B, E, K, normalize, img_f32, E, f.img16, E, f.invn_i, stream);
+    head_scratch_zeroed() = false;
+    if (rc) return rc;
     CVCL_CHECK_CUDA(cudaStreamWaitEvent(st, ss.join[0], 0));
     // ---- K3 + K4
     if ((rc = sim_infonce_fwd_impl(f.img16, f.txt16, f.txt16, f.img16, E, B, B, B, B, E, log_scale, 0,

@@ -925,4 +925,48 @@ __global__ void __launch_bounds__(256) p2p_gather_kernel(const PeerPtrs peers, u
     }
 }
 
+
+// --------------------------------------------------------------------------------------
+// bias + L2 normalise rows of a fp32 matrix in place (second half of the split-K projection head
+// used when M is small: u = x.W^T is accumulated by 8 K-splits with fp32 atomics, then this warp-per-
+// row pass adds the bias, normalises (F.normalize, eps 1e-12) and emits fp32 / bf16 / inv_norm).
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) bias_norm_rows_kernel(float* u, int ld_u, const float* bias, int M, int E,
+                                                             int normalize, __nv_bfloat16* out_bf16, int ld_bf16,
+                                                             float* inv_norm) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= M) return;
+    const int nch = (E + 127) >> 7;
+    float4 r[kMaxVec];
+    float ssq = 0.f;
+    float* row = u + static_cast<size_t>(warp) * ld_u;
+#pragma unroll
+    for (int c = 0; c < kMaxVec; ++c) {
+        r[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int e = (c * 32 + lane) * 4;
+        if (c < nch && e < E) {
+            r[c] = *reinterpret_cast<const float4*>(row + e);
+            if (bias) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(bias + e));
+                r[c].x += b.x; r[c].y += b.y; r[c].z += b.z; r[c].w += b.w;
+            }
+        }
+        ssq += r[c].x * r[c].x + r[c].y * r[c].y + r[c].z * r[c].z + r[c].w * r[c].w;
+    }
+    ssq = warp_sum(ssq);
+    const float denom = normalize ? fmaxf(sqrtf(ssq), 1e-12f) : 1.f;
+    if (lane == 0 && inv_norm) inv_norm[warp] = 1.f / denom;
+#pragma unroll
+    for (int c = 0; c < kMaxVec; ++c) {
+        const int e = (c * 32 + lane) * 4;
+        if (c < nch && e < E) {
+            const float4 t = make_float4(r[c].x / denom, r[c].y / denom, r[c].z / denom, r[c].w / denom);
+            *reinterpret_cast<float4*>(row + e) = t;
+            if (out_bf16) store_bf16x4(out_bf16 + static_cast<size_t>(warp) * ld_bf16 + e, t);
+        }
+    }
+}
+
 }  // namespace cvcl

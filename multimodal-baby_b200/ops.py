@@ -690,7 +690,8 @@ def flat_step_sharded(x, ids, lens, w, bias, table, log_scale, normalize, need_g
     w16 = torch.empty((E, K), **bf)
     C("cvcl_cast_transpose", _p(w), 0, _p(w16), None, 1, E, K, K, K, 0, 0, 0, 0, st)
     x16, _ = to_bf16_pair(x, False)
-    C("cvcl_head_proj_norm_fwd", _p(x16), K, _p(w16), K, _p(bias), B, E, K, int(normalize), _p(img_f), E,
+    img_u = img_f if img_f is not None else torch.empty((B, E), **f32)   # fp32 out = split-K accumulator
+    C("cvcl_head_proj_norm_fwd", _p(x16), K, _p(w16), K, _p(bias), B, E, K, int(normalize), _p(img_u), E,
       _p(img_l), 2 * E, _p(invn_i), st)
     main.wait_stream(side)
     if px is not None:       # barrier + 16-byte loads from the peers' blocks over NVLink
