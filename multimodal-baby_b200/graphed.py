@@ -112,9 +112,15 @@ class GraphedContrastiveStep:
         self._dims = (E, K, V, table)
 
     def _bind_grads(self, which, E, K, V, table):
-        ds, db, dtable, dW = ops.split_flat_grads(self.flats[which], E, K, V)
-        w_param, b_param = self._head_params()
-        w_param.grad = dW.view_as(w_param)
+        views = self._grad_views.get(which) if hasattr(self, "_grad_views") else None
+        if views is None:
+            if not hasattr(self, "_grad_views"):
+                self._grad_views = {}
+            ds, db, dtable, dW = ops.split_flat_grads(self.flats[which], E, K, V)
+            w_param, b_param = self._head_params()
+            views = self._grad_views[which] = (w_param, dW.view_as(w_param), b_param, db, table, dtable)
+        w_param, dW, b_param, db, table, dtable = views
+        w_param.grad = dW
         if b_param is not None:
             b_param.grad = db
         table.grad = dtable
