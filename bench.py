@@ -169,7 +169,7 @@ def kernel_breakdown(m, dev, B, reps, flush, peaks):
     ldB = (B + 7) // 8 * 8
     w16 = torch.empty((E, K), **bf)
     img16 = torch.empty((B, E), **bf); txt16 = torch.empty((B, E), **bf)
-    G0 = torch.empty((B, ldB), **bf); du16 = torch.empty((B, E), **bf)
+    G0 = torch.empty((B, ldB), **bf); du16 = torch.empty((B, E), **bf); u32 = torch.empty((B, E), **f32)
     invn_i = torch.empty((B,), **f32); invn_t = torch.empty((B,), **f32)
     lse0 = torch.empty((B,), **f32); lse1 = torch.empty((B,), **f32); dm = torch.empty((B, E), **f32)
     dW = torch.empty((E, K), **f32); db = torch.zeros((E,), **f32); dtab = torch.zeros((V, E), **f32)
@@ -187,9 +187,9 @@ def kernel_breakdown(m, dev, B, reps, flush, peaks):
         ("K1_text_encoder_fwd", lambda: C("cvcl_text_encoder_fwd", p(ids_d), p(lens_d), p(tab_d), B, L, E, V, 1, 0, 1.0,
                                           None, p(txt16), E, p(invn_t), None, None, None, st()),
          dict(bytes=8 * B * L + sum_len * E * 4 + B * E * 2)),
-        ("K2_head_proj_norm_fwd", lambda: C("cvcl_head_proj_norm_fwd", p(x16), K, p(w16), K, p(b_d), B, E, K, 1, None, 0,
+        ("K2_head_proj_norm_fwd", lambda: C("cvcl_head_proj_norm_fwd", p(x16), K, p(w16), K, p(b_d), B, E, K, 1, p(u32), E,
                                             p(img16), E, p(invn_i), st()),
-         dict(bytes=2 * B * K + 2 * E * K + 2 * B * E, flops=2 * B * K * E)),
+         dict(bytes=2 * B * K + 2 * E * K + 2 * B * E, flops=2 * B * K * E)),   # split-K GEMM + bias/normalise pass (+ memset)
         ("K3K4_sim_infonce_fwd", lambda: C("cvcl_sim_infonce_fwd", p(img16), p(txt16), p(txt16), p(img16), E, B, B, B, B, E,
                                            S_FIXED, 0, 1.0 / B, p(ws), p(lse0), p(lse1), None, None, p(out5), st()),
          dict(bytes=4 * B * E * 2, flops=4 * B * B * E)),
