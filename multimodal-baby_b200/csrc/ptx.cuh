@@ -76,9 +76,15 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
                  ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                  : "memory");
 }
+// wait only until the bulk store has finished READING shared memory (the staging tile may then be
+// reused / the CTA may exit); global visibility is guaranteed by kernel completion.
 __device__ __forceinline__ void tma_store_commit_and_wait() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#ifdef CVCL_TMA_STORE_FULL_WAIT
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#else
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
 }
 
 // ---------------------------------------------------------------- tcgen05 / TMEM
