@@ -486,8 +486,9 @@ def main():
     if world > 1:
         from multimodal_baby_b200 import sharding as _sh
         used = [v is not None for v in _sh.PeerExchange._cache.values()]
-        config["exchange"] = ("symmetric-memory barrier + P2P gather kernel over NVLink (features, LSEs); "
-                              "NCCL all-reduce (gradients)") if used and all(used) else "NCCL all-gather / all-reduce"
+        config["exchange"] = ("single kernels over NVLink peer memory with in-kernel cross-rank barriers: feature "
+                              "all-gather, LSE all-gather, two-shot in-place gradient all-reduce (csrc/peer_collectives.cuh)"
+                              ) if used and all(used) else "NCCL all-gather / all-reduce"
     line = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",

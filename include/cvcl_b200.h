@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CVCL_ABI_VERSION 2
+#define CVCL_ABI_VERSION 3
 #define CVCL_OK 0
 #define CVCL_ERR_INVALID (-1)
 #define CVCL_ERR_UNSUPPORTED (-2)
@@ -201,6 +201,32 @@ int cvcl_match_infonce_bwd(const float* match, int B, float log_scale, float coe
  * cross-rank barrier (torch symmetric-memory barrier). */
 int cvcl_p2p_gather(const void* const* peer_ptrs, int world, int skip_rank, long long bytes_per_rank, void* dst,
                     long long dst_stride_bytes, void* stream);
+
+/* ---- collectives over NVLink peer memory with in-kernel cross-rank barriers ---------
+ * The exchange steps and the gradient sum of the sharded step as single kernels instead of NCCL
+ * calls.  Every rank passes the same HOST tables of `world` device pointers: peer_data[r] = rank r's
+ * block and peer_flags[r] = rank r's flag area for THIS call site ("channel"), both in peer-mapped
+ * symmetric memory.  A channel's flag area holds cvcl_peer_flag_words() uint32 words, zeroed once
+ * before first use (followed by any cross-rank barrier); `epoch` is a LOCAL uint32 array of
+ * cvcl_peer_max_blocks() words, zeroed once; `status` (local int, nullable) becomes non-zero if a
+ * barrier did not complete within timeout_ms (0 = 10 s), after which the kernel traps.  All ranks
+ * must issue the same sequence of calls per channel with the same sizes.  Graph capturable.
+ *   allgather    : barrier, then dst[s*dst_seg_stride + r*seg_bytes ..] <- segment s (at
+ *                  s*src_seg_stride) of rank r's block, for all r (including the caller's own) and s.
+ *                  The blocks may be overwritten again only after a later barrier / all-reduce.
+ *   allreduce_f32: in-place sum over ranks of n floats (n % 4 == 0, world in {1,2,4,8}); slice r is
+ *                  summed by rank r in rank order and written to every rank: bit-identical results on
+ *                  all ranks, independent of timing.
+ *   barrier      : barrier only. */
+size_t cvcl_peer_flag_words(void);
+int cvcl_peer_max_blocks(void);
+int cvcl_peer_allgather(void* const* peer_data, void* const* peer_flags, unsigned int* epoch, int* status, int world,
+                        int rank, long long seg_bytes, int nseg, long long src_seg_stride_bytes, void* dst,
+                        long long dst_seg_stride_bytes, unsigned int timeout_ms, void* stream);
+int cvcl_peer_allreduce_f32(void* const* peer_data, void* const* peer_flags, unsigned int* epoch, int* status, int world,
+                            int rank, long long n, unsigned int timeout_ms, void* stream);
+int cvcl_peer_barrier(void* const* peer_flags, unsigned int* epoch, int* status, int world, int rank,
+                      unsigned int timeout_ms, void* stream);
 
 /* ---- fused AdamW for the head parameters -------------------------------------
  * replaces torch.optim.AdamW.step (multimodal_lit.py:112-128) for one fp32 tensor of n elements:

@@ -9,7 +9,7 @@ from ctypes import c_float, c_int, c_int64, c_size_t, c_void_p, c_char_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libcvcl_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class CvclLibraryMissing(RuntimeError):
@@ -59,6 +59,12 @@ PROTOTYPES = {
     "cvcl_match_infonce_fwd": (c_int, [_P, _I, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
     "cvcl_match_infonce_bwd": (c_int, [_P, _I, _F, _F, _P, _P, _P, _P, _P]),
     "cvcl_p2p_gather": (c_int, [_P, _I, _I, ctypes.c_longlong, _P, ctypes.c_longlong, _P]),
+    "cvcl_peer_flag_words": (c_size_t, []),
+    "cvcl_peer_max_blocks": (c_int, []),
+    "cvcl_peer_allgather": (c_int, [_P, _P, _P, _P, _I, _I, ctypes.c_longlong, _I, ctypes.c_longlong, _P,
+                                    ctypes.c_longlong, ctypes.c_uint, _P]),
+    "cvcl_peer_allreduce_f32": (c_int, [_P, _P, _P, _P, _I, _I, ctypes.c_longlong, ctypes.c_uint, _P]),
+    "cvcl_peer_barrier": (c_int, [_P, _P, _P, _I, _I, ctypes.c_uint, _P]),
     "cvcl_adamw_step": (c_int, [_P, _P, _P, _P, ctypes.c_longlong, _F, _F, _F, _F, _F, _I, _F, _P, _P]),
     "cvcl_eval_nway_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P]),
 }

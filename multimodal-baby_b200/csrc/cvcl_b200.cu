@@ -3,6 +3,7 @@
 #include "../../include/cvcl_b200.h"
 #include "gemm_launch.cuh"
 #include "kernels_simt.cuh"
+#include "peer_collectives.cuh"
 #include <cmath>
 #include <cstdlib>
 
@@ -670,6 +671,84 @@ int cvcl_p2p_gather(const void* const* peer_ptrs, int world, int skip_rank, long
     if (blocks > 64) blocks = 64;
     CVCL_CHECK_CUDA(launch_pdl(p2p_gather_kernel, dim3(static_cast<unsigned>(blocks), world), dim3(256), 0, as_stream(stream),
                                pp, static_cast<unsigned char*>(dst), bytes_per_rank, dst_stride_bytes, skip_rank));
+    count_launch();
+    return CVCL_OK;
+}
+
+// ------------------------------------------------------------------------------------ peer collectives
+namespace {
+int fill_peer_table(PeerTable* t, void* const* peer_data, void* const* peer_flags, unsigned int* epoch, int* status,
+                    int world, int rank, unsigned int timeout_ms, const char* who) {
+    CVCL_REQUIRE(world >= 1 && world <= kPeerMaxWorld, "%s: world size %d not in [1,%d]", who, world, kPeerMaxWorld);
+    CVCL_REQUIRE(rank >= 0 && rank < world, "%s: rank %d outside [0,%d)", who, rank, world);
+    CVCL_REQUIRE(peer_flags && epoch, "%s: null flag / epoch pointer", who);
+    for (int r = 0; r < world; ++r) {
+        CVCL_REQUIRE(peer_flags[r] && (reinterpret_cast<uintptr_t>(peer_flags[r]) & 3) == 0, "%s: bad flag pointer %d", who, r);
+        t->flags[r] = static_cast<uint32_t*>(peer_flags[r]);
+        if (peer_data) {
+            CVCL_REQUIRE(peer_data[r] && (reinterpret_cast<uintptr_t>(peer_data[r]) & 15) == 0, "%s: bad peer pointer %d", who, r);
+            t->data[r] = peer_data[r];
+        }
+    }
+    t->epoch = epoch; t->status = status; t->timeout_ms = timeout_ms ? timeout_ms : 10000u;
+    return CVCL_OK;
+}
+}  // namespace
+
+size_t cvcl_peer_flag_words(void) { return kPeerFlagWords; }
+int cvcl_peer_max_blocks(void) { return kPeerMaxBlocks; }
+
+int cvcl_peer_allgather(void* const* peer_data, void* const* peer_flags, unsigned int* epoch, int* status, int world,
+                        int rank, long long seg_bytes, int nseg, long long src_seg_stride_bytes, void* dst,
+                        long long dst_seg_stride_bytes, unsigned int timeout_ms, void* stream) {
+    CVCL_REQUIRE(peer_data && dst, "peer_allgather: null pointer");
+    CVCL_REQUIRE(seg_bytes > 0 && nseg >= 1, "peer_allgather: empty exchange");
+    CVCL_REQUIRE(seg_bytes % 16 == 0 && src_seg_stride_bytes % 16 == 0 && dst_seg_stride_bytes % 16 == 0 &&
+                 (reinterpret_cast<uintptr_t>(dst) & 15) == 0, "peer_allgather: 16-byte granularity required");
+    PeerTable t{};
+    int rc = fill_peer_table(&t, peer_data, peer_flags, epoch, status, world, rank, timeout_ms, "peer_allgather");
+    if (rc != CVCL_OK) return rc;
+    const long long total16 = seg_bytes / 16 * nseg * world;
+    long long blocks = (total16 + 4LL * kPeerThreads - 1) / (4LL * kPeerThreads);     // same on every rank
+    blocks = blocks < 1 ? 1 : (blocks > kPeerMaxBlocks ? kPeerMaxBlocks : blocks);
+    peer_allgather_kernel<<<static_cast<unsigned>(blocks), kPeerThreads, 0, as_stream(stream)>>>(
+        t, world, rank, seg_bytes / 16, nseg, src_seg_stride_bytes / 16, static_cast<uint4*>(dst), dst_seg_stride_bytes / 16);
+    CVCL_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return CVCL_OK;
+}
+
+int cvcl_peer_allreduce_f32(void* const* peer_data, void* const* peer_flags, unsigned int* epoch, int* status, int world,
+                            int rank, long long n, unsigned int timeout_ms, void* stream) {
+    CVCL_REQUIRE(peer_data, "peer_allreduce_f32: null pointer");
+    CVCL_REQUIRE(n > 0 && n % 4 == 0, "peer_allreduce_f32: n=%lld must be a positive multiple of 4", n);
+    if (world != 1 && world != 2 && world != 4 && world != 8)
+        return fail(CVCL_ERR_UNSUPPORTED, "peer_allreduce_f32: world size %d (supported: 1, 2, 4, 8)", world);
+    if (world == 1) return CVCL_OK;
+    PeerTable t{};
+    int rc = fill_peer_table(&t, peer_data, peer_flags, epoch, status, world, rank, timeout_ms, "peer_allreduce_f32");
+    if (rc != CVCL_OK) return rc;
+    const long long n4 = n / 4, per = (n4 + world - 1) / world;
+    long long blocks = (per + 2LL * kPeerThreads - 1) / (2LL * kPeerThreads);           // same on every rank
+    blocks = blocks < 1 ? 1 : (blocks > kPeerMaxBlocks ? kPeerMaxBlocks : blocks);
+    const dim3 grid(static_cast<unsigned>(blocks));
+    cudaStream_t st = as_stream(stream);
+    if (world == 2) peer_allreduce_f32_kernel<2><<<grid, kPeerThreads, 0, st>>>(t, rank, n4);
+    else if (world == 4) peer_allreduce_f32_kernel<4><<<grid, kPeerThreads, 0, st>>>(t, rank, n4);
+    else peer_allreduce_f32_kernel<8><<<grid, kPeerThreads, 0, st>>>(t, rank, n4);
+    CVCL_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return CVCL_OK;
+}
+
+int cvcl_peer_barrier(void* const* peer_flags, unsigned int* epoch, int* status, int world, int rank,
+                      unsigned int timeout_ms, void* stream) {
+    PeerTable t{};
+    int rc = fill_peer_table(&t, nullptr, peer_flags, epoch, status, world, rank, timeout_ms, "peer_barrier");
+    if (rc != CVCL_OK) return rc;
+    if (world == 1) return CVCL_OK;
+    peer_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(t, world, rank);
+    CVCL_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return CVCL_OK;
 }

@@ -412,8 +412,46 @@ __global__ void __launch_bounds__(256) eval_nway_kernel(const float* img, const 
         float tss = 0.f;
 #pragma unroll
         for (int c = 0; c < 4; ++c) tss += t[c].x * t[c].x + t[c].y * t[c].y + t[c].z * t[c].z + t[c].w * t[c].w;
+        tss = warp_sum(tss);
+        if (normalize && logits == nullptr) {
+            // Screen: raw sums of squares and raw dots, one division per candidate (cos = <x,t>/(|x||t|)).
+            // It differs from the reference arithmetic below (element-wise x/|x| and t/|t| before the
+            // products) by a few 1e-6 in the cosine at most, so it can only change the winner when the
+            // two best cosines agree to 1e-4; only those trials (and NaNs) take the exact path.
+            const float dt = fmaxf(sqrtf(tss), 1e-12f);
+            float ss[kWays], dot[kWays];
+#pragma unroll
+            for (int w = 0; w < kWays; ++w) {
+                ss[w] = 0.f; dot[w] = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    ss[w] = fmaf(x[w][c].x, x[w][c].x, ss[w]); ss[w] = fmaf(x[w][c].y, x[w][c].y, ss[w]);
+                    ss[w] = fmaf(x[w][c].z, x[w][c].z, ss[w]); ss[w] = fmaf(x[w][c].w, x[w][c].w, ss[w]);
+                    dot[w] = fmaf(x[w][c].x, t[c].x, dot[w]); dot[w] = fmaf(x[w][c].y, t[c].y, dot[w]);
+                    dot[w] = fmaf(x[w][c].z, t[c].z, dot[w]); dot[w] = fmaf(x[w][c].w, t[c].w, dot[w]);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int w = 0; w < kWays; ++w) {
+                    ss[w] += __shfl_xor_sync(0xffffffffu, ss[w], o);
+                    dot[w] += __shfl_xor_sync(0xffffffffu, dot[w], o);
+                }
+            }
+            float b1 = -INFINITY, b2 = -INFINITY; int a1 = 0;
+#pragma unroll
+            for (int w = 0; w < kWays; ++w) {
+                const float v = dot[w] / (fmaxf(sqrtf(ss[w]), 1e-12f) * dt);
+                if (v > b1) { b2 = b1; b1 = v; a1 = w; } else if (v > b2) { b2 = v; }
+            }
+            if (b1 - b2 > 1e-4f) {            // false for NaN / inf: those go through the exact path
+                if (lane == 0) pred[warp] = a1;
+                return;
+            }
+        }
         if (normalize) {
-            const float d = fmaxf(sqrtf(warp_sum(tss)), 1e-12f);
+            const float d = fmaxf(sqrtf(tss), 1e-12f);
 #pragma unroll
             for (int c = 0; c < 4; ++c) { t[c].x /= d; t[c].y /= d; t[c].z /= d; t[c].w /= d; }
         }

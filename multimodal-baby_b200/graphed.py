@@ -68,7 +68,7 @@ class GraphedContrastiveStep:
             buf[2].copy_(self.lens_host, non_blocking=True)
 
         @torch.no_grad()
-        def body(cur, nxt, stats_host):
+        def body(cur, nxt, stats_host, slot=0):
             main = torch.cuda.current_stream(dev)
             if nxt is None:
                 h2d(cur)                                   # copy, then compute (serial)
@@ -81,7 +81,7 @@ class GraphedContrastiveStep:
                 out5, _, _, flat = ops.flat_contrastive_step(x_d, ids_d, lens_d, w, b, table, ls, norm, True, False)
             else:
                 stats, _, _ = ops.flat_step_sharded(x_d, ids_d, lens_d, w, b, table, ls, norm, True, False,
-                                                    self.group)
+                                                    self.group, stats_slot=slot)
                 out5, flat = stats[:8], stats[8:]
             stats_host.copy_(out5, non_blocking=True)
             if nxt is not None:
@@ -94,16 +94,16 @@ class GraphedContrastiveStep:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                for cur, nxt, sh in pairs:
-                    body(cur, nxt, sh)
+                for k, (cur, nxt, sh) in enumerate(pairs):
+                    body(cur, nxt, sh, k)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         # one flat gradient buffer shared by all graphs: the parameters' .grad are static views of it
         self.graphs, flats = [], []
-        for cur, nxt, sh in pairs:
+        for k, (cur, nxt, sh) in enumerate(pairs):
             gph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gph):
-                flats.append(body(cur, nxt, sh))
+                flats.append(body(cur, nxt, sh, k))
             self.graphs.append(gph)
         self.graph = self.graphs[0]
         self.flats = flats

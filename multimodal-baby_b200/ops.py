@@ -648,11 +648,17 @@ def flat_contrastive_loss(x, ids, lens, w, bias, table, s, normalize=True, want_
                                       bool(want_features))
 
 
-def flat_step_sharded(x, ids, lens, w, bias, table, log_scale, normalize, need_grads, want_features, group):
+def flat_step_sharded(x, ids, lens, w, bias, table, log_scale, normalize, need_grads, want_features, group,
+                      stats_slot=0, phase_limit=None):
     """The flat train step with the batch sharded by pairs over `group`: local encoders,
     ONE all-gather of the bf16 [img|txt] features, row-block + column-block InfoNCE, one all-gather of
     the LSEs, local backward, ONE all-reduce of [out5 | ds | db | dtable | dW].
-    -> (stats_flat, img_feat | None, txt_feat | None); stats_flat = [out5(8) | split_flat_grads layout]."""
+    -> (stats_flat, img_feat | None, txt_feat | None); stats_flat = [out5(8) | split_flat_grads layout].
+    With the peer-memory exchange (sharding.PeerExchange) the three collectives are single kernels over
+    NVLink peer memory and stats_flat is the persistent symmetric block `stats_slot`: valid until the
+    next call with the same slot.  phase_limit (measurement hook, tools/sharded_phases.py): stop after
+    phase k of {1 local encoders, 2 feature exchange, 3 similarity + InfoNCE, 4 LSE exchange, 5 Gs,
+    6 local backward}; every rank must pass the same value."""
     from . import sharding
     _need_cuda(x, ids, lens, w, bias, table)
     world, rank = sharding.group_info(group)
@@ -673,14 +679,18 @@ def flat_step_sharded(x, ids, lens, w, bias, table, log_scale, normalize, need_g
     main = torch.cuda.current_stream(dev)
     side = _side_stream(dev)
     n_g = 4 + E + V * E + E * K
-    px = sharding.PeerExchange.get(group, B, E, dev) if (world > 1 and B % 4 == 0) else None
-    # [img | txt] per pair: one exchange moves both; in peer-mapped symmetric memory when available
+    n_stats = 8 + (n_g if need_grads else 0)
+    # the three collectives run over peer-mapped symmetric memory when available (sharding.PeerExchange):
+    # the arena is sized for the training step and shared with the forward-only call
+    px = sharding.PeerExchange.get(group, B, E, 8 + n_g, dev) if world > 1 else None
+    # [img | txt] per pair: one exchange moves both
     feats = px.feats if px is not None else torch.empty((B, 2 * E), **bf)
     img_l, txt_l = feats[:, :E], feats[:, E:]
     invn_i = torch.empty((B,), **f32); invn_t = torch.empty((B,), **f32)
     img_f = torch.empty((B, E), **f32) if want_features else None
     txt_f = torch.empty((B, E), **f32) if want_features else None
-    stats = torch.empty((8 + (n_g if need_grads else 0),), **f32)
+    # with the peer exchange `stats` is the persistent symmetric block: valid until the next call
+    stats = px.stats[stats_slot][:n_stats] if px is not None else torch.empty((n_stats,), **f32)
     # ---- forward: text encoder + accumulator zeroing (side) || cast W -> head GEMM (main)
     side.wait_stream(main)
     with torch.cuda.stream(side):
@@ -694,16 +704,22 @@ def flat_step_sharded(x, ids, lens, w, bias, table, log_scale, normalize, need_g
     C("cvcl_head_proj_norm_fwd", _p(x16), K, _p(w16), K, _p(bias), B, E, K, int(normalize), _p(img_u), E,
       _p(img_l), 2 * E, _p(invn_i), st)
     main.wait_stream(side)
-    if px is not None:       # barrier + 16-byte loads from the peers' blocks over NVLink
+    if phase_limit == 1:
+        return stats, img_f, txt_f
+    if px is not None:       # one kernel: cross-rank barrier + 16-byte loads from the peers' blocks (NVLink)
         feats_all = torch.empty((Bg, 2 * E), **bf)
         px.gather_feats(feats_all, st)
     else:
         feats_all = sharding.all_gather_rows(feats, group, world)      # [Bg, 2E] (NCCL)
     img_a, txt_a = feats_all[:, :E], feats_all[:, E:]
+    if phase_limit == 2:
+        return stats, img_f, txt_f
     ws = torch.empty((lib.cvcl_sim_workspace_bytes(B, Bg, B, Bg),), dtype=torch.uint8, device=dev)
     lse = px.lse if px is not None else torch.empty((2, B), **f32)
     C("cvcl_sim_infonce_fwd", _p(img_l), _p(txt_a), _p(txt_l), _p(img_a), 2 * E, B, Bg, B, Bg, E,
       float(log_scale), rank * B, 1.0 / Bg, _p(ws), _p(lse[0]), _p(lse[1]), None, None, _p(stats), st)
+    if phase_limit == 3:
+        return stats, img_f, txt_f
     if need_grads:
         if px is not None:
             lse_all = torch.empty((2, Bg), **f32)
@@ -713,6 +729,8 @@ def flat_step_sharded(x, ids, lens, w, bias, table, log_scale, normalize, need_g
         else:
             lse_all = lse
         lse0_all, lse1_all = lse_all[0].reshape(-1), lse_all[1].reshape(-1)
+        if phase_limit == 4:
+            return stats, img_f, txt_f
         ds, db, dtable, dW = split_flat_grads(stats[8:], E, K, V)
         ldg = _pad8(Bg)
         G0 = torch.empty((B, ldg), **bf); G1 = torch.empty((B, ldg), **bf)
@@ -720,6 +738,8 @@ def flat_step_sharded(x, ids, lens, w, bias, table, log_scale, normalize, need_g
         C("cvcl_sim_infonce_bwd_g", _p(img_l), _p(txt_a), _p(txt_l), _p(img_a), 2 * E, B, Bg, B, Bg, E,
           float(log_scale), rank * B, coef, _p(lse[0]), _p(lse1_all), _p(lse[1]), _p(lse0_all),
           _p(G0), ldg, _p(G1), ldg, _p(ds), st)
+        if phase_limit == 5:
+            return stats, img_f, txt_f
         dcoef = -2.0 * math.exp(log_scale) * coef
         du16 = torch.empty((B, E), **bf); dm = torch.empty((B, E), **f32)
         # ---- backward: dT -> embedding scatter (side) || dI -> dW (main)
@@ -733,11 +753,13 @@ def flat_step_sharded(x, ids, lens, w, bias, table, log_scale, normalize, need_g
           int(normalize), None, _p(txt_a), 2 * E, Bg, rank * B, dcoef, None, 0, _p(du16), E, _p(db), st)
         C("cvcl_head_weight_grad", _p(du16), E, _p(x16), K, E, K, B, _p(dW), K, st)
         main.wait_stream(side)        # every side-stream use is ordered before anything that follows
-    if world > 1:
+    if phase_limit == 6:
+        return stats, img_f, txt_f
+    if px is not None:       # one kernel: barrier, two-shot in-place sum over peer memory, barrier
+        px.allreduce_stats(stats_slot, n_stats, st)
+    elif world > 1:
         import torch.distributed as dist
         dist.all_reduce(stats, group=group)
-        if px is not None and not need_grads:
-            px.barrier()         # no gradient all-reduce to fence the next step's overwrite of the blocks
     return stats, img_f, txt_f
 
 
@@ -760,6 +782,8 @@ class _FlatContrastiveStepSharded(torch.autograd.Function):
             raise RuntimeError("the sharded flat step does not produce d/dx; use train_path='ops'")
         stats, img_f, txt_f = flat_step_sharded(x, ids, lens, w, bias, table, _scalar(s), normalize, need,
                                                 want_features, group)
+        if stats._base is not None:       # persistent symmetric block (peer exchange): the caller owns a copy
+            stats = stats.clone()
         ctx.need = need
         ctx.s_is_tensor = torch.is_tensor(s)
         ctx.dims = (table.shape[1], x.shape[1], table.shape[0])

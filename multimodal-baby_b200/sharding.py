@@ -83,65 +83,112 @@ def allreduce_gradients(params, group=None):
 
 
 # ----------------------------------------------------------------------------------------------
-# exchange over NVLink peer memory (symmetric memory) instead of NCCL all-gathers
+# exchange + gradient sum over NVLink peer memory (symmetric memory) instead of NCCL collectives
 # ----------------------------------------------------------------------------------------------
+def _align(n, a=256):
+    return (n + a - 1) // a * a
+
+
 class PeerExchange:
-    """Per-(group, b, E) symmetric-memory buffers for the two exchange steps of the sharded loss:
-    the bf16 [img|txt] feature block and the two fp32 LSE vectors of every rank live in peer-mapped
-    memory; an exchange = symmetric-memory barrier (about 6 us) + `cvcl_p2p_gather` (16-byte loads from
-    the peer pointers over NVLink) instead of an NCCL all-gather (about 17 us each at 2 GPUs).
-    Created once (the rendezvous is itself a collective) and reused every step: a rank can only start
-    overwriting its block for step s+1 after the gradient all-reduce of step s, which no rank leaves
-    before every rank has finished reading step s."""
+    """Per-(group, b, E, n_stats) symmetric-memory arena for the three collectives of the sharded step:
+
+        [ feats (b, 2E) bf16 | lse (2, b) f32 | stats (n_stats) f32 x N_SLOTS | flags ]
+
+    is allocated once in peer-mapped memory (one rendezvous); each collective is ONE kernel of
+    `csrc/peer_collectives.cuh` that carries its own cross-rank barrier (flag words written over
+    NVLink) -- `cvcl_peer_allgather` for the features and the LSEs, `cvcl_peer_allreduce_f32` (two-shot,
+    in place, deterministic) for [out5 | ds | db | dtable | dW] -- instead of two NCCL all-gathers and
+    an NCCL all-reduce.  Reuse across steps is safe because a rank overwrites its blocks for step s+1
+    only after the all-reduce (or the closing barrier) of step s, which no rank leaves before every
+    rank has finished reading step s.  Default on when symmetric memory is available;
+    CVCL_B200_SYMM=0 selects the NCCL collectives."""
 
     _cache = {}
+    CH_FEATS, CH_LSE, CH_REDUCE, CH_BARRIER = 0, 1, 2, 3
+    N_SLOTS = 2          # stats blocks: alternating CUDA graphs keep the previous step's gradients readable
 
-    def __init__(self, group, b, E, dev):
+    def __init__(self, group, b, E, n_stats, dev):
         import ctypes
         import torch.distributed._symmetric_memory as symm
+        from . import _cabi
+        lib = _cabi.load()
         self.world, self.rank = group_info(group)
-        self.b, self.E = b, E
-        self.feats = symm.empty((b, 2 * E), dtype=torch.bfloat16, device=dev)
-        self.h_feats = symm.rendezvous(self.feats, group)
-        self.lse = symm.empty((2, b), dtype=torch.float32, device=dev)
-        self.h_lse = symm.rendezvous(self.lse, group)
+        self.b, self.E, self.n_stats = b, E, n_stats
+        self.timeout_ms = int(os.environ.get("CVCL_B200_PEER_TIMEOUT_MS", "20000"))
+        fw = int(lib.cvcl_peer_flag_words())
+        nblk = int(lib.cvcl_peer_max_blocks())
+        o_feats = 0
+        o_lse = o_feats + _align(b * 2 * E * 2)
+        o_stats = o_lse + _align(2 * b * 4)
+        o_flags = o_stats + self.N_SLOTS * _align(n_stats * 4)
+        total = o_flags + _align(4 * fw * 4)
+        self.arena = symm.empty((total,), dtype=torch.uint8, device=dev)
+        self.arena.zero_()
+        self.handle = symm.rendezvous(self.arena, group)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)            # every rank's flag words are zero before anyone signals
+        torch.cuda.synchronize(dev)
+        self.feats = self.arena[o_feats:o_feats + b * 2 * E * 2].view(torch.bfloat16).view(b, 2 * E)
+        self.lse = self.arena[o_lse:o_lse + 2 * b * 4].view(torch.float32).view(2, b)
+        o_slot = [o_stats + k * _align(n_stats * 4) for k in range(self.N_SLOTS)]
+        self.stats = [self.arena[o:o + n_stats * 4].view(torch.float32) for o in o_slot]
+        self.epoch = torch.zeros((4, nblk), dtype=torch.int32, device=dev)
+        self.status = torch.zeros((1,), dtype=torch.int32, device=dev)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
         arr = ctypes.c_void_p * self.world
-        self.p_feats = arr(*[int(p) for p in self.h_feats.buffer_ptrs])
-        self.p_lse0 = arr(*[int(p) for p in self.h_lse.buffer_ptrs])
-        self.p_lse1 = arr(*[int(p) + 4 * b for p in self.h_lse.buffer_ptrs])
+        self.p_feats = arr(*[p + o_feats for p in ptrs])
+        self.p_lse = arr(*[p + o_lse for p in ptrs])
+        self.p_stats = [arr(*[p + o for p in ptrs]) for o in o_slot]
+        self.p_flags = [arr(*[p + o_flags + ch * fw * 4 for p in ptrs]) for ch in range(4)]
 
     @classmethod
-    def get(cls, group, b, E, dev):
-        import os
-        # opt-in (CVCL_B200_SYMM=1): measured identical to the NCCL all-gathers at 2 GPUs (174.1 vs
-        # 173.9 us per step) -- the step is bounded by the 9.6 MB gradient all-reduce, not by the
-        # gathers -- so the default stays on the path validated at 2/4/8 GPUs.
-        if os.environ.get("CVCL_B200_SYMM") != "1":
+    def get(cls, group, b, E, n_stats, dev):
+        if os.environ.get("CVCL_B200_SYMM", "1") == "0":
             return None
-        key = (id(group), b, E, dev.index)
+        world, _ = group_info(group)
+        if world not in (2, 4, 8) or b % 4 or n_stats % 4 or (b * 2 * E * 2) % 16:
+            return None
+        key = (id(group), b, E, n_stats, dev.index)
         if key not in cls._cache:
             try:
-                cls._cache[key] = cls(group, b, E, dev)
-            except Exception as exc:             # noqa: BLE001  (no symmetric memory: NCCL all-gathers)
+                cls._cache[key] = cls(group, b, E, n_stats, dev)
+            except Exception as exc:             # noqa: BLE001  (no symmetric memory: NCCL collectives)
                 if os.environ.get("CVCL_B200_DEBUG"):
-                    print("PeerExchange unavailable, using NCCL all-gathers: %r" % (exc,), flush=True)
+                    print("PeerExchange unavailable, using NCCL collectives: %r" % (exc,), flush=True)
                 cls._cache[key] = None
         return cls._cache[key]
 
+    def _ep(self, ch):
+        return self.epoch[ch].data_ptr()
+
     def gather_feats(self, dst, stream):
-        """dst [world*b, 2E] bf16 <- every rank's feature block (after a cross-rank barrier)."""
+        """dst [world*b, 2E] bf16 <- every rank's [img|txt] feature block."""
         from . import _cabi
-        self.h_feats.barrier()
         nbytes = self.b * 2 * self.E * 2
-        _cabi.call("cvcl_p2p_gather", self.p_feats, self.world, -1, nbytes, dst.data_ptr(), nbytes, stream)
+        _cabi.call("cvcl_peer_allgather", self.p_feats, self.p_flags[self.CH_FEATS], self._ep(self.CH_FEATS),
+                   self.status.data_ptr(), self.world, self.rank, nbytes, 1, 0, dst.data_ptr(), 0,
+                   self.timeout_ms, stream)
 
     def gather_lse(self, dst, stream):
         """dst [2, world*b] fp32 <- every rank's lse0 / lse1."""
         from . import _cabi
-        self.h_lse.barrier()
         nb = self.b * 4
-        _cabi.call("cvcl_p2p_gather", self.p_lse0, self.world, -1, nb, dst[0].data_ptr(), nb, stream)
-        _cabi.call("cvcl_p2p_gather", self.p_lse1, self.world, -1, nb, dst[1].data_ptr(), nb, stream)
+        _cabi.call("cvcl_peer_allgather", self.p_lse, self.p_flags[self.CH_LSE], self._ep(self.CH_LSE),
+                   self.status.data_ptr(), self.world, self.rank, nb, 2, nb, dst.data_ptr(), self.world * nb,
+                   self.timeout_ms, stream)
 
-    def barrier(self):
-        self.h_feats.barrier()
+    def allreduce_stats(self, slot, n, stream):
+        """in-place sum over ranks of the first n floats of stats block `slot`."""
+        from . import _cabi
+        _cabi.call("cvcl_peer_allreduce_f32", self.p_stats[slot], self.p_flags[self.CH_REDUCE], self._ep(self.CH_REDUCE),
+                   self.status.data_ptr(), self.world, self.rank, n, self.timeout_ms, stream)
+
+    def barrier(self, stream):
+        from . import _cabi
+        _cabi.call("cvcl_peer_barrier", self.p_flags[self.CH_BARRIER], self._ep(self.CH_BARRIER),
+                   self.status.data_ptr(), self.world, self.rank, self.timeout_ms, stream)
+
+    def check(self):
+        """raise if a cross-rank barrier timed out (synchronises the device)."""
+        if int(self.status.item()) != 0:
+            raise RuntimeError("peer collective barrier timed out (status %d)" % int(self.status.item()))

@@ -1,5 +1,6 @@
-"""-m gpu, needs >= 2 GPUs: sharded global-batch InfoNCE over NCCL equals the single-GPU result
-(feature-level op and the whole model step).  Launches tools/sharded_check.py under torchrun."""
+"""-m gpu, needs >= 2 GPUs: the sharded global-batch InfoNCE equals the single-GPU result (feature-level
+op and the whole model step), with the default peer-memory collectives and with NCCL.  Launches
+tools/sharded_check.py under torchrun."""
 import os
 import socket
 import subprocess
@@ -29,14 +30,15 @@ def test_sharded_equals_single_gpu(world):
     assert res.returncode == 0 and "SHARDED_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
 
 
-def test_sharded_peer_memory_exchange_equals_single_gpu():
-    """same check with the exchange steps over symmetric memory (barrier + P2P gather kernel over
-    NVLink) instead of NCCL all-gathers (CVCL_B200_SYMM=1)."""
+def test_sharded_nccl_collectives_equal_single_gpu():
+    """same check with the NCCL collectives (CVCL_B200_SYMM=0) instead of the default peer-memory
+    kernels (csrc/peer_collectives.cuh)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    env = dict(os.environ, CVCL_B200_SYMM="1")
+    env = dict(os.environ, CVCL_B200_SYMM="0")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(ROOT, "tools", "sharded_check.py"), "2048"]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
-    assert res.returncode == 0 and "SHARDED_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+    assert res.returncode == 0 and "SHARDED_OK" in res.stdout and "exchange=nccl" in res.stdout, \
+        res.stdout[-2000:] + res.stderr[-4000:]

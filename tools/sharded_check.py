@@ -1,4 +1,4 @@
-"""torchrun target: sharded global-batch InfoNCE (NCCL all-gather over NVLink) == the single-GPU
+"""torchrun target: sharded global-batch InfoNCE (exchange over NVLink: peer-memory kernels or NCCL) == the single-GPU
 global-batch result, and the full sharded model step == single-GPU step on the concatenated batch.
     python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/sharded_check.py [B_global]
 Prints `SHARDED_OK ...` on rank 0 on success, raises otherwise."""
@@ -65,7 +65,22 @@ for (n, p1), (_, po) in zip(model_1.named_parameters(), model_o.named_parameters
     if p1.grad is None:
         continue
     assert rel(po.grad, p1.grad) <= 5e-3, (n, rel(po.grad, p1.grad))
+# which exchange back end ran: peer-memory kernels by default, NCCL collectives with CVCL_B200_SYMM=0
+pxs = list(m.sharding.PeerExchange._cache.values())
+peer = bool(pxs) and all(v is not None for v in pxs)
+if os.environ.get("CVCL_B200_SYMM", "1") != "0":
+    assert peer, "peer-memory exchange expected but not active (symmetric memory unavailable?)"
+    for v in pxs:
+        v.check()                      # no cross-rank barrier timed out
+else:
+    assert not pxs
+# (4) repeated steps reuse the persistent symmetric blocks: same loss every time (split-K atomics: to rounding)
+for _ in range(3):
+    l_again = step_api(model_s, x_all[rank * 512:(rank + 1) * 512], ids_all[rank * 512:(rank + 1) * 512],
+                       lens_all[rank * 512:(rank + 1) * 512], world)
+    assert abs(l_again.item() - ls.item()) <= 2e-6 * abs(ls.item()), (l_again.item(), ls.item())
 torch.cuda.synchronize(); dist.barrier()
 if rank == 0:
-    print("SHARDED_OK world=%d B=%d loss=%.6f model_loss=%.6f" % (world, B, got5[0].item(), ls.item()))
+    print("SHARDED_OK world=%d B=%d loss=%.6f model_loss=%.6f exchange=%s" % (
+        world, B, got5[0].item(), ls.item(), "peer" if peer else "nccl"))
 dist.destroy_process_group()
