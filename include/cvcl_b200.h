@@ -217,7 +217,14 @@ int cvcl_p2p_gather(const void* const* peer_ptrs, int world, int skip_rank, long
  *   allreduce_f32: in-place sum over ranks of n floats (n % 4 == 0, world in {1,2,4,8}); slice r is
  *                  summed by rank r in rank order and written to every rank: bit-identical results on
  *                  all ranks, independent of timing.
- *   barrier      : barrier only. */
+ *   barrier      : barrier only.
+ *   allgather_push / allreduce_push_f32: the same results with PUSH traffic only (posted stores over
+ *                  NVLink, no load round trips): allgather_push stores the caller's block `src` into slot
+ *                  `rank` of every rank's gathered buffer peer_dst[p] and then barriers; allreduce_push
+ *                  scatters slice p of the caller's buffer into rank p's scratch block
+ *                  (cvcl_peer_allreduce_scratch_bytes, peer-mapped), barriers, sums its own slice locally
+ *                  in rank order, stores the sum into every rank's buffer, barriers.  Both are launched
+ *                  with programmatic dependent launch (their launch overlaps the tail of the previous kernel). */
 size_t cvcl_peer_flag_words(void);
 int cvcl_peer_max_blocks(void);
 int cvcl_peer_allgather(void* const* peer_data, void* const* peer_flags, unsigned int* epoch, int* status, int world,
@@ -225,6 +232,13 @@ int cvcl_peer_allgather(void* const* peer_data, void* const* peer_flags, unsigne
                         long long dst_seg_stride_bytes, unsigned int timeout_ms, void* stream);
 int cvcl_peer_allreduce_f32(void* const* peer_data, void* const* peer_flags, unsigned int* epoch, int* status, int world,
                             int rank, long long n, unsigned int timeout_ms, void* stream);
+int cvcl_peer_allgather_push(void* const* peer_dst, void* const* peer_flags, unsigned int* epoch, int* status, int world,
+                             int rank, const void* src, long long seg_bytes, int nseg, long long src_seg_stride_bytes,
+                             long long dst_seg_stride_bytes, unsigned int timeout_ms, void* stream);
+size_t cvcl_peer_allreduce_scratch_bytes(long long n, int world);
+int cvcl_peer_allreduce_push_f32(void* const* peer_data, void* const* peer_scratch, void* const* peer_flags,
+                                 unsigned int* epoch, int* status, int world, int rank, long long n,
+                                 unsigned int timeout_ms, void* stream);
 int cvcl_peer_barrier(void* const* peer_flags, unsigned int* epoch, int* status, int world, int rank,
                       unsigned int timeout_ms, void* stream);
 

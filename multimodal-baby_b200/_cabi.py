@@ -64,6 +64,10 @@ PROTOTYPES = {
     "cvcl_peer_allgather": (c_int, [_P, _P, _P, _P, _I, _I, ctypes.c_longlong, _I, ctypes.c_longlong, _P,
                                     ctypes.c_longlong, ctypes.c_uint, _P]),
     "cvcl_peer_allreduce_f32": (c_int, [_P, _P, _P, _P, _I, _I, ctypes.c_longlong, ctypes.c_uint, _P]),
+    "cvcl_peer_allgather_push": (c_int, [_P, _P, _P, _P, _I, _I, _P, ctypes.c_longlong, _I, ctypes.c_longlong,
+                                         ctypes.c_longlong, ctypes.c_uint, _P]),
+    "cvcl_peer_allreduce_scratch_bytes": (c_size_t, [ctypes.c_longlong, _I]),
+    "cvcl_peer_allreduce_push_f32": (c_int, [_P, _P, _P, _P, _P, _I, _I, ctypes.c_longlong, ctypes.c_uint, _P]),
     "cvcl_peer_barrier": (c_int, [_P, _P, _P, _I, _I, ctypes.c_uint, _P]),
     "cvcl_adamw_step": (c_int, [_P, _P, _P, _P, ctypes.c_longlong, _F, _F, _F, _F, _F, _I, _F, _P, _P]),
     "cvcl_eval_nway_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P]),

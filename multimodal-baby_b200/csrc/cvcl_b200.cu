@@ -741,6 +741,60 @@ int cvcl_peer_allreduce_f32(void* const* peer_data, void* const* peer_flags, uns
     return CVCL_OK;
 }
 
+int cvcl_peer_allgather_push(void* const* peer_dst, void* const* peer_flags, unsigned int* epoch, int* status, int world,
+                             int rank, const void* src, long long seg_bytes, int nseg, long long src_seg_stride_bytes,
+                             long long dst_seg_stride_bytes, unsigned int timeout_ms, void* stream) {
+    CVCL_REQUIRE(peer_dst && src, "peer_allgather_push: null pointer");
+    CVCL_REQUIRE(seg_bytes > 0 && nseg >= 1, "peer_allgather_push: empty exchange");
+    CVCL_REQUIRE(seg_bytes % 16 == 0 && src_seg_stride_bytes % 16 == 0 && dst_seg_stride_bytes % 16 == 0 &&
+                 (reinterpret_cast<uintptr_t>(src) & 15) == 0, "peer_allgather_push: 16-byte granularity required");
+    PeerTable t{};
+    int rc = fill_peer_table(&t, peer_dst, peer_flags, epoch, status, world, rank, timeout_ms, "peer_allgather_push");
+    if (rc != CVCL_OK) return rc;
+    const long long per16 = seg_bytes / 16 * nseg;
+    long long blocks = (per16 + 4LL * kPeerThreads - 1) / (4LL * kPeerThreads);        // same on every rank
+    blocks = blocks < 1 ? 1 : (blocks > kPeerMaxBlocks ? kPeerMaxBlocks : blocks);
+    CVCL_CHECK_CUDA(launch_pdl(peer_allgather_push_kernel, dim3(static_cast<unsigned>(blocks)), dim3(kPeerThreads), 0,
+                               as_stream(stream), t, world, rank, static_cast<const uint4*>(src), seg_bytes / 16, nseg,
+                               src_seg_stride_bytes / 16, dst_seg_stride_bytes / 16));
+    count_launch();
+    return CVCL_OK;
+}
+
+size_t cvcl_peer_allreduce_scratch_bytes(long long n, int world) {
+    if (n <= 0 || world < 1) return 0;
+    const long long n4 = (n + 3) / 4, per = (n4 + world - 1) / world;
+    return static_cast<size_t>(per) * world * 16;
+}
+
+int cvcl_peer_allreduce_push_f32(void* const* peer_data, void* const* peer_scratch, void* const* peer_flags,
+                                 unsigned int* epoch, int* status, int world, int rank, long long n,
+                                 unsigned int timeout_ms, void* stream) {
+    CVCL_REQUIRE(peer_data && peer_scratch, "peer_allreduce_push_f32: null pointer");
+    CVCL_REQUIRE(n > 0 && n % 4 == 0, "peer_allreduce_push_f32: n=%lld must be a positive multiple of 4", n);
+    if (world != 1 && world != 2 && world != 4 && world != 8)
+        return fail(CVCL_ERR_UNSUPPORTED, "peer_allreduce_push_f32: world size %d (supported: 1, 2, 4, 8)", world);
+    if (world == 1) return CVCL_OK;
+    PeerTable t{};
+    int rc = fill_peer_table(&t, peer_data, peer_flags, epoch, status, world, rank, timeout_ms, "peer_allreduce_push_f32");
+    if (rc != CVCL_OK) return rc;
+    for (int r = 0; r < world; ++r) {
+        CVCL_REQUIRE(peer_scratch[r] && (reinterpret_cast<uintptr_t>(peer_scratch[r]) & 15) == 0,
+                     "peer_allreduce_push_f32: bad scratch pointer %d", r);
+        t.aux[r] = peer_scratch[r];
+    }
+    const long long n4 = n / 4, per = (n4 + world - 1) / world;
+    long long blocks = (per + 2LL * kPeerThreads - 1) / (2LL * kPeerThreads);           // same on every rank
+    blocks = blocks < 1 ? 1 : (blocks > kPeerMaxBlocks ? kPeerMaxBlocks : blocks);
+    const dim3 grid(static_cast<unsigned>(blocks)), block(kPeerThreads);
+    cudaStream_t st = as_stream(stream);
+    if (world == 2) CVCL_CHECK_CUDA(launch_pdl(peer_allreduce_push_f32_kernel<2>, grid, block, 0, st, t, rank, n4));
+    else if (world == 4) CVCL_CHECK_CUDA(launch_pdl(peer_allreduce_push_f32_kernel<4>, grid, block, 0, st, t, rank, n4));
+    else CVCL_CHECK_CUDA(launch_pdl(peer_allreduce_push_f32_kernel<8>, grid, block, 0, st, t, rank, n4));
+    count_launch();
+    return CVCL_OK;
+}
+
 int cvcl_peer_barrier(void* const* peer_flags, unsigned int* epoch, int* status, int world, int rank,
                       unsigned int timeout_ms, void* stream) {
     PeerTable t{};

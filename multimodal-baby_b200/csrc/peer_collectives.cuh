@@ -22,6 +22,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "ptx.cuh"
 
 namespace cvcl {
 
@@ -33,6 +34,7 @@ constexpr int kPeerFlagWords = 2 * kPeerMaxBlocks * kPeerMaxWorld;
 
 struct PeerTable {
     void* data[kPeerMaxWorld];          // rank r's block (peer-mapped)
+    void* aux[kPeerMaxWorld];           // rank r's scratch block (push all-reduce), peer-mapped
     uint32_t* flags[kPeerMaxWorld];     // rank r's flag area for this channel (peer-mapped)
     uint32_t* epoch;                    // local [kPeerMaxBlocks]
     int* status;                        // local, nullable
@@ -178,6 +180,98 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_f32_kernel(const 
 __global__ void __launch_bounds__(32) peer_barrier_kernel(const PeerTable t, int world, int rank) {
     const uint32_t e = peer::epoch_begin(t);
     peer::barrier(t, world, rank, e, 0);
+    peer::epoch_end(t, e);
+}
+
+// --------------------------------------------------------------------------------------
+// PUSH variants: all NVLink traffic is posted stores (no load round trips over the switch).
+//
+// all-gather: every rank stores its block into slot `rank` of EVERY rank's gathered buffer (t.data[p] =
+// rank p's gathered buffer), then one barrier: when a peer's signal arrives its stores have landed.
+// The gathered buffers may be overwritten because the previous step's all-reduce (or closing barrier)
+// ended after every rank had finished reading them.
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPeerThreads) peer_allgather_push_kernel(const PeerTable t, int world, int rank,
+                                                                           const uint4* src, long long seg16,
+                                                                           int nseg, long long src_seg_stride16,
+                                                                           long long dst_seg_stride16) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
+    const uint32_t e = peer::epoch_begin(t);
+    const long long per_rank = seg16 * nseg;
+    const long long stride = static_cast<long long>(gridDim.x) * kPeerThreads;
+    constexpr int U = 4;
+    for (long long base = static_cast<long long>(blockIdx.x) * kPeerThreads + threadIdx.x; base < per_rank;
+         base += U * stride) {
+        uint4 v[U];
+        long long out[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long idx = base + u * stride;
+            out[u] = -1;
+            if (idx < per_rank) {
+                const long long s = idx / seg16, i = idx - s * seg16;
+                v[u] = src[s * src_seg_stride16 + i];
+                out[u] = s * dst_seg_stride16 + rank * seg16 + i;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (out[u] >= 0) {
+                for (int p = 0; p < world; ++p) static_cast<uint4*>(t.data[p])[out[u]] = v[u];
+            }
+        }
+    }
+    peer::barrier(t, world, rank, e, 0);
+    peer::epoch_end(t, e);
+}
+
+// --------------------------------------------------------------------------------------
+// all-reduce, two-shot, push: (A) rank r stores slice p of its buffer into rank p's scratch block
+// [src rank r][.] for every p != r; barrier; (B) rank r sums its slice over {own buffer, scratch[src]} in
+// rank order and stores the sum into slice r of every rank's buffer; barrier.  The scratch block of a
+// rank is rewritten by launch e+1 only after the end barrier of launch e, i.e. after it was consumed.
+// --------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(kPeerThreads) peer_allreduce_push_f32_kernel(const PeerTable t, int rank, long long n4) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
+    const uint32_t e = peer::epoch_begin(t);
+    const long long per = (n4 + W - 1) / W;
+    const long long stride = static_cast<long long>(gridDim.x) * kPeerThreads;
+    const long long tid = static_cast<long long>(blockIdx.x) * kPeerThreads + threadIdx.x;
+    const uint4* mine = static_cast<const uint4*>(t.data[rank]);
+    constexpr int U = (W >= 8) ? 1 : (W >= 4 ? 2 : 4);
+    // (A) scatter my contributions
+#pragma unroll U
+    for (long long j = tid; j < per; j += stride) {
+        uint4 v[W];
+#pragma unroll
+        for (int p = 0; p < W; ++p)
+            if (p != rank && p * per + j < n4) v[p] = mine[p * per + j];
+#pragma unroll
+        for (int p = 0; p < W; ++p)
+            if (p != rank && p * per + j < n4) static_cast<uint4*>(t.aux[p])[rank * per + j] = v[p];
+    }
+    peer::barrier(t, W, rank, e, 0);
+    // (B) reduce my slice, broadcast
+    const long long lo = rank * per;
+    const long long cnt = (lo + per <= n4) ? per : (n4 > lo ? n4 - lo : 0);
+    const uint4* scr = static_cast<const uint4*>(t.aux[rank]);
+#pragma unroll U
+    for (long long j = tid; j < cnt; j += stride) {
+        uint4 v[W];
+#pragma unroll
+        for (int p = 0; p < W; ++p) v[p] = (p == rank) ? mine[lo + j] : peer::ld_sys_v4(scr + p * per + j);
+        float4 acc = make_float4(__uint_as_float(v[0].x), __uint_as_float(v[0].y), __uint_as_float(v[0].z),
+                                 __uint_as_float(v[0].w));
+#pragma unroll
+        for (int p = 1; p < W; ++p) {               // rank order: the sum does not depend on the reducer
+            acc.x += __uint_as_float(v[p].x); acc.y += __uint_as_float(v[p].y);
+            acc.z += __uint_as_float(v[p].z); acc.w += __uint_as_float(v[p].w);
+        }
+#pragma unroll
+        for (int p = 0; p < W; ++p) static_cast<float4*>(t.data[p])[lo + j] = acc;
+    }
+    peer::barrier(t, W, rank, e, 1);
     peer::epoch_end(t, e);
 }
 

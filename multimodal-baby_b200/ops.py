@@ -706,9 +706,8 @@ def flat_step_sharded(x, ids, lens, w, bias, table, log_scale, normalize, need_g
     main.wait_stream(side)
     if phase_limit == 1:
         return stats, img_f, txt_f
-    if px is not None:       # one kernel: cross-rank barrier + 16-byte loads from the peers' blocks (NVLink)
-        feats_all = torch.empty((Bg, 2 * E), **bf)
-        px.gather_feats(feats_all, st)
+    if px is not None:       # one kernel: 16-byte stores into every rank's gathered buffer (NVLink) + barrier
+        feats_all = px.gather_feats(st)
     else:
         feats_all = sharding.all_gather_rows(feats, group, world)      # [Bg, 2E] (NCCL)
     img_a, txt_a = feats_all[:, :E], feats_all[:, E:]
@@ -722,8 +721,7 @@ def flat_step_sharded(x, ids, lens, w, bias, table, log_scale, normalize, need_g
         return stats, img_f, txt_f
     if need_grads:
         if px is not None:
-            lse_all = torch.empty((2, Bg), **f32)
-            px.gather_lse(lse_all, st)
+            lse_all = px.gather_lse(st)
         elif world > 1:
             lse_all = sharding.all_gather_rows(lse, group, world).view(world, 2, B).permute(1, 0, 2).contiguous()
         else:

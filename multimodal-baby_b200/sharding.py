@@ -92,13 +92,15 @@ def _align(n, a=256):
 class PeerExchange:
     """Per-(group, b, E, n_stats) symmetric-memory arena for the three collectives of the sharded step:
 
-        [ feats (b, 2E) bf16 | lse (2, b) f32 | stats (n_stats) f32 x N_SLOTS | flags ]
+        [ feats (b, 2E) bf16 | lse (2, b) f32 | feats_all (W*b, 2E) | lse_all (2, W*b) | reduce scratch |
+          stats (n_stats) f32 x N_SLOTS | flags ]
 
     is allocated once in peer-mapped memory (one rendezvous); each collective is ONE kernel of
     `csrc/peer_collectives.cuh` that carries its own cross-rank barrier (flag words written over
     NVLink) -- `cvcl_peer_allgather` for the features and the LSEs, `cvcl_peer_allreduce_f32` (two-shot,
     in place, deterministic) for [out5 | ds | db | dtable | dW] -- instead of two NCCL all-gathers and
-    an NCCL all-reduce.  Reuse across steps is safe because a rank overwrites its blocks for step s+1
+    an NCCL all-reduce.  Default: the PUSH kernels (posted stores over NVLink, no load round trips;
+    CVCL_B200_PEER_MODE=pull selects the pull kernels).  Reuse across steps is safe because a rank overwrites its blocks for step s+1
     only after the all-reduce (or the closing barrier) of step s, which no rank leaves before every
     rank has finished reading step s.  Default on when symmetric memory is available;
     CVCL_B200_SYMM=0 selects the NCCL collectives."""
@@ -117,29 +119,40 @@ class PeerExchange:
         self.timeout_ms = int(os.environ.get("CVCL_B200_PEER_TIMEOUT_MS", "20000"))
         fw = int(lib.cvcl_peer_flag_words())
         nblk = int(lib.cvcl_peer_max_blocks())
-        o_feats = 0
-        o_lse = o_feats + _align(b * 2 * E * 2)
-        o_stats = o_lse + _align(2 * b * 4)
-        o_flags = o_stats + self.N_SLOTS * _align(n_stats * 4)
-        total = o_flags + _align(4 * fw * 4)
+        self.push = os.environ.get("CVCL_B200_PEER_MODE", "push") != "pull"
+        Bg = self.world * b
+        sizes = [("feats", b * 2 * E * 2), ("lse", 2 * b * 4), ("feats_all", Bg * 2 * E * 2), ("lse_all", 2 * Bg * 4),
+                 ("scratch", int(lib.cvcl_peer_allreduce_scratch_bytes(n_stats, self.world)))]
+        sizes += [("stats%d" % k, n_stats * 4) for k in range(self.N_SLOTS)] + [("flags", 4 * fw * 4)]
+        off, total = {}, 0
+        for name, nb in sizes:
+            off[name] = total
+            total += _align(nb)
         self.arena = symm.empty((total,), dtype=torch.uint8, device=dev)
         self.arena.zero_()
         self.handle = symm.rendezvous(self.arena, group)
         torch.cuda.synchronize(dev)
         dist.barrier(group=group)            # every rank's flag words are zero before anyone signals
         torch.cuda.synchronize(dev)
-        self.feats = self.arena[o_feats:o_feats + b * 2 * E * 2].view(torch.bfloat16).view(b, 2 * E)
-        self.lse = self.arena[o_lse:o_lse + 2 * b * 4].view(torch.float32).view(2, b)
-        o_slot = [o_stats + k * _align(n_stats * 4) for k in range(self.N_SLOTS)]
-        self.stats = [self.arena[o:o + n_stats * 4].view(torch.float32) for o in o_slot]
+
+        def view(name, nbytes, dtype):
+            return self.arena[off[name]:off[name] + nbytes].view(dtype)
+        self.feats = view("feats", b * 2 * E * 2, torch.bfloat16).view(b, 2 * E)
+        self.lse = view("lse", 2 * b * 4, torch.float32).view(2, b)
+        self.feats_all = view("feats_all", Bg * 2 * E * 2, torch.bfloat16).view(Bg, 2 * E)
+        self.lse_all = view("lse_all", 2 * Bg * 4, torch.float32).view(2, Bg)
+        self.stats = [view("stats%d" % k, n_stats * 4, torch.float32) for k in range(self.N_SLOTS)]
         self.epoch = torch.zeros((4, nblk), dtype=torch.int32, device=dev)
         self.status = torch.zeros((1,), dtype=torch.int32, device=dev)
         ptrs = [int(p) for p in self.handle.buffer_ptrs]
         arr = ctypes.c_void_p * self.world
-        self.p_feats = arr(*[p + o_feats for p in ptrs])
-        self.p_lse = arr(*[p + o_lse for p in ptrs])
-        self.p_stats = [arr(*[p + o for p in ptrs]) for o in o_slot]
-        self.p_flags = [arr(*[p + o_flags + ch * fw * 4 for p in ptrs]) for ch in range(4)]
+
+        def table(name, extra=0):
+            return arr(*[p + off[name] + extra for p in ptrs])
+        self.p_feats, self.p_lse = table("feats"), table("lse")
+        self.p_feats_all, self.p_lse_all, self.p_scratch = table("feats_all"), table("lse_all"), table("scratch")
+        self.p_stats = [table("stats%d" % k) for k in range(self.N_SLOTS)]
+        self.p_flags = [table("flags", ch * fw * 4) for ch in range(4)]
 
     @classmethod
     def get(cls, group, b, E, n_stats, dev):
@@ -148,7 +161,7 @@ class PeerExchange:
         world, _ = group_info(group)
         if world not in (2, 4, 8) or b % 4 or n_stats % 4 or (b * 2 * E * 2) % 16:
             return None
-        key = (id(group), b, E, n_stats, dev.index)
+        key = (id(group), b, E, n_stats, dev.index, os.environ.get("CVCL_B200_PEER_MODE", "push"))
         if key not in cls._cache:
             try:
                 cls._cache[key] = cls(group, b, E, n_stats, dev)
@@ -161,27 +174,45 @@ class PeerExchange:
     def _ep(self, ch):
         return self.epoch[ch].data_ptr()
 
-    def gather_feats(self, dst, stream):
-        """dst [world*b, 2E] bf16 <- every rank's [img|txt] feature block."""
+    def gather_feats(self, stream):
+        """-> [world*b, 2E] bf16: every rank's [img|txt] feature block (persistent symmetric buffer)."""
         from . import _cabi
         nbytes = self.b * 2 * self.E * 2
-        _cabi.call("cvcl_peer_allgather", self.p_feats, self.p_flags[self.CH_FEATS], self._ep(self.CH_FEATS),
-                   self.status.data_ptr(), self.world, self.rank, nbytes, 1, 0, dst.data_ptr(), 0,
-                   self.timeout_ms, stream)
+        ch = self.CH_FEATS
+        if self.push:
+            _cabi.call("cvcl_peer_allgather_push", self.p_feats_all, self.p_flags[ch], self._ep(ch),
+                       self.status.data_ptr(), self.world, self.rank, self.feats.data_ptr(), nbytes, 1, 0, 0,
+                       self.timeout_ms, stream)
+        else:
+            _cabi.call("cvcl_peer_allgather", self.p_feats, self.p_flags[ch], self._ep(ch), self.status.data_ptr(),
+                       self.world, self.rank, nbytes, 1, 0, self.feats_all.data_ptr(), 0, self.timeout_ms, stream)
+        return self.feats_all
 
-    def gather_lse(self, dst, stream):
-        """dst [2, world*b] fp32 <- every rank's lse0 / lse1."""
+    def gather_lse(self, stream):
+        """-> [2, world*b] fp32: every rank's lse0 / lse1."""
         from . import _cabi
         nb = self.b * 4
-        _cabi.call("cvcl_peer_allgather", self.p_lse, self.p_flags[self.CH_LSE], self._ep(self.CH_LSE),
-                   self.status.data_ptr(), self.world, self.rank, nb, 2, nb, dst.data_ptr(), self.world * nb,
-                   self.timeout_ms, stream)
+        ch = self.CH_LSE
+        if self.push:
+            _cabi.call("cvcl_peer_allgather_push", self.p_lse_all, self.p_flags[ch], self._ep(ch),
+                       self.status.data_ptr(), self.world, self.rank, self.lse.data_ptr(), nb, 2, nb, self.world * nb,
+                       self.timeout_ms, stream)
+        else:
+            _cabi.call("cvcl_peer_allgather", self.p_lse, self.p_flags[ch], self._ep(ch), self.status.data_ptr(),
+                       self.world, self.rank, nb, 2, nb, self.lse_all.data_ptr(), self.world * nb, self.timeout_ms,
+                       stream)
+        return self.lse_all
 
     def allreduce_stats(self, slot, n, stream):
         """in-place sum over ranks of the first n floats of stats block `slot`."""
         from . import _cabi
-        _cabi.call("cvcl_peer_allreduce_f32", self.p_stats[slot], self.p_flags[self.CH_REDUCE], self._ep(self.CH_REDUCE),
-                   self.status.data_ptr(), self.world, self.rank, n, self.timeout_ms, stream)
+        ch = self.CH_REDUCE
+        if self.push:
+            _cabi.call("cvcl_peer_allreduce_push_f32", self.p_stats[slot], self.p_scratch, self.p_flags[ch],
+                       self._ep(ch), self.status.data_ptr(), self.world, self.rank, n, self.timeout_ms, stream)
+        else:
+            _cabi.call("cvcl_peer_allreduce_f32", self.p_stats[slot], self.p_flags[ch], self._ep(ch),
+                       self.status.data_ptr(), self.world, self.rank, n, self.timeout_ms, stream)
 
     def barrier(self, stream):
         from . import _cabi

@@ -115,3 +115,63 @@ def test_peer_barrier_orders_streams():
         out.copy_(val[:1])
     _join(streams, status)
     assert float(out.item()) == 42.0
+
+
+@pytest.mark.parametrize("world,n", [(2, 8 + 1024), (2, 2_400_012), (4, 2_400_012), (8, 1_000_012), (8, 8)])
+def test_peer_allreduce_push_emulated_ranks(world, n):
+    """push variant (scatter into the owners' scratch blocks, local reduce, broadcast): same contract."""
+    _cabi, dev, data, flags, epoch, status, arr, streams = _setup(world, n * 4)
+    nscr = int(_cabi.load().cvcl_peer_allreduce_scratch_bytes(n, world))
+    scratch = [torch.empty(nscr, dtype=torch.uint8, device=dev) for _ in range(world)]
+    p_data = arr(*[d.data_ptr() for d in data]); p_flags = arr(*[f.data_ptr() for f in flags])
+    p_scr = arr(*[d.data_ptr() for d in scratch])
+    g = torch.Generator(device="cpu").manual_seed(world * 1000 + n % 997 + 1)
+    for it in range(3):
+        src = [torch.randn(n, generator=g) for _ in range(world)]
+        for d, s in zip(data, src):
+            d.view(torch.float32).copy_(s.to(dev))
+        torch.cuda.synchronize()
+        for r in range(world):
+            _cabi.call("cvcl_peer_allreduce_push_f32", p_data, p_scr, p_flags, epoch[r].data_ptr(),
+                       status[r].data_ptr(), world, r, n, TIMEOUT_MS, streams[r].cuda_stream)
+        _join(streams, status)
+        want = src[0].clone()
+        for s in src[1:]:
+            want += s
+        for r in range(world):
+            assert torch.equal(data[r].view(torch.float32).cpu(), want), (world, n, it, r)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_peer_allgather_push_emulated_ranks(world):
+    b, E = 64, 512
+    _cabi, dev, _, flags, epoch, status, arr, streams = _setup(world, 16)
+    p_flags = arr(*[f.data_ptr() for f in flags])
+    g = torch.Generator(device="cpu").manual_seed(70 + world)
+    dst = [torch.zeros(world * b, 2 * E, dtype=torch.bfloat16, device=dev) for _ in range(world)]
+    p_dst = arr(*[d.data_ptr() for d in dst])
+    nbytes = b * 2 * E * 2
+    for it in range(2):
+        blocks = [torch.randn(b, 2 * E, generator=g).to(torch.bfloat16).to(dev) for _ in range(world)]
+        torch.cuda.synchronize()
+        for r in range(world):
+            _cabi.call("cvcl_peer_allgather_push", p_dst, p_flags, epoch[r].data_ptr(), status[r].data_ptr(), world, r,
+                       blocks[r].data_ptr(), nbytes, 1, 0, 0, TIMEOUT_MS, streams[r].cuda_stream)
+        _join(streams, status)
+        want = torch.cat(blocks).cpu()
+        for r in range(world):
+            assert torch.equal(dst[r].cpu(), want), (world, it, r)
+    # two segments per rank (lse0 | lse1) -> [2, world*b]
+    _cabi, dev, _, flags, epoch, status, arr, streams = _setup(world, 16)
+    p_flags = arr(*[f.data_ptr() for f in flags])
+    lses = [torch.randn(2, b, generator=g).to(dev) for _ in range(world)]
+    dst = [torch.zeros(2, world * b, device=dev) for _ in range(world)]
+    p_dst = arr(*[d.data_ptr() for d in dst])
+    torch.cuda.synchronize()
+    for r in range(world):
+        _cabi.call("cvcl_peer_allgather_push", p_dst, p_flags, epoch[r].data_ptr(), status[r].data_ptr(), world, r,
+                   lses[r].data_ptr(), b * 4, 2, b * 4, world * b * 4, TIMEOUT_MS, streams[r].cuda_stream)
+    _join(streams, status)
+    want = torch.cat(lses, dim=1).cpu()
+    for r in range(world):
+        assert torch.equal(dst[r].cpu(), want), (world, r)

@@ -3,9 +3,9 @@ For k = 1..7 the step is captured as a CUDA graph that stops after phase k (ops.
 `phase_limit`), replayed with an L2 flush in between and event-timed (max over ranks); the difference
 between consecutive k is what that phase adds to the step where it actually runs (with PDL overlap,
 side-stream branches and the other ranks' skew), which isolated per-collective timings do not show.
-Both exchange back ends are measured: NCCL collectives and the peer-memory kernels.
+Three exchange back ends are measured: NCCL collectives, the pull and the push peer-memory kernels.
 
-    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/sharded_phases.py [reps]
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/sharded_phases.py [reps] [nccl,pull,push]
 """
 import json, os, statistics, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -28,8 +28,10 @@ w, b = model.image_embed.model.fc.weight, model.image_embed.model.fc.bias
 table = model.text_embed.embedding.weight
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 out = {}
-for mode in ("nccl", "peer"):
+MODES = sys.argv[2].split(",") if len(sys.argv) > 2 else ["nccl", "pull", "push"]
+for mode in MODES:
     os.environ["CVCL_B200_SYMM"] = "0" if mode == "nccl" else "1"
+    os.environ["CVCL_B200_PEER_MODE"] = "pull" if mode == "pull" else "push"
     res = []
     for k in range(1, 8):
         lim = None if k == 7 else k
@@ -61,11 +63,10 @@ for mode in ("nccl", "peer"):
             print("%s  %-38s %8.1f us  (+%.1f)" % (mode, PHASES[k - 1], res[-1], res[-1] - (res[-2] if k > 1 else 0)), flush=True)
         del g
     used = [v is not None for v in m.sharding.PeerExchange._cache.values()]
-    out[mode] = dict(cumulative_us=res, peer_exchange_active=bool(used and all(used)) if mode == "peer" else False)
-if mode == "peer":
-    for px in m.sharding.PeerExchange._cache.values():
-        if px is not None:
-            px.check()
+    out[mode] = dict(cumulative_us=res, peer_exchange_active=bool(used and all(used)) if mode != "nccl" else False)
+for px in m.sharding.PeerExchange._cache.values():
+    if px is not None:
+        px.check()
 torch.cuda.synchronize(); dist.barrier()
 if rank == 0:
     print(json.dumps(dict(world=world, pairs_per_gpu=B, phases=PHASES, **out)))
