@@ -150,6 +150,15 @@ int cvcl_feat_grad_norm_bwd(const void* Gs, int ldg, int gs_transposed, const vo
                             int normalize, const int64_t* row_len, const void* diag_feat, int ld_diag,
                             int diag_rows, int diag_off, float diag_coef, float* out_f32, int ld_f32,
                             void* out_bf16, int ld_bf16, float* dbias, void* stream);
+/* same, with an optional fp32 scratch acc_scratch [M,E]: when the contraction is long (Kc >= 1536, the
+ * sharded global batch) and the output has few tiles, the GEMM is split over the contraction into
+ * acc_scratch (or into out_f32 itself when that is the output) with fp32 vector atomics, and a
+ * warp-per-row pass applies the diagonal term, the normalise backward, 1/len and the bias sums. */
+int cvcl_feat_grad_norm_bwd_ws(const void* Gs, int ldg, int gs_transposed, const void* other, int ld_other,
+                               int M, int E, int Kc, const void* feat_bf16, int ld_feat, const float* inv_norm,
+                               int normalize, const int64_t* row_len, const void* diag_feat, int ld_diag,
+                               int diag_rows, int diag_off, float diag_coef, float* out_f32, int ld_f32,
+                               void* out_bf16, int ld_bf16, float* dbias, float* acc_scratch, void* stream);
 /* (c) dW [E,K] = sum_m du[m,:]^T x[m,:]  (autograd of nn.Linear / 1x1 conv weight); du [M,E] and
  *     x [M,K] bf16 as stored (both read MN-major). */
 int cvcl_head_weight_grad(const void* du, int ld_du, const void* x, int ld_x, int E, int K, int M,

@@ -48,6 +48,8 @@ PROTOTYPES = {
                                        _P, _I, _P, _I, _P, _P]),
     "cvcl_feat_grad_norm_bwd": (c_int, [_P, _I, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _I, _I, _I,
                                         _F, _P, _I, _P, _I, _P, _P]),
+    "cvcl_feat_grad_norm_bwd_ws": (c_int, [_P, _I, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _I, _I, _I,
+                                           _F, _P, _I, _P, _I, _P, _P, _P]),
     "cvcl_head_weight_grad": (c_int, [_P, _I, _P, _I, _I, _I, _I, _P, _I, _P]),
     "cvcl_gemm_f32out": (c_int, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _F, _P, _I, _P]),
     "cvcl_flat_step_workspace_bytes": (c_size_t, [_I, _I, _I, _I, _I]),

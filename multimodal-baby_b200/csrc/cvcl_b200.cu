@@ -87,7 +87,10 @@ int cvcl_text_encoder_fwd(const int64_t* ids, const int64_t* lens, const float* 
     p.feat_bf16 = static_cast<__nv_bfloat16*>(feat_bf16); p.ld_bf16 = ld_bf16;
     p.inv_norm = inv_norm; p.tok_f32 = tok_f32; p.tok_bf16 = static_cast<__nv_bfloat16*>(tok_bf16);
     p.status = status;
-    CVCL_CHECK_CUDA(launch_pdl(text_encoder_fwd_kernel, dim3(warps_grid(B, 128)), dim3(128), 0, as_stream(stream), p));
+    if (!per_token && E <= 512 && B <= 4096)      // small batch: block per utterance, 8 rows in flight per lane
+        CVCL_CHECK_CUDA(launch_pdl(text_encoder_flat_wide_kernel, dim3(B), dim3(128), 0, as_stream(stream), p));
+    else
+        CVCL_CHECK_CUDA(launch_pdl(text_encoder_fwd_kernel, dim3(warps_grid(B, 128)), dim3(128), 0, as_stream(stream), p));
     count_launch();
     return CVCL_OK;
 }
@@ -381,7 +384,54 @@ int cvcl_feat_grad_norm_bwd(const void* Gs, int ldg, int gs_transposed, const vo
                             int normalize, const int64_t* row_len, const void* diag_feat, int ld_diag,
                             int diag_rows, int diag_off, float diag_coef, float* out_f32, int ld_f32,
                             void* out_bf16, int ld_bf16, float* dbias, void* stream) {
+    return cvcl_feat_grad_norm_bwd_ws(Gs, ldg, gs_transposed, other, ld_other, M, E, Kc, feat_bf16, ld_feat, inv_norm,
+                                      normalize, row_len, diag_feat, ld_diag, diag_rows, diag_off, diag_coef, out_f32,
+                                      ld_f32, out_bf16, ld_bf16, dbias, nullptr, stream);
+}
+
+int cvcl_feat_grad_norm_bwd_ws(const void* Gs, int ldg, int gs_transposed, const void* other, int ld_other,
+                               int M, int E, int Kc, const void* feat_bf16, int ld_feat, const float* inv_norm,
+                               int normalize, const int64_t* row_len, const void* diag_feat, int ld_diag,
+                               int diag_rows, int diag_off, float diag_coef, float* out_f32, int ld_f32,
+                               void* out_bf16, int ld_bf16, float* dbias, float* acc_scratch, void* stream) {
     CVCL_REQUIRE(Gs && other, "feat_grad_norm_bwd: null operand");
+    {
+        // Long contraction (sharded global batch: Kc = world * b) on few output tiles: every CTA of the
+        // single-kernel path would stream all of Kc serially (0.3 us per 64-wide chunk).  Split the
+        // contraction over blockIdx.z into an fp32 accumulator (vector atomics), then one warp-per-row
+        // pass applies the diagonal term, the normalise backward, 1/len and the bias column sums.
+        float* acc = acc_scratch ? acc_scratch : out_f32;
+        const int ld_acc = acc_scratch ? E : ld_f32;
+        const int tiles = ceil_div(M, kBM) * ceil_div(E, kBN);
+        const int chunks = ceil_div(Kc, kBK);
+        if (acc && chunks >= 24 && tiles * 2 <= sm_count() && E % 4 == 0 && ld_acc % 4 == 0 && E <= 128 * kMaxVec &&
+            (reinterpret_cast<uintptr_t>(acc) & 15) == 0 && (ld_feat % 4 == 0) && (ld_diag % 4 == 0 || !diag_feat) &&
+            (out_f32 != nullptr) != (out_bf16 != nullptr) && (!normalize || (feat_bf16 && inv_norm))) {
+            int splits = sm_count() / tiles;
+            if (splits > chunks / 6) splits = chunks / 6;
+            while (splits > 1 && ceil_div(chunks, splits) * (splits - 1) >= chunks) --splits;
+            if (splits > 1) {
+                cudaStream_t st = as_stream(stream);
+                CVCL_CHECK_CUDA(cudaMemsetAsync(acc, 0, sizeof(float) * static_cast<size_t>(M) * ld_acc, st));
+                GemmOperands op{}; op.ndir = 1;
+                op.A[0] = gs_transposed ? mat(Gs, Kc, M, ldg) : mat(Gs, M, Kc, ldg);
+                op.B[0] = mat(other, Kc, E, ld_other);
+                GemmShape gs{}; gs.M[0] = gs.M[1] = M; gs.N[0] = gs.N[1] = E; gs.K = Kc; gs.m_stride = kBM; gs.n_stride = kBN;
+                gs.k_splits = splits;
+                EpiAtomicAddF32::Params ea{}; ea.C = acc; ea.ldc = ld_acc; ea.alpha = 1.f;
+                int rc = gs_transposed ? launch_gemm<kBN, 3, EpiAtomicAddF32, true, true>(op, gs, ea, 1, st)
+                                       : launch_gemm<kBN, 3, EpiAtomicAddF32, false, true>(op, gs, ea, 1, st);
+                if (rc) return rc;
+                CVCL_CHECK_CUDA(launch_pdl(featgrad_finish_kernel, dim3(warps_grid(M)), dim3(256), 0, st, acc, ld_acc,
+                                           static_cast<const __nv_bfloat16*>(feat_bf16), ld_feat,
+                                           static_cast<const __nv_bfloat16*>(diag_feat), ld_diag, diag_rows, diag_off,
+                                           diag_coef, inv_norm, normalize, reinterpret_cast<const long long*>(row_len), M, E,
+                                           out_f32, ld_f32, static_cast<__nv_bfloat16*>(out_bf16), ld_bf16, dbias));
+                count_launch();
+                return CVCL_OK;
+            }
+        }
+    }
     CVCL_REQUIRE((out_f32 != nullptr) != (out_bf16 != nullptr), "feat_grad_norm_bwd: exactly one of out_f32 / out_bf16");
     CVCL_REQUIRE(!normalize || (feat_bf16 && inv_norm), "feat_grad_norm_bwd: normalize needs feat and inv_norm");
     CVCL_REQUIRE(feat_bf16 || diag_feat, "feat_grad_norm_bwd: needs feat or diag_feat (use cvcl_gemm_f32out otherwise)");
@@ -448,11 +498,13 @@ namespace {
 // dI || dT, dW || embedding scatter.  One side stream + 4 events per host thread, created lazily.
 struct SideStream {
     cudaStream_t s = nullptr;
+    cudaStream_t s2 = nullptr;        // gradient-buffer memset branch (4.8 MB, needed only by the backward)
     cudaEvent_t fork[3] = {nullptr, nullptr, nullptr}, join[3] = {nullptr, nullptr, nullptr};
     bool ok = false;
     int init() {
         if (ok) return CVCL_OK;
         CVCL_CHECK_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        CVCL_CHECK_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
         for (int i = 0; i < 3; ++i) {
             CVCL_CHECK_CUDA(cudaEventCreateWithFlags(&fork[i], cudaEventDisableTiming));
             CVCL_CHECK_CUDA(cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming));
@@ -525,14 +577,16 @@ int cvcl_flat_contrastive_step(const void* x, int x_is_bf16, const int64_t* ids,
         CVCL_CHECK_CUDA(cudaMemsetAsync(sw.rb_ticket, 0, sizeof(unsigned int) * (1 + sw.tiles_m[0] + sw.tiles_m[1]), ss.s));
     }
     CVCL_CHECK_CUDA(cudaEventRecord(ss.fork[2], ss.s));          // head GEMM (split-K atomics) waits for this only
-    if (need_grads) {
+    if (need_grads) {          // third branch: nothing before the backward reads these
+        CVCL_CHECK_CUDA(cudaStreamWaitEvent(ss.s2, ss.fork[0], 0));
         if (dbias == dscale + 4 && dtable == dbias + E) {
-            CVCL_CHECK_CUDA(cudaMemsetAsync(dscale, 0, sizeof(float) * (4 + E + static_cast<size_t>(V) * E), ss.s));
+            CVCL_CHECK_CUDA(cudaMemsetAsync(dscale, 0, sizeof(float) * (4 + E + static_cast<size_t>(V) * E), ss.s2));
         } else {
-            CVCL_CHECK_CUDA(cudaMemsetAsync(dscale, 0, sizeof(float), ss.s));
-            CVCL_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * E, ss.s));
-            CVCL_CHECK_CUDA(cudaMemsetAsync(dtable, 0, sizeof(float) * static_cast<size_t>(V) * E, ss.s));
+            CVCL_CHECK_CUDA(cudaMemsetAsync(dscale, 0, sizeof(float), ss.s2));
+            CVCL_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * E, ss.s2));
+            CVCL_CHECK_CUDA(cudaMemsetAsync(dtable, 0, sizeof(float) * static_cast<size_t>(V) * E, ss.s2));
         }
+        CVCL_CHECK_CUDA(cudaEventRecord(ss.join[2], ss.s2));
     }
     if ((rc = cvcl_text_encoder_fwd(ids, lens, table, B, L, E, V, normalize, 0, 1.f, txt_feat_f32, f.txt16, E,
                                     f.invn_t, nullptr, nullptr, status, side))) return rc;
@@ -555,6 +609,7 @@ int cvcl_flat_contrastive_step(const void* x, int x_is_bf16, const int64_t* ids,
                                    true))) return rc;
     if (!need_grads) return CVCL_OK;
     // ---- K5: Gs (one orientation) -> dI (K-major Gs, main) || dT (the same Gs read MN-major, side)
+    CVCL_CHECK_CUDA(cudaStreamWaitEvent(st, ss.join[2], 0));     // gradient accumulators are zero (ds is the first user)
     const float coef = 0.5f / static_cast<float>(B);
     if ((rc = cvcl_sim_infonce_bwd_g(f.img16, f.txt16, nullptr, nullptr, E, B, B, 0, 0, E, log_scale, 0, coef,
                                      f.lse0, f.lse1, nullptr, nullptr, f.G0, f.ldB, nullptr, 0, dscale, stream))) return rc;

@@ -188,6 +188,62 @@ __global__ void __launch_bounds__(128) text_encoder_fwd_kernel(const TextFwdPara
     }
 }
 
+// K1, flat, small batches (E <= 512): one 128-thread block per utterance instead of one warp.  Warp w
+// owns the 128-column slice w (one float4 per lane), so 8 token rows are in flight per lane and an
+// utterance's rows arrive in one or two round trips instead of len/4: at B = 512 the warp-per-utterance
+// form is bound by those serial round trips (512 warps on 148 SMs), not by bandwidth.  Per element the
+// additions happen in the same (position) order as in the kernel above.
+__global__ void __launch_bounds__(128) text_encoder_flat_wide_kernel(const TextFwdParams p) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = (warp * 32 + lane) * 4;
+    const bool col_ok = e < p.E;
+    constexpr int kInFlight = 8;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const long long* idrow = p.ids + static_cast<size_t>(b) * p.L;
+    for (int l0 = 0; l0 < p.L; l0 += 32) {
+        long long my_id = (l0 + lane < p.L) ? __ldg(idrow + l0 + lane) : 0;
+        if (my_id < 0 || my_id >= p.V) { if (p.status) atomicExch(p.status, 1); my_id = 0; }
+        const int nl = min(32, p.L - l0);
+        unsigned live = __ballot_sync(0xffffffffu, my_id != 0 && lane < nl);
+        while (live) {
+            float4 r[kInFlight];
+#pragma unroll
+            for (int k = 0; k < kInFlight; ++k) {
+                r[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live) {
+                    const int src_lane = __ffs(live) - 1;
+                    live &= live - 1;
+                    const long long id = __shfl_sync(0xffffffffu, my_id, src_lane);
+                    if (col_ok) r[k] = __ldg(reinterpret_cast<const float4*>(p.table + static_cast<size_t>(id) * p.E + e));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kInFlight; ++k) {           // position order, as sum(dim=1) does
+                acc.x += r[k].x; acc.y += r[k].y; acc.z += r[k].z; acc.w += r[k].w;
+            }
+        }
+    }
+    const float flen = static_cast<float>(__ldg(p.lens + b));
+    acc.x /= flen; acc.y /= flen; acc.z /= flen; acc.w /= flen;
+    // the row sum of squares is reduced in the order of the warp-per-utterance kernel: per lane over its
+    // 4 chunks (= the 4 warps here), then the butterfly over lanes
+    float part = acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+    __shared__ float s_part[4][32];
+    s_part[warp][lane] = part;
+    __syncthreads();
+    float ssq = ((0.f + s_part[0][lane]) + s_part[1][lane]) + s_part[2][lane] + s_part[3][lane];
+    ssq = warp_sum(ssq);
+    const float denom = p.normalize ? fmaxf(sqrtf(ssq), 1e-12f) : 1.f;
+    if (threadIdx.x == 0 && p.inv_norm) p.inv_norm[b] = 1.f / denom;
+    if (col_ok) {
+        const float4 t = make_float4(acc.x / denom, acc.y / denom, acc.z / denom, acc.w / denom);
+        if (p.feat_f32) *reinterpret_cast<float4*>(p.feat_f32 + static_cast<size_t>(b) * p.E + e) = t;
+        if (p.feat_bf16) store_bf16x4(p.feat_bf16 + static_cast<size_t>(b) * p.ld_bf16 + e, t);
+    }
+}
+
 // plain row gather table[ids] -> [B*L, E] fp32: the `text_outputs` tensor the reference API
 // returns (multimodal.py:496,575,584).  One warp per token row.
 __global__ void __launch_bounds__(256) embedding_gather_kernel(const long long* ids, const float* table,
@@ -651,6 +707,82 @@ __global__ void __launch_bounds__(256) rownorm_bwd_kernel(const float* g, const 
                 atomicAdd(dbias + e + 2, o.z); atomicAdd(dbias + e + 3, o.w);
             }
         }
+    }
+}
+
+// second half of the split-K feature-gradient path (long contractions: sharded global batches).
+// acc [M, E] fp32 holds Gs . other summed over the K-splits; this warp-per-row pass applies what the
+// EpiNormBwdT epilogue does in the single-kernel path, in the same order:
+//   g = acc + diag_coef * diag[m + diag_off];  du = (g - feat <feat, g>) * inv_norm;  out = du / len
+// Outputs: fp32 [M, ld_f32] (may alias acc) or bf16 [M, ld_bf16]; dbias[E] += column sums (shared-memory
+// pre-reduction over the 8 rows of a block, then one global atomic per column and block).
+__device__ __forceinline__ float4 load_bf16x4(const __nv_bfloat16* p) {
+    const uint2 q = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&q.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&q.y);
+    return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+}
+
+__global__ void __launch_bounds__(256) featgrad_finish_kernel(const float* acc, int ld_acc, const __nv_bfloat16* feat,
+                                                              int ld_feat, const __nv_bfloat16* diag, int ld_diag,
+                                                              int diag_rows, int diag_off, float diag_coef,
+                                                              const float* inv_norm, int normalize,
+                                                              const long long* row_len, int M, int E, float* out_f32,
+                                                              int ld_f32, __nv_bfloat16* out_bf16, int ld_bf16,
+                                                              float* dbias) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
+    __shared__ float s_col[128 * kMaxVec];
+    const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nch = (E + 127) >> 7;
+    if (dbias) {
+        for (int i = threadIdx.x; i < E; i += blockDim.x) s_col[i] = 0.f;
+        __syncthreads();
+    }
+    if (m < M) {
+        float4 g[kMaxVec], f[kMaxVec];
+        float dot = 0.f;
+        const bool use_diag = diag != nullptr && m + diag_off < diag_rows;
+#pragma unroll
+        for (int c = 0; c < kMaxVec; ++c) {
+            g[c] = make_float4(0.f, 0.f, 0.f, 0.f); f[c] = g[c];
+            const int e = (c * 32 + lane) * 4;
+            if (c < nch && e < E) {
+                g[c] = *reinterpret_cast<const float4*>(acc + static_cast<size_t>(m) * ld_acc + e);
+                if (use_diag) {
+                    const float4 d = load_bf16x4(diag + static_cast<size_t>(m + diag_off) * ld_diag + e);
+                    g[c].x = fmaf(diag_coef, d.x, g[c].x); g[c].y = fmaf(diag_coef, d.y, g[c].y);
+                    g[c].z = fmaf(diag_coef, d.z, g[c].z); g[c].w = fmaf(diag_coef, d.w, g[c].w);
+                }
+                if (normalize) f[c] = load_bf16x4(feat + static_cast<size_t>(m) * ld_feat + e);
+            }
+            dot = fmaf(f[c].x, g[c].x, dot); dot = fmaf(f[c].y, g[c].y, dot);
+            dot = fmaf(f[c].z, g[c].z, dot); dot = fmaf(f[c].w, g[c].w, dot);
+        }
+        dot = warp_sum(dot);
+        const float inv = normalize ? __ldg(inv_norm + m) : 1.f;
+        const float rs = row_len ? 1.f / static_cast<float>(row_len[m]) : 1.f;
+#pragma unroll
+        for (int c = 0; c < kMaxVec; ++c) {
+            const int e = (c * 32 + lane) * 4;
+            if (c < nch && e < E) {
+                float4 o = g[c];
+                if (normalize)
+                    o = make_float4((g[c].x - f[c].x * dot) * inv, (g[c].y - f[c].y * dot) * inv,
+                                    (g[c].z - f[c].z * dot) * inv, (g[c].w - f[c].w * dot) * inv);
+                o.x *= rs; o.y *= rs; o.z *= rs; o.w *= rs;
+                if (out_f32) *reinterpret_cast<float4*>(out_f32 + static_cast<size_t>(m) * ld_f32 + e) = o;
+                if (out_bf16) store_bf16x4(out_bf16 + static_cast<size_t>(m) * ld_bf16 + e, o);
+                if (dbias) {
+                    atomicAdd(s_col + e, o.x); atomicAdd(s_col + e + 1, o.y);
+                    atomicAdd(s_col + e + 2, o.z); atomicAdd(s_col + e + 3, o.w);
+                }
+            }
+        }
+    }
+    if (dbias) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < E; i += blockDim.x) atomicAdd(dbias + i, s_col[i]);
     }
 }
 

@@ -696,6 +696,9 @@ def flat_step_sharded(x, ids, lens, w, bias, table, log_scale, normalize, need_g
     with torch.cuda.stream(side):
         C("cvcl_text_encoder_fwd", _p(ids), _p(lens), _p(table), B, L, E, V, int(normalize), 0, 1.0,
           _p(txt_f), _p(txt_l), 2 * E, _p(invn_t), None, None, None, side.cuda_stream)
+    zero = _side_stream(dev, 1)          # third branch: the 9.6 MB accumulator memset is off both critical paths
+    zero.wait_stream(main)
+    with torch.cuda.stream(zero):
         stats.zero_()
     w16 = torch.empty((E, K), **bf)
     C("cvcl_cast_transpose", _p(w), 0, _p(w16), None, 1, E, K, K, K, 0, 0, 0, 0, st)
@@ -705,12 +708,14 @@ def flat_step_sharded(x, ids, lens, w, bias, table, log_scale, normalize, need_g
       _p(img_l), 2 * E, _p(invn_i), st)
     main.wait_stream(side)
     if phase_limit == 1:
+        main.wait_stream(zero)
         return stats, img_f, txt_f
     if px is not None:       # one kernel: 16-byte stores into every rank's gathered buffer (NVLink) + barrier
         feats_all = px.gather_feats(st)
     else:
         feats_all = sharding.all_gather_rows(feats, group, world)      # [Bg, 2E] (NCCL)
     img_a, txt_a = feats_all[:, :E], feats_all[:, E:]
+    main.wait_stream(zero)               # the similarity kernel accumulates out5 into stats[0:8]
     if phase_limit == 2:
         return stats, img_f, txt_f
     ws = torch.empty((lib.cvcl_sim_workspace_bytes(B, Bg, B, Bg),), dtype=torch.uint8, device=dev)
@@ -747,8 +752,10 @@ def flat_step_sharded(x, ids, lens, w, bias, table, log_scale, normalize, need_g
             C("cvcl_feat_grad_norm_bwd", _p(G1), ldg, 0, _p(img_a), 2 * E, B, E, Bg, _p(txt_l), 2 * E, _p(invn_t),
               int(normalize), _p(lens), _p(img_a), 2 * E, Bg, rank * B, dcoef, _p(dm), E, None, 0, None, ss)
             C("cvcl_embedding_scatter_add", _p(ids), _p(dm), _p(dtable), B, L, E, V, 0, ss)
-        C("cvcl_feat_grad_norm_bwd", _p(G0), ldg, 0, _p(txt_a), 2 * E, B, E, Bg, _p(img_l), 2 * E, _p(invn_i),
-          int(normalize), None, _p(txt_a), 2 * E, Bg, rank * B, dcoef, None, 0, _p(du16), E, _p(db), st)
+        # long contraction (Bg >= 1536): the library splits it over the SMs into this fp32 scratch
+        acc_i = torch.empty((B, E), **f32) if Bg >= 1536 else None
+        C("cvcl_feat_grad_norm_bwd_ws", _p(G0), ldg, 0, _p(txt_a), 2 * E, B, E, Bg, _p(img_l), 2 * E, _p(invn_i),
+          int(normalize), None, _p(txt_a), 2 * E, Bg, rank * B, dcoef, None, 0, _p(du16), E, _p(db), _p(acc_i), st)
         C("cvcl_head_weight_grad", _p(du16), E, _p(x16), K, E, K, B, _p(dW), K, st)
         main.wait_stream(side)        # every side-stream use is ordered before anything that follows
     if phase_limit == 6:
@@ -764,8 +771,8 @@ def flat_step_sharded(x, ids, lens, w, bias, table, log_scale, normalize, need_g
 _SIDE_STREAMS = {}
 
 
-def _side_stream(dev):
-    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+def _side_stream(dev, which=0):
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device(), which)
     s = _SIDE_STREAMS.get(key)
     if s is None:
         s = _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
