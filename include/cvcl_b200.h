@@ -218,7 +218,8 @@ int cvcl_p2p_gather(const void* const* peer_ptrs, int world, int skip_rank, long
  * symmetric memory.  A channel's flag area holds cvcl_peer_flag_words() uint32 words, zeroed once
  * before first use (followed by any cross-rank barrier); `epoch` is a LOCAL uint32 array of
  * cvcl_peer_max_blocks() words, zeroed once; `status` (local int, nullable) becomes non-zero if a
- * barrier did not complete within timeout_ms (0 = 10 s), after which the kernel traps.  All ranks
+ * barrier did not complete within timeout_ms (0 = 10 s), after which the kernel traps (or, with
+ * CVCL_PEER_NO_TRAP or'ed into timeout_ms, continues: probe mode, results undefined).  All ranks
  * must issue the same sequence of calls per channel with the same sizes.  Graph capturable.
  *   allgather    : barrier, then dst[s*dst_seg_stride + r*seg_bytes ..] <- segment s (at
  *                  s*src_seg_stride) of rank r's block, for all r (including the caller's own) and s.
@@ -234,6 +235,7 @@ int cvcl_p2p_gather(const void* const* peer_ptrs, int world, int skip_rank, long
  *                  (cvcl_peer_allreduce_scratch_bytes, peer-mapped), barriers, sums its own slice locally
  *                  in rank order, stores the sum into every rank's buffer, barriers.  Both are launched
  *                  with programmatic dependent launch (their launch overlaps the tail of the previous kernel). */
+#define CVCL_PEER_NO_TRAP 0x80000000u
 size_t cvcl_peer_flag_words(void);
 int cvcl_peer_max_blocks(void);
 int cvcl_peer_allgather(void* const* peer_data, void* const* peer_flags, unsigned int* epoch, int* status, int world,

@@ -566,6 +566,10 @@ int cvcl_flat_contrastive_step(const void* x, int x_is_bf16, const int64_t* ids,
     int rc;
     if ((rc = ss.init())) return rc;
     void* side = ss.s;
+    // measurement hook (tools/step_phases.py): stop after phase k of {1 encoders, 2 similarity + InfoNCE,
+    // 3 Gs, 4 dI and dT}; 11 / 12 run only the head chain / only the text encoder of phase 1
+    int limit = 0;
+    if (const char* e = getenv("CVCL_B200_STEP_PHASES")) limit = atoi(e);
     // ---- forward: [memsets -> text encoder] (side) || [cast W -> head GEMM] (main)
     CVCL_CHECK_CUDA(cudaEventRecord(ss.fork[0], st));
     CVCL_CHECK_CUDA(cudaStreamWaitEvent(ss.s, ss.fork[0], 0));
@@ -588,9 +592,14 @@ int cvcl_flat_contrastive_step(const void* x, int x_is_bf16, const int64_t* ids,
         }
         CVCL_CHECK_CUDA(cudaEventRecord(ss.join[2], ss.s2));
     }
-    if ((rc = cvcl_text_encoder_fwd(ids, lens, table, B, L, E, V, normalize, 0, 1.f, txt_feat_f32, f.txt16, E,
-                                    f.invn_t, nullptr, nullptr, status, side))) return rc;
+    if (limit != 11 && (rc = cvcl_text_encoder_fwd(ids, lens, table, B, L, E, V, normalize, 0, 1.f, txt_feat_f32, f.txt16, E,
+                                                   f.invn_t, nullptr, nullptr, status, side))) return rc;
     CVCL_CHECK_CUDA(cudaEventRecord(ss.join[0], ss.s));
+    if (limit == 12) {
+        CVCL_CHECK_CUDA(cudaStreamWaitEvent(st, ss.join[0], 0));
+        if (need_grads) CVCL_CHECK_CUDA(cudaStreamWaitEvent(st, ss.join[2], 0));
+        return CVCL_OK;
+    }
     if ((rc = cvcl_cast_transpose(w, 0, f.w16, nullptr, 1, E, K, K, K, 0, 0, 0, 0, stream))) return rc;
     const void* x16 = x;
     if (!x_is_bf16 || (reinterpret_cast<uintptr_t>(x) & 15)) {
@@ -603,6 +612,10 @@ int cvcl_flat_contrastive_step(const void* x, int x_is_bf16, const int64_t* ids,
     head_scratch_zeroed() = false;
     if (rc) return rc;
     CVCL_CHECK_CUDA(cudaStreamWaitEvent(st, ss.join[0], 0));
+    if (limit == 1 || limit == 11) {
+        if (need_grads) CVCL_CHECK_CUDA(cudaStreamWaitEvent(st, ss.join[2], 0));
+        return CVCL_OK;
+    }
     // ---- K3 + K4
     if ((rc = sim_infonce_fwd_impl(f.img16, f.txt16, f.txt16, f.img16, E, B, B, B, B, E, log_scale, 0,
                                    1.f / static_cast<float>(B), f.sim, f.lse0, f.lse1, nullptr, nullptr, out5, stream,
@@ -610,20 +623,22 @@ int cvcl_flat_contrastive_step(const void* x, int x_is_bf16, const int64_t* ids,
     if (!need_grads) return CVCL_OK;
     // ---- K5: Gs (one orientation) -> dI (K-major Gs, main) || dT (the same Gs read MN-major, side)
     CVCL_CHECK_CUDA(cudaStreamWaitEvent(st, ss.join[2], 0));     // gradient accumulators are zero (ds is the first user)
+    if (limit == 2) return CVCL_OK;
     const float coef = 0.5f / static_cast<float>(B);
     if ((rc = cvcl_sim_infonce_bwd_g(f.img16, f.txt16, nullptr, nullptr, E, B, B, 0, 0, E, log_scale, 0, coef,
                                      f.lse0, f.lse1, nullptr, nullptr, f.G0, f.ldB, nullptr, 0, dscale, stream))) return rc;
     const float dcoef = -2.f * expf(log_scale) * coef;
+    if (limit == 3) return CVCL_OK;
     CVCL_CHECK_CUDA(cudaEventRecord(ss.fork[1], st));
     CVCL_CHECK_CUDA(cudaStreamWaitEvent(ss.s, ss.fork[1], 0));
     if ((rc = cvcl_feat_grad_norm_bwd(f.G0, f.ldB, 1, f.img16, E, B, E, B, f.txt16, E, f.invn_t, normalize,
                                       lens, f.img16, E, B, 0, dcoef, f.dm, E, nullptr, 0, nullptr, side))) return rc;
     // ... then the embedding scatter follows dT on the side stream while dI -> dW run on the main one
-    if ((rc = cvcl_embedding_scatter_add(ids, f.dm, dtable, B, L, E, V, 0, side))) return rc;
+    if (limit != 4 && (rc = cvcl_embedding_scatter_add(ids, f.dm, dtable, B, L, E, V, 0, side))) return rc;
     CVCL_CHECK_CUDA(cudaEventRecord(ss.join[1], ss.s));
     if ((rc = cvcl_feat_grad_norm_bwd(f.G0, f.ldB, 0, f.txt16, E, B, E, B, f.img16, E, f.invn_i, normalize,
                                       nullptr, f.txt16, E, B, 0, dcoef, nullptr, 0, f.du16, E, dbias, stream))) return rc;
-    if ((rc = cvcl_head_weight_grad(f.du16, E, x16, K, E, K, B, dW, K, stream))) return rc;
+    if (limit != 4 && (rc = cvcl_head_weight_grad(f.du16, E, x16, K, E, K, B, dW, K, stream))) return rc;
     CVCL_CHECK_CUDA(cudaStreamWaitEvent(st, ss.join[1], 0));
     return CVCL_OK;
 }
@@ -745,7 +760,8 @@ int fill_peer_table(PeerTable* t, void* const* peer_data, void* const* peer_flag
             t->data[r] = peer_data[r];
         }
     }
-    t->epoch = epoch; t->status = status; t->timeout_ms = timeout_ms ? timeout_ms : 10000u;
+    t->epoch = epoch; t->status = status;
+    t->timeout_ms = (timeout_ms & 0x7fffffffu) ? timeout_ms : ((timeout_ms & 0x80000000u) | 10000u);
     return CVCL_OK;
 }
 }  // namespace
@@ -890,7 +906,21 @@ int cvcl_eval_nway_fwd(const float* img, const float* txt, const int* txt_index,
     CVCL_REQUIRE(n_trials >= 0 && n_way > 0, "eval_nway_fwd: bad shape");
     CVCL_REQUIRE(E > 0 && E % 4 == 0 && E <= 128 * kMaxVec, "eval_nway_fwd: bad E=%d", E);
     if (n_trials == 0) return CVCL_OK;
-    if (n_way == 4 && E <= 512)
+    if (n_way == 4 && E <= 512 && n_trials >= 4096 && (reinterpret_cast<uintptr_t>(img) & 15) == 0) {
+        // streaming form: persistent blocks, 32 KB stages filled by bulk async copies
+        const int smem = 128 + kEvalStages * kEvalGroup * 4 * E * 4;
+        static thread_local bool attr_done = false;
+        if (!attr_done) {
+            CVCL_CHECK_CUDA(cudaFuncSetAttribute(eval_nway_stream_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 128 + kEvalStages * kEvalGroup * 4 * 512 * 4));
+            attr_done = true;
+        }
+        const int n_groups = ceil_div(n_trials, kEvalGroup);
+        const int grid = n_groups < 2 * sm_count() ? n_groups : 2 * sm_count();
+        CVCL_CHECK_CUDA(launch_pdl(eval_nway_stream_kernel<4>, dim3(grid), dim3(32 * (kEvalGroup + 1)), smem,
+                                   as_stream(stream), img, txt, txt_index, n_trials, E, normalize, expf(log_scale), pred,
+                                   logits));
+    } else if (n_way == 4 && E <= 512)
         CVCL_CHECK_CUDA(launch_pdl(eval_nway_kernel<4>, dim3(warps_grid(n_trials)), dim3(256), 0, as_stream(stream), img, txt, txt_index, n_trials, n_way, E, normalize, expf(log_scale), pred, logits));
     else
         CVCL_CHECK_CUDA(launch_pdl(eval_nway_kernel<0>, dim3(warps_grid(n_trials)), dim3(256), 0, as_stream(stream), img, txt, txt_index, n_trials, n_way, E, normalize, expf(log_scale), pred, logits));

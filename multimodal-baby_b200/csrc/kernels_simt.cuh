@@ -436,35 +436,12 @@ __global__ void __launch_bounds__(256) infonce_finalize_kernel(const FinalizePar
 // label embedding are L2-normalised, dotted, scaled; pred = argmax (first maximal index).
 // One warp per trial; E <= 1024.
 // --------------------------------------------------------------------------------------
-template <int kWays>      // kWays > 0: all candidate rows are fetched before any reduction (MLP)
-__global__ void __launch_bounds__(256) eval_nway_kernel(const float* img, const float* txt,
-                                                        const int* txt_index, int n_trials, int n_way,
-                                                        int E, int normalize, float scale, int* pred,
-                                                        float* logits) {
-    ptx::pdl_launch_dependents(); ptx::pdl_wait();
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= n_trials) return;
-    const int ti = txt_index ? __ldg(txt_index + warp) : warp;
-    const float4* tsrc = reinterpret_cast<const float4*>(txt + static_cast<size_t>(ti) * E);
+// per-trial arithmetic of K7 on register-resident rows (x: kWays candidate rows, t: label row; 4 float4 per
+// lane each): screen on raw dots, exact reference arithmetic for near-ties / NaNs / requested logits.
+template <int kWays>
+__device__ __forceinline__ void eval_trial_from_regs(float4 (&x)[kWays][4], float4 (&t)[4], int trial, int lane,
+                                                     int normalize, float scale, int* pred, float* logits) {
     float best = -INFINITY; int arg = 0;
-    if constexpr (kWays > 0) {
-        // E <= 512: 4 float4 per lane per row; kWays image rows + the text row in flight together
-        float4 t[4], x[kWays][4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            t[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if ((c * 32 + lane) * 4 < E) t[c] = __ldg(tsrc + c * 32 + lane);
-        }
-#pragma unroll
-        for (int w = 0; w < kWays; ++w) {
-            const float4* isrc = reinterpret_cast<const float4*>(img + (static_cast<size_t>(warp) * kWays + w) * E);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                x[w][c] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if ((c * 32 + lane) * 4 < E) x[w][c] = __ldg(isrc + c * 32 + lane);
-            }
-        }
         float tss = 0.f;
 #pragma unroll
         for (int c = 0; c < 4; ++c) tss += t[c].x * t[c].x + t[c].y * t[c].y + t[c].z * t[c].z + t[c].w * t[c].w;
@@ -502,7 +479,7 @@ __global__ void __launch_bounds__(256) eval_nway_kernel(const float* img, const 
                 if (v > b1) { b2 = b1; b1 = v; a1 = w; } else if (v > b2) { b2 = v; }
             }
             if (b1 - b2 > 1e-4f) {            // false for NaN / inf: those go through the exact path
-                if (lane == 0) pred[warp] = a1;
+                if (lane == 0) pred[trial] = a1;
                 return;
             }
         }
@@ -526,9 +503,43 @@ __global__ void __launch_bounds__(256) eval_nway_kernel(const float* img, const 
                 dot = fmaf(x[w][c].z / d, t[c].z, dot); dot = fmaf(x[w][c].w / d, t[c].w, dot);
             }
             dot = warp_sum(dot) * scale;
-            if (logits && lane == 0) logits[static_cast<size_t>(warp) * kWays + w] = dot;
+            if (logits && lane == 0) logits[static_cast<size_t>(trial) * kWays + w] = dot;
             if (dot > best) { best = dot; arg = w; }
         }
+    if (lane == 0) pred[trial] = arg;
+}
+
+template <int kWays>      // kWays > 0: all candidate rows are fetched before any reduction (MLP)
+__global__ void __launch_bounds__(256) eval_nway_kernel(const float* img, const float* txt,
+                                                        const int* txt_index, int n_trials, int n_way,
+                                                        int E, int normalize, float scale, int* pred,
+                                                        float* logits) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n_trials) return;
+    const int ti = txt_index ? __ldg(txt_index + warp) : warp;
+    const float4* tsrc = reinterpret_cast<const float4*>(txt + static_cast<size_t>(ti) * E);
+    float best = -INFINITY; int arg = 0;
+    if constexpr (kWays > 0) {
+        // E <= 512: 4 float4 per lane per row; kWays image rows + the text row in flight together
+        float4 t[4], x[kWays][4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            t[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if ((c * 32 + lane) * 4 < E) t[c] = __ldg(tsrc + c * 32 + lane);
+        }
+#pragma unroll
+        for (int w = 0; w < kWays; ++w) {
+            const float4* isrc = reinterpret_cast<const float4*>(img + (static_cast<size_t>(warp) * kWays + w) * E);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                x[w][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if ((c * 32 + lane) * 4 < E) x[w][c] = __ldg(isrc + c * 32 + lane);
+            }
+        }
+        eval_trial_from_regs<kWays>(x, t, warp, lane, normalize, scale, pred, logits);
+        return;
     } else {
         const int nch = (E + 127) >> 7;
         float4 t[kMaxVec];
@@ -568,6 +579,86 @@ __global__ void __launch_bounds__(256) eval_nway_kernel(const float* img, const 
         }
     }
     if (lane == 0) pred[warp] = arg;
+}
+
+// K7, streaming form for large trial counts: persistent blocks, the candidate rows of kEvalGroup
+// consecutive trials (contiguous in memory: kEvalGroup * n_way * E floats) arrive by ONE bulk async copy
+// (cp.async.bulk, mbarrier complete_tx) into a ring of shared-memory stages filled by a producer warp,
+// so HBM reads never pause while the consumer warps reduce: warp w owns trial w of a stage.  The
+// warp-per-trial kernel above loads, then reduces, then loads again in lockstep waves (47 % of the HBM
+// peak on 100 000 frames); this one keeps kStages * 32 KB per block in flight all the time.
+// Arithmetic per trial is the same as eval_nway_kernel<kWays> (screen + exact path).
+constexpr int kEvalGroup = 4;          // trials per stage = consumer warps
+constexpr int kEvalStages = 3;
+
+template <int kWays>
+__global__ void __launch_bounds__(32 * (kEvalGroup + 1)) eval_nway_stream_kernel(
+        const float* img, const float* txt, const int* txt_index, int n_trials, int E, int normalize, float scale,
+        int* pred, float* logits) {
+    extern __shared__ __align__(128) unsigned char eval_smem[];
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t trial_bytes = static_cast<uint32_t>(kWays) * E * 4u;
+    const uint32_t stage_bytes = kEvalGroup * trial_bytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(eval_smem);
+    uint64_t* empty = full + kEvalStages;
+    unsigned char* ring = eval_smem + 128;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kEvalStages; ++s) { ptx::mbar_init(full + s, 1); ptx::mbar_init(empty + s, kEvalGroup); }
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();
+    const int n_groups = (n_trials + kEvalGroup - 1) / kEvalGroup;
+    if (warp == kEvalGroup) {                      // producer warp: one elected lane issues the copies
+        if (lane == 0) {
+            int it = 0;
+            for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++it) {
+                const int s = it % kEvalStages;
+                if (it >= kEvalStages) ptx::mbar_wait(empty + s, ((it / kEvalStages) - 1) & 1);
+                const int t0 = g * kEvalGroup;
+                const int nt = min(kEvalGroup, n_trials - t0);
+                const uint32_t bytes = static_cast<uint32_t>(nt) * trial_bytes;
+                ptx::mbar_arrive_expect_tx(full + s, bytes);
+                ptx::bulk_load_1d(ring + static_cast<size_t>(s) * stage_bytes,
+                                  img + static_cast<size_t>(t0) * kWays * E, bytes, full + s);
+            }
+        }
+        return;
+    }
+    int it = 0;
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++it) {
+        const int s = it % kEvalStages;
+        const int trial = g * kEvalGroup + warp;
+        // the label row comes from L2 (22 rows shared by every trial) while the stage lands
+        float4 t[4];
+        if (trial < n_trials) {
+            const int ti = txt_index ? __ldg(txt_index + trial) : trial;
+            const float4* tsrc = reinterpret_cast<const float4*>(txt + static_cast<size_t>(ti) * E);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                t[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if ((c * 32 + lane) * 4 < E) t[c] = __ldg(tsrc + c * 32 + lane);
+            }
+        }
+        ptx::mbar_wait(full + s, (it / kEvalStages) & 1);
+        if (trial < n_trials) {
+            const float4* rows = reinterpret_cast<const float4*>(ring + static_cast<size_t>(s) * stage_bytes +
+                                                                 static_cast<size_t>(warp) * trial_bytes);
+            float4 x[kWays][4];
+#pragma unroll
+            for (int w = 0; w < kWays; ++w)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    x[w][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if ((c * 32 + lane) * 4 < E) x[w][c] = rows[w * (E >> 2) + c * 32 + lane];
+                }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(empty + s);          // rows are in registers: release the stage
+            eval_trial_from_regs<kWays>(x, t, trial, lane, normalize, scale, pred, logits);
+        } else {
+            if (lane == 0) ptx::mbar_arrive(empty + s);
+        }
+    }
 }
 
 // contiguous fp32 -> bf16 cast, 8 elements per thread (two 16-byte loads, one 16-byte store)

@@ -18,7 +18,8 @@
 //                rank's buffer -> end barrier.  In place, deterministic, two NVLink traversals.
 //
 // A barrier that does not complete within timeout_ms sets *status and traps (the step fails loudly
-// instead of hanging the device).
+// instead of hanging the device); with CVCL_PEER_NO_TRAP or'ed into timeout_ms it only sets *status and
+// goes on (the start-up self-test of sharding.PeerExchange uses this to decide for or against the path).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -79,9 +80,10 @@ __device__ __forceinline__ void barrier(const PeerTable& t, int world, int rank,
             if ((++it & 255u) == 0) {
                 const unsigned long long now = globaltimer_ns();
                 if (t0 == 0) t0 = now;
-                else if (now - t0 > static_cast<unsigned long long>(t.timeout_ms) * 1000000ull) {
+                else if (now - t0 > static_cast<unsigned long long>(t.timeout_ms & 0x7fffffffu) * 1000000ull) {
                     if (t.status) atomicExch(t.status, 1 + phase);
                     __threadfence_system();
+                    if (t.timeout_ms & 0x80000000u) break;      // probe mode: report through *status, do not trap
                     __trap();
                 }
             }

@@ -69,6 +69,15 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
           "r"(c0), "r"(c1) : "memory");
 }
 
+// 1-D bulk copy global -> shared (no tensor map): `bytes` contiguous bytes, 16-byte aligned on both
+// sides, a multiple of 16; completion is signalled on the mbarrier (complete_tx).
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gmem_src)), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
 // 2-D tiled store shared -> global (bulk async group); out-of-bounds box elements are clipped.
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c0,
                                              int32_t c1) {

@@ -199,11 +199,11 @@ class MultiModalLitModel(_Base):
     # -- batched n-way evaluation (replaces the per-trial loop, eval.py:175-266) -----------------
     @torch.no_grad()
     def evaluate_trials(self, trial_features, label_ids, label_lens, label_index=None, n_way=4,
-                        from_trunk_boundary=True):
+                        from_trunk_boundary=True, want_logits=True):
         """trial_features: [N, n_way, 2048] trunk-boundary activations (target first) or, with
         from_trunk_boundary=False, [N, n_way, E] head outputs before normalisation.
         label_ids / label_lens: [C, L] / [C] token rows; label_index [N] picks the row per trial
-        (None: C == N).  Returns (pred int32 [N], logits fp32 [N, n_way]); fp32 end to end."""
+        (None: C == N).  Returns (pred int32 [N], logits fp32 [N, n_way] | empty); fp32 end to end."""
         m = self.model
         table = m.text_embed.embedding.weight
         s = ops._scalar(m.logit_neg_log_temperature)
@@ -213,4 +213,4 @@ class MultiModalLitModel(_Base):
         if from_trunk_boundary:
             w, b = m._head()
             feats = torch.addmm(b.float(), feats, w.float().t())          # fp32 head (exact mode)
-        return ops.eval_nway(feats, txt, label_index, n_way, bool(m.normalize_features), s)
+        return ops.eval_nway(feats, txt, label_index, n_way, bool(m.normalize_features), s, want_logits)

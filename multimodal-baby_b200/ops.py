@@ -815,8 +815,11 @@ class _FlatContrastiveStepSharded(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------
 @torch.library.custom_op(_NS + "::eval_nway", mutates_args=())
 def eval_nway(img: Tensor, txt: Tensor, txt_index: Optional[Tensor], n_way: int, normalize: bool,
-              log_scale: float) -> Tuple[Tensor, Tensor]:
-    """img [N*n_way, E] fp32, txt [C,E] fp32, txt_index [N] int32 | None -> (pred [N] i32, logits [N,n_way])."""
+              log_scale: float, want_logits: bool = True) -> Tuple[Tensor, Tensor]:
+    """img [N*n_way, E] fp32, txt [C,E] fp32, txt_index [N] int32 | None -> (pred [N] i32, logits [N,n_way]).
+    want_logits=False returns an empty logits tensor and lets the kernel decide clear-cut trials on raw
+    dot products (one division per candidate); near-ties still go through the reference arithmetic, so
+    the predictions are the same either way."""
     _need_cuda(img, txt)
     img = _f32(img); txt = _f32(txt)
     E = img.shape[-1]
@@ -824,16 +827,17 @@ def eval_nway(img: Tensor, txt: Tensor, txt_index: Optional[Tensor], n_way: int,
     if txt_index is not None:
         txt_index = txt_index.to(torch.int32).contiguous()
     pred = torch.empty((N,), dtype=torch.int32, device=img.device)
-    logits = torch.empty((N, n_way), dtype=torch.float32, device=img.device)
+    logits = torch.empty((N, n_way) if want_logits else (0, n_way), dtype=torch.float32, device=img.device)
     _cabi.call("cvcl_eval_nway_fwd", _p(img), _p(txt), _p(txt_index), N, n_way, E, int(normalize),
-               float(log_scale), _p(pred), _p(logits), _stream())
+               float(log_scale), _p(pred), _p(logits) if want_logits else None, _stream())
     return pred, logits
 
 
 @eval_nway.register_fake
-def _(img, txt, txt_index, n_way, normalize, log_scale):
+def _(img, txt, txt_index, n_way, normalize, log_scale, want_logits=True):
     N = img.numel() // (img.shape[-1] * n_way)
-    return img.new_empty((N,), dtype=torch.int32), img.new_empty((N, n_way), dtype=torch.float32)
+    return (img.new_empty((N,), dtype=torch.int32),
+            img.new_empty((N, n_way) if want_logits else (0, n_way), dtype=torch.float32))
 
 
 # ----------------------------------------------------------------------------------------

@@ -153,6 +153,50 @@ class PeerExchange:
         self.p_feats_all, self.p_lse_all, self.p_scratch = table("feats_all"), table("lse_all"), table("scratch")
         self.p_stats = [table("stats%d" % k) for k in range(self.N_SLOTS)]
         self.p_flags = [table("flags", ch * fw * 4) for ch in range(4)]
+        self._self_test(group, dev)
+
+    NO_TRAP = 0x80000000
+
+    def _self_test(self, group, dev):
+        """Run every collective twice on known patterns with a short, non-trapping timeout and compare on
+        every rank; all ranks agree (NCCL all-reduce of the verdict) or the exchange is rejected and the
+        step keeps the NCCL collectives.  Costs a few hundred microseconds once per (group, shape)."""
+        st = torch.cuda.current_stream(dev).cuda_stream
+        keep, self.timeout_ms = self.timeout_ms, 3000 | self.NO_TRAP
+        W, r, b, E, n = self.world, self.rank, self.b, self.E, self.n_stats
+        ok = True
+        try:
+            for it in (1, 2):
+                col = torch.arange(2 * E, device=dev, dtype=torch.float32) % 7
+                self.feats.copy_((col[None, :] + (r + it)).expand(b, 2 * E))
+                self.lse.copy_(torch.arange(2 * b, device=dev, dtype=torch.float32).view(2, b) + 1000.0 * (r + it))
+                base = (torch.arange(n, device=dev, dtype=torch.float32) % 13) - 6.0
+                for k in range(self.N_SLOTS):
+                    self.stats[k].copy_(base * (r + 1 + k))
+                fa = self.gather_feats(st)
+                la = self.gather_lse(st)
+                for k in range(self.N_SLOTS):
+                    self.allreduce_stats(k, n, st)
+                self.barrier(st)
+                torch.cuda.synchronize(dev)
+                want_f = torch.cat([(col[None, :] + (q + it)).expand(b, 2 * E) for q in range(W)]).to(torch.bfloat16)
+                want_l = torch.cat([torch.arange(2 * b, device=dev, dtype=torch.float32).view(2, b) + 1000.0 * (q + it)
+                                    for q in range(W)], dim=1)
+                ok = ok and torch.equal(fa, want_f) and torch.equal(la, want_l)
+                for k in range(self.N_SLOTS):
+                    ok = ok and torch.equal(self.stats[k], base * float(sum(q + 1 + k for q in range(W))))
+            ok = ok and int(self.status.item()) == 0
+        except Exception:                        # noqa: BLE001
+            ok = False
+        verdict = torch.tensor([1 if ok else 0], device=dev, dtype=torch.int32)
+        dist.all_reduce(verdict, op=dist.ReduceOp.MIN, group=group)
+        self.timeout_ms = keep
+        if int(verdict.item()) != 1:
+            raise RuntimeError("peer-memory collectives failed their start-up self-test on this machine")
+        for k in range(self.N_SLOTS):
+            self.stats[k].zero_()
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)
 
     @classmethod
     def get(cls, group, b, E, n_stats, dev):
@@ -165,9 +209,9 @@ class PeerExchange:
         if key not in cls._cache:
             try:
                 cls._cache[key] = cls(group, b, E, n_stats, dev)
-            except Exception as exc:             # noqa: BLE001  (no symmetric memory: NCCL collectives)
-                if os.environ.get("CVCL_B200_DEBUG"):
-                    print("PeerExchange unavailable, using NCCL collectives: %r" % (exc,), flush=True)
+            except Exception as exc:             # noqa: BLE001  (no symmetric memory / failed self-test)
+                import warnings
+                warnings.warn("cvcl_b200: peer-memory exchange unavailable (%r); using the NCCL collectives" % (exc,))
                 cls._cache[key] = None
         return cls._cache[key]
 

@@ -330,6 +330,35 @@ def test_eval_nway_100k_frames_vs_oracle(cv):
         gaps = (top2[:, 0] - top2[:, 1]).abs() / top2[:, 0].abs()
         assert float(gaps.max()) < 1e-6, f"{len(mism)} argmax mismatches, fp64 top-2 rel gap {gaps.max():.3e}"
     np.testing.assert_allclose(logits.cpu().numpy(), ref_logits.numpy(), atol=2e-5)
+    # predictions only (screen on raw dots, near-ties through the reference arithmetic): identical
+    pred2, empty = cv.ops.eval_nway(t(img, DEV), t(cat, DEV), t(idx, DEV), 4, True, S_DEFAULT, False)
+    assert empty.numel() == 0 and torch.equal(pred2, pred)
+
+
+@pytest.mark.parametrize("n_trials", [4099, 4097, 64, 3])
+def test_eval_nway_ragged_counts_and_ties(cv, n_trials):
+    """trial counts that are not a multiple of the streaming kernel's stage (4 trials), with exact ties
+    (duplicated candidate rows -> first index wins, torch.argmax semantics) and zero rows."""
+    rng = np.random.RandomState(n_trials)
+    E = 512
+    img = rng.standard_normal((n_trials * 4, E)).astype(np.float32)
+    img[5] = img[4]                       # trial 1: candidates 0 and 1 identical
+    img[8:12] = 0.0                       # trial 2: all-zero candidates (norm clamp 1e-12)
+    cat = rng.standard_normal((n_trials, E)).astype(np.float32)
+    cat[1] = img[4]                       # ... and they are the best match: an exact tie at the maximum
+    ref_pred, ref_logits = O.eval_nway(t(img).reshape(n_trials, 4, E), t(cat), S_DEFAULT)
+    for want in (True, False):
+        pred, logits = cv.ops.eval_nway(t(img, DEV), t(cat, DEV), None, 4, True, S_DEFAULT, want)
+        p = pred.cpu().numpy()
+        mism = np.nonzero(p != ref_pred.numpy().astype(np.int32))[0]
+        l64 = O.eval_nway(t(img).double().reshape(n_trials, 4, E), t(cat).double(), S_DEFAULT)[1]
+        for i in mism:                    # only fp32-unresolvable gaps may differ
+            top2 = torch.topk(l64[i], 2).values
+            assert float((top2[0] - top2[1]).abs()) <= 1e-6 * max(1.0, float(top2[0].abs())), (i, l64[i])
+        if n_trials > 2:
+            assert p[1] == 0 and ref_pred[1].item() == 0 and p[2] == 0
+        if want:
+            np.testing.assert_allclose(logits.cpu().numpy(), ref_logits.numpy(), atol=2e-5)
 
 
 # ------------------------------------------------------------------------------- error behaviour

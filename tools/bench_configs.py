@@ -84,8 +84,12 @@ rec("config4_spatial_mean_b1024_fwd_bwd", ms, mn, B4, "pairs", bytes_=2 * (B4 * 
 N, C = 25000, 22
 frames = torch.randn(N * 4, E, generator=g).to(dev); cats = torch.randn(C, E, generator=g).to(dev)
 idx = torch.randint(0, C, (N,), generator=g).to(torch.int32).to(dev)
-ms, mn = timeit(lambda: m.ops.eval_nway(frames, cats, idx, 4, True, S_FIXED), 20, 3)
-rec("config5_eval_4way_100k_frames", ms, mn, N * 4, "frames", bytes_=N * 4 * E * 4, note="fp32 normalise + dot + argmax")
+ms, mn = timeit(lambda: m.ops.eval_nway(frames, cats, idx, 4, True, S_FIXED, False), 20, 3)
+rec("config5_eval_4way_100k_frames", ms, mn, N * 4, "frames", bytes_=N * 4 * E * 4,
+    note="fp32 normalise + dot + argmax -> predictions (streaming kernel: bulk async copies into a shared-memory ring)")
+ms, mn = timeit(lambda: m.ops.eval_nway(frames, cats, idx, 4, True, S_FIXED, True), 20, 3)
+rec("config5_eval_4way_100k_frames_with_logits", ms, mn, N * 4, "frames", bytes_=N * 4 * E * 4 + N * 16,
+    note="same, logits [25000,4] also written (reference arithmetic for every trial)")
 # ---------------- per-kernel at scale: text encoder, embedding scatter, projection head (+ its backward)
 from multimodal_baby_b200 import _cabi
 C = _cabi.call; P = m.ops._p
