@@ -906,7 +906,7 @@ int cvcl_eval_nway_fwd(const float* img, const float* txt, const int* txt_index,
     CVCL_REQUIRE(n_trials >= 0 && n_way > 0, "eval_nway_fwd: bad shape");
     CVCL_REQUIRE(E > 0 && E % 4 == 0 && E <= 128 * kMaxVec, "eval_nway_fwd: bad E=%d", E);
     if (n_trials == 0) return CVCL_OK;
-    if (n_way == 4 && E <= 512 && n_trials >= 4096 && (reinterpret_cast<uintptr_t>(img) & 15) == 0) {
+    if (n_way == 4 && E <= 512 && n_trials >= 4096 && !(logits && normalize) && (reinterpret_cast<uintptr_t>(img) & 15) == 0) {
         // streaming form: persistent blocks, 32 KB stages filled by bulk async copies
         const int smem = 128 + kEvalStages * kEvalGroup * 4 * E * 4;
         static thread_local bool attr_done = false;

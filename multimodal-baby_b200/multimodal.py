@@ -306,7 +306,7 @@ class MultiModalModel(nn.Module):
         nhwc = image_features.permute(0, 2, 3, 1).reshape(B, H * W, E)
         if self.sim == "mean":
             _, tpool = ops.text_features_spatial(text, text_length, table, self.normalize_features,
-                                                 1.0 / (H * W))
+                                                 1.0 / (H * W), want_tok=False)
             return ops.sim_logits(ops.spatial_pool(nhwc), tpool, s)
         tok, _ = ops.text_features_spatial(text, text_length, table, self.normalize_features)
         match = ops.spatial_max_similarity(nhwc, tok, text_length, text)
@@ -354,7 +354,7 @@ class MultiModalModel(nn.Module):
                 image_features = image_features.permute(0, 3, 1, 2)
                 if self.sim == "mean":
                     _, txt_f = ops.text_features_spatial(y, y_len, table, self.normalize_features,
-                                                         1.0 / (H * W))
+                                                         1.0 / (H * W), want_tok=False)
                     img_f = ops.spatial_pool(nhwc)
                 else:
                     img_f = txt_f = None

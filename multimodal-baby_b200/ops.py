@@ -94,8 +94,10 @@ def to_bf16_pair(x: Tensor, want_t: bool) -> Tuple[Tensor, Optional[Tensor]]:
 # ----------------------------------------------------------------------------------------
 @torch.library.custom_op(_NS + "::text_encoder_fwd", mutates_args=())
 def text_encoder_fwd(ids: Tensor, lens: Tensor, table: Tensor, normalize: bool, per_token: bool,
-                     pool_scale: float) -> Tuple[Tensor, Tensor, Tensor]:
-    """-> (feat [B,E] fp32, inv_norm [B] or [B*L] fp32, tok [B,L,E] fp32 (per_token) or empty)."""
+                     pool_scale: float, want_tok: bool = True) -> Tuple[Tensor, Tensor, Tensor]:
+    """-> (feat [B,E] fp32, inv_norm [B] or [B*L] fp32, tok [B,L,E] fp32 (per_token and want_tok) or empty).
+    want_tok=False (spatial "mean" similarity, which only consumes the pooled factor) skips the
+    [B,L,E] per-token output."""
     _need_cuda(ids, lens, table)
     ids = _i64(ids); lens = _i64(lens); table = _f32(table)
     B, L = ids.shape
@@ -103,19 +105,19 @@ def text_encoder_fwd(ids: Tensor, lens: Tensor, table: Tensor, normalize: bool, 
     dev = ids.device
     feat = torch.empty((B, E), dtype=torch.float32, device=dev)
     inv = torch.empty((B * L if per_token else B,), dtype=torch.float32, device=dev)
-    tok = torch.empty((B, L, E) if per_token else (0,), dtype=torch.float32, device=dev)
+    tok = torch.empty((B, L, E) if (per_token and want_tok) else (0,), dtype=torch.float32, device=dev)
     _cabi.call("cvcl_text_encoder_fwd", _p(ids), _p(lens), _p(table), B, L, E, V, int(normalize),
                int(per_token), float(pool_scale), _p(feat), None, 0, _p(inv),
-               _p(tok) if per_token else None, None, None, _stream())
+               _p(tok) if (per_token and want_tok) else None, None, None, _stream())
     return feat, inv, tok
 
 
 @text_encoder_fwd.register_fake
-def _(ids, lens, table, normalize, per_token, pool_scale):
+def _(ids, lens, table, normalize, per_token, pool_scale, want_tok=True):
     B, L = ids.shape
     E = table.shape[1]
     return (table.new_empty((B, E)), table.new_empty((B * L if per_token else B,)),
-            table.new_empty((B, L, E) if per_token else (0,)))
+            table.new_empty((B, L, E) if (per_token and want_tok) else (0,)))
 
 
 @torch.library.custom_op(_NS + "::embedding_bag_bwd", mutates_args=())
@@ -207,18 +209,23 @@ class _TextFeaturesSpatial(torch.autograd.Function):
     """-> (tok [B,L,E] normalised per token, pooled [B,E] = sum_l tok * pool_scale / len)."""
 
     @staticmethod
-    def forward(ctx, ids, lens, table, normalize, pool_scale):
-        pooled, inv, tok = _raw(text_encoder_fwd)(ids, lens, table, normalize, True, pool_scale)
+    def forward(ctx, ids, lens, table, normalize, pool_scale, want_tok):
+        pooled, inv, tok = _raw(text_encoder_fwd)(ids, lens, table, normalize, True, pool_scale, want_tok)
         ctx.save_for_backward(ids, lens, table)
         ctx.normalize = normalize
         ctx.pool_scale = pool_scale
+        ctx.want_tok = want_tok
+        if not want_tok:
+            ctx.mark_non_differentiable(tok)
         return tok, pooled
 
     @staticmethod
     def backward(ctx, dtok, dpool):
         ids, lens, table = ctx.saved_tensors
+        if not ctx.want_tok:
+            dtok = None
         return None, None, _raw(text_token_bwd)(ids, lens, table, dtok, dpool, ctx.pool_scale,
-                                          ctx.normalize), None, None
+                                          ctx.normalize), None, None, None
 
 
 class _EmbeddingGather(torch.autograd.Function):
@@ -238,8 +245,9 @@ def text_features_flat(ids, lens, table, normalize=True):
     return _TextFeaturesFlat.apply(ids, lens, table, bool(normalize))
 
 
-def text_features_spatial(ids, lens, table, normalize=True, pool_scale=1.0 / 49):
-    return _TextFeaturesSpatial.apply(ids, lens, table, bool(normalize), float(pool_scale))
+def text_features_spatial(ids, lens, table, normalize=True, pool_scale=1.0 / 49, want_tok=True):
+    """-> (tok [B,L,E] | empty, pooled [B,E]); want_tok=False for the "mean" similarity (pooled only)."""
+    return _TextFeaturesSpatial.apply(ids, lens, table, bool(normalize), float(pool_scale), bool(want_tok))
 
 
 def text_outputs(ids, table):

@@ -173,10 +173,13 @@ class PeerExchange:
                 base = (torch.arange(n, device=dev, dtype=torch.float32) % 13) - 6.0
                 for k in range(self.N_SLOTS):
                     self.stats[k].copy_(base * (r + 1 + k))
-                fa = self.gather_feats(st)
-                la = self.gather_lse(st)
+                # copies are taken BEFORE the closing barrier in stream order: a faster rank may start the
+                # next round (and push into this rank's gathered buffers) as soon as it has passed it
+                fa = self.gather_feats(st).clone()
+                la = self.gather_lse(st).clone()
                 for k in range(self.N_SLOTS):
                     self.allreduce_stats(k, n, st)
+                got = [self.stats[k].clone() for k in range(self.N_SLOTS)]
                 self.barrier(st)
                 torch.cuda.synchronize(dev)
                 want_f = torch.cat([(col[None, :] + (q + it)).expand(b, 2 * E) for q in range(W)]).to(torch.bfloat16)
@@ -184,7 +187,7 @@ class PeerExchange:
                                     for q in range(W)], dim=1)
                 ok = ok and torch.equal(fa, want_f) and torch.equal(la, want_l)
                 for k in range(self.N_SLOTS):
-                    ok = ok and torch.equal(self.stats[k], base * float(sum(q + 1 + k for q in range(W))))
+                    ok = ok and torch.equal(got[k], base * float(sum(q + 1 + k for q in range(W))))
             ok = ok and int(self.status.item()) == 0
         except Exception:                        # noqa: BLE001
             ok = False
