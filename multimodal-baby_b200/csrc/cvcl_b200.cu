@@ -823,7 +823,7 @@ int cvcl_peer_allgather_push(void* const* peer_dst, void* const* peer_flags, uns
     int rc = fill_peer_table(&t, peer_dst, peer_flags, epoch, status, world, rank, timeout_ms, "peer_allgather_push");
     if (rc != CVCL_OK) return rc;
     const long long per16 = seg_bytes / 16 * nseg;
-    long long blocks = (per16 + 2LL * kPeerThreads - 1) / (2LL * kPeerThreads);        // same on every rank
+    long long blocks = (per16 + 4LL * kPeerThreads - 1) / (4LL * kPeerThreads);        // same on every rank
     blocks = blocks < 1 ? 1 : (blocks > kPeerMaxBlocks ? kPeerMaxBlocks : blocks);
     CVCL_CHECK_CUDA(launch_pdl(peer_allgather_push_kernel, dim3(static_cast<unsigned>(blocks)), dim3(kPeerThreads), 0,
                                as_stream(stream), t, world, rank, static_cast<const uint4*>(src), seg_bytes / 16, nseg,
@@ -855,7 +855,7 @@ int cvcl_peer_allreduce_push_f32(void* const* peer_data, void* const* peer_scrat
         t.aux[r] = peer_scratch[r];
     }
     const long long n4 = n / 4, per = (n4 + world - 1) / world;
-    long long blocks = (per + kPeerThreads - 1) / kPeerThreads;                         // same on every rank
+    long long blocks = (per + 2LL * kPeerThreads - 1) / (2LL * kPeerThreads);           // same on every rank
     blocks = blocks < 1 ? 1 : (blocks > kPeerMaxBlocks ? kPeerMaxBlocks : blocks);
     const dim3 grid(static_cast<unsigned>(blocks)), block(kPeerThreads);
     cudaStream_t st = as_stream(stream);

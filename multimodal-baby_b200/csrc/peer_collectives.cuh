@@ -8,7 +8,7 @@
 // storing the launch's epoch into the peer's flag word [phase][b][r] (st.release.sys over NVLink) and
 // spins (ld.acquire.sys) on its own words [phase][b][peer].  Epochs only grow (one per launch, kept in
 // a per-rank device array so CUDA-graph replays advance them), so flags are never reset.  All ranks
-// must launch a given channel with the same grid; the grid is at most kPeerMaxBlocks (128) CTAs of 512
+// must launch a given channel with the same grid; the grid is at most kPeerMaxBlocks CTAs of 512
 // threads, always co-resident on 148 SMs, so the spin cannot starve a block it waits for.
 //
 //   all-gather : start barrier (the peers' blocks are complete: a kernel only starts after all earlier
@@ -28,7 +28,7 @@
 namespace cvcl {
 
 constexpr int kPeerMaxWorld = 8;
-constexpr int kPeerMaxBlocks = 128;
+constexpr int kPeerMaxBlocks = 64;
 constexpr int kPeerThreads = 512;
 // flag words one channel needs in every rank's flag area: [phase 2][block][source rank]
 constexpr int kPeerFlagWords = 2 * kPeerMaxBlocks * kPeerMaxWorld;
