@@ -2,7 +2,7 @@
 captured as a CUDA graph that stops after phase k (CVCL_B200_STEP_PHASES, read by
 cvcl_flat_contrastive_step), replayed with an L2 flush in between and event-timed.  Differences between
 consecutive k show what each phase adds where it actually runs (PDL overlap, parallel graph branches).
-    python tools/step_phases.py [B] [reps]"""
+    python tools/step_phases.py [B] [reps] [phase list, e.g. 11,1,0]"""
 import json, os, statistics, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -22,7 +22,8 @@ NAMES = {11: "1a head chain only (cast W, split-K GEMM, bias+norm) + memsets", 1
          1: "1 encoders (both branches)", 2: "2 + similarity / InfoNCE (+ merge)", 3: "3 + Gs",
          4: "4 + dI, dT", 0: "5 + dW, embedding scatter (full step)", -1: "empty graph (one memset node)"}
 out = {}
-for k in (-1, 11, 12, 1, 2, 3, 4, 0):
+KS = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [-1, 11, 12, 1, 2, 3, 4, 0]
+for k in KS:
     os.environ["CVCL_B200_STEP_PHASES"] = str(k)
     def step():
         if k == -1:
