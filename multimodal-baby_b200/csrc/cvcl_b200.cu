@@ -222,29 +222,10 @@ int cvcl_gemm_f32out(const void* A, int lda, int a_mn, const void* Bm, int ldb, 
 }
 
 // ------------------------------------------------------------------------------------ K2
-} // extern "C"
-namespace {
-// head_tickets (nullable): >= ceil(M/128) zeroed uints -> the bias / normalise pass is fused into the
-// split-K GEMM (EpiHeadSplitK); the fused step passes them from its workspace
-int head_proj_norm_fwd_impl(const void* x, int ldx, const void* w, int ldw, const float* bias,
-                            int M, int E, int K, int normalize,
-                            float* out_f32, int ld_f32, void* out_bf16, int ld_bf16,
-                            float* inv_norm, unsigned int* head_tickets, void* stream);
-}
-extern "C" {
 int cvcl_head_proj_norm_fwd(const void* x, int ldx, const void* w, int ldw, const float* bias,
                             int M, int E, int K, int normalize,
                             float* out_f32, int ld_f32, void* out_bf16, int ld_bf16,
                             float* inv_norm, void* stream) {
-    return head_proj_norm_fwd_impl(x, ldx, w, ldw, bias, M, E, K, normalize, out_f32, ld_f32, out_bf16, ld_bf16,
-                                   inv_norm, nullptr, stream);
-}
-} // extern "C"
-namespace {
-int head_proj_norm_fwd_impl(const void* x, int ldx, const void* w, int ldw, const float* bias,
-                            int M, int E, int K, int normalize,
-                            float* out_f32, int ld_f32, void* out_bf16, int ld_bf16,
-                            float* inv_norm, unsigned int* head_tickets, void* stream) {
     CVCL_REQUIRE(x && w, "head_proj_norm_fwd: null operand");
     CVCL_REQUIRE(M > 0 && E > 0 && K > 0, "head_proj_norm_fwd: bad shape M=%d E=%d K=%d", M, E, K);
     const int cluster = ceil_div(E, kBN);
@@ -269,13 +250,6 @@ int head_proj_norm_fwd_impl(const void* x, int ldx, const void* w, int ldw, cons
                 if (!head_scratch_zeroed())
                     CVCL_CHECK_CUDA(cudaMemsetAsync(out_f32, 0, sizeof(float) * static_cast<size_t>(M) * ld_f32, as_stream(stream)));
                 gs.k_splits = splits;
-                if (head_tickets && tiles * splits <= sm_count() && E <= 1024 && ld_bf16 % 4 == 0) {
-                    EpiHeadSplitK::Params eh{};
-                    eh.C = out_f32; eh.ldc = ld_f32; eh.bias = bias; eh.normalize = normalize;
-                    eh.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); eh.ld_bf16 = ld_bf16; eh.inv_norm = inv_norm;
-                    eh.tickets = head_tickets;
-                    return launch_gemm<kBN, 4, EpiHeadSplitK, false, false>(op, gs, eh, 1, as_stream(stream));
-                }
                 EpiAtomicAddF32::Params ea{}; ea.C = out_f32; ea.ldc = ld_f32; ea.alpha = 1.f;
                 int rc = launch_gemm<kBN, 4, EpiAtomicAddF32, false, false>(op, gs, ea, 1, as_stream(stream));
                 if (rc) return rc;
@@ -297,8 +271,6 @@ int head_proj_norm_fwd_impl(const void* x, int ldx, const void* w, int ldw, cons
         return launch_gemm<kBN, 3, EpiHeadNorm, false, false>(op, gs, ep, cluster, as_stream(stream));
     return launch_gemm<kBN, 6, EpiHeadNorm, false, false>(op, gs, ep, cluster, as_stream(stream));
 }
-}  // namespace
-extern "C" {
 
 // ------------------------------------------------------------------------------------ K3+K4
 size_t cvcl_sim_workspace_bytes(int M0, int N0, int M1, int N1) {
@@ -527,13 +499,13 @@ namespace {
 struct SideStream {
     cudaStream_t s = nullptr;
     cudaStream_t s2 = nullptr;        // gradient-buffer memset branch (4.8 MB, needed only by the backward)
-    cudaEvent_t fork[4] = {nullptr, nullptr, nullptr, nullptr}, join[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t fork[3] = {nullptr, nullptr, nullptr}, join[3] = {nullptr, nullptr, nullptr};
     bool ok = false;
     int init() {
         if (ok) return CVCL_OK;
         CVCL_CHECK_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
         CVCL_CHECK_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 3; ++i) {
             CVCL_CHECK_CUDA(cudaEventCreateWithFlags(&fork[i], cudaEventDisableTiming));
             CVCL_CHECK_CUDA(cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming));
         }
@@ -546,7 +518,6 @@ SideStream& side_stream() { static thread_local SideStream ss; return ss; }
 struct FlatWs {
     __nv_bfloat16 *w16, *x16, *img16, *txt16, *G0, *du16;
     float *invn_i, *invn_t, *lse0, *lse1, *dm, *u32;
-    unsigned int* head_ticket;          // [<= 64] row-block tickets of the fused split-K head
     void* sim; int ldB; size_t bytes;
 };
 FlatWs carve_flat_ws(void* ws, int B, int L, int E, int K, int V) {
@@ -568,7 +539,6 @@ FlatWs carve_flat_ws(void* ws, int B, int L, int E, int K, int V) {
     f.lse1 = static_cast<float*>(take(4ull * B));
     f.dm = static_cast<float*>(take(4ull * B * E));
     f.u32 = static_cast<float*>(take(4ull * B * E));
-    f.head_ticket = static_cast<unsigned int*>(take(256));
     f.sim = base + off;
     off += align_up(cvcl_sim_workspace_bytes(B, B, B, B), 256);
     f.bytes = off;
@@ -610,10 +580,6 @@ int cvcl_flat_contrastive_step(const void* x, int x_is_bf16, const int64_t* ids,
         SimWs sw = carve_sim_ws(f.sim, B, B, B, B);
         CVCL_CHECK_CUDA(cudaMemsetAsync(sw.rb_ticket, 0, sizeof(unsigned int) * (1 + sw.tiles_m[0] + sw.tiles_m[1]), ss.s));
     }
-    static const bool fuse_head_norm = !(getenv("CVCL_B200_HEAD_FUSED_NORM") && getenv("CVCL_B200_HEAD_FUSED_NORM")[0] == '0');
-    static const bool k1_late = getenv("CVCL_B200_K1_LATE") && getenv("CVCL_B200_K1_LATE")[0] == '1';
-    unsigned int* head_tickets = (fuse_head_norm && ceil_div(B, kBM) <= 64) ? f.head_ticket : nullptr;
-    if (head_tickets) CVCL_CHECK_CUDA(cudaMemsetAsync(head_tickets, 0, 256, ss.s));
     CVCL_CHECK_CUDA(cudaEventRecord(ss.fork[2], ss.s));          // head GEMM (split-K atomics) waits for this only
     if (need_grads) {          // third branch: nothing before the backward reads these
         CVCL_CHECK_CUDA(cudaStreamWaitEvent(ss.s2, ss.fork[0], 0));
@@ -626,27 +592,15 @@ int cvcl_flat_contrastive_step(const void* x, int x_is_bf16, const int64_t* ids,
         }
         CVCL_CHECK_CUDA(cudaEventRecord(ss.join[2], ss.s2));
     }
-    auto text_encoder = [&]() -> int {
-        if (limit == 11) return CVCL_OK;
-        return cvcl_text_encoder_fwd(ids, lens, table, B, L, E, V, normalize, 0, 1.f, txt_feat_f32, f.txt16, E,
-                                     f.invn_t, nullptr, nullptr, status, side);
-    };
-    if (!k1_late || limit == 12) {
-        if ((rc = text_encoder())) return rc;
-        CVCL_CHECK_CUDA(cudaEventRecord(ss.join[0], ss.s));
-    }
+    if (limit != 11 && (rc = cvcl_text_encoder_fwd(ids, lens, table, B, L, E, V, normalize, 0, 1.f, txt_feat_f32, f.txt16, E,
+                                                   f.invn_t, nullptr, nullptr, status, side))) return rc;
+    CVCL_CHECK_CUDA(cudaEventRecord(ss.join[0], ss.s));
     if (limit == 12) {
         CVCL_CHECK_CUDA(cudaStreamWaitEvent(st, ss.join[0], 0));
         if (need_grads) CVCL_CHECK_CUDA(cudaStreamWaitEvent(st, ss.join[2], 0));
         return CVCL_OK;
     }
     if ((rc = cvcl_cast_transpose(w, 0, f.w16, nullptr, 1, E, K, K, K, 0, 0, 0, 0, stream))) return rc;
-    if (k1_late) {          // experiment: the text encoder starts once the weight cast has drained
-        CVCL_CHECK_CUDA(cudaEventRecord(ss.fork[3], st));
-        CVCL_CHECK_CUDA(cudaStreamWaitEvent(ss.s, ss.fork[3], 0));
-        if ((rc = text_encoder())) return rc;
-        CVCL_CHECK_CUDA(cudaEventRecord(ss.join[0], ss.s));
-    }
     const void* x16 = x;
     if (!x_is_bf16 || (reinterpret_cast<uintptr_t>(x) & 15)) {
         if ((rc = cvcl_cast_transpose(x, x_is_bf16, f.x16, nullptr, 1, B, K, K, K, 0, 0, 0, 0, stream))) return rc;
@@ -654,8 +608,7 @@ int cvcl_flat_contrastive_step(const void* x, int x_is_bf16, const int64_t* ids,
     }
     CVCL_CHECK_CUDA(cudaStreamWaitEvent(st, ss.fork[2], 0));
     head_scratch_zeroed() = true;
-    rc = head_proj_norm_fwd_impl(x16, K, f.w16, K, bias, B, E, K, normalize, img_f32, E, f.img16, E, f.invn_i,
-                                 head_tickets, stream);
+    rc = cvcl_head_proj_norm_fwd(x16, K, f.w16, K, bias, B, E, K, normalize, img_f32, E, f.img16, E, f.invn_i, stream);
     head_scratch_zeroed() = false;
     if (rc) return rc;
     CVCL_CHECK_CUDA(cudaStreamWaitEvent(st, ss.join[0], 0));

@@ -472,104 +472,6 @@ struct EpiAtomicAddF32 {
     static __device__ __forceinline__ void phase2(const EpiCtx&, const GemmShape&, const Params&) {}
 };
 
-// ---- split-K projection head with the bias / L2-normalise pass fused in (small M) ----------------
-// Every CTA adds its partial tile into the fp32 buffer (vector atomics, performed at L2).  The CTAs of a
-// 128-row block then meet at a ticket: once all tiles_n * k_splits partials of the block have landed, CTA j
-// of the block finishes rows [j*rpc, (j+1)*rpc): bias, row norm (warp reduction), fp32 in place + bf16 +
-// inv_norm -- the arithmetic of bias_norm_rows_kernel, without a second launch and its latency chain.
-// Every CTA of the launch is resident before any dependent grid may start (tiles * splits <= SM count,
-// one CTA per SM), so the wait cannot starve a CTA it waits for.  tickets[tile_m] must be zero at launch.
-struct EpiHeadSplitK {
-    static constexpr bool kClusterReduce = false;
-    static constexpr int kScratchBytes = 16;
-    static constexpr int kNumAux = 0;
-    static constexpr int kOutElemBytes = 0;
-    struct Params {
-        float* C; int ldc; const float* bias; int normalize;
-        __nv_bfloat16* out_bf16; int ld_bf16; float* inv_norm; unsigned int* tickets;
-    };
-    template <int BN>
-    static __device__ __forceinline__ void phase1(const EpiCtx& cx, const GemmShape& gs, const Params& p) {
-        const int m = cx.m0 + cx.row;
-        const int M = gs.M[0], N = gs.N[0];
-        float* crow = p.C + static_cast<size_t>(m) * p.ldc;
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-            float v[32];
-            ptx::tmem_ld_32x32(cx.tmem_row + c, v);
-            if (m >= M) continue;
-            const int n = cx.n0 + c;
-            if (n + 32 <= N) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    atomicAdd(reinterpret_cast<float4*>(crow + n) + j,
-                              make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) if (n + j < N) atomicAdd(crow + n + j, v[j]);
-            }
-        }
-        // ---- meet the other CTAs of this row block
-        __threadfence();
-        ptx::named_bar_sync(2 + cx.bar_base, kEpiThreads);
-        const unsigned int cpr = gridDim.y * gridDim.z;
-        if (cx.epi_tid == 0) {
-            atomicAdd(p.tickets + cx.tile_m, 1u);
-            unsigned int seen;
-            do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.tickets + cx.tile_m) : "memory");
-            } while (seen < cpr);
-        }
-        ptx::named_bar_sync(2 + cx.bar_base, kEpiThreads);
-        // ---- finish this CTA's share of the rows: one warp per row
-        const int j = blockIdx.y * gridDim.z + blockIdx.z;
-        const int rpc = (kBM + static_cast<int>(cpr) - 1) / static_cast<int>(cpr);
-        const int wq = cx.epi_tid >> 5, lane = cx.epi_tid & 31;
-        const int r_end = (j + 1) * rpc < kBM ? (j + 1) * rpc : kBM;
-        for (int r = j * rpc + wq; r < r_end; r += kEpiThreads / 32) {
-            const int mm = cx.m0 + r;
-            if (mm >= M) break;
-            float* row = p.C + static_cast<size_t>(mm) * p.ldc;
-            constexpr int kVec = 8;                       // N <= 1024
-            const int nch = (N + 127) >> 7;
-            float4 q[kVec];
-            float ssq = 0.f;
-#pragma unroll
-            for (int c = 0; c < kVec; ++c) {
-                q[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-                const int e = (c * 32 + lane) * 4;
-                if (c < nch && e < N) {
-                    q[c] = __ldcg(reinterpret_cast<const float4*>(row + e));      // L2: where the atomics landed
-                    if (p.bias) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + e));
-                        q[c].x += b.x; q[c].y += b.y; q[c].z += b.z; q[c].w += b.w;
-                    }
-                }
-                ssq += q[c].x * q[c].x + q[c].y * q[c].y + q[c].z * q[c].z + q[c].w * q[c].w;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
-            const float denom = p.normalize ? fmaxf(sqrtf(ssq), 1e-12f) : 1.f;
-            if (lane == 0 && p.inv_norm) p.inv_norm[mm] = 1.f / denom;
-#pragma unroll
-            for (int c = 0; c < kVec; ++c) {
-                const int e = (c * 32 + lane) * 4;
-                if (c < nch && e < N) {
-                    const float4 t = make_float4(q[c].x / denom, q[c].y / denom, q[c].z / denom, q[c].w / denom);
-                    *reinterpret_cast<float4*>(row + e) = t;
-                    if (p.out_bf16) {
-                        __nv_bfloat162 a = __floats2bfloat162_rn(t.x, t.y), b = __floats2bfloat162_rn(t.z, t.w);
-                        uint2 o2; o2.x = *reinterpret_cast<uint32_t*>(&a); o2.y = *reinterpret_cast<uint32_t*>(&b);
-                        *reinterpret_cast<uint2*>(p.out_bf16 + static_cast<size_t>(mm) * p.ld_bf16 + e) = o2;
-                    }
-                }
-            }
-        }
-    }
-    template <int BN>
-    static __device__ __forceinline__ void phase2(const EpiCtx&, const GemmShape&, const Params&) {}
-};
-
 // ---- same, direct global stores: for outputs whose row pitch is not 16-byte aligned (the 4 x 3 /
 // 4 x 1 logits of the inference API) ----
 struct EpiStoreF32Direct {
