@@ -271,16 +271,22 @@ def cpu_reference_step_fn(B):
     return fn
 
 
-def time_cpu(B, steps, warmup):
+def time_cpu(B, steps, warmup, budget_s=None):
+    """-> (seconds per step, steps timed).  budget_s bounds the timed region: the number of timed steps
+    is cut to what fits (estimated from the warm-up steps), never below 3."""
     torch.set_num_threads(os.cpu_count() or 1)
     fn = cpu_reference_step_fn(B)
+    t0 = time.perf_counter()
     for _ in range(warmup):
         fn()
+    est = (time.perf_counter() - t0) / max(warmup, 1)
+    if budget_s is not None and est > 0:
+        steps = max(3, min(steps, int(budget_s / est)))
     t0 = time.perf_counter()
     for _ in range(steps):
         fn()
     dt = (time.perf_counter() - t0) / steps
-    return dt
+    return dt, steps
 
 
 # ----------------------------------------------------------------------------------------------
@@ -309,17 +315,23 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        steps = a.steps
-        dt = time_cpu(B, steps, a.warmup)
-        val = B / dt
+        # the same workload as the B200 arm at this N: the global batch of B * world pairs in one process
+        # (the reference is single-process); timed steps are bounded to about 90 s of CPU work
+        Bref = B * max(world, a.gpus, 1)
+        config["global_batch"] = Bref
+        config["workload"] = config["workload"].replace("global InfoNCE batch %d" % (B * max(world, 1)),
+                                                        "global InfoNCE batch %d" % Bref)
+        dt, steps = time_cpu(Bref, a.steps, a.warmup, budget_s=90.0)
+        val = Bref / dt
         cores = os.cpu_count() or 1
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": a.gpus,
             "steps": steps, "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port",
-                             "sample": "%d steps of the B=%d flat train step (oracle port of the reference's "
-                                       "ATen fp32 op sequence, torch %d threads)" % (steps, B, cores)},
+                             "sample": "%d of the %d requested steps (bounded to ~90 s) of the B=%d flat train step "
+                                       "(oracle port of the reference's ATen fp32 op sequence, torch %d threads)"
+                                       % (steps, a.steps, Bref, cores)},
             "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))
         return
@@ -478,7 +490,7 @@ def main():
     cpu = None
     if world == 1:
         n_cpu = 40
-        cdt = time_cpu(B, n_cpu, 3)
+        cdt, n_cpu = time_cpu(B, n_cpu, 3, budget_s=30.0)
         cores = os.cpu_count() or 1
         cpu = {"value": B / cdt, "unit": "pairs/s", "cores": cores, "kind": "port", "ms_per_step": cdt * 1e3,
                "sample": "%d steps of the same B=%d flat train step (oracle port: the reference's ATen fp32 op "
