@@ -625,21 +625,34 @@ __global__ void __launch_bounds__(32 * (kEvalGroup + 1)) eval_nway_stream_kernel
         }
         return;
     }
+    // The label row of a trial is two dependent loads away (txt_index, then the row: about 2 us of
+    // latency per trial when taken in line -- ncu showed the consumer warps parked on exactly that), so it
+    // is software-pipelined: the index is fetched two groups ahead, the row one group ahead.
+    auto trial_of = [&](int k) -> int {
+        const long long g = blockIdx.x + static_cast<long long>(k) * gridDim.x;
+        return g < n_groups ? static_cast<int>(g) * kEvalGroup + warp : n_trials;
+    };
+    auto load_idx = [&](int trial) -> int {
+        if (trial >= n_trials) return -1;
+        return txt_index ? __ldg(txt_index + trial) : trial;
+    };
+    auto load_row = [&](int ti, float4 (&t)[4]) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            t[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ti >= 0 && (c * 32 + lane) * 4 < E)
+                t[c] = __ldg(reinterpret_cast<const float4*>(txt + static_cast<size_t>(ti) * E) + c * 32 + lane);
+        }
+    };
+    float4 t_cur[4], t_nxt[4];
+    load_row(load_idx(trial_of(0)), t_cur);
+    int idx_nxt = load_idx(trial_of(1));
     int it = 0;
     for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++it) {
         const int s = it % kEvalStages;
         const int trial = g * kEvalGroup + warp;
-        // the label row comes from L2 (22 rows shared by every trial) while the stage lands
-        float4 t[4];
-        if (trial < n_trials) {
-            const int ti = txt_index ? __ldg(txt_index + trial) : trial;
-            const float4* tsrc = reinterpret_cast<const float4*>(txt + static_cast<size_t>(ti) * E);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                t[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if ((c * 32 + lane) * 4 < E) t[c] = __ldg(tsrc + c * 32 + lane);
-            }
-        }
+        const int idx_nn = load_idx(trial_of(it + 2));
+        load_row(idx_nxt, t_nxt);
         ptx::mbar_wait(full + s, (it / kEvalStages) & 1);
         if (trial < n_trials) {
             const float4* rows = reinterpret_cast<const float4*>(ring + static_cast<size_t>(s) * stage_bytes +
@@ -654,10 +667,13 @@ __global__ void __launch_bounds__(32 * (kEvalGroup + 1)) eval_nway_stream_kernel
                 }
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(empty + s);          // rows are in registers: release the stage
-            eval_trial_from_regs<kWays>(x, t, trial, lane, normalize, scale, pred, logits);
+            eval_trial_from_regs<kWays>(x, t_cur, trial, lane, normalize, scale, pred, logits);
         } else {
             if (lane == 0) ptx::mbar_arrive(empty + s);
         }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) t_cur[c] = t_nxt[c];
+        idx_nxt = idx_nn;
     }
 }
 

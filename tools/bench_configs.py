@@ -88,9 +88,6 @@ ms, mn = timeit(lambda: m.ops.eval_nway(frames, cats, idx, 4, True, S_FIXED, Fal
 rec("config5_eval_4way_100k_frames", ms, mn, N * 4, "frames", bytes_=N * 4 * E * 4,
     note="fp32 normalise + dot + argmax -> predictions (streaming kernel: bulk async copies into a shared-memory ring); "
          "256 MiB memset between iterations: the kernel also pays the write-back of the dirty L2 lines it evicts")
-ms, mn = timeit(lambda: m.ops.eval_nway(frames, cats, idx, 4, True, S_FIXED, False), 20, 3, do_flush=False)
-rec("config5_eval_4way_100k_frames_noflush", ms, mn, N * 4, "frames", bytes_=N * 4 * E * 4,
-    note="same, no flush: the 205 MB input is larger than the 126 MB L2 (a sequential re-scan finds none of it cached)")
 ms, mn = timeit(lambda: m.ops.eval_nway(frames, cats, idx, 4, True, S_FIXED, True), 20, 3)
 rec("config5_eval_4way_100k_frames_with_logits", ms, mn, N * 4, "frames", bytes_=N * 4 * E * 4 + N * 16,
     note="same, logits [25000,4] also written (reference arithmetic for every trial)")
