@@ -916,7 +916,7 @@ int cvcl_eval_nway_fwd(const float* img, const float* txt, const int* txt_index,
             attr_done = true;
         }
         const int n_groups = ceil_div(n_trials, kEvalGroup);
-        const int grid = n_groups < 2 * sm_count() ? n_groups : 2 * sm_count();
+        const int grid = n_groups < 3 * sm_count() ? n_groups : 3 * sm_count();
         CVCL_CHECK_CUDA(launch_pdl(eval_nway_stream_kernel<4>, dim3(grid), dim3(32 * (kEvalGroup + 1)), smem,
                                    as_stream(stream), img, txt, txt_index, n_trials, E, normalize, expf(log_scale), pred,
                                    logits));

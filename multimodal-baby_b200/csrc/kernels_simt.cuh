@@ -589,7 +589,7 @@ __global__ void __launch_bounds__(256) eval_nway_kernel(const float* img, const 
 // peak on 100 000 frames); this one keeps kStages * 32 KB per block in flight all the time.
 // Arithmetic per trial is the same as eval_nway_kernel<kWays> (screen + exact path).
 constexpr int kEvalGroup = 4;          // trials per stage = consumer warps
-constexpr int kEvalStages = 3;
+constexpr int kEvalStages = 2;
 
 template <int kWays>
 __global__ void __launch_bounds__(32 * (kEvalGroup + 1)) eval_nway_stream_kernel(

@@ -2,11 +2,11 @@
 flat-step kernels from `ncu --set full` reports into profiles/r01_ncu_traffic.json; bench.py reads it to
 fill `roofline.traffic` for the dominant kernel."""
 import csv, json, subprocess, sys
-LABELS = [("EpiHeadNorm", "K2_head_proj_norm_fwd_cluster"), ("EpiAtomicAddF32, (bool)0, (bool)0", "K2_head_splitk_gemm"),
+LABELS = [("EpiHeadNorm", "K2_head_proj_norm_fwd_cluster"), ("EpiAtomicAddF32, 0, 0>", "K2_head_splitk_gemm"),
           ("bias_norm_rows", "K2_head_bias_norm"), ("text_encoder_flat_wide", "K1_text_encoder_fwd"),
           ("eval_nway_stream", "K7_eval_nway_stream"),
           ("EpiSimStats", "K3K4_sim_infonce_fwd"), ("EpiGradG", "K5a_sim_infonce_bwd_g"),
-          ("EpiNormBwdT<(bool)0>", "K5b_dimg_norm_bwd"), ("EpiNormBwdT<(bool)1>", "K5b_dtxt_norm_bwd"),
+          ("EpiNormBwdT<0>", "K5b_dimg_norm_bwd"), ("EpiNormBwdT<1>", "K5b_dtxt_norm_bwd"),
           ("EpiStoreF32", "K5c_head_weight_grad"), ("text_encoder_fwd", "K1_text_encoder_fwd"),
           ("embedding_scatter_add", "K5e_embedding_scatter_add"), ("cast_f32_bf16", "cast_w_f32_to_bf16"),
           ("infonce_finalize", "infonce_finalize")]
