@@ -262,6 +262,20 @@ int cvcl_adamw_step(float* p, const float* g, float* m, float* v, long long n, f
                     float beta2, float eps, float weight_decay, int step, float grad_scale, void* bf16_shadow,
                     void* stream);
 
+/* ---- Grad-CAM attention maps for the flat head ---------------------------------
+ * replaces multimodal/attention_maps.py:111-165 (gradCAM: forward through layer4 -> avgpool -> fc,
+ * F.normalize, output.backward(target), alpha = grad.mean((2,3)), clamp(sum_c act*alpha, 0)) for the
+ * saliency layer the reference uses (layer4).  The head is linear in the pooled activation, so the
+ * gradient is computed in closed form: no trunk backward.  fp32 end to end.
+ * act [N,K,HW] (NCHW layer4 activation, HW <= 64), w [E,K], bias [E] (nullable), target [N,E] ->
+ * cam [N,HW].  workspace: cvcl_gradcam_workspace_bytes(N,K,E), 16-byte aligned. */
+size_t cvcl_gradcam_workspace_bytes(int N, int K, int E);
+int cvcl_gradcam_flat(const float* act, const float* w, const float* bias, const float* target, int N, int K, int HW,
+                      int E, int normalize, void* workspace, float* cam, void* stream);
+/* F.interpolate(mode="bicubic", align_corners=False) of [N,h,w] fp32 maps to [N,H,W]
+ * (attention_maps.py:158-163). */
+int cvcl_bicubic_upsample(const float* in, int N, int h, int w, int H, int W, float* out, void* stream);
+
 /* ---- K7 n-way evaluation (fp32, bit-exact argmax contract) -----------------------------------
  * replaces the per-trial loop of eval.py:196-214 / multimodal_lit.py:466-511.
  * img [n_trials*n_way, E] fp32 embeddings (target first), txt [C,E] fp32 label embeddings,

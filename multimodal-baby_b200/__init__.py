@@ -10,7 +10,7 @@ is imported as `multimodal_baby_b200` through the shim module at the repository 
 registers `cvcl_b200::*` torch.library ops.  No CPU fallback exists: the ops raise on CPU tensors
 and `CvclLibraryMissing` if the library was not built (`python multimodal-baby_b200/build.py`).
 """
-from . import _cabi, build, ops, sharding                          # noqa: F401
+from . import _cabi, attention_maps, build, ops, sharding          # noqa: F401
 from ._cabi import CvclError, CvclLibraryMissing                   # noqa: F401
 from .multimodal import (MultiModalModel, PooledTrunk, TextEncoder, VisionEncoder,  # noqa: F401
                          split_trunk_forward)

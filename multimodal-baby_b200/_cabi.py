@@ -72,6 +72,9 @@ PROTOTYPES = {
     "cvcl_peer_allreduce_push_f32": (c_int, [_P, _P, _P, _P, _P, _I, _I, ctypes.c_longlong, ctypes.c_uint, _P]),
     "cvcl_peer_barrier": (c_int, [_P, _P, _P, _I, _I, ctypes.c_uint, _P]),
     "cvcl_adamw_step": (c_int, [_P, _P, _P, _P, ctypes.c_longlong, _F, _F, _F, _F, _F, _I, _F, _P, _P]),
+    "cvcl_gradcam_workspace_bytes": (c_size_t, [_I, _I, _I]),
+    "cvcl_gradcam_flat": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "cvcl_bicubic_upsample": (c_int, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "cvcl_eval_nway_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P]),
 }
 

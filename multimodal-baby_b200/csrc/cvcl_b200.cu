@@ -899,6 +899,53 @@ int cvcl_adamw_step(float* p, const float* g, float* m, float* v, long long n, f
     return CVCL_OK;
 }
 
+// ------------------------------------------------------------------------------------ Grad-CAM
+size_t cvcl_gradcam_workspace_bytes(int N, int K, int E) {
+    if (N <= 0 || K <= 0 || E <= 0) return 0;
+    return sizeof(float) * (2ull * N * K + 2ull * N * E);
+}
+
+int cvcl_gradcam_flat(const float* act, const float* w, const float* bias, const float* target, int N, int K, int HW,
+                      int E, int normalize, void* workspace, float* cam, void* stream) {
+    CVCL_REQUIRE(act && w && target && workspace && cam, "gradcam_flat: null pointer");
+    CVCL_REQUIRE(N >= 0 && K > 0 && E > 0 && HW > 0, "gradcam_flat: bad shape");
+    CVCL_REQUIRE(HW <= 64, "gradcam_flat: HW=%d > 64 locations", HW);
+    CVCL_REQUIRE(K % 4 == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
+                 "gradcam_flat: K %% 4 == 0 and 16-byte aligned weight / workspace required");
+    if (N == 0) return CVCL_OK;
+    cudaStream_t st = as_stream(stream);
+    float* pooled = static_cast<float*>(workspace);
+    float* alpha = pooled + static_cast<size_t>(N) * K;
+    float* u = alpha + static_cast<size_t>(N) * K;
+    float* g = u + static_cast<size_t>(N) * E;
+    const long long rows = static_cast<long long>(N) * K;
+    CVCL_CHECK_CUDA(launch_pdl(gradcam_pool_kernel, dim3(warps_grid(rows)), dim3(256), 0, st, act, pooled, rows, HW));
+    count_launch();
+    CVCL_CHECK_CUDA(launch_pdl(gradcam_head_kernel, dim3(warps_grid(static_cast<long long>(N) * E)), dim3(256), 0, st,
+                               static_cast<const float*>(pooled), w, bias, u, N, E, K));
+    count_launch();
+    CVCL_CHECK_CUDA(launch_pdl(gradcam_g_kernel, dim3(warps_grid(N, 128)), dim3(128), 0, st, static_cast<const float*>(u),
+                               target, g, N, E, normalize));
+    count_launch();
+    CVCL_CHECK_CUDA(launch_pdl(gradcam_alpha_kernel, dim3(ceil_div(K, 256), N), dim3(256), 0, st,
+                               static_cast<const float*>(g), w, alpha, N, E, K, 1.f / static_cast<float>(HW)));
+    count_launch();
+    CVCL_CHECK_CUDA(launch_pdl(gradcam_cam_kernel, dim3(N), dim3(256), 0, st, act, static_cast<const float*>(alpha), cam, K, HW));
+    count_launch();
+    return CVCL_OK;
+}
+
+int cvcl_bicubic_upsample(const float* in, int N, int h, int w, int H, int W, float* out, void* stream) {
+    CVCL_REQUIRE(in && out, "bicubic_upsample: null pointer");
+    CVCL_REQUIRE(N >= 0 && h > 0 && w > 0 && H > 0 && W > 0, "bicubic_upsample: bad shape");
+    const long long total = static_cast<long long>(N) * H * W;
+    if (total == 0) return CVCL_OK;
+    CVCL_CHECK_CUDA(launch_pdl(bicubic_upsample_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0,
+                               as_stream(stream), in, out, N, h, w, H, W));
+    count_launch();
+    return CVCL_OK;
+}
+
 // ------------------------------------------------------------------------------------ K7
 int cvcl_eval_nway_fwd(const float* img, const float* txt, const int* txt_index, int n_trials, int n_way,
                        int E, int normalize, float log_scale, int* pred, float* logits, void* stream) {

@@ -677,6 +677,150 @@ __global__ void __launch_bounds__(32 * (kEvalGroup + 1)) eval_nway_stream_kernel
     }
 }
 
+// --------------------------------------------------------------------------------------
+// Grad-CAM attention maps for the flat head (multimodal/attention_maps.py:111-165).
+// The saliency layer is layer4, followed by the global average pool and fc, so the head is linear in the
+// pooled activation and d output / d act[n,c,h,w] does not depend on (h,w): no trunk backward is needed.
+//   pooled[n,c] = mean_hw act[n,c,:]            u[n] = W pooled[n] + b            (:143, ResNet forward)
+//   g[n] = target[n]                            or (t - y <y,t>) / ||u||, y = u/||u||   (:144-146)
+//   alpha[n,c] = (W^T g[n])[c] / HW             (= grad.mean((2,3)), :114)
+//   cam[n,p] = max(0, sum_c act[n,c,p] alpha[n,c])                                  (:116-119)
+// fp32 throughout.  act is NCHW contiguous ([N, K, HW]).
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gradcam_pool_kernel(const float* act, float* pooled, long long n_rows, int HW) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
+    const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n_rows) return;
+    const float* src = act + row * HW;
+    float s = 0.f;
+    for (int i = lane; i < HW; i += 32) s += __ldg(src + i);
+    s = warp_sum(s);
+    if (lane == 0) pooled[row] = s / static_cast<float>(HW);
+}
+
+// u[n,e] = b[e] + <pooled[n,:], W[e,:]>: one warp per output, float4 loads (K % 4 == 0)
+__global__ void __launch_bounds__(256) gradcam_head_kernel(const float* pooled, const float* w, const float* bias,
+                                                           float* u, int N, int E, int K) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
+    const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (o >= N * E) return;
+    const int n = o / E, e = o - n * E;
+    const float4* a = reinterpret_cast<const float4*>(pooled + static_cast<size_t>(n) * K);
+    const float4* b = reinterpret_cast<const float4*>(w + static_cast<size_t>(e) * K);
+    float s = 0.f;
+    for (int i = lane; i < (K >> 2); i += 32) {
+        const float4 x = __ldg(a + i), y = __ldg(b + i);
+        s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) u[o] = s + (bias ? __ldg(bias + e) : 0.f);
+}
+
+// g[n,:] from u[n,:] and target[n,:]: one warp per image (F.normalize backward, eps 1e-12)
+__global__ void __launch_bounds__(128) gradcam_g_kernel(const float* u, const float* target, float* g, int N, int E,
+                                                        int normalize) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
+    const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const float* ur = u + static_cast<size_t>(n) * E;
+    const float* tr = target + static_cast<size_t>(n) * E;
+    float* gr = g + static_cast<size_t>(n) * E;
+    if (!normalize) {
+        for (int e = lane; e < E; e += 32) gr[e] = __ldg(tr + e);
+        return;
+    }
+    float ssq = 0.f;
+    for (int e = lane; e < E; e += 32) { const float v = ur[e]; ssq = fmaf(v, v, ssq); }
+    ssq = warp_sum(ssq);
+    const float nrm = sqrtf(ssq);
+    const float denom = fmaxf(nrm, 1e-12f);
+    float dot = 0.f;
+    for (int e = lane; e < E; e += 32) dot = fmaf(ur[e] / denom, __ldg(tr + e), dot);
+    dot = warp_sum(dot);
+    if (nrm < 1e-12f) dot = 0.f;                 // clamp active: y = u / eps, dy/du = I / eps
+    for (int e = lane; e < E; e += 32) gr[e] = (__ldg(tr + e) - (ur[e] / denom) * dot) / denom;
+}
+
+// alpha[n,c] = sum_e g[n,e] W[e,c] / HW: one thread per (n,c), coalesced over c
+__global__ void __launch_bounds__(256) gradcam_alpha_kernel(const float* g, const float* w, float* alpha, int N, int E,
+                                                            int K, float inv_hw) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = blockIdx.y;
+    if (c >= K) return;
+    const float* gr = g + static_cast<size_t>(n) * E;
+    float s = 0.f;
+#pragma unroll 4
+    for (int e = 0; e < E; ++e) s = fmaf(__ldg(gr + e), __ldg(w + static_cast<size_t>(e) * K + c), s);
+    alpha[static_cast<size_t>(n) * K + c] = s * inv_hw;
+}
+
+// cam[n,p] = max(0, sum_c act[n,c,p] alpha[n,c]): one block per image, 4 channel groups x 64 lanes (HW <= 64)
+__global__ void __launch_bounds__(256) gradcam_cam_kernel(const float* act, const float* alpha, float* cam, int K, int HW) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
+    __shared__ float part[4][64];
+    const int n = blockIdx.x;
+    const int q = threadIdx.x >> 6, p = threadIdx.x & 63;
+    const float* a = act + static_cast<size_t>(n) * K * HW;
+    const float* al = alpha + static_cast<size_t>(n) * K;
+    const int c0 = q * ((K + 3) / 4), c1 = min(K, c0 + (K + 3) / 4);
+    float s = 0.f;
+    if (p < HW) {
+#pragma unroll 4
+        for (int c = c0; c < c1; ++c) s = fmaf(__ldg(a + static_cast<size_t>(c) * HW + p), __ldg(al + c), s);
+    }
+    part[q][p] = s;
+    __syncthreads();
+    if (q == 0 && p < HW) cam[static_cast<size_t>(n) * HW + p] = fmaxf(((part[0][p] + part[1][p]) + part[2][p]) + part[3][p], 0.f);
+}
+
+// bicubic resize of [N, h, w] maps to [N, H, W] as F.interpolate(mode="bicubic", align_corners=False)
+// does it (attention_maps.py:158-163): Keys kernel with A = -0.75, source index (dst + 0.5) * in/out - 0.5,
+// border taps clamped; rows first, then columns.
+__device__ __forceinline__ void cubic_coeffs(float t, float* c) {
+    const float A = -0.75f;
+    const float x1 = t, x2 = 1.f - t;
+    c[0] = ((A * (x1 + 1.f) - 5.f * A) * (x1 + 1.f) + 8.f * A) * (x1 + 1.f) - 4.f * A;
+    c[1] = ((A + 2.f) * x1 - (A + 3.f)) * x1 * x1 + 1.f;
+    c[2] = ((A + 2.f) * x2 - (A + 3.f)) * x2 * x2 + 1.f;
+    c[3] = ((A * (x2 + 1.f) - 5.f * A) * (x2 + 1.f) + 8.f * A) * (x2 + 1.f) - 4.f * A;
+}
+
+__global__ void __launch_bounds__(256) bicubic_upsample_kernel(const float* in, float* out, int N, int h, int w, int H,
+                                                               int W) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(N) * H * W;
+    if (idx >= total) return;
+    const int ox = static_cast<int>(idx % W);
+    const int oy = static_cast<int>((idx / W) % H);
+    const int n = static_cast<int>(idx / (static_cast<long long>(W) * H));
+    const float sy = static_cast<float>(h) / static_cast<float>(H), sx = static_cast<float>(w) / static_cast<float>(W);
+    const float ry = sy * (static_cast<float>(oy) + 0.5f) - 0.5f, rx = sx * (static_cast<float>(ox) + 0.5f) - 0.5f;
+    const float fy = floorf(ry), fx = floorf(rx);
+    const int iy = static_cast<int>(fy), ix = static_cast<int>(fx);
+    float cy[4], cx[4];
+    cubic_coeffs(ry - fy, cy);
+    cubic_coeffs(rx - fx, cx);
+    const float* src = in + static_cast<size_t>(n) * h * w;
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int yy = min(max(iy - 1 + i, 0), h - 1);
+        float row = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int xx = min(max(ix - 1 + j, 0), w - 1);
+            row = fmaf(__ldg(src + yy * w + xx), cx[j], row);
+        }
+        acc = fmaf(row, cy[i], acc);
+    }
+    out[idx] = acc;
+}
+
 // contiguous fp32 -> bf16 cast, 8 elements per thread (two 16-byte loads, one 16-byte store)
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* src, __nv_bfloat16* dst, long long n8) {
     ptx::pdl_launch_dependents(); ptx::pdl_wait();

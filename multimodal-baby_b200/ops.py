@@ -999,3 +999,49 @@ def infonce_from_match(match, s):
     with torch.no_grad():
         lpi = match * math.exp(_scalar(s))
     return loss, iacc, tacc, ient, tent, lpi, lpi.t()
+
+
+# ----------------------------------------------------------------------------------------
+# Grad-CAM attention maps (multimodal/attention_maps.py:111-165)
+# ----------------------------------------------------------------------------------------
+@torch.library.custom_op(_NS + "::gradcam_flat", mutates_args=())
+def gradcam_flat(act: Tensor, w: Tensor, bias: Optional[Tensor], target: Tensor, normalize: bool) -> Tensor:
+    """act [N,K,H,W] fp32 layer4 activation, w [E,K], bias [E] | None, target [N,E] -> cam [N,1,H,W] fp32
+    = clamp(sum_c act * alpha, 0) with alpha the spatial mean of d<normalize(fc(avgpool(act))), target>/d act
+    (closed form: the head is linear in the pooled activation, no trunk backward)."""
+    _need_cuda(act, w, target)
+    act = _f32(act); w = _f32(w); target = _f32(target)
+    bias = None if bias is None else _f32(bias)
+    N, K, H, W = act.shape
+    E = w.shape[0]
+    if w.shape[1] != K or tuple(target.shape) != (N, E):
+        raise ValueError("gradcam_flat: act %s, w %s, target %s do not fit" % (tuple(act.shape), tuple(w.shape),
+                                                                              tuple(target.shape)))
+    lib = _cabi.load()
+    ws = torch.empty((max(int(lib.cvcl_gradcam_workspace_bytes(N, K, E)), 16),), dtype=torch.uint8, device=act.device)
+    cam = torch.empty((N, 1, H, W), dtype=torch.float32, device=act.device)
+    _cabi.call("cvcl_gradcam_flat", _p(act), _p(w), _p(bias), _p(target), N, K, H * W, E, int(normalize), _p(ws),
+               _p(cam), _stream())
+    return cam
+
+
+@gradcam_flat.register_fake
+def _(act, w, bias, target, normalize):
+    N, K, H, W = act.shape
+    return act.new_empty((N, 1, H, W), dtype=torch.float32)
+
+
+@torch.library.custom_op(_NS + "::bicubic_upsample", mutates_args=())
+def bicubic_upsample(x: Tensor, out_h: int, out_w: int) -> Tensor:
+    """x [N,1,h,w] fp32 -> [N,1,out_h,out_w]: F.interpolate(mode="bicubic", align_corners=False)."""
+    _need_cuda(x)
+    x = _f32(x)
+    N, C, h, w = x.shape
+    out = torch.empty((N, C, out_h, out_w), dtype=torch.float32, device=x.device)
+    _cabi.call("cvcl_bicubic_upsample", _p(x), N * C, h, w, int(out_h), int(out_w), _p(out), _stream())
+    return out
+
+
+@bicubic_upsample.register_fake
+def _(x, out_h, out_w):
+    return x.new_empty((x.shape[0], x.shape[1], out_h, out_w), dtype=torch.float32)

@@ -292,6 +292,45 @@ def eval_trial_loop(f_trials, ids, lens, W, b, table, s):
 # --------------------------------------------------------------------------------------
 # synthetic inputs shared by tests, bench and golden generation
 # --------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------------
+# Grad-CAM attention maps: multimodal/attention_maps.py:111-165 restated for the flat
+# head (saliency layer = layer4, followed by the trunk's global average pool and `fc`).
+# ------------------------------------------------------------------------------------------------
+def gradcam_flat(act, W, b, target, normalize=True, out_hw=None):
+    """act [N,K,H,W] = layer4 activation, W [E,K], b [E] = fc, target [N,E] (text features).
+    The reference's op sequence: output = fc(avgpool(act)) (attention_maps.py:143, torchvision ResNet
+    forward), F.normalize (:144-145), output.backward(target) (:146), alpha = grad.mean((2,3)) (:114),
+    cam = clamp(sum_c act*alpha, min=0) (:116-119), optional bicubic resize (:158-163).
+    -> (cam [N,1,H,W], resized [N,1,*out_hw] | None)."""
+    act = act.detach().clone().requires_grad_(True)
+    out = F.linear(F.adaptive_avg_pool2d(act, 1).flatten(1), W, b)
+    if normalize:
+        out = F.normalize(out, p=2, dim=1)
+    out.backward(target)
+    grad = act.grad
+    alpha = grad.mean(dim=(2, 3), keepdim=True)
+    cam = torch.clamp(torch.sum(act.detach() * alpha, dim=1, keepdim=True), min=0)
+    resized = None
+    if out_hw is not None:
+        resized = F.interpolate(cam, tuple(out_hw), mode="bicubic", align_corners=False)
+    return cam, resized
+
+
+def gradcam_flat_closed_form(act, W, b, target, normalize=True):
+    """The same map without autograd: the head is linear in the pooled activation, so the gradient
+    w.r.t. act[n,c,h,w] does not depend on (h,w): alpha[n,c] = (W^T g[n])[c] / (H*W) with
+    g = target (no normalisation) or (target - y <y,target>) / ||u|| (F.normalize backward)."""
+    N, K, H, Wd = act.shape
+    u = F.linear(act.mean(dim=(2, 3)), W, b)
+    g = target
+    if normalize:
+        nrm = u.norm(dim=1, keepdim=True).clamp_min(1e-12)
+        y = u / nrm
+        g = (target - y * (y * target).sum(1, keepdim=True)) / nrm
+    alpha = (g @ W) / float(H * Wd)
+    return torch.clamp(torch.einsum("nchw,nc->nhw", act, alpha), min=0).unsqueeze(1)
+
+
 def synth_tokens(rng: np.random.RandomState, B, L=MAX_LEN_UTTERANCE, V=2350, min_len=3):
     """len ~ U{3..L}; ids[b,0]=<sos>, ids[b,len-1]=<eos>, interior ~ U{4..V-1}, pads 0
     (collate layout of multimodal_data_module.py:98-109)."""

@@ -128,6 +128,47 @@ def run_eval_case(name, seed, n_trials, E, n_way=4):
     print(name, "acc", np.mean(np.array(preds) == 0))
 
 
+def gradcam_inputs(seed, N, E, K=2048, HW=7):
+    """inputs of the Grad-CAM golden case (tests call this too): post-ReLU layer4 activations, the
+    reference's fc init, L2-normalised text features as the backward target."""
+    rng = np.random.RandomState(seed)
+    W, b, _ = O.synth_weights(rng, E, K, 8)
+    act = O.synth_trunk_features(rng, (N, K, HW, HW))
+    tgt = rng.standard_normal((N, E)).astype(np.float32)
+    tgt /= np.linalg.norm(tgt, axis=1, keepdims=True)
+    return dict(W=W, b=b, act=act, target=tgt.astype(np.float32))
+
+
+def run_gradcam_case(name, seed, N, E):
+    """attention_maps.gradCAM of the UNMODIFIED reference on a head-only vision model whose saliency layer
+    (`layer4`) is an identity fed the activation map (the trunk stays outside the product); the resize is
+    the reference's own F.interpolate call (attention_maps.py:158-163) applied to 224 x 224."""
+    import collections
+    R.load_reference()
+    from multimodal import attention_maps as ref_am
+    inp = gradcam_inputs(seed, N, E)
+    fc = torch.nn.Linear(inp["W"].shape[1], E)
+    with torch.no_grad():
+        fc.weight.copy_(torch.from_numpy(inp["W"])); fc.bias.copy_(torch.from_numpy(inp["b"]))
+    model = torch.nn.Sequential(collections.OrderedDict(
+        layer4=torch.nn.Identity(), avgpool=torch.nn.AdaptiveAvgPool2d((1, 1)), flatten=torch.nn.Flatten(1), fc=fc))
+    out = {}
+    for norm in (True, False):
+        cams = []
+        for i in range(N):                      # the reference calls it image by image (generate_attention_maps.py:103-110)
+            cam = ref_am.gradCAM(model, torch.from_numpy(inp["act"][i:i + 1]).clone(),
+                                 torch.from_numpy(inp["target"][i:i + 1]), model.layer4,
+                                 normalize_features=norm, resize=False)
+            cams.append(cam.detach())
+        cam = torch.cat(cams)
+        big = torch.nn.functional.interpolate(cam, (224, 224), mode="bicubic", align_corners=False)
+        key = "norm" if norm else "raw"
+        out["cam_" + key] = cam.numpy()
+        out["resized_" + key] = big.numpy()[:, :, ::3, ::3].copy()       # every third pixel: 75 x 75
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), seed=seed, N=N, E=E, **out)
+    print(name, "cam max", float(out["cam_norm"].max()), "nonzero frac", float((out["cam_norm"] > 0).mean()))
+
+
 def run_tokenize_case(name):
     """MultiModalLitModel.tokenize (multimodal_lit.py:161-190) on pre-tokenised text
     (whitespace split; spaCy itself is not available offline)."""
@@ -172,6 +213,7 @@ def main():
     run_forward_case("forward_4x3_e512", 108, 4, 3, 512)
     run_forward_case("forward_4x1_e512", 109, 4, 1, 512)
     run_eval_case("eval_4way_e512", 110, 64, 512)
+    run_gradcam_case("gradcam_e512_n3", 111, 3, 512)
     run_tokenize_case("tokenize")
     run_state_dict_case("state_dict_keys")
 

@@ -139,3 +139,25 @@ def test_synth_tokens_contract():
     assert lens.min() >= 3 and lens.max() <= 25
     for row, n in zip(ids, lens):
         assert row[0] == 2 and row[n - 1] == 3 and (row[1:n - 1] >= 4).all() and not row[n:].any()
+
+
+# ---------------------------------------------------------------- Grad-CAM
+def test_oracle_gradcam_matches_reference_golden():
+    """oracle restatement (autograd and closed form) of attention_maps.gradCAM vs the maps the unmodified
+    reference produced (oracle/make_golden.py: run_gradcam_case), both normalisation modes + the resize."""
+    from oracle.make_golden import gradcam_inputs
+    g = golden("gradcam_e512_n3")
+    inp = gradcam_inputs(int(g["seed"]), int(g["N"]), int(g["E"]))
+    for norm, key in ((True, "norm"), (False, "raw")):
+        cam, big = O.gradcam_flat(t(inp["act"]), t(inp["W"]), t(inp["b"]), t(inp["target"]), norm, (224, 224))
+        scale = float(np.abs(g["cam_" + key]).max())
+        assert scale > 0 and (g["cam_" + key] > 0).any() and (g["cam_" + key] == 0).any()     # the clamp is exercised
+        assert np.abs(cam.numpy() - g["cam_" + key]).max() <= 1e-5 * scale
+        assert np.abs(big.numpy()[:, :, ::3, ::3] - g["resized_" + key]).max() <= 1e-5 * scale
+        cf = O.gradcam_flat_closed_form(t(inp["act"]), t(inp["W"]), t(inp["b"]), t(inp["target"]), norm)
+        assert float((cf - cam).abs().max()) <= 1e-5 * scale
+    # fp64: autograd and closed form agree to rounding
+    a64 = t(inp["act"]).double(); W64 = t(inp["W"]).double(); b64 = t(inp["b"]).double(); t64 = t(inp["target"]).double()
+    cam64, _ = O.gradcam_flat(a64, W64, b64, t64, True)
+    cf64 = O.gradcam_flat_closed_form(a64, W64, b64, t64, True)
+    assert float((cam64 - cf64).abs().max()) <= 1e-12
