@@ -168,3 +168,26 @@ def test_full_resnext_trunk_split_matches_torchvision():
         assert torch.allclose(ve.model.fc(pooled), ref, atol=1e-5)
     assert not any(p.requires_grad for n, p in ve.model.named_parameters() if not n.startswith("fc."))
     assert all(p.requires_grad for p in ve.model.fc.parameters())
+
+
+# ------------------------------------------------------------------------------ bench.py contract
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the B200 arm) prints ONE JSON line with
+    the metric of BASELINE.json, its own cpu_baseline and a zero-copy e2e object; no GPU needed."""
+    import json
+    import subprocess
+    import sys
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3",
+                          "--warmup", "3", "--pairs-per-gpu", "64"], capture_output=True, text=True, timeout=600,
+                         cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
+    assert d["impl"] == "reference" and d["metric"] == base["metric"] and d["unit"] == "pairs/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 3 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"] and "model" not in d["config"]
