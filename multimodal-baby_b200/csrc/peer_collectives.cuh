@@ -11,11 +11,17 @@
 // must launch a given channel with the same grid; the grid is at most kPeerMaxBlocks CTAs of 512
 // threads, always co-resident on 148 SMs, so the spin cannot starve a block it waits for.
 //
-//   all-gather : start barrier (the peers' blocks are complete: a kernel only starts after all earlier
-//                work of its stream) -> pull every block with 16-byte loads, several in flight.
-//   all-reduce : start barrier -> rank r sums slice r of every rank's buffer in rank order (so the
+// Two families, same results (the PUSH kernels further down are the default of sharding.PeerExchange:
+// all NVLink traffic is posted stores; measured 151.9 us vs 158.5 us (pull) vs 165.0 us (NCCL) per step at
+// 2 GPUs and 193 us vs 256 us (NCCL) at 8 GPUs, profiles/r01_sharded_phases_*.txt):
+//
+//   all-gather : pull: start barrier (the peers' blocks are complete: a kernel only starts after all
+//                earlier work of its stream) -> load every block with 16-byte loads, several in flight.
+//                push: store the own block into every rank's gathered buffer -> barrier.
+//   all-reduce : pull: start barrier -> rank r sums slice r of every rank's buffer in rank order (so the
 //                result does not depend on who reduces it) and stores the sum into slice r of EVERY
-//                rank's buffer -> end barrier.  In place, deterministic, two NVLink traversals.
+//                rank's buffer -> end barrier.  push: scatter slice p into rank p's scratch -> barrier ->
+//                local sum in rank order, store to every rank -> barrier.  In place, deterministic.
 //
 // A barrier that does not complete within timeout_ms sets *status and traps (the step fails loudly
 // instead of hanging the device); with CVCL_PEER_NO_TRAP or'ed into timeout_ms it only sets *status and
