@@ -1,0 +1,92 @@
+"""Host -> device input staging for the contrastive step.
+
+The reference collates a batch with `multiModalDataset_collate_fn`
+(multimodal/multimodal_data_module.py:98-109): pad the token rows of the batch to the longest utterance,
+truncate to MAX_LEN_UTTERANCE = 25, clamp the lengths.  The padded width therefore changes from batch to
+batch, and every step pays pageable-host H2D copies of freshly allocated tensors.
+
+`multiModalDataset_collate_fn` below returns exactly what the reference's function returns (drop-in for the
+data module).  `PinnedBatchStager` is what the CUDA-graph train step wants instead: fixed-shape
+[B, 25] int64 ids / [B] int64 lengths (and optionally the trunk-boundary features) in PINNED host buffers
+that `GraphedContrastiveStep` copies from inside its graph; positions >= len hold PAD (0), which is the
+invariant the text-encoder kernel relies on (SURVEY 8a note on implicit masking).
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+from torch.nn.utils.rnn import pad_sequence
+
+MAX_LEN_UTTERANCE = 25          # multimodal_data_module.py:30
+PAD_TOKEN_ID = 0                # multimodal_data_module.py:24
+
+
+def multiModalDataset_collate_fn(batch):
+    """multimodal_data_module.py:98-109, same outputs: (img [B,...], ids [B, min(max_len, 25)] int64,
+    lengths [B] int64 clamped to 25, raw utterances list)."""
+    img, utterance_idxs, utterance_length, raw_utterance = zip(*batch)
+    img = torch.stack(img, 0)
+    utterance_idxs = pad_sequence(utterance_idxs, batch_first=True, padding_value=PAD_TOKEN_ID)
+    utterance_length = torch.tensor(utterance_length, dtype=torch.long)
+    if utterance_idxs.size(1) > MAX_LEN_UTTERANCE:
+        utterance_idxs = utterance_idxs[:, :MAX_LEN_UTTERANCE]
+        utterance_length = torch.minimum(utterance_length, torch.tensor(MAX_LEN_UTTERANCE, dtype=torch.long))
+    return img, utterance_idxs, utterance_length, list(raw_utterance)
+
+
+class PinnedBatchStager:
+    """Fixed-shape pinned staging buffers for `GraphedContrastiveStep(model, x_host, ids_host, lens_host)`.
+
+        stager = PinnedBatchStager(batch_size=512, feat_shape=(2048,))
+        step = GraphedContrastiveStep(model, stager.x_host, stager.ids_host, stager.lens_host, prefetch=True)
+        for feats, token_rows, lengths in loader:
+            stager.stage(token_rows, lengths, feats)      # host-side writes only, no allocation
+            loss = step()
+
+    `stage` accepts the per-sample token rows (a sequence of 1-D int64 tensors, as the dataset yields them)
+    or an already padded [B, L'] tensor (as the reference's collate produces), pads / truncates to
+    `max_len`, forces PAD beyond each length and clamps the lengths -- the same ids / lengths the reference's
+    collate would hand to the model, in a layout that never changes shape."""
+
+    def __init__(self, batch_size: int, feat_shape: Optional[Sequence[int]] = None,
+                 feat_dtype: torch.dtype = torch.bfloat16, max_len: int = MAX_LEN_UTTERANCE,
+                 pin: Optional[bool] = None):
+        pin = torch.cuda.is_available() if pin is None else bool(pin)
+
+        def buf(shape, dtype):
+            t = torch.zeros(tuple(shape), dtype=dtype)
+            return t.pin_memory() if pin else t
+        self.batch_size, self.max_len = int(batch_size), int(max_len)
+        self.ids_host = buf((batch_size, max_len), torch.int64)
+        self.lens_host = buf((batch_size,), torch.int64)
+        self.x_host = buf((batch_size,) + tuple(feat_shape), feat_dtype) if feat_shape is not None else None
+
+    @torch.no_grad()
+    def stage(self, utterance_idxs, utterance_length, feats: Optional[torch.Tensor] = None):
+        B, L = self.batch_size, self.max_len
+        lens = torch.as_tensor(utterance_length, dtype=torch.int64).reshape(-1)
+        if lens.numel() != B:
+            raise ValueError("PinnedBatchStager: got %d utterances for a batch of %d" % (lens.numel(), B))
+        self.ids_host.fill_(PAD_TOKEN_ID)
+        if torch.is_tensor(utterance_idxs) and utterance_idxs.dim() == 2:
+            if utterance_idxs.shape[0] != B:
+                raise ValueError("PinnedBatchStager: padded ids have %d rows, batch is %d" % (utterance_idxs.shape[0], B))
+            w = min(L, utterance_idxs.shape[1])
+            self.ids_host[:, :w].copy_(utterance_idxs[:, :w])
+        else:
+            if len(utterance_idxs) != B:
+                raise ValueError("PinnedBatchStager: got %d token rows for a batch of %d" % (len(utterance_idxs), B))
+            for i, row in enumerate(utterance_idxs):
+                row = torch.as_tensor(row, dtype=torch.int64).reshape(-1)
+                w = min(L, row.numel())
+                self.ids_host[i, :w].copy_(row[:w])
+        torch.clamp(lens, max=L, out=self.lens_host)
+        # the invariant the kernels rely on: every position >= len holds PAD
+        pos = torch.arange(L, dtype=torch.int64)[None, :]
+        self.ids_host.masked_fill_(pos >= self.lens_host[:, None], PAD_TOKEN_ID)
+        if feats is not None:
+            if self.x_host is None:
+                raise ValueError("PinnedBatchStager was built without a feature buffer")
+            self.x_host.copy_(feats)              # casts (e.g. fp32 -> bf16) on the host
+        return self.ids_host, self.lens_host

@@ -169,6 +169,34 @@ def run_gradcam_case(name, seed, N, E):
     print(name, "cam max", float(out["cam_norm"].max()), "nonzero frac", float((out["cam_norm"] > 0).mean()))
 
 
+def collate_batch(seed=112):
+    """a batch as the reference's datasets yield it (img, token row, length, raw utterance) with lengths
+    around and beyond MAX_LEN_UTTERANCE = 25; the tests rebuild it from the seed."""
+    rng = np.random.RandomState(seed)
+    lens = [3, 25, 31, 1, 26, 12, 40]
+    batch = []
+    for i, n in enumerate(lens):
+        row = rng.randint(4, 2350, size=n).astype(np.int64)
+        row[0] = O.SOS_TOKEN_ID; row[-1] = O.EOS_TOKEN_ID
+        batch.append((torch.full((3, 4, 4), float(i)), torch.from_numpy(row), n, "utt %d" % i))
+    return batch
+
+
+def run_collate_case(name, long=True):
+    """multiModalDataset_collate_fn of the UNMODIFIED reference (multimodal_data_module.py:98-109)."""
+    R.load_reference()
+    from multimodal import multimodal_data_module as ref_dm
+    batch = collate_batch()
+    if not long:
+        batch = [b for b in batch if b[2] <= 12]
+    img, ids, lens, raw = ref_dm.multiModalDataset_collate_fn(batch)
+    with open(os.path.join(GOLD, name + ".json"), "w") as fh:
+        json.dump(dict(long=long, img_shape=list(img.shape), img_first=[float(v) for v in img[:, 0, 0, 0]],
+                       ids=ids.tolist(), lens=lens.tolist(), raw=raw, ids_dtype=str(ids.dtype),
+                       lens_dtype=str(lens.dtype)), fh)
+    print(name, tuple(ids.shape), lens.tolist())
+
+
 def run_tokenize_case(name):
     """MultiModalLitModel.tokenize (multimodal_lit.py:161-190) on pre-tokenised text
     (whitespace split; spaCy itself is not available offline)."""
@@ -214,6 +242,8 @@ def main():
     run_forward_case("forward_4x1_e512", 109, 4, 1, 512)
     run_eval_case("eval_4way_e512", 110, 64, 512)
     run_gradcam_case("gradcam_e512_n3", 111, 3, 512)
+    run_collate_case("collate_long", True)
+    run_collate_case("collate_short", False)
     run_tokenize_case("tokenize")
     run_state_dict_case("state_dict_keys")
 

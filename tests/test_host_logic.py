@@ -208,3 +208,52 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+# ------------------------------------------------------------------------------ input staging
+@pytest.mark.parametrize("name", ["collate_long", "collate_short"])
+def test_collate_matches_reference_golden(name):
+    """multiModalDataset_collate_fn mirror == the reference's own function (multimodal_data_module.py:98-109) on a
+    batch with lengths around and beyond 25 (golden written by oracle/make_golden.py from the live reference)."""
+    from oracle.make_golden import collate_batch
+    with open(os.path.join(GOLD, name + ".json")) as fh:
+        g = json.load(fh)
+    batch = collate_batch()
+    if not g["long"]:
+        batch = [b for b in batch if b[2] <= 12]
+    img, ids, lens, raw = cv.multiModalDataset_collate_fn(batch)
+    assert list(img.shape) == g["img_shape"] and [float(v) for v in img[:, 0, 0, 0]] == g["img_first"]
+    assert str(ids.dtype) == g["ids_dtype"] and str(lens.dtype) == g["lens_dtype"]
+    assert ids.tolist() == g["ids"] and lens.tolist() == g["lens"] and raw == g["raw"]
+
+
+def test_pinned_stager_holds_what_the_reference_collate_hands_to_the_model():
+    """fixed-shape [B,25] staging: same ids (zero-padded to 25) and the same clamped lengths as the reference's
+    collate, from per-sample rows and from an already padded tensor; PAD beyond every length; stale contents of a
+    previous batch never leak."""
+    from oracle.make_golden import collate_batch
+    with open(os.path.join(GOLD, "collate_long.json")) as fh:
+        g = json.load(fh)
+    batch = collate_batch()
+    B = len(batch)
+    st = cv.PinnedBatchStager(B, feat_shape=(8,), feat_dtype=torch.bfloat16, pin=False)
+    st.ids_host.fill_(7)                                       # garbage from an earlier batch
+    feats = torch.arange(B * 8, dtype=torch.float32).reshape(B, 8)
+    ids, lens = st.stage([b[1] for b in batch], [b[2] for b in batch], feats)
+    want = torch.zeros(B, 25, dtype=torch.int64)
+    gi = torch.tensor(g["ids"])
+    want[:, :gi.shape[1]] = gi
+    assert ids.shape == (B, 25) and ids.dtype == torch.int64 and torch.equal(ids, want)
+    assert lens.tolist() == g["lens"] and lens.dtype == torch.int64
+    assert st.x_host.dtype == torch.bfloat16 and torch.equal(st.x_host.float(), feats.to(torch.bfloat16).float())
+    pos = torch.arange(25)[None, :]
+    assert bool((ids[pos >= lens[:, None]] == 0).all())
+    # the same from the reference-style padded tensor (short batch: width 12 < 25)
+    with open(os.path.join(GOLD, "collate_short.json")) as fh:
+        gs = json.load(fh)
+    st2 = cv.PinnedBatchStager(len(gs["lens"]), pin=False)
+    st2.ids_host.fill_(9)
+    ids2, lens2 = st2.stage(torch.tensor(gs["ids"]), gs["lens"])
+    assert ids2[:, :12].tolist() == gs["ids"] and bool((ids2[:, 12:] == 0).all()) and lens2.tolist() == gs["lens"]
+    with pytest.raises(ValueError):
+        st2.stage(torch.tensor(gs["ids"])[:2], gs["lens"])
