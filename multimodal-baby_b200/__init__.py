@@ -16,7 +16,7 @@ from .multimodal import (MultiModalModel, PooledTrunk, TextEncoder, VisionEncode
                          split_trunk_forward)
 from .graphed import GraphedContrastiveStep                         # noqa: F401
 from .optim import FusedAdamW                                       # noqa: F401
-from .staging import PinnedBatchStager, multiModalDataset_collate_fn  # noqa: F401
+from .staging import PinnedBatchStager, batch_trials, multiModalDataset_collate_fn  # noqa: F401
 from .multimodal_lit import MultiModalLitModel, WhitespaceTokenizer, load_vocab      # noqa: F401
 
 __version__ = "0.1.0"

@@ -90,3 +90,42 @@ class PinnedBatchStager:
                 raise ValueError("PinnedBatchStager was built without a feature buffer")
             self.x_host.copy_(feats)              # casts (e.g. fp32 -> bf16) on the host
         return self.ids_host, self.lens_host
+
+
+def batch_trials(items, max_len: Optional[int] = None):
+    """Host front-end of the batched Labeled-S evaluation.  `items` are what the reference's
+    `LabeledSEvalDataset.__getitem__` returns (multimodal_data_module.py:124-156): (imgs [n_way,3,H,W] with the
+    target first, label row [L] int64, label_len, [raw_label]).  The reference feeds them to the model one trial at
+    a time (eval.py:196-214, multimodal_lit.py:466-511: 2200 trunk passes of 4 images and 2200 text encodings of
+    22 distinct labels).  Here the frames are stacked for ONE trunk pass and identical label rows are shared:
+
+        frames [N*n_way, 3, H, W], label_ids [C, L] int64 (zero padded), label_lens [C] int64,
+        label_index [N] int32 (row of label_ids per trial), raw_labels [N]
+
+    which is the input of `MultiModalLitModel.evaluate_trials` (`ops.eval_nway`, K7)."""
+    if len(items) == 0:
+        raise ValueError("batch_trials: no trials")
+    n_way = items[0][0].shape[0]
+    rows, lens, index, raw, seen = [], [], [], [], {}
+    for imgs, label, label_len, raw_label in items:
+        if imgs.shape[0] != n_way:
+            raise ValueError("batch_trials: trials with %d and %d candidates cannot share a batch" % (n_way, imgs.shape[0]))
+        label = torch.as_tensor(label, dtype=torch.int64).reshape(-1)
+        n = int(label_len)
+        if n < 1 or n > label.numel():
+            raise ValueError("batch_trials: label length %d does not fit a row of %d ids" % (n, label.numel()))
+        key = tuple(label[:n].tolist())
+        if key not in seen:
+            seen[key] = len(rows)
+            rows.append(label[:n])
+            lens.append(n)
+        index.append(seen[key])
+        raw.append(raw_label[0] if isinstance(raw_label, (list, tuple)) else raw_label)
+    L = max(lens) if max_len is None else int(max_len)
+    if max(lens) > L:
+        raise ValueError("batch_trials: a label of %d ids does not fit max_len=%d" % (max(lens), L))
+    label_ids = torch.full((len(rows), L), PAD_TOKEN_ID, dtype=torch.int64)
+    for i, r in enumerate(rows):
+        label_ids[i, :r.numel()] = r
+    frames = torch.cat([it[0] for it in items], dim=0)
+    return (frames, label_ids, torch.tensor(lens, dtype=torch.int64), torch.tensor(index, dtype=torch.int32), raw)

@@ -257,3 +257,29 @@ def test_pinned_stager_holds_what_the_reference_collate_hands_to_the_model():
     assert ids2[:, :12].tolist() == gs["ids"] and bool((ids2[:, 12:] == 0).all()) and lens2.tolist() == gs["lens"]
     with pytest.raises(ValueError):
         st2.stage(torch.tensor(gs["ids"])[:2], gs["lens"])
+
+
+def test_batch_trials_shares_label_rows_and_keeps_trial_order():
+    """Labeled-S items (imgs [4,3,H,W] target first, label row, len, [raw]) -> stacked frames + distinct label rows
+    + per-trial index: decoding the index gives back every trial's own label row; frames keep trial-major order."""
+    g = torch.Generator().manual_seed(0)
+    vocab = {"ball": 71, "car": 90, "kitty": 76}
+    names = ["ball", "car", "ball", "kitty", "car", "ball"]
+    items = []
+    for i, nm in enumerate(names):
+        imgs = torch.full((4, 3, 2, 2), float(i)) + torch.arange(4, dtype=torch.float32)[:, None, None, None] / 10
+        label = torch.tensor([2, vocab[nm], 3]) if i % 2 == 0 else torch.tensor([vocab[nm]])   # with / without sos-eos
+        items.append((imgs, label, label.numel(), [nm]))
+    frames, ids, lens, index, raw = cv.batch_trials(items)
+    assert frames.shape == (24, 3, 2, 2) and ids.dtype == torch.int64 and index.dtype == torch.int32
+    assert raw == names and index.shape == (6,)
+    assert ids.shape[0] == len({tuple(it[1].tolist()) for it in items}) < len(items)      # rows are shared
+    for i, it in enumerate(items):
+        row = ids[index[i]]
+        n = int(lens[index[i]])
+        assert row[:n].tolist() == it[1].tolist() and bool((row[n:] == 0).all())
+        assert torch.equal(frames[4 * i:4 * i + 4], it[0])                                  # target stays first
+    with pytest.raises(ValueError):
+        cv.batch_trials(items + [(torch.zeros(3, 3, 2, 2), torch.tensor([5]), 1, ["x"])])
+    with pytest.raises(ValueError):
+        cv.batch_trials(items, max_len=2)
