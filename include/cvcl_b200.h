@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CVCL_ABI_VERSION 3
+#define CVCL_ABI_VERSION 4
 #define CVCL_OK 0
 #define CVCL_ERR_INVALID (-1)
 #define CVCL_ERR_UNSUPPORTED (-2)
@@ -179,6 +179,34 @@ int cvcl_flat_contrastive_step(const void* x, int x_is_bf16, const int64_t* ids,
                                float* dW, float* dbias, float* dtable, float* dscale,
                                int* status, void* stream);
 
+/* ---- fused flat train step as ONE persistent kernel ---------------------------------------------
+ * Same contract as cvcl_flat_contrastive_step (multimodal.py:796-822 + loss.backward()), executed by a
+ * single cooperative launch (one CTA per SM, grid-wide barriers between the phases; csrc/fused_step.cuh):
+ * no weight cast, no memsets, the logits tile stays in TMEM from the statistics to dL/dlogits.
+ * x16 [B,K] and w16 [E,K] are bf16 (the caller keeps a bf16 shadow of the fp32 master weight: refreshed by
+ * cvcl_adamw_step's bf16_shadow output, or cast once after loading); bias/table fp32 masters.
+ * log_scale_dev (nullable) is a DEVICE scalar s = -log(temperature): when given it is read by the kernel
+ * (trainable temperature without a host sync, multimodal.py:711-715) and log_scale is ignored.
+ * Shapes covered: E in {128,256,384,512}, K % 64 == 0, B <= 1024 (cvcl_flat_fused_supported); anything
+ * else returns CVCL_ERR_UNSUPPORTED (callers then use cvcl_flat_contrastive_step).
+ * workspace: cvcl_flat_fused_workspace_bytes bytes, 256-byte aligned, its first 512 bytes zeroed ONCE before
+ * the first call (the kernel leaves them reusable); one step in flight per workspace.
+ * phase_limit: 0 = whole step; k = 1..5 leaves after phase k (measurement / debugging; outputs then
+ * partial).  Deterministic except for the embedding scatter (fp32 atomics, as the reference's
+ * embedding_dense_backward on CUDA). */
+int cvcl_flat_fused_supported(int B, int L, int E, int K, int V);
+size_t cvcl_flat_fused_workspace_bytes(int B, int L, int E, int K, int V);
+/* byte offsets of the workspace blocks (tests / tools): out[0..13] = ctrl, hpart, img16, txt16, invn, part, diag,
+ * lse, rb_part, dspart, dqpart, du16, dbpart, total; out[14..19] = Bp, KS, nPart, dw_bn, grid, nCB.
+ * ctrl + 128 holds 16 globaltimer stamps (ns) of CTA 0: [0] start, [k] after grid barrier k, [15] end. */
+int cvcl_flat_fused_layout(int B, int L, int E, int K, int V, long long* out, int n);
+int cvcl_flat_step_fused(const void* x16, const void* w16, const int64_t* ids, const int64_t* lens,
+                         const float* bias, const float* table, int B, int L, int E, int K, int V,
+                         int normalize, float log_scale, const float* log_scale_dev, int need_grads,
+                         void* workspace, float* out5, float* img_feat_f32, float* txt_feat_f32,
+                         float* dW, float* dbias, float* dtable, float* dscale, int* status, int phase_limit,
+                         void* stream);
+
 /* ---- K6 spatial "max" similarity --------------------------------------------------------------
  * replaces multimodal.py:771-780 (einsum 'iehw,tle->itlhw' + amax over (h,w) + sum over l / len)
  * without materialising the [B,B,L,H,W] tensor.  tok [Bt*L, E] bf16 (per-token normalised text
@@ -218,7 +246,7 @@ int cvcl_p2p_gather(const void* const* peer_ptrs, int world, int skip_rank, long
  * symmetric memory.  A channel's flag area holds cvcl_peer_flag_words() uint32 words, zeroed once
  * before first use (followed by any cross-rank barrier); `epoch` is a LOCAL uint32 array of
  * cvcl_peer_max_blocks() words, zeroed once; `status` (local int, nullable) becomes non-zero if a
- * barrier did not complete within timeout_ms (0 = 10 s), after which the kernel traps (or, with
+ * barrier did not complete within timeout_ms (0 = 10 minutes), after which the kernel traps (or, with
  * CVCL_PEER_NO_TRAP or'ed into timeout_ms, continues: probe mode, results undefined).  All ranks
  * must issue the same sequence of calls per channel with the same sizes.  Graph capturable.
  *   allgather    : barrier, then dst[s*dst_seg_stride + r*seg_bytes ..] <- segment s (at
@@ -261,6 +289,16 @@ int cvcl_peer_barrier(void* const* peer_flags, unsigned int* epoch, int* status,
 int cvcl_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
                     float beta2, float eps, float weight_decay, int step, float grad_scale, void* bf16_shadow,
                     void* stream);
+
+/* the same update for `count` (<= 8) tensors in ONE launch with the step number kept on the DEVICE
+ * (step_dev[0] = completed steps, incremented by the kernel; ticket[0] = 0 on entry): the launch can be
+ * captured in a CUDA graph and replayed, which makes a whole train step -- cvcl_flat_step_fused + this --
+ * one graph.  All arrays are HOST arrays of `count` entries; p/g/m/v/bf16_shadow entries are device pointers
+ * (bf16_shadow, or single entries of it, may be NULL). */
+int cvcl_adamw_multi_step(int count, float* const* p, const float* const* g, float* const* m, float* const* v,
+                          const long long* n, void* const* bf16_shadow, const float* lr, const float* weight_decay,
+                          float beta1, float beta2, float eps, float grad_scale, int* step_dev,
+                          unsigned int* ticket, void* stream);
 
 /* ---- Grad-CAM attention maps for the flat head ---------------------------------
  * replaces multimodal/attention_maps.py:111-165 (gradCAM: forward through layer4 -> avgpool -> fc,

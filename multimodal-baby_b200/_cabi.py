@@ -9,7 +9,7 @@ from ctypes import c_float, c_int, c_int64, c_size_t, c_void_p, c_char_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libcvcl_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class CvclLibraryMissing(RuntimeError):
@@ -55,6 +55,11 @@ PROTOTYPES = {
     "cvcl_flat_step_workspace_bytes": (c_size_t, [_I, _I, _I, _I, _I]),
     "cvcl_flat_contrastive_step": (c_int, [_P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P,
                                            _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "cvcl_flat_fused_supported": (c_int, [_I, _I, _I, _I, _I]),
+    "cvcl_flat_fused_workspace_bytes": (c_size_t, [_I, _I, _I, _I, _I]),
+    "cvcl_flat_fused_layout": (c_int, [_I, _I, _I, _I, _I, _P, _I]),
+    "cvcl_flat_step_fused": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _I, _P, _P, _P,
+                                     _P, _P, _P, _P, _P, _P, _I, _P]),
     "cvcl_spatial_max_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "cvcl_spatial_max_bwd_workspace_bytes": (c_size_t, [_I, _I, _I, _I]),
     "cvcl_spatial_max_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
@@ -72,6 +77,7 @@ PROTOTYPES = {
     "cvcl_peer_allreduce_push_f32": (c_int, [_P, _P, _P, _P, _P, _I, _I, ctypes.c_longlong, ctypes.c_uint, _P]),
     "cvcl_peer_barrier": (c_int, [_P, _P, _P, _I, _I, ctypes.c_uint, _P]),
     "cvcl_adamw_step": (c_int, [_P, _P, _P, _P, ctypes.c_longlong, _F, _F, _F, _F, _F, _I, _F, _P, _P]),
+    "cvcl_adamw_multi_step": (c_int, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _P, _P, _P]),
     "cvcl_gradcam_workspace_bytes": (c_size_t, [_I, _I, _I]),
     "cvcl_gradcam_flat": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "cvcl_bicubic_upsample": (c_int, [_P, _I, _I, _I, _I, _I, _P, _P]),
@@ -88,13 +94,16 @@ def load(path=None):
         return _lib
     explicit = path or os.environ.get("CVCL_B200_LIB")
     path = explicit or LIB_PATH
-    if not os.path.exists(path) and not explicit:
-        # in-tree build on first use (nvcc cross-compiles sm_100a anywhere); still no CPU path
+    if not explicit:
+        # in-tree build on first use, and again when a source is newer than the library (nvcc
+        # cross-compiles sm_100a anywhere; locked + atomic rename, see build.py); still no CPU path
         try:
             from . import build as _build
-            _build.build_library()
+            if _build.is_stale():
+                _build.build_library()
         except Exception as exc:                                   # noqa: BLE001
-            raise CvclLibraryMissing("libcvcl_b200.so is missing and could not be built: %s" % exc)
+            if not os.path.exists(path):
+                raise CvclLibraryMissing("libcvcl_b200.so is missing and could not be built: %s" % exc)
     if not os.path.exists(path):
         raise CvclLibraryMissing(
             "libcvcl_b200.so not found at %s -- build it with `python multimodal-baby_b200/build.py` "

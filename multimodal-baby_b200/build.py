@@ -39,17 +39,31 @@ def is_stale():
 
 
 def build_library(force=False, verbose=False):
-    """Compile csrc/cvcl_b200.cu -> lib/libcvcl_b200.so.  Returns the library path."""
+    """Compile csrc/cvcl_b200.cu -> lib/libcvcl_b200.so.  Returns the library path.
+    Safe under torchrun: ranks serialise on a file lock, nvcc writes a temporary file and the finished
+    library is renamed into place (a rank never dlopens a half-written .so)."""
     if not force and not is_stale():
         return LIB_PATH
+    import fcntl
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB_PATH, os.path.join(CSRC, "cvcl_b200.cu")]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():         # another rank built it while we waited
+                return LIB_PATH
+            tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+            cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+                  ["-diag-suppress", "39", "-o", tmp, os.path.join(CSRC, "cvcl_b200.cu")]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+            os.replace(tmp, LIB_PATH)
+            if verbose:
+                print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 

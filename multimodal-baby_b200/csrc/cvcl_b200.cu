@@ -4,6 +4,7 @@
 #include "gemm_launch.cuh"
 #include "kernels_simt.cuh"
 #include "peer_collectives.cuh"
+#include "fused_step.cuh"
 #include <cmath>
 #include <cstdlib>
 
@@ -643,6 +644,163 @@ int cvcl_flat_contrastive_step(const void* x, int x_is_bf16, const int64_t* ids,
     return CVCL_OK;
 }
 
+// ------------------------------------------------------------------------------------ fused flat step, one kernel
+namespace {
+struct FusedPlan {
+    int Bp, nMB, nEB, nCB, KS, kc_per_split, num_kc, T, nPart, dw_bn, grid;
+    size_t off_ctrl, off_hpart, off_img16, off_txt16, off_invn, off_part, off_diag, off_lse, off_rbpart, off_dspart,
+           off_dqpart, off_du16, off_dbpart, bytes;
+};
+// -> 0 when the persistent kernel covers the shape, else the reason (unsupported, not an error)
+const char* plan_fused(FusedPlan* f, int B, int E, int K, int V) {
+    (void)V;
+    const int G = sm_count();
+    if (B < 1) return "B < 1";
+    if (E % 128 != 0 || E < 128 || E > 512) return "E must be 128, 256, 384 or 512";
+    if (K % 64 != 0 || K < 64) return "K must be a multiple of 64";
+    f->grid = G;
+    f->Bp = ceil_div(B, 128) * 128;
+    f->nMB = f->Bp / 128; f->nEB = E / 128; f->nCB = f->nMB;
+    f->T = 1; f->nPart = f->nCB / f->T;
+    if (2 * f->nMB * f->nPart > G - 1) return "batch too large for one similarity tile per SM";
+    const int tiles = f->nMB * f->nEB;
+    if (tiles > G) return "batch too large for the head phase";
+    f->num_kc = K / 64;
+    int ks = G / tiles; if (ks > f->num_kc) ks = f->num_kc;
+    f->kc_per_split = ceil_div(f->num_kc, ks);
+    f->KS = ceil_div(f->num_kc, f->kc_per_split);
+    f->dw_bn = (f->nEB * (K / 64) <= G - 1 || K % 128 != 0) ? 64 : 128;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+    const size_t Bp = f->Bp;
+    f->off_ctrl = take(512);
+    f->off_hpart = take(4ull * f->KS * Bp * E);
+    f->off_img16 = take(2ull * Bp * E);
+    f->off_txt16 = take(2ull * Bp * E);
+    f->off_invn = take(4ull * 2 * Bp);
+    f->off_part = take(sizeof(RowStat) * 2ull * f->nCB * Bp);
+    f->off_diag = take(4ull * 2 * Bp);
+    f->off_lse = take(4ull * 2 * Bp);
+    f->off_rbpart = take(4ull * 2 * f->nMB * 6);
+    f->off_dspart = take(4ull * f->nMB * f->nPart);
+    f->off_dqpart = take(4ull * 2 * f->nPart * Bp * E);
+    f->off_du16 = take(2ull * Bp * E);
+    f->off_dbpart = take(4ull * G * E);
+    f->bytes = off;
+    return nullptr;
+}
+}  // namespace
+
+int cvcl_flat_fused_supported(int B, int L, int E, int K, int V) {
+    (void)L;
+    FusedPlan f{};
+    return plan_fused(&f, B, E, K, V) == nullptr ? 1 : 0;
+}
+
+size_t cvcl_flat_fused_workspace_bytes(int B, int L, int E, int K, int V) {
+    (void)L;
+    FusedPlan f{};
+    return plan_fused(&f, B, E, K, V) == nullptr ? f.bytes : 0;
+}
+
+int cvcl_flat_fused_layout(int B, int L, int E, int K, int V, long long* out, int n) {
+    (void)L;
+    FusedPlan f{};
+    const char* why = plan_fused(&f, B, E, K, V);
+    if (why) return fail(CVCL_ERR_UNSUPPORTED, "flat_fused_layout: %s", why);
+    const long long v[] = {(long long)f.off_ctrl, (long long)f.off_hpart, (long long)f.off_img16, (long long)f.off_txt16,
+                           (long long)f.off_invn, (long long)f.off_part, (long long)f.off_diag, (long long)f.off_lse,
+                           (long long)f.off_rbpart, (long long)f.off_dspart, (long long)f.off_dqpart, (long long)f.off_du16,
+                           (long long)f.off_dbpart, (long long)f.bytes, f.Bp, f.KS, f.nPart, f.dw_bn, f.grid, f.nCB};
+    for (int i = 0; i < n && i < (int)(sizeof(v) / sizeof(v[0])); ++i) out[i] = v[i];
+    return CVCL_OK;
+}
+
+int cvcl_flat_step_fused(const void* x16, const void* w16, const int64_t* ids, const int64_t* lens,
+                         const float* bias, const float* table, int B, int L, int E, int K, int V,
+                         int normalize, float log_scale, const float* log_scale_dev, int need_grads,
+                         void* workspace, float* out5, float* img_feat_f32, float* txt_feat_f32,
+                         float* dW, float* dbias, float* dtable, float* dscale, int* status, int phase_limit,
+                         void* stream) {
+    CVCL_REQUIRE(x16 && w16 && ids && lens && table && workspace && out5, "flat_step_fused: null pointer");
+    CVCL_REQUIRE(!need_grads || (dW && dbias && dtable && dscale), "flat_step_fused: null gradient output");
+    CVCL_REQUIRE(L >= 1 && V >= 1, "flat_step_fused: bad shape");
+    FusedPlan f{};
+    if (const char* why = plan_fused(&f, B, E, K, V))
+        return fail(CVCL_ERR_UNSUPPORTED, "flat_step_fused: %s (B=%d E=%d K=%d)", why, B, E, K);
+    CVCL_REQUIRE(((reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(table) |
+                   reinterpret_cast<uintptr_t>(bias)) & 15) == 0, "flat_step_fused: 16-byte alignment required");
+    CVCL_REQUIRE(!need_grads || ((reinterpret_cast<uintptr_t>(dtable) | reinterpret_cast<uintptr_t>(dW)) & 15) == 0,
+                 "flat_step_fused: gradient outputs must be 16-byte aligned");
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    fused::StepParams p{};
+    p.ids = reinterpret_cast<const long long*>(ids); p.lens = reinterpret_cast<const long long*>(lens);
+    p.table = table; p.bias = bias; p.log_scale_dev = log_scale_dev; p.log_scale = log_scale;
+    p.B = B; p.L = L; p.E = E; p.K = K; p.V = V; p.normalize = normalize; p.need_grads = need_grads;
+    p.Bg = B; p.diag_off = 0;
+    p.Bp = f.Bp; p.nMB = f.nMB; p.nEB = f.nEB; p.nCB = f.nCB; p.KS = f.KS; p.kc_per_split = f.kc_per_split;
+    p.num_kc = f.num_kc; p.T = f.T; p.nPart = f.nPart; p.dw_bn = f.dw_bn; p.phase_limit = phase_limit;
+    p.hpart = reinterpret_cast<float*>(ws + f.off_hpart);
+    p.q16[0] = reinterpret_cast<__nv_bfloat16*>(ws + f.off_img16);
+    p.q16[1] = reinterpret_cast<__nv_bfloat16*>(ws + f.off_txt16);
+    p.ldq = E;
+    p.kf16[0] = p.q16[1]; p.kf16[1] = p.q16[0]; p.ldk = E;
+    for (int z = 0; z < 2; ++z) {
+        p.invn[z] = reinterpret_cast<float*>(ws + f.off_invn) + z * f.Bp;
+        p.part[z] = reinterpret_cast<RowStat*>(ws + f.off_part) + static_cast<size_t>(z) * f.nCB * f.Bp;
+        p.diag[z] = reinterpret_cast<float*>(ws + f.off_diag) + z * f.Bp;
+        p.lse[z] = reinterpret_cast<float*>(ws + f.off_lse) + z * f.Bp;
+        p.lse_all[z] = nullptr;
+    }
+    p.rb_part = reinterpret_cast<float*>(ws + f.off_rbpart);
+    p.dspart = reinterpret_cast<float*>(ws + f.off_dspart);
+    p.dqpart = reinterpret_cast<float*>(ws + f.off_dqpart);
+    p.du16 = reinterpret_cast<__nv_bfloat16*>(ws + f.off_du16);
+    p.dbpart = reinterpret_cast<float*>(ws + f.off_dbpart);
+    p.sync = reinterpret_cast<unsigned int*>(ws + f.off_ctrl);
+    p.fault = reinterpret_cast<int*>(ws + f.off_ctrl + 64);
+    p.timing = reinterpret_cast<unsigned long long*>(ws + f.off_ctrl + 128);
+    p.status = status;
+    p.out5 = out5; p.img_f32 = img_feat_f32; p.txt_f32 = txt_feat_f32;
+    p.dW = dW; p.dbias = dbias; p.dtable = dtable; p.dscale = dscale;
+    p.inv_rows = 1.f / static_cast<float>(p.Bg);
+
+    fused::StepMaps maps;
+    int rc;
+    if ((rc = make_tmap(&maps.x_k, x16, 2, B, K, K, 64, 128))) return rc;
+    if ((rc = make_tmap(&maps.w_k, w16, 2, E, K, K, 64, 128))) return rc;
+    if ((rc = make_tmap(&maps.hp_out, p.hpart, 4, static_cast<uint64_t>(f.KS) * f.Bp, E, E, 32, 128))) return rc;
+    for (int z = 0; z < 2; ++z) {
+        if ((rc = make_tmap(&maps.q_k[z], p.q16[z], 2, B, E, p.ldq, 64, 128))) return rc;
+        if ((rc = make_tmap(&maps.kf_k[z], p.kf16[z], 2, p.Bg, E, p.ldk, 64, 128))) return rc;
+        if ((rc = make_tmap(&maps.kf_mn[z], p.kf16[z], 2, p.Bg, E, p.ldk, 64, 64))) return rc;
+    }
+    if ((rc = make_tmap(&maps.dq_out, p.dqpart, 4, 2ull * f.nPart * f.Bp, E, E, 32, 128))) return rc;
+    if ((rc = make_tmap(&maps.du_mn, p.du16, 2, B, E, E, 64, 64))) return rc;
+    if ((rc = make_tmap(&maps.x_mn, x16, 2, B, K, K, 64, 64))) return rc;
+    if (need_grads) { if ((rc = make_tmap(&maps.dw_out, dW, 4, E, K, K, 32, 128))) return rc; }
+    else maps.dw_out = maps.hp_out;
+
+    static thread_local bool attr_done = false;
+    if (!attr_done) {
+        CVCL_CHECK_CUDA(cudaFuncSetAttribute(fused::flat_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             fused::kSmemBytes));
+        attr_done = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(f.grid);
+    cfg.blockDim = dim3(fused::kThreads);
+    cfg.dynamicSmemBytes = fused::kSmemBytes;
+    cfg.stream = as_stream(stream);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;          // all CTAs co-resident: the grid barriers cannot starve
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CVCL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fused::flat_step_kernel, maps, p));
+    count_launch();
+    return CVCL_OK;
+}
+
 // ------------------------------------------------------------------------------------ K6 spatial max
 int cvcl_spatial_max_fwd(const void* tok, const void* img, const int64_t* lens, int Bt, int L, int Bi, int HW,
                          int E, float* match, unsigned char* amax_it, unsigned char* amax_ti, void* stream) {
@@ -761,7 +919,7 @@ int fill_peer_table(PeerTable* t, void* const* peer_data, void* const* peer_flag
         }
     }
     t->epoch = epoch; t->status = status;
-    t->timeout_ms = (timeout_ms & 0x7fffffffu) ? timeout_ms : ((timeout_ms & 0x80000000u) | 10000u);
+    t->timeout_ms = (timeout_ms & 0x7fffffffu) ? timeout_ms : ((timeout_ms & 0x80000000u) | 600000u);
     return CVCL_OK;
 }
 }  // namespace
@@ -895,6 +1053,36 @@ int cvcl_adamw_step(float* p, const float* g, float* m, float* v, long long n, f
     CVCL_CHECK_CUDA(launch_pdl(adamw_step_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, as_stream(stream),
                                p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, grad_scale,
                                static_cast<__nv_bfloat16*>(bf16_shadow)));
+    count_launch();
+    return CVCL_OK;
+}
+
+int cvcl_adamw_multi_step(int count, float* const* p, const float* const* g, float* const* m, float* const* v,
+                          const long long* n, void* const* bf16_shadow, const float* lr, const float* weight_decay,
+                          float beta1, float beta2, float eps, float grad_scale, int* step_dev,
+                          unsigned int* ticket, void* stream) {
+    CVCL_REQUIRE(count >= 1 && count <= kAdamMaxTensors, "adamw_multi_step: 1..%d tensors (got %d)", kAdamMaxTensors, count);
+    CVCL_REQUIRE(p && g && m && v && n && lr && weight_decay && step_dev && ticket, "adamw_multi_step: null pointer");
+    AdamMultiParams a{};
+    a.count = count; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.grad_scale = grad_scale;
+    a.step_dev = step_dev; a.ticket = ticket;
+    long long off = 0;
+    for (int t = 0; t < count; ++t) {
+        CVCL_REQUIRE(p[t] && g[t] && m[t] && v[t] && n[t] > 0, "adamw_multi_step: bad tensor %d", t);
+        CVCL_REQUIRE(((reinterpret_cast<uintptr_t>(p[t]) | reinterpret_cast<uintptr_t>(g[t]) |
+                       reinterpret_cast<uintptr_t>(m[t]) | reinterpret_cast<uintptr_t>(v[t])) & 15) == 0 || n[t] < 4,
+                     "adamw_multi_step: tensor %d must be 16-byte aligned", t);
+        a.p[t] = p[t]; a.g[t] = g[t]; a.m[t] = m[t]; a.v[t] = v[t]; a.n[t] = n[t];
+        a.shadow[t] = bf16_shadow ? static_cast<__nv_bfloat16*>(bf16_shadow[t]) : nullptr;
+        a.lr[t] = lr[t]; a.wd[t] = weight_decay[t];
+        a.n4_begin[t] = off;
+        off += (n[t] + 3) / 4;
+    }
+    a.n4_begin[count] = off;
+    for (int t = count + 1; t <= kAdamMaxTensors; ++t) a.n4_begin[t] = off;
+    long long blocks = (off + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    CVCL_CHECK_CUDA(launch_pdl(adamw_multi_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, as_stream(stream), a));
     count_launch();
     return CVCL_OK;
 }

@@ -1,0 +1,892 @@
+// The flat contrastive train step as ONE persistent kernel (sm_100a).
+//
+// reference: MultiModalModel.calculate_contrastive_loss (multimodal/multimodal.py:796-822) + loss.backward()
+// for embedding_type = "flat": text encoder (:496-503), projection head (:186-192), F.normalize (:736,:743),
+// similarity + symmetric InfoNCE (:755,:783-787,:801-818) and their autograd.
+//
+// Why one kernel: at 512 pairs the step is ~3.2 GFLOP / ~31 MB (about 5 us of roofline work) and the
+// ten-kernel version spent its 78 us on launch gaps, per-launch TMEM/barrier set-up and 16-32-CTA grids
+// (profiles/r01_step_phases_n1.txt).  Here one co-resident grid (one CTA per SM, cooperative launch) walks
+// through the phases with grid-wide barriers (one atomic counter in L2, ~1 us each); TMEM, the mbarrier
+// ring and the tensor maps are set up once.
+//
+//   P0  head GEMM, split over the contraction so that ~128 CTAs each stream 1/KS of K (tcgen05, fp32
+//       partial tile -> its own slab by TMA store: no atomics, no memset)         || text encoder on the
+//       epilogue warps of every CTA (one warp per utterance, 8 table rows in flight per lane)
+//   P1  slab sum (fixed order) + bias + L2 normalise -> bf16 image features, 1/norm     (warp per row)
+//   P2  similarity tiles: both directions as row problems (direction 0: images x texts, direction 1:
+//       texts x images; 2*(B/128)^2 CTAs), the 128x128 fp32 tile stays in TMEM; online-softmax row
+//       statistics per tile.  Idle CTAs zero the embedding-gradient table meanwhile.
+//   P3  merge the statistics (row LSEs of both directions), dL/dlogits from the SAME TMEM tile (no
+//       recompute GEMM), written as the bf16 A operand straight into swizzled shared memory, then
+//       dQ_partial = Gs_tile . K_block (tcgen05, N = E) -> slab by TMA store
+//   P4  slab sum + the -2I term in fp32 + F.normalize backward; image rows -> bf16 du (operand of dW)
+//       and per-CTA bias partials; text rows -> /len and the embedding scatter (red.global.add.v4)
+//   P5  dW = du^T x (both operands MN-major, read in place) -> fp32 tiles by TMA store; the last CTA adds
+//       the per-block partial sums of loss / accuracy / entropy / ds / db in a fixed order.
+//
+// Sharded use enters through the same code: Q = the local pairs, K = the gathered features,
+// diag_off = rank * B (see StepParams::kf16 / lse_all).
+#pragma once
+#include "gemm_sm100.cuh"
+#include "kernels_simt.cuh"
+
+namespace cvcl {
+namespace fused {
+
+constexpr int kThreads = 192;                    // warp 0 TMA, warp 1 MMA + TMEM, warps 2..5 epilogue
+constexpr int kWarps = kThreads / 32;
+constexpr int kStages = 4;
+constexpr int kStageBytes = 32768;               // A 128x64 bf16 + B 128x64 bf16 (or one 64 x 256 MN-major slab)
+constexpr int kRingBytes = kStages * kStageBytes;
+constexpr int kGsOff = kRingBytes;               // dL/dlogits as the A operand: up to 2 tiles x 2 k-chunks x 16 KB
+constexpr int kGsBytes = 65536;
+constexpr int kMiscOff = kGsOff + kGsBytes;
+constexpr int kMiscBytes = 16384;
+constexpr int kSmemBytes = kMiscOff + kMiscBytes + 1024;     // + alignment slack
+constexpr int kMaxT = 2;                         // similarity tiles per CTA (same row block)
+constexpr int kNumSync = 8;
+
+struct alignas(64) StepMaps {
+    CUtensorMap x_k;         // x16   [B, K]        box 64 x 128   (P0 A)
+    CUtensorMap w_k;         // w16   [E, K]        box 64 x 128   (P0 B)
+    CUtensorMap hp_out;      // hpart [KS*Bp, E] f32 box 32 x 128  (P0 out)
+    CUtensorMap q_k[2];      // local features of direction z (0: images, 1: texts) [B, E] box 64 x 128 (P2 A)
+    CUtensorMap kf_k[2];     // key features of direction z (0: texts, 1: images) [Bg, E] box 64 x 128 (P2 B)
+    CUtensorMap kf_mn[2];    // the same tensors, box 64 x 64 (P3 B, MN-major)
+    CUtensorMap dq_out;      // dqpart [2*nPart*Bp, E] f32 box 32 x 128 (P3 out)
+    CUtensorMap du_mn;       // du16 [B, E]  box 64 x 64  (P5 A, MN-major)
+    CUtensorMap x_mn;        // x16  [B, K]  box 64 x 64  (P5 B, MN-major)
+    CUtensorMap dw_out;      // dW [E, K] f32 box 32 x 128 (P5 out)
+};
+
+struct StepParams {
+    // ---- inputs
+    const long long* ids; const long long* lens; const float* table; const float* bias;
+    const float* log_scale_dev;          // device scalar s (nullable: use log_scale)
+    float log_scale;
+    int B, L, E, K, V, normalize, need_grads;
+    int Bg, diag_off;                    // global batch and the column offset of the local positives
+    // ---- derived tiling
+    int Bp;                              // B rounded up to 128
+    int nMB, nEB, nCB;                   // row blocks (local), E / 128, column blocks (global)
+    int KS, kc_per_split, num_kc;        // head split-K
+    int T, nPart;                        // similarity tiles per CTA, partial slabs per row block
+    int dw_bn;                           // 64 or 128: width of a dW tile
+    int phase_limit;                     // measurement / debugging: leave after phase k (0 = run all)
+    // ---- workspace
+    float* hpart;                        // [KS][Bp][E]
+    __nv_bfloat16* q16[2]; int ldq;      // local features, bf16 (0: img16, 1: txt16)
+    const __nv_bfloat16* kf16[2]; int ldk;   // key features (0: texts, 1: images) [Bg, ldk]
+    float* invn[2];                      // [Bp] 1 / max(||u||, 1e-12) per direction
+    RowStat* part[2];                    // [nCB][Bp]
+    float* diag[2];                      // [Bp] logit at the positive
+    float* lse[2];                       // [Bp] (local rows)
+    const float* lse_all[2];             // [Bg] LSEs of every row of direction z (== lse[z] on one GPU)
+    float* rb_part;                      // [2*nMB][6]
+    float* dspart;                       // [nMB*nPart]
+    float* dqpart;                       // [2][nPart][Bp][E]
+    __nv_bfloat16* du16;                 // [Bp][E]
+    float* dbpart;                       // [grid][E]
+    unsigned int* sync;                  // [kNumSync] zero on entry, left zero on exit
+    unsigned long long* timing;          // [16] globaltimer stamps of CTA 0 (nullable)
+    int* status;                         // out-of-range token id -> 1 (nullable)
+    int* fault;                          // barrier time-out code (nullable)
+    // ---- outputs
+    float* out5;                         // loss, image_accuracy, text_accuracy, image_entropy, text_entropy
+    float* img_f32; float* txt_f32;      // [B,E] fp32 features (nullable)
+    float* dW; float* dbias; float* dtable; float* dscale;
+    float inv_rows;                      // 1 / Bg
+};
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+// bounded mbarrier wait: a protocol bug traps (loud failure) instead of hanging the device
+__device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
+    unsigned int it = 0;
+    while (!ptx::mbar_try_wait(bar, parity)) {
+        if (++it > 40000000u) __trap();
+    }
+}
+
+// Grid-wide barrier k (k = 0, 1, ... in program order): every CTA is resident (cooperative launch, one
+// CTA per SM), so spinning on one L2 counter cannot starve anybody.  The proxy fences order the generic
+// global writes of a phase against the TMA (async proxy) reads of the next and vice versa.
+__device__ __forceinline__ void grid_sync(const StepParams& p, int k) {
+    fence_proxy_async_all();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(p.sync, 1u);
+        const unsigned int target = static_cast<unsigned int>(k + 1) * gridDim.x;
+        unsigned int it = 0; unsigned long long t0 = 0;
+        while (ld_acquire_gpu(p.sync) < target) {
+            if ((++it & 4095u) == 0) {
+                const unsigned long long now = globaltimer_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 2000000000ull) {              // 2 s: a CTA never arrived
+                    if (p.fault) atomicExch(p.fault, 100 + k);
+                    __threadfence_system();
+                    __trap();
+                }
+            }
+        }
+        __threadfence();
+        if (blockIdx.x == 0 && p.timing) p.timing[k + 1] = globaltimer_ns();
+    }
+    __syncthreads();
+    fence_proxy_async_all();
+}
+
+struct Ring {
+    int stage; uint32_t phase;
+    __device__ __forceinline__ void next() { if (++stage == kStages) { stage = 0; phase ^= 1u; } }
+};
+
+// one utterance per warp: feat = normalise(sum_l table[ids[b,l]] / len[b]) in position order
+// (same arithmetic, same order as text_encoder_fwd_kernel; E <= 512)
+__device__ __forceinline__ void text_row(const StepParams& p, int b, int lane) {
+    const int nch = p.E >> 7;
+    constexpr int kInFlight = 8;
+    float4 acc[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const long long* idrow = p.ids + static_cast<size_t>(b) * p.L;
+    for (int l0 = 0; l0 < p.L; l0 += 32) {
+        long long my_id = (l0 + lane < p.L) ? __ldg(idrow + l0 + lane) : 0;
+        if (my_id < 0 || my_id >= p.V) { if (p.status) atomicExch(p.status, 1); my_id = 0; }
+        unsigned live = __ballot_sync(0xffffffffu, my_id != 0 && l0 + lane < p.L);
+        while (live) {
+            float4 r[kInFlight][4];
+#pragma unroll
+            for (int k = 0; k < kInFlight; ++k) {
+                int src_lane = -1;
+                if (live) { src_lane = __ffs(live) - 1; live &= live - 1; }
+                const long long id = __shfl_sync(0xffffffffu, my_id, src_lane < 0 ? 0 : src_lane);
+                const float4* src = reinterpret_cast<const float4*>(p.table + static_cast<size_t>(id) * p.E);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    r[k][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (src_lane >= 0 && c < nch) r[k][c] = __ldg(src + c * 32 + lane);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kInFlight; ++k)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    acc[c].x += r[k][c].x; acc[c].y += r[k][c].y; acc[c].z += r[k][c].z; acc[c].w += r[k][c].w;
+                }
+        }
+    }
+    const float flen = static_cast<float>(__ldg(p.lens + b));
+    float ssq = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        acc[c].x /= flen; acc[c].y /= flen; acc[c].z /= flen; acc[c].w /= flen;
+        ssq += acc[c].x * acc[c].x + acc[c].y * acc[c].y + acc[c].z * acc[c].z + acc[c].w * acc[c].w;
+    }
+    ssq = warp_sum(ssq);
+    const float denom = p.normalize ? fmaxf(sqrtf(ssq), 1e-12f) : 1.f;
+    if (lane == 0) p.invn[1][b] = 1.f / denom;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        if (c < nch) {
+            const int e = (c * 32 + lane) * 4;
+            const float4 t = make_float4(acc[c].x / denom, acc[c].y / denom, acc[c].z / denom, acc[c].w / denom);
+            if (p.txt_f32) *reinterpret_cast<float4*>(p.txt_f32 + static_cast<size_t>(b) * p.E + e) = t;
+            store_bf16x4(p.q16[1] + static_cast<size_t>(b) * p.ldq + e, t);
+        }
+    }
+}
+
+// fp32 accumulator columns [c0, c0 + ncols) of this thread's row -> swizzled staging (boxes of 32 fp32)
+__device__ __forceinline__ void stage_f32_cols(uint32_t tmem_row, int c0, int ncols, unsigned char* stage, int row) {
+#pragma unroll 1
+    for (int c = 0; c < ncols; c += 32) {
+        float v[32];
+        ptx::tmem_ld_32x32(tmem_row + c0 + c, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            uint4 q;
+            q.x = __float_as_uint(v[4 * j]); q.y = __float_as_uint(v[4 * j + 1]);
+            q.z = __float_as_uint(v[4 * j + 2]); q.w = __float_as_uint(v[4 * j + 3]);
+            swz_st16(stage, row, (c + 4 * j) * 4, q);
+        }
+    }
+}
+
+// online merge of per-tile softmax partials (strict >: the first tile wins ties, as torch.argmax does)
+__device__ __forceinline__ void merge_stats(const RowStat* base, size_t stride, int n, float& gm, float& gl, float& ga,
+                                            int& garg) {
+    gm = -INFINITY; gl = 0.f; ga = 0.f; garg = 0x7fffffff;
+    for (int t = 0; t < n; ++t) {
+        const float4 q = __ldcg(reinterpret_cast<const float4*>(base + static_cast<size_t>(t) * stride));
+        const float rm = q.x, rl = q.y, ra = q.z; const int rarg = __float_as_int(q.w);
+        if (rm > gm) { const float w = __expf(gm - rm); gl = gl * w + rl; ga = ga * w + ra; gm = rm; garg = rarg; }
+        else { const float w = __expf(rm - gm); gl = fmaf(rl, w, gl); ga = fmaf(ra, w, ga); }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    unsigned char* misc = smem + kMiscOff;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(misc);             // [kStages]
+    uint64_t* empty_bar = full_bar + kStages;                            // [kStages]
+    uint64_t* tfull_bar = empty_bar + kStages;                           // accumulator complete
+    uint64_t* gs_bar = tfull_bar + 1;                                    // Gs tiles written, S tile consumed
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gs_bar + 1);
+    float* lk = reinterpret_cast<float*>(misc + 256);                    // [256] column LSE terms (P3)
+    float* red = reinterpret_cast<float*>(misc + 256 + 1024);            // [64] block reductions
+    float* sdb = reinterpret_cast<float*>(misc + 2048);                  // [kWarps][512] bias partials (P4)
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int G = gridDim.x;
+    const int cta = blockIdx.x;
+
+    if (threadIdx.x == 0) {
+        if (cta == 0 && p.timing) p.timing[0] = globaltimer_ns();
+        for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+        ptx::mbar_init(tfull_bar, 1);
+        ptx::mbar_init(gs_bar, kEpiThreads);
+        ptx::fence_mbar_init();
+        ptx::prefetch_tmap(&maps.x_k); ptx::prefetch_tmap(&maps.w_k); ptx::prefetch_tmap(&maps.hp_out);
+    }
+    if (warp == 1) ptx::tmem_alloc<512>(tmem_ptr_smem);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    Ring ring{0, 0};                       // producer and MMA issuer walk the same sequence of stages
+    uint32_t tfull_uses = 0;               // MMA issuer and epilogue warps count accumulator hand-overs alike
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;      // epilogue warps: accumulator row of this thread
+    const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const int epi_tid = threadIdx.x - 64;
+    const float s_log = p.log_scale_dev ? __ldg(p.log_scale_dev) : p.log_scale;
+    const float scale = expf(s_log);
+    constexpr float kLog2e = 1.4426950408889634f;
+    int sync_k = 0;
+
+    // ============================================================================ P0
+    {
+        const int n_items = p.nMB * p.nEB * p.KS;
+        const bool has = cta < n_items;
+        const int ks = cta / (p.nMB * p.nEB);
+        const int tile = cta % (p.nMB * p.nEB);
+        const int mb = tile / p.nEB, nb = tile % p.nEB;
+        const int kc0 = ks * p.kc_per_split;
+        const int kc1 = min(kc0 + p.kc_per_split, p.num_kc);
+        if (warp == 0) {
+            if (lane == 0 && has) {
+                for (int kc = kc0; kc < kc1; ++kc) {
+                    mbar_wait_b(&empty_bar[ring.stage], ring.phase ^ 1u);
+                    unsigned char* sa = smem + ring.stage * kStageBytes;
+                    ptx::mbar_arrive_expect_tx(&full_bar[ring.stage], kStageBytes);
+                    ptx::tma_load_2d(sa, &maps.x_k, &full_bar[ring.stage], kc * kBK, mb * kBM);
+                    ptx::tma_load_2d(sa + 16384, &maps.w_k, &full_bar[ring.stage], kc * kBK, nb * 128);
+                    ring.next();
+                }
+            }
+            __syncwarp();
+        } else if (warp == 1) {
+            if (lane == 0 && has) {
+                constexpr uint32_t idesc = ptx::make_idesc_bf16(kBM, 128, false, false);
+                for (int kc = kc0; kc < kc1; ++kc) {
+                    mbar_wait_b(&full_bar[ring.stage], ring.phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = ptx::smem_u32(smem + ring.stage * kStageBytes);
+                    const uint64_t adesc = ptx::make_kmajor_sw128_desc(sa);
+                    const uint64_t bdesc = ptx::make_kmajor_sw128_desc(sa + 16384);
+#pragma unroll
+                    for (int k = 0; k < kBK / kUmmaK; ++k)
+                        ptx::umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kc > kc0 || k > 0) ? 1u : 0u);
+                    ptx::umma_commit(&empty_bar[ring.stage]);
+                    if (kc == kc1 - 1) ptx::umma_commit(tfull_bar);
+                    ring.next();
+                }
+            }
+            __syncwarp();
+        } else {
+            // text encoder on the epilogue warps while the TMA / MMA warps stream the head tile
+            for (int u = cta * 4 + (warp - 2); u < p.B; u += G * 4) text_row(p, u, lane);
+            if (has) {
+                mbar_wait_b(tfull_bar, tfull_uses & 1u);
+                ptx::tc_fence_after();
+                stage_f32_cols(tmem_row, 0, 128, smem, row);          // the ring is idle: all MMAs have retired
+                ptx::fence_proxy_async_smem();
+                ptx::tc_fence_before();
+                ptx::named_bar_sync(1, kEpiThreads);
+                if (epi_tid == 0) {
+#pragma unroll
+                    for (int b4 = 0; b4 < 4; ++b4)
+                        ptx::tma_store_2d(&maps.hp_out, smem + b4 * 16384, nb * 128 + b4 * 32, ks * p.Bp + mb * kBM);
+                    tma_store_commit();
+                    tma_store_wait_all();
+                }
+            }
+        }
+        if (has) ++tfull_uses;
+    }
+    // (the ring state is only ever used by lane 0 of warps 0 and 1, which walk identical sequences)
+    grid_sync(p, sync_k++);
+    if (p.phase_limit == 1) goto done;
+
+    // ============================================================================ P1
+    {
+        const int nch = p.E >> 7;
+        const size_t slab = static_cast<size_t>(p.Bp) * p.E;
+        for (int r = cta * kWarps + warp; r < p.B; r += G * kWarps) {
+            float4 acc[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float* base = p.hpart + static_cast<size_t>(r) * p.E;
+            for (int k0 = 0; k0 < p.KS; k0 += 4) {
+                float4 v[4][4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        v[k][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (k0 + k < p.KS && c < nch)
+                            v[k][c] = __ldcg(reinterpret_cast<const float4*>(base + (k0 + k) * slab) + c * 32 + lane);
+                    }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        acc[c].x += v[k][c].x; acc[c].y += v[k][c].y; acc[c].z += v[k][c].z; acc[c].w += v[k][c].w;
+                    }
+            }
+            float ssq = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (c < nch && p.bias) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias) + c * 32 + lane);
+                    acc[c].x += b4.x; acc[c].y += b4.y; acc[c].z += b4.z; acc[c].w += b4.w;
+                }
+                ssq += acc[c].x * acc[c].x + acc[c].y * acc[c].y + acc[c].z * acc[c].z + acc[c].w * acc[c].w;
+            }
+            ssq = warp_sum(ssq);
+            const float denom = p.normalize ? fmaxf(sqrtf(ssq), 1e-12f) : 1.f;
+            if (lane == 0) p.invn[0][r] = 1.f / denom;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (c < nch) {
+                    const int e = (c * 32 + lane) * 4;
+                    const float4 t = make_float4(acc[c].x / denom, acc[c].y / denom, acc[c].z / denom, acc[c].w / denom);
+                    if (p.img_f32) *reinterpret_cast<float4*>(p.img_f32 + static_cast<size_t>(r) * p.E + e) = t;
+                    store_bf16x4(p.q16[0] + static_cast<size_t>(r) * p.ldq + e, t);
+                }
+            }
+        }
+    }
+    grid_sync(p, sync_k++);
+    if (p.phase_limit == 2) goto done;
+
+    {
+        // ======================================================================== P2
+        // similarity CTA s: direction z, local row block rb, partial index pi -> column blocks pi*T + j
+        const int n_sim = 2 * p.nMB * p.nPart;
+        const bool has = cta < n_sim;
+        const int z = cta / (p.nMB * p.nPart);
+        const int rem = cta % (p.nMB * p.nPart);
+        const int rb = rem / p.nPart, pi = rem % p.nPart;
+        const int num_ke = p.E / kBK;
+        const int M = p.B, N = p.Bg;
+        const int m = rb * kBM + row;                       // local row of this epilogue thread
+        const int dcol = m + p.diag_off;
+        if (warp == 0) {
+            if (lane == 0 && has) {
+                for (int j = 0; j < p.T; ++j)
+                    for (int kc = 0; kc < num_ke; ++kc) {
+                        mbar_wait_b(&empty_bar[ring.stage], ring.phase ^ 1u);
+                        unsigned char* sa = smem + ring.stage * kStageBytes;
+                        ptx::mbar_arrive_expect_tx(&full_bar[ring.stage], kStageBytes);
+                        ptx::tma_load_2d(sa, &maps.q_k[z], &full_bar[ring.stage], kc * kBK, rb * kBM);
+                        ptx::tma_load_2d(sa + 16384, &maps.kf_k[z], &full_bar[ring.stage], kc * kBK, (pi * p.T + j) * 128);
+                        ring.next();
+                    }
+            }
+            __syncwarp();
+        } else if (warp == 1) {
+            if (lane == 0 && has) {
+                constexpr uint32_t idesc = ptx::make_idesc_bf16(kBM, 128, false, false);
+                for (int j = 0; j < p.T; ++j)
+                    for (int kc = 0; kc < num_ke; ++kc) {
+                        mbar_wait_b(&full_bar[ring.stage], ring.phase);
+                        ptx::tc_fence_after();
+                        const uint32_t sa = ptx::smem_u32(smem + ring.stage * kStageBytes);
+                        const uint64_t adesc = ptx::make_kmajor_sw128_desc(sa);
+                        const uint64_t bdesc = ptx::make_kmajor_sw128_desc(sa + 16384);
+#pragma unroll
+                        for (int k = 0; k < kBK / kUmmaK; ++k)
+                            ptx::umma_bf16(tmem_base + 128 * j, adesc + 2 * k, bdesc + 2 * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                        ptx::umma_commit(&empty_bar[ring.stage]);
+                        if (j == p.T - 1 && kc == num_ke - 1) ptx::umma_commit(tfull_bar);
+                        ring.next();
+                    }
+            }
+            __syncwarp();
+        }
+        if (has && warp >= 2) {
+            mbar_wait_b(tfull_bar, tfull_uses & 1u);
+            ptx::tc_fence_after();
+            const float sc2 = scale * kLog2e;
+            for (int j = 0; j < p.T; ++j) {
+                // raw-domain online softmax over this tile's 128 columns (see EpiSimStats)
+                const int n0 = (pi * p.T + j) * 128;
+                float mx = -INFINITY, l = 0.f, a = 0.f; int arg = n0;
+#pragma unroll 1
+                for (int c = 0; c < 128; c += 32) {
+                    float v[32];
+                    ptx::tmem_ld_32x32(tmem_row + 128 * j + c, v);
+                    const int n = n0 + c;
+                    if (n >= N) continue;                               // warp-uniform
+                    const bool full = n + 32 <= N;
+                    if (!full) {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) if (n + q >= N) v[q] = -INFINITY;
+                    }
+                    float cm = v[0];
+#pragma unroll
+                    for (int q = 1; q < 32; ++q) cm = fmaxf(cm, v[q]);
+                    if (cm > mx) {
+                        int k = 31;
+#pragma unroll
+                        for (int q = 31; q >= 0; --q) if (v[q] == cm) k = q;
+                        arg = n + k;
+                    }
+                    if (dcol >= n && dcol < n + 32 && m < M) {
+                        float dv = 0.f;
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) if (n + q == dcol) dv = v[q];
+                        p.diag[z][m] = dv * scale;
+                    }
+                    const float nm = fmaxf(mx, cm);
+                    const float corr = exp2f((mx - nm) * sc2);
+                    l *= corr; a *= corr;
+                    const float nm2 = nm * sc2;
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) {
+                        const float e = exp2f(fmaf(v[q], sc2, -nm2));
+                        l += e;
+                        a = fmaf(e, full ? v[q] : (n + q < N ? v[q] : 0.f), a);
+                    }
+                    mx = nm;
+                }
+                if (m < M) {
+                    RowStat rs; rs.m = mx * scale; rs.l = l; rs.a = a * scale; rs.arg = arg;
+                    p.part[z][static_cast<size_t>(pi * p.T + j) * p.Bp + m] = rs;
+                }
+            }
+            ptx::tc_fence_before();
+        }
+        if (!has && p.need_grads) {
+            // idle CTAs: zero the embedding-gradient table for the scatter of P4
+            const int n_idle = G - n_sim;
+            const size_t n4 = static_cast<size_t>(p.V) * p.E / 4;
+            float4* dst = reinterpret_cast<float4*>(p.dtable);
+            for (size_t i = static_cast<size_t>(cta - n_sim) * kThreads + threadIdx.x; i < n4;
+                 i += static_cast<size_t>(n_idle) * kThreads)
+                dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (has) ++tfull_uses;
+        grid_sync(p, sync_k++);
+        if (p.phase_limit == 3) goto done;
+
+        // ======================================================================== P3
+        if (has && warp >= 2) {
+            // (a) row statistics of this row block: LSE, cross-entropy / entropy / accuracy terms
+            float gm, gl, ga; int garg;
+            float lse_row = 0.f;
+            float v6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (m < M) {
+                merge_stats(p.part[z] + m, p.Bp, p.nCB, gm, gl, ga, garg);
+                lse_row = gm + logf(gl);
+                if (pi == 0) {
+                    p.lse[z][m] = lse_row;
+                    v6[z] = lse_row - __ldcg(p.diag[z] + m);
+                    v6[2 + z] = lse_row - ga / gl;
+                    v6[4 + z] = (garg == dcol) ? 1.f : 0.f;
+                }
+            }
+            if (pi == 0) {                                   // fixed-order block sum -> rb_part
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    const float s = warp_sum(v6[i]);
+                    if (lane == 0) red[(warp - 2) * 6 + i] = s;
+                }
+                ptx::named_bar_sync(1, kEpiThreads);
+                if (epi_tid < 6)
+                    p.rb_part[(z * p.nMB + rb) * 6 + epi_tid] =
+                        red[epi_tid] + red[6 + epi_tid] + red[12 + epi_tid] + red[18 + epi_tid];
+            }
+            if (p.need_grads) {
+                // (b) column terms: LSE of the OTHER direction's rows (one GPU: merged here from its partials;
+                //     sharded: gathered beforehand into lse_all)
+                const float w = scale * (0.5f * p.inv_rows);             // exp(s) * coef
+                const float l2w = log2f(w);
+                for (int c = epi_tid; c < 128 * p.T; c += kEpiThreads) {
+                    const int n = (pi * p.T) * 128 + c;
+                    float lkv = INFINITY;
+                    if (n < N) {
+                        float lse_c;
+                        if (p.lse_all[1 - z]) lse_c = __ldcg(p.lse_all[1 - z] + n);
+                        else {
+                            float cm_, cl_, ca_; int carg_;
+                            merge_stats(p.part[1 - z] + n, p.Bp, p.nCB, cm_, cl_, ca_, carg_);
+                            lse_c = cm_ + logf(cl_);
+                        }
+                        lkv = lse_c * kLog2e - l2w;
+                    }
+                    lk[c] = lkv;
+                }
+                ptx::named_bar_sync(1, kEpiThreads);
+                // (c) Gs = w * (softmax_row + softmax_col) from the tile still in TMEM -> bf16 A operand
+                const float lq = (m < M) ? lse_row * kLog2e - l2w : INFINITY;
+                const float sc2 = scale * kLog2e;
+                float ds = 0.f;
+                for (int j = 0; j < p.T; ++j) {
+                    unsigned char* gs_tile = smem + kGsOff + j * 32768;
+                    const int n0 = (pi * p.T + j) * 128;
+#pragma unroll 1
+                    for (int c = 0; c < 128; c += 32) {
+                        float v[32];
+                        ptx::tmem_ld_32x32(tmem_row + 128 * j + c, v);
+                        const int n = n0 + c;
+                        float dv = 0.f;
+                        if (dcol >= n && dcol < n + 32) {
+#pragma unroll
+                            for (int q = 0; q < 32; ++q) if (n + q == dcol) dv = v[q];
+                        }
+                        float g[32];
+#pragma unroll
+                        for (int q4 = 0; q4 < 8; ++q4) {
+                            const float4 k4 = *reinterpret_cast<const float4*>(lk + 128 * j + c + 4 * q4);
+                            const float kk[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float r = v[4 * q4 + q];
+                                const float gg = exp2f(fmaf(r, sc2, -lq)) + exp2f(fmaf(r, sc2, -kk[q]));
+                                ds = fmaf(gg, r, ds);
+                                g[4 * q4 + q] = gg;
+                            }
+                        }
+                        ds = fmaf(-2.f * w, dv, ds);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) swz_st16(gs_tile, row, (c + 8 * q) * 2, pack_bf16x8(g + 8 * q));
+                    }
+                }
+                ptx::fence_proxy_async_smem();              // generic smem writes -> tcgen05 (async proxy) reads
+                ptx::tc_fence_before();                     // the S tile has been read: its columns may be overwritten
+                ptx::mbar_arrive(gs_bar);
+                if (z == 0) {                               // dL/ds partial of this tile (direction 0 only)
+                    ds = warp_sum(ds);
+                    if (lane == 0) red[32 + (warp - 2)] = ds;
+                    ptx::named_bar_sync(1, kEpiThreads);
+                    if (epi_tid == 0) p.dspart[rb * p.nPart + pi] = (red[32] + red[33]) + (red[34] + red[35]);
+                }
+            }
+        }
+        if (has && p.need_grads) {
+            const int nH = (p.E + 255) / 256;
+            const int num_kc3 = 2 * p.T;
+            if (warp == 0) {
+                if (lane == 0) {
+                    for (int kc = 0; kc < num_kc3; ++kc)
+                        for (int h = 0; h < nH; ++h) {
+                            const int nh = min(256, p.E - 256 * h);
+                            mbar_wait_b(&empty_bar[ring.stage], ring.phase ^ 1u);
+                            unsigned char* sb = smem + ring.stage * kStageBytes;
+                            ptx::mbar_arrive_expect_tx(&full_bar[ring.stage], static_cast<uint32_t>(nh) * 128);
+                            const int crow = (pi * p.T + (kc >> 1)) * 128 + (kc & 1) * 64;
+                            for (int jb = 0; jb < nh / 64; ++jb)
+                                ptx::tma_load_2d(sb + jb * 8192, &maps.kf_mn[z], &full_bar[ring.stage], 256 * h + 64 * jb, crow);
+                            ring.next();
+                        }
+                }
+                __syncwarp();
+            } else if (warp == 1) {
+                if (lane == 0) {
+                    mbar_wait_b(gs_bar, 0);                 // single use per launch
+                    ptx::tc_fence_after();
+                    for (int kc = 0; kc < num_kc3; ++kc)
+                        for (int h = 0; h < nH; ++h) {
+                            const int nh = min(256, p.E - 256 * h);
+                            const uint32_t idesc = ptx::make_idesc_bf16(kBM, nh, false, true);
+                            mbar_wait_b(&full_bar[ring.stage], ring.phase);
+                            ptx::tc_fence_after();
+                            const uint32_t sa = ptx::smem_u32(smem + kGsOff + kc * 16384);
+                            const uint32_t sb = ptx::smem_u32(smem + ring.stage * kStageBytes);
+                            const uint64_t adesc = ptx::make_kmajor_sw128_desc(sa);
+                            const uint64_t bdesc = ptx::make_mnmajor_sw128_desc(sb, 8192);
+#pragma unroll
+                            for (int k = 0; k < kBK / kUmmaK; ++k)
+                                ptx::umma_bf16(tmem_base + 256 * h, adesc + 2 * k, bdesc + 128 * k, idesc,
+                                               (kc > 0 || k > 0) ? 1u : 0u);
+                            ptx::umma_commit(&empty_bar[ring.stage]);
+                            if (kc == num_kc3 - 1 && h == nH - 1) ptx::umma_commit(tfull_bar);
+                            ring.next();
+                        }
+                }
+                __syncwarp();
+            } else {
+                // dQ partial [128, E] -> slab (z, pi): 128 columns per pass through two staging halves
+                mbar_wait_b(tfull_bar, tfull_uses & 1u);
+                ptx::tc_fence_after();
+                const int out_row = ((z * p.nPart + pi) * p.Bp) + rb * kBM;
+                for (int q = 0; q < p.nEB; ++q) {
+                    unsigned char* stg = smem + (q & 1) * 65536;
+                    if (q >= 2) { if (epi_tid == 0) tma_store_wait_read<1>(); ptx::named_bar_sync(1, kEpiThreads); }
+                    stage_f32_cols(tmem_row, 128 * q, 128, stg, row);
+                    ptx::fence_proxy_async_smem();
+                    ptx::named_bar_sync(1, kEpiThreads);
+                    if (epi_tid == 0) {
+#pragma unroll
+                        for (int b4 = 0; b4 < 4; ++b4)
+                            ptx::tma_store_2d(&maps.dq_out, stg + b4 * 16384, 128 * q + b4 * 32, out_row);
+                        tma_store_commit();
+                    }
+                }
+                if (epi_tid == 0) tma_store_wait_all();
+                ptx::tc_fence_before();
+            }
+            ++tfull_uses;
+        }
+    }
+    grid_sync(p, sync_k++);
+    if (p.phase_limit == 4) goto done;
+
+    if (p.need_grads) {
+        // ======================================================================== P4
+        // task t < B: text row t (direction 1) -> d mean-embedding / len, scattered into d table;
+        // task B + r: image row r (direction 0) -> bf16 du (operand of dW) + bias partials
+        const int nch = p.E >> 7;
+        const size_t slab = static_cast<size_t>(p.Bp) * p.E;
+        const float dcoef = -2.f * scale * (0.5f * p.inv_rows);
+        float4 dbacc[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dbacc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = cta * kWarps + warp; t < 2 * p.B; t += G * kWarps) {
+            const int z = t < p.B ? 1 : 0;
+            const int r = z ? t : t - p.B;
+            float4 acc[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float* base = p.dqpart + (static_cast<size_t>(z) * p.nPart * p.Bp + r) * p.E;
+            for (int k0 = 0; k0 < p.nPart; k0 += 4) {
+                float4 v[4][4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        v[k][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (k0 + k < p.nPart && c < nch)
+                            v[k][c] = __ldcg(reinterpret_cast<const float4*>(base + (k0 + k) * slab) + c * 32 + lane);
+                    }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        acc[c].x += v[k][c].x; acc[c].y += v[k][c].y; acc[c].z += v[k][c].z; acc[c].w += v[k][c].w;
+                    }
+            }
+            // the -2*I term of G in fp32 (positives of the other modality) and <q, acc>
+            const __nv_bfloat16* posrow = p.kf16[z] + static_cast<size_t>(p.diag_off + r) * p.ldk;
+            const __nv_bfloat16* qrow = p.q16[z] + static_cast<size_t>(r) * p.ldq;
+            float4 qf[4];
+            float dot = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                qf[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c < nch) {
+                    const int e = (c * 32 + lane) * 4;
+                    const uint2 pr = __ldcg(reinterpret_cast<const uint2*>(posrow + e));
+                    const uint2 qr = __ldcg(reinterpret_cast<const uint2*>(qrow + e));
+                    const float2 p0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pr.x));
+                    const float2 p1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pr.y));
+                    const float2 q0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qr.x));
+                    const float2 q1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qr.y));
+                    acc[c].x = fmaf(dcoef, p0.x, acc[c].x); acc[c].y = fmaf(dcoef, p0.y, acc[c].y);
+                    acc[c].z = fmaf(dcoef, p1.x, acc[c].z); acc[c].w = fmaf(dcoef, p1.y, acc[c].w);
+                    qf[c] = make_float4(q0.x, q0.y, q1.x, q1.y);
+                    dot = fmaf(qf[c].x, acc[c].x, dot); dot = fmaf(qf[c].y, acc[c].y, dot);
+                    dot = fmaf(qf[c].z, acc[c].z, dot); dot = fmaf(qf[c].w, acc[c].w, dot);
+                }
+            }
+            float inv = 1.f;
+            if (p.normalize) { dot = warp_sum(dot); inv = __ldcg(p.invn[z] + r); } else dot = 0.f;
+            const float rs = z ? 1.f / static_cast<float>(__ldg(p.lens + r)) : 1.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                acc[c].x = (acc[c].x - qf[c].x * dot) * inv * rs; acc[c].y = (acc[c].y - qf[c].y * dot) * inv * rs;
+                acc[c].z = (acc[c].z - qf[c].z * dot) * inv * rs; acc[c].w = (acc[c].w - qf[c].w * dot) * inv * rs;
+            }
+            if (z == 0) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c < nch) {
+                        store_bf16x4(p.du16 + static_cast<size_t>(r) * p.E + (c * 32 + lane) * 4, acc[c]);
+                        dbacc[c].x += acc[c].x; dbacc[c].y += acc[c].y; dbacc[c].z += acc[c].z; dbacc[c].w += acc[c].w;
+                    }
+                }
+            } else {
+                const long long* idrow = p.ids + static_cast<size_t>(r) * p.L;
+                for (int l0 = 0; l0 < p.L; l0 += 32) {
+                    const long long my_id = (l0 + lane < p.L) ? __ldg(idrow + l0 + lane) : 0;
+                    unsigned live = __ballot_sync(0xffffffffu, my_id > 0 && my_id < p.V);
+                    while (live) {
+                        const int src = __ffs(live) - 1; live &= live - 1;
+                        const long long id = __shfl_sync(0xffffffffu, my_id, src);
+                        float4* dst = reinterpret_cast<float4*>(p.dtable + static_cast<size_t>(id) * p.E);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) if (c < nch) atomicAdd(dst + c * 32 + lane, acc[c]);
+                    }
+                }
+            }
+        }
+        // per-CTA bias partial: warps in fixed order
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (c < nch) *reinterpret_cast<float4*>(sdb + warp * 512 + (c * 32 + lane) * 4) = dbacc[c];
+        __syncthreads();
+        for (int e = threadIdx.x; e < p.E; e += kThreads) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) s += sdb[w * 512 + e];
+            p.dbpart[static_cast<size_t>(cta) * p.E + e] = s;
+        }
+    }
+    if (p.need_grads) grid_sync(p, sync_k++);
+    if (p.phase_limit == 5) goto done;
+
+    if (p.need_grads) {
+        // ======================================================================== P5: dW = du^T . x
+        const int bn = p.dw_bn;
+        const int nKT = p.K / bn;
+        const int n_tiles = p.nEB * nKT;
+        const int num_kc5 = (p.B + kBK - 1) / kBK;
+        for (int t = cta; t < n_tiles; t += G - 1) {       // the last CTA is kept for the final sums
+            if (cta == G - 1) break;
+            const int eb = t % p.nEB, kt = t / p.nEB;
+            if (warp == 0) {
+                if (lane == 0) {
+                    for (int kc = 0; kc < num_kc5; ++kc) {
+                        mbar_wait_b(&empty_bar[ring.stage], ring.phase ^ 1u);
+                        unsigned char* sa = smem + ring.stage * kStageBytes;
+                        ptx::mbar_arrive_expect_tx(&full_bar[ring.stage], 16384u + static_cast<uint32_t>(bn) * 128u);
+                        ptx::tma_load_2d(sa, &maps.du_mn, &full_bar[ring.stage], eb * 128, kc * kBK);
+                        ptx::tma_load_2d(sa + 8192, &maps.du_mn, &full_bar[ring.stage], eb * 128 + 64, kc * kBK);
+                        for (int jb = 0; jb < bn / 64; ++jb)
+                            ptx::tma_load_2d(sa + 16384 + jb * 8192, &maps.x_mn, &full_bar[ring.stage], kt * bn + 64 * jb, kc * kBK);
+                        ring.next();
+                    }
+                }
+                __syncwarp();
+            } else if (warp == 1) {
+                if (lane == 0) {
+                    const uint32_t idesc = ptx::make_idesc_bf16(kBM, bn, true, true);
+                    for (int kc = 0; kc < num_kc5; ++kc) {
+                        mbar_wait_b(&full_bar[ring.stage], ring.phase);
+                        ptx::tc_fence_after();
+                        const uint32_t sa = ptx::smem_u32(smem + ring.stage * kStageBytes);
+                        const uint64_t adesc = ptx::make_mnmajor_sw128_desc(sa, 8192);
+                        const uint64_t bdesc = ptx::make_mnmajor_sw128_desc(sa + 16384, 8192);
+#pragma unroll
+                        for (int k = 0; k < kBK / kUmmaK; ++k)
+                            ptx::umma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                        ptx::umma_commit(&empty_bar[ring.stage]);
+                        if (kc == num_kc5 - 1) ptx::umma_commit(tfull_bar);
+                        ring.next();
+                    }
+                }
+                __syncwarp();
+            } else {
+                mbar_wait_b(tfull_bar, tfull_uses & 1u);
+                ptx::tc_fence_after();
+                stage_f32_cols(tmem_row, 0, bn, smem, row);
+                ptx::fence_proxy_async_smem();
+                ptx::tc_fence_before();
+                ptx::named_bar_sync(1, kEpiThreads);
+                if (epi_tid == 0) {
+                    for (int b4 = 0; b4 < bn / 32; ++b4)
+                        ptx::tma_store_2d(&maps.dw_out, smem + b4 * 16384, kt * bn + b4 * 32, eb * 128);
+                    tma_store_commit();
+                    tma_store_wait_read<0>();
+                }
+            }
+            ++tfull_uses;
+            __syncthreads();                                // staging / accumulator reuse across tiles
+            ptx::tc_fence_after();
+        }
+    }
+
+    // ---- final sums by the last CTA, every one in a fixed order (deterministic)
+    if (cta == G - 1) {
+        if (threadIdx.x == 0) {
+            float s6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int b = 0; b < 2 * p.nMB; ++b) {
+                const int z = b / p.nMB;
+                s6[z] += __ldcg(p.rb_part + b * 6 + z);
+                s6[2 + z] += __ldcg(p.rb_part + b * 6 + 2 + z);
+                s6[4 + z] += __ldcg(p.rb_part + b * 6 + 4 + z);
+            }
+            p.out5[0] = (s6[0] + s6[1]) * 0.5f * p.inv_rows;
+            p.out5[1] = s6[4] * p.inv_rows;
+            p.out5[2] = s6[5] * p.inv_rows;
+            p.out5[3] = s6[2] * p.inv_rows;
+            p.out5[4] = s6[3] * p.inv_rows;
+            if (p.need_grads) {
+                float ds = 0.f;
+                for (int i = 0; i < p.nMB * p.nPart; ++i) ds += __ldcg(p.dspart + i);
+                p.dscale[0] = ds;
+            }
+        }
+        if (p.need_grads) {
+            for (int e = threadIdx.x; e < p.E; e += kThreads) {
+                float s = 0.f;
+                for (int b = 0; b < G; ++b) s += __ldcg(p.dbpart + static_cast<size_t>(b) * p.E + e);
+                p.dbias[e] = s;
+            }
+        }
+    }
+
+done:
+    // leave the barrier counter zeroed for the next launch: the last CTA through the exit ticket resets both
+    // (every CTA has passed its last grid barrier before it takes a ticket)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (cta == 0 && p.timing) p.timing[15] = globaltimer_ns();
+        __threadfence();
+        if (atomicAdd(p.sync + 1, 1u) == static_cast<unsigned int>(G - 1)) {
+            p.sync[0] = 0u; p.sync[1] = 0u;
+            __threadfence();
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace fused
+}  // namespace cvcl

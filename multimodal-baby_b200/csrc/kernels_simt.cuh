@@ -1319,6 +1319,86 @@ __global__ void __launch_bounds__(256) adamw_step_kernel(float* p, const float* 
 }
 
 
+// The same update for up to kAdamMaxTensors tensors in ONE launch, with the step counter kept on the
+// device: bias corrections are computed in the kernel from *step_dev + 1 and the last block to finish
+// (atomic ticket) increments it, so the launch can be captured in a CUDA graph and replayed (a host-side
+// step number would be baked into the graph).  Used by GraphedContrastiveStep to make a whole train step
+// -- forward, backward, optimizer, refreshed bf16 weight shadow -- one graph.
+constexpr int kAdamMaxTensors = 8;
+struct AdamMultiParams {
+    float* p[kAdamMaxTensors]; const float* g[kAdamMaxTensors]; float* m[kAdamMaxTensors]; float* v[kAdamMaxTensors];
+    __nv_bfloat16* shadow[kAdamMaxTensors];
+    long long n4_begin[kAdamMaxTensors + 1];       // prefix sums of ceil(n / 4) per tensor
+    long long n[kAdamMaxTensors];
+    float lr[kAdamMaxTensors], wd[kAdamMaxTensors];
+    int count;
+    float beta1, beta2, eps, grad_scale;
+    int* step_dev;               // [1] completed steps; this launch performs step *step_dev + 1
+    unsigned int* ticket;        // [1] zero on entry, left zero on exit
+};
+
+__global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamMultiParams a) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
+    const int step = *reinterpret_cast<volatile int*>(a.step_dev) + 1;
+    const float bc1 = 1.f - powf(a.beta1, static_cast<float>(step));
+    const float bc2_sqrt = sqrtf(1.f - powf(a.beta2, static_cast<float>(step)));
+    const long long total4 = a.n4_begin[a.count];
+    for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < total4;
+         q += static_cast<long long>(gridDim.x) * blockDim.x) {
+        int t = 0;
+#pragma unroll
+        for (int k = 1; k < kAdamMaxTensors; ++k) if (k < a.count && q >= a.n4_begin[k]) t = k;
+        const long long i = (q - a.n4_begin[t]) * 4;
+        const long long n = a.n[t];
+        const float lr = a.lr[t], wd = a.wd[t];
+        const float step_size = lr / bc1;
+        float* p = a.p[t]; const float* g = a.g[t]; float* m = a.m[t]; float* v = a.v[t];
+        const int cnt = (i + 4 <= n) ? 4 : static_cast<int>(n - i);
+        float pp[4], gg[4], mm[4], vv[4];
+        if (cnt == 4) {
+            const float4 P = *reinterpret_cast<const float4*>(p + i), G = *reinterpret_cast<const float4*>(g + i);
+            const float4 M = *reinterpret_cast<const float4*>(m + i), V = *reinterpret_cast<const float4*>(v + i);
+            pp[0] = P.x; pp[1] = P.y; pp[2] = P.z; pp[3] = P.w; gg[0] = G.x; gg[1] = G.y; gg[2] = G.z; gg[3] = G.w;
+            mm[0] = M.x; mm[1] = M.y; mm[2] = M.z; mm[3] = M.w; vv[0] = V.x; vv[1] = V.y; vv[2] = V.z; vv[3] = V.w;
+        } else {
+            for (int k = 0; k < cnt; ++k) { pp[k] = p[i + k]; gg[k] = g[i + k]; mm[k] = m[i + k]; vv[k] = v[i + k]; }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k < cnt) {
+                const float gk = gg[k] * a.grad_scale;
+                pp[k] *= 1.f - lr * wd;
+                mm[k] = mm[k] + (gk - mm[k]) * (1.f - a.beta1);
+                vv[k] = vv[k] * a.beta2 + gk * gk * (1.f - a.beta2);
+                const float denom = sqrtf(vv[k]) / bc2_sqrt + a.eps;
+                pp[k] -= step_size * (mm[k] / denom);
+            }
+        }
+        if (cnt == 4) {
+            *reinterpret_cast<float4*>(p + i) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+            *reinterpret_cast<float4*>(m + i) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+            *reinterpret_cast<float4*>(v + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+            if (a.shadow[t]) store_bf16x4(a.shadow[t] + i, make_float4(pp[0], pp[1], pp[2], pp[3]));
+        } else {
+            for (int k = 0; k < cnt; ++k) {
+                p[i + k] = pp[k]; m[i + k] = mm[k]; v[i + k] = vv[k];
+                if (a.shadow[t]) a.shadow[t][i + k] = __float2bfloat16_rn(pp[k]);
+            }
+        }
+    }
+    // every block has read the step number before any block can pass the ticket as the last one
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(a.ticket, 1u) == gridDim.x - 1) {
+            *a.step_dev = step;
+            *a.ticket = 0u;
+            __threadfence();
+        }
+    }
+}
+
+
 // --------------------------------------------------------------------------------------
 // All-gather over NVLink peer memory: every rank exposes its block in symmetric memory; after a
 // cross-rank barrier each rank pulls the other ranks' blocks with 16-byte loads from the PEER

@@ -8,8 +8,10 @@
 // storing the launch's epoch into the peer's flag word [phase][b][r] (st.release.sys over NVLink) and
 // spins (ld.acquire.sys) on its own words [phase][b][peer].  Epochs only grow (one per launch, kept in
 // a per-rank device array so CUDA-graph replays advance them), so flags are never reset.  All ranks
-// must launch a given channel with the same grid; the grid is at most kPeerMaxBlocks CTAs of 512
-// threads, always co-resident on 148 SMs, so the spin cannot starve a block it waits for.
+// must issue the same sequence of launches per channel (the grid may differ from launch to launch: flag
+// words are indexed by a fixed per-phase stride and epochs are kept per block index); the grid is at
+// most kPeerMaxBlocks CTAs of 512 threads, always co-resident on 148 SMs, so the spin cannot starve a
+// block it waits for.
 //
 // Two families, same results (the PUSH kernels further down are the default of sharding.PeerExchange:
 // all NVLink traffic is posted stores; measured 151.9 us vs 158.5 us (pull) vs 165.0 us (NCCL) per step at
@@ -23,8 +25,9 @@
 //                rank's buffer -> end barrier.  push: scatter slice p into rank p's scratch -> barrier ->
 //                local sum in rank order, store to every rank -> barrier.  In place, deterministic.
 //
-// A barrier that does not complete within timeout_ms sets *status and traps (the step fails loudly
-// instead of hanging the device); with CVCL_PEER_NO_TRAP or'ed into timeout_ms it only sets *status and
+// A barrier that does not complete within timeout_ms (default 10 minutes, the order of NCCL's own
+// watchdog: a rank may legitimately stall between steps -- data-loader start-up, a checkpoint) sets
+// *status and traps (the step fails loudly instead of hanging the device); with CVCL_PEER_NO_TRAP or'ed into timeout_ms it only sets *status and
 // goes on (the start-up self-test of sharding.PeerExchange uses this to decide for or against the path).
 #pragma once
 #include <cstdint>
@@ -77,7 +80,9 @@ __device__ __forceinline__ void barrier(const PeerTable& t, int world, int rank,
     __syncthreads();
     const int peer = threadIdx.x;
     if (peer < world && peer != rank) {
-        const int slot = (phase * gridDim.x + blockIdx.x) * kPeerMaxWorld;
+        // fixed stride per phase (NOT gridDim.x): launches of one channel with different grids (a training
+        // step, then a forward-only step) must never alias flag words that carry different epochs
+        const int slot = (phase * kPeerMaxBlocks + blockIdx.x) * kPeerMaxWorld;
         st_release_sys(t.flags[peer] + slot + rank, e);
         const uint32_t* mine = t.flags[rank] + slot + peer;
         unsigned long long t0 = 0;

@@ -1,13 +1,17 @@
-"""CUDA-graph train step for the flat contrastive path: H2D staging, the fused step and the D2H read
-of the loss are captured ONCE and replayed per batch (B200-first: graphs instead of per-op Python
-dispatch; the captured body is exactly `ops.flat_contrastive_step` / `ops.flat_step_sharded`, i.e.
-MultiModalModel.calculate_contrastive_loss + backward, multimodal.py:796-822).
+"""CUDA-graph train step for the flat contrastive path: H2D staging, the fused step, (optionally) the
+optimizer update and the D2H read of the loss are captured ONCE and replayed per batch (B200-first: graphs
+instead of per-op Python dispatch; the captured body is exactly `ops.flat_contrastive_step` /
+`ops.flat_step_sharded`, i.e. MultiModalModel.calculate_contrastive_loss + backward, multimodal.py:796-822).
 
     step = GraphedContrastiveStep(model, x_host, ids_host, lens_host)   # pinned host staging buffers
     loss = step()            # copies the staged batch, runs fwd+bwd, returns the loss (python float)
     # gradients are in p.grad of the head parameters (static views of one flat buffer)
 
 The loader writes the next batch into `step.x_host / ids_host / lens_host` (pinned) between calls.
+
+`optimizer=FusedAdamW(...)` puts the parameter update (and the refresh of the bf16 weight shadow the head
+GEMM reads) into the same graph: one replay = one complete training step, and because replays are
+stream-ordered every step sees the weights the previous step produced.
 
 `prefetch=True` double-buffers the device inputs: replay k computes on the batch that replay k-1
 copied while it was computing, and copies the batch now staged in the pinned buffers for replay k+1
@@ -18,7 +22,13 @@ staging the first batch).
 `lagged_loss=True` (needs prefetch) additionally keeps one replay in flight: a call enqueues replay k and
 waits only for replay k-1, whose loss it returns (each graph writes its own pinned stats buffer).  The
 host never idles behind the GPU; every step's loss is still read back, one call later.  `flush()` waits
-for the replay in flight and returns its loss.
+for the replay in flight and returns its loss.  Two consequences, both handled here:
+  * the H2D copies of the replay still in flight read the pinned staging buffers, so the staging buffers
+    are DOUBLE-BUFFERED too: `x_host / ids_host / lens_host` always name the set the next call will copy,
+    which no replay in flight is reading (the set alternates with every call);
+  * without `optimizer=`, an optimizer step issued by the caller after call k lands behind replay k in the
+    stream, so replay k computed its gradients with the weights of step k-2: gradients are one step stale
+    (asynchronous-SGD semantics).  Pass `optimizer=` to keep the update inside the graph and exact.
 """
 from __future__ import annotations
 
@@ -28,7 +38,8 @@ from . import ops
 
 
 class GraphedContrastiveStep:
-    def __init__(self, model, x_host, ids_host, lens_host, warmup=3, prefetch=False, lagged_loss=False):
+    def __init__(self, model, x_host, ids_host, lens_host, warmup=3, prefetch=False, lagged_loss=False,
+                 optimizer=None):
         if model.embedding_type != "flat":
             raise NotImplementedError("GraphedContrastiveStep covers the flat-embedding train step")
         for t in (x_host, ids_host, lens_host):
@@ -36,53 +47,73 @@ class GraphedContrastiveStep:
                 raise ValueError("staging buffers must be pinned host tensors")
         self.model = model
         self.group = model.process_group
-        self.x_host, self.ids_host, self.lens_host = x_host, ids_host, lens_host
         w, b = model._head()
         table = model.text_embed.embedding.weight
         dev = table.device
         self.dev = dev
         self.prefetch = bool(prefetch)
         nbuf = 2 if self.prefetch else 1
-        self.bufs = [(torch.empty_like(x_host, device=dev), torch.empty_like(ids_host, device=dev),
-                      torch.empty_like(lens_host, device=dev)) for _ in range(nbuf)]
-        self.x, self.ids, self.lens = self.bufs[0]
         if lagged_loss and not prefetch:
             raise ValueError("lagged_loss=True needs prefetch=True (two alternating graphs)")
         self.lagged = bool(lagged_loss)
+        # pinned staging: one set per graph in lagged mode (the replay in flight may still be reading its set)
+        self.host_sets = [(x_host, ids_host, lens_host)]
+        if self.lagged:
+            self.host_sets.append(tuple(torch.empty_like(t).pin_memory() for t in (x_host, ids_host, lens_host)))
+            for dst, src in zip(self.host_sets[1], self.host_sets[0]):
+                dst.copy_(src)
+        self.bufs = [(torch.empty_like(x_host, device=dev), torch.empty_like(ids_host, device=dev),
+                      torch.empty_like(lens_host, device=dev)) for _ in range(nbuf)]
+        self.x, self.ids, self.lens = self.bufs[0]
         self.stats_bufs = [torch.zeros(8, dtype=torch.float32).pin_memory() for _ in range(nbuf)]
         self.stats_host = self.stats_bufs[0]
         self.events = [torch.cuda.Event() for _ in range(nbuf)]
         self.pending = None
         self.copy_stream = torch.cuda.Stream(device=dev) if self.prefetch else None
         self.calls = 0
+        self.optimizer = optimizer
         s = model.logit_neg_log_temperature
-        if isinstance(s, torch.nn.Parameter):
-            raise NotImplementedError("graphed step needs fix_temperature=True (s is baked into the graph)")
-        ls = ops._scalar(s)
+        self.s_param = s if isinstance(s, torch.nn.Parameter) else None
+        if self.s_param is not None and (self.group is not None or not s.is_cuda):
+            raise NotImplementedError("a trainable temperature in the graphed step needs the single-GPU "
+                                      "one-kernel path with the parameter on the device")
+        ls = 0.0 if self.s_param is not None else ops._scalar(s)
+        s_dev = self.s_param.detach().reshape(1) if self.s_param is not None else None
         norm = bool(model.normalize_features)
         E, K, V = table.shape[1], w.shape[1], table.shape[0]
+        if self.s_param is not None and not ops.fused_supported(x_host.shape[0], ids_host.shape[1], E, K, V):
+            raise NotImplementedError("trainable temperature: shape not covered by the one-kernel step")
+        if optimizer is not None:
+            optimizer.attach_shadow(self._head_params()[0])      # the update kernel keeps bf16(W) current
+        # with the update inside the graph every graph binds the .grad views of ITS gradient buffer while it
+        # is captured (the optimizer launch bakes those pointers in); nothing outside reads older gradients
+        self._opt_in_graph = optimizer is not None
 
-        def h2d(buf):
-            buf[0].copy_(self.x_host, non_blocking=True)
-            buf[1].copy_(self.ids_host, non_blocking=True)
-            buf[2].copy_(self.lens_host, non_blocking=True)
+        def h2d(buf, host):
+            buf[0].copy_(host[0], non_blocking=True)
+            buf[1].copy_(host[1], non_blocking=True)
+            buf[2].copy_(host[2], non_blocking=True)
 
         @torch.no_grad()
-        def body(cur, nxt, stats_host, slot=0):
+        def body(cur, nxt, stats_host, slot, host):
             main = torch.cuda.current_stream(dev)
             if nxt is None:
-                h2d(cur)                                   # copy, then compute (serial)
+                h2d(cur, host)                             # copy, then compute (serial)
             else:
                 self.copy_stream.wait_stream(main)         # copy the NEXT batch beside the kernels
                 with torch.cuda.stream(self.copy_stream):
-                    h2d(nxt)
+                    h2d(nxt, host)
             x_d, ids_d, lens_d = cur
             if self.group is None:
-                out5, _, _, flat = ops.flat_contrastive_step(x_d, ids_d, lens_d, w, b, table, ls, norm, True, False)
+                out5, _, _, flat = ops.flat_contrastive_step(x_d, ids_d, lens_d, w, b, table, ls, norm, True, False,
+                                                             s_dev)
             else:
                 stats, _, _ = ops.flat_step_sharded(x_d, ids_d, lens_d, w, b, table, ls, norm, True, False,
                                                     self.group, stats_slot=slot)
                 out5, flat = stats[:8], stats[8:]
+            if self._opt_in_graph:
+                self._bind_views(flat, E, K, V, table)
+                self.optimizer.graph_step()
             stats_host.copy_(out5, non_blocking=True)
             if nxt is not None:
                 main.wait_stream(self.copy_stream)
@@ -90,44 +121,83 @@ class GraphedContrastiveStep:
 
         pairs = [(self.bufs[0], None, self.stats_bufs[0])] if not self.prefetch else [
             (self.bufs[0], self.bufs[1], self.stats_bufs[0]), (self.bufs[1], self.bufs[0], self.stats_bufs[1])]
+        self._dims = (E, K, V, table)
+        backup = None
+        if optimizer is not None:            # the warm-up iterations run real updates: undone below
+            backup = [(p, p.detach().clone()) for g in optimizer.param_groups for p in g["params"]]
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(warmup):
                 for k, (cur, nxt, sh) in enumerate(pairs):
-                    body(cur, nxt, sh, k)
+                    body(cur, nxt, sh, k, self.host_sets[k % len(self.host_sets)])
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        # one flat gradient buffer shared by all graphs: the parameters' .grad are static views of it
+        if optimizer is not None:
+            self._reset_optimizer_after_warmup(backup)
         self.graphs, flats = [], []
         for k, (cur, nxt, sh) in enumerate(pairs):
             gph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gph):
-                flats.append(body(cur, nxt, sh, k))
+                flats.append(body(cur, nxt, sh, k, self.host_sets[k % len(self.host_sets)]))
             self.graphs.append(gph)
         self.graph = self.graphs[0]
         self.flats = flats
         self.flat = flats[0]
+        self._grad_views = {}
         self._bind_grads(0, E, K, V, table)
-        self._dims = (E, K, V, table)
+
+    # the warm-up iterations ran real optimizer steps on whatever was staged: undo them
+    def _reset_optimizer_after_warmup(self, backup):
+        opt = self.optimizer
+        with torch.no_grad():
+            for p, v in backup:
+                p.copy_(v)
+        opt.reset_state()
+        torch.cuda.synchronize(self.dev)
+
+    def _bind_views(self, flat, E, K, V, table):
+        ds, db, dtable, dW = ops.split_flat_grads(flat, E, K, V)
+        w_param, b_param = self._head_params()
+        w_param.grad = dW.view_as(w_param)
+        if b_param is not None:
+            b_param.grad = db
+        table.grad = dtable
+        if self.s_param is not None:
+            self.s_param.grad = ds.view(())
 
     def _bind_grads(self, which, E, K, V, table):
-        views = self._grad_views.get(which) if hasattr(self, "_grad_views") else None
+        if self._opt_in_graph:
+            return
+        views = self._grad_views.get(which)
         if views is None:
-            if not hasattr(self, "_grad_views"):
-                self._grad_views = {}
             ds, db, dtable, dW = ops.split_flat_grads(self.flats[which], E, K, V)
             w_param, b_param = self._head_params()
-            views = self._grad_views[which] = (w_param, dW.view_as(w_param), b_param, db, table, dtable)
-        w_param, dW, b_param, db, table, dtable = views
+            views = self._grad_views[which] = (w_param, dW.view_as(w_param), b_param, db, table, dtable, ds.view(()))
+        w_param, dW, b_param, db, table, dtable, ds = views
         w_param.grad = dW
         if b_param is not None:
             b_param.grad = db
         table.grad = dtable
+        if self.s_param is not None:
+            self.s_param.grad = ds
+
+    # pinned staging buffers the NEXT call will copy (never read by a replay in flight)
+    @property
+    def x_host(self):
+        return self.host_sets[self.calls % len(self.host_sets)][0]
+
+    @property
+    def ids_host(self):
+        return self.host_sets[self.calls % len(self.host_sets)][1]
+
+    @property
+    def lens_host(self):
+        return self.host_sets[self.calls % len(self.host_sets)][2]
 
     def prime(self):
         """prefetch mode: copy the batch currently staged in the pinned buffers into device buffer 0."""
-        for d, h in zip(self.bufs[0], (self.x_host, self.ids_host, self.lens_host)):
+        for d, h in zip(self.bufs[0], self.host_sets[self.calls % len(self.host_sets)]):
             d.copy_(h, non_blocking=True)
         torch.cuda.current_stream(self.dev).synchronize()
         self.calls = 0

@@ -567,27 +567,105 @@ def split_flat_grads(flat: Tensor, E: int, K: int, V: int):
             flat[4 + E + V * E:4 + E + V * E + E * K].view(E, K))
 
 
+# bf16 shadows of fp32 master weights, keyed by storage: recast only when the parameter's version changed
+# (an optimizer step).  `register_weight_shadow` lets an optimizer that writes the shadow itself
+# (FusedAdamW: cvcl_adamw_step's bf16_shadow output) hand it over, so no cast runs at all.
+_SHADOWS = {}
+_FUSED_WS = {}
+FUSED_STEP = True          # False (or CVCL_B200_FUSED=0): always use the multi-kernel step
+
+
+def _shadow_entry(w):
+    ent = _SHADOWS.get(id(w))
+    if ent is not None and (ent[0]() is not w or ent[1] != w.data_ptr()):
+        ent = None                                   # id reused by another tensor / storage swapped
+    return ent
+
+
+def register_weight_shadow(w: Tensor, w16: Tensor):
+    """w16 (bf16, same shape) is kept equal to bf16(w) by its owner from now on (e.g. FusedAdamW, whose
+    kernel writes the refreshed shadow together with the fp32 master)."""
+    import weakref
+    key = id(w)
+    _SHADOWS[key] = [weakref.ref(w, lambda _r, k=key: _SHADOWS.pop(k, None)), w.data_ptr(), None, w16]
+
+
+def drop_weight_shadow(w: Tensor):
+    _SHADOWS.pop(id(w), None)
+
+
+def weight_shadow(w: Tensor) -> Tensor:
+    """bf16 copy of the fp32 master weight `w` [E,K]: one cast per parameter version (an optimizer step
+    bumps the version), none at all when an owner registered the shadow."""
+    import weakref
+    ent = _shadow_entry(w)
+    ver = w._version
+    if ent is not None and (ent[2] is None or ent[2] == ver):
+        return ent[3]
+    w32 = _f32(w)
+    if torch.cuda.is_current_stream_capturing():
+        # a capture must not bake in "no cast needed": cast inside the graph into a private buffer
+        return to_bf16_pair(w32, False)[0]
+    w16 = ent[3] if ent is not None else torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
+    R, C = w.shape
+    _cabi.call("cvcl_cast_transpose", _p(w32), 0, _p(w16), None, 1, R, C, C, C, 0, 0, 0, 0, _stream())
+    key = id(w)
+    _SHADOWS[key] = [weakref.ref(w, lambda _r, k=key: _SHADOWS.pop(k, None)), w.data_ptr(), ver, w16]
+    return w16
+
+
+def _fused_workspace(dev, B, L, E, K, V):
+    """persistent, zero-initialised workspace of the one-kernel step (one step in flight per device and
+    shape; calls on one stream are ordered, which is how a training loop uses it)."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), B, L, E, K, V)
+    ws = _FUSED_WS.get(key)
+    if ws is None:
+        nbytes = int(_cabi.load().cvcl_flat_fused_workspace_bytes(B, L, E, K, V))
+        ws = _FUSED_WS[key] = torch.zeros((nbytes,), dtype=torch.uint8, device=dev)
+    return ws
+
+
+def fused_supported(B, L, E, K, V) -> bool:
+    import os
+    if not FUSED_STEP or os.environ.get("CVCL_B200_FUSED", "1") == "0":
+        return False
+    return bool(_cabi.load().cvcl_flat_fused_supported(B, L, E, K, V))
+
+
+def fused_layout(B, L, E, K, V):
+    """workspace block offsets of the one-kernel step (see cvcl_flat_fused_layout)."""
+    import ctypes
+    arr = (ctypes.c_longlong * 20)()
+    _cabi.call("cvcl_flat_fused_layout", B, L, E, K, V, arr, 20)
+    names = ["ctrl", "hpart", "img16", "txt16", "invn", "part", "diag", "lse", "rb_part", "dspart", "dqpart",
+             "du16", "dbpart", "bytes", "Bp", "KS", "nPart", "dw_bn", "grid", "nCB"]
+    return dict(zip(names, [int(v) for v in arr]))
+
+
 @torch.library.custom_op(_NS + "::flat_contrastive_step", mutates_args=())
 def flat_contrastive_step(x: Tensor, ids: Tensor, lens: Tensor, w: Tensor, bias: Tensor, table: Tensor,
-                          log_scale: float, normalize: bool, need_grads: bool, want_features: bool
+                          log_scale: float, normalize: bool, need_grads: bool, want_features: bool,
+                          log_scale_t: Optional[Tensor] = None, phase_limit: int = 0
                           ) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """-> (out5 [8], img_feat [B,E] | empty, txt_feat [B,E] | empty, grads_flat | empty); the flat
-    buffer holds [ds(4) | db(E) | dtable(V*E) | dW(E*K)] (see split_flat_grads): one memset node,
-    one all-reduce when sharded."""
+    buffer holds [ds(4) | db(E) | dtable(V*E) | dW(E*K)] (see split_flat_grads): one all-reduce when
+    sharded.  log_scale_t: optional CUDA scalar s read on the device (no host sync; one-kernel path).
+    Shapes the persistent kernel covers (cvcl_flat_fused_supported) run as ONE launch; others as the
+    multi-kernel sequence of cvcl_flat_contrastive_step."""
     _need_cuda(x, ids, lens, w, bias, table)
     if x.dtype not in (torch.float32, torch.bfloat16):
         x = x.float()
     x = x.detach().contiguous()
     ids = _i64(ids); lens = _i64(lens)
+    w_param = w
     w = _f32(w); bias = _f32(bias); table = _f32(table)
     B, K = x.shape
     L = ids.shape[1]
     V, E = table.shape
     dev = x.device
     lib = _cabi.load()
-    ws = torch.empty((lib.cvcl_flat_step_workspace_bytes(B, L, E, K, V),), dtype=torch.uint8, device=dev)
-    out5 = torch.zeros((8,), dtype=torch.float32, device=dev)
     f32 = dict(dtype=torch.float32, device=dev)
+    out5 = torch.empty((8,), **f32)
     img_f = torch.empty((B, E), **f32) if want_features else torch.empty((0,), **f32)
     txt_f = torch.empty((B, E), **f32) if want_features else torch.empty((0,), **f32)
     if need_grads:
@@ -596,6 +674,20 @@ def flat_contrastive_step(x: Tensor, ids: Tensor, lens: Tensor, w: Tensor, bias:
     else:
         flat = torch.empty((0,), **f32)
         ds = db = dtable = dW = None
+    if fused_supported(B, L, E, K, V):
+        x16, _ = to_bf16_pair(x, False)
+        w16 = weight_shadow(w_param)
+        ws = _fused_workspace(dev, B, L, E, K, V)
+        _cabi.call("cvcl_flat_step_fused", _p(x16), _p(w16), _p(ids), _p(lens), _p(bias), _p(table),
+                   B, L, E, K, V, int(normalize), float(log_scale), _p(log_scale_t), int(need_grads),
+                   _p(ws), _p(out5), _p(img_f) if want_features else None,
+                   _p(txt_f) if want_features else None, _p(dW), _p(db), _p(dtable), _p(ds), None,
+                   int(phase_limit), _stream())
+        return out5, img_f, txt_f, flat
+    if log_scale_t is not None:
+        log_scale = float(log_scale_t)               # multi-kernel path: host scalar (one D2H sync)
+    out5.zero_()
+    ws = torch.empty((lib.cvcl_flat_step_workspace_bytes(B, L, E, K, V),), dtype=torch.uint8, device=dev)
     _cabi.call("cvcl_flat_contrastive_step", _p(x), int(x.dtype == torch.bfloat16), _p(ids), _p(lens),
                _p(w), _p(bias), _p(table), B, L, E, K, V, int(normalize), float(log_scale),
                int(need_grads), _p(ws), _p(out5), _p(img_f) if want_features else None,
@@ -604,7 +696,8 @@ def flat_contrastive_step(x: Tensor, ids: Tensor, lens: Tensor, w: Tensor, bias:
 
 
 @flat_contrastive_step.register_fake
-def _(x, ids, lens, w, bias, table, log_scale, normalize, need_grads, want_features):
+def _(x, ids, lens, w, bias, table, log_scale, normalize, need_grads, want_features, log_scale_t=None,
+      phase_limit=0):
     f = dict(dtype=torch.float32)
     B, K = x.shape
     V, E = table.shape
@@ -625,8 +718,11 @@ class _FlatContrastiveStep(torch.autograd.Function):
         if torch.is_tensor(x) and x.requires_grad:
             raise RuntimeError("flat_contrastive_step does not produce d/dx; use the op-by-op path "
                                "(finetune_cnn=True) instead")
+        # a CUDA scalar s (trainable temperature) is read on the device: no .item() sync per step
+        s_dev = s.detach().reshape(1).float() if (torch.is_tensor(s) and s.is_cuda) else None
         out5, img_f, txt_f, flat = _raw(flat_contrastive_step)(
-            x, ids, lens, w, bias, table, _scalar(s), normalize, need, want_features)
+            x, ids, lens, w, bias, table, 0.0 if s_dev is not None else _scalar(s), normalize, need,
+            want_features, s_dev)
         ctx.need = need
         ctx.s_is_tensor = torch.is_tensor(s)
         ctx.dims = (table.shape[1], x.shape[1], table.shape[0])

@@ -116,7 +116,7 @@ class PeerExchange:
         lib = _cabi.load()
         self.world, self.rank = group_info(group)
         self.b, self.E, self.n_stats = b, E, n_stats
-        self.timeout_ms = int(os.environ.get("CVCL_B200_PEER_TIMEOUT_MS", "20000"))
+        self.timeout_ms = int(os.environ.get("CVCL_B200_PEER_TIMEOUT_MS", "600000"))
         fw = int(lib.cvcl_peer_flag_words())
         nblk = int(lib.cvcl_peer_max_blocks())
         self.push = os.environ.get("CVCL_B200_PEER_MODE", "push") != "pull"
@@ -208,7 +208,12 @@ class PeerExchange:
         world, _ = group_info(group)
         if world not in (2, 4, 8) or b % 4 or n_stats % 4 or (b * 2 * E * 2) % 16:
             return None
-        key = (id(group), b, E, n_stats, dev.index, os.environ.get("CVCL_B200_PEER_MODE", "push"))
+        # keyed by the group's identity (name + ranks), not id(): a destroyed group's id can be recycled
+        try:
+            gkey = (dist.get_process_group_ranks(group).__repr__(), getattr(group, "group_name", ""))
+        except Exception:                        # noqa: BLE001
+            gkey = id(group)
+        key = (gkey, b, E, n_stats, dev.index, os.environ.get("CVCL_B200_PEER_MODE", "push"))
         if key not in cls._cache:
             try:
                 cls._cache[key] = cls(group, b, E, n_stats, dev)

@@ -176,3 +176,35 @@ def test_peer_allgather_push_emulated_ranks(world):
     want = torch.cat(lses, dim=1).cpu()
     for r in range(world):
         assert torch.equal(dst[r].cpu(), want), (world, r)
+
+
+@pytest.mark.parametrize("push", [False, True])
+def test_peer_allreduce_alternating_sizes_share_a_channel(push):
+    """A training step (large all-reduce, many CTAs) followed by forward-only steps (n = 8, one CTA)
+    and a training step again on the SAME channel: flag words are indexed with a fixed per-phase stride, so
+    the single-CTA launches cannot leave a high epoch in a word that the many-CTA grid reads as another
+    block's (slot = (phase * gridDim.x + block) aliased phase 1 / block 0 onto phase 0 /
+    block 1)."""
+    world, big, small = 2, 1_200_000, 8
+    _cabi, dev, data, flags, epoch, status, arr, streams = _setup(world, big * 4)
+    nscr = int(_cabi.load().cvcl_peer_allreduce_scratch_bytes(big, world))
+    scratch = [torch.empty(nscr, dtype=torch.uint8, device=dev) for _ in range(world)]
+    p_data = arr(*[d.data_ptr() for d in data]); p_flags = arr(*[f.data_ptr() for f in flags])
+    p_scr = arr(*[d.data_ptr() for d in scratch])
+    g = torch.Generator(device="cpu").manual_seed(4242)
+    for it, n in enumerate([big, small, small, small, big, small, big]):
+        src = [torch.randn(n, generator=g) for _ in range(world)]
+        for d, s in zip(data, src):
+            d.view(torch.float32)[:n].copy_(s.to(dev))
+        torch.cuda.synchronize()
+        for r in range(world):
+            if push:
+                _cabi.call("cvcl_peer_allreduce_push_f32", p_data, p_scr, p_flags, epoch[r].data_ptr(),
+                           status[r].data_ptr(), world, r, n, TIMEOUT_MS, streams[r].cuda_stream)
+            else:
+                _cabi.call("cvcl_peer_allreduce_f32", p_data, p_flags, epoch[r].data_ptr(), status[r].data_ptr(),
+                           world, r, n, TIMEOUT_MS, streams[r].cuda_stream)
+        _join(streams, status)
+        want = src[0] + src[1]
+        for r in range(world):
+            assert torch.equal(data[r].view(torch.float32)[:n].cpu(), want), (it, n, r)
