@@ -189,16 +189,18 @@ int cvcl_flat_contrastive_step(const void* x, int x_is_bf16, const int64_t* ids,
  * (trainable temperature without a host sync, multimodal.py:711-715) and log_scale is ignored.
  * Shapes covered: E in {128,256,384,512}, K % 64 == 0, B <= 1024 (cvcl_flat_fused_supported); anything
  * else returns CVCL_ERR_UNSUPPORTED (callers then use cvcl_flat_contrastive_step).
- * workspace: cvcl_flat_fused_workspace_bytes bytes, 256-byte aligned, its first 512 bytes zeroed ONCE before
+ * workspace: cvcl_flat_fused_workspace_bytes bytes, 256-byte aligned, its first 1024 bytes zeroed ONCE before
  * the first call (the kernel leaves them reusable); one step in flight per workspace.
- * phase_limit: 0 = whole step; k = 1..5 leaves after phase k (measurement / debugging; outputs then
- * partial).  Deterministic except for the embedding scatter (fp32 atomics, as the reference's
- * embedding_dense_backward on CUDA). */
+ * phase_limit: 0 = whole step; k = 1..5 leaves after phase k, 100 = six grid barriers only (measurement /
+ * debugging; outputs then partial).  No atomics on data: every reduction is a fixed-order sum and the
+ * embedding gradient is the GEMM  d table = C^T . dm  against the token-count matrix C[b,v], so the step
+ * is bit-reproducible (the reference's embedding_dense_backward on CUDA is not). */
 int cvcl_flat_fused_supported(int B, int L, int E, int K, int V);
 size_t cvcl_flat_fused_workspace_bytes(int B, int L, int E, int K, int V);
 /* byte offsets of the workspace blocks (tests / tools): out[0..13] = ctrl, hpart, img16, txt16, invn, part, diag,
- * lse, rb_part, dspart, dqpart, du16, dbpart, total; out[14..19] = Bp, KS, nPart, dw_bn, grid, nCB.
- * ctrl + 128 holds 16 globaltimer stamps (ns) of CTA 0: [0] start, [k] after grid barrier k, [15] end. */
+ * lse, rb_part, dspart, dqpart, du16, dbpart, total; out[14..19] = Bp, KS, nPart, dw_bn, grid, nCB;
+ * out[20..23] = dm16, cmat, QS, Vp.  ctrl + 128 holds 48 globaltimer stamps (ns) of CTA 0: [0] start,
+ * [k] after grid barrier k, [15] end, [16..28] inside the phases (csrc/fused_step.cuh: CVCL_STAMP). */
 int cvcl_flat_fused_layout(int B, int L, int E, int K, int V, long long* out, int n);
 int cvcl_flat_step_fused(const void* x16, const void* w16, const int64_t* ids, const int64_t* lens,
                          const float* bias, const float* table, int B, int L, int E, int K, int V,

@@ -647,33 +647,38 @@ int cvcl_flat_contrastive_step(const void* x, int x_is_bf16, const int64_t* ids,
 // ------------------------------------------------------------------------------------ fused flat step, one kernel
 namespace {
 struct FusedPlan {
-    int Bp, nMB, nEB, nCB, KS, kc_per_split, num_kc, T, nPart, dw_bn, grid;
+    int Bp, nMB, nEB, nCB, KS, kc_per_split, num_kc, T, nPart, QS, Vp, dw_bn, grid;
     size_t off_ctrl, off_hpart, off_img16, off_txt16, off_invn, off_part, off_diag, off_lse, off_rbpart, off_dspart,
-           off_dqpart, off_du16, off_dbpart, bytes;
+           off_dqpart, off_du16, off_dbpart, off_dm16, off_cmat, bytes;
 };
 // -> 0 when the persistent kernel covers the shape, else the reason (unsupported, not an error)
 const char* plan_fused(FusedPlan* f, int B, int E, int K, int V) {
-    (void)V;
     const int G = sm_count();
     if (B < 1) return "B < 1";
     if (E % 128 != 0 || E < 128 || E > 512) return "E must be 128, 256, 384 or 512";
     if (K % 64 != 0 || K < 64) return "K must be a multiple of 64";
+    if (V < 1) return "V < 1";
     f->grid = G;
     f->Bp = ceil_div(B, 128) * 128;
     f->nMB = f->Bp / 128; f->nEB = E / 128; f->nCB = f->nMB;
     f->T = 1; f->nPart = f->nCB / f->T;
-    if (2 * f->nMB * f->nPart > G - 1) return "batch too large for one similarity tile per SM";
+    const int n_tiles = 2 * f->nMB * f->nPart;
+    if (n_tiles > G) return "batch too large for one similarity tile per SM";
+    f->QS = 1;                                   // CTAs per similarity tile: the largest divisor of E/128 that fits
+    for (int d = f->nEB; d >= 1; --d)
+        if (f->nEB % d == 0 && n_tiles * d <= G) { f->QS = d; break; }
     const int tiles = f->nMB * f->nEB;
     if (tiles > G) return "batch too large for the head phase";
     f->num_kc = K / 64;
     int ks = G / tiles; if (ks > f->num_kc) ks = f->num_kc;
     f->kc_per_split = ceil_div(f->num_kc, ks);
     f->KS = ceil_div(f->num_kc, f->kc_per_split);
-    f->dw_bn = (f->nEB * (K / 64) <= G - 1 || K % 128 != 0) ? 64 : 128;
+    f->dw_bn = (K % 128 == 0) ? 128 : 64;
+    f->Vp = pad8(V);
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
     const size_t Bp = f->Bp;
-    f->off_ctrl = take(512);
+    f->off_ctrl = take(1024);
     f->off_hpart = take(4ull * f->KS * Bp * E);
     f->off_img16 = take(2ull * Bp * E);
     f->off_txt16 = take(2ull * Bp * E);
@@ -686,6 +691,8 @@ const char* plan_fused(FusedPlan* f, int B, int E, int K, int V) {
     f->off_dqpart = take(4ull * 2 * f->nPart * Bp * E);
     f->off_du16 = take(2ull * Bp * E);
     f->off_dbpart = take(4ull * G * E);
+    f->off_dm16 = take(2ull * Bp * E);
+    f->off_cmat = take(2ull * Bp * f->Vp);
     f->bytes = off;
     return nullptr;
 }
@@ -711,7 +718,8 @@ int cvcl_flat_fused_layout(int B, int L, int E, int K, int V, long long* out, in
     const long long v[] = {(long long)f.off_ctrl, (long long)f.off_hpart, (long long)f.off_img16, (long long)f.off_txt16,
                            (long long)f.off_invn, (long long)f.off_part, (long long)f.off_diag, (long long)f.off_lse,
                            (long long)f.off_rbpart, (long long)f.off_dspart, (long long)f.off_dqpart, (long long)f.off_du16,
-                           (long long)f.off_dbpart, (long long)f.bytes, f.Bp, f.KS, f.nPart, f.dw_bn, f.grid, f.nCB};
+                           (long long)f.off_dbpart, (long long)f.bytes, f.Bp, f.KS, f.nPart, f.dw_bn, f.grid, f.nCB,
+                           (long long)f.off_dm16, (long long)f.off_cmat, f.QS, f.Vp};
     for (int i = 0; i < n && i < (int)(sizeof(v) / sizeof(v[0])); ++i) out[i] = v[i];
     return CVCL_OK;
 }
@@ -739,7 +747,8 @@ int cvcl_flat_step_fused(const void* x16, const void* w16, const int64_t* ids, c
     p.B = B; p.L = L; p.E = E; p.K = K; p.V = V; p.normalize = normalize; p.need_grads = need_grads;
     p.Bg = B; p.diag_off = 0;
     p.Bp = f.Bp; p.nMB = f.nMB; p.nEB = f.nEB; p.nCB = f.nCB; p.KS = f.KS; p.kc_per_split = f.kc_per_split;
-    p.num_kc = f.num_kc; p.T = f.T; p.nPart = f.nPart; p.dw_bn = f.dw_bn; p.phase_limit = phase_limit;
+    p.num_kc = f.num_kc; p.T = f.T; p.nPart = f.nPart; p.QS = f.QS; p.Vp = f.Vp; p.dw_bn = f.dw_bn;
+    p.phase_limit = phase_limit;
     p.hpart = reinterpret_cast<float*>(ws + f.off_hpart);
     p.q16[0] = reinterpret_cast<__nv_bfloat16*>(ws + f.off_img16);
     p.q16[1] = reinterpret_cast<__nv_bfloat16*>(ws + f.off_txt16);
@@ -757,6 +766,8 @@ int cvcl_flat_step_fused(const void* x16, const void* w16, const int64_t* ids, c
     p.dqpart = reinterpret_cast<float*>(ws + f.off_dqpart);
     p.du16 = reinterpret_cast<__nv_bfloat16*>(ws + f.off_du16);
     p.dbpart = reinterpret_cast<float*>(ws + f.off_dbpart);
+    p.dm16 = reinterpret_cast<__nv_bfloat16*>(ws + f.off_dm16);
+    p.cmat = reinterpret_cast<__nv_bfloat16*>(ws + f.off_cmat);
     p.sync = reinterpret_cast<unsigned int*>(ws + f.off_ctrl);
     p.fault = reinterpret_cast<int*>(ws + f.off_ctrl + 64);
     p.timing = reinterpret_cast<unsigned long long*>(ws + f.off_ctrl + 128);
@@ -778,8 +789,14 @@ int cvcl_flat_step_fused(const void* x16, const void* w16, const int64_t* ids, c
     if ((rc = make_tmap(&maps.dq_out, p.dqpart, 4, 2ull * f.nPart * f.Bp, E, E, 32, 128))) return rc;
     if ((rc = make_tmap(&maps.du_mn, p.du16, 2, B, E, E, 64, 64))) return rc;
     if ((rc = make_tmap(&maps.x_mn, x16, 2, B, K, K, 64, 64))) return rc;
-    if (need_grads) { if ((rc = make_tmap(&maps.dw_out, dW, 4, E, K, K, 32, 128))) return rc; }
-    else maps.dw_out = maps.hp_out;
+    if ((rc = make_tmap(&maps.c_mn, p.cmat, 2, B, V, f.Vp, 64, 64))) return rc;
+    if ((rc = make_tmap(&maps.dm_mn, p.dm16, 2, B, E, E, 64, 64))) return rc;
+    if (need_grads) {
+        if ((rc = make_tmap(&maps.dw_out, dW, 4, E, K, K, 32, 128))) return rc;
+        if ((rc = make_tmap(&maps.dt_out, dtable, 4, V, E, E, 32, 128))) return rc;
+    } else {
+        maps.dw_out = maps.hp_out; maps.dt_out = maps.hp_out;
+    }
 
     static thread_local bool attr_done = false;
     if (!attr_done) {

@@ -7,23 +7,28 @@
 // Why one kernel: at 512 pairs the step is ~3.2 GFLOP / ~31 MB (about 5 us of roofline work) and the
 // ten-kernel version spent its 78 us on launch gaps, per-launch TMEM/barrier set-up and 16-32-CTA grids
 // (profiles/r01_step_phases_n1.txt).  Here one co-resident grid (one CTA per SM, cooperative launch) walks
-// through the phases with grid-wide barriers (one atomic counter in L2, ~1 us each); TMEM, the mbarrier
-// ring and the tensor maps are set up once.
+// through the phases with grid-wide barriers (one atomic counter in L2); TMEM, the mbarrier ring and the
+// tensor maps are set up once.  No atomics on data anywhere: every reduction is a fixed-order sum, so the
+// whole step is bit-reproducible.
 //
 //   P0  head GEMM, split over the contraction so that ~128 CTAs each stream 1/KS of K (tcgen05, fp32
-//       partial tile -> its own slab by TMA store: no atomics, no memset)         || text encoder on the
-//       epilogue warps of every CTA (one warp per utterance, 8 table rows in flight per lane)
-//   P1  slab sum (fixed order) + bias + L2 normalise -> bf16 image features, 1/norm     (warp per row)
+//       partial tile -> its own slab by TMA store: no atomics, no memset)   ||   text encoder on the two
+//       auxiliary warps of every CTA and on the epilogue warps once they are free (one warp per utterance
+//       from a work queue, 8 table rows in flight per lane)   ||   zeroing of the token-count matrix
+//   P1  slab sum (fixed order) + bias + L2 normalise -> bf16 image features, 1/norm (warp per row); the same
+//       warp writes row r of the token-count matrix C[r, v] = #{l : ids[r,l] = v != 0} (bf16, exact)
 //   P2  similarity tiles: both directions as row problems (direction 0: images x texts, direction 1:
-//       texts x images; 2*(B/128)^2 CTAs), the 128x128 fp32 tile stays in TMEM; online-softmax row
-//       statistics per tile.  Idle CTAs zero the embedding-gradient table meanwhile.
+//       texts x images), the 128x128 fp32 tile stays in TMEM; online-softmax row statistics per tile
 //   P3  merge the statistics (row LSEs of both directions), dL/dlogits from the SAME TMEM tile (no
 //       recompute GEMM), written as the bf16 A operand straight into swizzled shared memory, then
-//       dQ_partial = Gs_tile . K_block (tcgen05, N = E) -> slab by TMA store
-//   P4  slab sum + the -2I term in fp32 + F.normalize backward; image rows -> bf16 du (operand of dW)
-//       and per-CTA bias partials; text rows -> /len and the embedding scatter (red.global.add.v4)
-//   P5  dW = du^T x (both operands MN-major, read in place) -> fp32 tiles by TMA store; the last CTA adds
-//       the per-block partial sums of loss / accuracy / entropy / ds / db in a fixed order.
+//       dQ_partial = Gs_tile . K_block (tcgen05) -> slab by TMA store.  P2/P3 run on QS CTAs per tile, each
+//       owning E/QS output columns of dQ (the tile GEMM is repeated: latency, not flops, is the limit here)
+//   P4  slab sum + the -2I term in fp32 + F.normalize backward; image rows -> bf16 du (operand of dW) and
+//       per-CTA bias partials; text rows -> /len -> bf16 dm (operand of the embedding gradient)
+//   P5  dW = du^T x  and  d table = C^T dm  (the embedding-bag backward as a GEMM against the token counts:
+//       nn.Embedding(padding_idx=0) semantics fall out of C[:,0] = 0), both operands MN-major, read in place,
+//       fp32 tiles by TMA store; the last CTA adds the per-block partial sums of loss / accuracy / entropy /
+//       ds / db in a fixed order.
 //
 // Sharded use enters through the same code: Q = the local pairs, K = the gathered features,
 // diag_off = rank * B (see StepParams::kf16 / lse_all).
@@ -34,7 +39,7 @@
 namespace cvcl {
 namespace fused {
 
-constexpr int kThreads = 192;                    // warp 0 TMA, warp 1 MMA + TMEM, warps 2..5 epilogue
+constexpr int kThreads = 256;                    // warp 0 TMA, warp 1 MMA + TMEM, warps 2..5 epilogue, 6..7 auxiliary
 constexpr int kWarps = kThreads / 32;
 constexpr int kStages = 4;
 constexpr int kStageBytes = 32768;               // A 128x64 bf16 + B 128x64 bf16 (or one 64 x 256 MN-major slab)
@@ -42,7 +47,7 @@ constexpr int kRingBytes = kStages * kStageBytes;
 constexpr int kGsOff = kRingBytes;               // dL/dlogits as the A operand: up to 2 tiles x 2 k-chunks x 16 KB
 constexpr int kGsBytes = 65536;
 constexpr int kMiscOff = kGsOff + kGsBytes;
-constexpr int kMiscBytes = 16384;
+constexpr int kMiscBytes = 20480;
 constexpr int kSmemBytes = kMiscOff + kMiscBytes + 1024;     // + alignment slack
 constexpr int kMaxT = 2;                         // similarity tiles per CTA (same row block)
 constexpr int kNumSync = 8;
@@ -58,6 +63,9 @@ struct alignas(64) StepMaps {
     CUtensorMap du_mn;       // du16 [B, E]  box 64 x 64  (P5 A, MN-major)
     CUtensorMap x_mn;        // x16  [B, K]  box 64 x 64  (P5 B, MN-major)
     CUtensorMap dw_out;      // dW [E, K] f32 box 32 x 128 (P5 out)
+    CUtensorMap c_mn;        // token counts C [B, V] bf16 (ld Vp) box 64 x 64 (P5 A, MN-major)
+    CUtensorMap dm_mn;       // dm16 [B, E] box 64 x 64 (P5 B, MN-major)
+    CUtensorMap dt_out;      // d table [V, E] f32 box 32 x 128 (P5 out)
 };
 
 struct StepParams {
@@ -72,6 +80,8 @@ struct StepParams {
     int nMB, nEB, nCB;                   // row blocks (local), E / 128, column blocks (global)
     int KS, kc_per_split, num_kc;        // head split-K
     int T, nPart;                        // similarity tiles per CTA, partial slabs per row block
+    int QS;                              // CTAs per similarity tile; each owns E / QS columns of dQ
+    int Vp;                              // leading dimension of the token-count matrix (V rounded up to 8)
     int dw_bn;                           // 64 or 128: width of a dW tile
     int phase_limit;                     // measurement / debugging: leave after phase k (0 = run all)
     // ---- workspace
@@ -87,9 +97,11 @@ struct StepParams {
     float* dspart;                       // [nMB*nPart]
     float* dqpart;                       // [2][nPart][Bp][E]
     __nv_bfloat16* du16;                 // [Bp][E]
+    __nv_bfloat16* dm16;                 // [Bp][E]  d mean-embedding / len (text side)
+    __nv_bfloat16* cmat;                 // [Bp][Vp] token counts
     float* dbpart;                       // [grid][E]
     unsigned int* sync;                  // [kNumSync] zero on entry, left zero on exit
-    unsigned long long* timing;          // [16] globaltimer stamps of CTA 0 (nullable)
+    unsigned long long* timing;          // [48] globaltimer stamps of CTA 0 (nullable): [0..15] barriers, [16..] in-phase
     int* status;                         // out-of-range token id -> 1 (nullable)
     int* fault;                          // barrier time-out code (nullable)
     // ---- outputs
@@ -230,17 +242,28 @@ __device__ __forceinline__ void stage_f32_cols(uint32_t tmem_row, int c0, int nc
     }
 }
 
-// online merge of per-tile softmax partials (strict >: the first tile wins ties, as torch.argmax does)
+// online merge of per-tile softmax partials (strict >: the first tile wins ties, as torch.argmax does);
+// the partials are fetched first (independent loads), then merged in tile order
 __device__ __forceinline__ void merge_stats(const RowStat* base, size_t stride, int n, float& gm, float& gl, float& ga,
                                             int& garg) {
     gm = -INFINITY; gl = 0.f; ga = 0.f; garg = 0x7fffffff;
-    for (int t = 0; t < n; ++t) {
-        const float4 q = __ldcg(reinterpret_cast<const float4*>(base + static_cast<size_t>(t) * stride));
-        const float rm = q.x, rl = q.y, ra = q.z; const int rarg = __float_as_int(q.w);
-        if (rm > gm) { const float w = __expf(gm - rm); gl = gl * w + rl; ga = ga * w + ra; gm = rm; garg = rarg; }
-        else { const float w = __expf(rm - gm); gl = fmaf(rl, w, gl); ga = fmaf(ra, w, ga); }
+    for (int t0 = 0; t0 < n; t0 += 8) {
+        float4 q[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (t0 + k < n) q[k] = __ldcg(reinterpret_cast<const float4*>(base + static_cast<size_t>(t0 + k) * stride));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (t0 + k < n) {
+                const float rm = q[k].x, rl = q[k].y, ra = q[k].z; const int rarg = __float_as_int(q[k].w);
+                if (rm > gm) { const float w = __expf(gm - rm); gl = gl * w + rl; ga = ga * w + ra; gm = rm; garg = rarg; }
+                else { const float w = __expf(rm - gm); gl = fmaf(rl, w, gl); ga = fmaf(ra, w, ga); }
+            }
+        }
     }
 }
+
+#define CVCL_STAMP(i) do { if (cta == 0 && p.timing) p.timing[i] = globaltimer_ns(); } while (0)
 
 __global__ void __launch_bounds__(kThreads, 1)
 flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
@@ -253,6 +276,7 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
     uint64_t* tfull_bar = empty_bar + kStages;                           // accumulator complete
     uint64_t* gs_bar = tfull_bar + 1;                                    // Gs tiles written, S tile consumed
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gs_bar + 1);
+    int* s_next = reinterpret_cast<int*>(misc + 128);                    // [kWarps] work-queue tickets
     float* lk = reinterpret_cast<float*>(misc + 256);                    // [256] column LSE terms (P3)
     float* red = reinterpret_cast<float*>(misc + 256 + 1024);            // [64] block reductions
     float* sdb = reinterpret_cast<float*>(misc + 2048);                  // [kWarps][512] bias partials (P4)
@@ -278,6 +302,7 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
 
     Ring ring{0, 0};                       // producer and MMA issuer walk the same sequence of stages
     uint32_t tfull_uses = 0;               // MMA issuer and epilogue warps count accumulator hand-overs alike
+    const bool is_epi = warp >= 2 && warp < 6;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;      // epilogue warps: accumulator row of this thread
     const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
@@ -286,6 +311,11 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
     const float scale = expf(s_log);
     constexpr float kLog2e = 1.4426950408889634f;
     int sync_k = 0;
+
+    if (p.phase_limit == 100) {            // measurement: the cost of the grid barrier alone
+        for (int i = 0; i < 6; ++i) grid_sync(p, sync_k++);
+        goto done;
+    }
 
     // ============================================================================ P0
     {
@@ -326,24 +356,42 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
                 }
             }
             __syncwarp();
-        } else {
-            // text encoder on the epilogue warps while the TMA / MMA warps stream the head tile
-            for (int u = cta * 4 + (warp - 2); u < p.B; u += G * 4) text_row(p, u, lane);
-            if (has) {
-                mbar_wait_b(tfull_bar, tfull_uses & 1u);
-                ptx::tc_fence_after();
-                stage_f32_cols(tmem_row, 0, 128, smem, row);          // the ring is idle: all MMAs have retired
-                ptx::fence_proxy_async_smem();
-                ptx::tc_fence_before();
-                ptx::named_bar_sync(1, kEpiThreads);
-                if (epi_tid == 0) {
+        }
+        // zero this CTA's slice of the token-count matrix (filled in P1, consumed in P5)
+        if (p.need_grads) {
+            const size_t n16 = static_cast<size_t>(p.B) * p.Vp * 2 / 16;
+            uint4* dst = reinterpret_cast<uint4*>(p.cmat);
+            for (size_t i = static_cast<size_t>(cta) * kThreads + threadIdx.x; i < n16; i += static_cast<size_t>(G) * kThreads)
+                dst[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (is_epi && has) {
+            mbar_wait_b(tfull_bar, tfull_uses & 1u);
+            ptx::tc_fence_after();
+            if (epi_tid == 0) CVCL_STAMP(16);
+            stage_f32_cols(tmem_row, 0, 128, smem, row);          // the ring is idle: all MMAs have retired
+            ptx::fence_proxy_async_smem();
+            ptx::tc_fence_before();
+            ptx::named_bar_sync(1, kEpiThreads);
+            if (epi_tid == 0) {
 #pragma unroll
-                    for (int b4 = 0; b4 < 4; ++b4)
-                        ptx::tma_store_2d(&maps.hp_out, smem + b4 * 16384, nb * 128 + b4 * 32, ks * p.Bp + mb * kBM);
-                    tma_store_commit();
-                    tma_store_wait_all();
-                }
+                for (int b4 = 0; b4 < 4; ++b4)
+                    ptx::tma_store_2d(&maps.hp_out, smem + b4 * 16384, nb * 128 + b4 * 32, ks * p.Bp + mb * kBM);
+                tma_store_commit();
+                tma_store_wait_all();
+                CVCL_STAMP(17);
             }
+        }
+        // text encoder: utterances from a work queue (auxiliary warps at once, epilogue warps when free)
+        if (warp >= 2) {
+            for (;;) {
+                if (lane == 0) s_next[warp] = static_cast<int>(atomicAdd(p.sync + 2, 1u));
+                __syncwarp();
+                const int u = s_next[warp];
+                __syncwarp();
+                if (u >= p.B) break;
+                text_row(p, u, lane);
+            }
+            if (warp == 2 && lane == 0) CVCL_STAMP(18);
         }
         if (has) ++tfull_uses;
     }
@@ -360,10 +408,10 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
             const float* base = p.hpart + static_cast<size_t>(r) * p.E;
-            for (int k0 = 0; k0 < p.KS; k0 += 4) {
-                float4 v[4][4];
+            for (int k0 = 0; k0 < p.KS; k0 += 8) {
+                float4 v[8][4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
+                for (int k = 0; k < 8; ++k)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         v[k][c] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -371,7 +419,7 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
                             v[k][c] = __ldcg(reinterpret_cast<const float4*>(base + (k0 + k) * slab) + c * 32 + lane);
                     }
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
+                for (int k = 0; k < 8; ++k)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         acc[c].x += v[k][c].x; acc[c].y += v[k][c].y; acc[c].z += v[k][c].z; acc[c].w += v[k][c].w;
@@ -398,18 +446,38 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
                     store_bf16x4(p.q16[0] + static_cast<size_t>(r) * p.ldq + e, t);
                 }
             }
+            if (p.need_grads) {
+                // row r of the token-count matrix: C[r, v] = #{l : ids[r, l] = v}, v != 0 (this warp owns the row)
+                __nv_bfloat16* crow = p.cmat + static_cast<size_t>(r) * p.Vp;
+                const long long* idrow = p.ids + static_cast<size_t>(r) * p.L;
+                for (int l0 = 0; l0 < p.L; l0 += 32) {
+                    const long long id = (l0 + lane < p.L) ? __ldg(idrow + l0 + lane) : 0;
+                    const bool valid = id > 0 && id < p.V;
+                    const unsigned grp = __match_any_sync(0xffffffffu, valid ? static_cast<int>(id) : -1 - lane);
+                    if (valid && lane == __ffs(grp) - 1) {
+                        float cnt = static_cast<float>(__popc(grp));
+                        if (l0 > 0) cnt += __bfloat162float(crow[id]);     // earlier chunk of a long utterance
+                        crow[id] = __float2bfloat16_rn(cnt);
+                    }
+                    __syncwarp();
+                }
+            }
         }
+        if (threadIdx.x == 0) CVCL_STAMP(19);
     }
     grid_sync(p, sync_k++);
     if (p.phase_limit == 2) goto done;
 
     {
         // ======================================================================== P2
-        // similarity CTA s: direction z, local row block rb, partial index pi -> column blocks pi*T + j
-        const int n_sim = 2 * p.nMB * p.nPart;
+        // similarity CTA: direction z, local row block rb, partial index pi (column blocks pi*T + j), and
+        // q = which E/QS columns of dQ this CTA produces in P3 (the S tile itself is computed by all QS CTAs)
+        const int n_sim = 2 * p.nMB * p.nPart * p.QS;
         const bool has = cta < n_sim;
-        const int z = cta / (p.nMB * p.nPart);
-        const int rem = cta % (p.nMB * p.nPart);
+        const int qs = cta % p.QS;
+        const int tix = cta / p.QS;
+        const int z = tix / (p.nMB * p.nPart);
+        const int rem = tix % (p.nMB * p.nPart);
         const int rb = rem / p.nPart, pi = rem % p.nPart;
         const int num_ke = p.E / kBK;
         const int M = p.B, N = p.Bg;
@@ -448,89 +516,86 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
             }
             __syncwarp();
         }
-        if (has && warp >= 2) {
+        if (has && is_epi) {
             mbar_wait_b(tfull_bar, tfull_uses & 1u);
             ptx::tc_fence_after();
-            const float sc2 = scale * kLog2e;
-            for (int j = 0; j < p.T; ++j) {
-                // raw-domain online softmax over this tile's 128 columns (see EpiSimStats)
-                const int n0 = (pi * p.T + j) * 128;
-                float mx = -INFINITY, l = 0.f, a = 0.f; int arg = n0;
+            if (epi_tid == 0) CVCL_STAMP(20);
+            if (qs == 0) {                                  // the statistics are written once per tile
+                const float sc2 = scale * kLog2e;
+                for (int j = 0; j < p.T; ++j) {
+                    // raw-domain online softmax over this tile's 128 columns (see EpiSimStats)
+                    const int n0 = (pi * p.T + j) * 128;
+                    float mx = -INFINITY, l = 0.f, a = 0.f; int arg = n0;
 #pragma unroll 1
-                for (int c = 0; c < 128; c += 32) {
-                    float v[32];
-                    ptx::tmem_ld_32x32(tmem_row + 128 * j + c, v);
-                    const int n = n0 + c;
-                    if (n >= N) continue;                               // warp-uniform
-                    const bool full = n + 32 <= N;
-                    if (!full) {
+                    for (int c = 0; c < 128; c += 32) {
+                        float v[32];
+                        ptx::tmem_ld_32x32(tmem_row + 128 * j + c, v);
+                        const int n = n0 + c;
+                        if (n >= N) continue;                               // warp-uniform
+                        const bool full = n + 32 <= N;
+                        if (!full) {
 #pragma unroll
-                        for (int q = 0; q < 32; ++q) if (n + q >= N) v[q] = -INFINITY;
+                            for (int q = 0; q < 32; ++q) if (n + q >= N) v[q] = -INFINITY;
+                        }
+                        float cm = v[0];
+#pragma unroll
+                        for (int q = 1; q < 32; ++q) cm = fmaxf(cm, v[q]);
+                        if (cm > mx) {
+                            int k = 31;
+#pragma unroll
+                            for (int q = 31; q >= 0; --q) if (v[q] == cm) k = q;
+                            arg = n + k;
+                        }
+                        if (dcol >= n && dcol < n + 32 && m < M) {
+                            float dv = 0.f;
+#pragma unroll
+                            for (int q = 0; q < 32; ++q) if (n + q == dcol) dv = v[q];
+                            p.diag[z][m] = dv * scale;
+                        }
+                        const float nm = fmaxf(mx, cm);
+                        const float corr = exp2f((mx - nm) * sc2);
+                        l *= corr; a *= corr;
+                        const float nm2 = nm * sc2;
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) {
+                            const float e = exp2f(fmaf(v[q], sc2, -nm2));
+                            l += e;
+                            a = fmaf(e, full ? v[q] : (n + q < N ? v[q] : 0.f), a);
+                        }
+                        mx = nm;
                     }
-                    float cm = v[0];
-#pragma unroll
-                    for (int q = 1; q < 32; ++q) cm = fmaxf(cm, v[q]);
-                    if (cm > mx) {
-                        int k = 31;
-#pragma unroll
-                        for (int q = 31; q >= 0; --q) if (v[q] == cm) k = q;
-                        arg = n + k;
+                    if (m < M) {
+                        RowStat rs; rs.m = mx * scale; rs.l = l; rs.a = a * scale; rs.arg = arg;
+                        p.part[z][static_cast<size_t>(pi * p.T + j) * p.Bp + m] = rs;
                     }
-                    if (dcol >= n && dcol < n + 32 && m < M) {
-                        float dv = 0.f;
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) if (n + q == dcol) dv = v[q];
-                        p.diag[z][m] = dv * scale;
-                    }
-                    const float nm = fmaxf(mx, cm);
-                    const float corr = exp2f((mx - nm) * sc2);
-                    l *= corr; a *= corr;
-                    const float nm2 = nm * sc2;
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) {
-                        const float e = exp2f(fmaf(v[q], sc2, -nm2));
-                        l += e;
-                        a = fmaf(e, full ? v[q] : (n + q < N ? v[q] : 0.f), a);
-                    }
-                    mx = nm;
-                }
-                if (m < M) {
-                    RowStat rs; rs.m = mx * scale; rs.l = l; rs.a = a * scale; rs.arg = arg;
-                    p.part[z][static_cast<size_t>(pi * p.T + j) * p.Bp + m] = rs;
                 }
             }
             ptx::tc_fence_before();
-        }
-        if (!has && p.need_grads) {
-            // idle CTAs: zero the embedding-gradient table for the scatter of P4
-            const int n_idle = G - n_sim;
-            const size_t n4 = static_cast<size_t>(p.V) * p.E / 4;
-            float4* dst = reinterpret_cast<float4*>(p.dtable);
-            for (size_t i = static_cast<size_t>(cta - n_sim) * kThreads + threadIdx.x; i < n4;
-                 i += static_cast<size_t>(n_idle) * kThreads)
-                dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (epi_tid == 0) CVCL_STAMP(21);
         }
         if (has) ++tfull_uses;
         grid_sync(p, sync_k++);
         if (p.phase_limit == 3) goto done;
 
         // ======================================================================== P3
-        if (has && warp >= 2) {
+        const int wq = p.E / p.QS;                          // dQ columns of this CTA: [qs*wq, qs*wq + wq)
+        if (has && is_epi) {
             // (a) row statistics of this row block: LSE, cross-entropy / entropy / accuracy terms
             float gm, gl, ga; int garg;
             float lse_row = 0.f;
             float v6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const bool lead = pi == 0 && qs == 0;
             if (m < M) {
                 merge_stats(p.part[z] + m, p.Bp, p.nCB, gm, gl, ga, garg);
                 lse_row = gm + logf(gl);
-                if (pi == 0) {
+                if (lead) {
                     p.lse[z][m] = lse_row;
                     v6[z] = lse_row - __ldcg(p.diag[z] + m);
                     v6[2 + z] = lse_row - ga / gl;
                     v6[4 + z] = (garg == dcol) ? 1.f : 0.f;
                 }
             }
-            if (pi == 0) {                                   // fixed-order block sum -> rb_part
+            if (lead) {                                      // fixed-order block sum -> rb_part
 #pragma unroll
                 for (int i = 0; i < 6; ++i) {
                     const float s = warp_sum(v6[i]);
@@ -562,6 +627,7 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
                     lk[c] = lkv;
                 }
                 ptx::named_bar_sync(1, kEpiThreads);
+                if (epi_tid == 0) CVCL_STAMP(22);
                 // (c) Gs = w * (softmax_row + softmax_col) from the tile still in TMEM -> bf16 A operand
                 const float lq = (m < M) ? lse_row * kLog2e - l2w : INFINITY;
                 const float sc2 = scale * kLog2e;
@@ -600,7 +666,8 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
                 ptx::fence_proxy_async_smem();              // generic smem writes -> tcgen05 (async proxy) reads
                 ptx::tc_fence_before();                     // the S tile has been read: its columns may be overwritten
                 ptx::mbar_arrive(gs_bar);
-                if (z == 0) {                               // dL/ds partial of this tile (direction 0 only)
+                if (epi_tid == 0) CVCL_STAMP(23);
+                if (z == 0 && qs == 0) {                    // dL/ds partial of this tile (direction 0 only)
                     ds = warp_sum(ds);
                     if (lane == 0) red[32 + (warp - 2)] = ds;
                     ptx::named_bar_sync(1, kEpiThreads);
@@ -609,19 +676,20 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
             }
         }
         if (has && p.need_grads) {
-            const int nH = (p.E + 255) / 256;
+            const int nH = (wq + 255) / 256;
             const int num_kc3 = 2 * p.T;
             if (warp == 0) {
                 if (lane == 0) {
                     for (int kc = 0; kc < num_kc3; ++kc)
                         for (int h = 0; h < nH; ++h) {
-                            const int nh = min(256, p.E - 256 * h);
+                            const int nh = min(256, wq - 256 * h);
                             mbar_wait_b(&empty_bar[ring.stage], ring.phase ^ 1u);
                             unsigned char* sb = smem + ring.stage * kStageBytes;
                             ptx::mbar_arrive_expect_tx(&full_bar[ring.stage], static_cast<uint32_t>(nh) * 128);
                             const int crow = (pi * p.T + (kc >> 1)) * 128 + (kc & 1) * 64;
                             for (int jb = 0; jb < nh / 64; ++jb)
-                                ptx::tma_load_2d(sb + jb * 8192, &maps.kf_mn[z], &full_bar[ring.stage], 256 * h + 64 * jb, crow);
+                                ptx::tma_load_2d(sb + jb * 8192, &maps.kf_mn[z], &full_bar[ring.stage],
+                                                 qs * wq + 256 * h + 64 * jb, crow);
                             ring.next();
                         }
                 }
@@ -632,7 +700,7 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
                     ptx::tc_fence_after();
                     for (int kc = 0; kc < num_kc3; ++kc)
                         for (int h = 0; h < nH; ++h) {
-                            const int nh = min(256, p.E - 256 * h);
+                            const int nh = min(256, wq - 256 * h);
                             const uint32_t idesc = ptx::make_idesc_bf16(kBM, nh, false, true);
                             mbar_wait_b(&full_bar[ring.stage], ring.phase);
                             ptx::tc_fence_after();
@@ -650,12 +718,13 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
                         }
                 }
                 __syncwarp();
-            } else {
-                // dQ partial [128, E] -> slab (z, pi): 128 columns per pass through two staging halves
+            } else if (is_epi) {
+                // dQ partial [128, wq] -> slab (z, pi), columns qs*wq..: 128 columns per pass, two staging halves
                 mbar_wait_b(tfull_bar, tfull_uses & 1u);
                 ptx::tc_fence_after();
+                if (epi_tid == 0) CVCL_STAMP(24);
                 const int out_row = ((z * p.nPart + pi) * p.Bp) + rb * kBM;
-                for (int q = 0; q < p.nEB; ++q) {
+                for (int q = 0; q < wq / 128; ++q) {
                     unsigned char* stg = smem + (q & 1) * 65536;
                     if (q >= 2) { if (epi_tid == 0) tma_store_wait_read<1>(); ptx::named_bar_sync(1, kEpiThreads); }
                     stage_f32_cols(tmem_row, 128 * q, 128, stg, row);
@@ -664,11 +733,11 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
                     if (epi_tid == 0) {
 #pragma unroll
                         for (int b4 = 0; b4 < 4; ++b4)
-                            ptx::tma_store_2d(&maps.dq_out, stg + b4 * 16384, 128 * q + b4 * 32, out_row);
+                            ptx::tma_store_2d(&maps.dq_out, stg + b4 * 16384, qs * wq + 128 * q + b4 * 32, out_row);
                         tma_store_commit();
                     }
                 }
-                if (epi_tid == 0) tma_store_wait_all();
+                if (epi_tid == 0) { tma_store_wait_all(); CVCL_STAMP(25); }
                 ptx::tc_fence_before();
             }
             ++tfull_uses;
@@ -679,7 +748,7 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
 
     if (p.need_grads) {
         // ======================================================================== P4
-        // task t < B: text row t (direction 1) -> d mean-embedding / len, scattered into d table;
+        // task t < B: text row t (direction 1) -> bf16 d mean-embedding / len (operand of the embedding gradient);
         // task B + r: image row r (direction 0) -> bf16 du (operand of dW) + bias partials
         const int nch = p.E >> 7;
         const size_t slab = static_cast<size_t>(p.Bp) * p.E;
@@ -694,6 +763,20 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
             const float* base = p.dqpart + (static_cast<size_t>(z) * p.nPart * p.Bp + r) * p.E;
+            // the positives of the other modality (the -2*I term of G, in fp32) and this row's own features
+            const __nv_bfloat16* posrow = p.kf16[z] + static_cast<size_t>(p.diag_off + r) * p.ldk;
+            const __nv_bfloat16* qrow = p.q16[z] + static_cast<size_t>(r) * p.ldq;
+            uint2 pr[4], qr[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                pr[c] = make_uint2(0u, 0u); qr[c] = make_uint2(0u, 0u);
+                if (c < nch) {
+                    pr[c] = __ldcg(reinterpret_cast<const uint2*>(posrow + (c * 32 + lane) * 4));
+                    qr[c] = __ldcg(reinterpret_cast<const uint2*>(qrow + (c * 32 + lane) * 4));
+                }
+            }
+            const float inv = p.normalize ? __ldcg(p.invn[z] + r) : 1.f;
+            const float rs = z ? 1.f / static_cast<float>(__ldg(p.lens + r)) : 1.f;
             for (int k0 = 0; k0 < p.nPart; k0 += 4) {
                 float4 v[4][4];
 #pragma unroll
@@ -711,56 +794,30 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
                         acc[c].x += v[k][c].x; acc[c].y += v[k][c].y; acc[c].z += v[k][c].z; acc[c].w += v[k][c].w;
                     }
             }
-            // the -2*I term of G in fp32 (positives of the other modality) and <q, acc>
-            const __nv_bfloat16* posrow = p.kf16[z] + static_cast<size_t>(p.diag_off + r) * p.ldk;
-            const __nv_bfloat16* qrow = p.q16[z] + static_cast<size_t>(r) * p.ldq;
             float4 qf[4];
             float dot = 0.f;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                qf[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (c < nch) {
-                    const int e = (c * 32 + lane) * 4;
-                    const uint2 pr = __ldcg(reinterpret_cast<const uint2*>(posrow + e));
-                    const uint2 qr = __ldcg(reinterpret_cast<const uint2*>(qrow + e));
-                    const float2 p0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pr.x));
-                    const float2 p1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pr.y));
-                    const float2 q0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qr.x));
-                    const float2 q1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qr.y));
-                    acc[c].x = fmaf(dcoef, p0.x, acc[c].x); acc[c].y = fmaf(dcoef, p0.y, acc[c].y);
-                    acc[c].z = fmaf(dcoef, p1.x, acc[c].z); acc[c].w = fmaf(dcoef, p1.y, acc[c].w);
-                    qf[c] = make_float4(q0.x, q0.y, q1.x, q1.y);
-                    dot = fmaf(qf[c].x, acc[c].x, dot); dot = fmaf(qf[c].y, acc[c].y, dot);
-                    dot = fmaf(qf[c].z, acc[c].z, dot); dot = fmaf(qf[c].w, acc[c].w, dot);
-                }
+                const float2 p0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pr[c].x));
+                const float2 p1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pr[c].y));
+                const float2 q0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qr[c].x));
+                const float2 q1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qr[c].y));
+                acc[c].x = fmaf(dcoef, p0.x, acc[c].x); acc[c].y = fmaf(dcoef, p0.y, acc[c].y);
+                acc[c].z = fmaf(dcoef, p1.x, acc[c].z); acc[c].w = fmaf(dcoef, p1.y, acc[c].w);
+                qf[c] = make_float4(q0.x, q0.y, q1.x, q1.y);
+                dot = fmaf(qf[c].x, acc[c].x, dot); dot = fmaf(qf[c].y, acc[c].y, dot);
+                dot = fmaf(qf[c].z, acc[c].z, dot); dot = fmaf(qf[c].w, acc[c].w, dot);
             }
-            float inv = 1.f;
-            if (p.normalize) { dot = warp_sum(dot); inv = __ldcg(p.invn[z] + r); } else dot = 0.f;
-            const float rs = z ? 1.f / static_cast<float>(__ldg(p.lens + r)) : 1.f;
+            if (p.normalize) dot = warp_sum(dot); else dot = 0.f;
+            __nv_bfloat16* orow = (z ? p.dm16 : p.du16) + static_cast<size_t>(r) * p.E;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 acc[c].x = (acc[c].x - qf[c].x * dot) * inv * rs; acc[c].y = (acc[c].y - qf[c].y * dot) * inv * rs;
                 acc[c].z = (acc[c].z - qf[c].z * dot) * inv * rs; acc[c].w = (acc[c].w - qf[c].w * dot) * inv * rs;
-            }
-            if (z == 0) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (c < nch) {
-                        store_bf16x4(p.du16 + static_cast<size_t>(r) * p.E + (c * 32 + lane) * 4, acc[c]);
+                if (c < nch) {
+                    store_bf16x4(orow + (c * 32 + lane) * 4, acc[c]);
+                    if (z == 0) {
                         dbacc[c].x += acc[c].x; dbacc[c].y += acc[c].y; dbacc[c].z += acc[c].z; dbacc[c].w += acc[c].w;
-                    }
-                }
-            } else {
-                const long long* idrow = p.ids + static_cast<size_t>(r) * p.L;
-                for (int l0 = 0; l0 < p.L; l0 += 32) {
-                    const long long my_id = (l0 + lane < p.L) ? __ldg(idrow + l0 + lane) : 0;
-                    unsigned live = __ballot_sync(0xffffffffu, my_id > 0 && my_id < p.V);
-                    while (live) {
-                        const int src = __ffs(live) - 1; live &= live - 1;
-                        const long long id = __shfl_sync(0xffffffffu, my_id, src);
-                        float4* dst = reinterpret_cast<float4*>(p.dtable + static_cast<size_t>(id) * p.E);
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) if (c < nch) atomicAdd(dst + c * 32 + lane, acc[c]);
                     }
                 }
             }
@@ -776,36 +833,45 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
             for (int w = 0; w < kWarps; ++w) s += sdb[w * 512 + e];
             p.dbpart[static_cast<size_t>(cta) * p.E + e] = s;
         }
+        if (threadIdx.x == 0) CVCL_STAMP(26);
     }
     if (p.need_grads) grid_sync(p, sync_k++);
     if (p.phase_limit == 5) goto done;
 
     if (p.need_grads) {
-        // ======================================================================== P5: dW = du^T . x
+        // ======================================================================== P5
+        // tiles [0, n_dw): dW[e, k] = sum_b du[b, e] x[b, k];  tiles [n_dw, ...): dtable[v, e] = sum_b C[b, v] dm[b, e]
         const int bn = p.dw_bn;
-        const int nKT = p.K / bn;
-        const int n_tiles = p.nEB * nKT;
+        const int n_dw = p.nEB * (p.K / bn);
+        const int n_dt = ((p.V + 127) / 128) * p.nEB;
         const int num_kc5 = (p.B + kBK - 1) / kBK;
-        for (int t = cta; t < n_tiles; t += G - 1) {       // the last CTA is kept for the final sums
+        for (int t = cta; t < n_dw + n_dt; t += G - 1) {   // the last CTA is kept for the final sums
             if (cta == G - 1) break;
-            const int eb = t % p.nEB, kt = t / p.nEB;
+            const bool is_dw = t < n_dw;
+            const int u = is_dw ? t : t - n_dw;
+            const int eb = u % p.nEB, ot = u / p.nEB;       // ot: k tile (dW) or vocabulary tile (d table)
+            const int tn = is_dw ? bn : 128;                // tile width
+            const CUtensorMap* mA = is_dw ? &maps.du_mn : &maps.c_mn;
+            const CUtensorMap* mB = is_dw ? &maps.x_mn : &maps.dm_mn;
+            const int a_col = is_dw ? eb * 128 : ot * 128;
+            const int b_col = is_dw ? ot * bn : eb * 128;
             if (warp == 0) {
                 if (lane == 0) {
                     for (int kc = 0; kc < num_kc5; ++kc) {
                         mbar_wait_b(&empty_bar[ring.stage], ring.phase ^ 1u);
                         unsigned char* sa = smem + ring.stage * kStageBytes;
-                        ptx::mbar_arrive_expect_tx(&full_bar[ring.stage], 16384u + static_cast<uint32_t>(bn) * 128u);
-                        ptx::tma_load_2d(sa, &maps.du_mn, &full_bar[ring.stage], eb * 128, kc * kBK);
-                        ptx::tma_load_2d(sa + 8192, &maps.du_mn, &full_bar[ring.stage], eb * 128 + 64, kc * kBK);
-                        for (int jb = 0; jb < bn / 64; ++jb)
-                            ptx::tma_load_2d(sa + 16384 + jb * 8192, &maps.x_mn, &full_bar[ring.stage], kt * bn + 64 * jb, kc * kBK);
+                        ptx::mbar_arrive_expect_tx(&full_bar[ring.stage], 16384u + static_cast<uint32_t>(tn) * 128u);
+                        ptx::tma_load_2d(sa, mA, &full_bar[ring.stage], a_col, kc * kBK);
+                        ptx::tma_load_2d(sa + 8192, mA, &full_bar[ring.stage], a_col + 64, kc * kBK);
+                        for (int jb = 0; jb < tn / 64; ++jb)
+                            ptx::tma_load_2d(sa + 16384 + jb * 8192, mB, &full_bar[ring.stage], b_col + 64 * jb, kc * kBK);
                         ring.next();
                     }
                 }
                 __syncwarp();
             } else if (warp == 1) {
                 if (lane == 0) {
-                    const uint32_t idesc = ptx::make_idesc_bf16(kBM, bn, true, true);
+                    const uint32_t idesc = ptx::make_idesc_bf16(kBM, tn, true, true);
                     for (int kc = 0; kc < num_kc5; ++kc) {
                         mbar_wait_b(&full_bar[ring.stage], ring.phase);
                         ptx::tc_fence_after();
@@ -821,18 +887,25 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
                     }
                 }
                 __syncwarp();
-            } else {
+            } else if (is_epi) {
                 mbar_wait_b(tfull_bar, tfull_uses & 1u);
                 ptx::tc_fence_after();
-                stage_f32_cols(tmem_row, 0, bn, smem, row);
+                if (epi_tid == 0) CVCL_STAMP(27);
+                stage_f32_cols(tmem_row, 0, tn, smem, row);
                 ptx::fence_proxy_async_smem();
                 ptx::tc_fence_before();
                 ptx::named_bar_sync(1, kEpiThreads);
                 if (epi_tid == 0) {
-                    for (int b4 = 0; b4 < bn / 32; ++b4)
-                        ptx::tma_store_2d(&maps.dw_out, smem + b4 * 16384, kt * bn + b4 * 32, eb * 128);
+                    if (is_dw) {
+                        for (int b4 = 0; b4 < tn / 32; ++b4)
+                            ptx::tma_store_2d(&maps.dw_out, smem + b4 * 16384, ot * bn + b4 * 32, eb * 128);
+                    } else {
+                        for (int b4 = 0; b4 < 4; ++b4)            // rows >= V are clipped by the tensor map
+                            ptx::tma_store_2d(&maps.dt_out, smem + b4 * 16384, eb * 128 + b4 * 32, ot * 128);
+                    }
                     tma_store_commit();
                     tma_store_wait_read<0>();
+                    CVCL_STAMP(28);
                 }
             }
             ++tfull_uses;
@@ -863,23 +936,31 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
             }
         }
         if (p.need_grads) {
+            // d bias: per-CTA partials in CTA order, 8 independent loads in flight
             for (int e = threadIdx.x; e < p.E; e += kThreads) {
                 float s = 0.f;
-                for (int b = 0; b < G; ++b) s += __ldcg(p.dbpart + static_cast<size_t>(b) * p.E + e);
+                for (int b0 = 0; b0 < G; b0 += 8) {
+                    float v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        v[k] = (b0 + k < G) ? __ldcg(p.dbpart + static_cast<size_t>(b0 + k) * p.E + e) : 0.f;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) s += v[k];
+                }
                 p.dbias[e] = s;
             }
         }
     }
 
 done:
-    // leave the barrier counter zeroed for the next launch: the last CTA through the exit ticket resets both
-    // (every CTA has passed its last grid barrier before it takes a ticket)
+    // leave the barrier counter and the work queue zeroed for the next launch: the last CTA through the exit
+    // ticket resets them (every CTA has passed its last grid barrier before it takes a ticket)
     __syncthreads();
     if (threadIdx.x == 0) {
         if (cta == 0 && p.timing) p.timing[15] = globaltimer_ns();
         __threadfence();
         if (atomicAdd(p.sync + 1, 1u) == static_cast<unsigned int>(G - 1)) {
-            p.sync[0] = 0u; p.sync[1] = 0u;
+            p.sync[0] = 0u; p.sync[1] = 0u; p.sync[2] = 0u;
             __threadfence();
         }
     }
@@ -887,6 +968,8 @@ done:
     __syncthreads();
     if (warp == 1) ptx::tmem_dealloc<512>(tmem_base);
 }
+
+#undef CVCL_STAMP
 
 }  // namespace fused
 }  // namespace cvcl

@@ -134,8 +134,12 @@ def run(B, E, K, V=2350, L=25, normalize=True, need_grads=True, verbose=True):
         launch(5)
         du16 = blk("du16", 2 * Bp * E, torch.bfloat16).view(Bp, E)[:B]
         rep["P4 du16"] = relerr(du16.float(), ref["du16"].float())
-        rep["P4 dtable"] = relerr(dtable, ref["dtable"])
-        rep["P4 dtable row0 zero"] = float(dtable[0].abs().max())
+        dm16 = blk("dm16", 2 * Bp * E, torch.bfloat16).view(Bp, E)[:B]
+        rep["P4 dm16"] = relerr(dm16.float(), ref["dm"].bfloat16().float())
+        cm = blk("cmat", 2 * Bp * lay["Vp"], torch.bfloat16).view(Bp, lay["Vp"])[:B, :V].float()
+        cref = torch.zeros(B, V, device=DEV)
+        cref.scatter_add_(1, ids, torch.ones_like(ids, dtype=torch.float32)); cref[:, 0] = 0
+        rep["P1 token counts exact"] = bool(torch.equal(cm, cref))
     flat.fill_(float("nan")); out5.zero_()
     launch(0)
     rep["loss"] = (float(out5[0]), float(ref["loss"]))
@@ -143,6 +147,7 @@ def run(B, E, K, V=2350, L=25, normalize=True, need_grads=True, verbose=True):
     rep["ent"] = (float(out5[3]), float(ref["ent0"]), float(out5[4]), float(ref["ent1"]))
     if need_grads:
         rep["dW"] = relerr(dW, ref["dW"]); rep["db"] = relerr(db, ref["db"]); rep["dtable"] = relerr(dtable, ref["dtable"])
+        rep["dtable row0 zero"] = float(dtable[0].abs().max())
         rep["ds"] = (float(ds[0]), float(ref["ds"]))
         rep["nan in grads"] = bool(torch.isnan(flat[0:1]).any() or torch.isnan(flat[4:]).any())
     # replay stability (the barrier counter must come back to zero) + timeline
@@ -151,20 +156,29 @@ def run(B, E, K, V=2350, L=25, normalize=True, need_grads=True, verbose=True):
         launch(0)
     rep["replay: out5 bit-identical"] = bool(torch.equal(o1[:5], out5[:5]))
     if need_grads:
-        rep["replay: dW/db/ds bit-identical"] = bool(torch.equal(g1[0:1], flat[0:1]) and torch.equal(g1[4:4 + E], flat[4:4 + E])
-                                                     and torch.equal(g1[4 + E + V * E:], flat[4 + E + V * E:]))
-    tm = ws[lay["ctrl"] + 128:lay["ctrl"] + 256].view(torch.int64).cpu().numpy()
-    names = ["start", "P0 head+text", "P1 normalise", "P2 similarity", "P3 Gs+dQ", "P4 finish+scatter"]
+        rep["replay: all gradients bit-identical"] = bool(torch.equal(g1[0:1], flat[0:1]) and torch.equal(g1[4:], flat[4:]))
+    tm = ws[lay["ctrl"] + 128:lay["ctrl"] + 512].view(torch.int64).cpu().numpy()
+    names = ["start", "P0 head+text", "P1 normalise", "P2 similarity", "P3 Gs+dQ", "P4 finish"]
     line = []
     for k in range(1, 6):
         if tm[k]:
             line.append("%s %.2f us" % (names[k], (tm[k] - tm[k - 1]) / 1e3))
     if tm[15]:
         last = max(k for k in range(6) if tm[k])
-        line.append("P5 dW+final %.2f us" % ((tm[15] - tm[last]) / 1e3))
+        line.append("P5 dW+dtable+final %.2f us" % ((tm[15] - tm[last]) / 1e3))
         line.append("total %.2f us" % ((tm[15] - tm[0]) / 1e3))
     rep["timeline (CTA 0, warm L2)"] = "; ".join(line)
+    fine = {16: ("P0 accumulator ready", 0), 17: ("P0 slab stored", 0), 18: ("P0 text queue drained", 0), 19: ("P1 rows done", 1),
+            20: ("P2 accumulator ready", 2), 21: ("P2 statistics done", 2), 22: ("P3 LSEs merged", 3), 23: ("P3 Gs written", 3),
+            24: ("P3 accumulator ready", 3), 25: ("P3 slab stored", 3), 26: ("P4 rows done", 4), 27: ("P5 accumulator ready", 5),
+            28: ("P5 tile stored", 5)}
+    rep["in-phase stamps (us after the phase began)"] = "; ".join(
+        "%s +%.2f" % (nm, (tm[i] - tm[ph]) / 1e3) for i, (nm, ph) in fine.items() if tm[i] and tm[ph])
     rep["control block after run"] = ws[:8].view(torch.int32).cpu().tolist()
+    ws[lay["ctrl"] + 128:lay["ctrl"] + 512].zero_()
+    launch(100)
+    tb = ws[lay["ctrl"] + 128:lay["ctrl"] + 512].view(torch.int64).cpu().numpy()
+    rep["grid barrier alone (us each, 6 in a row)"] = " ".join("%.2f" % ((tb[k + 1] - tb[k]) / 1e3) for k in range(1, 6))
     if verbose:
         for k, v in rep.items():
             print("%-36s %s" % (k, v))
