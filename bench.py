@@ -14,8 +14,9 @@ One JSON line on stdout (rank 0):
   value        pairs/s, inputs resident in HBM, CUDA-event timed per step, L2 flushed between steps
   e2e          pairs/s through MultiModalModel.calculate_contrastive_loss(...) + backward() with
                pinned HOST inputs (H2D inside the timed region) and a D2H read of the loss
-  roofline     dominant kernel of the step, event-timed in isolation: algorithmic bytes or flops
-               / duration vs MEASURED_PEAKS.json
+  roofline     the step kernel (one persistent kernel = the whole step at N = 1): algorithmic bytes and
+               flops / the same CUDA-event duration the value is computed from, vs MEASURED_PEAKS.json;
+               `phases` = in-kernel globaltimer stamps of its six phases
   cpu_baseline the oracle port (same ATen fp32 op sequence as the reference) on the host cores
 
 `--impl reference` times that CPU path alone (rank 0 only) and prints the same line shape.
@@ -155,106 +156,73 @@ def step_api(model, x, ids, lens, world):
     return out[0]
 
 
-def kernel_breakdown(m, dev, B, reps, flush, peaks):
-    """event-time each C-ABI kernel of the flat step in isolation (same shapes / buffers)."""
-    from multimodal_baby_b200 import _cabi
-    ops = m.ops
-    lib = _cabi.load()
-    f, ids, lens = synth_batch(1234, B)
-    W, b, table = synth_weights()
-    x16 = torch.from_numpy(f).to(dev).to(torch.bfloat16)
-    ids_d = torch.from_numpy(ids).to(dev); lens_d = torch.from_numpy(lens).to(dev)
-    W_d = torch.from_numpy(W).to(dev); b_d = torch.from_numpy(b).to(dev); tab_d = torch.from_numpy(table).to(dev)
-    bf = dict(dtype=torch.bfloat16, device=dev); f32 = dict(dtype=torch.float32, device=dev)
-    ldB = (B + 7) // 8 * 8
-    w16 = torch.empty((E, K), **bf)
-    img16 = torch.empty((B, E), **bf); txt16 = torch.empty((B, E), **bf)
-    G0 = torch.empty((B, ldB), **bf); du16 = torch.empty((B, E), **bf); u32 = torch.empty((B, E), **f32)
-    invn_i = torch.empty((B,), **f32); invn_t = torch.empty((B,), **f32)
-    lse0 = torch.empty((B,), **f32); lse1 = torch.empty((B,), **f32); dm = torch.empty((B, E), **f32)
-    dW = torch.empty((E, K), **f32); db = torch.zeros((E,), **f32); dtab = torch.zeros((V, E), **f32)
-    ds = torch.zeros((1,), **f32); out5 = torch.zeros((8,), **f32)
-    ws = torch.empty((lib.cvcl_sim_workspace_bytes(B, B, B, B),), dtype=torch.uint8, device=dev)
-    p = ops._p
-    st = lambda: torch.cuda.current_stream().cuda_stream
-    sum_len = int(lens.sum())
-    coef = 0.5 / B
-    dcoef = -2.0 * math.exp(S_FIXED) * coef
-    C = _cabi.call
-    kernels = [
-        ("cast_w_f32_to_bf16", lambda: C("cvcl_cast_transpose", p(W_d), 0, p(w16), None, 1, E, K, K, K, 0, 0, 0, 0, st()),
-         dict(bytes=E * K * 6)),
-        ("K1_text_encoder_fwd", lambda: C("cvcl_text_encoder_fwd", p(ids_d), p(lens_d), p(tab_d), B, L, E, V, 1, 0, 1.0,
-                                          None, p(txt16), E, p(invn_t), None, None, None, st()),
-         dict(bytes=8 * B * L + sum_len * E * 4 + B * E * 2)),
-        ("K2_head_proj_norm_fwd", lambda: C("cvcl_head_proj_norm_fwd", p(x16), K, p(w16), K, p(b_d), B, E, K, 1, p(u32), E,
-                                            p(img16), E, p(invn_i), st()),
-         dict(bytes=2 * B * K + 2 * E * K + 2 * B * E, flops=2 * B * K * E)),   # split-K GEMM + bias/normalise pass (+ memset)
-        ("K3K4_sim_infonce_fwd", lambda: C("cvcl_sim_infonce_fwd", p(img16), p(txt16), p(txt16), p(img16), E, B, B, B, B, E,
-                                           S_FIXED, 0, 1.0 / B, p(ws), p(lse0), p(lse1), None, None, p(out5), st()),
-         dict(bytes=4 * B * E * 2, flops=4 * B * B * E)),
-        ("K5a_sim_infonce_bwd_g", lambda: C("cvcl_sim_infonce_bwd_g", p(img16), p(txt16), None, None, E, B, B, 0, 0, E,
-                                            S_FIXED, 0, coef, p(lse0), p(lse1), None, None, p(G0), ldB, None, 0,
-                                            p(ds), st()),
-         dict(bytes=2 * B * E * 2 + B * B * 2, flops=2 * B * B * E)),
-        ("K5b_dimg_norm_bwd", lambda: C("cvcl_feat_grad_norm_bwd", p(G0), ldB, 0, p(txt16), E, B, E, B, p(img16), E, p(invn_i),
-                                        1, None, p(txt16), E, B, 0, dcoef, None, 0, p(du16), E, p(db), st()),
-         dict(bytes=2 * B * B + 2 * B * E * 3 + 2 * B * E, flops=2 * B * B * E)),
-        ("K5b_dtxt_norm_bwd", lambda: C("cvcl_feat_grad_norm_bwd", p(G0), ldB, 1, p(img16), E, B, E, B, p(txt16), E, p(invn_t),
-                                        1, p(lens_d), p(img16), E, B, 0, dcoef, p(dm), E, None, 0, None, st()),
-         dict(bytes=2 * B * B + 2 * B * E * 3 + 4 * B * E, flops=2 * B * B * E)),
-        ("K5c_head_weight_grad", lambda: C("cvcl_head_weight_grad", p(du16), E, p(x16), K, E, K, B, p(dW), K, st()),
-         dict(bytes=2 * E * B + 2 * K * B + 4 * E * K, flops=2 * E * K * B)),
-        ("K5e_embedding_scatter_add", lambda: C("cvcl_embedding_scatter_add", p(ids_d), p(dm), p(dtab), B, L, E, V, 0, st()),
-         dict(bytes=8 * B * L + 4 * B * E + 2 * sum_len * E * 4)),
-    ]
-    rows = []
-    for name, fn, work in kernels:
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        ts = []
-        for _ in range(reps):
-            flush.zero_()
-            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-            e0.record(); fn(); e1.record()
-            e1.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        ms = statistics.mean(ts)
-        gbs = work["bytes"] / (ms * 1e-3) / 1e9
-        row = dict(kernel=name, ms=ms, ms_min=min(ts), bytes=work["bytes"], gb_s=gbs,
-                   hbm_frac=gbs / peaks["hbm_gbs"])
-        t_h = work["bytes"] / (peaks["hbm_gbs"] * 1e9)
-        bound = "hbm"
-        if "flops" in work:
-            tf = work["flops"] / (ms * 1e-3) / 1e12
-            row.update(flops=work["flops"], tflop_s=tf, tensor_frac=tf / peaks["bf16_tflops"])
-            if work["flops"] / (peaks["bf16_tflops"] * 1e12) > t_h:
-                bound = "tensor"
-        row["bound"] = bound
-        rows.append(row)
-    return rows
+def step_work(B, world, sum_len):
+    """algorithmic work of one rank's step: bytes every operand / result
+    has to cross HBM at least once, flops of the contractions the reference performs."""
+    Bg = B * world
+    bytes_ = (2 * B * K            # x (bf16), read by the head GEMM; the dW GEMM re-reads it from L2
+              + 2 * E * K          # bf16 weight shadow
+              + 8 * B * L + 8 * B  # token ids, lengths
+              + sum_len * E * 4    # embedding rows gathered (the 4.8 MB table is L2 resident across steps)
+              + 4 * E * K + 4 * V * E + 4 * E)      # dW, d table, d bias written
+    flops = 2 * B * K * E * 2 + 2 * B * Bg * E * (4 if world == 1 else 6)   # head + dW; S, dI, dT (+ column block)
+    return bytes_, flops
 
 
 def ncu_traffic(label):
     """DRAM bytes per launch of that kernel from the committed `ncu --set full` capture
-    (profiles/r01_ncu_traffic.json, written by tools/ncu_traffic.py); None if not captured."""
+    (profiles/r02_ncu_traffic.json, written by tools/ncu_traffic.py); None if not captured."""
+    for name in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as fh:
+                v = json.load(fh).get(label, {}).get("traffic")
+            if v is not None:
+                return v
+        except (OSError, ValueError):
+            pass
+    return None
+
+
+def step_roofline(ms, B, world, sum_len, peaks, kernel, phases=None):
+    """roofline of the dominant kernel.  At N = 1 the whole step is ONE kernel, so its duration is the
+    CUDA-event step time itself (no separate, differently-timed measurement).  The step is classified by
+    the slower of its two ceilings."""
+    bytes_, flops = step_work(B, world, sum_len)
+    t_h = bytes_ / (peaks["hbm_gbs"] * 1e9)
+    t_t = flops / (peaks["bf16_tflops"] * 1e12)
+    sec = ms * 1e-3
+    r = dict(kernel=kernel, ms=ms, algorithmic_bytes=bytes_, algorithmic_flops=flops,
+             hbm_gb_s=bytes_ / sec / 1e9, hbm_frac=t_h / sec, tflop_s=flops / sec / 1e12, tensor_frac=t_t / sec,
+             ceiling_us=max(t_h, t_t) * 1e6, peak_source=peaks["source"], traffic=ncu_traffic(kernel))
+    if t_h >= t_t:
+        r.update(bound="hbm", achieved=r["hbm_gb_s"], peak=peaks["hbm_gbs"], unit="GB/s", frac=r["hbm_frac"])
+    else:
+        r.update(bound="tensor", achieved=r["tflop_s"], peak=peaks["bf16_tflops"], unit="TFLOP/s", frac=r["tensor_frac"])
+    if phases:
+        r["phases_us"] = phases
+    return r
+
+
+def fused_phase_timeline(m, B):
+    """in-kernel phase durations (globaltimer stamps of CTA 0, see include/cvcl_b200.h) of the last launch."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as fh:
-            return json.load(fh).get(label, {}).get("traffic")
-    except (OSError, ValueError):
+        lay = m.ops.fused_layout(B, L, E, K, V)
+        ws = m.ops._FUSED_WS.get((torch.cuda.current_device(), B, L, E, K, V))
+        if ws is None:
+            return None
+        tm = ws[lay["ctrl"] + 128:lay["ctrl"] + 256].view(torch.int64).cpu().numpy()
+        names = ["P0 head GEMM + text encoder", "P1 slab sum + normalise + token counts", "P2 similarity + row statistics",
+                 "P3 dL/dlogits + dQ partials", "P4 normalise-backward", "P5 dW + d table + final sums"]
+        out, prev = {}, tm[0]
+        for k in range(1, 6):
+            if tm[k]:
+                out[names[k - 1]] = round(float(tm[k] - prev) / 1e3, 2); prev = tm[k]
+        if tm[15]:
+            out[names[5]] = round(float(tm[15] - prev) / 1e3, 2)
+            out["kernel total"] = round(float(tm[15] - tm[0]) / 1e3, 2)
+        return out
+    except Exception:                              # noqa: BLE001
         return None
-
-
-def roofline_from(rows, peaks):
-    top = max(rows, key=lambda r: r["ms"])
-    if top["bound"] == "tensor":
-        return dict(kernel=top["kernel"], bound="tensor", achieved=top["tflop_s"], peak=peaks["bf16_tflops"],
-                    unit="TFLOP/s", frac=top["tensor_frac"], traffic=ncu_traffic(top["kernel"]),
-                    peak_source=peaks["source"], ms=top["ms"])
-    return dict(kernel=top["kernel"], bound="hbm", achieved=top["gb_s"], peak=peaks["hbm_gbs"], unit="GB/s",
-                frac=top["hbm_frac"], traffic=ncu_traffic(top["kernel"]), algorithmic_bytes=top["bytes"],
-                peak_source=peaks["source"], ms=top["ms"])
 
 
 def cpu_reference_step_fn(B):
@@ -297,8 +265,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs-per-gpu", type=int, default=512)
-    ap.add_argument("--no-breakdown", action="store_true")
-    ap.add_argument("--breakdown-out", default="")
+    ap.add_argument("--no-breakdown", action="store_true", help="(kept for old command lines; ignored)")
     a = ap.parse_args()
     if a.warmup < 3:
         a.warmup = 3
@@ -309,7 +276,9 @@ def main():
     config = {"workload": "CVCL flat-embedding contrastive train step (fwd+bwd), %d synthetic pairs per GPU, "
                           "global InfoNCE batch %d, L<=25, E=512, K=2048, V=2350" % (B, B * max(world, 1)),
               "pairs_per_gpu": B, "global_batch": B * max(world, 1), "max_len": L,
-              "parallelism": "pairs sharded over %d rank(s), NCCL feature all-gather" % world if world > 1 else "single GPU",
+              "parallelism": ("pairs sharded over %d ranks: feature / LSE exchange and gradient sum over NVLink peer "
+                              "memory (own kernels; NCCL only as the fallback)" % world) if world > 1 else
+                             "single GPU, the whole step is one persistent kernel",
               "l2": "256 MiB write between timed steps (inputs are smaller than L2)"}
 
     if a.impl == "reference":
@@ -364,6 +333,14 @@ def main():
     # ------------------------------------------------------------------ device-timed value
     fcw, fcb = model.image_embed.model.fc.weight, model.image_embed.model.fc.bias
     table = model.text_embed.embedding.weight
+    fused = world == 1 and m.ops.fused_supported(B, L, E, K, V)
+    if fused:
+        # bf16 shadow of the projection weight: cast ONCE after loading; in training the optimizer kernel
+        # (FusedAdamW / cvcl_adamw_multi_step) rewrites it together with the fp32 master, so the step itself
+        # never casts W (round 1 spent 4-5 us per step on that cast)
+        m.ops.register_weight_shadow(fcw, fcw.detach().to(torch.bfloat16).contiguous())
+    config["step_kernel"] = ("one persistent cooperative kernel (csrc/fused_step.cuh)" if fused else
+                             "multi-kernel sequence (cvcl_flat_contrastive_step / flat_step_sharded)")
     graph = None
     if world == 1:
         def raw_step():
@@ -440,6 +417,12 @@ def main():
     e2e_dt, e2e_api = eager_dt, "MultiModalModel.calculate_contrastive_loss + backward (eager)"
     try:
         gstep = m.GraphedContrastiveStep(model, x_host, ids_host, lens_host, prefetch=True, lagged_loss=True)
+        # the pinned staging buffers are double-buffered (a replay in flight may still be reading its set): stage a
+        # second, different batch in the other set so that consecutive steps copy different data
+        f2, ids2, lens2 = synth_batch(4321 + rank, B)
+        for dst, src in zip(gstep.host_sets[-1], (torch.from_numpy(f2).to(torch.bfloat16), torch.from_numpy(ids2),
+                                                  torch.from_numpy(lens2))):
+            dst.copy_(src)
         gstep.prime()
         for _ in range(6):
             gstep()
@@ -466,11 +449,17 @@ def main():
     e2e_dt, eager_dt = float(t[0].item()), float(t[1].item())
     h2d = x_host.numel() * 2 + ids_host.numel() * 8 + lens_host.numel() * 8
 
-    # ------------------------------------------------------------------ per-kernel roofline
-    rows, roof = [], None
-    if not a.no_breakdown and rank == 0:
-        rows = kernel_breakdown(m, dev, B, 50, flush, peaks)
-        roof = roofline_from(rows, peaks)
+    # ------------------------------------------------------------------ roofline of the step kernel
+    roof = None
+    if rank == 0:
+        sum_len = int(lens.sum())
+        if world == 1 and fused:
+            run_step(); torch.cuda.synchronize()
+            roof = step_roofline(ms, B, 1, sum_len, peaks, "flat_step_kernel", fused_phase_timeline(m, B))
+        else:
+            roof = step_roofline(ms, B, world, sum_len, peaks,
+                                 "sharded step (multi-kernel sequence incl. the peer-memory collectives)" if world > 1
+                                 else "flat step (multi-kernel sequence)")
     clocks = sampler.stop() if rank == 0 else None
 
     def finish():
@@ -508,18 +497,11 @@ def main():
         "e2e": {"value": B * world / e2e_dt, "unit": "pairs/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 32, "ms_per_step": e2e_dt * 1e3, "steps": e2e_steps, "api": e2e_api,
                 "eager_module_api": {"value": B * world / eager_dt, "ms_per_step": eager_dt * 1e3}},
-        "gpu_launches": int(n_launch), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "gpu_launches": int(n_launch), "gpu_launches_per_step": int(n_launch // max(a.steps, 1)),
+        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         "timing": {"ms_min": min(step_ms), "ms_median": statistics.median(step_ms),
                    "wall_s_incl_flush": t_wall, "cuda_graph": graph is not None},
     }
-    if rows:
-        out = a.breakdown_out or os.path.join(ROOT, "gpurun_out", "bench_breakdown_n%d.json" % world)
-        try:
-            os.makedirs(os.path.dirname(out), exist_ok=True)
-            with open(out, "w") as fh:
-                json.dump({"peaks": peaks, "kernels": rows, "step_ms": ms}, fh, indent=1)
-        except OSError:
-            pass
     print(json.dumps(line))
     finish()
 

@@ -683,7 +683,7 @@ const char* plan_fused(FusedPlan* f, int B, int E, int K, int V) {
     f->off_img16 = take(2ull * Bp * E);
     f->off_txt16 = take(2ull * Bp * E);
     f->off_invn = take(4ull * 2 * Bp);
-    f->off_part = take(sizeof(RowStat) * 2ull * f->nCB * Bp);
+    f->off_part = take(sizeof(RowStat) * 2ull * 2 * f->nCB * Bp);      // two half-tile partials per column block
     f->off_diag = take(4ull * 2 * Bp);
     f->off_lse = take(4ull * 2 * Bp);
     f->off_rbpart = take(4ull * 2 * f->nMB * 6);
@@ -756,7 +756,7 @@ int cvcl_flat_step_fused(const void* x16, const void* w16, const int64_t* ids, c
     p.kf16[0] = p.q16[1]; p.kf16[1] = p.q16[0]; p.ldk = E;
     for (int z = 0; z < 2; ++z) {
         p.invn[z] = reinterpret_cast<float*>(ws + f.off_invn) + z * f.Bp;
-        p.part[z] = reinterpret_cast<RowStat*>(ws + f.off_part) + static_cast<size_t>(z) * f.nCB * f.Bp;
+        p.part[z] = reinterpret_cast<RowStat*>(ws + f.off_part) + static_cast<size_t>(z) * 2 * f.nCB * f.Bp;
         p.diag[z] = reinterpret_cast<float*>(ws + f.off_diag) + z * f.Bp;
         p.lse[z] = reinterpret_cast<float*>(ws + f.off_lse) + z * f.Bp;
         p.lse_all[z] = nullptr;

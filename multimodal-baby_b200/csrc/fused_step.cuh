@@ -39,9 +39,18 @@
 namespace cvcl {
 namespace fused {
 
+// Helpers are force-inlined: every phase runs once per launch, so the kernel is one long instruction stream
+// and the sequential instruction prefetch only works on fall-through code (measured at 512 pairs: 40.4 us
+// with the helpers inlined vs 43.1 us as shared functions, although the latter is smaller).
+#ifdef CVCL_FUSED_NOINLINE
+#define CVCL_HELPER __device__ __noinline__
+#else
+#define CVCL_HELPER __device__ __forceinline__
+#endif
 constexpr int kThreads = 256;                    // warp 0 TMA, warp 1 MMA + TMEM, warps 2..5 epilogue, 6..7 auxiliary
 constexpr int kWarps = kThreads / 32;
 constexpr int kStages = 4;
+constexpr int kStages2 = 6;                       // P2 only: the Gs region is idle then and extends the ring
 constexpr int kStageBytes = 32768;               // A 128x64 bf16 + B 128x64 bf16 (or one 64 x 256 MN-major slab)
 constexpr int kRingBytes = kStages * kStageBytes;
 constexpr int kGsOff = kRingBytes;               // dL/dlogits as the A operand: up to 2 tiles x 2 k-chunks x 16 KB
@@ -137,10 +146,13 @@ __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
 }
 
 // Grid-wide barrier k (k = 0, 1, ... in program order): every CTA is resident (cooperative launch, one
-// CTA per SM), so spinning on one L2 counter cannot starve anybody.  The proxy fences order the generic
-// global writes of a phase against the TMA (async proxy) reads of the next and vice versa.
-__device__ __forceinline__ void grid_sync(const StepParams& p, int k) {
-    fence_proxy_async_all();
+// CTA per SM), so spinning on one L2 counter cannot starve anybody.  Fence + add and an acquire-spin by
+// thread 0 (measured 1.5 us; atom.add.release was slower); bar.sync makes the CTA's writes part of the release.  kWriterFence: this phase wrote global
+// memory with ordinary stores that a later phase reads through TMA (async proxy), so every thread orders its
+// stores against the async proxy first; the TMA-issuing thread fences again after the barrier.
+template <bool kWriterFence>
+CVCL_HELPER void grid_sync(const StepParams& p, int k) {
+    if (kWriterFence) fence_proxy_async_all();
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -158,11 +170,10 @@ __device__ __forceinline__ void grid_sync(const StepParams& p, int k) {
                 }
             }
         }
-        __threadfence();
+        fence_proxy_async_all();                                  // thread 0 = warp 0 lane 0 issues the TMA loads
         if (blockIdx.x == 0 && p.timing) p.timing[k + 1] = globaltimer_ns();
     }
     __syncthreads();
-    fence_proxy_async_all();
 }
 
 struct Ring {
@@ -172,13 +183,14 @@ struct Ring {
 
 // one utterance per warp: feat = normalise(sum_l table[ids[b,l]] / len[b]) in position order
 // (same arithmetic, same order as text_encoder_fwd_kernel; E <= 512)
-__device__ __forceinline__ void text_row(const StepParams& p, int b, int lane) {
+CVCL_HELPER void text_row(const StepParams& p, int b, int lane) {
     const int nch = p.E >> 7;
-    constexpr int kInFlight = 8;
+    constexpr int kInFlight = 12;          // covers half of the utterances (mean length 14) in one round trip
     float4 acc[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     const long long* idrow = p.ids + static_cast<size_t>(b) * p.L;
+    const float flen = static_cast<float>(__ldg(p.lens + b));          // fetched with the ids, used at the end
     for (int l0 = 0; l0 < p.L; l0 += 32) {
         long long my_id = (l0 + lane < p.L) ? __ldg(idrow + l0 + lane) : 0;
         if (my_id < 0 || my_id >= p.V) { if (p.status) atomicExch(p.status, 1); my_id = 0; }
@@ -205,46 +217,48 @@ __device__ __forceinline__ void text_row(const StepParams& p, int b, int lane) {
                 }
         }
     }
-    const float flen = static_cast<float>(__ldg(p.lens + b));
+    // one reciprocal per row, then multiplies (the reference divides element-wise: at most 1 ulp apart)
+    const float rlen = 1.f / flen;
     float ssq = 0.f;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        acc[c].x /= flen; acc[c].y /= flen; acc[c].z /= flen; acc[c].w /= flen;
+        acc[c].x *= rlen; acc[c].y *= rlen; acc[c].z *= rlen; acc[c].w *= rlen;
         ssq += acc[c].x * acc[c].x + acc[c].y * acc[c].y + acc[c].z * acc[c].z + acc[c].w * acc[c].w;
     }
     ssq = warp_sum(ssq);
-    const float denom = p.normalize ? fmaxf(sqrtf(ssq), 1e-12f) : 1.f;
-    if (lane == 0) p.invn[1][b] = 1.f / denom;
+    const float inv = p.normalize ? 1.f / fmaxf(sqrtf(ssq), 1e-12f) : 1.f;
+    if (lane == 0) p.invn[1][b] = inv;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         if (c < nch) {
             const int e = (c * 32 + lane) * 4;
-            const float4 t = make_float4(acc[c].x / denom, acc[c].y / denom, acc[c].z / denom, acc[c].w / denom);
+            const float4 t = make_float4(acc[c].x * inv, acc[c].y * inv, acc[c].z * inv, acc[c].w * inv);
             if (p.txt_f32) *reinterpret_cast<float4*>(p.txt_f32 + static_cast<size_t>(b) * p.E + e) = t;
             store_bf16x4(p.q16[1] + static_cast<size_t>(b) * p.ldq + e, t);
         }
     }
 }
 
-// fp32 accumulator columns [c0, c0 + ncols) of this thread's row -> swizzled staging (boxes of 32 fp32)
-__device__ __forceinline__ void stage_f32_cols(uint32_t tmem_row, int c0, int ncols, unsigned char* stage, int row) {
+// fp32 accumulator columns [tc0, tc0 + ncols) of this thread's row -> swizzled staging columns [sc0, sc0 + ncols)
+// (boxes of 32 fp32 columns, 128 rows each)
+CVCL_HELPER void stage_f32_cols(uint32_t tmem_row, int tc0, int sc0, int ncols, unsigned char* stage, int row) {
 #pragma unroll 1
     for (int c = 0; c < ncols; c += 32) {
         float v[32];
-        ptx::tmem_ld_32x32(tmem_row + c0 + c, v);
+        ptx::tmem_ld_32x32(tmem_row + tc0 + c, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             uint4 q;
             q.x = __float_as_uint(v[4 * j]); q.y = __float_as_uint(v[4 * j + 1]);
             q.z = __float_as_uint(v[4 * j + 2]); q.w = __float_as_uint(v[4 * j + 3]);
-            swz_st16(stage, row, (c + 4 * j) * 4, q);
+            swz_st16(stage, row, (sc0 + c + 4 * j) * 4, q);
         }
     }
 }
 
 // online merge of per-tile softmax partials (strict >: the first tile wins ties, as torch.argmax does);
 // the partials are fetched first (independent loads), then merged in tile order
-__device__ __forceinline__ void merge_stats(const RowStat* base, size_t stride, int n, float& gm, float& gl, float& ga,
+CVCL_HELPER void merge_stats(const RowStat* base, size_t stride, int n, float& gm, float& gl, float& ga,
                                             int& garg) {
     gm = -INFINITY; gl = 0.f; ga = 0.f; garg = 0x7fffffff;
     for (int t0 = 0; t0 < n; t0 += 8) {
@@ -266,7 +280,7 @@ __device__ __forceinline__ void merge_stats(const RowStat* base, size_t stride, 
 #define CVCL_STAMP(i) do { if (cta == 0 && p.timing) p.timing[i] = globaltimer_ns(); } while (0)
 
 __global__ void __launch_bounds__(kThreads, 1)
-flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
+flat_step_kernel(const __grid_constant__ StepMaps maps, const __grid_constant__ StepParams p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -277,6 +291,8 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
     uint64_t* gs_bar = tfull_bar + 1;                                    // Gs tiles written, S tile consumed
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gs_bar + 1);
     int* s_next = reinterpret_cast<int*>(misc + 128);                    // [kWarps] work-queue tickets
+    uint64_t* full2_bar = reinterpret_cast<uint64_t*>(misc + 160);       // [kStages2] P2 ring (ring + idle Gs region)
+    uint64_t* empty2_bar = full2_bar + kStages2;                         // [kStages2]
     float* lk = reinterpret_cast<float*>(misc + 256);                    // [256] column LSE terms (P3)
     float* red = reinterpret_cast<float*>(misc + 256 + 1024);            // [64] block reductions
     float* sdb = reinterpret_cast<float*>(misc + 2048);                  // [kWarps][512] bias partials (P4)
@@ -289,8 +305,9 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
     if (threadIdx.x == 0) {
         if (cta == 0 && p.timing) p.timing[0] = globaltimer_ns();
         for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < kStages2; ++s) { ptx::mbar_init(&full2_bar[s], 1); ptx::mbar_init(&empty2_bar[s], 1); }
         ptx::mbar_init(tfull_bar, 1);
-        ptx::mbar_init(gs_bar, kEpiThreads);
+        ptx::mbar_init(gs_bar, kThreads);
         ptx::fence_mbar_init();
         ptx::prefetch_tmap(&maps.x_k); ptx::prefetch_tmap(&maps.w_k); ptx::prefetch_tmap(&maps.hp_out);
     }
@@ -302,18 +319,22 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
 
     Ring ring{0, 0};                       // producer and MMA issuer walk the same sequence of stages
     uint32_t tfull_uses = 0;               // MMA issuer and epilogue warps count accumulator hand-overs alike
-    const bool is_epi = warp >= 2 && warp < 6;
+    // Epilogue work is shared by ALL eight warps: a warp may only touch TMEM lanes 32*(warp%4)..+31, so two
+    // warps serve each lane quadrant and split the columns of a tile in halves (warps 2..5: half 0, warps
+    // 0, 1, 6, 7: half 1; the TMA / MMA warps join once their lane 0 has issued everything).  One warp per
+    // scheduler cannot hide the TMEM / MUFU latencies of these passes (measured: 0.62 us per 32 columns).
     const int quad = warp & 3;
-    const int row = quad * 32 + lane;      // epilogue warps: accumulator row of this thread
+    const int half = (warp >= 2 && warp < 6) ? 0 : 1;
+    const int row = quad * 32 + lane;      // accumulator row of this thread
     const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    const int epi_tid = threadIdx.x - 64;
+    float* lrow = reinterpret_cast<float*>(misc + 256 + 1024 + 256);     // [128] row LSE terms shared by the halves (P3)
     const float s_log = p.log_scale_dev ? __ldg(p.log_scale_dev) : p.log_scale;
     const float scale = expf(s_log);
     constexpr float kLog2e = 1.4426950408889634f;
     int sync_k = 0;
 
     if (p.phase_limit == 100) {            // measurement: the cost of the grid barrier alone
-        for (int i = 0; i < 6; ++i) grid_sync(p, sync_k++);
+        for (int i = 0; i < 6; ++i) grid_sync<false>(p, sync_k++);
         goto done;
     }
 
@@ -364,15 +385,23 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
             for (size_t i = static_cast<size_t>(cta) * kThreads + threadIdx.x; i < n16; i += static_cast<size_t>(G) * kThreads)
                 dst[i] = make_uint4(0u, 0u, 0u, 0u);
         }
-        if (is_epi && has) {
+        // text encoder: one warp per utterance, static assignment -- slot j of CTA c owns utterance j*G + c and
+        // the slots go to the auxiliary warps first (6, 7), then to the epilogue warps (2..5), which encode
+        // theirs before the accumulator of the head tile is ready (~2 us after the loads were issued anyway)
+        if (warp >= 2) {
+            const int slot = warp >= 6 ? warp - 6 : warp;
+            for (int u = slot * G + cta; u < p.B; u += 6 * G) text_row(p, u, lane);
+            if (warp == 2 && lane == 0) CVCL_STAMP(18);
+        }
+        if (has) {                                          // all eight warps drain the head tile
             mbar_wait_b(tfull_bar, tfull_uses & 1u);
             ptx::tc_fence_after();
-            if (epi_tid == 0) CVCL_STAMP(16);
-            stage_f32_cols(tmem_row, 0, 128, smem, row);          // the ring is idle: all MMAs have retired
+            if (threadIdx.x == 64) CVCL_STAMP(16);
+            stage_f32_cols(tmem_row, 64 * half, 64 * half, 64, smem, row);   // the ring is idle: all MMAs have retired
             ptx::fence_proxy_async_smem();
             ptx::tc_fence_before();
-            ptx::named_bar_sync(1, kEpiThreads);
-            if (epi_tid == 0) {
+            __syncthreads();
+            if (threadIdx.x == 64) {
 #pragma unroll
                 for (int b4 = 0; b4 < 4; ++b4)
                     ptx::tma_store_2d(&maps.hp_out, smem + b4 * 16384, nb * 128 + b4 * 32, ks * p.Bp + mb * kBM);
@@ -381,22 +410,10 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
                 CVCL_STAMP(17);
             }
         }
-        // text encoder: utterances from a work queue (auxiliary warps at once, epilogue warps when free)
-        if (warp >= 2) {
-            for (;;) {
-                if (lane == 0) s_next[warp] = static_cast<int>(atomicAdd(p.sync + 2, 1u));
-                __syncwarp();
-                const int u = s_next[warp];
-                __syncwarp();
-                if (u >= p.B) break;
-                text_row(p, u, lane);
-            }
-            if (warp == 2 && lane == 0) CVCL_STAMP(18);
-        }
         if (has) ++tfull_uses;
     }
     // (the ring state is only ever used by lane 0 of warps 0 and 1, which walk identical sequences)
-    grid_sync(p, sync_k++);
+    grid_sync<true>(p, sync_k++);
     if (p.phase_limit == 1) goto done;
 
     // ============================================================================ P1
@@ -408,6 +425,8 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
             const float* base = p.hpart + static_cast<size_t>(r) * p.E;
+            // the token ids of the row (for the count matrix below) are fetched with the slabs
+            const long long id0 = (p.need_grads && lane < p.L) ? __ldg(p.ids + static_cast<size_t>(r) * p.L + lane) : 0;
             for (int k0 = 0; k0 < p.KS; k0 += 8) {
                 float4 v[8][4];
 #pragma unroll
@@ -435,13 +454,13 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
                 ssq += acc[c].x * acc[c].x + acc[c].y * acc[c].y + acc[c].z * acc[c].z + acc[c].w * acc[c].w;
             }
             ssq = warp_sum(ssq);
-            const float denom = p.normalize ? fmaxf(sqrtf(ssq), 1e-12f) : 1.f;
-            if (lane == 0) p.invn[0][r] = 1.f / denom;
+            const float inv = p.normalize ? 1.f / fmaxf(sqrtf(ssq), 1e-12f) : 1.f;
+            if (lane == 0) p.invn[0][r] = inv;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 if (c < nch) {
                     const int e = (c * 32 + lane) * 4;
-                    const float4 t = make_float4(acc[c].x / denom, acc[c].y / denom, acc[c].z / denom, acc[c].w / denom);
+                    const float4 t = make_float4(acc[c].x * inv, acc[c].y * inv, acc[c].z * inv, acc[c].w * inv);
                     if (p.img_f32) *reinterpret_cast<float4*>(p.img_f32 + static_cast<size_t>(r) * p.E + e) = t;
                     store_bf16x4(p.q16[0] + static_cast<size_t>(r) * p.ldq + e, t);
                 }
@@ -451,7 +470,7 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
                 __nv_bfloat16* crow = p.cmat + static_cast<size_t>(r) * p.Vp;
                 const long long* idrow = p.ids + static_cast<size_t>(r) * p.L;
                 for (int l0 = 0; l0 < p.L; l0 += 32) {
-                    const long long id = (l0 + lane < p.L) ? __ldg(idrow + l0 + lane) : 0;
+                    const long long id = l0 == 0 ? id0 : ((l0 + lane < p.L) ? __ldg(idrow + l0 + lane) : 0);
                     const bool valid = id > 0 && id < p.V;
                     const unsigned grp = __match_any_sync(0xffffffffu, valid ? static_cast<int>(id) : -1 - lane);
                     if (valid && lane == __ffs(grp) - 1) {
@@ -465,7 +484,7 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
         }
         if (threadIdx.x == 0) CVCL_STAMP(19);
     }
-    grid_sync(p, sync_k++);
+    grid_sync<true>(p, sync_k++);
     if (p.phase_limit == 2) goto done;
 
     {
@@ -483,16 +502,18 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
         const int M = p.B, N = p.Bg;
         const int m = rb * kBM + row;                       // local row of this epilogue thread
         const int dcol = m + p.diag_off;
+        // this phase runs once per launch on its own 6-deep ring: 6 of the 8 k-chunks are in flight at once
+        int st2 = 0; uint32_t ph2 = 0;
         if (warp == 0) {
             if (lane == 0 && has) {
                 for (int j = 0; j < p.T; ++j)
                     for (int kc = 0; kc < num_ke; ++kc) {
-                        mbar_wait_b(&empty_bar[ring.stage], ring.phase ^ 1u);
-                        unsigned char* sa = smem + ring.stage * kStageBytes;
-                        ptx::mbar_arrive_expect_tx(&full_bar[ring.stage], kStageBytes);
-                        ptx::tma_load_2d(sa, &maps.q_k[z], &full_bar[ring.stage], kc * kBK, rb * kBM);
-                        ptx::tma_load_2d(sa + 16384, &maps.kf_k[z], &full_bar[ring.stage], kc * kBK, (pi * p.T + j) * 128);
-                        ring.next();
+                        mbar_wait_b(&empty2_bar[st2], ph2 ^ 1u);
+                        unsigned char* sa = smem + st2 * kStageBytes;
+                        ptx::mbar_arrive_expect_tx(&full2_bar[st2], kStageBytes);
+                        ptx::tma_load_2d(sa, &maps.q_k[z], &full2_bar[st2], kc * kBK, rb * kBM);
+                        ptx::tma_load_2d(sa + 16384, &maps.kf_k[z], &full2_bar[st2], kc * kBK, (pi * p.T + j) * 128);
+                        if (++st2 == kStages2) { st2 = 0; ph2 ^= 1u; }
                     }
             }
             __syncwarp();
@@ -501,35 +522,36 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
                 constexpr uint32_t idesc = ptx::make_idesc_bf16(kBM, 128, false, false);
                 for (int j = 0; j < p.T; ++j)
                     for (int kc = 0; kc < num_ke; ++kc) {
-                        mbar_wait_b(&full_bar[ring.stage], ring.phase);
+                        mbar_wait_b(&full2_bar[st2], ph2);
                         ptx::tc_fence_after();
-                        const uint32_t sa = ptx::smem_u32(smem + ring.stage * kStageBytes);
+                        const uint32_t sa = ptx::smem_u32(smem + st2 * kStageBytes);
                         const uint64_t adesc = ptx::make_kmajor_sw128_desc(sa);
                         const uint64_t bdesc = ptx::make_kmajor_sw128_desc(sa + 16384);
 #pragma unroll
                         for (int k = 0; k < kBK / kUmmaK; ++k)
                             ptx::umma_bf16(tmem_base + 128 * j, adesc + 2 * k, bdesc + 2 * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);
-                        ptx::umma_commit(&empty_bar[ring.stage]);
+                        ptx::umma_commit(&empty2_bar[st2]);
                         if (j == p.T - 1 && kc == num_ke - 1) ptx::umma_commit(tfull_bar);
-                        ring.next();
+                        if (++st2 == kStages2) { st2 = 0; ph2 ^= 1u; }
                     }
             }
             __syncwarp();
         }
-        if (has && is_epi) {
+        if (has) {
             mbar_wait_b(tfull_bar, tfull_uses & 1u);
             ptx::tc_fence_after();
-            if (epi_tid == 0) CVCL_STAMP(20);
+            if (threadIdx.x == 64) CVCL_STAMP(20);
             if (qs == 0) {                                  // the statistics are written once per tile
+                // raw-domain online softmax (see EpiSimStats); each thread owns 64 columns of its row, so a
+                // 128-column tile contributes two partials per row: index (column block)*2 + half
                 const float sc2 = scale * kLog2e;
                 for (int j = 0; j < p.T; ++j) {
-                    // raw-domain online softmax over this tile's 128 columns (see EpiSimStats)
-                    const int n0 = (pi * p.T + j) * 128;
+                    const int n0 = (pi * p.T + j) * 128 + 64 * half;
                     float mx = -INFINITY, l = 0.f, a = 0.f; int arg = n0;
 #pragma unroll 1
-                    for (int c = 0; c < 128; c += 32) {
+                    for (int c = 0; c < 64; c += 32) {
                         float v[32];
-                        ptx::tmem_ld_32x32(tmem_row + 128 * j + c, v);
+                        ptx::tmem_ld_32x32(tmem_row + 128 * j + 64 * half + c, v);
                         const int n = n0 + c;
                         if (n >= N) continue;                               // warp-uniform
                         const bool full = n + 32 <= N;
@@ -566,77 +588,103 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
                     }
                     if (m < M) {
                         RowStat rs; rs.m = mx * scale; rs.l = l; rs.a = a * scale; rs.arg = arg;
-                        p.part[z][static_cast<size_t>(pi * p.T + j) * p.Bp + m] = rs;
+                        p.part[z][static_cast<size_t>((pi * p.T + j) * 2 + half) * p.Bp + m] = rs;
                     }
                 }
             }
             ptx::tc_fence_before();
-            if (epi_tid == 0) CVCL_STAMP(21);
+            if (threadIdx.x == 64) CVCL_STAMP(21);
         }
         if (has) ++tfull_uses;
-        grid_sync(p, sync_k++);
+        grid_sync<false>(p, sync_k++);
         if (p.phase_limit == 3) goto done;
 
         // ======================================================================== P3
         const int wq = p.E / p.QS;                          // dQ columns of this CTA: [qs*wq, qs*wq + wq)
-        if (has && is_epi) {
-            // (a) row statistics of this row block: LSE, cross-entropy / entropy / accuracy terms
-            float gm, gl, ga; int garg;
-            float lse_row = 0.f;
-            float v6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const int nH = (wq + 255) / 256;
+        const int num_kc3 = 2 * p.T;
+        if (has && p.need_grads && warp == 0 && lane == 0) {
+            // the key-feature slabs of the dQ GEMM do not depend on anything computed in this phase: fetch now
+            for (int kc = 0; kc < num_kc3; ++kc)
+                for (int h = 0; h < nH; ++h) {
+                    const int nh = min(256, wq - 256 * h);
+                    mbar_wait_b(&empty_bar[ring.stage], ring.phase ^ 1u);
+                    unsigned char* sb = smem + ring.stage * kStageBytes;
+                    ptx::mbar_arrive_expect_tx(&full_bar[ring.stage], static_cast<uint32_t>(nh) * 128);
+                    const int crow = (pi * p.T + (kc >> 1)) * 128 + (kc & 1) * 64;
+                    for (int jb = 0; jb < nh / 64; ++jb)
+                        ptx::tma_load_2d(sb + jb * 8192, &maps.kf_mn[z], &full_bar[ring.stage],
+                                         qs * wq + 256 * h + 64 * jb, crow);
+                    ring.next();
+                }
+        }
+        __syncwarp();
+        if (has) {
+            // (a) half 0: the LSE of this thread's ROW (+ cross-entropy / entropy / accuracy terms on the lead
+            //     CTA); half 1: the LSE of COLUMN `row` of the tile = a row of the other direction (one GPU:
+            //     merged here from its partials; sharded: gathered beforehand into lse_all).  Both halves run
+            //     at the same time on different warps: one round trip to L2 instead of three.
             const bool lead = pi == 0 && qs == 0;
-            if (m < M) {
-                merge_stats(p.part[z] + m, p.Bp, p.nCB, gm, gl, ga, garg);
-                lse_row = gm + logf(gl);
-                if (lead) {
-                    p.lse[z][m] = lse_row;
-                    v6[z] = lse_row - __ldcg(p.diag[z] + m);
-                    v6[2 + z] = lse_row - ga / gl;
-                    v6[4 + z] = (garg == dcol) ? 1.f : 0.f;
+            const float w = scale * (0.5f * p.inv_rows);             // exp(s) * coef
+            const float l2w = log2f(w);
+            float v6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (half == 0) {
+                float lse_row = 0.f;
+                if (m < M) {
+                    float gm, gl, ga; int garg;
+                    const float dg = lead ? __ldcg(p.diag[z] + m) : 0.f;
+                    merge_stats(p.part[z] + m, p.Bp, 2 * p.nCB, gm, gl, ga, garg);
+                    lse_row = gm + logf(gl);
+                    if (lead) {
+                        p.lse[z][m] = lse_row;
+                        v6[z] = lse_row - dg;
+                        v6[2 + z] = lse_row - ga / gl;
+                        v6[4 + z] = (garg == dcol) ? 1.f : 0.f;
+                    }
                 }
-            }
-            if (lead) {                                      // fixed-order block sum -> rb_part
-#pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                    const float s = warp_sum(v6[i]);
-                    if (lane == 0) red[(warp - 2) * 6 + i] = s;
-                }
-                ptx::named_bar_sync(1, kEpiThreads);
-                if (epi_tid < 6)
-                    p.rb_part[(z * p.nMB + rb) * 6 + epi_tid] =
-                        red[epi_tid] + red[6 + epi_tid] + red[12 + epi_tid] + red[18 + epi_tid];
-            }
-            if (p.need_grads) {
-                // (b) column terms: LSE of the OTHER direction's rows (one GPU: merged here from its partials;
-                //     sharded: gathered beforehand into lse_all)
-                const float w = scale * (0.5f * p.inv_rows);             // exp(s) * coef
-                const float l2w = log2f(w);
-                for (int c = epi_tid; c < 128 * p.T; c += kEpiThreads) {
-                    const int n = (pi * p.T) * 128 + c;
+                lrow[row] = (m < M) ? lse_row * kLog2e - l2w : INFINITY;     // dead rows -> 0
+            } else if (p.need_grads) {
+                for (int j = 0; j < p.T; ++j) {
+                    const int n = (pi * p.T + j) * 128 + row;
                     float lkv = INFINITY;
                     if (n < N) {
                         float lse_c;
                         if (p.lse_all[1 - z]) lse_c = __ldcg(p.lse_all[1 - z] + n);
                         else {
                             float cm_, cl_, ca_; int carg_;
-                            merge_stats(p.part[1 - z] + n, p.Bp, p.nCB, cm_, cl_, ca_, carg_);
+                            merge_stats(p.part[1 - z] + n, p.Bp, 2 * p.nCB, cm_, cl_, ca_, carg_);
                             lse_c = cm_ + logf(cl_);
                         }
                         lkv = lse_c * kLog2e - l2w;
                     }
-                    lk[c] = lkv;
+                    lk[128 * j + row] = lkv;
                 }
-                ptx::named_bar_sync(1, kEpiThreads);
-                if (epi_tid == 0) CVCL_STAMP(22);
-                // (c) Gs = w * (softmax_row + softmax_col) from the tile still in TMEM -> bf16 A operand
-                const float lq = (m < M) ? lse_row * kLog2e - l2w : INFINITY;
+            }
+            if (lead) {                                      // fixed-order block sum -> rb_part (half 0 warps: 2..5)
+                if (half == 0) {
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) {
+                        const float sv = warp_sum(v6[i]);
+                        if (lane == 0) red[(warp - 2) * 6 + i] = sv;
+                    }
+                }
+            }
+            __syncthreads();
+            if (lead && threadIdx.x < 6)
+                p.rb_part[(z * p.nMB + rb) * 6 + threadIdx.x] =
+                    red[threadIdx.x] + red[6 + threadIdx.x] + red[12 + threadIdx.x] + red[18 + threadIdx.x];
+            if (threadIdx.x == 64) CVCL_STAMP(22);
+            if (p.need_grads) {
+                // (c) Gs = w * (softmax_row + softmax_col) from the tile still in TMEM -> bf16 A operand; this
+                //     thread's 64 columns are exactly k-chunk `half` of the operand
+                const float lq = lrow[row];
                 const float sc2 = scale * kLog2e;
                 float ds = 0.f;
                 for (int j = 0; j < p.T; ++j) {
                     unsigned char* gs_tile = smem + kGsOff + j * 32768;
                     const int n0 = (pi * p.T + j) * 128;
 #pragma unroll 1
-                    for (int c = 0; c < 128; c += 32) {
+                    for (int c = 64 * half; c < 64 * half + 64; c += 32) {
                         float v[32];
                         ptx::tmem_ld_32x32(tmem_row + 128 * j + c, v);
                         const int n = n0 + c;
@@ -666,36 +714,12 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
                 ptx::fence_proxy_async_smem();              // generic smem writes -> tcgen05 (async proxy) reads
                 ptx::tc_fence_before();                     // the S tile has been read: its columns may be overwritten
                 ptx::mbar_arrive(gs_bar);
-                if (epi_tid == 0) CVCL_STAMP(23);
+                if (threadIdx.x == 64) CVCL_STAMP(23);
                 if (z == 0 && qs == 0) {                    // dL/ds partial of this tile (direction 0 only)
                     ds = warp_sum(ds);
-                    if (lane == 0) red[32 + (warp - 2)] = ds;
-                    ptx::named_bar_sync(1, kEpiThreads);
-                    if (epi_tid == 0) p.dspart[rb * p.nPart + pi] = (red[32] + red[33]) + (red[34] + red[35]);
+                    if (lane == 0) red[32 + warp] = ds;
                 }
-            }
-        }
-        if (has && p.need_grads) {
-            const int nH = (wq + 255) / 256;
-            const int num_kc3 = 2 * p.T;
-            if (warp == 0) {
-                if (lane == 0) {
-                    for (int kc = 0; kc < num_kc3; ++kc)
-                        for (int h = 0; h < nH; ++h) {
-                            const int nh = min(256, wq - 256 * h);
-                            mbar_wait_b(&empty_bar[ring.stage], ring.phase ^ 1u);
-                            unsigned char* sb = smem + ring.stage * kStageBytes;
-                            ptx::mbar_arrive_expect_tx(&full_bar[ring.stage], static_cast<uint32_t>(nh) * 128);
-                            const int crow = (pi * p.T + (kc >> 1)) * 128 + (kc & 1) * 64;
-                            for (int jb = 0; jb < nh / 64; ++jb)
-                                ptx::tma_load_2d(sb + jb * 8192, &maps.kf_mn[z], &full_bar[ring.stage],
-                                                 qs * wq + 256 * h + 64 * jb, crow);
-                            ring.next();
-                        }
-                }
-                __syncwarp();
-            } else if (warp == 1) {
-                if (lane == 0) {
+                if (warp == 1 && lane == 0) {
                     mbar_wait_b(gs_bar, 0);                 // single use per launch
                     ptx::tc_fence_after();
                     for (int kc = 0; kc < num_kc3; ++kc)
@@ -718,32 +742,39 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
                         }
                 }
                 __syncwarp();
-            } else if (is_epi) {
-                // dQ partial [128, wq] -> slab (z, pi), columns qs*wq..: 128 columns per pass, two staging halves
+                // dQ partial [128, wq] -> slab (z, pi), columns qs*wq..: 128 columns per pass (64 per thread),
+                // two staging halves
                 mbar_wait_b(tfull_bar, tfull_uses & 1u);
                 ptx::tc_fence_after();
-                if (epi_tid == 0) CVCL_STAMP(24);
+                if (threadIdx.x == 64) {
+                    CVCL_STAMP(24);
+                    if (z == 0 && qs == 0) {                // warps in fixed order
+                        float dsum = 0.f;
+                        for (int wv = 0; wv < kWarps; ++wv) dsum += red[32 + wv];
+                        p.dspart[rb * p.nPart + pi] = dsum;
+                    }
+                }
                 const int out_row = ((z * p.nPart + pi) * p.Bp) + rb * kBM;
                 for (int q = 0; q < wq / 128; ++q) {
                     unsigned char* stg = smem + (q & 1) * 65536;
-                    if (q >= 2) { if (epi_tid == 0) tma_store_wait_read<1>(); ptx::named_bar_sync(1, kEpiThreads); }
-                    stage_f32_cols(tmem_row, 128 * q, 128, stg, row);
+                    if (q >= 2) { if (threadIdx.x == 64) tma_store_wait_read<1>(); __syncthreads(); }
+                    stage_f32_cols(tmem_row, 128 * q + 64 * half, 64 * half, 64, stg, row);
                     ptx::fence_proxy_async_smem();
-                    ptx::named_bar_sync(1, kEpiThreads);
-                    if (epi_tid == 0) {
+                    __syncthreads();
+                    if (threadIdx.x == 64) {
 #pragma unroll
                         for (int b4 = 0; b4 < 4; ++b4)
                             ptx::tma_store_2d(&maps.dq_out, stg + b4 * 16384, qs * wq + 128 * q + b4 * 32, out_row);
                         tma_store_commit();
                     }
                 }
-                if (epi_tid == 0) { tma_store_wait_all(); CVCL_STAMP(25); }
+                if (threadIdx.x == 64) { tma_store_wait_all(); CVCL_STAMP(25); }
                 ptx::tc_fence_before();
+                ++tfull_uses;
             }
-            ++tfull_uses;
         }
     }
-    grid_sync(p, sync_k++);
+    grid_sync<false>(p, sync_k++);
     if (p.phase_limit == 4) goto done;
 
     if (p.need_grads) {
@@ -835,7 +866,7 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
         }
         if (threadIdx.x == 0) CVCL_STAMP(26);
     }
-    if (p.need_grads) grid_sync(p, sync_k++);
+    if (p.need_grads) grid_sync<true>(p, sync_k++);
     if (p.phase_limit == 5) goto done;
 
     if (p.need_grads) {
@@ -887,15 +918,17 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const StepParams p) {
                     }
                 }
                 __syncwarp();
-            } else if (is_epi) {
+            }
+            {
+                // all eight warps drain the tile (each thread: its row, half of the columns)
                 mbar_wait_b(tfull_bar, tfull_uses & 1u);
                 ptx::tc_fence_after();
-                if (epi_tid == 0) CVCL_STAMP(27);
-                stage_f32_cols(tmem_row, 0, tn, smem, row);
+                if (threadIdx.x == 64) CVCL_STAMP(27);
+                stage_f32_cols(tmem_row, (tn / 2) * half, (tn / 2) * half, tn / 2, smem, row);
                 ptx::fence_proxy_async_smem();
                 ptx::tc_fence_before();
-                ptx::named_bar_sync(1, kEpiThreads);
-                if (epi_tid == 0) {
+                __syncthreads();
+                if (threadIdx.x == 64) {
                     if (is_dw) {
                         for (int b4 = 0; b4 < tn / 32; ++b4)
                             ptx::tma_store_2d(&maps.dw_out, smem + b4 * 16384, ot * bn + b4 * 32, eb * 128);

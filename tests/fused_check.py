@@ -119,7 +119,7 @@ def run(B, E, K, V=2350, L=25, normalize=True, need_grads=True, verbose=True):
     invn = blk("invn", 4 * 2 * Bp, torch.float32).view(2, Bp)[:, :B]
     rep["P1 invn_i"] = relerr(invn[0], ref["invn_i"]); rep["P0 invn_t"] = relerr(invn[1], ref["invn_t"])
     launch(3)
-    part = blk("part", 16 * 2 * nCB * Bp, torch.float32).view(2, nCB, Bp, 4)[:, :, :B]
+    part = blk("part", 16 * 2 * 2 * nCB * Bp, torch.float32).view(2, 2 * nCB, Bp, 4)[:, :, :B]
     mx = part[..., 0]; l = part[..., 1]
     gm = mx.max(1).values
     lse = gm + torch.log((l * torch.exp(mx - gm[:, None])).sum(1))
@@ -157,7 +157,7 @@ def run(B, E, K, V=2350, L=25, normalize=True, need_grads=True, verbose=True):
     rep["replay: out5 bit-identical"] = bool(torch.equal(o1[:5], out5[:5]))
     if need_grads:
         rep["replay: all gradients bit-identical"] = bool(torch.equal(g1[0:1], flat[0:1]) and torch.equal(g1[4:], flat[4:]))
-    tm = ws[lay["ctrl"] + 128:lay["ctrl"] + 512].view(torch.int64).cpu().numpy()
+    tm = ws[lay["ctrl"] + 128:lay["ctrl"] + 640].view(torch.int64).cpu().numpy()
     names = ["start", "P0 head+text", "P1 normalise", "P2 similarity", "P3 Gs+dQ", "P4 finish"]
     line = []
     for k in range(1, 6):
@@ -174,10 +174,10 @@ def run(B, E, K, V=2350, L=25, normalize=True, need_grads=True, verbose=True):
             28: ("P5 tile stored", 5)}
     rep["in-phase stamps (us after the phase began)"] = "; ".join(
         "%s +%.2f" % (nm, (tm[i] - tm[ph]) / 1e3) for i, (nm, ph) in fine.items() if tm[i] and tm[ph])
-    rep["control block after run"] = ws[:8].view(torch.int32).cpu().tolist()
-    ws[lay["ctrl"] + 128:lay["ctrl"] + 512].zero_()
+    rep["control block after run"] = ws[:16].view(torch.int32).cpu().tolist()
+    ws[lay["ctrl"] + 128:lay["ctrl"] + 640].zero_()
     launch(100)
-    tb = ws[lay["ctrl"] + 128:lay["ctrl"] + 512].view(torch.int64).cpu().numpy()
+    tb = ws[lay["ctrl"] + 128:lay["ctrl"] + 640].view(torch.int64).cpu().numpy()
     rep["grid barrier alone (us each, 6 in a row)"] = " ".join("%.2f" % ((tb[k + 1] - tb[k]) / 1e3) for k in range(1, 6))
     if verbose:
         for k, v in rep.items():

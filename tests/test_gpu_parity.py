@@ -492,10 +492,75 @@ def test_graphed_step_lagged_loss(cv):
     step.prime()                                        # batch 0 on the device
     got = []
     for k in (1, 2, 2):                                 # replay j computes batch j (copied during replay j-1)
-        xh.copy_(t(inps[k]["f"])); ih.copy_(t(inps[k]["ids"])); lh.copy_(t(inps[k]["lens"]))
+        # the pinned staging buffers are double-buffered in lagged mode: step.x_host / ids_host / lens_host name
+        # the set the NEXT call copies, which no replay in flight reads -- no synchronize needed here
+        step.x_host.copy_(t(inps[k]["f"])); step.ids_host.copy_(t(inps[k]["ids"])); step.lens_host.copy_(t(inps[k]["lens"]))
         got.append(step())
-        torch.cuda.synchronize()                        # the staged batch must not change while it is copied
+        step.x_host.fill_(float("nan"))                 # scribbling on the OTHER set cannot disturb the replay in flight
     got.append(step.flush())
     assert got[0] != got[0]                             # NaN: nothing had finished at the first call
     for a, b in zip(got[1:], ref):
         assert abs(a - b) <= 1e-6 * abs(b), (got, ref)
+
+
+def _flat_model(cv, inp, E=512, fix_temperature=True):
+    import argparse
+    args = argparse.Namespace(embedding_type="flat", embedding_dim=E, normalize_features=True,
+                              fix_temperature=fix_temperature, temperature=0.07, text_encoder="embedding")
+    vocab = {str(i): i for i in range(2350)}
+    m = cv.MultiModalModel(cv.VisionEncoder(args, trunk="pooled"), cv.TextEncoder(vocab, 2048, args), args)
+    with torch.no_grad():
+        m.image_embed.model.fc.weight.copy_(t(inp["W"])); m.image_embed.model.fc.bias.copy_(t(inp["b"]))
+        m.text_embed.embedding.weight.copy_(t(inp["table"]))
+    m.to(DEV).train()
+    m.materialize_logits = m.materialize_text_outputs = m.materialize_features = False
+    return m
+
+
+def _head_params(mm):
+    return [mm.image_embed.model.fc.weight, mm.image_embed.model.fc.bias, mm.text_embed.embedding.weight]
+
+
+def test_graphed_train_step_with_optimizer_in_graph(cv):
+    """GraphedContrastiveStep(optimizer=FusedAdamW): forward + backward + AdamW + bf16 weight shadow refresh as ONE
+    graph == the eager loop (calculate_contrastive_loss, backward, torch.optim.AdamW) on the same batches."""
+    inps = [case_inputs(700 + k, 256, 512, "flat") for k in range(4)]
+    ref_m = _flat_model(cv, inps[0]); got_m = _flat_model(cv, inps[0])
+    ref_opt = torch.optim.AdamW(_head_params(ref_m), lr=1e-3, weight_decay=0.1)
+    ref_losses = []
+    for i in inps:
+        ref_opt.zero_grad(set_to_none=True)
+        loss = ref_m.calculate_contrastive_loss(t(i["f"], DEV), t(i["ids"], DEV), t(i["lens"], DEV))[0]
+        loss.backward(); ref_opt.step(); ref_losses.append(loss.item())
+    opt = cv.FusedAdamW(_head_params(got_m), lr=1e-3, weight_decay=0.1)
+    xh = t(inps[0]["f"]).pin_memory(); ih = t(inps[0]["ids"]).pin_memory(); lh = t(inps[0]["lens"]).pin_memory()
+    step = cv.GraphedContrastiveStep(got_m, xh, ih, lh, optimizer=opt)
+    got_losses = []
+    for i in inps:
+        step.x_host.copy_(t(i["f"])); step.ids_host.copy_(t(i["ids"])); step.lens_host.copy_(t(i["lens"]))
+        got_losses.append(step())
+    assert opt.device_step_count() == len(inps)
+    for a, b in zip(got_losses, ref_losses):            # later losses depend on the earlier updates
+        assert abs(a - b) <= 2e-3 * abs(b), (got_losses, ref_losses)
+    for pa, pb in zip(_head_params(got_m), _head_params(ref_m)):
+        assert float((pa - pb).abs().max()) <= 2e-3 * max(1.0, float(pb.abs().max()))
+    # the shadow the head GEMM reads is the bf16 image of the updated master weight
+    w = got_m.image_embed.model.fc.weight
+    assert torch.equal(cv.ops.weight_shadow(w), w.detach().to(torch.bfloat16))
+
+
+def test_graphed_step_trainable_temperature(cv):
+    """fix_temperature=False (the reference default, multimodal.py:711-715): s lives on the device, the graph
+    reads it every replay and writes ds into s.grad -- no host sync, no rebuild when s changes."""
+    inp = case_inputs(810, 256, 512, "flat")
+    m = _flat_model(cv, inp, fix_temperature=False)
+    xh = t(inp["f"]).pin_memory(); ih = t(inp["ids"]).pin_memory(); lh = t(inp["lens"]).pin_memory()
+    step = cv.GraphedContrastiveStep(m, xh, ih, lh)
+    for sval in (S_DEFAULT, 2.0):
+        with torch.no_grad():
+            m.logit_neg_log_temperature.fill_(sval)
+        loss = step()
+        ref = oracle_flat_step(inp, s=sval)
+        assert abs(loss - ref["loss"].item()) <= 1e-3 * abs(ref["loss"].item())
+        ds = m.logit_neg_log_temperature.grad.item()
+        assert abs(ds - ref["ds"].item()) <= 2e-2 * abs(ref["ds"].item()) + 1e-3
