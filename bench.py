@@ -225,6 +225,161 @@ def fused_phase_timeline(m, B):
         return None
 
 
+def _event_time(fn, reps, warm, flush):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        if flush is not None:
+            flush.zero_()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return statistics.mean(ts), min(ts)
+
+
+def config3_object(m, dev, peaks, flush, world, rank, group, B3=32768):
+    """BASELINE configs[2]: global-batch contrastive loss over 32 768 pairs, fwd + bwd at the feature level
+    (d img, d txt, d s).  N = 1: the whole batch on one GPU.  N > 1: rank r owns B3/N pairs, the features are
+    all-gathered and every rank evaluates its row block and column block; max over ranks."""
+    b = B3 // world
+    g = torch.Generator().manual_seed(77 + rank)
+    img = torch.nn.functional.normalize(torch.randn(b, E, generator=g), dim=1).to(dev)
+    txt = torch.nn.functional.normalize(torch.randn(b, E, generator=g), dim=1).to(dev)
+
+    def step():
+        i = img.detach().requires_grad_(True); t = txt.detach().requires_grad_(True)
+        out = m.ops.sim_infonce(i, t, S_FIXED, group)
+        out[0].backward()
+    ms, mn = _event_time(step, 5, 2, flush)
+    tt = torch.tensor([ms], device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item())
+    flops_alg = 8.0 * B3 * B3 * E                       # one S for both directions + recompute + dI + dT
+    flops_exec_rank = (10.0 if world == 1 else 12.0) * b * B3 * E
+    sec = ms * 1e-3
+    return {"workload": "global-batch InfoNCE, %d pairs, features in, fwd+bwd (d img, d txt, d s)" % B3,
+            "pairs_per_gpu": b, "ms": ms, "pairs_per_s": B3 / sec,
+            "algorithmic_flops": flops_alg, "tflop_s_algorithmic": flops_alg / sec / 1e12,
+            "tensor_frac_per_gpu": flops_alg / world / sec / 1e12 / peaks["bf16_tflops_sustained"],
+            "executed_flops_per_gpu": flops_exec_rank,
+            "tensor_frac_executed_per_gpu": flops_exec_rank / sec / 1e12 / peaks["bf16_tflops_sustained"],
+            "peak": "bf16_tflops_sustained (%s)" % peaks["source"],
+            "exchange": "NCCL all-gather of the bf16 features + LSEs (feature-level op)" if world > 1 else None}
+
+
+def secondary_configs(m, dev, peaks, flush):
+    """BASELINE configs 1, 4, 5 on one GPU, bounded to a few seconds each (config 3: config3_object)."""
+    out = {}
+    # ---- config 1: full model (ResNeXt-50 trunk as the stock torch module + this library's head), B = 8, 224^2
+    try:
+        args = argparse.Namespace(embedding_type="flat", embedding_dim=E, normalize_features=True,
+                                  fix_temperature=True, temperature=0.07, text_encoder="embedding",
+                                  cnn_model="resnext50_32x4d", finetune_cnn=False)
+        vocab = {str(i): i for i in range(V)}
+        torch.manual_seed(0)
+        model = m.MultiModalModel(m.VisionEncoder(args, trunk="resnext"), m.TextEncoder(vocab, K, args), args)
+        model.materialize_logits = model.materialize_text_outputs = model.materialize_features = False
+        B1 = 8
+        from oracle import cvcl_oracle as O
+        ids, lens = O.synth_tokens(np.random.RandomState(3), B1, L, V)
+        imgs_h = torch.rand(B1, 3, 224, 224).pin_memory()
+        ids_h = torch.from_numpy(ids).pin_memory(); lens_h = torch.from_numpy(lens).pin_memory()
+        # CPU baseline first (the same modules on the host cores: torch trunk + the oracle's op sequence for the head)
+        model.train()
+        torch.set_num_threads(os.cpu_count() or 1)
+        fc = model.image_embed.model.fc
+        tab = model.text_embed.embedding.weight
+
+        def cpu_step():
+            with torch.no_grad():
+                pooled, _ = m.split_trunk_forward(model.image_embed, imgs_h, run_head=False)
+            return O.contrastive_step(pooled, ids_h, lens_h, fc.weight.detach().clone(), fc.bias.detach().clone(),
+                                      tab.detach().clone(), S_FIXED)["loss"]
+        cpu_step()
+        t0 = time.perf_counter(); n_cpu = 3
+        for _ in range(n_cpu):
+            cpu_loss = float(cpu_step())
+        cpu_dt = (time.perf_counter() - t0) / n_cpu
+        model.to(dev)
+        x_d = torch.empty_like(imgs_h, device=dev); i_d = ids_h.to(dev); l_d = lens_h.to(dev)
+
+        def gpu_step():
+            x_d.copy_(imgs_h, non_blocking=True); i_d.copy_(ids_h, non_blocking=True); l_d.copy_(lens_h, non_blocking=True)
+            for prm in model.parameters():
+                prm.grad = None
+            o = model.calculate_contrastive_loss(x_d, i_d, l_d)
+            o[0].backward()
+            return o[0].item()
+        for _ in range(3):
+            gpu_loss = gpu_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter(); n_gpu = 20
+        for _ in range(n_gpu):
+            gpu_loss = gpu_step()
+        torch.cuda.synchronize()
+        gpu_dt = (time.perf_counter() - t0) / n_gpu
+        out["config1"] = {"workload": "full CVCL model, random init, B=8, 224x224: ResNeXt-50 trunk (stock torch module, frozen) "
+                                      "+ contrastive head fwd+bwd; e2e with H2D of the images and D2H of the loss",
+                          "gpu_ms": gpu_dt * 1e3, "gpu_pairs_per_s": B1 / gpu_dt, "gpu_loss": gpu_loss,
+                          "cpu_ms": cpu_dt * 1e3, "cpu_pairs_per_s": B1 / cpu_dt, "cpu_loss": cpu_loss,
+                          "cpu_cores": os.cpu_count(), "cpu_kind": "port (torch trunk + oracle head on the host cores)",
+                          "loss_rel_diff": abs(gpu_loss - cpu_loss) / max(abs(cpu_loss), 1e-9),
+                          "h2d_bytes_per_step": imgs_h.numel() * 4 + ids_h.numel() * 8 + lens_h.numel() * 8}
+        del model
+    except Exception as exc:                               # noqa: BLE001
+        out["config1"] = {"error": repr(exc)[:300]}
+    # ---- config 4: spatial 7x7 embeddings, max and mean, B = 1024, fwd+bwd from projected features
+    try:
+        from oracle import cvcl_oracle as O
+        B4, HW = 1024, 49
+        rng = np.random.RandomState(4)
+        ids, lens = O.synth_tokens(rng, B4, L, V)
+        table = O.synth_weights(rng, E, 8, V)[2]
+        ids_d = torch.from_numpy(ids).to(dev); lens_d = torch.from_numpy(lens).to(dev); table_d = torch.from_numpy(table).to(dev)
+        g = torch.Generator().manual_seed(4)
+        imgs = torch.nn.functional.normalize(torch.randn(B4, HW, E, generator=g), dim=-1).to(dev)
+
+        def sp(sim):
+            def fn():
+                i = imgs.detach().requires_grad_(True); tab = table_d.detach().requires_grad_(True)
+                if sim == "max":
+                    tok, _ = m.ops.text_features_spatial(ids_d, lens_d, tab, True)
+                    loss = m.ops.infonce_from_match(m.ops.spatial_max_similarity(i, tok, lens_d, ids_d), S_FIXED)[0]
+                else:
+                    _, tp = m.ops.text_features_spatial(ids_d, lens_d, tab, True, 1.0 / HW, want_tok=False)
+                    loss = m.ops.sim_infonce(m.ops.spatial_pool(i), tp, S_FIXED)[0]
+                loss.backward()
+            return fn
+        ms, _ = _event_time(sp("max"), 5, 2, flush)
+        fl = 2.0 * B4 * B4 * HW * L * E + 4.0 * B4 * B4 * L * E
+        out["config4_max"] = {"workload": "spatial 7x7, sim=max, B=1024, fwd+bwd", "ms": ms, "pairs_per_s": B4 / (ms * 1e-3),
+                              "algorithmic_flops": fl, "tensor_frac": fl / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"]}
+        ms, _ = _event_time(sp("mean"), 10, 3, flush)
+        by = 2.0 * (B4 * HW * E + B4 * L * E) * 4
+        out["config4_mean"] = {"workload": "spatial 7x7, sim=mean, B=1024, fwd+bwd", "ms": ms, "pairs_per_s": B4 / (ms * 1e-3),
+                               "algorithmic_bytes": by, "hbm_frac": by / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+    except Exception as exc:                               # noqa: BLE001
+        out["config4"] = {"error": repr(exc)[:300]}
+    # ---- config 5: Labeled-S style 4-way eval, 100k frames, 22 categories, fp32
+    try:
+        N5, C5 = 25000, 22
+        g = torch.Generator().manual_seed(5)
+        frames = torch.randn(N5 * 4, E, generator=g).to(dev); cats = torch.randn(C5, E, generator=g).to(dev)
+        idx = torch.randint(0, C5, (N5,), generator=g).to(torch.int32).to(dev)
+        ms, mn = _event_time(lambda: m.ops.eval_nway(frames, cats, idx, 4, True, S_FIXED, False), 20, 3, flush)
+        by = N5 * 4 * E * 4.0
+        out["config5"] = {"workload": "4-way eval, 100 000 frames, 22 categories, fp32 -> predictions", "ms": ms, "ms_min": mn,
+                          "frames_per_s": N5 * 4 / (ms * 1e-3), "algorithmic_bytes": by,
+                          "hbm_frac": by / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+    except Exception as exc:                               # noqa: BLE001
+        out["config5"] = {"error": repr(exc)[:300]}
+    return out
+
+
 def cpu_reference_step_fn(B):
     """the oracle port: same ATen fp32 op sequence as the reference's calculate_contrastive_loss +
     backward, on trunk-boundary features, all host threads."""
@@ -266,6 +421,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs-per-gpu", type=int, default=512)
     ap.add_argument("--no-breakdown", action="store_true", help="(kept for old command lines; ignored)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the bounded runs of BASELINE configs 1, 3, 4, 5")
     a = ap.parse_args()
     if a.warmup < 3:
         a.warmup = 3
@@ -461,6 +617,15 @@ def main():
                                  "sharded step (multi-kernel sequence incl. the peer-memory collectives)" if world > 1
                                  else "flat step (multi-kernel sequence)")
     clocks = sampler.stop() if rank == 0 else None
+    # ------------------------------------------------------------------ the other BASELINE configurations (bounded)
+    configs = None
+    if not a.no_configs:
+        try:
+            configs = {"config3": config3_object(m, dev, peaks, flush, world, rank, group)}    # every rank takes part
+        except Exception as exc:                           # noqa: BLE001
+            configs = {"config3": {"error": repr(exc)[:300]}}
+        if rank == 0 and world == 1:
+            configs.update(secondary_configs(m, dev, peaks, flush))
 
     def finish():
         # leave without tearing the communicator down: destroying an NCCL process group while a
@@ -498,7 +663,7 @@ def main():
                 "d2h_bytes_per_step": 32, "ms_per_step": e2e_dt * 1e3, "steps": e2e_steps, "api": e2e_api,
                 "eager_module_api": {"value": B * world / eager_dt, "ms_per_step": eager_dt * 1e3}},
         "gpu_launches": int(n_launch), "gpu_launches_per_step": int(n_launch // max(a.steps, 1)),
-        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "configs": configs,
         "timing": {"ms_min": min(step_ms), "ms_median": statistics.median(step_ms),
                    "wall_s_incl_flush": t_wall, "cuda_graph": graph is not None},
     }

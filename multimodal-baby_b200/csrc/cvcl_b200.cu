@@ -7,6 +7,7 @@
 #include "fused_step.cuh"
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 using namespace cvcl;
 
@@ -776,26 +777,37 @@ int cvcl_flat_step_fused(const void* x16, const void* w16, const int64_t* ids, c
     p.dW = dW; p.dbias = dbias; p.dtable = dtable; p.dscale = dscale;
     p.inv_rows = 1.f / static_cast<float>(p.Bg);
 
-    fused::StepMaps maps;
+    // the 16 tensor maps depend only on the pointers and the shape: a training loop passes the same ones every
+    // step (torch's caching allocator hands back the same blocks), so the last set is kept per host thread
+    struct MapKey { const void* x16; const void* w16; void* ws; float* dW; float* dtable; int B, E, K, V, need; };
+    static thread_local MapKey last_key{};
+    static thread_local fused::StepMaps maps;
+    static thread_local bool maps_valid = false;
+    const MapKey key{x16, w16, workspace, dW, dtable, B, E, K, V, need_grads};
     int rc;
-    if ((rc = make_tmap(&maps.x_k, x16, 2, B, K, K, 64, 128))) return rc;
-    if ((rc = make_tmap(&maps.w_k, w16, 2, E, K, K, 64, 128))) return rc;
-    if ((rc = make_tmap(&maps.hp_out, p.hpart, 4, static_cast<uint64_t>(f.KS) * f.Bp, E, E, 32, 128))) return rc;
-    for (int z = 0; z < 2; ++z) {
-        if ((rc = make_tmap(&maps.q_k[z], p.q16[z], 2, B, E, p.ldq, 64, 128))) return rc;
-        if ((rc = make_tmap(&maps.kf_k[z], p.kf16[z], 2, p.Bg, E, p.ldk, 64, 128))) return rc;
-        if ((rc = make_tmap(&maps.kf_mn[z], p.kf16[z], 2, p.Bg, E, p.ldk, 64, 64))) return rc;
-    }
-    if ((rc = make_tmap(&maps.dq_out, p.dqpart, 4, 2ull * f.nPart * f.Bp, E, E, 32, 128))) return rc;
-    if ((rc = make_tmap(&maps.du_mn, p.du16, 2, B, E, E, 64, 64))) return rc;
-    if ((rc = make_tmap(&maps.x_mn, x16, 2, B, K, K, 64, 64))) return rc;
-    if ((rc = make_tmap(&maps.c_mn, p.cmat, 2, B, V, f.Vp, 64, 64))) return rc;
-    if ((rc = make_tmap(&maps.dm_mn, p.dm16, 2, B, E, E, 64, 64))) return rc;
-    if (need_grads) {
-        if ((rc = make_tmap(&maps.dw_out, dW, 4, E, K, K, 32, 128))) return rc;
-        if ((rc = make_tmap(&maps.dt_out, dtable, 4, V, E, E, 32, 128))) return rc;
-    } else {
-        maps.dw_out = maps.hp_out; maps.dt_out = maps.hp_out;
+    if (!maps_valid || memcmp(&key, &last_key, sizeof(MapKey)) != 0) {
+        maps_valid = false;
+        if ((rc = make_tmap(&maps.x_k, x16, 2, B, K, K, 64, 128))) return rc;
+        if ((rc = make_tmap(&maps.w_k, w16, 2, E, K, K, 64, 128))) return rc;
+        if ((rc = make_tmap(&maps.hp_out, p.hpart, 4, static_cast<uint64_t>(f.KS) * f.Bp, E, E, 32, 128))) return rc;
+        for (int z = 0; z < 2; ++z) {
+            if ((rc = make_tmap(&maps.q_k[z], p.q16[z], 2, B, E, p.ldq, 64, 128))) return rc;
+            if ((rc = make_tmap(&maps.kf_k[z], p.kf16[z], 2, p.Bg, E, p.ldk, 64, 128))) return rc;
+            if ((rc = make_tmap(&maps.kf_mn[z], p.kf16[z], 2, p.Bg, E, p.ldk, 64, 64))) return rc;
+        }
+        if ((rc = make_tmap(&maps.dq_out, p.dqpart, 4, 2ull * f.nPart * f.Bp, E, E, 32, 128))) return rc;
+        if ((rc = make_tmap(&maps.du_mn, p.du16, 2, B, E, E, 64, 64))) return rc;
+        if ((rc = make_tmap(&maps.x_mn, x16, 2, B, K, K, 64, 64))) return rc;
+        if ((rc = make_tmap(&maps.c_mn, p.cmat, 2, B, V, f.Vp, 64, 64))) return rc;
+        if ((rc = make_tmap(&maps.dm_mn, p.dm16, 2, B, E, E, 64, 64))) return rc;
+        if (need_grads) {
+            if ((rc = make_tmap(&maps.dw_out, dW, 4, E, K, K, 32, 128))) return rc;
+            if ((rc = make_tmap(&maps.dt_out, dtable, 4, V, E, E, 32, 128))) return rc;
+        } else {
+            maps.dw_out = maps.hp_out; maps.dt_out = maps.hp_out;
+        }
+        last_key = key;
+        maps_valid = true;
     }
 
     static thread_local bool attr_done = false;

@@ -252,6 +252,10 @@ class MultiModalModel(nn.Module):
         # "ops": op-by-op autograd path (always used for spatial embeddings / finetune_cnn).
         self.train_path = "fused"
         self.process_group = None         # set to a torch.distributed group to shard the batch
+        # spatial "max" similarity: "split_bf16" evaluates head and scores with two-term bf16 operands (fp32-grade,
+        # 3x the tensor work) so that the arg-max over the 7x7 locations agrees with the reference's fp32
+        # arithmetic; "bf16" is the fast single-term form (near-tied locations may flip, moving gradient rows)
+        self.spatial_max_precision = "split_bf16"
 
     # -- helpers ---------------------------------------------------------------------------
     def _head(self):
@@ -268,13 +272,16 @@ class MultiModalModel(nn.Module):
         with torch.set_grad_enabled(torch.is_grad_enabled()):
             return split_trunk_forward(self.image_embed, image, run_head=False)
 
+    def _split(self):
+        return self.embedding_type == "spatial" and self.sim == "max" and self.spatial_max_precision == "split_bf16"
+
     def _image_features_from_trunk(self, boundary):
         w, b = self._head()
         if self.embedding_type == "flat":
             return ops.head_features(boundary, w, b, self.normalize_features)
         B, K, H, W = boundary.shape
         rows = boundary.permute(0, 2, 3, 1).reshape(B * H * W, K)          # NHWC rows
-        feat = ops.head_features(rows, w, b, self.normalize_features)      # [B*H*W, E]
+        feat = ops.head_features(rows, w, b, self.normalize_features, split=self._split())      # [B*H*W, E]
         return feat.view(B, H, W, -1)                                      # NHWC
 
     # -- reference API ---------------------------------------------------------------------
@@ -309,7 +316,7 @@ class MultiModalModel(nn.Module):
                                                  1.0 / (H * W), want_tok=False)
             return ops.sim_logits(ops.spatial_pool(nhwc), tpool, s)
         tok, _ = ops.text_features_spatial(text, text_length, table, self.normalize_features)
-        match = ops.spatial_max_similarity(nhwc, tok, text_length, text)
+        match = ops.spatial_max_similarity(nhwc, tok, text_length, text, split=self._split())
         scale = s.exp() if torch.is_tensor(s) else math.exp(s)
         scale = scale.to(match.device) if torch.is_tensor(scale) else scale
         return match * scale, match.t() * scale
@@ -362,7 +369,7 @@ class MultiModalModel(nn.Module):
                 loss, iacc, tacc, ient, tent, _, _ = ops.sim_infonce(img_f, txt_f, s, self.process_group)
             else:
                 tok, _ = ops.text_features_spatial(y, y_len, table, self.normalize_features)
-                match = ops.spatial_max_similarity(nhwc, tok, y_len, y)
+                match = ops.spatial_max_similarity(nhwc, tok, y_len, y, split=self._split())
                 loss, iacc, tacc, ient, tent, lpi, lpt = ops.infonce_from_match(match, s)
         logits_per_image = logits_per_text = None
         if self.materialize_logits and img_f is not None and img_f.numel() == 0:

@@ -65,10 +65,12 @@ def _pad8(n: int) -> int:
 def _i64(t: Tensor) -> Tensor:
     if t.dtype != torch.int64:
         raise TypeError("token ids / lengths must be int64 (got %s)" % t.dtype)
-    return t.contiguous()
+    return t if t.is_contiguous() else t.contiguous()
 
 
 def _f32(t: Tensor) -> Tensor:
+    if t.dtype == torch.float32 and t.is_contiguous():
+        return t.detach() if t.requires_grad else t
     return t.detach().to(torch.float32).contiguous()
 
 
@@ -310,10 +312,26 @@ def _(g, feat, inv_norm, x, w, normalize, need_dx):
             g.new_empty(x.shape if need_dx else (0,), dtype=torch.float32))
 
 
+def split_bf16_cat(x: Tensor, pattern: str) -> Tensor:
+    """x [R, C] fp32 -> bf16 [R, 3C]: the two-term bf16 expansion x = hi + lo (hi = bf16(x), lo = bf16(x - hi))
+    laid out along the contraction as `pattern` ("hlh" or "hhl").  With A as "hlh" and B as "hhl" one bf16 GEMM
+    over 3C evaluates hi.hi + lo.hi + hi.lo with fp32 accumulation: the product to ~2^-16 relative instead of
+    2^-8.  Used where a result feeds an ARG-MAX (spatial "max" similarity): near-tied candidates must be ordered
+    as the reference's fp32 arithmetic orders them, or gradient rows move to other locations."""
+    x = x.detach().float()
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    parts = {"h": hi, "l": lo}
+    return torch.cat([parts[c] for c in pattern], dim=1).contiguous()
+
+
 class _HeadFeatures(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, bias, normalize):
-        feat, inv = _raw(head_proj_norm_fwd)(x, w, bias, normalize)
+    def forward(ctx, x, w, bias, normalize, split=False):
+        if split and x.dtype == torch.float32:
+            feat, inv = _raw(head_proj_norm_fwd)(split_bf16_cat(x, "hlh"), split_bf16_cat(w, "hhl"), bias, normalize)
+        else:
+            feat, inv = _raw(head_proj_norm_fwd)(x, w, bias, normalize)
         ctx.save_for_backward(x, w, feat, inv)
         ctx.normalize = normalize
         ctx.has_bias = bias is not None
@@ -325,12 +343,13 @@ class _HeadFeatures(torch.autograd.Function):
         need_dx = ctx.needs_input_grad[0]
         dW, db, dx = _raw(head_proj_norm_bwd)(g, feat, inv, x, w, ctx.normalize, need_dx)
         return (dx.to(x.dtype) if need_dx else None, dW.to(w.dtype),
-                db if ctx.has_bias else None, None)
+                db if ctx.has_bias else None, None, None)
 
 
-def head_features(x, w, bias, normalize=True):
-    """normalise(x @ w.T + bias) on the tcgen05 engine; x [M,K] -> [M,E] fp32."""
-    return _HeadFeatures.apply(x, w, bias, bool(normalize))
+def head_features(x, w, bias, normalize=True, split=False):
+    """normalise(x @ w.T + bias) on the tcgen05 engine; x [M,K] -> [M,E] fp32.  split=True: two-term bf16
+    operands (see split_bf16_cat) -- fp32-grade features for consumers that take an arg-max."""
+    return _HeadFeatures.apply(x, w, bias, bool(normalize), bool(split))
 
 
 # ----------------------------------------------------------------------------------------
@@ -625,11 +644,22 @@ def _fused_workspace(dev, B, L, E, K, V):
     return ws
 
 
+_FUSED_OK = {}
+_FUSED_ENV = None
+
+
 def fused_supported(B, L, E, K, V) -> bool:
-    import os
-    if not FUSED_STEP or os.environ.get("CVCL_B200_FUSED", "1") == "0":
+    global _FUSED_ENV
+    if _FUSED_ENV is None:
+        import os
+        _FUSED_ENV = os.environ.get("CVCL_B200_FUSED", "1") != "0"
+    if not (FUSED_STEP and _FUSED_ENV):
         return False
-    return bool(_cabi.load().cvcl_flat_fused_supported(B, L, E, K, V))
+    key = (B, L, E, K, V)
+    ok = _FUSED_OK.get(key)
+    if ok is None:
+        ok = _FUSED_OK[key] = bool(_cabi.load().cvcl_flat_fused_supported(B, L, E, K, V))
+    return ok
 
 
 def fused_layout(B, L, E, K, V):
@@ -724,12 +754,14 @@ class _FlatContrastiveStep(torch.autograd.Function):
             x, ids, lens, w, bias, table, 0.0 if s_dev is not None else _scalar(s), normalize, need,
             want_features, s_dev)
         ctx.need = need
+        ctx.consumed = False
         ctx.s_is_tensor = torch.is_tensor(s)
         ctx.dims = (table.shape[1], x.shape[1], table.shape[0])
         if need:
             ctx.save_for_backward(flat)
         ctx.mark_non_differentiable(img_f, txt_f)
-        return out5[0], out5[1], out5[2], out5[3], out5[4], img_f, txt_f
+        o = out5.unbind(0)                       # one op for the five scalars
+        return o[0], o[1], o[2], o[3], o[4], img_f, txt_f
 
     @staticmethod
     def backward(ctx, gloss, *unused):
@@ -737,7 +769,13 @@ class _FlatContrastiveStep(torch.autograd.Function):
             return (None,) * 9
         (flat,) = ctx.saved_tensors
         E, K, V = ctx.dims
-        ds, db, dtable, dW = split_flat_grads(flat * gloss, E, K, V)
+        # the gradients were computed for upstream = 1; scale in place (no 9.6 MB temporary).  Marked so a
+        # second backward through the same graph (retain_graph) is rejected instead of scaling twice.
+        if ctx.consumed:
+            raise RuntimeError("flat_contrastive_step: backward through this step a second time is not supported")
+        ctx.consumed = True
+        flat.mul_(gloss)
+        ds, db, dtable, dW = split_flat_grads(flat, E, K, V)
         return (None, None, None, dW, db, dtable, ds[0] if ctx.s_is_tensor else None, None, None)
 
 
@@ -1001,13 +1039,20 @@ def _(g, lens, ids, a_it, a_ti, img16, tok16, need_dimg, need_dtok):
 
 class _SpatialMax(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, img, tok, lens, ids):
+    def forward(ctx, img, tok, lens, ids, split=False):
         Bi, HW, E = img.shape
         Bt, L, _ = tok.shape
         i16, _ = to_bf16_pair(img.reshape(Bi * HW, E), False)
         t16, _ = to_bf16_pair(tok.reshape(Bt * L, E), False)
         i16 = i16.view(Bi, HW, E); t16 = t16.view(Bt, L, E)
-        match, a_it, a_ti = _raw(spatial_max_fwd)(i16, t16, lens)
+        if split and img.dtype == torch.float32 and tok.dtype == torch.float32:
+            # scores to fp32 accuracy (hi.hi + lo.hi + hi.lo over a 3E contraction): the arg-max location of
+            # near-tied locations agrees with the reference's fp32 einsum; the backward keeps the plain bf16 features
+            ic = split_bf16_cat(img.reshape(Bi * HW, E), "hhl").view(Bi, HW, 3 * E)
+            tc = split_bf16_cat(tok.reshape(Bt * L, E), "hlh").view(Bt, L, 3 * E)
+            match, a_it, a_ti = _raw(spatial_max_fwd)(ic, tc, lens)
+        else:
+            match, a_it, a_ti = _raw(spatial_max_fwd)(i16, t16, lens)
         ctx.save_for_backward(lens, ids, a_it, a_ti, i16, t16)
         ctx.dt = (img.dtype, tok.dtype)
         return match
@@ -1018,13 +1063,14 @@ class _SpatialMax(torch.autograd.Function):
         dimg, dtok = _raw(spatial_max_bwd)(g, lens, ids, a_it, a_ti, i16, t16, ctx.needs_input_grad[0],
                                      ctx.needs_input_grad[1])
         return (dimg.to(ctx.dt[0]) if ctx.needs_input_grad[0] else None,
-                dtok.to(ctx.dt[1]) if ctx.needs_input_grad[1] else None, None, None)
+                dtok.to(ctx.dt[1]) if ctx.needs_input_grad[1] else None, None, None, None)
 
 
-def spatial_max_similarity(img_nhwc, tok, lens, ids=None):
+def spatial_max_similarity(img_nhwc, tok, lens, ids=None, split=False):
     """match[i,t] = sum_l max_hw <img[i,hw,:], tok[t,l,:]> / len[t]   (multimodal.py:771-780).
-    img_nhwc [Bi,HW,E], tok [Bt,L,E] (fp32 or bf16) -> [Bi,Bt] fp32."""
-    return _SpatialMax.apply(img_nhwc, tok, lens, ids)
+    img_nhwc [Bi,HW,E], tok [Bt,L,E] (fp32 or bf16) -> [Bi,Bt] fp32.  split=True (fp32 inputs): two-term bf16
+    operands, scores and arg-max locations to fp32 accuracy at 3x the tensor work."""
+    return _SpatialMax.apply(img_nhwc, tok, lens, ids, bool(split))
 
 
 @torch.library.custom_op(_NS + "::match_infonce_fwd", mutates_args=())
