@@ -504,7 +504,10 @@ def sim_infonce_bwd(img_q: Tensor, txt_k: Tensor, txt_q: Tensor, img_k: Tensor, 
     M1 = txt_q.shape[0]
     N1 = img_k.shape[0]
     dev = img_q.device
-    single = img_q.data_ptr() == img_k.data_ptr() and txt_q.data_ptr() == txt_k.data_ptr()
+    # one GPU: queries and keys are the same tensors.  (A shard whose local block sits at offset 0 of the gathered
+    # buffer shares the POINTER with it -- rank 0 -- so the shapes must agree too.)
+    single = (img_q.data_ptr() == img_k.data_ptr() and txt_q.data_ptr() == txt_k.data_ptr()
+              and M0 == N1 and M1 == N0)
     ld0, ld1 = _pad8(N0), _pad8(N1)
     G0 = torch.empty((M0, ld0), dtype=torch.bfloat16, device=dev)
     G1 = None if single else torch.empty((M1, ld1), dtype=torch.bfloat16, device=dev)
