@@ -209,6 +209,28 @@ int cvcl_flat_step_fused(const void* x16, const void* w16, const int64_t* ids, c
                          float* dW, float* dbias, float* dtable, float* dscale, int* status, int phase_limit,
                          void* stream);
 
+/* The same kernel with the batch sharded by pairs over `world` ranks of one NVLink domain: rank r owns
+ * pairs [r*B, r*B + B) of the global batch of world*B pairs, the head / embedding parameters are replicated.
+ * All peer_* arguments are HOST arrays of `world` device pointers into peer-mapped symmetric memory, entry p =
+ * rank p's buffer: gathered text / image features [world*B, E] bf16, gathered LSEs [2, world*B] fp32, 32 flag
+ * words (zero before first use).  `epoch` is a LOCAL device word, zero before first use.  The phases that produce
+ * features and LSEs store them straight into every rank's gathered buffers (posted stores over NVLink) and the
+ * grid barrier that follows also spans the ranks (flag words, st.release.sys / ld.acquire.sys): no exchange
+ * kernel, no NCCL.  Outputs are this rank's PARTIAL sums (out5 scaled by 1/(world*B), gradients of the
+ * replicated parameters): the caller sums them over the ranks (cvcl_peer_allreduce_push_f32 when they live in
+ * symmetric memory), which also fences the reuse of the gathered buffers by the next step; a forward-only caller
+ * issues cvcl_peer_barrier instead.  Every rank must call with the same shapes.  world = 1 is allowed. */
+int cvcl_flat_fused_sharded_supported(int B, int L, int E, int K, int V, int world);
+size_t cvcl_flat_fused_sharded_workspace_bytes(int B, int L, int E, int K, int V, int world);
+int cvcl_flat_step_fused_sharded(const void* x16, const void* w16, const int64_t* ids, const int64_t* lens,
+                                 const float* bias, const float* table, int B, int L, int E, int K, int V,
+                                 int normalize, float log_scale, const float* log_scale_dev, int need_grads,
+                                 void* workspace, float* out5, float* img_feat_f32, float* txt_feat_f32,
+                                 float* dW, float* dbias, float* dtable, float* dscale, int* status, int phase_limit,
+                                 int world, int rank, void* const* peer_txt_all, void* const* peer_img_all,
+                                 void* const* peer_lse_all, void* const* peer_flags, unsigned int* epoch,
+                                 void* stream);
+
 /* ---- K6 spatial "max" similarity --------------------------------------------------------------
  * replaces multimodal.py:771-780 (einsum 'iehw,tle->itlhw' + amax over (h,w) + sum over l / len)
  * without materialising the [B,B,L,H,W] tensor.  tok [Bt*L, E] bf16 (per-token normalised text

@@ -653,18 +653,25 @@ struct FusedPlan {
            off_dqpart, off_du16, off_dbpart, off_dm16, off_cmat, bytes;
 };
 // -> 0 when the persistent kernel covers the shape, else the reason (unsupported, not an error)
-const char* plan_fused(FusedPlan* f, int B, int E, int K, int V) {
+const char* plan_fused(FusedPlan* f, int B, int E, int K, int V, int world = 1) {
     const int G = sm_count();
     if (B < 1) return "B < 1";
     if (E % 128 != 0 || E < 128 || E > 512) return "E must be 128, 256, 384 or 512";
     if (K % 64 != 0 || K < 64) return "K must be a multiple of 64";
     if (V < 1) return "V < 1";
+    if (world != 1 && world != 2 && world != 4 && world != 8) return "world size must be 1, 2, 4 or 8";
+    if (world > 1 && B % 128 != 0) return "sharded: pairs per rank must be a multiple of 128";
     f->grid = G;
     f->Bp = ceil_div(B, 128) * 128;
-    f->nMB = f->Bp / 128; f->nEB = E / 128; f->nCB = f->nMB;
-    f->T = 1; f->nPart = f->nCB / f->T;
-    const int n_tiles = 2 * f->nMB * f->nPart;
-    if (n_tiles > G) return "batch too large for one similarity tile per SM";
+    f->nMB = f->Bp / 128; f->nEB = E / 128;
+    f->nCB = world == 1 ? f->nMB : world * f->nMB;            // column blocks span the GLOBAL batch
+    int n_tiles = 2 * f->nMB * f->nCB;
+    f->T = 1;
+    if (const char* e = getenv("CVCL_B200_FUSED_FORCE_T")) { if (atoi(e) == 2 && f->nCB % 2 == 0) f->T = 2; }   // test hook
+    if (n_tiles > G) f->T = 2;                                // two tiles of one row block per CTA (TMEM: 2 x 128 columns)
+    if (f->nCB % f->T != 0 || n_tiles / f->T > G) return "batch too large for the similarity phase";
+    f->nPart = f->nCB / f->T;
+    n_tiles /= f->T;
     f->QS = 1;                                   // CTAs per similarity tile: the largest divisor of E/128 that fits
     for (int d = f->nEB; d >= 1; --d)
         if (f->nEB % d == 0 && n_tiles * d <= G) { f->QS = d; break; }
@@ -697,6 +704,16 @@ const char* plan_fused(FusedPlan* f, int B, int E, int K, int V) {
     f->bytes = off;
     return nullptr;
 }
+
+// sharding descriptor of the one-kernel step (null = one GPU)
+struct FusedShard {
+    int world, rank;
+    void* const* peer_txt_all;      // [world] rank p's gathered text features  [world*B, E] bf16
+    void* const* peer_img_all;      // [world] rank p's gathered image features [world*B, E] bf16
+    void* const* peer_lse_all;      // [world] rank p's gathered LSEs [2, world*B] fp32
+    void* const* peer_flags;        // [world] rank p's flag words (32 x u32, zero before first use)
+    unsigned int* epoch;            // local u32, zero before first use
+};
 }  // namespace
 
 int cvcl_flat_fused_supported(int B, int L, int E, int K, int V) {
@@ -725,18 +742,20 @@ int cvcl_flat_fused_layout(int B, int L, int E, int K, int V, long long* out, in
     return CVCL_OK;
 }
 
-int cvcl_flat_step_fused(const void* x16, const void* w16, const int64_t* ids, const int64_t* lens,
-                         const float* bias, const float* table, int B, int L, int E, int K, int V,
-                         int normalize, float log_scale, const float* log_scale_dev, int need_grads,
-                         void* workspace, float* out5, float* img_feat_f32, float* txt_feat_f32,
-                         float* dW, float* dbias, float* dtable, float* dscale, int* status, int phase_limit,
-                         void* stream) {
+static int flat_step_fused_impl(const void* x16, const void* w16, const int64_t* ids, const int64_t* lens,
+                                const float* bias, const float* table, int B, int L, int E, int K, int V,
+                                int normalize, float log_scale, const float* log_scale_dev, int need_grads,
+                                void* workspace, float* out5, float* img_feat_f32, float* txt_feat_f32,
+                                float* dW, float* dbias, float* dtable, float* dscale, int* status, int phase_limit,
+                                const FusedShard* sh, void* stream) {
     CVCL_REQUIRE(x16 && w16 && ids && lens && table && workspace && out5, "flat_step_fused: null pointer");
     CVCL_REQUIRE(!need_grads || (dW && dbias && dtable && dscale), "flat_step_fused: null gradient output");
     CVCL_REQUIRE(L >= 1 && V >= 1, "flat_step_fused: bad shape");
+    const int world = sh ? sh->world : 1, rank = sh ? sh->rank : 0;
+    CVCL_REQUIRE(rank >= 0 && rank < world, "flat_step_fused: rank %d outside [0,%d)", rank, world);
     FusedPlan f{};
-    if (const char* why = plan_fused(&f, B, E, K, V))
-        return fail(CVCL_ERR_UNSUPPORTED, "flat_step_fused: %s (B=%d E=%d K=%d)", why, B, E, K);
+    if (const char* why = plan_fused(&f, B, E, K, V, world))
+        return fail(CVCL_ERR_UNSUPPORTED, "flat_step_fused: %s (B=%d E=%d K=%d world=%d)", why, B, E, K, world);
     CVCL_REQUIRE(((reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(table) |
                    reinterpret_cast<uintptr_t>(bias)) & 15) == 0, "flat_step_fused: 16-byte alignment required");
     CVCL_REQUIRE(!need_grads || ((reinterpret_cast<uintptr_t>(dtable) | reinterpret_cast<uintptr_t>(dW)) & 15) == 0,
@@ -746,21 +765,42 @@ int cvcl_flat_step_fused(const void* x16, const void* w16, const int64_t* ids, c
     p.ids = reinterpret_cast<const long long*>(ids); p.lens = reinterpret_cast<const long long*>(lens);
     p.table = table; p.bias = bias; p.log_scale_dev = log_scale_dev; p.log_scale = log_scale;
     p.B = B; p.L = L; p.E = E; p.K = K; p.V = V; p.normalize = normalize; p.need_grads = need_grads;
-    p.Bg = B; p.diag_off = 0;
+    p.Bg = B * world; p.diag_off = rank * B;
+    p.world = world; p.rank = rank;
     p.Bp = f.Bp; p.nMB = f.nMB; p.nEB = f.nEB; p.nCB = f.nCB; p.KS = f.KS; p.kc_per_split = f.kc_per_split;
     p.num_kc = f.num_kc; p.T = f.T; p.nPart = f.nPart; p.QS = f.QS; p.Vp = f.Vp; p.dw_bn = f.dw_bn;
     p.phase_limit = phase_limit;
     p.hpart = reinterpret_cast<float*>(ws + f.off_hpart);
-    p.q16[0] = reinterpret_cast<__nv_bfloat16*>(ws + f.off_img16);
-    p.q16[1] = reinterpret_cast<__nv_bfloat16*>(ws + f.off_txt16);
-    p.ldq = E;
-    p.kf16[0] = p.q16[1]; p.kf16[1] = p.q16[0]; p.ldk = E;
+    p.ldq = E; p.ldk = E;
+    if (sh) {
+        // gathered buffers in peer-mapped symmetric memory: kf16[0] = all texts, kf16[1] = all images; the local
+        // features are the slice [rank*B, rank*B + B) of this rank's own copies
+        for (int r = 0; r < world; ++r) {
+            CVCL_REQUIRE(sh->peer_txt_all[r] && sh->peer_img_all[r] && sh->peer_lse_all[r] && sh->peer_flags[r],
+                         "flat_step_fused: null peer pointer %d", r);
+            p.peer_kf[0][r] = static_cast<__nv_bfloat16*>(sh->peer_txt_all[r]);
+            p.peer_kf[1][r] = static_cast<__nv_bfloat16*>(sh->peer_img_all[r]);
+            p.peer_lse[0][r] = static_cast<float*>(sh->peer_lse_all[r]);
+            p.peer_lse[1][r] = static_cast<float*>(sh->peer_lse_all[r]) + p.Bg;
+            p.peer_flags[r] = static_cast<unsigned int*>(sh->peer_flags[r]);
+        }
+        p.epoch = sh->epoch;
+        p.kf16[0] = p.peer_kf[0][rank]; p.kf16[1] = p.peer_kf[1][rank];
+        p.q16[0] = p.peer_kf[1][rank] + static_cast<size_t>(p.diag_off) * E;
+        p.q16[1] = p.peer_kf[0][rank] + static_cast<size_t>(p.diag_off) * E;
+    } else {
+        p.q16[0] = reinterpret_cast<__nv_bfloat16*>(ws + f.off_img16);
+        p.q16[1] = reinterpret_cast<__nv_bfloat16*>(ws + f.off_txt16);
+        p.kf16[0] = p.q16[1]; p.kf16[1] = p.q16[0];
+        p.peer_kf[0][0] = p.q16[1]; p.peer_kf[1][0] = p.q16[0];
+        p.epoch = nullptr;
+    }
     for (int z = 0; z < 2; ++z) {
         p.invn[z] = reinterpret_cast<float*>(ws + f.off_invn) + z * f.Bp;
         p.part[z] = reinterpret_cast<RowStat*>(ws + f.off_part) + static_cast<size_t>(z) * 2 * f.nCB * f.Bp;
         p.diag[z] = reinterpret_cast<float*>(ws + f.off_diag) + z * f.Bp;
         p.lse[z] = reinterpret_cast<float*>(ws + f.off_lse) + z * f.Bp;
-        p.lse_all[z] = nullptr;
+        p.lse_all[z] = (sh && world > 1) ? p.peer_lse[z][rank] : nullptr;
     }
     p.rb_part = reinterpret_cast<float*>(ws + f.off_rbpart);
     p.dspart = reinterpret_cast<float*>(ws + f.off_dspart);
@@ -779,11 +819,15 @@ int cvcl_flat_step_fused(const void* x16, const void* w16, const int64_t* ids, c
 
     // the 16 tensor maps depend only on the pointers and the shape: a training loop passes the same ones every
     // step (torch's caching allocator hands back the same blocks), so the last set is kept per host thread
-    struct MapKey { const void* x16; const void* w16; void* ws; float* dW; float* dtable; int B, E, K, V, need; };
+    struct MapKey { const void* x16; const void* w16; void* ws; float* dW; float* dtable; const void* kf0; const void* kf1;
+                    int B, E, K, V, need, world, rank, T; };
     static thread_local MapKey last_key{};
     static thread_local fused::StepMaps maps;
     static thread_local bool maps_valid = false;
-    const MapKey key{x16, w16, workspace, dW, dtable, B, E, K, V, need_grads};
+    MapKey key{};                                    // zero the padding: the key is compared with memcmp
+    key.x16 = x16; key.w16 = w16; key.ws = workspace; key.dW = dW; key.dtable = dtable; key.kf0 = p.kf16[0];
+    key.kf1 = p.kf16[1]; key.B = B; key.E = E; key.K = K; key.V = V; key.need = need_grads; key.world = world;
+    key.rank = rank; key.T = f.T;
     int rc;
     if (!maps_valid || memcmp(&key, &last_key, sizeof(MapKey)) != 0) {
         maps_valid = false;
@@ -828,6 +872,46 @@ int cvcl_flat_step_fused(const void* x16, const void* w16, const int64_t* ids, c
     CVCL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fused::flat_step_kernel, maps, p));
     count_launch();
     return CVCL_OK;
+}
+
+int cvcl_flat_step_fused(const void* x16, const void* w16, const int64_t* ids, const int64_t* lens,
+                         const float* bias, const float* table, int B, int L, int E, int K, int V,
+                         int normalize, float log_scale, const float* log_scale_dev, int need_grads,
+                         void* workspace, float* out5, float* img_feat_f32, float* txt_feat_f32,
+                         float* dW, float* dbias, float* dtable, float* dscale, int* status, int phase_limit,
+                         void* stream) {
+    return flat_step_fused_impl(x16, w16, ids, lens, bias, table, B, L, E, K, V, normalize, log_scale, log_scale_dev,
+                                need_grads, workspace, out5, img_feat_f32, txt_feat_f32, dW, dbias, dtable, dscale, status,
+                                phase_limit, nullptr, stream);
+}
+
+int cvcl_flat_fused_sharded_supported(int B, int L, int E, int K, int V, int world) {
+    (void)L;
+    FusedPlan f{};
+    return plan_fused(&f, B, E, K, V, world) == nullptr ? 1 : 0;
+}
+
+size_t cvcl_flat_fused_sharded_workspace_bytes(int B, int L, int E, int K, int V, int world) {
+    (void)L;
+    FusedPlan f{};
+    return plan_fused(&f, B, E, K, V, world) == nullptr ? f.bytes : 0;
+}
+
+int cvcl_flat_step_fused_sharded(const void* x16, const void* w16, const int64_t* ids, const int64_t* lens,
+                                 const float* bias, const float* table, int B, int L, int E, int K, int V,
+                                 int normalize, float log_scale, const float* log_scale_dev, int need_grads,
+                                 void* workspace, float* out5, float* img_feat_f32, float* txt_feat_f32,
+                                 float* dW, float* dbias, float* dtable, float* dscale, int* status, int phase_limit,
+                                 int world, int rank, void* const* peer_txt_all, void* const* peer_img_all,
+                                 void* const* peer_lse_all, void* const* peer_flags, unsigned int* epoch,
+                                 void* stream) {
+    CVCL_REQUIRE(peer_txt_all && peer_img_all && peer_lse_all && peer_flags && epoch,
+                 "flat_step_fused_sharded: null peer table");
+    CVCL_REQUIRE(world >= 1 && world <= 8, "flat_step_fused_sharded: world size %d", world);
+    FusedShard sh{world, rank, peer_txt_all, peer_img_all, peer_lse_all, peer_flags, epoch};
+    return flat_step_fused_impl(x16, w16, ids, lens, bias, table, B, L, E, K, V, normalize, log_scale, log_scale_dev,
+                                need_grads, workspace, out5, img_feat_f32, txt_feat_f32, dW, dbias, dtable, dscale, status,
+                                phase_limit, &sh, stream);
 }
 
 // ------------------------------------------------------------------------------------ K6 spatial max

@@ -101,7 +101,16 @@ struct StepParams {
     RowStat* part[2];                    // [nCB][Bp]
     float* diag[2];                      // [Bp] logit at the positive
     float* lse[2];                       // [Bp] (local rows)
-    const float* lse_all[2];             // [Bg] LSEs of every row of direction z (== lse[z] on one GPU)
+    const float* lse_all[2];             // [Bg] LSEs of every row of direction z, gathered (sharded only; null on one GPU)
+    // ---- sharding: rank `rank` of `world` owns pairs [diag_off, diag_off + B) of the global batch.
+    // Every rank maps every rank's gathered buffers (symmetric memory over NVLink): the phases that PRODUCE
+    // features / LSEs store them straight into all ranks' buffers, and the grid barrier that follows carries a
+    // cross-rank stage.  world == 1: the tables hold the local buffers and nothing crosses a link.
+    int world, rank;
+    __nv_bfloat16* peer_kf[2][8];        // [z][p]: rank p's gathered key features of direction z ([Bg, ldk])
+    float* peer_lse[2][8];               // [z][p]: rank p's lse_all[z]
+    unsigned int* peer_flags[8];         // rank p's flag words [4 stages][8 source ranks], epochs only grow
+    unsigned int* epoch;                 // local: launches completed so far (this launch signals epoch + 1)
     float* rb_part;                      // [2*nMB][6]
     float* dspart;                       // [nMB*nPart]
     float* dqpart;                       // [2][nPart][Bp][E]
@@ -150,15 +159,51 @@ __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
 // thread 0 (measured 1.5 us; atom.add.release was slower); bar.sync makes the CTA's writes part of the release.  kWriterFence: this phase wrote global
 // memory with ordinary stores that a later phase reads through TMA (async proxy), so every thread orders its
 // stores against the async proxy first; the TMA-issuing thread fences again after the barrier.
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// xstage >= 0 (sharded runs): the barrier also spans the ranks.  Every CTA fences its stores at system scope
+// before it arrives; the LAST local arrival (it has seen all the others through the counter) stores this
+// launch's epoch into flag word [xstage][rank] of every peer, and every CTA then also waits until its own
+// words [xstage][peer] carry the epoch: all stores a peer issued before ITS barrier have landed here.
 template <bool kWriterFence>
-CVCL_HELPER void grid_sync(const StepParams& p, int k) {
+CVCL_HELPER void grid_sync(const StepParams& p, int k, int xstage = -1, unsigned int epoch = 0) {
     if (kWriterFence) fence_proxy_async_all();
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(p.sync, 1u);
+        const bool cross = xstage >= 0 && p.world > 1;
+        if (cross) __threadfence_system(); else __threadfence();
         const unsigned int target = static_cast<unsigned int>(k + 1) * gridDim.x;
+        const unsigned int prev = atomicAdd(p.sync, 1u);
+        if (cross && prev == target - 1) {
+            for (int pp = 0; pp < p.world; ++pp)
+                if (pp != p.rank) st_release_sys(p.peer_flags[pp] + xstage * 8 + p.rank, epoch);
+        }
         unsigned int it = 0; unsigned long long t0 = 0;
+        if (cross) {
+            for (int pp = 0; pp < p.world; ++pp) {
+                if (pp == p.rank) continue;
+                const unsigned int* w = p.peer_flags[p.rank] + xstage * 8 + pp;
+                while (static_cast<int>(ld_acquire_sys(w) - epoch) < 0) {
+                    if ((++it & 4095u) == 0) {
+                        const unsigned long long now = globaltimer_ns();
+                        if (t0 == 0) t0 = now;
+                        else if (now - t0 > 20000000000ull) {     // 20 s: a peer never reached this step
+                            if (p.fault) atomicExch(p.fault, 200 + 10 * xstage + pp);
+                            __threadfence_system();
+                            __trap();
+                        }
+                    }
+                }
+            }
+            it = 0; t0 = 0;
+        }
         while (ld_acquire_gpu(p.sync) < target) {
             if ((++it & 4095u) == 0) {
                 const unsigned long long now = globaltimer_ns();
@@ -234,7 +279,8 @@ CVCL_HELPER void text_row(const StepParams& p, int b, int lane) {
             const int e = (c * 32 + lane) * 4;
             const float4 t = make_float4(acc[c].x * inv, acc[c].y * inv, acc[c].z * inv, acc[c].w * inv);
             if (p.txt_f32) *reinterpret_cast<float4*>(p.txt_f32 + static_cast<size_t>(b) * p.E + e) = t;
-            store_bf16x4(p.q16[1] + static_cast<size_t>(b) * p.ldq + e, t);
+            for (int pp = 0; pp < p.world; ++pp)          // texts are the keys of direction 0
+                store_bf16x4(p.peer_kf[0][pp] + static_cast<size_t>(p.diag_off + b) * p.ldk + e, t);
         }
     }
 }
@@ -332,6 +378,8 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const __grid_constant__ 
     const float scale = expf(s_log);
     constexpr float kLog2e = 1.4426950408889634f;
     int sync_k = 0;
+    // cross-rank flag value of this launch (sharded runs; every CTA reads it before any CTA can bump it at exit)
+    const unsigned int xepoch = p.epoch ? *reinterpret_cast<volatile unsigned int*>(p.epoch) + 1u : 0u;
 
     if (p.phase_limit == 100) {            // measurement: the cost of the grid barrier alone
         for (int i = 0; i < 6; ++i) grid_sync<false>(p, sync_k++);
@@ -464,7 +512,8 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const __grid_constant__ 
                     const int e = (c * 32 + lane) * 4;
                     const float4 t = make_float4(acc[c].x * inv, acc[c].y * inv, acc[c].z * inv, acc[c].w * inv);
                     if (p.img_f32) *reinterpret_cast<float4*>(p.img_f32 + static_cast<size_t>(r) * p.E + e) = t;
-                    store_bf16x4(p.q16[0] + static_cast<size_t>(r) * p.ldq + e, t);
+                    for (int pp = 0; pp < p.world; ++pp)  // images are the keys of direction 1
+                        store_bf16x4(p.peer_kf[1][pp] + static_cast<size_t>(p.diag_off + r) * p.ldk + e, t);
                 }
             }
             if (p.need_grads) {
@@ -486,7 +535,7 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const __grid_constant__ 
         }
         if (threadIdx.x == 0) CVCL_STAMP(19);
     }
-    grid_sync<true>(p, sync_k++);
+    grid_sync<true>(p, sync_k++, 0, xepoch);               // sharded: every rank's features are in place behind this
     if (p.phase_limit == 2) goto done;
 
     {
@@ -600,6 +649,19 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const __grid_constant__ 
         if (has) ++tfull_uses;
         grid_sync<false>(p, sync_k++);
         if (p.phase_limit == 3) goto done;
+
+        if (p.world > 1) {
+            // ---- sharded only: the LSEs of this rank's rows (both directions) go to every rank, because the
+            // column terms of dL/dlogits need the LSE of rows that other ranks own.  The lead CTA of
+            // each row block merges the partials and stores 128 floats per peer; then a cross-rank barrier.
+            if (has && pi == 0 && qs == 0 && half == 0 && m < M) {
+                float gm, gl, ga; int garg;
+                merge_stats(p.part[z] + m, p.Bp, 2 * p.nCB, gm, gl, ga, garg);
+                const float lse_row = gm + logf(gl);
+                for (int pp = 0; pp < p.world; ++pp) p.peer_lse[z][pp][p.diag_off + m] = lse_row;
+            }
+            grid_sync<false>(p, sync_k++, 1, xepoch);
+        }
 
         // ======================================================================== P3
         const int wq = p.E / p.QS;                          // dQ columns of this CTA: [qs*wq, qs*wq + wq)
@@ -996,6 +1058,7 @@ done:
         __threadfence();
         if (atomicAdd(p.sync + 1, 1u) == static_cast<unsigned int>(G - 1)) {
             p.sync[0] = 0u; p.sync[1] = 0u; p.sync[2] = 0u;
+            if (p.epoch) *p.epoch = xepoch;
             __threadfence();
         }
     }

@@ -651,6 +651,14 @@ _FUSED_OK = {}
 _FUSED_ENV = None
 
 
+def _fused_env() -> bool:
+    global _FUSED_ENV
+    if _FUSED_ENV is None:
+        import os
+        _FUSED_ENV = os.environ.get("CVCL_B200_FUSED", "1") != "0"
+    return _FUSED_ENV
+
+
 def fused_supported(B, L, E, K, V) -> bool:
     global _FUSED_ENV
     if _FUSED_ENV is None:
@@ -811,6 +819,7 @@ def flat_step_sharded(x, ids, lens, w, bias, table, log_scale, normalize, need_g
         x = x.float()
     x = x.detach().contiguous()
     ids = _i64(ids); lens = _i64(lens)
+    w_param = w
     w = _f32(w); bias = _f32(bias); table = _f32(table)
     B, K = x.shape
     L = ids.shape[1]
@@ -828,6 +837,30 @@ def flat_step_sharded(x, ids, lens, w, bias, table, log_scale, normalize, need_g
     # the three collectives run over peer-mapped symmetric memory when available (sharding.PeerExchange):
     # the arena is sized for the training step and shared with the forward-only call
     px = sharding.PeerExchange.get(group, B, E, 8 + n_g, dev) if world > 1 else None
+    if (px is not None and phase_limit is None and FUSED_STEP and _fused_env()
+            and lib.cvcl_flat_fused_sharded_supported(B, L, E, K, V, world)):
+        # ---- ONE persistent kernel per rank: the producing phases store features / LSEs into every rank's gathered
+        # buffers over NVLink and its grid barriers span the ranks; then one kernel sums the gradients
+        x16, _ = to_bf16_pair(x, False)
+        w16 = weight_shadow(w_param)
+        key = ("sharded", dev.index if dev.index is not None else torch.cuda.current_device(), B, L, E, K, V, world)
+        ws = _FUSED_WS.get(key)
+        if ws is None:
+            ws = _FUSED_WS[key] = torch.zeros((int(lib.cvcl_flat_fused_sharded_workspace_bytes(B, L, E, K, V, world)),),
+                                              dtype=torch.uint8, device=dev)
+        stats = px.stats[stats_slot][:8 + n_g]
+        img_f = torch.empty((B, E), **f32) if want_features else None
+        txt_f = torch.empty((B, E), **f32) if want_features else None
+        ds, db, dtable, dW = split_flat_grads(stats[8:], E, K, V)
+        C("cvcl_flat_step_fused_sharded", _p(x16), _p(w16), _p(ids), _p(lens), _p(bias), _p(table), B, L, E, K, V,
+          int(normalize), float(log_scale), None, int(need_grads), _p(ws), _p(stats), _p(img_f), _p(txt_f),
+          _p(dW) if need_grads else None, _p(db) if need_grads else None, _p(dtable) if need_grads else None,
+          _p(ds) if need_grads else None, None, 0, world, rank, px.p_txt_all, px.p_img_all, px.p_lse_all,
+          px.p_flags[px.CH_FUSED], px.fused_epoch.data_ptr(), st)
+        # partial sums -> global values on every rank (and the fence that lets the next step overwrite the gathered
+        # buffers); a forward-only step sums just the five scalars
+        px.allreduce_stats(stats_slot, n_stats if need_grads else 8, st)
+        return stats[:n_stats], img_f, txt_f
     # [img | txt] per pair: one exchange moves both
     feats = px.feats if px is not None else torch.empty((B, 2 * E), **bf)
     img_l, txt_l = feats[:, :E], feats[:, E:]

@@ -106,7 +106,7 @@ class PeerExchange:
     CVCL_B200_SYMM=0 selects the NCCL collectives."""
 
     _cache = {}
-    CH_FEATS, CH_LSE, CH_REDUCE, CH_BARRIER = 0, 1, 2, 3
+    CH_FEATS, CH_LSE, CH_REDUCE, CH_BARRIER, CH_FUSED = 0, 1, 2, 3, 4
     N_SLOTS = 2          # stats blocks: alternating CUDA graphs keep the previous step's gradients readable
 
     def __init__(self, group, b, E, n_stats, dev):
@@ -123,7 +123,10 @@ class PeerExchange:
         Bg = self.world * b
         sizes = [("feats", b * 2 * E * 2), ("lse", 2 * b * 4), ("feats_all", Bg * 2 * E * 2), ("lse_all", 2 * Bg * 4),
                  ("scratch", int(lib.cvcl_peer_allreduce_scratch_bytes(n_stats, self.world)))]
-        sizes += [("stats%d" % k, n_stats * 4) for k in range(self.N_SLOTS)] + [("flags", 4 * fw * 4)]
+        # gathered features of the one-kernel sharded step (texts and images separately: each is the key operand of
+        # one direction) and a fifth flag channel for its in-kernel cross-rank barriers
+        sizes += [("txt_all", Bg * E * 2), ("img_all", Bg * E * 2)]
+        sizes += [("stats%d" % k, n_stats * 4) for k in range(self.N_SLOTS)] + [("flags", 5 * fw * 4)]
         off, total = {}, 0
         for name, nb in sizes:
             off[name] = total
@@ -152,7 +155,11 @@ class PeerExchange:
         self.p_feats, self.p_lse = table("feats"), table("lse")
         self.p_feats_all, self.p_lse_all, self.p_scratch = table("feats_all"), table("lse_all"), table("scratch")
         self.p_stats = [table("stats%d" % k) for k in range(self.N_SLOTS)]
-        self.p_flags = [table("flags", ch * fw * 4) for ch in range(4)]
+        self.p_flags = [table("flags", ch * fw * 4) for ch in range(5)]
+        self.txt_all = view("txt_all", Bg * E * 2, torch.bfloat16).view(Bg, E)
+        self.img_all = view("img_all", Bg * E * 2, torch.bfloat16).view(Bg, E)
+        self.p_txt_all, self.p_img_all = table("txt_all"), table("img_all")
+        self.fused_epoch = torch.zeros((1,), dtype=torch.int32, device=dev)
         self._self_test(group, dev)
 
     NO_TRAP = 0x80000000

@@ -128,3 +128,57 @@ def test_weight_shadow_tracks_parameter_updates(cv):
     l3 = cv.ops.flat_contrastive_loss(d["f"], d["ids"], d["lens"], W, b, table, S_DEFAULT, True)[0].item()
     ref = oracle_flat_step({**inp, "W": inp["W"] * 0.5})
     assert abs(l3 - ref["loss"].item()) <= 1e-3 * abs(ref["loss"].item())
+
+
+def test_two_tiles_per_cta_layout(cv, monkeypatch):
+    """T = 2 (two similarity tiles of one row block per CTA: the layout 8 ranks x 512 pairs need) forced on one GPU at
+    1024 pairs: every phase against the restatement."""
+    import fused_check
+    monkeypatch.setenv("CVCL_B200_FUSED_FORCE_T", "2")
+    lay = cv.ops.fused_layout(1024, 25, 512, 2048, 2350)
+    assert lay["nPart"] * 2 == lay["nCB"]
+    rep = fused_check.run(1024, 512, 2048, verbose=False)
+    assert rep["P2 lse0 max abs"] <= 2e-3 and rep["P2 lse1 max abs"] <= 2e-3, rep
+    assert rep["P3 dI (no diag term)"] <= 1e-2 and rep["P3 dT (no diag term)"] <= 1e-2, rep
+    assert abs(rep["loss"][0] - rep["loss"][1]) <= 1e-3 * abs(rep["loss"][1]), rep
+    assert rep["dW"] <= 2e-2 and rep["db"] <= 2e-2 and rep["dtable"] <= 2e-2, rep
+    assert abs(rep["ds"][0] - rep["ds"][1]) <= 2e-2 * abs(rep["ds"][1]) + 1e-3, rep
+    assert rep["replay: all gradients bit-identical"], rep
+
+
+def test_sharded_entry_with_one_rank_equals_single_gpu_entry(cv):
+    """cvcl_flat_step_fused_sharded with world = 1 (the peer tables name local buffers): the pointer plumbing of the
+    sharded form -- gathered buffers, local slices, flag words, epoch -- gives bit-identical results."""
+    import ctypes
+    from multimodal_baby_b200 import _cabi
+    B, E, K, V, L = 256, 512, 2048, 2350, 25
+    inp = case_inputs(31337, B, E, "flat")
+    d = dev_inputs(inp)
+    x16 = d["f"].to(torch.bfloat16).contiguous(); w16 = d["W"].to(torch.bfloat16).contiguous()
+    p = cv.ops._p
+    st = torch.cuda.current_stream().cuda_stream
+    lib = _cabi.load()
+    f32 = dict(dtype=torch.float32, device=DEV)
+
+    def outputs():
+        flat = torch.zeros(4 + E + V * E + E * K, **f32)
+        return torch.zeros(8, **f32), flat, cv.ops.split_flat_grads(flat, E, K, V)
+    o1, flat1, (ds, db, dt, dW) = outputs()
+    ws1 = torch.zeros(int(lib.cvcl_flat_fused_workspace_bytes(B, L, E, K, V)), dtype=torch.uint8, device=DEV)
+    _cabi.call("cvcl_flat_step_fused", p(x16), p(w16), p(d["ids"]), p(d["lens"]), p(d["b"]), p(d["table"]), B, L, E, K, V,
+               1, S_DEFAULT, None, 1, p(ws1), p(o1), None, None, p(dW), p(db), p(dt), p(ds), None, 0, st)
+    o2, flat2, (ds2, db2, dt2, dW2) = outputs()
+    ws2 = torch.zeros(int(lib.cvcl_flat_fused_sharded_workspace_bytes(B, L, E, K, V, 1)), dtype=torch.uint8, device=DEV)
+    txt_all = torch.zeros(B, E, dtype=torch.bfloat16, device=DEV); img_all = torch.zeros_like(txt_all)
+    lse_all = torch.zeros(2, B, **f32); flags = torch.zeros(32, dtype=torch.int32, device=DEV)
+    epoch = torch.zeros(1, dtype=torch.int32, device=DEV)
+    arr = ctypes.c_void_p * 1
+    for _ in range(2):                                   # twice: the epoch advances, the control block is reusable
+        _cabi.call("cvcl_flat_step_fused_sharded", p(x16), p(w16), p(d["ids"]), p(d["lens"]), p(d["b"]), p(d["table"]),
+                   B, L, E, K, V, 1, S_DEFAULT, None, 1, p(ws2), p(o2), None, None, p(dW2), p(db2), p(dt2), p(ds2), None, 0,
+                   1, 0, arr(txt_all.data_ptr()), arr(img_all.data_ptr()), arr(lse_all.data_ptr()), arr(flags.data_ptr()),
+                   epoch.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert int(epoch.item()) == 2
+    assert torch.equal(o1[:5], o2[:5]) and torch.equal(flat1, flat2)
+    assert float(txt_all.float().norm(dim=1).min()) > 0.99               # the features landed in the gathered buffers
