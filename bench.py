@@ -147,6 +147,11 @@ def build_model(dev, group=None):
     return m, model
 
 
+def m_staging():
+    from multimodal_baby_b200 import staging
+    return staging
+
+
 def step_api(model, x, ids, lens, world):
     """the call a user makes: loss + backward (+ DDP-style gradient sum across ranks)."""
     for p in model.parameters():
@@ -475,8 +480,10 @@ def main():
     lib = _cabi.load()
 
     f, ids, lens = synth_batch(1234 + rank, B)
-    x_host = torch.from_numpy(f).to(torch.bfloat16).pin_memory()
-    ids_host = torch.from_numpy(ids).pin_memory(); lens_host = torch.from_numpy(lens).pin_memory()
+    # pinned staging as ONE arena [x | ids | lens] (what staging.PinnedBatchStager hands out): one H2D copy per step
+    x_host, ids_host, lens_host = m_staging().packed_buffers(
+        [((B, K), torch.bfloat16), ((B, L), torch.int64), ((B,), torch.int64)])
+    x_host.copy_(torch.from_numpy(f)); ids_host.copy_(torch.from_numpy(ids)); lens_host.copy_(torch.from_numpy(lens))
     x = x_host.to(dev); ids_d = ids_host.to(dev); lens_d = lens_host.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -543,6 +550,26 @@ def main():
     step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
     ms = statistics.mean(step_ms)
     n_launch = lib.cvcl_launch_count() - n0
+    # the same K steps launched directly (one C-ABI call per step, no graph): with a single kernel per step a graph
+    # replay only adds its own launch latency; the faster of the two forms is the value, both are reported
+    launch_form = "cuda graph replay" if graph is not None else "direct launch"
+    ms_graph = ms if graph is not None else None
+    ms_direct = None
+    if graph is not None and world == 1:
+        for _ in range(a.warmup):
+            flush.zero_(); raw_step()
+        barrier()
+        evs2 = []
+        for _ in range(a.steps):
+            flush.zero_()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); raw_step(); e1.record()
+            evs2.append((e0, e1))
+        barrier()
+        direct_ms = [e0.elapsed_time(e1) for e0, e1 in evs2]
+        ms_direct = statistics.mean(direct_ms)
+        if ms_direct < ms:
+            ms, step_ms, launch_form = ms_direct, direct_ms, "direct launch"
     if graph is not None:       # replays launch the captured kernels without passing through the C ABI
         n1 = lib.cvcl_launch_count(); raw_step(); per = lib.cvcl_launch_count() - n1
         n_launch = per * a.steps
@@ -556,7 +583,7 @@ def main():
 
     # ------------------------------------------------------------------ e2e through the public API
     # (a) eager: MultiModalModel.calculate_contrastive_loss(...) + backward(), pinned host inputs
-    e2e_steps = max(50, min(a.steps, 500))
+    e2e_steps = max(500, min(a.steps, 2000))     # wall-clock timed: enough calls that start-up effects do not dominate
     for _ in range(3):
         x.copy_(x_host, non_blocking=True); step_api(model, x, ids_d, lens_d, world).item()
     barrier()
@@ -665,7 +692,8 @@ def main():
         "gpu_launches": int(n_launch), "gpu_launches_per_step": int(n_launch // max(a.steps, 1)),
         "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "configs": configs,
         "timing": {"ms_min": min(step_ms), "ms_median": statistics.median(step_ms),
-                   "wall_s_incl_flush": t_wall, "cuda_graph": graph is not None},
+                   "wall_s_incl_flush": t_wall, "cuda_graph": graph is not None, "launch_form": launch_form,
+                   "ms_graph_replay": ms_graph, "ms_direct_launch": ms_direct},
     }
     print(json.dumps(line))
     finish()

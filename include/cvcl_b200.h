@@ -212,23 +212,35 @@ int cvcl_flat_step_fused(const void* x16, const void* w16, const int64_t* ids, c
 /* The same kernel with the batch sharded by pairs over `world` ranks of one NVLink domain: rank r owns
  * pairs [r*B, r*B + B) of the global batch of world*B pairs, the head / embedding parameters are replicated.
  * All peer_* arguments are HOST arrays of `world` device pointers into peer-mapped symmetric memory, entry p =
- * rank p's buffer: gathered text / image features [world*B, E] bf16, gathered LSEs [2, world*B] fp32, 32 flag
+ * rank p's buffer: gathered text / image features [world*B, E] bf16, gathered softmax partials
+ * (cvcl_flat_fused_sharded_part_bytes(B, world) bytes: (max, sum) pairs [2 directions][2*nCB][world*B]), 32 flag
  * words (zero before first use).  `epoch` is a LOCAL device word, zero before first use.  The phases that produce
- * features and LSEs store them straight into every rank's gathered buffers (posted stores over NVLink) and the
+ * features and softmax partials store them straight into every rank's gathered buffers (posted stores over NVLink) and the
  * grid barrier that follows also spans the ranks (flag words, st.release.sys / ld.acquire.sys): no exchange
- * kernel, no NCCL.  Outputs are this rank's PARTIAL sums (out5 scaled by 1/(world*B), gradients of the
- * replicated parameters): the caller sums them over the ranks (cvcl_peer_allreduce_push_f32 when they live in
- * symmetric memory), which also fences the reuse of the gathered buffers by the next step; a forward-only caller
- * issues cvcl_peer_barrier instead.  Every rank must call with the same shapes.  world = 1 is allowed. */
+ * kernel, no NCCL.  Gradient sum: with peer_stats / peer_scratch (HOST arrays of `world` device pointers: rank p's
+ * block [out5(8) | ds(4) | db(E) | d table(V*E) | dW(E*K)] floats and rank p's scratch of
+ * cvcl_flat_fused_sharded_scratch_bytes(...) bytes, both in symmetric memory) and reduce_floats > 0 (8 = the five
+ * scalars only, or 8 + 4 + E + V*E + E*K), the kernel sums the block over the ranks itself: every 128 x 128 tile of
+ * dW / d table is owned by rank (tile % world); the tile GEMMs store their partial tiles straight into the owner's
+ * scratch (TMA store over NVLink), the owner adds the partials in rank order (bit-identical on every rank) and
+ * stores the sum into every rank's block; scalars and d bias go one-shot.  out5, dscale, dbias, dtable, dW must
+ * then be this rank's pointers INTO peer_stats[rank] at those offsets.  The closing cross-rank barrier fences the
+ * reuse of every exchange buffer by the next step.  With reduce_floats = 0 (tables may
+ * be null) the outputs are this rank's PARTIAL sums (out5 scaled by 1/(world*B)) and the caller sums them
+ * (cvcl_peer_allreduce_push_f32), which is then also the fence.  Every rank must call with the same shapes.
+ * world = 1 is allowed (nothing crosses a link). */
 int cvcl_flat_fused_sharded_supported(int B, int L, int E, int K, int V, int world);
 size_t cvcl_flat_fused_sharded_workspace_bytes(int B, int L, int E, int K, int V, int world);
+size_t cvcl_flat_fused_sharded_part_bytes(int B, int world);
+size_t cvcl_flat_fused_sharded_scratch_bytes(int B, int L, int E, int K, int V, int world);
 int cvcl_flat_step_fused_sharded(const void* x16, const void* w16, const int64_t* ids, const int64_t* lens,
                                  const float* bias, const float* table, int B, int L, int E, int K, int V,
                                  int normalize, float log_scale, const float* log_scale_dev, int need_grads,
                                  void* workspace, float* out5, float* img_feat_f32, float* txt_feat_f32,
                                  float* dW, float* dbias, float* dtable, float* dscale, int* status, int phase_limit,
                                  int world, int rank, void* const* peer_txt_all, void* const* peer_img_all,
-                                 void* const* peer_lse_all, void* const* peer_flags, unsigned int* epoch,
+                                 void* const* peer_part_all, void* const* peer_flags, unsigned int* epoch,
+                                 void* const* peer_stats, void* const* peer_scratch, long long reduce_floats,
                                  void* stream);
 
 /* ---- K6 spatial "max" similarity --------------------------------------------------------------

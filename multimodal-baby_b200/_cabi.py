@@ -62,8 +62,11 @@ PROTOTYPES = {
                                      _P, _P, _P, _P, _P, _P, _I, _P]),
     "cvcl_flat_fused_sharded_supported": (c_int, [_I, _I, _I, _I, _I, _I]),
     "cvcl_flat_fused_sharded_workspace_bytes": (c_size_t, [_I, _I, _I, _I, _I, _I]),
+    "cvcl_flat_fused_sharded_part_bytes": (c_size_t, [_I, _I]),
+    "cvcl_flat_fused_sharded_scratch_bytes": (c_size_t, [_I, _I, _I, _I, _I, _I]),
     "cvcl_flat_step_fused_sharded": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _I, _P, _P, _P,
-                                             _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+                                             _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P,
+                                             _L, _P]),
     "cvcl_spatial_max_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "cvcl_spatial_max_bwd_workspace_bytes": (c_size_t, [_I, _I, _I, _I]),
     "cvcl_spatial_max_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),

@@ -661,6 +661,7 @@ const char* plan_fused(FusedPlan* f, int B, int E, int K, int V, int world = 1) 
     if (V < 1) return "V < 1";
     if (world != 1 && world != 2 && world != 4 && world != 8) return "world size must be 1, 2, 4 or 8";
     if (world > 1 && B % 128 != 0) return "sharded: pairs per rank must be a multiple of 128";
+    if (world > 1 && K % 128 != 0) return "sharded: K must be a multiple of 128";
     f->grid = G;
     f->Bp = ceil_div(B, 128) * 128;
     f->nMB = f->Bp / 128; f->nEB = E / 128;
@@ -675,6 +676,10 @@ const char* plan_fused(FusedPlan* f, int B, int E, int K, int V, int world = 1) 
     f->QS = 1;                                   // CTAs per similarity tile: the largest divisor of E/128 that fits
     for (int d = f->nEB; d >= 1; --d)
         if (f->nEB % d == 0 && n_tiles * d <= G) { f->QS = d; break; }
+    if (const char* e = getenv("CVCL_B200_FUSED_FORCE_QS")) {                  // test hook (the 8-rank layout: QS = 1)
+        const int d = atoi(e);
+        if (d >= 1 && f->nEB % d == 0 && n_tiles * d <= G) f->QS = d;
+    }
     const int tiles = f->nMB * f->nEB;
     if (tiles > G) return "batch too large for the head phase";
     f->num_kc = K / 64;
@@ -710,9 +715,12 @@ struct FusedShard {
     int world, rank;
     void* const* peer_txt_all;      // [world] rank p's gathered text features  [world*B, E] bf16
     void* const* peer_img_all;      // [world] rank p's gathered image features [world*B, E] bf16
-    void* const* peer_lse_all;      // [world] rank p's gathered LSEs [2, world*B] fp32
+    void* const* peer_part_all;     // [world] rank p's gathered softmax partials [2][2*nCB][world*B] float2
     void* const* peer_flags;        // [world] rank p's flag words (32 x u32, zero before first use)
     unsigned int* epoch;            // local u32, zero before first use
+    void* const* peer_stats;        // [world] rank p's block [out5 | ds | db | d table | dW] (nullable: no in-kernel sum)
+    void* const* peer_scratch;      // [world] rank p's scatter scratch
+    long long reduce_floats;        // floats of the block to sum over the ranks in the kernel (0: none)
 };
 }  // namespace
 
@@ -776,15 +784,36 @@ static int flat_step_fused_impl(const void* x16, const void* w16, const int64_t*
         // gathered buffers in peer-mapped symmetric memory: kf16[0] = all texts, kf16[1] = all images; the local
         // features are the slice [rank*B, rank*B + B) of this rank's own copies
         for (int r = 0; r < world; ++r) {
-            CVCL_REQUIRE(sh->peer_txt_all[r] && sh->peer_img_all[r] && sh->peer_lse_all[r] && sh->peer_flags[r],
+            CVCL_REQUIRE(sh->peer_txt_all[r] && sh->peer_img_all[r] && sh->peer_part_all[r] && sh->peer_flags[r],
                          "flat_step_fused: null peer pointer %d", r);
             p.peer_kf[0][r] = static_cast<__nv_bfloat16*>(sh->peer_txt_all[r]);
             p.peer_kf[1][r] = static_cast<__nv_bfloat16*>(sh->peer_img_all[r]);
-            p.peer_lse[0][r] = static_cast<float*>(sh->peer_lse_all[r]);
-            p.peer_lse[1][r] = static_cast<float*>(sh->peer_lse_all[r]) + p.Bg;
+            p.peer_part[0][r] = static_cast<float2*>(sh->peer_part_all[r]);
+            p.peer_part[1][r] = static_cast<float2*>(sh->peer_part_all[r]) + static_cast<size_t>(2) * f.nCB * p.Bg;
             p.peer_flags[r] = static_cast<unsigned int*>(sh->peer_flags[r]);
         }
         p.epoch = sh->epoch;
+        if (sh->reduce_floats > 0 && world > 1) {
+            const int n_tiles5 = f.nEB * (K / 128) + ceil_div(V, 128) * f.nEB;
+            p.nslot = ceil_div(n_tiles5, world);
+            p.reduce = 1;
+            CVCL_REQUIRE(sh->peer_stats && sh->peer_scratch, "flat_step_fused: null gradient-sum table");
+            CVCL_REQUIRE(sh->reduce_floats % 4 == 0, "flat_step_fused: reduce_floats must be a multiple of 4");
+            const long long n_g = 4ll + E + static_cast<long long>(V) * E + static_cast<long long>(E) * K;
+            CVCL_REQUIRE(sh->reduce_floats == 8 || (need_grads && sh->reduce_floats == 8 + n_g),
+                         "flat_step_fused: reduce_floats must be 8 or 8 + the gradient block (%lld)", 8 + n_g);
+            for (int r = 0; r < world; ++r) {
+                CVCL_REQUIRE(sh->peer_stats[r] && sh->peer_scratch[r], "flat_step_fused: null gradient-sum pointer %d", r);
+                p.peer_stats[r] = static_cast<float*>(sh->peer_stats[r]);
+                p.peer_scratch[r] = static_cast<float*>(sh->peer_scratch[r]);
+                p.peer_small[r] = p.peer_scratch[r] + static_cast<size_t>(world) * p.nslot * 128 * 128;
+            }
+            float* blk = p.peer_stats[rank];
+            CVCL_REQUIRE(out5 == blk, "flat_step_fused: out5 must be the start of this rank's block");
+            CVCL_REQUIRE(!need_grads || (dscale == blk + 8 && dbias == blk + 12 && dtable == blk + 12 + E &&
+                                         dW == blk + 12 + E + static_cast<size_t>(V) * E),
+                         "flat_step_fused: gradient outputs must lie in this rank's block (layout [out5|ds|db|dtable|dW])");
+        }
         p.kf16[0] = p.peer_kf[0][rank]; p.kf16[1] = p.peer_kf[1][rank];
         p.q16[0] = p.peer_kf[1][rank] + static_cast<size_t>(p.diag_off) * E;
         p.q16[1] = p.peer_kf[0][rank] + static_cast<size_t>(p.diag_off) * E;
@@ -800,7 +829,7 @@ static int flat_step_fused_impl(const void* x16, const void* w16, const int64_t*
         p.part[z] = reinterpret_cast<RowStat*>(ws + f.off_part) + static_cast<size_t>(z) * 2 * f.nCB * f.Bp;
         p.diag[z] = reinterpret_cast<float*>(ws + f.off_diag) + z * f.Bp;
         p.lse[z] = reinterpret_cast<float*>(ws + f.off_lse) + z * f.Bp;
-        p.lse_all[z] = (sh && world > 1) ? p.peer_lse[z][rank] : nullptr;
+        p.part_all[z] = (sh && world > 1) ? p.peer_part[z][rank] : nullptr;
     }
     p.rb_part = reinterpret_cast<float*>(ws + f.off_rbpart);
     p.dspart = reinterpret_cast<float*>(ws + f.off_dspart);
@@ -820,14 +849,15 @@ static int flat_step_fused_impl(const void* x16, const void* w16, const int64_t*
     // the 16 tensor maps depend only on the pointers and the shape: a training loop passes the same ones every
     // step (torch's caching allocator hands back the same blocks), so the last set is kept per host thread
     struct MapKey { const void* x16; const void* w16; void* ws; float* dW; float* dtable; const void* kf0; const void* kf1;
-                    int B, E, K, V, need, world, rank, T; };
+                    const void* scr[8]; int B, E, K, V, need, world, rank, T, reduce; };
     static thread_local MapKey last_key{};
     static thread_local fused::StepMaps maps;
     static thread_local bool maps_valid = false;
     MapKey key{};                                    // zero the padding: the key is compared with memcmp
     key.x16 = x16; key.w16 = w16; key.ws = workspace; key.dW = dW; key.dtable = dtable; key.kf0 = p.kf16[0];
     key.kf1 = p.kf16[1]; key.B = B; key.E = E; key.K = K; key.V = V; key.need = need_grads; key.world = world;
-    key.rank = rank; key.T = f.T;
+    key.rank = rank; key.T = f.T; key.reduce = p.reduce;
+    if (p.reduce) for (int r = 0; r < world; ++r) key.scr[r] = p.peer_scratch[r];
     int rc;
     if (!maps_valid || memcmp(&key, &last_key, sizeof(MapKey)) != 0) {
         maps_valid = false;
@@ -897,18 +927,36 @@ size_t cvcl_flat_fused_sharded_workspace_bytes(int B, int L, int E, int K, int V
     return plan_fused(&f, B, E, K, V, world) == nullptr ? f.bytes : 0;
 }
 
+size_t cvcl_flat_fused_sharded_scratch_bytes(int B, int L, int E, int K, int V, int world) {
+    (void)L;
+    FusedPlan f{};
+    if (plan_fused(&f, B, E, K, V, world) != nullptr || world < 2) return 0;
+    const int n_tiles5 = f.nEB * (K / 128) + ceil_div(V, 128) * f.nEB;
+    const size_t nslot = ceil_div(n_tiles5, world);
+    return align_up(static_cast<size_t>(world) * nslot * 128 * 128 * 4 + static_cast<size_t>(world) * fused::kSmall * 4, 256);
+}
+
+size_t cvcl_flat_fused_sharded_part_bytes(int B, int world) {
+    if (B < 1 || world < 1) return 0;
+    const size_t nCB = static_cast<size_t>(world) * ceil_div(B, 128);
+    return 2 * (2 * nCB) * (static_cast<size_t>(world) * B) * sizeof(float2);
+}
+
 int cvcl_flat_step_fused_sharded(const void* x16, const void* w16, const int64_t* ids, const int64_t* lens,
                                  const float* bias, const float* table, int B, int L, int E, int K, int V,
                                  int normalize, float log_scale, const float* log_scale_dev, int need_grads,
                                  void* workspace, float* out5, float* img_feat_f32, float* txt_feat_f32,
                                  float* dW, float* dbias, float* dtable, float* dscale, int* status, int phase_limit,
                                  int world, int rank, void* const* peer_txt_all, void* const* peer_img_all,
-                                 void* const* peer_lse_all, void* const* peer_flags, unsigned int* epoch,
+                                 void* const* peer_part_all, void* const* peer_flags, unsigned int* epoch,
+                                 void* const* peer_stats, void* const* peer_scratch, long long reduce_floats,
                                  void* stream) {
-    CVCL_REQUIRE(peer_txt_all && peer_img_all && peer_lse_all && peer_flags && epoch,
+    CVCL_REQUIRE(peer_txt_all && peer_img_all && peer_part_all && peer_flags && epoch,
                  "flat_step_fused_sharded: null peer table");
     CVCL_REQUIRE(world >= 1 && world <= 8, "flat_step_fused_sharded: world size %d", world);
-    FusedShard sh{world, rank, peer_txt_all, peer_img_all, peer_lse_all, peer_flags, epoch};
+    CVCL_REQUIRE(reduce_floats >= 0, "flat_step_fused_sharded: reduce_floats < 0");
+    FusedShard sh{world, rank, peer_txt_all, peer_img_all, peer_part_all, peer_flags, epoch, peer_stats, peer_scratch,
+                  reduce_floats};
     return flat_step_fused_impl(x16, w16, ids, lens, bias, table, B, L, E, K, V, normalize, log_scale, log_scale_dev,
                                 need_grads, workspace, out5, img_feat_f32, txt_feat_f32, dW, dbias, dtable, dscale, status,
                                 phase_limit, &sh, stream);

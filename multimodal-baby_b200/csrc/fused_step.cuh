@@ -31,7 +31,7 @@
 //       ds / db in a fixed order.
 //
 // Sharded use enters through the same code: Q = the local pairs, K = the gathered features,
-// diag_off = rank * B (see StepParams::kf16 / lse_all).
+// diag_off = rank * B (see StepParams::kf16 / part_all).
 #pragma once
 #include "gemm_sm100.cuh"
 #include "kernels_simt.cuh"
@@ -60,6 +60,7 @@ constexpr int kMiscBytes = 20480;
 constexpr int kSmemBytes = kMiscOff + kMiscBytes + 1024;     // + alignment slack
 constexpr int kMaxT = 2;                         // similarity tiles per CTA (same row block)
 constexpr int kNumSync = 8;
+constexpr int kSmall = 8 + 4 + 512 + 4;          // out5 | ds | d bias (E <= 512), padded: one-shot exchange block per rank
 
 struct alignas(64) StepMaps {
     CUtensorMap x_k;         // x16   [B, K]        box 64 x 128   (P0 A)
@@ -101,16 +102,32 @@ struct StepParams {
     RowStat* part[2];                    // [nCB][Bp]
     float* diag[2];                      // [Bp] logit at the positive
     float* lse[2];                       // [Bp] (local rows)
-    const float* lse_all[2];             // [Bg] LSEs of every row of direction z, gathered (sharded only; null on one GPU)
+    // sharded only (null on one GPU): the (max, sum) softmax partials of EVERY row of direction z, gathered:
+    // part_all[z][partial 0..2*nCB)[global row 0..Bg) -- P2 stores its partials into every rank's copy, so the column
+    // LSEs of P3 (rows that other ranks own) need no exchange phase of their own
+    const float2* part_all[2];
     // ---- sharding: rank `rank` of `world` owns pairs [diag_off, diag_off + B) of the global batch.
     // Every rank maps every rank's gathered buffers (symmetric memory over NVLink): the phases that PRODUCE
     // features / LSEs store them straight into all ranks' buffers, and the grid barrier that follows carries a
     // cross-rank stage.  world == 1: the tables hold the local buffers and nothing crosses a link.
     int world, rank;
     __nv_bfloat16* peer_kf[2][8];        // [z][p]: rank p's gathered key features of direction z ([Bg, ldk])
-    float* peer_lse[2][8];               // [z][p]: rank p's lse_all[z]
+    float2* peer_part[2][8];             // [z][p]: rank p's part_all[z]
     unsigned int* peer_flags[8];         // rank p's flag words [4 stages][8 source ranks], epochs only grow
     unsigned int* epoch;                 // local: launches completed so far (this launch signals epoch + 1)
+    // gradient sum over the ranks inside the kernel (sharded, reduce != 0).  Tile t of P5 (a 128 x 128 fp32 block of
+    // dW or d table) is OWNED by rank t % world: every rank stores its partial tile straight from P5's epilogue into
+    // the owner's scratch [source rank][slot t / world][128][128] (row stores over NVLink), a cross-rank barrier
+    // follows, the owner adds the `world` partials in RANK order (bit-identical everywhere) and stores the sum into
+    // the final dW / d table of EVERY rank (peer_stats[q] = rank q's block [out5(8) | ds(4) | db(E) | d table | dW]);
+    // the closing cross-rank barrier makes the sums visible and fences the reuse of all exchange buffers.  The
+    // scalars and d bias (8 + 4 + E floats) go one-shot: each rank stores its partials into slot `rank` of every
+    // rank's peer_small [world][kSmall] and adds them up locally.
+    float* peer_stats[8];
+    float* peer_scratch[8];
+    float* peer_small[8];
+    int reduce;                          // 0: outputs are this rank's partial sums; 1: summed over the ranks in P6
+    int nslot;                           // scratch slots per source rank = ceil(P5 tiles / world)
     float* rb_part;                      // [2*nMB][6]
     float* dspart;                       // [nMB*nPart]
     float* dqpart;                       // [2][nPart][Bp][E]
@@ -321,6 +338,33 @@ CVCL_HELPER void merge_stats(const RowStat* base, size_t stride, int n, float& g
             }
         }
     }
+}
+
+__device__ __forceinline__ uint4 ld_relaxed_sys_v4(const uint4* q) {
+    uint4 v;
+    asm volatile("ld.global.relaxed.sys.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(q) : "memory");
+    return v;
+}
+
+// log-sum-exp of one row from its gathered (max, sum) partials
+CVCL_HELPER float merge_ml(const float2* base, size_t stride, int n) {
+    float gm = -INFINITY, gl = 0.f;
+    for (int t0 = 0; t0 < n; t0 += 8) {
+        float2 q[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (t0 + k < n) q[k] = __ldcg(base + static_cast<size_t>(t0 + k) * stride);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (t0 + k < n) {
+                const float rm = q[k].x, rl = q[k].y;
+                if (rm > gm) { gl = gl * __expf(gm - rm) + rl; gm = rm; }
+                else gl = fmaf(rl, __expf(rm - gm), gl);
+            }
+        }
+    }
+    return gm + logf(gl);
 }
 
 #define CVCL_STAMP(i) do { if (cta == 0 && p.timing) p.timing[i] = globaltimer_ns(); } while (0)
@@ -639,7 +683,12 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const __grid_constant__ 
                     }
                     if (m < M) {
                         RowStat rs; rs.m = mx * scale; rs.l = l; rs.a = a * scale; rs.arg = arg;
-                        p.part[z][static_cast<size_t>((pi * p.T + j) * 2 + half) * p.Bp + m] = rs;
+                        const int pidx = (pi * p.T + j) * 2 + half;
+                        p.part[z][static_cast<size_t>(pidx) * p.Bp + m] = rs;
+                        if (p.world > 1) {              // (max, sum) of this row's partial -> every rank's gathered copy
+                            const size_t o = static_cast<size_t>(pidx) * p.Bg + p.diag_off + m;
+                            for (int pp = 0; pp < p.world; ++pp) p.peer_part[z][pp][o] = make_float2(rs.m, rs.l);
+                        }
                     }
                 }
             }
@@ -647,46 +696,35 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const __grid_constant__ 
             if (threadIdx.x == 64) CVCL_STAMP(21);
         }
         if (has) ++tfull_uses;
-        grid_sync<false>(p, sync_k++);
+        grid_sync<false>(p, sync_k++, 1, xepoch);          // sharded: every rank's softmax partials are in place behind this
         if (p.phase_limit == 3) goto done;
-
-        if (p.world > 1) {
-            // ---- sharded only: the LSEs of this rank's rows (both directions) go to every rank, because the
-            // column terms of dL/dlogits need the LSE of rows that other ranks own.  The lead CTA of
-            // each row block merges the partials and stores 128 floats per peer; then a cross-rank barrier.
-            if (has && pi == 0 && qs == 0 && half == 0 && m < M) {
-                float gm, gl, ga; int garg;
-                merge_stats(p.part[z] + m, p.Bp, 2 * p.nCB, gm, gl, ga, garg);
-                const float lse_row = gm + logf(gl);
-                for (int pp = 0; pp < p.world; ++pp) p.peer_lse[z][pp][p.diag_off + m] = lse_row;
-            }
-            grid_sync<false>(p, sync_k++, 1, xepoch);
-        }
 
         // ======================================================================== P3
         const int wq = p.E / p.QS;                          // dQ columns of this CTA: [qs*wq, qs*wq + wq)
         const int nH = (wq + 255) / 256;
         const int num_kc3 = 2 * p.T;
-        if (has && p.need_grads && warp == 0 && lane == 0) {
-            // the key-feature slabs of the dQ GEMM do not depend on anything computed in this phase: fetch now
-            for (int kc = 0; kc < num_kc3; ++kc)
-                for (int h = 0; h < nH; ++h) {
-                    const int nh = min(256, wq - 256 * h);
-                    mbar_wait_b(&empty_bar[ring.stage], ring.phase ^ 1u);
-                    unsigned char* sb = smem + ring.stage * kStageBytes;
-                    ptx::mbar_arrive_expect_tx(&full_bar[ring.stage], static_cast<uint32_t>(nh) * 128);
-                    const int crow = (pi * p.T + (kc >> 1)) * 128 + (kc & 1) * 64;
-                    for (int jb = 0; jb < nh / 64; ++jb)
-                        ptx::tma_load_2d(sb + jb * 8192, &maps.kf_mn[z], &full_bar[ring.stage],
-                                         qs * wq + 256 * h + 64 * jb, crow);
-                    ring.next();
-                }
-        }
+        // the key-feature slabs of the dQ GEMM do not depend on anything computed in this phase: the producer fetches
+        // as many as the ring holds NOW and the rest after its share of the Gs pass (it is an epilogue thread too:
+        // waiting here for a slot that only the MMA can free -- which waits for the Gs pass -- would deadlock)
+        const int n_fill3 = num_kc3 * nH;
+        auto fill3 = [&](int idx) {
+            const int kc = idx / nH, h = idx % nH;
+            const int nh = min(256, wq - 256 * h);
+            mbar_wait_b(&empty_bar[ring.stage], ring.phase ^ 1u);
+            unsigned char* sb = smem + ring.stage * kStageBytes;
+            ptx::mbar_arrive_expect_tx(&full_bar[ring.stage], static_cast<uint32_t>(nh) * 128);
+            const int crow = (pi * p.T + (kc >> 1)) * 128 + (kc & 1) * 64;
+            for (int jb = 0; jb < nh / 64; ++jb)
+                ptx::tma_load_2d(sb + jb * 8192, &maps.kf_mn[z], &full_bar[ring.stage], qs * wq + 256 * h + 64 * jb, crow);
+            ring.next();
+        };
+        if (has && p.need_grads && warp == 0 && lane == 0)
+            for (int idx = 0; idx < min(n_fill3, kStages); ++idx) fill3(idx);
         __syncwarp();
         if (has) {
             // (a) half 0: the LSE of this thread's ROW (+ cross-entropy / entropy / accuracy terms on the lead
-            //     CTA); half 1: the LSE of COLUMN `row` of the tile = a row of the other direction (one GPU:
-            //     merged here from its partials; sharded: gathered beforehand into lse_all).  Both halves run
+            //     CTA); half 1: the LSE of COLUMN `row` of the tile = a row of the other direction, merged here from
+            //     its partials (one GPU: the local ones; sharded: the gathered (max, sum) pairs).  Both halves run
             //     at the same time on different warps: one round trip to L2 instead of three.
             const bool lead = pi == 0 && qs == 0;
             const float w = scale * (0.5f * p.inv_rows);             // exp(s) * coef
@@ -713,7 +751,7 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const __grid_constant__ 
                     float lkv = INFINITY;
                     if (n < N) {
                         float lse_c;
-                        if (p.lse_all[1 - z]) lse_c = __ldcg(p.lse_all[1 - z] + n);
+                        if (p.part_all[1 - z]) lse_c = merge_ml(p.part_all[1 - z] + n, p.Bg, 2 * p.nCB);
                         else {
                             float cm_, cl_, ca_; int carg_;
                             merge_stats(p.part[1 - z] + n, p.Bp, 2 * p.nCB, cm_, cl_, ca_, carg_);
@@ -783,6 +821,8 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const __grid_constant__ 
                     ds = warp_sum(ds);
                     if (lane == 0) red[32 + warp] = ds;
                 }
+                if (warp == 0 && lane == 0)
+                    for (int idx = kStages; idx < n_fill3; ++idx) fill3(idx);      // slots free up as the MMAs retire
                 if (warp == 1 && lane == 0) {
                     mbar_wait_b(gs_bar, 0);                 // single use per launch
                     ptx::tc_fence_after();
@@ -992,7 +1032,22 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const __grid_constant__ 
                 ptx::fence_proxy_async_smem();
                 ptx::tc_fence_before();
                 __syncthreads();
-                if (threadIdx.x == 64) {
+                if (p.reduce) {
+                    // partial tile -> scratch of the rank that owns tile t: every warp copies 16 rows out of the staging
+                    // boxes with 512-byte row stores (posted stores over NVLink; measured faster than a TMA store to peer
+                    // memory, which drained at ~270 GB/s)
+                    float* dstt = p.peer_scratch[t % p.world] +
+                                  static_cast<size_t>(p.rank * p.nslot + t / p.world) * 128 * 128;
+#pragma unroll
+                    for (int i = 0; i < 16; i += 8) {
+                        uint4 v[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) v[k] = swz_ld16(smem, warp * 16 + i + k, lane * 16);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            *reinterpret_cast<uint4*>(dstt + (warp * 16 + i + k) * 128 + lane * 4) = v[k];
+                    }
+                } else if (threadIdx.x == 64) {
                     if (is_dw) {
                         for (int b4 = 0; b4 < tn / 32; ++b4)
                             ptx::tma_store_2d(&maps.dw_out, smem + b4 * 16384, ot * bn + b4 * 32, eb * 128);
@@ -1011,42 +1066,141 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const __grid_constant__ 
         }
     }
 
-    // ---- final sums by the last CTA, every one in a fixed order (deterministic)
+    // ---- final sums by the last CTA, every one in a fixed order (deterministic).  This CTA is the tail of the
+    // kernel, so every partial is fetched with independent loads (one or two round trips to L2), never one
+    // dependent load per addend.
     if (cta == G - 1) {
+        float* fs = reinterpret_cast<float*>(smem);                      // the ring is idle: this CTA ran no P5 tile
+        const int n_rb = 2 * p.nMB * 6, n_ds = p.need_grads ? p.nMB * p.nPart : 0;
+        for (int i = threadIdx.x; i < n_rb + n_ds; i += kThreads)
+            fs[i] = i < n_rb ? __ldcg(p.rb_part + i) : __ldcg(p.dspart + (i - n_rb));
+        float* dbs = fs + 1024;                                          // [2][512]
+        if (p.need_grads) {
+            // d bias: per-CTA partials of P4 in CTA order; only the CTAs that held image rows there contribute
+            // (tasks [B, 2B) of P4's warp-per-row schedule) unless the schedule wrapped around the grid
+            const bool wrapped = 2 * p.B > G * kWarps;
+            const int c_lo = wrapped ? 0 : p.B / kWarps;
+            const int c_hi = wrapped ? G : (2 * p.B + kWarps - 1) / kWarps;
+            const int col4 = threadIdx.x & 127, grp = threadIdx.x >> 7;  // two interleaved row groups
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col4 * 4 < p.E) {
+                for (int c0 = c_lo + grp; c0 < c_hi; c0 += 16) {
+                    float4 v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int c = c0 + 2 * k;
+                        v[k] = c < c_hi ? __ldcg(reinterpret_cast<const float4*>(p.dbpart + static_cast<size_t>(c) * p.E) + col4)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
+                }
+                *reinterpret_cast<float4*>(dbs + grp * 512 + col4 * 4) = acc;
+            }
+        }
+        __syncthreads();
+        float* fin = fs + 2048;                                          // [kSmall]: out5(8) | ds(4) | d bias
+        if (p.need_grads)
+            for (int e = threadIdx.x; e < p.E; e += kThreads) fin[12 + e] = dbs[e] + dbs[512 + e];
         if (threadIdx.x == 0) {
             float s6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             for (int b = 0; b < 2 * p.nMB; ++b) {
                 const int z = b / p.nMB;
-                s6[z] += __ldcg(p.rb_part + b * 6 + z);
-                s6[2 + z] += __ldcg(p.rb_part + b * 6 + 2 + z);
-                s6[4 + z] += __ldcg(p.rb_part + b * 6 + 4 + z);
+                s6[z] += fs[b * 6 + z];
+                s6[2 + z] += fs[b * 6 + 2 + z];
+                s6[4 + z] += fs[b * 6 + 4 + z];
             }
-            p.out5[0] = (s6[0] + s6[1]) * 0.5f * p.inv_rows;
-            p.out5[1] = s6[4] * p.inv_rows;
-            p.out5[2] = s6[5] * p.inv_rows;
-            p.out5[3] = s6[2] * p.inv_rows;
-            p.out5[4] = s6[3] * p.inv_rows;
-            if (p.need_grads) {
-                float ds = 0.f;
-                for (int i = 0; i < p.nMB * p.nPart; ++i) ds += __ldcg(p.dspart + i);
-                p.dscale[0] = ds;
+            fin[0] = (s6[0] + s6[1]) * 0.5f * p.inv_rows;
+            fin[1] = s6[4] * p.inv_rows;
+            fin[2] = s6[5] * p.inv_rows;
+            fin[3] = s6[2] * p.inv_rows;
+            fin[4] = s6[3] * p.inv_rows;
+            fin[5] = fin[6] = fin[7] = 0.f;
+            float ds = 0.f;
+            for (int i = 0; i < n_ds; ++i) ds += fs[n_rb + i];
+            fin[8] = ds; fin[9] = fin[10] = fin[11] = 0.f;
+        }
+        __syncthreads();
+        const int n_fin = p.need_grads ? 12 + p.E : 8;
+        if (p.reduce) {                                  // this rank's partials -> slot `rank` of every rank's block
+            for (int i = threadIdx.x; i < n_fin; i += kThreads) {
+                const float v = fin[i];
+                for (int pp = 0; pp < p.world; ++pp) p.peer_small[pp][p.rank * kSmall + i] = v;
+            }
+        } else {
+            for (int i = threadIdx.x; i < n_fin; i += kThreads) {
+                const float v = fin[i];
+                if (i < 5) p.out5[i] = v;
+                else if (i == 8) p.dscale[0] = v;
+                else if (i >= 12) p.dbias[i - 12] = v;
             }
         }
+    }
+
+    if (p.reduce) {
+        // ======================================================================== P6 (sharded)
+        grid_sync<false>(p, sync_k++, 2, xepoch);          // every rank's partial tiles and scalars have landed here
+        // (a) scalars + d bias: one-shot, summed locally in rank order (CTA 0)
+        if (cta == 0) {
+            const int n_fin = p.need_grads ? 12 + p.E : 8;
+            const float* sm = p.peer_small[p.rank];
+            for (int i = threadIdx.x; i < n_fin; i += kThreads) {
+                float v = 0.f;
+                for (int q = 0; q < p.world; ++q) v += __ldcg(sm + q * kSmall + i);
+                if (i < 5) p.out5[i] = v;
+                else if (i == 8) p.dscale[0] = v;
+                else if (i >= 12) p.dbias[i - 12] = v;
+            }
+        }
+        // (b) the tiles this rank owns: one warp per tile row (512 bytes), `world` partials summed in rank order,
+        //     the sum stored into the final dW / d table of every rank
         if (p.need_grads) {
-            // d bias: per-CTA partials in CTA order, 8 independent loads in flight
-            for (int e = threadIdx.x; e < p.E; e += kThreads) {
-                float s = 0.f;
-                for (int b0 = 0; b0 < G; b0 += 8) {
-                    float v[8];
+            const int n_dw = p.nEB * (p.K / 128);
+            const int n_t = n_dw + ((p.V + 127) / 128) * p.nEB;
+            const int n_own = (n_t - p.rank + p.world - 1) / p.world;            // tiles rank, rank + world, ...
+            const size_t off_dt = 12 + static_cast<size_t>(p.E);
+            const size_t off_dw = off_dt + static_cast<size_t>(p.V) * p.E;
+            const float* scr = p.peer_scratch[p.rank];
+            const size_t src_stride = static_cast<size_t>(p.nslot) * 128 * 128;
+            constexpr int U = 4;
+            const int n_rows = n_own * 128;
+            for (int r0 = cta * kWarps + warp; r0 < n_rows; r0 += U * G * kWarps) {
+                float4 v[U][8];
+                size_t dst[U];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        v[k] = (b0 + k < G) ? __ldcg(p.dbpart + static_cast<size_t>(b0 + k) * p.E + e) : 0.f;
+                for (int u = 0; u < U; ++u) {
+                    const int r = r0 + u * G * kWarps;
+                    dst[u] = ~static_cast<size_t>(0);
+                    if (r < n_rows) {
+                        const int slot = r >> 7, rr = r & 127;
+                        const int t = slot * p.world + p.rank;
+                        const bool is_dw = t < n_dw;
+                        const int uu = is_dw ? t : t - n_dw;
+                        const int eb = uu % p.nEB, ot = uu / p.nEB;
+                        if (is_dw) dst[u] = off_dw + static_cast<size_t>(eb * 128 + rr) * p.K + ot * 128 + lane * 4;
+                        else if (ot * 128 + rr < p.V) dst[u] = off_dt + static_cast<size_t>(ot * 128 + rr) * p.E + eb * 128 + lane * 4;
+                        if (dst[u] != ~static_cast<size_t>(0)) {
+                            const float* src = scr + (static_cast<size_t>(slot) * 128 + rr) * 128 + lane * 4;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) s += v[k];
+                            for (int q = 0; q < 8; ++q)
+                                if (q < p.world) v[u][q] = __ldcg(reinterpret_cast<const float4*>(src + q * src_stride));
+                        }
+                    }
                 }
-                p.dbias[e] = s;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (dst[u] != ~static_cast<size_t>(0)) {
+                        float4 acc = v[u][0];
+#pragma unroll
+                        for (int q = 1; q < 8; ++q)
+                            if (q < p.world) { acc.x += v[u][q].x; acc.y += v[u][q].y; acc.z += v[u][q].z; acc.w += v[u][q].w; }
+                        for (int q = 0; q < p.world; ++q)
+                            *reinterpret_cast<float4*>(p.peer_stats[q] + dst[u]) = acc;
+                    }
+                }
             }
         }
+        grid_sync<false>(p, sync_k++, 3, xepoch);          // every rank's block holds the global sums behind this
     }
 
 done:

@@ -56,14 +56,43 @@ class GraphedContrastiveStep:
         if lagged_loss and not prefetch:
             raise ValueError("lagged_loss=True needs prefetch=True (two alternating graphs)")
         self.lagged = bool(lagged_loss)
+        # Staging buffers that are views of ONE pinned arena (staging.PinnedBatchStager / staging.packed_buffers)
+        # cross PCIe as a single copy per step; separately allocated tensors take three (each small copy adds
+        # ~4.5 us of latency: measured 53.7 us vs 44.5 us for the 2 MB of features alone).
+        from . import staging
+        span = staging.packed_span((x_host, ids_host, lens_host))
+
+        def byte_view(t, lo, n):
+            return torch.empty(0, dtype=torch.uint8, device=t.device).set_(t.untyped_storage(), lo, (n,))
+
+        def carve(arena, like, off):
+            nb = like.numel() * like.element_size()
+            return arena[off:off + nb].view(like.dtype).view(like.shape)
+
+        def new_set(device=None):
+            """a set of (x, ids, lens) buffers shaped like the caller's, on `device` or pinned; packed when the
+            caller's are.  -> (views, arena | None)"""
+            if span is None:
+                ts = tuple(torch.empty_like(t, device=device) if device is not None else torch.empty_like(t).pin_memory()
+                           for t in (x_host, ids_host, lens_host))
+                return ts, None
+            arena = torch.empty((span[1],), dtype=torch.uint8, device=device) if device is not None else \
+                torch.empty((span[1],), dtype=torch.uint8).pin_memory()
+            return tuple(carve(arena, t, o) for t, o in zip((x_host, ids_host, lens_host), span[2])), arena
+
         # pinned staging: one set per graph in lagged mode (the replay in flight may still be reading its set)
         self.host_sets = [(x_host, ids_host, lens_host)]
+        self._host_arenas = [byte_view(x_host, span[0], span[1]) if span is not None else None]
         if self.lagged:
-            self.host_sets.append(tuple(torch.empty_like(t).pin_memory() for t in (x_host, ids_host, lens_host)))
+            hs, ha = new_set()
+            self.host_sets.append(hs); self._host_arenas.append(ha)
             for dst, src in zip(self.host_sets[1], self.host_sets[0]):
                 dst.copy_(src)
-        self.bufs = [(torch.empty_like(x_host, device=dev), torch.empty_like(ids_host, device=dev),
-                      torch.empty_like(lens_host, device=dev)) for _ in range(nbuf)]
+        self.bufs, self._dev_arenas = [], []
+        for _ in range(nbuf):
+            ds_, da = new_set(dev)
+            self.bufs.append(ds_); self._dev_arenas.append(da)
+        self.packed = span is not None
         self.x, self.ids, self.lens = self.bufs[0]
         self.stats_bufs = [torch.zeros(8, dtype=torch.float32).pin_memory() for _ in range(nbuf)]
         self.stats_host = self.stats_bufs[0]
@@ -90,6 +119,11 @@ class GraphedContrastiveStep:
         self._opt_in_graph = optimizer is not None
 
         def h2d(buf, host):
+            if self.packed:                                # the whole batch in one copy
+                kb = next(i for i, b_ in enumerate(self.bufs) if b_ is buf)
+                kh = next(i for i, h_ in enumerate(self.host_sets) if h_ is host)
+                self._dev_arenas[kb].copy_(self._host_arenas[kh], non_blocking=True)
+                return
             buf[0].copy_(host[0], non_blocking=True)
             buf[1].copy_(host[1], non_blocking=True)
             buf[2].copy_(host[2], non_blocking=True)
@@ -197,8 +231,12 @@ class GraphedContrastiveStep:
 
     def prime(self):
         """prefetch mode: copy the batch currently staged in the pinned buffers into device buffer 0."""
-        for d, h in zip(self.bufs[0], self.host_sets[self.calls % len(self.host_sets)]):
-            d.copy_(h, non_blocking=True)
+        k = self.calls % len(self.host_sets)
+        if self.packed:
+            self._dev_arenas[0].copy_(self._host_arenas[k], non_blocking=True)
+        else:
+            for d, h in zip(self.bufs[0], self.host_sets[k]):
+                d.copy_(h, non_blocking=True)
         torch.cuda.current_stream(self.dev).synchronize()
         self.calls = 0
 

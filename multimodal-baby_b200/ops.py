@@ -836,11 +836,14 @@ def flat_step_sharded(x, ids, lens, w, bias, table, log_scale, normalize, need_g
     n_stats = 8 + (n_g if need_grads else 0)
     # the three collectives run over peer-mapped symmetric memory when available (sharding.PeerExchange):
     # the arena is sized for the training step and shared with the forward-only call
-    px = sharding.PeerExchange.get(group, B, E, 8 + n_g, dev) if world > 1 else None
-    if (px is not None and phase_limit is None and FUSED_STEP and _fused_env()
-            and lib.cvcl_flat_fused_sharded_supported(B, L, E, K, V, world)):
+    use_fused = (world > 1 and phase_limit is None and FUSED_STEP and _fused_env()
+                 and bool(lib.cvcl_flat_fused_sharded_supported(B, L, E, K, V, world)))
+    # (the one-kernel step keeps its per-tile gradient scratch in the same arena)
+    min_scr = int(lib.cvcl_flat_fused_sharded_scratch_bytes(B, L, E, K, V, world)) if use_fused else 0
+    px = sharding.PeerExchange.get(group, B, E, 8 + n_g, dev, min_scr) if world > 1 else None
+    if px is not None and use_fused:
         # ---- ONE persistent kernel per rank: the producing phases store features / LSEs into every rank's gathered
-        # buffers over NVLink and its grid barriers span the ranks; then one kernel sums the gradients
+        # buffers over NVLink, its grid barriers span the ranks, and its last phase sums the gradients over the ranks
         x16, _ = to_bf16_pair(x, False)
         w16 = weight_shadow(w_param)
         key = ("sharded", dev.index if dev.index is not None else torch.cuda.current_device(), B, L, E, K, V, world)
@@ -855,11 +858,12 @@ def flat_step_sharded(x, ids, lens, w, bias, table, log_scale, normalize, need_g
         C("cvcl_flat_step_fused_sharded", _p(x16), _p(w16), _p(ids), _p(lens), _p(bias), _p(table), B, L, E, K, V,
           int(normalize), float(log_scale), None, int(need_grads), _p(ws), _p(stats), _p(img_f), _p(txt_f),
           _p(dW) if need_grads else None, _p(db) if need_grads else None, _p(dtable) if need_grads else None,
-          _p(ds) if need_grads else None, None, 0, world, rank, px.p_txt_all, px.p_img_all, px.p_lse_all,
-          px.p_flags[px.CH_FUSED], px.fused_epoch.data_ptr(), st)
-        # partial sums -> global values on every rank (and the fence that lets the next step overwrite the gathered
-        # buffers); a forward-only step sums just the five scalars
-        px.allreduce_stats(stats_slot, n_stats if need_grads else 8, st)
+          _p(ds) if need_grads else None, None, 0, world, rank, px.p_txt_all, px.p_img_all, px.p_part_all,
+          px.p_flags[px.CH_FUSED], px.fused_epoch.data_ptr(),
+          # the kernel's last phase sums [out5 | ds | db | d table | dW] over the ranks in place (two-shot, push, fixed
+          # rank order) and its closing cross-rank barrier lets the next step overwrite the exchange buffers; a
+          # forward-only step sums just the five scalars
+          px.p_stats[stats_slot], px.p_scratch, n_stats if need_grads else 8, st)
         return stats[:n_stats], img_f, txt_f
     # [img | txt] per pair: one exchange moves both
     feats = px.feats if px is not None else torch.empty((B, 2 * E), **bf)

@@ -109,7 +109,7 @@ class PeerExchange:
     CH_FEATS, CH_LSE, CH_REDUCE, CH_BARRIER, CH_FUSED = 0, 1, 2, 3, 4
     N_SLOTS = 2          # stats blocks: alternating CUDA graphs keep the previous step's gradients readable
 
-    def __init__(self, group, b, E, n_stats, dev):
+    def __init__(self, group, b, E, n_stats, dev, min_scratch=0):
         import ctypes
         import torch.distributed._symmetric_memory as symm
         from . import _cabi
@@ -122,10 +122,11 @@ class PeerExchange:
         self.push = os.environ.get("CVCL_B200_PEER_MODE", "push") != "pull"
         Bg = self.world * b
         sizes = [("feats", b * 2 * E * 2), ("lse", 2 * b * 4), ("feats_all", Bg * 2 * E * 2), ("lse_all", 2 * Bg * 4),
-                 ("scratch", int(lib.cvcl_peer_allreduce_scratch_bytes(n_stats, self.world)))]
+                 ("scratch", max(int(lib.cvcl_peer_allreduce_scratch_bytes(n_stats, self.world)), int(min_scratch)))]
         # gathered features of the one-kernel sharded step (texts and images separately: each is the key operand of
         # one direction) and a fifth flag channel for its in-kernel cross-rank barriers
-        sizes += [("txt_all", Bg * E * 2), ("img_all", Bg * E * 2)]
+        part_bytes = int(lib.cvcl_flat_fused_sharded_part_bytes(b, self.world))
+        sizes += [("txt_all", Bg * E * 2), ("img_all", Bg * E * 2), ("part_all", part_bytes)]
         sizes += [("stats%d" % k, n_stats * 4) for k in range(self.N_SLOTS)] + [("flags", 5 * fw * 4)]
         off, total = {}, 0
         for name, nb in sizes:
@@ -158,7 +159,7 @@ class PeerExchange:
         self.p_flags = [table("flags", ch * fw * 4) for ch in range(5)]
         self.txt_all = view("txt_all", Bg * E * 2, torch.bfloat16).view(Bg, E)
         self.img_all = view("img_all", Bg * E * 2, torch.bfloat16).view(Bg, E)
-        self.p_txt_all, self.p_img_all = table("txt_all"), table("img_all")
+        self.p_txt_all, self.p_img_all, self.p_part_all = table("txt_all"), table("img_all"), table("part_all")
         self.fused_epoch = torch.zeros((1,), dtype=torch.int32, device=dev)
         self._self_test(group, dev)
 
@@ -209,7 +210,7 @@ class PeerExchange:
         dist.barrier(group=group)
 
     @classmethod
-    def get(cls, group, b, E, n_stats, dev):
+    def get(cls, group, b, E, n_stats, dev, min_scratch=0):
         if os.environ.get("CVCL_B200_SYMM", "1") == "0":
             return None
         world, _ = group_info(group)
@@ -220,10 +221,10 @@ class PeerExchange:
             gkey = (dist.get_process_group_ranks(group).__repr__(), getattr(group, "group_name", ""))
         except Exception:                        # noqa: BLE001
             gkey = id(group)
-        key = (gkey, b, E, n_stats, dev.index, os.environ.get("CVCL_B200_PEER_MODE", "push"))
+        key = (gkey, b, E, n_stats, dev.index, os.environ.get("CVCL_B200_PEER_MODE", "push"), int(min_scratch))
         if key not in cls._cache:
             try:
-                cls._cache[key] = cls(group, b, E, n_stats, dev)
+                cls._cache[key] = cls(group, b, E, n_stats, dev, min_scratch)
             except Exception as exc:             # noqa: BLE001  (no symmetric memory / failed self-test)
                 import warnings
                 warnings.warn("cvcl_b200: peer-memory exchange unavailable (%r); using the NCCL collectives" % (exc,))

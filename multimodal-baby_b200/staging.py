@@ -35,6 +35,46 @@ def multiModalDataset_collate_fn(batch):
     return img, utterance_idxs, utterance_length, list(raw_utterance)
 
 
+def packed_buffers(specs, pin=True, device=None, align=256):
+    """[(shape, dtype), ...] -> zero-initialised tensors that are views of ONE byte arena (each segment `align`-byte
+    aligned), pinned host memory by default or on `device`: a batch laid out like this crosses PCIe as one copy."""
+    offs, n = [], 0
+    for shape, dtype in specs:
+        n = (n + align - 1) // align * align
+        offs.append(n)
+        n += int(torch.Size(shape).numel()) * torch.empty((), dtype=dtype).element_size()
+    if device is not None:
+        arena = torch.zeros((n,), dtype=torch.uint8, device=device)
+    else:
+        arena = torch.zeros((n,), dtype=torch.uint8)
+        if pin:
+            arena = arena.pin_memory()
+    out = []
+    for (shape, dtype), o in zip(specs, offs):
+        nb = int(torch.Size(shape).numel()) * torch.empty((), dtype=dtype).element_size()
+        out.append(arena[o:o + nb].view(dtype).view(tuple(shape)))
+    return out
+
+
+def packed_span(tensors):
+    """If `tensors` are contiguous views of one storage, in ascending order and without big holes: (storage byte
+    offset of the first, total span in bytes, per-tensor offsets relative to the span); else None."""
+    try:
+        base = tensors[0].untyped_storage().data_ptr()
+        if any(t.untyped_storage().data_ptr() != base or not t.is_contiguous() for t in tensors):
+            return None
+        lo = [t.data_ptr() - base for t in tensors]
+        hi = [o + t.numel() * t.element_size() for o, t in zip(lo, tensors)]
+        if any(lo[i + 1] < hi[i] for i in range(len(lo) - 1)) or any((o - lo[0]) % 16 for o in lo):
+            return None
+        span = hi[-1] - lo[0]
+        if span > sum(h - l for l, h in zip(lo, hi)) + 4096 * len(tensors):
+            return None
+        return lo[0], span, [o - lo[0] for o in lo]
+    except (RuntimeError, IndexError):
+        return None
+
+
 class PinnedBatchStager:
     """Fixed-shape pinned staging buffers for `GraphedContrastiveStep(model, x_host, ids_host, lens_host)`.
 
@@ -54,13 +94,14 @@ class PinnedBatchStager:
                  pin: Optional[bool] = None):
         pin = torch.cuda.is_available() if pin is None else bool(pin)
 
-        def buf(shape, dtype):
-            t = torch.zeros(tuple(shape), dtype=dtype)
-            return t.pin_memory() if pin else t
         self.batch_size, self.max_len = int(batch_size), int(max_len)
-        self.ids_host = buf((batch_size, max_len), torch.int64)
-        self.lens_host = buf((batch_size,), torch.int64)
-        self.x_host = buf((batch_size,) + tuple(feat_shape), feat_dtype) if feat_shape is not None else None
+        # ONE pinned arena [x | ids | lens]: GraphedContrastiveStep recognises views of one storage and moves the
+        # whole batch with a single H2D copy (three separate copies cost ~4.5 us of latency each on top of the bytes)
+        specs = [((batch_size,) + tuple(feat_shape), feat_dtype)] if feat_shape is not None else []
+        specs += [((batch_size, max_len), torch.int64), ((batch_size,), torch.int64)]
+        views = packed_buffers(specs, pin=pin)
+        self.x_host = views[0] if feat_shape is not None else None
+        self.ids_host, self.lens_host = views[-2], views[-1]
 
     @torch.no_grad()
     def stage(self, utterance_idxs, utterance_length, feats: Optional[torch.Tensor] = None):

@@ -146,6 +146,22 @@ def test_two_tiles_per_cta_layout(cv, monkeypatch):
     assert rep["replay: all gradients bit-identical"], rep
 
 
+def test_eight_rank_tile_layout_on_one_gpu(cv, monkeypatch):
+    """T = 2 AND one CTA per similarity tile (QS = 1: the layout of 8 ranks x 512 pairs, where the dQ GEMM of P3 needs
+    eight operand slabs through a four-deep ring -- the producer must not wait for a slot before its share of the Gs
+    pass), forced on one GPU at 1024 pairs."""
+    import fused_check
+    monkeypatch.setenv("CVCL_B200_FUSED_FORCE_T", "2")
+    monkeypatch.setenv("CVCL_B200_FUSED_FORCE_QS", "1")
+    lay = cv.ops.fused_layout(1024, 25, 512, 2048, 2350)
+    assert lay["nPart"] * 2 == lay["nCB"] and lay["QS"] == 1
+    rep = fused_check.run(1024, 512, 2048, verbose=False)
+    assert rep["P3 dI (no diag term)"] <= 1e-2 and rep["P3 dT (no diag term)"] <= 1e-2, rep
+    assert abs(rep["loss"][0] - rep["loss"][1]) <= 1e-3 * abs(rep["loss"][1]), rep
+    assert rep["dW"] <= 2e-2 and rep["db"] <= 2e-2 and rep["dtable"] <= 2e-2, rep
+    assert rep["replay: all gradients bit-identical"], rep
+
+
 def test_sharded_entry_with_one_rank_equals_single_gpu_entry(cv):
     """cvcl_flat_step_fused_sharded with world = 1 (the peer tables name local buffers): the pointer plumbing of the
     sharded form -- gathered buffers, local slices, flag words, epoch -- gives bit-identical results."""
@@ -170,14 +186,14 @@ def test_sharded_entry_with_one_rank_equals_single_gpu_entry(cv):
     o2, flat2, (ds2, db2, dt2, dW2) = outputs()
     ws2 = torch.zeros(int(lib.cvcl_flat_fused_sharded_workspace_bytes(B, L, E, K, V, 1)), dtype=torch.uint8, device=DEV)
     txt_all = torch.zeros(B, E, dtype=torch.bfloat16, device=DEV); img_all = torch.zeros_like(txt_all)
-    lse_all = torch.zeros(2, B, **f32); flags = torch.zeros(32, dtype=torch.int32, device=DEV)
+    lse_all = torch.zeros(int(lib.cvcl_flat_fused_sharded_part_bytes(B, 1)) // 4, **f32); flags = torch.zeros(32, dtype=torch.int32, device=DEV)
     epoch = torch.zeros(1, dtype=torch.int32, device=DEV)
     arr = ctypes.c_void_p * 1
     for _ in range(2):                                   # twice: the epoch advances, the control block is reusable
         _cabi.call("cvcl_flat_step_fused_sharded", p(x16), p(w16), p(d["ids"]), p(d["lens"]), p(d["b"]), p(d["table"]),
                    B, L, E, K, V, 1, S_DEFAULT, None, 1, p(ws2), p(o2), None, None, p(dW2), p(db2), p(dt2), p(ds2), None, 0,
                    1, 0, arr(txt_all.data_ptr()), arr(img_all.data_ptr()), arr(lse_all.data_ptr()), arr(flags.data_ptr()),
-                   epoch.data_ptr(), st)
+                   epoch.data_ptr(), None, None, 0, st)
     torch.cuda.synchronize()
     assert int(epoch.item()) == 2
     assert torch.equal(o1[:5], o2[:5]) and torch.equal(flat1, flat2)

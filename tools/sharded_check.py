@@ -51,6 +51,24 @@ for (n, p1), (_, ps) in zip(model_1.named_parameters(), model_s.named_parameters
         continue
     r = rel(ps.grad, p1.grad)
     assert r <= 5e-3, (n, r)
+# (2b) the gradient sum runs in a fixed rank order: every rank holds bit-identical gradients
+sums = torch.stack([ps.grad.double().sum() for ps in model_s.parameters() if ps.grad is not None])
+allsums = [torch.empty_like(sums) for _ in range(world)]
+dist.all_gather(allsums, sums)
+for q in range(world):
+    assert torch.equal(allsums[q], allsums[0]), ("gradients differ between ranks", q)
+# (2c) forward-only sharded step (only the five scalars are summed over the ranks), then a training step again: the
+# two forms alternate on the same exchange buffers
+fw = model_s.image_embed.model.fc
+xs, is_, ls_ = (x_all[rank * 512:(rank + 1) * 512], ids_all[rank * 512:(rank + 1) * 512], lens_all[rank * 512:(rank + 1) * 512])
+st5, _, _ = m.ops.flat_step_sharded(xs, is_, ls_, fw.weight, fw.bias, model_s.text_embed.embedding.weight, S_FIXED,
+                                    True, False, False, dist.group.WORLD)
+assert abs(st5[0].item() - l1.item()) <= 2e-6 * abs(l1.item()), (st5[0].item(), l1.item())
+ls2 = step_api(model_s, xs, is_, ls_, world)
+assert abs(ls2.item() - ls.item()) <= 2e-6 * abs(ls.item()), (ls2.item(), ls.item())
+for (n, p1), (_, ps) in zip(model_1.named_parameters(), model_s.named_parameters()):
+    if p1.grad is not None:
+        assert rel(ps.grad, p1.grad) <= 5e-3, (n, rel(ps.grad, p1.grad))
 # (3) op-by-op sharded path (features -> sim_infonce with the group) + explicit gradient all-reduce
 _, model_o = build_model(dev, dist.group.WORLD)
 model_o.train_path = "ops"
