@@ -37,6 +37,12 @@ const char* cvcl_last_error(void);
 /* number of CUDA kernels this library has launched so far in the process (host-side counter). */
 unsigned long long cvcl_launch_count(void);
 
+/* Page-locked host staging memory for the per-step H2D copy (staging.PinnedBatchStager); write_combined != 0:
+ * cudaHostAllocWriteCombined -- the CPU only writes it, the DMA engine never has to snoop CPU caches.  NULL on
+ * failure (cvcl_last_error). */
+void* cvcl_host_alloc(size_t bytes, int write_combined);
+int cvcl_host_free(void* p);
+
 /* ---- K1 text encoder, embedding branch ------------------------------------------------
  * replaces TextEncoder.forward (multimodal.py:496-503,575-584) + F.normalize (:743).
  * per_token = 0 (flat): feat[b] = normalise(sum_l table[ids[b,l]] / len[b]).
@@ -87,6 +93,8 @@ int cvcl_rownorm_bwd(const float* g, const float* feat, const float* inv_norm, i
  * similarity (multimodal.py:765-770). */
 int cvcl_spatial_pool(const float* src, int B, int HW, int E, float* out_f32, void* out_bf16, int ld,
                       void* out_bf16_t, int ld_t, void* stream);
+/* its backward: dst [B,HW,E] fp32 = g [B,E] broadcast over the locations (autograd of the sum, multimodal.py:765). */
+int cvcl_spatial_pool_bwd(const float* g, int B, int HW, int E, float* dst, void* stream);
 
 /* generic C [M,N] fp32 = alpha * A . B^T on the tcgen05 engine (bf16 operands, fp32 accumulate).
  * a_mn = 0: A stored [M,K] (K-major);  a_mn = 1: A stored [K,M] (MN-major, i.e. the transposed

@@ -14,7 +14,7 @@ from . import _cabi, attention_maps, build, ops, sharding, staging  # noqa: F401
 from ._cabi import CvclError, CvclLibraryMissing                   # noqa: F401
 from .multimodal import (MultiModalModel, PooledTrunk, TextEncoder, VisionEncoder,  # noqa: F401
                          split_trunk_forward)
-from .graphed import GraphedContrastiveStep                         # noqa: F401
+from .graphed import GraphedContrastiveStep, GraphedLossStep        # noqa: F401
 from .optim import FusedAdamW                                       # noqa: F401
 from .staging import PinnedBatchStager, batch_trials, multiModalDataset_collate_fn  # noqa: F401
 from .multimodal_lit import MultiModalLitModel, WhitespaceTokenizer, load_vocab      # noqa: F401

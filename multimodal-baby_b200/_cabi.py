@@ -30,6 +30,8 @@ PROTOTYPES = {
     "cvcl_abi_version": (c_int, []),
     "cvcl_last_error": (c_char_p, []),
     "cvcl_launch_count": (ctypes.c_ulonglong, []),
+    "cvcl_host_alloc": (c_void_p, [c_size_t, _I]),
+    "cvcl_host_free": (c_int, [_P]),
     "cvcl_text_encoder_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _I, _P,
                                       _P, _P, _P, _P]),
     "cvcl_embedding_gather": (c_int, [_P, _P, _P, _I, _I, _I, _P]),
@@ -39,6 +41,7 @@ PROTOTYPES = {
     "cvcl_cast_transpose": (c_int, [_P, _I, _P, _P, _I, _I, _I, _L, _L, _L, _L, _L, _L, _P]),
     "cvcl_rownorm_bwd": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P]),
     "cvcl_spatial_pool": (c_int, [_P, _I, _I, _I, _P, _P, _I, _P, _I, _P]),
+    "cvcl_spatial_pool_bwd": (c_int, [_P, _I, _I, _I, _P, _P]),
     "cvcl_head_proj_norm_fwd": (c_int, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P]),
     "cvcl_sim_workspace_bytes": (c_size_t, [_I, _I, _I, _I]),
     "cvcl_sim_infonce_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _F, _P, _P, _P, _P,

@@ -128,31 +128,74 @@ __global__ void __launch_bounds__(128) text_encoder_fwd_kernel(const TextFwdPara
                 (void)n;
             }
         } else {
-            for (int k = 0; k < nl; ++k) {
-                const long long id = __shfl_sync(0xffffffffu, my_id, k);
-                const size_t tok = static_cast<size_t>(b) * p.L + l0 + k;
-                float4 r[kMaxVec];
-                const float4* src = reinterpret_cast<const float4*>(p.table + static_cast<size_t>(id) * p.E);
+            // per token: tok = normalise(row).  Pads (id 0) are exact zero rows: written when the token output is
+            // wanted, never fetched.  Live tokens go in groups of four whose rows are in flight together (one
+            // dependent round trip per token made this the slowest kernel of the spatial step: 81 us at B = 1024).
+            const unsigned in_range = nl == 32 ? 0xffffffffu : ((1u << nl) - 1u);
+            unsigned live = __ballot_sync(0xffffffffu, my_id != 0 && lane < nl);
+            if (p.tok_f32 || p.tok_bf16 || p.inv_norm) {
+                unsigned pad = ~live & in_range;
+                const float pad_inv = 1.f / (p.normalize ? fmaxf(0.f, 1e-12f) : 1.f);
+                while (pad) {
+                    const int k = __ffs(pad) - 1; pad &= pad - 1;
+                    const size_t tok = static_cast<size_t>(b) * p.L + l0 + k;
+                    if (lane == 0 && p.inv_norm) p.inv_norm[tok] = pad_inv;
 #pragma unroll
-                for (int c = 0; c < kMaxVec; ++c) {
-                    r[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (id != 0 && c < nch && (c * 32 + lane) * 4 < p.E) r[c] = __ldg(src + c * 32 + lane);
+                    for (int c = 0; c < kMaxVec; ++c) {
+                        if (c < nch && (c * 32 + lane) * 4 < p.E) {
+                            const size_t off = tok * p.E + (c * 32 + lane) * 4;
+                            if (p.tok_f32) *reinterpret_cast<float4*>(p.tok_f32 + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (p.tok_bf16) *reinterpret_cast<uint2*>(p.tok_bf16 + off) = make_uint2(0u, 0u);
+                        }
+                    }
                 }
-                float ssq = 0.f;
+            }
+            constexpr int kG = 4;
+            while (live) {
+                int pos[kG];
 #pragma unroll
-                for (int c = 0; c < kMaxVec; ++c)
-                    ssq += r[c].x * r[c].x + r[c].y * r[c].y + r[c].z * r[c].z + r[c].w * r[c].w;
-                ssq = warp_sum(ssq);
-                const float denom = p.normalize ? fmaxf(sqrtf(ssq), 1e-12f) : 1.f;
-                if (lane == 0 && p.inv_norm) p.inv_norm[tok] = 1.f / denom;
+                for (int k = 0; k < kG; ++k) {
+                    pos[k] = -1;
+                    if (live) { pos[k] = __ffs(live) - 1; live &= live - 1; }
+                }
+                float4 r[kG][kMaxVec];
 #pragma unroll
-                for (int c = 0; c < kMaxVec; ++c) {
-                    if (c < nch && (c * 32 + lane) * 4 < p.E) {
-                        float4 t = make_float4(r[c].x / denom, r[c].y / denom, r[c].z / denom, r[c].w / denom);
-                        const size_t off = tok * p.E + (c * 32 + lane) * 4;
-                        if (p.tok_f32) *reinterpret_cast<float4*>(p.tok_f32 + off) = t;
-                        if (p.tok_bf16) store_bf16x4(p.tok_bf16 + off, t);
-                        acc[c].x += t.x; acc[c].y += t.y; acc[c].z += t.z; acc[c].w += t.w;
+                for (int k = 0; k < kG; ++k) {
+                    const long long id = __shfl_sync(0xffffffffu, my_id, pos[k] < 0 ? 0 : pos[k]);
+                    const float4* src = reinterpret_cast<const float4*>(p.table + static_cast<size_t>(id) * p.E);
+#pragma unroll
+                    for (int c = 0; c < kMaxVec; ++c) {
+                        r[k][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (pos[k] >= 0 && c < nch && (c * 32 + lane) * 4 < p.E) r[k][c] = __ldg(src + c * 32 + lane);
+                    }
+                }
+                float ssq[kG];
+#pragma unroll
+                for (int k = 0; k < kG; ++k) {
+                    ssq[k] = 0.f;
+#pragma unroll
+                    for (int c = 0; c < kMaxVec; ++c)
+                        ssq[k] += r[k][c].x * r[k][c].x + r[k][c].y * r[k][c].y + r[k][c].z * r[k][c].z + r[k][c].w * r[k][c].w;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)                     // four independent butterfly chains
+#pragma unroll
+                    for (int k = 0; k < kG; ++k) ssq[k] += __shfl_xor_sync(0xffffffffu, ssq[k], o);
+#pragma unroll
+                for (int k = 0; k < kG; ++k) {                       // position order, as sum(dim=1) does
+                    if (pos[k] < 0) continue;
+                    const size_t tok = static_cast<size_t>(b) * p.L + l0 + pos[k];
+                    const float denom = p.normalize ? fmaxf(sqrtf(ssq[k]), 1e-12f) : 1.f;
+                    if (lane == 0 && p.inv_norm) p.inv_norm[tok] = 1.f / denom;
+#pragma unroll
+                    for (int c = 0; c < kMaxVec; ++c) {
+                        if (c < nch && (c * 32 + lane) * 4 < p.E) {
+                            float4 t = make_float4(r[k][c].x / denom, r[k][c].y / denom, r[k][c].z / denom, r[k][c].w / denom);
+                            const size_t off = tok * p.E + (c * 32 + lane) * 4;
+                            if (p.tok_f32) *reinterpret_cast<float4*>(p.tok_f32 + off) = t;
+                            if (p.tok_bf16) store_bf16x4(p.tok_bf16 + off, t);
+                            acc[c].x += t.x; acc[c].y += t.y; acc[c].z += t.z; acc[c].w += t.w;
+                        }
                     }
                 }
             }
@@ -1062,6 +1105,18 @@ __global__ void __launch_bounds__(128) spatial_pool_kernel(const float* src, int
     }
 }
 
+
+// backward of spatial_pool: d src[b, h, :] = g[b, :] for every location h (the sum's gradient is a broadcast).
+// Thread = 4 consecutive channels of one image; the row is read once and stored HW times with streaming stores.
+__global__ void __launch_bounds__(128) spatial_pool_bwd_kernel(const float* g, int B, int HW, int E, float* dst) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
+    const int b = blockIdx.y;
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (e >= E) return;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(g + static_cast<size_t>(b) * E + e));
+    float4* p = reinterpret_cast<float4*>(dst + (static_cast<size_t>(b) * HW) * E + e);
+    for (int h = 0; h < HW; ++h) __stcs(p + static_cast<size_t>(h) * (E >> 2), v);
+}
 
 // --------------------------------------------------------------------------------------
 // spatial "max" similarity backward (SIMT gather form, v1).  g = dL/dmatch [Bi,Bt];

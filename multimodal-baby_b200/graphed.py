@@ -277,3 +277,53 @@ class GraphedContrastiveStep:
     def stats(self):
         """(loss, image_accuracy, text_accuracy, image_entropy, text_entropy) of the last step."""
         return tuple(float(v) for v in self.stats_host[:5])
+
+
+class GraphedLossStep:
+    """Whole-step CUDA graph of an arbitrary loss closure built from this package's ops: `loss_fn()` (forward through
+    the autograd wrappers of ops.py) and `loss.backward()` are captured once and replayed per batch.  This is how the
+    spatial paths (multimodal.py:757-780: `sim = mean` and `sim = max` over the 7x7 map), which run as a sequence of
+    eight to twelve kernels, get rid of their per-op host cost (B200-first: a graph, not Python dispatch; spatial mean
+    at 1024 pairs: 470 us eager -> see profiles/README.md).
+
+        x = torch.empty(B, 49, E, device=dev); ...                 # static input buffers, refilled between calls
+        step = GraphedLossStep(lambda: loss_of(x, ids, lens), params=[table, x_leaf, ...])
+        loss = step()            # replays forward + backward; returns the static 0-dim loss tensor (no sync)
+        # gradients: p.grad of every tensor in `params` (static buffers, overwritten by the next call)
+
+    `loss_fn` must not synchronise (no .item(), no host-side reads) and must read its inputs from fixed buffers.
+    Every tensor in `params` must be a leaf that requires grad and is used by `loss_fn`."""
+
+    def __init__(self, loss_fn, params, warmup=3):
+        self.params = list(params)
+        if not self.params:
+            raise ValueError("GraphedLossStep: no parameters")
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedLossStep runs on CUDA tensors only")
+        self.dev = dev
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                for p in self.params:
+                    p.grad = None
+                loss_fn().backward()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        for p in self.params:
+            p.grad = None
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = loss_fn()
+            self.loss.backward()
+        self.grads = [p.grad for p in self.params]
+        if any(g is None for g in self.grads):
+            raise RuntimeError("GraphedLossStep: a tensor in `params` received no gradient from loss_fn")
+
+    def __call__(self):
+        self.graph.replay()
+        for p, g in zip(self.params, self.grads):      # the static gradient buffers (in case the caller reset .grad)
+            p.grad = g
+        return self.loss

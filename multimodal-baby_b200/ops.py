@@ -34,7 +34,9 @@ def _p(t: Optional[Tensor]):
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    """raw handle of the current CUDA stream (the C-level query: torch.cuda.current_stream() builds a Stream object
+    and costs ~6 us per call, this ~0.3 us)"""
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def _need_cuda(*ts):
@@ -378,7 +380,13 @@ class _SpatialPool(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        return g.unsqueeze(1).expand(-1, ctx.hw, -1)
+        # the sum's gradient is a broadcast over the locations: materialised by one streaming-store kernel (returning
+        # the expanded view instead made autograd copy it with a strided elementwise kernel: 62 us vs 17 at B = 1024)
+        g = _f32(g)
+        B, E = g.shape
+        out = torch.empty((B, ctx.hw, E), dtype=torch.float32, device=g.device)
+        _cabi.call("cvcl_spatial_pool_bwd", _p(g), B, ctx.hw, E, _p(out), _stream())
+        return out
 
 
 def spatial_pool(x):
@@ -584,9 +592,12 @@ def sim_infonce(img, txt, s, group=None):
 # fused flat train step (K1..K5 sequenced inside one C call)
 # ----------------------------------------------------------------------------------------
 def split_flat_grads(flat: Tensor, E: int, K: int, V: int):
-    """views into the flat gradient buffer [ds(4) | db(E) | dtable(V*E) | dW(E*K)]."""
-    return (flat[0:1], flat[4:4 + E], flat[4 + E:4 + E + V * E].view(V, E),
-            flat[4 + E + V * E:4 + E + V * E + E * K].view(E, K))
+    """views into the flat gradient buffer [ds(4) | db(E) | dtable(V*E) | dW(E*K)] (one split op + three views)."""
+    n = 4 + E + V * E + E * K
+    if flat.numel() != n:
+        flat = flat[:n]
+    ds4, db, dt, dw = flat.split_with_sizes((4, E, V * E, E * K))
+    return ds4[0:1], db, dt.view(V, E), dw.view(E, K)
 
 
 # bf16 shadows of fp32 master weights, keyed by storage: recast only when the parameter's version changed
@@ -711,20 +722,25 @@ def flat_contrastive_step(x: Tensor, ids: Tensor, lens: Tensor, w: Tensor, bias:
     txt_f = torch.empty((B, E), **f32) if want_features else torch.empty((0,), **f32)
     if need_grads:
         flat = torch.empty((4 + E + V * E + E * K,), **f32)
-        ds, db, dtable, dW = split_flat_grads(flat, E, K, V)
     else:
         flat = torch.empty((0,), **f32)
-        ds = db = dtable = dW = None
     if fused_supported(B, L, E, K, V):
         x16, _ = to_bf16_pair(x, False)
         w16 = weight_shadow(w_param)
         ws = _fused_workspace(dev, B, L, E, K, V)
+        # gradient pointers straight from the layout of the flat buffer (split_flat_grads): no views on this path
+        g0 = flat.data_ptr() if need_grads else None
         _cabi.call("cvcl_flat_step_fused", _p(x16), _p(w16), _p(ids), _p(lens), _p(bias), _p(table),
                    B, L, E, K, V, int(normalize), float(log_scale), _p(log_scale_t), int(need_grads),
                    _p(ws), _p(out5), _p(img_f) if want_features else None,
-                   _p(txt_f) if want_features else None, _p(dW), _p(db), _p(dtable), _p(ds), None,
-                   int(phase_limit), _stream())
+                   _p(txt_f) if want_features else None,
+                   g0 + 4 * (4 + E + V * E) if need_grads else None, g0 + 16 if need_grads else None,
+                   g0 + 4 * (4 + E) if need_grads else None, g0, None, int(phase_limit), _stream())
         return out5, img_f, txt_f, flat
+    if need_grads:
+        ds, db, dtable, dW = split_flat_grads(flat, E, K, V)
+    else:
+        ds = db = dtable = dW = None
     if log_scale_t is not None:
         log_scale = float(log_scale_t)               # multi-kernel path: host scalar (one D2H sync)
     out5.zero_()

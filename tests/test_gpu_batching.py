@@ -89,3 +89,22 @@ def test_model_forward_batched_equals_per_pair(cv):
             for j in range(3):
                 one, _ = m(x[i:i + 1], ids[j:j + 1], lens[j:j + 1])
                 assert abs(one.item() - lpi[i, j].item()) <= 1e-4
+
+
+def test_write_combined_staging_arena():
+    """staging.host_arena: page-locked (optionally write-combined) host memory from the library's own allocator,
+    usable as the source of an asynchronous H2D copy and as a packed staging set."""
+    import multimodal_baby_b200 as cv
+    a = cv.staging.host_arena(1 << 20, True)
+    assert a.dtype == torch.uint8 and a.numel() == 1 << 20 and a.is_pinned()
+    src = torch.arange(1 << 20, dtype=torch.int64).to(torch.uint8)
+    a.copy_(src)
+    d = torch.empty(1 << 20, dtype=torch.uint8, device="cuda")
+    d.copy_(a, non_blocking=True)
+    torch.cuda.synchronize()
+    assert torch.equal(d.cpu(), src)
+    x, ids, lens = cv.staging.packed_buffers([((4, 8), torch.bfloat16), ((4, 25), torch.int64), ((4,), torch.int64)],
+                                             write_combined=True)
+    assert x.is_pinned() and cv.staging.packed_span((x, ids, lens)) is not None
+    assert float(x.float().abs().sum()) == 0.0 and int(ids.sum()) == 0
+    del a, x, ids, lens                                # the finalizer frees the allocation with the last view

@@ -165,3 +165,31 @@ def test_spatial_max_backward_mma_form_equals_gather_form(cv):
     (ref * g.double()).sum().backward()
     assert rel_fro(res[True][0], ir.grad.numpy()) <= 4e-3
     assert rel_fro(res[True][1][valid], tr.grad.numpy()[valid]) <= 4e-3
+
+
+@pytest.mark.parametrize("sim", ["mean", "max"])
+def test_graphed_spatial_step_equals_eager(cv, sim):
+    """GraphedLossStep: the whole spatial train step (head on the 7x7 map, text tokens, similarity, InfoNCE, backward)
+    captured as one CUDA graph == the eager module call, and a replay picks up new inputs in the static buffers."""
+    E, B = 512, 24
+    inps = [case_inputs(900 + k, B, E, "spatial") for k in range(2)]
+    m = build(cv, E, sim, inps[0], fix_temperature=True)
+    m.materialize_logits = m.materialize_text_outputs = False
+    conv = m.image_embed.model[-1]
+    params = [conv.weight, conv.bias, m.text_embed.embedding.weight]
+
+    def eager(inp):
+        for p in params:
+            p.grad = None
+        out = m.calculate_contrastive_loss(t(inp["f"], DEV), t(inp["ids"], DEV), t(inp["lens"], DEV))
+        out[0].backward()
+        return out[0].item(), [p.grad.clone() for p in params]
+    ref = [eager(i) for i in inps]
+    x = t(inps[0]["f"], DEV).clone(); ids = t(inps[0]["ids"], DEV).clone(); lens = t(inps[0]["lens"], DEV).clone()
+    step = cv.GraphedLossStep(lambda: m.calculate_contrastive_loss(x, ids, lens)[0], params)
+    for k in (0, 1, 0):
+        x.copy_(t(inps[k]["f"], DEV)); ids.copy_(t(inps[k]["ids"], DEV)); lens.copy_(t(inps[k]["lens"], DEV))
+        loss = step()
+        assert abs(loss.item() - ref[k][0]) <= 1e-5 * abs(ref[k][0]), (k, loss.item(), ref[k][0])
+        for p, g in zip(params, ref[k][1]):
+            assert rel_fro(p.grad.cpu().numpy(), g.cpu().numpy()) <= 1e-4, k       # float-atomic order only

@@ -78,6 +78,44 @@ def main():
         tot = (time.perf_counter() - t00) / 2000 * 1e6
         print("graphed %s: mean %.1f us/call; p10 %.1f p50 %.1f p90 %.1f p99 %.1f max %.1f" % (
             kw, tot, pct(per, .1), pct(per, .5), pct(per, .9), pct(per, .99), max(per)))
+        print("   calls 1000..1047:", " ".join("%d" % v for v in per[1000:1048]))
+        if kw["lagged_loss"]:
+            for k, ha in enumerate(g._host_arenas):          # the two pinned staging sets: is one of them slow?
+                ts = []
+                for _ in range(30):
+                    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                    e0.record(); g._dev_arenas[0].copy_(ha, non_blocking=True); e1.record(); e1.synchronize()
+                    ts.append(e0.elapsed_time(e1) * 1e3)
+                print("   H2D from staging set %d (%d bytes, pinned=%s, ptr %x): median %.1f us" % (
+                    k, ha.numel(), ha.is_pinned(), ha.data_ptr(), statistics.median(ts)))
+            fresh = [torch.empty(2203648, dtype=torch.uint8).pin_memory() for _ in range(3)]
+            big = torch.empty(3 * 2203648, dtype=torch.uint8).pin_memory()
+            fresh += [big[i * 2203648:(i + 1) * 2203648] for i in range(3)]
+            for k, ha in enumerate(fresh):
+                ha.fill_(1)
+                ts = []
+                for _ in range(30):
+                    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                    e0.record(); g._dev_arenas[0].copy_(ha, non_blocking=True); e1.record(); e1.synchronize()
+                    ts.append(e0.elapsed_time(e1) * 1e3)
+                print("   H2D from fresh pinned buffer %d (ptr %x): median %.1f us" % (k, ha.data_ptr(), statistics.median(ts)))
+            # where does a slow call spend its time: the replay (cudaGraphLaunch) or the wait for the previous replay?
+            tr, tw = [], []
+            for _ in range(400):
+                which = g.calls % len(g.graphs)
+                t0 = time.perf_counter(); g.graphs[which].replay(); t1 = time.perf_counter()
+                g.calls += 1
+                g.events[which].record(torch.cuda.current_stream(dev))
+                prev, g.pending = g.pending, which
+                if prev is not None:
+                    g.events[prev].synchronize()
+                t2 = time.perf_counter()
+                tr.append((t1 - t0) * 1e6); tw.append((t2 - t1) * 1e6)
+            g.flush(); torch.cuda.synchronize()
+            print("   lagged split: replay() p10 %.1f p50 %.1f p90 %.1f | record+wait p10 %.1f p50 %.1f p90 %.1f" % (
+                pct(tr, .1), pct(tr, .5), pct(tr, .9), pct(tw, .1), pct(tw, .5), pct(tw, .9)))
+            print("   replay us:", " ".join("%d" % v for v in tr[200:232]))
+            print("   wait   us:", " ".join("%d" % v for v in tw[200:232]))
 
     # eager module API
     per = []
