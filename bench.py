@@ -611,13 +611,16 @@ def main():
     # the same step keeps running (untimed) until two samples exist; then the poller is stopped: its driver queries
     # must not sit on the host path of the wall-clock e2e loops below.
     clocks = None
-    if rank == 0:
+    if world == 1:
         t_s = time.perf_counter()
         while len(sampler.rows) < 2 and time.perf_counter() - t_s < 1.5:
             flush.zero_(); run_step()
-        torch.cuda.synchronize()
-        clocks = sampler.stop()
+    else:
+        for _ in range(1000):               # sharded steps are collective: the same fixed count on every rank
+            flush.zero_(); run_step()
     barrier()
+    if rank == 0:
+        clocks = sampler.stop()
     if graph is not None:       # replays launch the captured kernels without passing through the C ABI
         n1 = lib.cvcl_launch_count(); raw_step(); per = lib.cvcl_launch_count() - n1
         n_launch = per * a.steps
@@ -659,14 +662,21 @@ def main():
         # warm-up to the steady state: blocks of 200 calls until the staging memory is at least 3 s old AND two
         # consecutive blocks agree within 5 % (6 s of warm-up at most)
         prev_blk, t_w0 = None, time.perf_counter()
-        while time.perf_counter() - t_w0 < 6.0:
+        while True:
             tb = time.perf_counter()
             for _ in range(200):
                 gstep()
             gstep.flush()
             blk = time.perf_counter() - tb
             aged = time.perf_counter() - t_gstep >= 3.0
-            if aged and prev_blk is not None and abs(blk - prev_blk) <= 0.05 * prev_blk:
+            done = aged and prev_blk is not None and abs(blk - prev_blk) <= 0.05 * prev_blk
+            done = done or time.perf_counter() - t_w0 >= 6.0
+            if world > 1:                    # sharded steps are collective: every rank leaves after the same block
+                import torch.distributed as dist
+                flag = torch.tensor([0 if done else 1], device=dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+                done = int(flag.item()) == 0
+            if done:
                 break
             prev_blk = blk
         barrier()
