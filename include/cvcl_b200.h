@@ -93,6 +93,24 @@ int cvcl_rownorm_bwd(const float* g, const float* feat, const float* inv_norm, i
  * similarity (multimodal.py:765-770). */
 int cvcl_spatial_pool(const float* src, int B, int HW, int E, float* out_f32, void* out_bf16, int ld,
                       void* out_bf16_t, int ld_t, void* stream);
+/* C [M,N] fp32 = A [M,K] . W[N,K]^T + bias [N], fp32 operands and fp32 FMA accumulation (no tensor cores): the
+ * exact-mode projection head of the evaluation path (reference fc in fp32, multimodal.py:186-192, called per trial
+ * from eval.py:196-214).  K % 4 == 0. */
+int cvcl_linear_f32(const float* A, int lda, const float* W, int ldw, const float* bias, int M, int N, int K,
+                    float* C, int ldc, void* stream);
+
+/* The two other evaluation forms of the reference, both "normalise, all-pairs cosine, arg-max" in fp32:
+ *   - n-category classification of a frame (multimodal_saycam_data_module.py:545-606: image vs every category text,
+ *     argmax over the categories): normalize_rows (frames, texts) -> linear_f32 (scores) -> row_argmax;
+ *   - cosine nearest-neighbour search between two feature sets (analysis_cvcl/duplicates.py:561-607: F.normalize +
+ *     F.cosine_similarity + np.argmax/np.max per evaluation frame), chunked over the keys with `merge`.
+ * normalize_rows: dst[m,:] = src[m,:] / max(||src[m,:]||, 1e-12).  row_argmax: first maximum of each row of
+ * scores [M,N] (leading dimension ld) and its index + col0; merge != 0 folds it into the (best, arg) of earlier,
+ * lower-index column chunks. */
+int cvcl_normalize_rows_f32(const float* src, float* dst, long long M, int E, void* stream);
+int cvcl_row_argmax_f32(const float* scores, long long ld, long long M, int N, int col0, int merge, float* best,
+                        int* arg, void* stream);
+
 /* its backward: dst [B,HW,E] fp32 = g [B,E] broadcast over the locations (autograd of the sum, multimodal.py:765). */
 int cvcl_spatial_pool_bwd(const float* g, int B, int HW, int E, float* dst, void* stream);
 

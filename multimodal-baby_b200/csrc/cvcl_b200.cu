@@ -208,6 +208,39 @@ int cvcl_spatial_pool(const float* src, int B, int HW, int E, float* out_f32, vo
     return CVCL_OK;
 }
 
+int cvcl_linear_f32(const float* A, int lda, const float* W, int ldw, const float* bias, int M, int N, int K,
+                    float* C, int ldc, void* stream) {
+    CVCL_REQUIRE(A && W && C, "linear_f32: null pointer");
+    CVCL_REQUIRE(M >= 0 && N > 0 && K > 0 && K % 4 == 0 && lda % 4 == 0 && ldw % 4 == 0, "linear_f32: bad shape");
+    CVCL_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W)) & 15) == 0,
+                 "linear_f32: 16-byte alignment required");
+    if (M == 0) return CVCL_OK;
+    dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
+    CVCL_CHECK_CUDA(launch_pdl(linear_f32_kernel, grid, dim3(256), 0, as_stream(stream), A, lda, W, ldw, bias, M, N, K, C, ldc));
+    count_launch();
+    return CVCL_OK;
+}
+
+int cvcl_normalize_rows_f32(const float* src, float* dst, long long M, int E, void* stream) {
+    CVCL_REQUIRE(src && dst, "normalize_rows_f32: null pointer");
+    CVCL_REQUIRE(M >= 0 && E > 0 && E % 4 == 0, "normalize_rows_f32: bad shape");
+    if (M == 0) return CVCL_OK;
+    CVCL_CHECK_CUDA(launch_pdl(normalize_rows_f32_kernel, dim3(warps_grid(M)), dim3(256), 0, as_stream(stream), src, dst, M, E));
+    count_launch();
+    return CVCL_OK;
+}
+
+int cvcl_row_argmax_f32(const float* scores, long long ld, long long M, int N, int col0, int merge, float* best,
+                        int* arg, void* stream) {
+    CVCL_REQUIRE(scores && best && arg, "row_argmax_f32: null pointer");
+    CVCL_REQUIRE(M >= 0 && N > 0 && ld >= N, "row_argmax_f32: bad shape");
+    if (M == 0) return CVCL_OK;
+    CVCL_CHECK_CUDA(launch_pdl(row_argmax_f32_kernel, dim3(warps_grid(M)), dim3(256), 0, as_stream(stream), scores, ld, M, N,
+                               col0, merge, best, arg));
+    count_launch();
+    return CVCL_OK;
+}
+
 int cvcl_spatial_pool_bwd(const float* g, int B, int HW, int E, float* dst, void* stream) {
     CVCL_REQUIRE(g && dst, "spatial_pool_bwd: null pointer");
     CVCL_REQUIRE(E > 0 && E % 4 == 0 && HW > 0, "spatial_pool_bwd: bad shape");

@@ -193,47 +193,59 @@ template <bool kWriterFence>
 CVCL_HELPER void grid_sync(const StepParams& p, int k, int xstage = -1, unsigned int epoch = 0) {
     if (kWriterFence) fence_proxy_async_all();
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
+        // warp 0: lane 0 arrives on the local counter; in a cross-rank barrier lane q talks to rank q, so the `world`
+        // signals and the `world` polls run side by side instead of one release (fence + store) after the other
+        // (measured at 8 ranks: ~14 us per barrier for seven serial releases)
+        const int lane = threadIdx.x;
         const bool cross = xstage >= 0 && p.world > 1;
-        if (cross) __threadfence_system(); else __threadfence();
         const unsigned int target = static_cast<unsigned int>(k + 1) * gridDim.x;
-        const unsigned int prev = atomicAdd(p.sync, 1u);
-        if (cross && prev == target - 1) {
-            for (int pp = 0; pp < p.world; ++pp)
-                if (pp != p.rank) st_release_sys(p.peer_flags[pp] + xstage * 8 + p.rank, epoch);
+        unsigned int prev = 0;
+        if (lane == 0) {
+            if (cross) __threadfence_system(); else __threadfence();
+            prev = atomicAdd(p.sync, 1u);
         }
+        prev = __shfl_sync(0xffffffffu, prev, 0);
+        __syncwarp();                       // memory ordering lane 0 -> the signalling lanes (shfl alone gives none)
         unsigned int it = 0; unsigned long long t0 = 0;
         if (cross) {
-            for (int pp = 0; pp < p.world; ++pp) {
-                if (pp == p.rank) continue;
-                const unsigned int* w = p.peer_flags[p.rank] + xstage * 8 + pp;
+            const bool peer = lane < p.world && lane != p.rank;
+            // the LAST local arrival has seen every other CTA's arrival (each behind that CTA's system-scope fence):
+            // its release stores publish the whole rank's writes
+            if (prev == target - 1 && peer) st_release_sys(p.peer_flags[lane] + xstage * 8 + p.rank, epoch);
+            if (peer) {
+                const unsigned int* w = p.peer_flags[p.rank] + xstage * 8 + lane;
                 while (static_cast<int>(ld_acquire_sys(w) - epoch) < 0) {
                     if ((++it & 4095u) == 0) {
                         const unsigned long long now = globaltimer_ns();
                         if (t0 == 0) t0 = now;
                         else if (now - t0 > 20000000000ull) {     // 20 s: a peer never reached this step
-                            if (p.fault) atomicExch(p.fault, 200 + 10 * xstage + pp);
+                            if (p.fault) atomicExch(p.fault, 200 + 10 * xstage + lane);
                             __threadfence_system();
                             __trap();
                         }
                     }
                 }
             }
+            __syncwarp();
             it = 0; t0 = 0;
         }
-        while (ld_acquire_gpu(p.sync) < target) {
-            if ((++it & 4095u) == 0) {
-                const unsigned long long now = globaltimer_ns();
-                if (t0 == 0) t0 = now;
-                else if (now - t0 > 2000000000ull) {              // 2 s: a CTA never arrived
-                    if (p.fault) atomicExch(p.fault, 100 + k);
-                    __threadfence_system();
-                    __trap();
+        if (lane == 0) {
+            while (ld_acquire_gpu(p.sync) < target) {
+                if ((++it & 4095u) == 0) {
+                    const unsigned long long now = globaltimer_ns();
+                    if (t0 == 0) t0 = now;
+                    else if (now - t0 > 2000000000ull) {              // 2 s: a CTA never arrived
+                        if (p.fault) atomicExch(p.fault, 100 + k);
+                        __threadfence_system();
+                        __trap();
+                    }
                 }
             }
+            fence_proxy_async_all();                                  // thread 0 = warp 0 lane 0 issues the TMA loads
+            if (blockIdx.x == 0 && p.timing) p.timing[k + 1] = globaltimer_ns();
         }
-        fence_proxy_async_all();                                  // thread 0 = warp 0 lane 0 issues the TMA loads
-        if (blockIdx.x == 0 && p.timing) p.timing[k + 1] = globaltimer_ns();
+        __syncwarp();
     }
     __syncthreads();
 }

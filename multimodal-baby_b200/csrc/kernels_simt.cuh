@@ -761,6 +761,112 @@ __global__ void __launch_bounds__(256) gradcam_head_kernel(const float* pooled, 
     if (lane == 0) u[o] = s + (bias ? __ldg(bias + e) : 0.f);
 }
 
+// C[m,n] = bias[n] + <A[m,:], W[n,:]>, all fp32 with fp32 FMA accumulation (the exact-mode projection head of the
+// evaluation path: reference `fc` in fp32, multimodal.py:186-192).  64 x 64 output tile per 256-thread block, 4 x 4
+// outputs per thread, 16-deep k slabs staged in shared memory (k-major, +1 padding); K % 4 == 0.
+__global__ void __launch_bounds__(256) linear_f32_kernel(const float* A, int lda, const float* W, int ldw,
+                                                         const float* bias, int M, int N, int K, float* C, int ldc) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
+    __shared__ float sa[16][65];
+    __shared__ float sw[16][65];
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;             // outputs rows ty*4.., cols tx*4..
+    const int lr = threadIdx.x >> 2, lk = (threadIdx.x & 3) * 4;        // loader: row lr (0..63), k offset lk
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vw = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m0 + lr < M && k0 + lk < K) va = __ldg(reinterpret_cast<const float4*>(A + static_cast<size_t>(m0 + lr) * lda + k0 + lk));
+        if (n0 + lr < N && k0 + lk < K) vw = __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(n0 + lr) * ldw + k0 + lk));
+        __syncthreads();
+        sa[lk][lr] = va.x; sa[lk + 1][lr] = va.y; sa[lk + 2][lr] = va.z; sa[lk + 3][lr] = va.w;
+        sw[lk][lr] = vw.x; sw[lk + 1][lr] = vw.y; sw[lk + 2][lr] = vw.z; sw[lk + 3][lr] = vw.w;
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            float a[4], w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = sa[kk][ty * 4 + i]; w[i] = sw[kk][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n < N) C[static_cast<size_t>(m) * ldc + n] = acc[i][j] + (bias ? __ldg(bias + n) : 0.f);
+        }
+    }
+}
+
+// dst[m,:] = src[m,:] / max(||src[m,:]||, 1e-12)  (F.normalize, fp32; one warp per row, E % 4 == 0)
+__global__ void __launch_bounds__(256) normalize_rows_f32_kernel(const float* src, float* dst, long long M, int E) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
+    const long long m = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (m >= M) return;
+    const float4* p = reinterpret_cast<const float4*>(src + m * E);
+    float ssq = 0.f;
+    for (int i = lane; i < (E >> 2); i += 32) {
+        const float4 v = __ldg(p + i);
+        ssq += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    ssq = warp_sum(ssq);
+    const float d = fmaxf(sqrtf(ssq), 1e-12f);
+    float4* q = reinterpret_cast<float4*>(dst + m * E);
+    for (int i = lane; i < (E >> 2); i += 32) {
+        const float4 v = __ldg(p + i);
+        q[i] = make_float4(v.x / d, v.y / d, v.z / d, v.w / d);
+    }
+}
+
+// per row of scores [M, N] (ld): the first maximum and its index (torch.argmax / np.argmax semantics: the lowest index
+// wins ties; a NaN row entry wins like in torch).  One warp per row; merged into (best, arg) that already hold the
+// result of earlier column chunks when `merge` (chunked nearest-neighbour search), col0 = index of column 0.
+__global__ void __launch_bounds__(256) row_argmax_f32_kernel(const float* scores, long long ld, long long M, int N,
+                                                             int col0, int merge, float* best, int* arg) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
+    const long long m = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (m >= M) return;
+    const float* row = scores + m * ld;
+    float b = -INFINITY; int a = 0x7fffffff; bool nan_seen = false;
+    for (int n = lane; n < N; n += 32) {
+        const float v = __ldg(row + n);
+        if (v != v) { if (!nan_seen) { nan_seen = true; b = v; a = n; } }
+        else if (!nan_seen && (v > b || a == 0x7fffffff)) { b = v; a = n; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, b, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, a, o);
+        const bool o_nan = ob != ob, m_nan = b != b;
+        bool take;
+        if (o_nan || m_nan) take = o_nan && (!m_nan || oa < a);
+        else take = (ob > b) || (ob == b && oa < a);
+        if (take) { b = ob; a = oa; }
+    }
+    if (lane == 0 && a != 0x7fffffff) {
+        a += col0;
+        if (merge) {
+            const float pb = best[m]; const int pa = arg[m];
+            const bool p_nan = pb != pb, m_nan = b != b;
+            const bool keep_prev = p_nan || (!m_nan && pb >= b);         // earlier chunk = lower indices: wins ties
+            if (keep_prev) { b = pb; a = pa; }
+        }
+        best[m] = b; arg[m] = a;
+    }
+}
+
 // g[n,:] from u[n,:] and target[n,:]: one warp per image (F.normalize backward, eps 1e-12)
 __global__ void __launch_bounds__(128) gradcam_g_kernel(const float* u, const float* target, float* g, int N, int E,
                                                         int normalize) {

@@ -197,6 +197,8 @@ def split_trunk_forward(image_embed, x, run_head=True):
     if getattr(image_embed, "vit_dino", False):
         raise NotImplementedError("vit_dino trunk is outside the cvcl_b200 hot path")
     if isinstance(model, PooledTrunk):             # trunk-boundary features fed directly
+        if x.dim() > 2:                            # e.g. a Labeled-S trial viewed as [n_way, 1, 1, 2048]
+            x = x.reshape(-1, x.shape[-1])
         return (model.fc(x) if run_head else x), x
     if image_embed.embedding_type == "spatial":
         fmap = x

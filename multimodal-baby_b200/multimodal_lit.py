@@ -8,6 +8,7 @@ Keeps the caller-facing API of the reference's Lightning wrapper that touches th
       .tokenize(texts) -> (ids int64 [N,25], lens int64 [N])                     :161-190
       .calculate_joint_loss(batch, stage, log)   (contrastive branch)            :227-375
       .training_step / .validation_test_step (Labeled-S 4-way trial)             :445-511
+      .joint_loss_epoch_end / *_epoch_end  (example-weighted epoch metrics)      :376-444, :450-541
       .configure_optimizers()                                                    :112-128
       .evaluate_trials(...)  batched replacement of the per-trial loop of eval.py:175-266
 
@@ -18,7 +19,9 @@ multimodal_lit.py:266-358) are outside the hot path and raise NotImplementedErro
 """
 from __future__ import annotations
 
+import functools
 import json
+import math
 import os
 
 import torch
@@ -27,6 +30,8 @@ import torch.nn as nn
 from . import ops
 from .multimodal import (MultiModalModel, MAX_LEN_UTTERANCE, PAD_TOKEN_ID, SOS_TOKEN_ID,
                          EOS_TOKEN_ID, _args_dict)
+
+N_VAL_DATALOADERS_PER_SPLIT = 2                    # multimodal_data_module.py:32
 
 try:                                               # pragma: no cover - not installed here
     import pytorch_lightning as pl
@@ -159,6 +164,8 @@ class MultiModalLitModel(_Base):
         log(f"{stage}_text_accuracy", text_accuracy)
         log(f"{stage}_image_entropy", image_entropy)
         log(f"{stage}_text_entropy", text_entropy)
+        # multimodal_lit.py:252 (one D2H read when the temperature is a CUDA parameter, as in the reference)
+        log("temperature", math.exp(-ops._scalar(self.model.logit_neg_log_temperature)))
         ret.update({
             'infonce_loss': infonce_loss.detach(),
             'image_accuracy': image_accuracy,
@@ -171,11 +178,27 @@ class MultiModalLitModel(_Base):
         ret.update({'loss': loss})
         return ret
 
+    def joint_loss_epoch_end(self, outputs, stage, log, eval_textgen=False):
+        """multimodal_lit.py:376-444, contrastive branch: example-weighted means of the step outputs."""
+        n = sum(o['batch_size'] for o in outputs)
+
+        def mean(name):
+            return sum(float(o[name]) * o['batch_size'] for o in outputs) / n
+        for name in ('infonce_loss', 'image_accuracy', 'text_accuracy', 'image_entropy', 'text_entropy'):
+            log(f"{stage}_{name}", mean(name))
+        log(f"{stage}_loss", mean('loss'))
+
     def training_step(self, batch, batch_idx):
         return self.calculate_joint_loss(batch, 'train', self.log)
 
+    def training_epoch_end(self, outputs):
+        def log(name, value, *a, **k):
+            return self.log(f"{name}_epoch", value, *a, on_step=False, on_epoch=True, **k)
+        return self.joint_loss_epoch_end(outputs, 'train', log)
+
     # -- Labeled-S trial (multimodal_lit.py:466-511) --------------------------------------------
     def validation_test_step(self, stage, batch, batch_idx, dataloader_idx=0):
+        log = functools.partial(self.log, on_step=False, on_epoch=True)
         ret = {}
         if dataloader_idx == 0:
             ret.update(self.calculate_joint_loss(batch, stage, lambda *a, **k: None))
@@ -185,16 +208,34 @@ class MultiModalLitModel(_Base):
             logits_per_image, logits_per_text = self.model(x, y, y_len)
             logits = logits_per_text[0]
             pred = torch.argmax(logits).item()
-            accuracy = int(pred == 0)
-            self.log(f"{stage}_accuracy", accuracy)
+            accuracy = int(pred == 0)                  # the target is always the first candidate
+            log_p = torch.log_softmax(logits, dim=-1)  # utils.get_entropy (utils.py:106-108)
+            entropy = (torch.softmax(log_p, dim=-1) * -log_p).sum(dim=-1)
+            log(f"{stage}_accuracy", accuracy)
+            log(f"{stage}_entropy", entropy)
+            log(f"{stage}_accuracy_{raw_y[0][0]}", accuracy)      # per-category metric
             ret.update({'accuracy': accuracy})
         return ret
 
+    def validation_test_epoch_end(self, stage, outputs):
+        log = functools.partial(self.log, on_step=False, on_epoch=True)
+        return self.joint_loss_epoch_end(outputs[0], stage, log)
+
     def validation_step(self, batch, batch_idx, dataloader_idx=0):
-        return self.validation_test_step('val', batch, batch_idx, dataloader_idx)
+        if dataloader_idx < N_VAL_DATALOADERS_PER_SPLIT:
+            return self.validation_test_step('val', batch, batch_idx, dataloader_idx)
+        return self.test_step(batch, batch_idx, dataloader_idx - N_VAL_DATALOADERS_PER_SPLIT)
+
+    def validation_epoch_end(self, outputs):
+        self.validation_test_epoch_end('val', outputs[:N_VAL_DATALOADERS_PER_SPLIT])
+        if len(outputs) > N_VAL_DATALOADERS_PER_SPLIT:
+            self.test_epoch_end(outputs[N_VAL_DATALOADERS_PER_SPLIT:])
 
     def test_step(self, batch, batch_idx, dataloader_idx=0):
         return self.validation_test_step('test', batch, batch_idx, dataloader_idx)
+
+    def test_epoch_end(self, outputs):
+        return self.validation_test_epoch_end('test', outputs)
 
     # -- batched n-way evaluation (replaces the per-trial loop, eval.py:175-266) -----------------
     @torch.no_grad()
@@ -212,5 +253,21 @@ class MultiModalLitModel(_Base):
         feats = trial_features.reshape(N * n_way, -1).float()
         if from_trunk_boundary:
             w, b = m._head()
-            feats = torch.addmm(b.float(), feats, w.float().t())          # fp32 head (exact mode)
+            feats = ops.linear_f32(feats, w, b)                           # fp32 head (exact mode), own kernel
         return ops.eval_nway(feats, txt, label_index, n_way, bool(m.normalize_features), s, want_logits)
+
+    @torch.no_grad()
+    def classify_frames(self, frame_features, label_ids, label_lens, from_trunk_boundary=True, want_logits=True):
+        """n-category classification (the reference's other Labeled-S form, multimodal_saycam_data_module.py:545-606:
+        every frame against ALL C category labels, argmax over the categories).  frame_features [N, 2048] trunk-
+        boundary rows (or [N, E] head outputs with from_trunk_boundary=False); label_ids / label_lens [C, L] / [C].
+        -> (pred int32 [N] = category row, logits_per_image fp32 [N, C] | empty); fp32 end to end."""
+        m = self.model
+        s = ops._scalar(m.logit_neg_log_temperature)
+        txt = ops.text_features_flat(label_ids, label_lens, m.text_embed.embedding.weight, normalize=False)
+        feats = frame_features.reshape(-1, frame_features.shape[-1]).float()
+        if from_trunk_boundary:
+            w, b = m._head()
+            feats = ops.linear_f32(feats, w, b)
+        return ops.classify_ncat(feats, txt, bool(m.normalize_features), s, want_logits)
+

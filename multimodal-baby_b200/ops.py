@@ -1008,6 +1008,66 @@ class _FlatContrastiveStepSharded(torch.autograd.Function):
         return (None, None, None, dW, db, dtable, ds[0] if ctx.s_is_tensor else None, None, None, None)
 
 
+def linear_f32(x: Tensor, w: Tensor, bias: Optional[Tensor]) -> Tensor:
+    """x [M,K] . w[N,K]^T + bias in fp32 with fp32 accumulation (cvcl_linear_f32): the exact-mode projection head
+    of the evaluation path (no tensor cores, no library GEMM)."""
+    _need_cuda(x, w, bias)
+    x = _f32(x); w = _f32(w)
+    bias = _f32(bias) if bias is not None else None
+    M, K = x.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    _cabi.call("cvcl_linear_f32", _p(x), K, _p(w), K, _p(bias), M, N, K, _p(out), N, _stream())
+    return out
+
+
+def normalize_rows_f32(x: Tensor) -> Tensor:
+    """F.normalize(x, dim=-1) in fp32 (eps 1e-12), rows of a 2-D tensor."""
+    _need_cuda(x)
+    x = _f32(x)
+    out = torch.empty_like(x)
+    _cabi.call("cvcl_normalize_rows_f32", _p(x), _p(out), x.shape[0], x.shape[1], _stream())
+    return out
+
+
+@torch.no_grad()
+def classify_ncat(img: Tensor, txt: Tensor, normalize: bool = True, log_scale: float = 0.0,
+                  want_logits: bool = True) -> Tuple[Tensor, Tensor]:
+    """Category classification of frames (the reference's n-category evaluation form,
+    multimodal_saycam_data_module.py:545-606 / forward(): logits_per_image = exp(s) * I.T^T, argmax over the C
+    category texts).  img [N,E], txt [C,E] features before normalisation.  fp32 end to end.
+    -> (pred int32 [N], logits [N,C] | empty)."""
+    _need_cuda(img, txt)
+    i = normalize_rows_f32(img) if normalize else _f32(img)
+    t = normalize_rows_f32(txt) if normalize else _f32(txt)
+    scores = linear_f32(i, t, None)                                   # [N, C] cosines
+    N, C = scores.shape
+    best = torch.empty((N,), dtype=torch.float32, device=img.device)
+    pred = torch.empty((N,), dtype=torch.int32, device=img.device)
+    _cabi.call("cvcl_row_argmax_f32", _p(scores), C, N, C, 0, 0, _p(best), _p(pred), _stream())
+    if not want_logits:
+        return pred, scores.new_empty((0,))
+    return pred, scores * math.exp(float(log_scale))
+
+
+@torch.no_grad()
+def cosine_nearest(queries: Tensor, keys: Tensor, chunk: int = 16384) -> Tuple[Tensor, Tensor]:
+    """Cosine nearest neighbour of every query row among the key rows (analysis_cvcl/duplicates.py:561-607:
+    F.normalize + cosine similarity + np.argmax / np.max per evaluation frame).  fp32; the [Nq, Nk] matrix is
+    produced in chunks of `chunk` keys and never held whole.  -> (max cosine fp32 [Nq], index int32 [Nq])."""
+    _need_cuda(queries, keys)
+    q = normalize_rows_f32(queries)
+    Nq, Nk = q.shape[0], keys.shape[0]
+    best = torch.empty((Nq,), dtype=torch.float32, device=q.device)
+    arg = torch.empty((Nq,), dtype=torch.int32, device=q.device)
+    for c0 in range(0, Nk, chunk):
+        k = normalize_rows_f32(keys[c0:c0 + chunk])
+        scores = linear_f32(q, k, None)
+        _cabi.call("cvcl_row_argmax_f32", _p(scores), scores.shape[1], Nq, scores.shape[1], c0, int(c0 > 0),
+                   _p(best), _p(arg), _stream())
+    return best, arg
+
+
 # ----------------------------------------------------------------------------------------
 # K7 evaluation
 # ----------------------------------------------------------------------------------------

@@ -279,6 +279,24 @@ def eval_nway(img_feat, txt_feat, s=None, normalize=True):
     return torch.argmax(logits, dim=-1), logits
 
 
+def classify_ncat(img_feat, txt_feat, s=None, normalize=True):
+    """n-category classification of frames (multimodal_saycam_data_module.py:545-606 / forward(), multimodal.py:
+    782-794): logits_per_image = scale * I.T^T over the C category texts; pred = argmax (first max)."""
+    if normalize:
+        img_feat = l2_normalize(img_feat, -1)
+        txt_feat = l2_normalize(txt_feat, -1)
+    scale = 1.0 if s is None else math.exp(float(s))
+    logits = img_feat @ txt_feat.t() * scale
+    return torch.argmax(logits, dim=-1), logits
+
+
+def cosine_nearest(queries, keys):
+    """analysis_cvcl/duplicates.py:561-607: F.normalize both sets, all-pairs cosine, per query (evaluation frame)
+    np.max / np.argmax over the keys (training frames)."""
+    sim = l2_normalize(queries, -1) @ l2_normalize(keys, -1).t()
+    return sim.max(dim=1).values, torch.argmax(sim, dim=1)
+
+
 def eval_trial_loop(f_trials, ids, lens, W, b, table, s):
     """The reference's literal per-trial loop (eval.py:196-214): one model() call per
     trial on 4 frames + 1 label; used on small N to pin eval_nway()."""

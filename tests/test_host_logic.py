@@ -283,3 +283,28 @@ def test_batch_trials_shares_label_rows_and_keeps_trial_order():
         cv.batch_trials(items + [(torch.zeros(3, 3, 2, 2), torch.tensor([5]), 1, ["x"])])
     with pytest.raises(ValueError):
         cv.batch_trials(items, max_len=2)
+
+
+def test_lit_epoch_end_hooks_log_example_weighted_means():
+    """joint_loss_epoch_end / *_epoch_end (multimodal_lit.py:376-444, 450-541): example-weighted means of the step
+    outputs under the reference's metric names; validation_step routes dataloaders >= 2 to the test split."""
+    lit = _lit(fix_temperature=True)
+    logged = {}
+    lit.log = lambda name, value, *a, **k: logged.__setitem__(name, (float(value), k))
+    outs = [dict(batch_size=2, loss=torch.tensor(1.0), infonce_loss=torch.tensor(1.0), image_accuracy=torch.tensor(0.5),
+                 text_accuracy=torch.tensor(0.0), image_entropy=torch.tensor(2.0), text_entropy=torch.tensor(4.0)),
+            dict(batch_size=6, loss=torch.tensor(3.0), infonce_loss=torch.tensor(3.0), image_accuracy=torch.tensor(1.0),
+                 text_accuracy=torch.tensor(1.0), image_entropy=torch.tensor(0.0), text_entropy=torch.tensor(0.0))]
+    lit.training_epoch_end(outs)
+    assert logged["train_loss_epoch"][0] == pytest.approx(2.5) and logged["train_image_accuracy_epoch"][0] == pytest.approx(0.875)
+    assert logged["train_loss_epoch"][1] == dict(on_step=False, on_epoch=True)
+    logged.clear()
+    lit.validation_epoch_end([outs, [], outs[:1], []])
+    assert logged["val_loss"][0] == pytest.approx(2.5) and logged["val_text_entropy"][0] == pytest.approx(1.0)
+    assert logged["test_loss"][0] == pytest.approx(1.0)
+    for name in ("infonce_loss", "image_accuracy", "text_accuracy", "image_entropy", "text_entropy", "loss"):
+        assert "val_" + name in logged and "test_" + name in logged
+    calls = []
+    lit.validation_test_step = lambda stage, batch, idx, dataloader_idx=0: calls.append((stage, dataloader_idx))
+    lit.validation_step(None, 0, 1); lit.validation_step(None, 0, 3)
+    assert calls == [("val", 1), ("test", 1)]
