@@ -267,6 +267,10 @@ int cvcl_gemm_f32out(const void* A, int lda, int a_mn, const void* Bm, int ldb, 
             // long contraction, enough tiles: 128 x 256 tiles read A once per 256 columns
             // (measured 975 -> 1127 TF/s at 32768 x 512 x 32768)
             gs.n_stride = 256;
+            // few column tiles, long rows of A (the spatial-max backward: A = the 2.5 GB arg-max matrix, N = E): let
+            // the column tiles of one row block run side by side so A crosses HBM once (ncu: 5.2 GB read for a
+            // 2.5 GB operand with the row-block-major order)
+            gs.n_fast = ceil_div(N, 256) <= 4 ? 1 : 0;
             if (!a_mn && !b_mn) return launch_gemm<256, 3, EpiStoreF32, false, false>(op, gs, ep, 1, st);
             if (!a_mn && b_mn) return launch_gemm<256, 3, EpiStoreF32, false, true>(op, gs, ep, 1, st);
             if (a_mn && !b_mn) return launch_gemm<256, 3, EpiStoreF32, true, false>(op, gs, ep, 1, st);
@@ -1054,7 +1058,7 @@ int cvcl_spatial_max_bwd(const float* gmatch, const int64_t* lens, const int64_t
                          void* workspace, void* stream) {
     CVCL_REQUIRE(gmatch && lens && amax_it && amax_ti && tok && img, "spatial_max_bwd: null pointer");
     CVCL_REQUIRE(E % 8 == 0 && E <= 1024, "spatial_max_bwd: E=%d must be a multiple of 8, <= 1024", E);
-    if (workspace) {
+    if (workspace && HW >= 8) {         // (the expansion kernel's 8-column windows assume a map of >= 8 locations)
         // tensor-core form: P (bf16, [Bt*L, Bi*HW]) then two GEMMs; P is read K-major for dtok and
         // MN-major (transposed in place) for dimg, the features are read MN-major as stored.
         const int ntl = Bt * L, ncol = Bi * HW, ldp = pad8(ncol);

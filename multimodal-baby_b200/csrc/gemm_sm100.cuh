@@ -34,6 +34,8 @@ struct GemmShape {
     int n_stride;        // tile origin step along N
     int aux_row_off[2];  // row offset of each epilogue input tile relative to m0
     int k_splits;        // > 1: blockIdx.z splits the contraction (single direction, additive epilogue)
+    int n_fast;          // 1: consecutive CTAs walk the N tiles of one M tile first (the few CTAs that share an A
+                         //    row block run together and the second reads it from L2; no clusters in this mode)
 };
 
 // All tensor maps of one launch (passed as a single __grid_constant__ parameter).
@@ -137,8 +139,13 @@ gemm_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmShape gs, cons
     const int z = split ? 0 : blockIdx.z;
     const CUtensorMap* tmA = &maps.a[z];
     const CUtensorMap* tmB = &maps.b[z];
-    const int m0 = blockIdx.x * gs.m_stride;
-    const int n0 = blockIdx.y * gs.n_stride;
+    int bx = blockIdx.x, by = blockIdx.y;
+    if (gs.n_fast) {
+        const int lin = blockIdx.y * gridDim.x + blockIdx.x;
+        by = lin % static_cast<int>(gridDim.y); bx = lin / static_cast<int>(gridDim.y);
+    }
+    const int m0 = bx * gs.m_stride;
+    const int n0 = by * gs.n_stride;
     const int num_k_all = (gs.K + kBK - 1) / kBK;
     const int per_split = split ? (num_k_all + gs.k_splits - 1) / gs.k_splits : num_k_all;
     const int kc_begin = split ? blockIdx.z * per_split : 0;
@@ -235,7 +242,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmShape gs, cons
     const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
     cx.row = quad * 32 + lane;
     cx.tmem_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    cx.m0 = m0; cx.n0 = n0; cx.z = z; cx.tile_m = blockIdx.x; cx.tile_n = blockIdx.y;
+    cx.m0 = m0; cx.n0 = n0; cx.z = z; cx.tile_m = bx; cx.tile_n = by;
     cx.scratch = scratch;
     cx.aux[0] = smem + L::kAuxOff;
     cx.aux[1] = smem + L::kAuxOff + (Epi::kNumAux > 1 ? L::kAuxBytes : 0);

@@ -1412,21 +1412,35 @@ __global__ void __launch_bounds__(256) spatial_max_expand_kernel(const float* g,
     const unsigned char* arow = amax_ti + static_cast<size_t>(tl) * Bi;
     __nv_bfloat16* prow = P + static_cast<size_t>(tl) * ldp;
     const int ncol = Bi * HW;
-    // two columns per thread (one 4-byte store); ldp is a multiple of 8 so rows stay 4-byte aligned
-    for (int c = threadIdx.x * 2; c < ncol; c += blockDim.x * 2) {
-        float v[2];
+    // eight columns (one 16-byte store) per thread: the window touches at most two images (HW >= 8) and is all zero
+    // unless an arg-max lies inside it, so g is fetched for about one window in six.  ldp is a multiple of 8 and P is
+    // 16-byte aligned (the caller's workspace), so every full window is one aligned store.
+    for (int c = threadIdx.x * 8; c < ncol; c += blockDim.x * 8) {
+        const int i0 = c / HW;
+        const int h0 = c - i0 * HW;                        // window = locations h0.. of image i0, then image i0 + 1
+        int k0 = static_cast<int>(arow[i0]) - h0, k1 = -1;  // positions of the (at most two) non-zeros in the window
+        float v0 = 0.f, v1 = 0.f;
+        if (k0 >= 0 && k0 < 8) v0 = __ldg(g + static_cast<size_t>(i0) * Bt + t) * invlen; else k0 = -1;
+        if (HW - h0 < 8 && i0 + 1 < Bi) {
+            k1 = HW - h0 + static_cast<int>(arow[i0 + 1]);
+            if (k1 < 8) v1 = __ldg(g + static_cast<size_t>(i0 + 1) * Bt + t) * invlen; else k1 = -1;
+        }
+        unsigned int w[4];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int cc = c + k;
-            v[k] = 0.f;
-            if (cc < ncol) {
-                const int i = cc / HW, hw = cc - i * HW;
-                if (arow[i] == hw) v[k] = __ldg(g + static_cast<size_t>(i) * Bt + t) * invlen;
+        for (int q = 0; q < 4; ++q) {
+            const float lo = (2 * q == k0) ? v0 : ((2 * q == k1) ? v1 : 0.f);
+            const float hi = (2 * q + 1 == k0) ? v0 : ((2 * q + 1 == k1) ? v1 : 0.f);
+            const __nv_bfloat162 o = __floats2bfloat162_rn(lo, hi);
+            w[q] = *reinterpret_cast<const unsigned int*>(&o);
+        }
+        if (c + 8 <= ncol) *reinterpret_cast<uint4*>(prow + c) = make_uint4(w[0], w[1], w[2], w[3]);
+        else {
+            for (int k = 0; c + k < ncol; ++k) {
+                const unsigned int word = w[k >> 1];
+                const unsigned short h = (k & 1) ? static_cast<unsigned short>(word >> 16) : static_cast<unsigned short>(word & 0xffffu);
+                reinterpret_cast<unsigned short*>(prow)[c + k] = h;
             }
         }
-        __nv_bfloat162 o = __floats2bfloat162_rn(v[0], v[1]);
-        if (c + 1 < ncol) *reinterpret_cast<__nv_bfloat162*>(prow + c) = o;
-        else prow[c] = __float2bfloat16_rn(v[0]);
     }
 }
 
