@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CVCL_ABI_VERSION 4
+#define CVCL_ABI_VERSION 5
 #define CVCL_OK 0
 #define CVCL_ERR_INVALID (-1)
 #define CVCL_ERR_UNSUPPORTED (-2)

@@ -9,7 +9,7 @@ from ctypes import c_float, c_int, c_int64, c_size_t, c_void_p, c_char_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libcvcl_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class CvclLibraryMissing(RuntimeError):

@@ -47,7 +47,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), "libcvcl_b200.so does not export %s" % name
     # the ctypes prototype table covers exactly the header
     assert sorted(cv._cabi.PROTOTYPES) == declared
-    assert cv._cabi.load().cvcl_abi_version() == cv._cabi.ABI_VERSION == 4
+    assert cv._cabi.load().cvcl_abi_version() == cv._cabi.ABI_VERSION == 5
 
 
 def test_library_links_no_torch_and_is_sm100a():
