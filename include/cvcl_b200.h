@@ -277,11 +277,12 @@ int cvcl_flat_step_fused_sharded(const void* x16, const void* w16, const int64_t
 int cvcl_spatial_max_fwd(const void* tok, const void* img, const int64_t* lens, int Bt, int L, int Bi, int HW,
                          int E, float* match, unsigned char* amax_it, unsigned char* amax_ti, void* stream);
 /* autograd of the above: dtok [Bt*L,E] and dimg [Bi*HW,E] fp32 (either may be NULL) from
- * gmatch = dL/dmatch [Bi,Bt].  With a workspace (cvcl_spatial_max_bwd_workspace_bytes) the saved
- * arg-max is expanded into the bf16 matrix P[(t,l),(i,hw)] = [hw = argmax] * g[i,t]/len[t] and both
+ * gmatch = dL/dmatch [Bi,Bt].  With a workspace (cvcl_spatial_max_bwd_workspace_bytes, 256-byte aligned) the saved
+ * arg-max is expanded into the bf16 matrix P[(t,l),(i,hw)] = [hw = argmax] * g[i,t]/len[t] over the REAL token rows
+ * only (pad positions are dropped; their count stays on the device and bounds the GEMMs from there, no sync) and both
  * gradients run as tcgen05 GEMMs (dtok = P.img, dimg = P^T.tok, P^T read in place MN-major);
  * workspace = NULL selects the SIMT gather form (ids [Bt*L], nullable, lets pad tokens be skipped). */
-size_t cvcl_spatial_max_bwd_workspace_bytes(int Bt, int L, int Bi, int HW);
+size_t cvcl_spatial_max_bwd_workspace_bytes(int Bt, int L, int Bi, int HW, int E);
 int cvcl_spatial_max_bwd(const float* gmatch, const int64_t* lens, const int64_t* ids,
                          const unsigned char* amax_it, const unsigned char* amax_ti, const void* tok,
                          const void* img, int Bt, int L, int Bi, int HW, int E, float* dtok, float* dimg,

@@ -74,7 +74,7 @@ PROTOTYPES = {
                                              _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P,
                                              _L, _P]),
     "cvcl_spatial_max_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
-    "cvcl_spatial_max_bwd_workspace_bytes": (c_size_t, [_I, _I, _I, _I]),
+    "cvcl_spatial_max_bwd_workspace_bytes": (c_size_t, [_I, _I, _I, _I, _I]),
     "cvcl_spatial_max_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "cvcl_match_infonce_fwd": (c_int, [_P, _I, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
     "cvcl_match_infonce_bwd": (c_int, [_P, _I, _F, _F, _P, _P, _P, _P, _P]),

@@ -251,8 +251,17 @@ int cvcl_spatial_pool_bwd(const float* g, int B, int HW, int E, float* dst, void
     return CVCL_OK;
 }
 
+// m_limit / k_limit: device-side sizes (see GemmShape); null = the host shapes
+static int gemm_f32out_limited(const void* A, int lda, int a_mn, const void* Bm, int ldb, int b_mn, int M, int N, int K,
+                               float alpha, float* C, int ldc, const int* m_limit, const int* k_limit, void* stream);
+
 int cvcl_gemm_f32out(const void* A, int lda, int a_mn, const void* Bm, int ldb, int b_mn, int M, int N, int K,
                      float alpha, float* C, int ldc, void* stream) {
+    return gemm_f32out_limited(A, lda, a_mn, Bm, ldb, b_mn, M, N, K, alpha, C, ldc, nullptr, nullptr, stream);
+}
+
+static int gemm_f32out_limited(const void* A, int lda, int a_mn, const void* Bm, int ldb, int b_mn, int M, int N, int K,
+                               float alpha, float* C, int ldc, const int* m_limit, const int* k_limit, void* stream) {
     CVCL_REQUIRE(A && Bm && C, "gemm_f32out: null pointer");
     CVCL_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_f32out: bad shape");
     GemmOperands op{}; op.ndir = 1;
@@ -260,6 +269,7 @@ int cvcl_gemm_f32out(const void* A, int lda, int a_mn, const void* Bm, int ldb, 
     op.B[0] = b_mn ? mat(Bm, K, N, ldb) : mat(Bm, N, K, ldb);
     op.out[0] = mat(C, M, N, ldc);
     GemmShape gs{}; gs.M[0] = gs.M[1] = M; gs.N[0] = gs.N[1] = N; gs.K = K; gs.m_stride = kBM; gs.n_stride = kBN;
+    gs.m_limit = m_limit; gs.k_limit = k_limit;
     cudaStream_t st = as_stream(stream);
     if ((ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) {
         EpiStoreF32::Params ep{}; ep.alpha = alpha;
@@ -582,7 +592,13 @@ struct SideStream {
         return CVCL_OK;
     }
 };
-SideStream& side_stream() { static thread_local SideStream ss; return ss; }
+// one set per (host thread, device): streams and events belong to the device that was current when they were created
+SideStream& side_stream() {
+    static thread_local SideStream per_dev[16];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) dev = 0;
+    return per_dev[dev];
+}
 
 struct FlatWs {
     __nv_bfloat16 *w16, *x16, *img16, *txt16, *G0, *du16;
@@ -951,11 +967,13 @@ static int flat_step_fused_impl(const void* x16, const void* w16, const int64_t*
         maps_valid = true;
     }
 
-    static thread_local bool attr_done = false;
-    if (!attr_done) {
+    static thread_local unsigned attr_mask = 0;     // per device: function attributes live in the device's context
+    int attr_dev = 0;
+    if (cudaGetDevice(&attr_dev) != cudaSuccess || attr_dev < 0 || attr_dev > 31) attr_dev = 0;
+    if (!((attr_mask >> attr_dev) & 1u)) {
         CVCL_CHECK_CUDA(cudaFuncSetAttribute(fused::flat_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              fused::kSmemBytes));
-        attr_done = true;
+        attr_mask |= 1u << attr_dev;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(f.grid);
@@ -1048,8 +1066,24 @@ int cvcl_spatial_max_fwd(const void* tok, const void* img, const int64_t* lens, 
     return launch_gemm<BN, 2, EpiSpatialMax, false, false>(op, gs, ep, 1, as_stream(stream));   // 96 KB ring: 2 CTAs/SM
 }
 
-size_t cvcl_spatial_max_bwd_workspace_bytes(int Bt, int L, int Bi, int HW) {
-    return align_up(2ull * static_cast<size_t>(Bt) * L * pad8(Bi * HW), 256);
+namespace {
+struct SpatialBwdWs { size_t off_p, off_offs, off_tokc, off_dtokc, bytes; int ntlp; };
+SpatialBwdWs spatial_bwd_ws(int Bt, int L, int Bi, int HW, int E) {
+    SpatialBwdWs w{};
+    w.ntlp = ceil_div(Bt * L, 128) * 128;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+    w.off_p = take(2ull * w.ntlp * pad8(Bi * HW));            // compacted arg-max matrix P (bf16)
+    w.off_offs = take(4ull * (Bt + 2));                       // token-row offsets, [Bt] = number of real tokens
+    w.off_tokc = take(2ull * w.ntlp * E);                     // compacted token features (bf16)
+    w.off_dtokc = take(4ull * w.ntlp * E);                    // compacted d tok (fp32)
+    w.bytes = off;
+    return w;
+}
+}  // namespace
+
+size_t cvcl_spatial_max_bwd_workspace_bytes(int Bt, int L, int Bi, int HW, int E) {
+    return spatial_bwd_ws(Bt, L, Bi, HW, E).bytes;
 }
 
 int cvcl_spatial_max_bwd(const float* gmatch, const int64_t* lens, const int64_t* ids,
@@ -1059,17 +1093,35 @@ int cvcl_spatial_max_bwd(const float* gmatch, const int64_t* lens, const int64_t
     CVCL_REQUIRE(gmatch && lens && amax_it && amax_ti && tok && img, "spatial_max_bwd: null pointer");
     CVCL_REQUIRE(E % 8 == 0 && E <= 1024, "spatial_max_bwd: E=%d must be a multiple of 8, <= 1024", E);
     if (workspace && HW >= 8) {         // (the expansion kernel's 8-column windows assume a map of >= 8 locations)
-        // tensor-core form: P (bf16, [Bt*L, Bi*HW]) then two GEMMs; P is read K-major for dtok and
-        // MN-major (transposed in place) for dimg, the features are read MN-major as stored.
+        // tensor-core form on COMPACTED token rows (pad positions dropped; their count is only known on the device):
+        // offsets -> P_c (bf16, [Mv, Bi*HW]) + tok_c -> two GEMMs with a device-side row / contraction limit -> d tok
+        // scattered back.  P_c is read K-major for dtok and MN-major (transposed in place) for dimg, the features are
+        // read MN-major as stored.
+        CVCL_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "spatial_max_bwd: workspace must be 256-byte aligned");
         const int ntl = Bt * L, ncol = Bi * HW, ldp = pad8(ncol);
-        __nv_bfloat16* P = static_cast<__nv_bfloat16*>(workspace);
-        CVCL_CHECK_CUDA(launch_pdl(spatial_max_expand_kernel, dim3(ntl), dim3(256), 0, as_stream(stream), gmatch,
+        const SpatialBwdWs w = spatial_bwd_ws(Bt, L, Bi, HW, E);
+        unsigned char* base = static_cast<unsigned char*>(workspace);
+        __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(base + w.off_p);
+        int* offs = reinterpret_cast<int*>(base + w.off_offs);
+        __nv_bfloat16* tokc = reinterpret_cast<__nv_bfloat16*>(base + w.off_tokc);
+        float* dtokc = reinterpret_cast<float*>(base + w.off_dtokc);
+        cudaStream_t st = as_stream(stream);
+        CVCL_CHECK_CUDA(launch_pdl(token_row_offsets_kernel, dim3(1), dim3(1024), 0, st,
+                                   reinterpret_cast<const long long*>(lens), Bt, L, offs));
+        count_launch();
+        CVCL_CHECK_CUDA(launch_pdl(spatial_max_expand_kernel, dim3(ntl), dim3(256), 0, st, gmatch,
                                    reinterpret_cast<const long long*>(lens), amax_ti, P, static_cast<long long>(ldp),
-                                   Bi, Bt, L, HW));
+                                   Bi, Bt, L, HW, static_cast<const int*>(offs), static_cast<const __nv_bfloat16*>(tok), tokc, E));
         count_launch();
         int rc;
-        if (dtok && (rc = cvcl_gemm_f32out(P, ldp, 0, img, E, 1, ntl, E, ncol, 1.f, dtok, E, stream))) return rc;
-        if (dimg && (rc = cvcl_gemm_f32out(P, ldp, 1, tok, E, 1, ncol, E, ntl, 1.f, dimg, E, stream))) return rc;
+        if (dtok) {
+            if ((rc = gemm_f32out_limited(P, ldp, 0, img, E, 1, ntl, E, ncol, 1.f, dtokc, E, offs + Bt, nullptr, stream))) return rc;
+            CVCL_CHECK_CUDA(launch_pdl(token_rows_scatter_kernel, dim3(warps_grid(ntl)), dim3(256), 0, st,
+                                       static_cast<const float*>(dtokc), reinterpret_cast<const long long*>(lens),
+                                       static_cast<const int*>(offs), dtok, Bt, L, E));
+            count_launch();
+        }
+        if (dimg && (rc = gemm_f32out_limited(P, ldp, 1, tokc, E, 1, ncol, E, ntl, 1.f, dimg, E, nullptr, offs + Bt, stream))) return rc;
         return CVCL_OK;
     }
     if (dtok) {
@@ -1372,11 +1424,13 @@ int cvcl_eval_nway_fwd(const float* img, const float* txt, const int* txt_index,
     if (n_way == 4 && E <= 512 && n_trials >= 4096 && !(logits && normalize) && (reinterpret_cast<uintptr_t>(img) & 15) == 0) {
         // streaming form: persistent blocks, 32 KB stages filled by bulk async copies
         const int smem = 128 + kEvalStages * kEvalGroup * 4 * E * 4;
-        static thread_local bool attr_done = false;
-        if (!attr_done) {
+        static thread_local unsigned attr_mask = 0;     // per device: function attributes live in the device's context
+        int attr_dev = 0;
+        if (cudaGetDevice(&attr_dev) != cudaSuccess || attr_dev < 0 || attr_dev > 31) attr_dev = 0;
+        if (!((attr_mask >> attr_dev) & 1u)) {
             CVCL_CHECK_CUDA(cudaFuncSetAttribute(eval_nway_stream_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  128 + kEvalStages * kEvalGroup * 4 * 512 * 4));
-            attr_done = true;
+            attr_mask |= 1u << attr_dev;
         }
         const int n_groups = ceil_div(n_trials, kEvalGroup);
         const int grid = n_groups < 3 * sm_count() ? n_groups : 3 * sm_count();

@@ -24,10 +24,12 @@ int launch_gemm(const GemmOperands& op, const GemmShape& gs, const typename Epi:
     constexpr int smem_bytes = L::template total<Epi>();
     static_assert(smem_bytes <= 227 * 1024, "shared memory budget");
     auto kern = gemm_bf16_kernel<BN, STAGES, Epi, A_MN, B_MN>;
-    static thread_local bool attr_done = false;
-    if (!attr_done) {
+    static thread_local unsigned attr_mask = 0;     // per device: function attributes live in the device's context
+    int attr_dev = 0;
+    if (cudaGetDevice(&attr_dev) != cudaSuccess || attr_dev < 0 || attr_dev > 31) attr_dev = 0;
+    if (!((attr_mask >> attr_dev) & 1u)) {
         CVCL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        attr_done = true;
+        attr_mask |= 1u << attr_dev;
     }
     GemmMaps maps;
     int rc;
@@ -99,10 +101,12 @@ int launch_gemm_persistent(const GemmOperands& op, const GemmShape& gs, const ty
     constexpr int smem_bytes = L::total();
     static_assert(smem_bytes <= 227 * 1024, "shared memory budget");
     auto kern = gemm_bf16_persistent_kernel<BN, STAGES, Epi>;
-    static thread_local bool attr_done = false;
-    if (!attr_done) {
+    static thread_local unsigned attr_mask = 0;     // per device: function attributes live in the device's context
+    int attr_dev = 0;
+    if (cudaGetDevice(&attr_dev) != cudaSuccess || attr_dev < 0 || attr_dev > 31) attr_dev = 0;
+    if (!((attr_mask >> attr_dev) & 1u)) {
         CVCL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        attr_done = true;
+        attr_mask |= 1u << attr_dev;
     }
     GemmMaps maps;
     TileGrid tg{};

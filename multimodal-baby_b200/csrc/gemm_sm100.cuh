@@ -36,6 +36,12 @@ struct GemmShape {
     int k_splits;        // > 1: blockIdx.z splits the contraction (single direction, additive epilogue)
     int n_fast;          // 1: consecutive CTAs walk the N tiles of one M tile first (the few CTAs that share an A
                          //    row block run together and the second reads it from L2; no clusters in this mode)
+    // device-side problem size (nullable; plain one-tile-per-CTA kernel without clusters / split-K only): a size the
+    // host does not know without a sync, e.g. the number of non-pad token rows.  CTAs whose tile starts at or beyond
+    // *m_limit leave at once; the contraction stops after ceil(*k_limit / 64) chunks (operands must be finite --
+    // zero -- between *k_limit and the end of that chunk).
+    const int* m_limit;
+    const int* k_limit;
 };
 
 // All tensor maps of one launch (passed as a single __grid_constant__ parameter).
@@ -146,7 +152,16 @@ gemm_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmShape gs, cons
     }
     const int m0 = bx * gs.m_stride;
     const int n0 = by * gs.n_stride;
-    const int num_k_all = (gs.K + kBK - 1) / kBK;
+    int num_k_all = (gs.K + kBK - 1) / kBK;
+    if (gs.m_limit || gs.k_limit) {
+        ptx::pdl_wait();                   // the limits were written by an earlier kernel of the stream
+        if (gs.m_limit && m0 >= __ldg(gs.m_limit)) return;       // whole CTA, before any barrier / TMEM set-up
+        if (gs.k_limit) {
+            int lim = (__ldg(gs.k_limit) + kBK - 1) / kBK;
+            lim = lim < 1 ? 1 : lim;
+            num_k_all = lim < num_k_all ? lim : num_k_all;
+        }
+    }
     const int per_split = split ? (num_k_all + gs.k_splits - 1) / gs.k_splits : num_k_all;
     const int kc_begin = split ? blockIdx.z * per_split : 0;
     const int kc_end = (kc_begin + per_split < num_k_all) ? kc_begin + per_split : num_k_all;

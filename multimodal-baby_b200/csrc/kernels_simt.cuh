@@ -1401,17 +1401,72 @@ __global__ void __launch_bounds__(256) match_grad_kernel(const float* match, int
 // plain GEMMs on the tcgen05 engine:  dtok = P . img   and   dimg = P^T . tok  (P read MN-major).
 // One block per token row; threads sweep the Bi*HW columns coalesced.
 // --------------------------------------------------------------------------------------
+// Row compaction of the token axis: pad positions (l >= len[t]) carry no gradient, and they are 44 % of the [Bt, L]
+// slots at the corpus' mean length of 14.  offs[t] = number of real tokens before utterance t (exclusive scan,
+// one block), offs[Bt] = their total Mv -- a DEVICE-side size: the GEMMs that follow read it as their row /
+// contraction limit, so no host sync is needed and the step stays graph-capturable.
+__global__ void __launch_bounds__(1024) token_row_offsets_kernel(const long long* lens, int Bt, int L, int* offs) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
+    __shared__ int part[1024];
+    const int per = (Bt + 1023) / 1024;
+    const int t0 = threadIdx.x * per;
+    int s = 0;
+    for (int t = t0; t < t0 + per && t < Bt; ++t) {
+        const long long n = __ldg(lens + t);
+        s += static_cast<int>(n < 0 ? 0 : (n > L ? L : n));
+    }
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {                   // Hillis-Steele inclusive scan of the per-thread sums
+        const int v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = threadIdx.x ? part[threadIdx.x - 1] : 0;
+    for (int t = t0; t < t0 + per && t < Bt; ++t) {
+        offs[t] = run;
+        const long long n = __ldg(lens + t);
+        run += static_cast<int>(n < 0 ? 0 : (n > L ? L : n));
+    }
+    if (threadIdx.x == 1023) offs[Bt] = part[1023];
+}
+
+// One block per (t, l) slot.  Real token: row r = offs[t] + l of the compacted P (bf16, [Mv, Bi*HW]) =
+// [hw = argmax(i,t,l)] * g[i,t] / len[t], and row r of the compacted token features.  Pad slot number j (in slot
+// order): ZERO row Mv + j of both while that is below the next multiple of 128 -- the contraction of dimg = P^T . tok
+// runs in 64-row chunks and must read finite values up to the end of its last chunk.
 __global__ void __launch_bounds__(256) spatial_max_expand_kernel(const float* g, const long long* lens,
                                                                  const unsigned char* amax_ti,
                                                                  __nv_bfloat16* P, long long ldp,
-                                                                 int Bi, int Bt, int L, int HW) {
+                                                                 int Bi, int Bt, int L, int HW,
+                                                                 const int* offs, const __nv_bfloat16* tok,
+                                                                 __nv_bfloat16* tokc, int E) {
     ptx::pdl_launch_dependents(); ptx::pdl_wait();
     const int tl = blockIdx.x;
-    const int t = tl / L;
-    const float invlen = 1.f / static_cast<float>(__ldg(lens + t));
-    const unsigned char* arow = amax_ti + static_cast<size_t>(tl) * Bi;
-    __nv_bfloat16* prow = P + static_cast<size_t>(tl) * ldp;
+    const int t = tl / L, l = tl - t * L;
+    const long long len_raw = __ldg(lens + t);
+    const int len = static_cast<int>(len_raw < 0 ? 0 : (len_raw > L ? L : len_raw));
     const int ncol = Bi * HW;
+    const int off_t = __ldg(offs + t), mv = __ldg(offs + Bt);
+    if (l >= len) {                                                   // pad slot
+        const int zr = mv + (tl - (off_t + len));
+        if (zr >= ((mv + 127) / 128) * 128 || zr >= Bt * L) return;
+        uint4* prow = reinterpret_cast<uint4*>(P + static_cast<size_t>(zr) * ldp);
+        for (int c = threadIdx.x; c < static_cast<int>(ldp / 8); c += blockDim.x) prow[c] = make_uint4(0u, 0u, 0u, 0u);
+        uint4* trow = reinterpret_cast<uint4*>(tokc + static_cast<size_t>(zr) * E);
+        for (int c = threadIdx.x; c < E / 8; c += blockDim.x) trow[c] = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
+    const int r = off_t + l;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(tok + static_cast<size_t>(tl) * E);
+        uint4* dst = reinterpret_cast<uint4*>(tokc + static_cast<size_t>(r) * E);
+        for (int c = threadIdx.x; c < E / 8; c += blockDim.x) dst[c] = __ldg(src + c);
+    }
+    const float invlen = 1.f / static_cast<float>(len_raw);
+    const unsigned char* arow = amax_ti + static_cast<size_t>(tl) * Bi;
+    __nv_bfloat16* prow = P + static_cast<size_t>(r) * ldp;
     // eight columns (one 16-byte store) per thread: the window touches at most two images (HW >= 8) and is all zero
     // unless an arg-max lies inside it, so g is fetched for about one window in six.  ldp is a multiple of 8 and P is
     // 16-byte aligned (the caller's workspace), so every full window is one aligned store.
@@ -1440,7 +1495,28 @@ __global__ void __launch_bounds__(256) spatial_max_expand_kernel(const float* g,
                 const unsigned short h = (k & 1) ? static_cast<unsigned short>(word >> 16) : static_cast<unsigned short>(word & 0xffffu);
                 reinterpret_cast<unsigned short*>(prow)[c + k] = h;
             }
+            for (int k = ncol - c; k < 8 && c + k < static_cast<int>(ldp); ++k)      // the padding columns up to ldp
+                reinterpret_cast<unsigned short*>(prow)[c + k] = 0;
         }
+    }
+}
+
+// d tok [Bt*L, E] fp32 from its compacted form: real tokens copy row offs[t] + l, pad slots are zero.  One warp per slot.
+__global__ void __launch_bounds__(256) token_rows_scatter_kernel(const float* src, const long long* lens, const int* offs,
+                                                                 float* dst, int Bt, int L, int E) {
+    ptx::pdl_launch_dependents(); ptx::pdl_wait();
+    const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= static_cast<long long>(Bt) * L) return;
+    const int t = static_cast<int>(w / L), l = static_cast<int>(w - static_cast<long long>(t) * L);
+    const long long len_raw = __ldg(lens + t);
+    const int len = static_cast<int>(len_raw < 0 ? 0 : (len_raw > L ? L : len_raw));
+    float4* d = reinterpret_cast<float4*>(dst + w * E);
+    if (l < len) {
+        const float4* s = reinterpret_cast<const float4*>(src + static_cast<size_t>(__ldg(offs + t) + l) * E);
+        for (int c = lane; c < E / 4; c += 32) d[c] = __ldg(s + c);
+    } else {
+        for (int c = lane; c < E / 4; c += 32) d[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 

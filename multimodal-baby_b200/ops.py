@@ -1139,7 +1139,7 @@ def spatial_max_bwd(g: Tensor, lens: Tensor, ids: Optional[Tensor], a_it: Tensor
     # tensor-core form (P expansion + two GEMMs) once the problem is big enough to pay for P
     ws = None
     if SPATIAL_MAX_BWD_MMA and Bi * Bt >= 64 * 64:
-        nbytes = _cabi.load().cvcl_spatial_max_bwd_workspace_bytes(Bt, L, Bi, HW)
+        nbytes = _cabi.load().cvcl_spatial_max_bwd_workspace_bytes(Bt, L, Bi, HW, E)
         ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
     _cabi.call("cvcl_spatial_max_bwd", _p(g), _p(_i64(lens)), None if ids is None else _p(_i64(ids)),
                _p(a_it), _p(a_ti), _p(tok16), _p(img16), Bt, L, Bi, HW, E,
