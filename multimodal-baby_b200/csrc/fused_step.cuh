@@ -825,14 +825,17 @@ flat_step_kernel(const __grid_constant__ StepMaps maps, const __grid_constant__ 
                         for (int q = 0; q < 4; ++q) swz_st16(gs_tile, row, (c + 8 * q) * 2, pack_bf16x8(g + 8 * q));
                     }
                 }
+                // dL/ds partial of this tile (direction 0 only).  Written BEFORE the arrival below: the reader (thread 64,
+                // behind tfull_bar, which fires after gs_bar) is then ordered after every warp's write (racecheck found
+                // the write after the arrival unordered)
+                if (z == 0 && qs == 0) {
+                    ds = warp_sum(ds);
+                    if (lane == 0) red[32 + warp] = ds;
+                }
                 ptx::fence_proxy_async_smem();              // generic smem writes -> tcgen05 (async proxy) reads
                 ptx::tc_fence_before();                     // the S tile has been read: its columns may be overwritten
                 ptx::mbar_arrive(gs_bar);
                 if (threadIdx.x == 64) CVCL_STAMP(23);
-                if (z == 0 && qs == 0) {                    // dL/ds partial of this tile (direction 0 only)
-                    ds = warp_sum(ds);
-                    if (lane == 0) red[32 + warp] = ds;
-                }
                 if (warp == 0 && lane == 0)
                     for (int idx = kStages; idx < n_fill3; ++idx) fill3(idx);      // slots free up as the MMAs retire
                 if (warp == 1 && lane == 0) {

@@ -47,6 +47,12 @@ def main():
             tl.append(bench.fused_phase_timeline(m, B))
         print(mode, "kernel total us:", [t["kernel total"] for t in tl])
         print(mode, "phases:", tl[-1])
+        lay = m.ops.fused_layout(B, bench.L, bench.E, bench.K, bench.V)
+        ws = m.ops._FUSED_WS.get((torch.cuda.current_device(), B, bench.L, bench.E, bench.K, bench.V))
+        tm = ws[lay["ctrl"] + 128:lay["ctrl"] + 128 + 8 * 48].view(torch.int64).cpu().numpy()
+        print(mode, "stamps us from start: barriers", " ".join("%.1f" % ((tm[k] - tm[0]) / 1e3) for k in range(1, 7) if tm[k]),
+              "| end %.1f |" % ((tm[15] - tm[0]) / 1e3),
+              " ".join("%d:%.1f" % (k, (tm[k] - tm[0]) / 1e3) for k in range(16, 30) if tm[k]))
 
     # H2D copies alone
     s = torch.cuda.current_stream()
