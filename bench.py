@@ -258,13 +258,13 @@ def config3_object(m, dev, peaks, flush, world, rank, group, B3=32768):
 
     def step():
         i = img.detach().requires_grad_(True); t = txt.detach().requires_grad_(True)
-        out = m.ops.sim_infonce(i, t, S_FIXED, group)
+        out = m.ops.sim_infonce(i, t, S_FIXED, group, True)          # unit-norm rows (F.normalize above)
         out[0].backward()
     ms_eager, _ = _event_time(step, 5, 2, flush)
     ms, form = ms_eager, "eager autograd (op by op)"
     try:       # the same fwd+bwd as ONE CUDA graph (collectives included): no per-op host cost between the kernels
         i_leaf = img.clone().requires_grad_(True); t_leaf = txt.clone().requires_grad_(True)
-        gstep3 = m.GraphedLossStep(lambda: m.ops.sim_infonce(i_leaf, t_leaf, S_FIXED, group)[0], [i_leaf, t_leaf])
+        gstep3 = m.GraphedLossStep(lambda: m.ops.sim_infonce(i_leaf, t_leaf, S_FIXED, group, True)[0], [i_leaf, t_leaf])
         ms_g, _ = _event_time(gstep3, 5, 2, flush)
         del gstep3
     except Exception as exc:                               # noqa: BLE001

@@ -144,7 +144,11 @@ int cvcl_sim_infonce_fwd(const void* img_q, const void* txt_k, const void* txt_q
                          int ld, int M0, int N0, int M1, int N1, int E, float log_scale,
                          int diag_off, float inv_rows, void* workspace,
                          float* lse0, float* lse1, int* argmax0, int* argmax1, float* out5,
-                         void* stream);
+                         int unit_norm, void* stream);
+/* unit_norm != 0: the caller promises unit-norm feature rows (F.normalize, multimodal.py:736/743).  Large square
+ * single-device problems (queries = keys, >= 4096 pairs, a multiple of 256, exp(s) <= 32) then take ONE similarity
+ * pass for both directions (multimodal.py:755 computes `match` once): row statistics per thread, column statistics
+ * through a transposed butterfly over the lanes, one exp per element against the fixed reference exp(s). */
 
 /* materialised logits for the forward() API (multimodal.py:783-794):
  * lpi [Ni,Nt] = exp(s) * img . txt^T ; lpt [Nt,Ni] (either may be NULL). */

@@ -48,7 +48,7 @@ PROTOTYPES = {
     "cvcl_head_proj_norm_fwd": (c_int, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P]),
     "cvcl_sim_workspace_bytes": (c_size_t, [_I, _I, _I, _I]),
     "cvcl_sim_infonce_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _F, _P, _P, _P, _P,
-                                     _P, _P, _P]),
+                                     _P, _P, _I, _P]),
     "cvcl_sim_logits_fwd": (c_int, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P]),
     "cvcl_sim_infonce_bwd_g": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _F, _P, _P, _P, _P,
                                        _P, _I, _P, _I, _P, _P]),

@@ -360,7 +360,7 @@ static int sim_infonce_fwd_impl(const void* img_q, const void* txt_k, const void
                                int ld, int M0, int N0, int M1, int N1, int E, float log_scale,
                                int diag_off, float inv_rows, void* workspace,
                                float* lse0, float* lse1, int* argmax0, int* argmax1, float* out5,
-                               void* stream, bool tickets_zeroed) {
+                               void* stream, bool tickets_zeroed, bool unit_norm = false) {
     CVCL_REQUIRE(img_q && txt_k && txt_q && img_k && workspace && lse0 && lse1 && out5,
                  "sim_infonce_fwd: null pointer");
     CVCL_REQUIRE(M0 > 0 && N0 > 0 && M1 > 0 && N1 > 0 && E > 0, "sim_infonce_fwd: bad shape");
@@ -391,7 +391,20 @@ static int sim_infonce_fwd_impl(const void* img_q, const void* txt_k, const void
     // overlaps another tile's MMAs; wide tiles (fewer per-CTA fixed costs, less smem traffic per
     // flop) once the problem is large enough to fill the machine anyway
     int rc;
-    if (sim_bn(N0, N1) == 256) {       // large: persistent CTAs, double-buffered TMEM accumulator
+    // one similarity pass for both directions (EpiSimStats1P): single device (queries = keys), square, full tiles,
+    // unit-norm features (the caller's promise) and a scale that keeps exp(scale*(r-1)) in the normal fp32 range
+    const bool one_pass = unit_norm && sim_bn(N0, N1) == 256 && img_q == img_k && txt_q == txt_k && M0 == N1 &&
+                          M1 == N0 && M0 == N0 && diag_off == 0 && M0 % 256 == 0 && ep.scale <= 32.f &&
+                          getenv("CVCL_B200_SIM_TWO_PASS") == nullptr;
+    if (one_pass) {
+        EpiSimStats1P::Params e1{};
+        e1.scale = ep.scale;
+        for (int z = 0; z < 2; ++z) { e1.part[z] = w.part[z]; e1.m_pad[z] = w.m_pad[z]; e1.diag[z] = w.diag[z]; }
+        e1.ticket = w.ticket;
+        op.ndir = 1;
+        gs.n_stride = 256;
+        rc = launch_gemm_persistent<256, 3, EpiSimStats1P>(op, gs, e1, as_stream(stream));   // 3-deep ring: room for the transpose buffers
+    } else if (sim_bn(N0, N1) == 256) {       // large: persistent CTAs, double-buffered TMEM accumulator
         gs.n_stride = 256;
         rc = launch_gemm_persistent<256, 4, EpiSimStats>(op, gs, ep, as_stream(stream));
     } else {
@@ -415,9 +428,9 @@ int cvcl_sim_infonce_fwd(const void* img_q, const void* txt_k, const void* txt_q
                          int ld, int M0, int N0, int M1, int N1, int E, float log_scale,
                          int diag_off, float inv_rows, void* workspace,
                          float* lse0, float* lse1, int* argmax0, int* argmax1, float* out5,
-                         void* stream) {
+                         int unit_norm, void* stream) {
     return sim_infonce_fwd_impl(img_q, txt_k, txt_q, img_k, ld, M0, N0, M1, N1, E, log_scale, diag_off, inv_rows,
-                                workspace, lse0, lse1, argmax0, argmax1, out5, stream, false);
+                                workspace, lse0, lse1, argmax0, argmax1, out5, stream, false, unit_norm != 0);
 }
 
 int cvcl_sim_logits_fwd(const void* img, const void* txt, int ld, int Ni, int Nt, int E, float log_scale,

@@ -749,6 +749,149 @@ struct EpiSimStats {
     static __device__ __forceinline__ void phase2(const EpiCtx&, const GemmShape&, const Params&) {}
 };
 
+// ---- similarity tile -> row AND column softmax statistics in ONE pass (multimodal.py:755 computes `match` once and
+// :808-810 reads it along both axes).  EpiSimStats above evaluates S once per direction (two GEMMs and two exp
+// passes); here each 128 x 128 slice of an image x text tile yields the partial of its 128 image rows (direction 0)
+// and, through a transposed butterfly over the lanes, the partial of its 128 text columns (direction 1: rows of S^T,
+// partial index = the image row block).  One exp per element serves both: the exponent uses the FIXED reference
+// `scale` (unit-norm features: every raw product is <= 1, so exp(scale*(r-1)) never overflows and, for
+// scale <= 32, never leaves the normal fp32 range); each partial is rescaled once to its true maximum so the
+// merge (infonce_finalize_kernel) and the arg-max logic are unchanged.  Single device, square problem, full tiles.
+struct EpiSimStats1P {
+    static constexpr bool kClusterReduce = false;
+    static constexpr int kPitch = 36;                                  // floats per row of a warp's transpose buffer
+    static constexpr int kWarpBuf = 32 * kPitch * 4;                   // 4608 bytes
+    static constexpr int kScratchBytes = 4 * 128 * 16 + 4 * kWarpBuf;  // column partials of the four warps + buffers
+    static constexpr int kNumAux = 0;
+    static constexpr int kOutElemBytes = 0;
+    struct Params {
+        float scale;                // exp(s)
+        RowStat* part[2];           // [0]: [N/128][m_pad0] image rows; [1]: [M/128][m_pad1] text rows
+        int m_pad[2];
+        float* diag[2];             // logit at the positive (identical for both directions)
+        unsigned int* ticket;       // zeroed here for the merge kernel that follows
+    };
+    // Column reduction over the 32 rows a warp holds (one row per lane, 32 columns each) through a shared-memory
+    // transpose: every lane stores its row (8 x 16 bytes, conflict-free at a pitch of 36 floats), then lane
+    // (rg, cg) = (lane / 8, lane % 8) reads columns 4cg..4cg+3 of rows 8rg..8rg+7 with 16-byte loads and the four
+    // row groups are folded with two shuffles.  A first version reduced with 31-step lane butterflies: 3x the
+    // instructions in long dependent chains, 9.7 us per 128 x 256 tile -- slower than evaluating S twice.
+    static __device__ __forceinline__ void store_row(float* buf, int lane, const float (&x)[32]) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(buf + lane * kPitch + 4 * j) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+    }
+    static __device__ __forceinline__ float4 cols_sum(float* buf, int lane, const float (&x)[32]) {
+        store_row(buf, lane, x);
+        __syncwarp();
+        const int rg = lane >> 3, cg = lane & 7;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float4 q = *reinterpret_cast<const float4*>(buf + (8 * rg + k) * kPitch + 4 * cg);
+            acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+        }
+        __syncwarp();                                                  // the buffer is reused right away
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+            acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+        }
+        return acc;
+    }
+    template <int BN>
+    static __device__ __forceinline__ void phase1(const EpiCtx& cx, const GemmShape&, const Params& p) {
+        static_assert(BN == 128, "one 128-column slice per epilogue group");
+        constexpr float kLog2e = 1.4426950408889634f;
+        const int m = cx.m0 + cx.row;                          // image row of this thread
+        const int lane = cx.row & 31, wq = cx.row >> 5;
+        if (cx.tile_m == 0 && cx.tile_n == 0 && cx.epi_tid == 0) *p.ticket = 0u;
+        const float sc2 = p.scale * kLog2e;
+        float4* colp = reinterpret_cast<float4*>(cx.scratch);  // [4 warps][128 columns]: sum e, sum e*r, max r, row
+        float* buf = reinterpret_cast<float*>(cx.scratch + 4 * 128 * 16 + wq * kWarpBuf);
+        const int rg = lane >> 3, cg = lane & 7;
+        const int row0 = cx.m0 + wq * 32 + 8 * rg;             // first of the eight rows this lane folds per column
+        float rmx = -INFINITY, rl = 0.f, ra = 0.f; int rarg = cx.n0;
+        // (one register buffer: prefetching the next 32 columns into a second one spilled and measured slower, 1.80 vs 1.71 ms)
+#pragma unroll 1
+        for (int c = 0; c < 128; c += 32) {
+            float v[32];
+            ptx::tmem_ld_32x32(cx.tmem_row + c, v);
+            const int n = cx.n0 + c;
+            float cm = v[0];
+#pragma unroll
+            for (int j = 1; j < 32; ++j) cm = fmaxf(cm, v[j]);
+            if (cm > rmx) {                                    // strict >: the first maximum of the row
+                int k = 31;
+#pragma unroll
+                for (int j = 31; j >= 0; --j) if (v[j] == cm) k = j;
+                rarg = n + k; rmx = cm;
+            }
+            if (m >= n && m < n + 32) {                        // the positive (square problem: column m)
+                float dv = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (n + j == m) dv = v[j];
+                p.diag[0][m] = dv * p.scale; p.diag[1][m] = dv * p.scale;
+            }
+            float e[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { e[j] = exp2f(fmaf(v[j], sc2, -sc2)); rl += e[j]; }
+            const float4 ce = cols_sum(buf, lane, e);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { e[j] *= v[j]; ra += e[j]; }
+            const float4 ca = cols_sum(buf, lane, e);
+            // column maxima with the lowest row on ties: rows ascend inside a lane, then the row groups fold
+            store_row(buf, lane, v);
+            __syncwarp();
+            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}; int id[4] = {row0, row0, row0, row0};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float4 q = *reinterpret_cast<const float4*>(buf + (8 * rg + k) * kPitch + 4 * cg);
+                const float qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) if (qq[t] > mx[t]) { mx[t] = qq[t]; id[t] = row0 + k; }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, mx[t], o);
+                    const int oid = __shfl_xor_sync(0xffffffffu, id[t], o);
+                    if (ov > mx[t] || (ov == mx[t] && oid < id[t])) { mx[t] = ov; id[t] = oid; }
+                }
+            }
+            if (rg == 0) {                                     // lanes 0..7: columns c + 4cg .. c + 4cg + 3
+                float4* dst = colp + wq * 128 + c + 4 * cg;
+                dst[0] = make_float4(ce.x, ca.x, mx[0], __int_as_float(id[0]));
+                dst[1] = make_float4(ce.y, ca.y, mx[1], __int_as_float(id[1]));
+                dst[2] = make_float4(ce.z, ca.z, mx[2], __int_as_float(id[2]));
+                dst[3] = make_float4(ce.w, ca.w, mx[3], __int_as_float(id[3]));
+            }
+        }
+        {   // row partial, rescaled from the fixed reference to its own maximum
+            const float f = exp2f((1.f - rmx) * sc2);
+            RowStat rs; rs.m = rmx * p.scale; rs.l = rl * f; rs.a = ra * f * p.scale; rs.arg = rarg;
+            p.part[0][static_cast<size_t>(cx.tile_n) * p.m_pad[0] + m] = rs;
+        }
+        ptx::named_bar_sync(1 + cx.bar_base, kEpiThreads);
+        {   // column partial of text row n0 + epi_tid: the four warps in row order (strict >: the lowest row wins ties)
+            float l = 0.f, a = 0.f, mx = -INFINITY; int arg = 0;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const float4 q = colp[w * 128 + cx.epi_tid];
+                l += q.x; a += q.y;
+                if (q.z > mx) { mx = q.z; arg = __float_as_int(q.w); }
+            }
+            const float f = exp2f((1.f - mx) * sc2);
+            RowStat rs; rs.m = mx * p.scale; rs.l = l * f; rs.a = a * f * p.scale; rs.arg = arg;
+            p.part[1][static_cast<size_t>(cx.tile_m) * p.m_pad[1] + cx.n0 + cx.epi_tid] = rs;
+        }
+    }
+    template <int BN>
+    static __device__ __forceinline__ void phase2(const EpiCtx&, const GemmShape&, const Params&) {}
+};
+
 
 // ---- backward, step 1: recompute the logits tile and emit dL/dlogits (bf16) --------------
 // G = (softmax_row + softmax_col - 2*I) / (2B)  (the autograd of

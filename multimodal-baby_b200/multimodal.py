@@ -368,7 +368,10 @@ class MultiModalModel(nn.Module):
                 else:
                     img_f = txt_f = None
             if img_f is not None:
-                loss, iacc, tacc, ient, tent, _, _ = ops.sim_infonce(img_f, txt_f, s, self.process_group)
+                # flat features are unit vectors when normalize_features is on (one similarity pass at large batch);
+                # the pooled spatial factors are not
+                unit = self.embedding_type == "flat" and bool(self.normalize_features)
+                loss, iacc, tacc, ient, tent, _, _ = ops.sim_infonce(img_f, txt_f, s, self.process_group, unit)
             else:
                 tok, _ = ops.text_features_spatial(y, y_len, table, self.normalize_features)
                 match = ops.spatial_max_similarity(nhwc, tok, y_len, y, split=self._split())

@@ -471,8 +471,11 @@ def sim_logits(img, txt, s):
 # ----------------------------------------------------------------------------------------
 @torch.library.custom_op(_NS + "::sim_infonce_fwd", mutates_args=())
 def sim_infonce_fwd(img_q: Tensor, txt_k: Tensor, txt_q: Tensor, img_k: Tensor, log_scale: float,
-                    diag_off: int, inv_rows: float) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
-    """bf16 operands [.,E] -> (out5 [8] fp32, lse0 [M0], lse1 [M1], argmax0 [M0], argmax1 [M1])."""
+                    diag_off: int, inv_rows: float, unit_norm: bool = False
+                    ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """bf16 operands [.,E] -> (out5 [8] fp32, lse0 [M0], lse1 [M1], argmax0 [M0], argmax1 [M1]).
+    unit_norm: the rows are unit vectors (F.normalize) -- large single-device problems then take one similarity
+    pass for both directions (see cvcl_sim_infonce_fwd)."""
     _need_cuda(img_q, txt_k, txt_q, img_k)
     M0, E = img_q.shape
     N0 = txt_k.shape[0]
@@ -488,12 +491,12 @@ def sim_infonce_fwd(img_q: Tensor, txt_k: Tensor, txt_q: Tensor, img_k: Tensor, 
     a1 = torch.empty((M1,), dtype=torch.int32, device=dev)
     _cabi.call("cvcl_sim_infonce_fwd", _p(img_q), _p(txt_k), _p(txt_q), _p(img_k), E, M0, N0, M1, N1, E,
                float(log_scale), int(diag_off), float(inv_rows), _p(ws), _p(lse0), _p(lse1), _p(a0), _p(a1),
-               _p(out5), _stream())
+               _p(out5), int(bool(unit_norm)), _stream())
     return out5, lse0, lse1, a0, a1
 
 
 @sim_infonce_fwd.register_fake
-def _(img_q, txt_k, txt_q, img_k, log_scale, diag_off, inv_rows):
+def _(img_q, txt_k, txt_q, img_k, log_scale, diag_off, inv_rows, unit_norm=False):
     f = dict(dtype=torch.float32)
     return (img_q.new_empty((8,), **f), img_q.new_empty((img_q.shape[0],), **f),
             img_q.new_empty((txt_q.shape[0],), **f),
@@ -561,11 +564,15 @@ class _SimInfoNCE(torch.autograd.Function):
     local pairs are complete; d s is summed over ranks so every rank holds the full value."""
 
     @staticmethod
-    def forward(ctx, img, txt, s, group):
+    def forward(ctx, img, txt, s, group, unit_norm=False):
         from . import sharding
         i16, _ = to_bf16_pair(img, False)
         t16, _ = to_bf16_pair(txt, False)
-        out5, saved, (a0, a1) = sharding.infonce_forward(i16, t16, _scalar(s), group, _raw(sim_infonce_fwd))
+        fwd = _raw(sim_infonce_fwd)
+        if unit_norm:
+            def fwd(*a, _f=_raw(sim_infonce_fwd)):
+                return _f(*a, True)
+        out5, saved, (a0, a1) = sharding.infonce_forward(i16, t16, _scalar(s), group, fwd)
         ctx.saved = saved
         ctx.group = group
         ctx.meta = (img.dtype, txt.dtype, torch.is_tensor(s))
@@ -580,12 +587,14 @@ class _SimInfoNCE(torch.autograd.Function):
         dimg = (dimg * gloss).to(idt)
         dtxt = (dtxt * gloss).to(tdt)
         ds_out = (ds[0] * gloss) if (s_is_tensor and ctx.needs_input_grad[2]) else None
-        return dimg, dtxt, ds_out, None
+        return dimg, dtxt, ds_out, None, None
 
 
-def sim_infonce(img, txt, s, group=None):
-    """-> (loss, image_accuracy, text_accuracy, image_entropy, text_entropy, image_pred, text_pred)."""
-    return _SimInfoNCE.apply(img, txt, s, group)
+def sim_infonce(img, txt, s, group=None, unit_norm=False):
+    """-> (loss, image_accuracy, text_accuracy, image_entropy, text_entropy, image_pred, text_pred).
+    unit_norm=True: img / txt rows are unit vectors (the output of F.normalize); lets large single-device batches
+    evaluate the similarity once for both directions."""
+    return _SimInfoNCE.apply(img, txt, s, group, bool(unit_norm))
 
 
 # ----------------------------------------------------------------------------------------
@@ -919,7 +928,7 @@ def flat_step_sharded(x, ids, lens, w, bias, table, log_scale, normalize, need_g
     ws = torch.empty((lib.cvcl_sim_workspace_bytes(B, Bg, B, Bg),), dtype=torch.uint8, device=dev)
     lse = px.lse if px is not None else torch.empty((2, B), **f32)
     C("cvcl_sim_infonce_fwd", _p(img_l), _p(txt_a), _p(txt_l), _p(img_a), 2 * E, B, Bg, B, Bg, E,
-      float(log_scale), rank * B, 1.0 / Bg, _p(ws), _p(lse[0]), _p(lse[1]), None, None, _p(stats), st)
+      float(log_scale), rank * B, 1.0 / Bg, _p(ws), _p(lse[0]), _p(lse[1]), None, None, _p(stats), 0, st)
     if phase_limit == 3:
         return stats, img_f, txt_f
     if need_grads:

@@ -300,6 +300,45 @@ def test_sim_infonce_properties_full_size(cv):
     assert (a0[:64].cpu().long() == ref_arg).float().mean().item() >= 0.98
 
 
+def test_sim_infonce_one_pass_equals_two_pass(cv):
+    """unit_norm=True at >= 4096 pairs: ONE similarity pass yields the statistics of both directions (row partials
+    per thread, column partials through the lane butterfly, fixed-reference exponent) == the two-GEMM form, and both
+    == fp64 on sampled rows and columns; structured inputs (planted positives, duplicated rows -> arg-max ties)."""
+    B, E = 8192, 512
+    gen = torch.Generator(device="cpu").manual_seed(17)
+    x = torch.nn.functional.normalize(torch.randn(B, E, generator=gen), dim=1)
+    y = torch.nn.functional.normalize(0.6 * x + 0.8 * torch.nn.functional.normalize(torch.randn(B, E, generator=gen), dim=1), dim=1)
+    y[100] = y[7]; x[4000] = x[4001]                     # exact ties for the arg-max of text 7/100 and image rows
+    xb, yb = x.to(torch.bfloat16).to(DEV), y.to(torch.bfloat16).to(DEV)
+    one = cv.ops.sim_infonce_fwd(xb, yb, yb, xb, S_DEFAULT, 0, 1.0 / B, True)
+    import os
+    os.environ["CVCL_B200_SIM_TWO_PASS"] = "1"
+    try:
+        two = cv.ops.sim_infonce_fwd(xb, yb, yb, xb, S_DEFAULT, 0, 1.0 / B, True)
+    finally:
+        del os.environ["CVCL_B200_SIM_TWO_PASS"]
+    torch.cuda.synchronize()
+    for a, b_ in zip(one[0][:5].tolist(), two[0][:5].tolist()):
+        assert abs(a - b_) <= 2e-5 * max(1.0, abs(b_)), (one[0], two[0])
+    assert float((one[1] - two[1]).abs().max()) <= 2e-4 and float((one[2] - two[2]).abs().max()) <= 2e-4
+    assert torch.equal(one[3], two[3]) and torch.equal(one[4], two[4])
+    # fp64 on a subset: rows (images) and columns (texts)
+    S64 = math.exp(S_DEFAULT) * (xb[:96].double().cpu() @ yb.double().cpu().T)
+    assert float((one[1][:96].double().cpu() - torch.logsumexp(S64, dim=1)).abs().max()) <= 1e-4
+    assert torch.equal(one[3][:96].cpu().long(), torch.argmax(S64, dim=1))
+    S64t = math.exp(S_DEFAULT) * (yb[:128].double().cpu() @ xb.double().cpu().T)
+    assert float((one[2][:128].double().cpu() - torch.logsumexp(S64t, dim=1)).abs().max()) <= 1e-4
+    assert torch.equal(one[4][:128].cpu().long(), torch.argmax(S64t, dim=1))
+    # the whole op through autograd (the model's flat "ops" path passes unit_norm for normalised features)
+    xi = x.to(DEV).requires_grad_(True); yi = y.to(DEV).requires_grad_(True)
+    l1 = cv.ops.sim_infonce(xi, yi, S_DEFAULT, None, True); l1[0].backward()
+    xj = x.to(DEV).requires_grad_(True); yj = y.to(DEV).requires_grad_(True)
+    l2 = cv.ops.sim_infonce(xj, yj, S_DEFAULT, None, False); l2[0].backward()
+    assert abs(l1[0].item() - l2[0].item()) <= 2e-5 * abs(l2[0].item())
+    assert rel_fro(xi.grad.cpu().numpy(), xj.grad.cpu().numpy()) <= 1e-3
+    assert rel_fro(yi.grad.cpu().numpy(), yj.grad.cpu().numpy()) <= 1e-3
+
+
 # ------------------------------------------------------------------------------- K7
 def test_eval_nway_golden_bit_exact(cv):
     from test_oracle_golden import eval_case_inputs
