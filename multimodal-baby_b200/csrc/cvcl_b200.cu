@@ -889,6 +889,11 @@ static int flat_step_fused_impl(const void* x16, const void* w16, const int64_t*
             p.peer_flags[r] = static_cast<unsigned int*>(sh->peer_flags[r]);
         }
         p.epoch = sh->epoch;
+        {   // CVCL_B200_PEER_TIMEOUT_MS (default 10 minutes, as for the peer collectives)
+            const char* e = getenv("CVCL_B200_PEER_TIMEOUT_MS");
+            const long long ms = e ? atoll(e) : 600000ll;
+            p.xtimeout_ns = static_cast<unsigned long long>(ms > 0 ? ms : 600000ll) * 1000000ull;
+        }
         if (sh->reduce_floats > 0 && world > 1) {
             const int n_tiles5 = f.nEB * (K / 128) + ceil_div(V, 128) * f.nEB;
             p.nslot = ceil_div(n_tiles5, world);

@@ -126,6 +126,8 @@ struct StepParams {
     float* peer_stats[8];
     float* peer_scratch[8];
     float* peer_small[8];
+    unsigned long long xtimeout_ns;      // a cross-rank barrier that waits longer sets *fault and traps (a rank may
+                                         // legitimately stall between steps: the default is NCCL-watchdog sized)
     int reduce;                          // 0: outputs are this rank's partial sums; 1: summed over the ranks in P6
     int nslot;                           // scratch slots per source rank = ceil(P5 tiles / world)
     float* rb_part;                      // [2*nMB][6]
@@ -219,7 +221,7 @@ CVCL_HELPER void grid_sync(const StepParams& p, int k, int xstage = -1, unsigned
                     if ((++it & 4095u) == 0) {
                         const unsigned long long now = globaltimer_ns();
                         if (t0 == 0) t0 = now;
-                        else if (now - t0 > 20000000000ull) {     // 20 s: a peer never reached this step
+                        else if (now - t0 > p.xtimeout_ns) {      // a peer never reached this step
                             if (p.fault) atomicExch(p.fault, 200 + 10 * xstage + lane);
                             __threadfence_system();
                             __trap();

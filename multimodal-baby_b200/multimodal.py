@@ -367,6 +367,9 @@ class MultiModalModel(nn.Module):
                     img_f = ops.spatial_pool(nhwc)
                 else:
                     img_f = txt_f = None
+            if img_f is None and self.process_group is not None:
+                raise NotImplementedError("spatial embeddings with sim='max' are not sharded over a process group "
+                                          "(the loss would silently be the local-batch loss)")
             if img_f is not None:
                 # flat features are unit vectors when normalize_features is on (one similarity pass at large batch);
                 # the pooled spatial factors are not

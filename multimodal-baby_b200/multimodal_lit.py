@@ -192,6 +192,7 @@ class MultiModalLitModel(_Base):
         return self.calculate_joint_loss(batch, 'train', self.log)
 
     def training_epoch_end(self, outputs):
+        ops.check_token_ids()            # a token id outside the vocabulary reached the kernels this epoch -> IndexError
         def log(name, value, *a, **k):
             return self.log(f"{name}_epoch", value, *a, on_step=False, on_epoch=True, **k)
         return self.joint_loss_epoch_end(outputs, 'train', log)
@@ -218,6 +219,7 @@ class MultiModalLitModel(_Base):
         return ret
 
     def validation_test_epoch_end(self, stage, outputs):
+        ops.check_token_ids()
         log = functools.partial(self.log, on_step=False, on_epoch=True)
         return self.joint_loss_epoch_end(outputs[0], stage, log)
 

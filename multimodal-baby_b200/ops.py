@@ -46,6 +46,31 @@ def _need_cuda(*ts):
                                "fallback (got a %s tensor)" % t.device)
 
 
+_TOKEN_STATUS = {}
+
+
+def token_status(dev) -> Tensor:
+    """persistent int32 word per device: the text-encoder kernels set it to 1 when they meet a token id outside
+    [0, V) (they then treat the id as <pad>; the reference's nn.Embedding fails with a device-side assert)."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    t = _TOKEN_STATUS.get(key)
+    if t is None:
+        t = _TOKEN_STATUS[key] = torch.zeros((1,), dtype=torch.int32, device=dev)
+    return t
+
+
+def check_token_ids(dev=None):
+    """Raise IndexError if any text-encoder launch since the last check saw a token id outside the embedding table
+    (a vocabulary / checkpoint mismatch would otherwise train silently on <pad> rows).  Synchronises: call it where
+    a sync is acceptable (epoch end, validation, or once per dataset)."""
+    items = list(_TOKEN_STATUS.items()) if dev is None else \
+        [(k, v) for k, v in _TOKEN_STATUS.items() if k == (dev.index if dev.index is not None else torch.cuda.current_device())]
+    for _, t in items:
+        if int(t.item()) != 0:
+            t.zero_()
+            raise IndexError("cvcl_b200: a token id outside [0, vocab_size) reached the text encoder")
+
+
 def _scalar(s) -> float:
     """host value of the log-scale `s` (a python float, a CPU 0-dim tensor when the temperature is
     fixed -- multimodal.py:712 -- or a CUDA Parameter, in which case this is the one D2H sync the
@@ -112,7 +137,7 @@ def text_encoder_fwd(ids: Tensor, lens: Tensor, table: Tensor, normalize: bool, 
     tok = torch.empty((B, L, E) if (per_token and want_tok) else (0,), dtype=torch.float32, device=dev)
     _cabi.call("cvcl_text_encoder_fwd", _p(ids), _p(lens), _p(table), B, L, E, V, int(normalize),
                int(per_token), float(pool_scale), _p(feat), None, 0, _p(inv),
-               _p(tok) if (per_token and want_tok) else None, None, None, _stream())
+               _p(tok) if (per_token and want_tok) else None, None, _p(token_status(dev)), _stream())
     return feat, inv, tok
 
 
@@ -744,7 +769,7 @@ def flat_contrastive_step(x: Tensor, ids: Tensor, lens: Tensor, w: Tensor, bias:
                    _p(ws), _p(out5), _p(img_f) if want_features else None,
                    _p(txt_f) if want_features else None,
                    g0 + 4 * (4 + E + V * E) if need_grads else None, g0 + 16 if need_grads else None,
-                   g0 + 4 * (4 + E) if need_grads else None, g0, None, int(phase_limit), _stream())
+                   g0 + 4 * (4 + E) if need_grads else None, g0, _p(token_status(dev)), int(phase_limit), _stream())
         return out5, img_f, txt_f, flat
     if need_grads:
         ds, db, dtable, dW = split_flat_grads(flat, E, K, V)
@@ -883,7 +908,7 @@ def flat_step_sharded(x, ids, lens, w, bias, table, log_scale, normalize, need_g
         C("cvcl_flat_step_fused_sharded", _p(x16), _p(w16), _p(ids), _p(lens), _p(bias), _p(table), B, L, E, K, V,
           int(normalize), float(log_scale), None, int(need_grads), _p(ws), _p(stats), _p(img_f), _p(txt_f),
           _p(dW) if need_grads else None, _p(db) if need_grads else None, _p(dtable) if need_grads else None,
-          _p(ds) if need_grads else None, None, 0, world, rank, px.p_txt_all, px.p_img_all, px.p_part_all,
+          _p(ds) if need_grads else None, _p(token_status(dev)), 0, world, rank, px.p_txt_all, px.p_img_all, px.p_part_all,
           px.p_flags[px.CH_FUSED], px.fused_epoch.data_ptr(),
           # the kernel's last phase sums [out5 | ds | db | d table | dW] over the ranks in place (two-shot, push, fixed
           # rank order) and its closing cross-rank barrier lets the next step overwrite the exchange buffers; a

@@ -198,3 +198,20 @@ def test_sharded_entry_with_one_rank_equals_single_gpu_entry(cv):
     assert int(epoch.item()) == 2
     assert torch.equal(o1[:5], o2[:5]) and torch.equal(flat1, flat2)
     assert float(txt_all.float().norm(dim=1).min()) > 0.99               # the features landed in the gathered buffers
+
+
+def test_out_of_range_token_id_is_reported(cv):
+    """a token id outside [0, V) is treated as <pad> by the kernels and flagged in the device status word:
+    ops.check_token_ids() raises IndexError (the reference's nn.Embedding fails with a device-side assert)."""
+    inp = case_inputs(99, 128, 512, "flat")
+    d = dev_inputs(inp)
+    cv.ops.check_token_ids()                                   # clean so far
+    ids = d["ids"].clone(); ids[3, 0] = 2350 + 7
+    cv.ops.flat_contrastive_step(d["f"], ids, d["lens"], d["W"], d["b"], d["table"], S_DEFAULT, True, True, False)
+    with pytest.raises(IndexError):
+        cv.ops.check_token_ids()
+    cv.ops.check_token_ids()                                   # the word was reset
+    ids[3, 0] = -1
+    cv.ops.text_features_flat(ids, d["lens"], d["table"])
+    with pytest.raises(IndexError):
+        cv.ops.check_token_ids()
