@@ -186,11 +186,14 @@ __global__ void __launch_bounds__(128) text_encoder_fwd_kernel(const TextFwdPara
                     if (pos[k] < 0) continue;
                     const size_t tok = static_cast<size_t>(b) * p.L + l0 + pos[k];
                     const float denom = p.normalize ? fmaxf(sqrtf(ssq[k]), 1e-12f) : 1.f;
-                    if (lane == 0 && p.inv_norm) p.inv_norm[tok] = 1.f / denom;
+                    // one reciprocal per token, then multiplies (the reference divides element-wise: at most 1 ulp
+                    // apart; 16 IEEE divisions per lane and token were two thirds of this kernel's instructions)
+                    const float rinv = 1.f / denom;
+                    if (lane == 0 && p.inv_norm) p.inv_norm[tok] = rinv;
 #pragma unroll
                     for (int c = 0; c < kMaxVec; ++c) {
                         if (c < nch && (c * 32 + lane) * 4 < p.E) {
-                            float4 t = make_float4(r[k][c].x / denom, r[k][c].y / denom, r[k][c].z / denom, r[k][c].w / denom);
+                            float4 t = make_float4(r[k][c].x * rinv, r[k][c].y * rinv, r[k][c].z * rinv, r[k][c].w * rinv);
                             const size_t off = tok * p.E + (c * 32 + lane) * 4;
                             if (p.tok_f32) *reinterpret_cast<float4*>(p.tok_f32 + off) = t;
                             if (p.tok_bf16) store_bf16x4(p.tok_bf16 + off, t);
