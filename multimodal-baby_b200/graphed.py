@@ -19,6 +19,9 @@ copied while it was computing, and copies the batch now staged in the pinned buf
 device; the returned loss belongs to the batch staged one call earlier (call `prime()` once after
 staging the first batch).
 
+`own_staging=True` (packed staging only): the step allocates all of its pinned staging sets itself -- a few
+candidates are timed and the fastest kept -- and the caller's tensors only provide the initial contents.
+
 `lagged_loss=True` (needs prefetch) additionally keeps one replay in flight: a call enqueues replay k and
 waits only for replay k-1, whose loss it returns (each graph writes its own pinned stats buffer).  The
 host never idles behind the GPU; every step's loss is still read back, one call later.  `flush()` waits
@@ -39,7 +42,7 @@ from . import ops
 
 class GraphedContrastiveStep:
     def __init__(self, model, x_host, ids_host, lens_host, warmup=3, prefetch=False, lagged_loss=False,
-                 optimizer=None):
+                 optimizer=None, own_staging=False):
         if model.embedding_type != "flat":
             raise NotImplementedError("GraphedContrastiveStep covers the flat-embedding train step")
         for t in (x_host, ids_host, lens_host):
@@ -80,19 +83,42 @@ class GraphedContrastiveStep:
                 torch.empty((span[1],), dtype=torch.uint8).pin_memory()
             return tuple(carve(arena, t, o) for t, o in zip((x_host, ids_host, lens_host), span[2])), arena
 
-        # pinned staging: one set per graph in lagged mode (the replay in flight may still be reading its set)
-        self.host_sets = [(x_host, ids_host, lens_host)]
-        self._host_arenas = [byte_view(x_host, span[0], span[1]) if span is not None else None]
-        if self.lagged:
-            hs, ha = new_set()
-            self.host_sets.append(hs); self._host_arenas.append(ha)
-            for dst, src in zip(self.host_sets[1], self.host_sets[0]):
-                dst.copy_(src)
         self.bufs, self._dev_arenas = [], []
         for _ in range(nbuf):
             ds_, da = new_set(dev)
             self.bufs.append(ds_); self._dev_arenas.append(da)
         self.packed = span is not None
+        # pinned staging: one set per graph in lagged mode (the replay in flight may still be reading its set)
+        n_sets = 2 if self.lagged else 1
+        self.staging_probe_us = None
+        if own_staging and span is not None:
+            # Every staging set is allocated HERE (the caller's tensors only provide the initial contents; write the
+            # next batch into `step.x_host / ids_host / lens_host`).  On the hosts this was developed on, pinned
+            # allocations come in a fast and a slow flavour (2.2 MB in 46 us or in 70-200 us, profiles/
+            # r02_h2d_staging_probe.txt), so a few candidates are timed and the fastest ones kept.
+            cands = [new_set() for _ in range(n_sets + 3)]
+            times = []
+            for hs, ha in cands:
+                for dst, src in zip(hs, (x_host, ids_host, lens_host)):
+                    dst.copy_(src)
+                ts = []
+                for _ in range(9):
+                    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                    e0.record(); self._dev_arenas[0].copy_(ha, non_blocking=True); e1.record(); e1.synchronize()
+                    ts.append(e0.elapsed_time(e1) * 1e3)
+                times.append(sorted(ts)[len(ts) // 2])
+            order = sorted(range(len(cands)), key=lambda i: times[i])[:n_sets]
+            self.host_sets = [cands[i][0] for i in order]
+            self._host_arenas = [cands[i][1] for i in order]
+            self.staging_probe_us = {"candidates": [round(v, 1) for v in times], "kept": [round(times[i], 1) for i in order]}
+        else:
+            self.host_sets = [(x_host, ids_host, lens_host)]
+            self._host_arenas = [byte_view(x_host, span[0], span[1]) if span is not None else None]
+            if self.lagged:
+                hs, ha = new_set()
+                self.host_sets.append(hs); self._host_arenas.append(ha)
+                for dst, src in zip(self.host_sets[1], self.host_sets[0]):
+                    dst.copy_(src)
         self.x, self.ids, self.lens = self.bufs[0]
         self.stats_bufs = [torch.zeros(8, dtype=torch.float32).pin_memory() for _ in range(nbuf)]
         self.stats_host = self.stats_bufs[0]
@@ -169,17 +195,67 @@ class GraphedContrastiveStep:
         torch.cuda.synchronize(dev)
         if optimizer is not None:
             self._reset_optimizer_after_warmup(backup)
-        self.graphs, flats = [], []
-        for k, (cur, nxt, sh) in enumerate(pairs):
-            gph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gph):
-                flats.append(body(cur, nxt, sh, k, self.host_sets[k % len(self.host_sets)]))
-            self.graphs.append(gph)
-        self.graph = self.graphs[0]
-        self.flats = flats
-        self.flat = flats[0]
-        self._grad_views = {}
+        self._body, self._pairs, self._new_set = body, pairs, new_set
+        self.graphs, self.flats, self._grad_views = [None] * len(pairs), [None] * len(pairs), {}
+        for k in range(len(pairs)):
+            self._capture(k)
         self._bind_grads(0, E, K, V, table)
+
+    def _capture(self, k):
+        cur, nxt, sh = self._pairs[k]
+        gph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gph):
+            flat = self._body(cur, nxt, sh, k, self.host_sets[k % len(self.host_sets)])
+        self.graphs[k], self.flats[k] = gph, flat
+        self._grad_views.pop(k, None)
+        if k == 0:
+            self.graph, self.flat = gph, flat
+
+    def _time_set(self, host_arena, n=7):
+        if getattr(self, "_probe_dev", None) is None:      # scratch target: the input buffers hold staged batches
+            self._probe_dev = torch.empty_like(host_arena, device=self.dev)
+        ts = []
+        for _ in range(n):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); self._probe_dev.copy_(host_arena, non_blocking=True); e1.record(); e1.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        return sorted(ts)[len(ts) // 2]
+
+    def check_staging(self, slow_factor=1.4):
+        """own_staging=True only.  Re-time the H2D copy of every staging set; a set that has become slow (a pinned
+        allocation can drop from 46 us to 70-200 us per 2.2 MB on some hosts, profiles/r02_h2d_staging_probe.txt) is
+        replaced by a freshly allocated fast one (contents preserved) and the graphs that copy from it are captured
+        again.  Waits for the replay in flight; no step is executed.  -> number of sets replaced.  A training loop may
+        call it every few thousand steps."""
+        if not self.packed or self.staging_probe_us is None:
+            return 0
+        self.flush()
+        torch.cuda.synchronize(self.dev)
+        ref = min(self.staging_probe_us["kept"])
+        replaced = 0
+        for j in range(len(self.host_sets)):
+            t = self._time_set(self._host_arenas[j])
+            if t <= slow_factor * ref:
+                continue
+            best = None
+            for _ in range(4):
+                hs, ha = self._new_set()
+                ha.copy_(self._host_arenas[j])
+                tt = self._time_set(ha)
+                if best is None or tt < best[0]:
+                    best = (tt, hs, ha)
+                if tt <= slow_factor * ref:
+                    break
+            if best[0] < t:
+                self.host_sets[j], self._host_arenas[j] = best[1], best[2]
+                replaced += 1
+                for k in range(len(self.graphs)):
+                    if k % len(self.host_sets) == j:
+                        self._capture(k)
+        if replaced:
+            torch.cuda.synchronize(self.dev)
+            self._bind_grads(0, *self._dims)
+        return replaced
 
     # the warm-up iterations ran real optimizer steps on whatever was staged: undo them
     def _reset_optimizer_after_warmup(self, backup):

@@ -502,8 +502,9 @@ def test_graphed_step_packed_staging(cv):
         stage(step, k)
         loss = step()
         assert abs(loss - ref[k]) <= 1e-6 * abs(ref[k]), (k, loss, ref[k])
-    step = cv.GraphedContrastiveStep(m, st.x_host, st.ids_host, st.lens_host, prefetch=True, lagged_loss=True)
-    assert step.packed
+    step = cv.GraphedContrastiveStep(m, st.x_host, st.ids_host, st.lens_host, prefetch=True, lagged_loss=True,
+                                     own_staging=True)        # all staging sets allocated (and timed) by the step
+    assert step.packed and len(step.staging_probe_us["kept"]) == 2 and step.x_host is not st.x_host
     stage(step, 0)
     step.prime()
     got = []
@@ -513,6 +514,17 @@ def test_graphed_step_packed_staging(cv):
     got.append(step.flush())
     assert got[0] != got[0]                             # nothing finished at the first call
     for a, b in zip(got[1:], ref[:3]):
+        assert abs(a - b) <= 1e-6 * abs(b), (got, ref)
+    # staging health check (re-times the sets, replaces slow ones) and a forced re-capture keep the step intact
+    assert step.check_staging() in (0, 1, 2)
+    step._capture(1); step._capture(0)
+    stage(step, 0); step.prime()
+    got = []
+    for k in (1, 2):
+        stage(step, k)
+        got.append(step())
+    got.append(step.flush())
+    for a, b in zip(got[1:], ref[:2]):
         assert abs(a - b) <= 1e-6 * abs(b), (got, ref)
 
 
