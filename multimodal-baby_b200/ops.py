@@ -601,12 +601,16 @@ class _SimInfoNCE(torch.autograd.Function):
         ctx.saved = saved
         ctx.group = group
         ctx.meta = (img.dtype, txt.dtype, torch.is_tensor(s))
-        ctx.mark_non_differentiable(a0, a1)
-        return out5[0], out5[1], out5[2], out5[3], out5[4], a0, a1
+        ctx.set_materialize_grads(False)          # only the loss is differentiated: no zero gradients for the metrics
+        o = out5[:5].unbind(0)
+        ctx.mark_non_differentiable(o[1], o[2], o[3], o[4], a0, a1)
+        return o[0], o[1], o[2], o[3], o[4], a0, a1
 
     @staticmethod
     def backward(ctx, gloss, *unused):
         from . import sharding
+        if gloss is None:
+            return None, None, None, None, None
         idt, tdt, s_is_tensor = ctx.meta
         dimg, dtxt, ds = sharding.infonce_backward(ctx.saved, ctx.group, _raw(sim_infonce_bwd))
         dimg = (dimg * gloss).to(idt)
@@ -820,13 +824,16 @@ class _FlatContrastiveStep(torch.autograd.Function):
         ctx.dims = (table.shape[1], x.shape[1], table.shape[0])
         if need:
             ctx.save_for_backward(flat)
-        ctx.mark_non_differentiable(img_f, txt_f)
+        # only the loss carries a gradient: the other scalars are metrics.  Without this the engine materialises a
+        # zero gradient for each unused output on every backward (four fill kernels per step in the launch list)
+        ctx.set_materialize_grads(False)
         o = out5.unbind(0)                       # one op for the five scalars
+        ctx.mark_non_differentiable(o[1], o[2], o[3], o[4], img_f, txt_f)
         return o[0], o[1], o[2], o[3], o[4], img_f, txt_f
 
     @staticmethod
     def backward(ctx, gloss, *unused):
-        if not ctx.need:
+        if not ctx.need or gloss is None:
             return (None,) * 9
         (flat,) = ctx.saved_tensors
         E, K, V = ctx.dims
@@ -1029,12 +1036,14 @@ class _FlatContrastiveStepSharded(torch.autograd.Function):
         e = stats.new_empty((0,))
         img_f = e if img_f is None else img_f
         txt_f = e.clone() if txt_f is None else txt_f
-        ctx.mark_non_differentiable(img_f, txt_f)
-        return stats[0], stats[1], stats[2], stats[3], stats[4], img_f, txt_f
+        ctx.set_materialize_grads(False)
+        o = stats[:5].unbind(0)
+        ctx.mark_non_differentiable(o[1], o[2], o[3], o[4], img_f, txt_f)
+        return o[0], o[1], o[2], o[3], o[4], img_f, txt_f
 
     @staticmethod
     def backward(ctx, gloss, *unused):
-        if not ctx.need:
+        if not ctx.need or gloss is None:
             return (None,) * 10
         (stats,) = ctx.saved_tensors
         E, K, V = ctx.dims
@@ -1274,11 +1283,15 @@ class _MatchInfoNCE(torch.autograd.Function):
         ctx.save_for_backward(match, lse0, lse1)
         ctx.ls = ls
         ctx.s_is_tensor = torch.is_tensor(s)
-        ctx.mark_non_differentiable(a0, a1)
-        return out5[0], out5[1], out5[2], out5[3], out5[4], a0, a1
+        ctx.set_materialize_grads(False)          # only the loss is differentiated: no zero gradients for the metrics
+        o = out5.unbind(0)
+        ctx.mark_non_differentiable(o[1], o[2], o[3], o[4], a0, a1)
+        return o[0], o[1], o[2], o[3], o[4], a0, a1
 
     @staticmethod
     def backward(ctx, gloss, *unused):
+        if gloss is None:
+            return None, None
         match, lse0, lse1 = ctx.saved_tensors
         dmatch, ds = _raw(match_infonce_bwd)(match, ctx.ls, lse0, lse1)
         return dmatch * gloss, (ds[0] * gloss) if ctx.s_is_tensor and ctx.needs_input_grad[1] else None
