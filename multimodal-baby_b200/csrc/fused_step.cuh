@@ -31,7 +31,12 @@
 //       ds / db in a fixed order.
 //
 // Sharded use enters through the same code: Q = the local pairs, K = the gathered features,
-// diag_off = rank * B (see StepParams::kf16 / part_all).
+// diag_off = rank * B (see StepParams::kf16 / part_all).  Nothing is exchanged by a separate kernel: P0 / P1 store each
+// feature row into every rank's gathered buffers, P2 stores its softmax partials into every rank's copy (the column
+// LSEs of P3 are merged from those), P5 stores each partial gradient tile into the scratch of the rank that owns it and
+//   P6  (sharded only) the owner adds the `world` partial tiles in rank order and stores the sum into every rank's
+//       gradient block; the scalars and d bias go one-shot.
+// Four of the grid barriers then also span the ranks (flag words over NVLink, grid_sync with xstage >= 0).
 #pragma once
 #include "gemm_sm100.cuh"
 #include "kernels_simt.cuh"
