@@ -193,3 +193,64 @@ def test_graphed_spatial_step_equals_eager(cv, sim):
         assert abs(loss.item() - ref[k][0]) <= 1e-5 * abs(ref[k][0]), (k, loss.item(), ref[k][0])
         for p, g in zip(params, ref[k][1]):
             assert rel_fro(p.grad.cpu().numpy(), g.cpu().numpy()) <= 1e-4, k       # float-atomic order only
+
+
+def test_spatial_config4_size_subsampled(cv):
+    """BASELINE config 4 (B = 1024, 7x7 map, L = 25): the spatial max / mean paths at their stated size.  The oracle
+    would need the [B, B, L, 49] score tensor, so the checks are on sub-blocks against fp64 torch (computed on the
+    GPU, independent of the kernels): match values and arg-max locations for 24 sampled images x all texts, the
+    tensor-core backward (compacted token rows) against the SIMT gather backward on the whole problem, d img rows of
+    the sampled images against the closed form from the fp64 arg-max, and the mean-path loss against fp64."""
+    rng = np.random.RandomState(41)
+    B, L, HW, E = 1024, 25, 49, 512
+    gen = torch.Generator().manual_seed(41)
+    img = torch.nn.functional.normalize(torch.randn(B, HW, E, generator=gen), dim=-1).to(torch.bfloat16).float()
+    tok = torch.nn.functional.normalize(torch.randn(B, L, E, generator=gen), dim=-1).to(torch.bfloat16).float()
+    ids, lens = O.synth_tokens(rng, B, L, 2350)
+    lens_t = t(lens)
+    valid = torch.arange(L)[None, :] < lens_t[:, None]                  # [B, L]
+    tok = tok * valid[:, :, None]
+    g = torch.randn(B, B, generator=gen) / B
+    imd, tkd, ld, idd, gd = img.to(DEV), tok.to(DEV), lens_t.to(DEV), t(ids, DEV), g.to(DEV)
+    res = {}
+    for flag in (True, False):
+        cv.ops.SPATIAL_MAX_BWD_MMA = flag
+        iv = imd.clone().requires_grad_(True); tv = tkd.clone().requires_grad_(True)
+        match = cv.ops.spatial_max_similarity(iv, tv, ld, idd)
+        (match * gd).sum().backward()
+        res[flag] = (match.detach(), iv.grad, tv.grad)
+    cv.ops.SPATIAL_MAX_BWD_MMA = True
+    torch.cuda.synchronize()
+    # forward on sampled images, fp64
+    sel = torch.from_numpy(rng.choice(B, 24, replace=False)).to(DEV)
+    sc = torch.einsum('ihe,tle->itlh', imd[sel].double(), tkd.double())          # [24, B, L, 49]
+    mx, am = sc.max(dim=-1)
+    vd = valid.to(DEV)
+    ref_match = (mx * vd[None]).sum(-1) / ld[None].double()
+    assert float((res[True][0][sel].double() - ref_match).abs().max()) <= 2e-6
+    # the two backward forms agree on the whole problem (P coefficients are bf16 in the tensor-core form)
+    assert rel_fro(res[True][1].cpu().numpy(), res[False][1].cpu().numpy()) <= 4e-3
+    vm = valid.numpy()
+    assert rel_fro(res[True][2].cpu().numpy()[vm], res[False][2].cpu().numpy()[vm]) <= 4e-3
+    assert float(res[True][2].cpu()[~valid].abs().max()) == 0.0                  # pad rows: exact zeros
+    # d img of the sampled images from the fp64 arg-max: dimg[i, h] = sum_{t,l valid} [am = h] g[i,t]/len[t] tok[t,l]
+    coef = (gd[sel].double() / ld[None].double())[:, :, None] * vd[None]         # [24, B, L]
+    onehot = torch.nn.functional.one_hot(am, HW).double() * coef[..., None]       # [24, B, L, 49]
+    ref_dimg = torch.einsum('itlh,tle->ihe', onehot, tkd.double())
+    assert rel_fro(res[False][1][sel].cpu().numpy(), ref_dimg.cpu().numpy()) <= 1e-5
+    assert rel_fro(res[True][1][sel].cpu().numpy(), ref_dimg.cpu().numpy()) <= 4e-3
+    # mean path: pooled factors -> InfoNCE loss vs fp64 (features rounded to bf16 as the kernels' operands)
+    table = torch.randn(2350, E, generator=gen) * 0.1
+    table[0] = 0
+    tb = table.to(DEV).requires_grad_(True); iv = imd.clone().requires_grad_(True)
+    _, tp = cv.ops.text_features_spatial(idd, ld, tb, True, 1.0 / HW, want_tok=False)
+    out = cv.ops.sim_infonce(cv.ops.spatial_pool(iv), tp, S_DEFAULT)
+    out[0].backward()
+    rows = torch.nn.functional.normalize(tb.detach().double()[idd], dim=-1) * (idd != 0)[..., None]
+    tp64 = rows.sum(1) / ld[:, None].double() / HW
+    ip64 = imd.double().sum(1)
+    logits = float(np.exp(S_DEFAULT)) * ip64.to(torch.bfloat16).double() @ tp64.to(torch.bfloat16).double().T
+    lab = torch.arange(B, device=DEV)
+    ref_loss = 0.5 * (torch.nn.functional.cross_entropy(logits, lab) + torch.nn.functional.cross_entropy(logits.T, lab))
+    assert abs(out[0].item() - ref_loss.item()) <= 1e-3 * abs(ref_loss.item())
+    assert iv.grad is not None and tb.grad is not None and not tb.grad[0].any()
