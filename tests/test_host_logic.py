@@ -71,8 +71,18 @@ def test_sass_shows_the_sm100a_instructions_the_design_claims():
     names = subprocess.run(["cuobjdump", "-elf", cv._cabi.LIB_PATH], capture_output=True, text=True).stdout
     for kernel in ("peer_allreduce_push_f32_kernel", "peer_allgather_push_kernel", "eval_nway_stream_kernel",
                    "text_encoder_flat_wide_kernel", "featgrad_finish_kernel", "gradcam_cam_kernel",
-                   "gemm_bf16_persistent_kernel"):
+                   "gemm_bf16_persistent_kernel",
+                   # round 2: the one-kernel step, the one-pass similarity epilogue, compacted spatial backward, eval forms
+                   "flat_step_kernel", "EpiSimStats1P", "token_row_offsets_kernel", "token_rows_scatter_kernel",
+                   "spatial_pool_bwd_kernel", "linear_f32_kernel", "row_argmax_f32_kernel", "normalize_rows_f32_kernel"):
         assert kernel in names, "kernel %s not in the library" % kernel
+    # the one-kernel step itself issues tcgen05 MMAs, TMEM loads and TMA traffic (not a wrapper around other launches)
+    import re
+    body = sass[sass.index("flat_step_kernel"):]
+    nxt = re.search(r"\n\s*Function : ", body[100:])
+    body = body[:100 + nxt.start()] if nxt else body
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG.2D", "UTMASTG.2D", "STG.E.STRONG.SYS"):
+        assert mnemonic in body, "flat_step_kernel lacks %s" % mnemonic
 
 
 def test_missing_library_is_loud(monkeypatch):
