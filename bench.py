@@ -373,8 +373,8 @@ def secondary_configs(m, dev, peaks, flush):
                     tok, _ = m.ops.text_features_spatial(ids_d, lens_d, tab, True)
                     loss = m.ops.infonce_from_match(m.ops.spatial_max_similarity(i, tok, lens_d, ids_d), S_FIXED)[0]
                 else:
-                    _, tp = m.ops.text_features_spatial(ids_d, lens_d, tab, True, 1.0 / HW, want_tok=False)
-                    loss = m.ops.sim_infonce(m.ops.spatial_pool(i), tp, S_FIXED)[0]
+                    ip, tp = m.ops.spatial_mean_factors(i, ids_d, lens_d, tab, True)
+                    loss = m.ops.sim_infonce(ip, tp, S_FIXED)[0]
                 loss.backward()
             return fn
         # the same closures as ONE CUDA graph each (GraphedLossStep: forward + backward captured once): the form a
@@ -386,8 +386,8 @@ def secondary_configs(m, dev, peaks, flush):
                 if sim == "max":
                     tok, _ = m.ops.text_features_spatial(ids_d, lens_d, tab_leaf, True)
                     return m.ops.infonce_from_match(m.ops.spatial_max_similarity(i_leaf, tok, lens_d, ids_d), S_FIXED)[0]
-                _, tp = m.ops.text_features_spatial(ids_d, lens_d, tab_leaf, True, 1.0 / HW, want_tok=False)
-                return m.ops.sim_infonce(m.ops.spatial_pool(i_leaf), tp, S_FIXED)[0]
+                ip, tp = m.ops.spatial_mean_factors(i_leaf, ids_d, lens_d, tab_leaf, True)
+                return m.ops.sim_infonce(ip, tp, S_FIXED)[0]
             return fn
         ms_eager, _ = _event_time(sp("max"), 5, 2, flush)
         gmax = m.GraphedLossStep(spg("max"), [i_leaf, tab_leaf])

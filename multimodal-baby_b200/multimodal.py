@@ -362,9 +362,7 @@ class MultiModalModel(nn.Module):
                 nhwc = image_features.reshape(B, H * W, E)
                 image_features = image_features.permute(0, 3, 1, 2)
                 if self.sim == "mean":
-                    _, txt_f = ops.text_features_spatial(y, y_len, table, self.normalize_features,
-                                                         1.0 / (H * W), want_tok=False)
-                    img_f = ops.spatial_pool(nhwc)
+                    img_f, txt_f = ops.spatial_mean_factors(nhwc, y, y_len, table, self.normalize_features)
                 else:
                     img_f = txt_f = None
             if img_f is None and self.process_group is not None:

@@ -418,6 +418,25 @@ def spatial_pool(x):
     return _SpatialPool.apply(x)
 
 
+def spatial_mean_factors(img_nhwc, ids, lens, table, normalize=True):
+    """The two factors of the spatial "mean" similarity (multimodal.py:761-770: the mean over locations and words of
+    <img[i,hw], tok[t,l]> factorises): (sum over the H*W locations of the image map [Bi,E], mean over the words of the
+    normalised token rows / (H*W) [Bt,E]).  The text branch runs on a side stream beside the image branch (forward
+    here; autograd replays each branch's backward on the stream its forward ran on), so under a CUDA graph the two
+    become parallel branches."""
+    HW = img_nhwc.shape[1]
+    dev = img_nhwc.device
+    main = torch.cuda.current_stream(dev)
+    side = _side_stream(dev, 2)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        _, tpool = text_features_spatial(ids, lens, table, normalize, 1.0 / HW, want_tok=False)
+    ipool = spatial_pool(img_nhwc)
+    main.wait_stream(side)
+    tpool.record_stream(main)
+    return ipool, tpool
+
+
 # ----------------------------------------------------------------------------------------
 # K3 logits (materialised, for the forward() API)
 # ----------------------------------------------------------------------------------------
